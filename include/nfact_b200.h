@@ -1,0 +1,132 @@
+/* nfact_b200 -- C ABI of the B200-native NFACT decomposition hot path.
+ *
+ * libnfact_b200.so is the drop-in boundary: plain pointers and sizes, no torch / numpy types.
+ * NFACT itself is pure Python and has no FFI layer; the three seams below are the Python call
+ * sites where NFACT hands NumPy arrays to third-party numerics.  Each entry
+ * point cites the reference interface it replaces; INTEGRATION.md shows the ctypes binding a
+ * maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - every function returns 0 on success; otherwise nfb_last_error() describes the failure
+ *     (thread-local, valid until the next failing call on that thread)
+ *   - "host" pointers are ordinary (pageable or pinned) host memory; "dev" pointers are CUDA device
+ *     pointers on the handle's device
+ *   - matrices are C-order (row-major); W is [m, k], H is [k, n] exactly like sklearn / NFACT
+ *   - all work is issued on the handle's stream; *_host entry points return after the results
+ *     have landed in the host buffers
+ */
+#ifndef NFACT_B200_H
+#define NFACT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct nfb_handle nfb_handle;   /* device + stream + scratch (+ optional NCCL communicator) */
+typedef struct nfb_matrix nfb_matrix;   /* a connectivity matrix X resident in HBM as fp16 hi/lo planes */
+typedef struct nfb_nmf nfb_nmf;         /* NMF solver state for one (X, k): factors, Grams, workspaces */
+
+/* ---- library / handle ------------------------------------------------------------------------ */
+const char* nfb_last_error(void);
+const char* nfb_version(void);
+/* `stream` is a cudaStream_t (NULL: the library creates its own non-blocking stream). */
+int nfb_create(int device, void* stream, nfb_handle** out);
+int nfb_destroy(nfb_handle* h);
+int nfb_synchronize(nfb_handle* h);
+/* Row-sharded multi-GPU: attach an initialised ncclComm_t (one rank per GPU).  When set, the H half-step
+ * all-reduces the k x n numerator and the k x k Gram W'W across ranks; W shards stay local.
+ * `nccl_allreduce_fn` is the address of ncclAllReduce in the NCCL library that created the communicator. */
+int nfb_set_comm(nfb_handle* h, void* nccl_comm, void* nccl_allreduce_fn, int rank, int world_size);
+/* helpers so the host language can create the communicator without linking NCCL itself */
+int nfb_nccl_unique_id(const char* libnccl_path, void* id_out_128_bytes);
+int nfb_nccl_init_rank(nfb_handle* h, const char* libnccl_path, const void* id_128_bytes, int rank, int world_size);
+
+/* ---- ingest -------------------------------------------------------------------------------------
+ * replaces  NFACT/base/matrix_handling.py:116-158  load_single_matrix / load_fdt_matrix
+ *           NFACT/decomp/decomposition/matrix_handling.py:73-100  avg_fdt
+ * rows/cols are 0-based (the caller subtracts 1 exactly like load_single_matrix does), vals are the
+ * float64 third column, scale[s] = 1e8 / waytotal_s computed by the caller in float64.
+ * group_mode == 0: exactly one subject, X = float32(d * scale).
+ * group_mode != 0: X = float32((m_0 + m_1 + ...) * (1.0 / n_subjects)), float64 throughout.
+ * The result is bit-identical to the reference (see ingest.cu for the duplicate-coordinate caveat).
+ * x_out_host: float32 [nrows, ncols] (may be NULL); x_out_dev: same on the device (may be NULL).   */
+int nfb_ingest_coo(nfb_handle* h, int n_subjects, const int32_t* const* rows_host, const int32_t* const* cols_host,
+                   const double* const* vals_host, const int64_t* nnz, const double* scale, int64_t nrows,
+                   int64_t ncols, int group_mode, float* x_out_host, float* x_out_dev);
+
+/* ---- resident matrix --------------------------------------------------------------------------
+ * X float32 [m, n] -> fp16 hi/lo planes in HBM (4 B/element, read by both X H' and W'X). */
+int nfb_matrix_from_host(nfb_handle* h, const float* x_host, int64_t m, int64_t n, nfb_matrix** out);
+int nfb_matrix_from_device(nfb_handle* h, const float* x_dev, int64_t m, int64_t n, int64_t ld, nfb_matrix** out);
+int nfb_matrix_free(nfb_matrix* x);
+int nfb_matrix_shape(const nfb_matrix* x, int64_t* m, int64_t* n);
+/* ||X||_F^2 accumulated in float64 from the original float32 values */
+int nfb_matrix_sumsq(const nfb_matrix* x, double* out);
+
+/* Generic product of the resident matrix with a dense float32 factor given component-major:
+ *   trans == 0 : out[t*ld_out + i] = sum_j X[i,j] * b_dev[t*n + j]     (b_dev [n_b, n], out [n_b, m])
+ *   trans != 0 : out[t*ld_out + j] = sum_i X[i,j] * b_dev[t*m + i]     (b_dev [n_b, m], out [n_b, n])
+ * Used by the NNDSVD initialisation (randomized range finder, sklearn/utils/extmath.py:313-383). */
+int nfb_matrix_matmul(nfb_handle* h, const nfb_matrix* x, int trans, const float* b_dev, int64_t n_b,
+                      float* out_dev, int64_t ld_out);
+
+/* ---- NMF solve ----------------------------------------------------------------------------------
+ * replaces  NFACT/decomp/decomposition/sso/nmfsso.py:32-59  nmf_decomp  ->  sklearn NMF.fit_transform
+ *           (sklearn/decomposition/_nmf.py:399-518 coordinate descent, :726-897 multiplicative update,
+ *            beta_loss = 'frobenius'), from given initial factors. */
+typedef struct nfb_nmf_params {
+    int solver;        /* 0 = "cd" (sklearn default, NFACT default), 1 = "mu" */
+    int max_iter;      /* sklearn max_iter */
+    double tol;        /* sklearn tol */
+    double l1_reg_W;   /* sklearn _compute_regularization (_nmf.py:1249-1259), computed by the caller */
+    double l1_reg_H;
+    double l2_reg_W;
+    double l2_reg_H;
+    int verbose;
+} nfb_nmf_params;
+
+/* One call, host buffers in and out (the reference-facing entry point):
+ *   w_host [m, k] float32 in/out (initial guess -> solution), h_host [k, n] float32 in/out.
+ *   n_iter_out, recon_err_out (||X - WH||_F, sklearn reconstruction_err_) may be NULL. */
+int nfb_nmf_fit_host(nfb_handle* h, const nfb_matrix* x, int k, const nfb_nmf_params* p, float* w_host,
+                     float* h_host, int* n_iter_out, double* recon_err_out);
+
+/* Stepwise interface (inputs resident; used by the benchmark and by per-iteration parity tests). */
+int nfb_nmf_create(nfb_handle* h, const nfb_matrix* x, int k, const nfb_nmf_params* p, nfb_nmf** out);
+int nfb_nmf_free(nfb_nmf* s);
+int nfb_nmf_set_factors_host(nfb_nmf* s, const float* w_host /* [m,k] */, const float* h_host /* [k,n] */);
+int nfb_nmf_set_factors_dev(nfb_nmf* s, const float* w_dev /* [m,k] */, const float* h_dev /* [k,n] */);
+int nfb_nmf_get_factors_host(nfb_nmf* s, float* w_host, float* h_host);
+int nfb_nmf_get_factors_dev(nfb_nmf* s, float* w_dev, float* h_dev);
+/* Run `n_iters` full iterations (W half-step then H half-step) without convergence checks.
+ * violation_out (CD only, may be NULL) receives the projected-gradient violation of the last iteration. */
+int nfb_nmf_iterate(nfb_nmf* s, int n_iters, double* violation_out);
+/* Full sklearn loop with its stopping rule from the current factors. */
+int nfb_nmf_run(nfb_nmf* s, int* n_iter_out, double* recon_err_out);
+/* ||X - WH||_F for the current factors (one extra X H' pass). */
+int nfb_nmf_error(nfb_nmf* s, double* err_out);
+/* number of kernels the last iterate/run call launched (for the benchmark's gpu_launches) */
+int64_t nfb_launch_count(const nfb_handle* h);
+
+/* ---- non-negative dual regression ---------------------------------------------------------------
+ * replaces  NFACT/dual_reg/dual_regression/dual_regression_methods.py:92-167  nmf_dual_regression
+ *           (scipy.optimize.nnls per column / per row).
+ *   g_host   [m, k] float64  group grey-matter components
+ *   gs_out   [m, k] float64  subject grey components      (stage 2)
+ *   hs_out   [k, n] float64  subject white components     (stage 1, already transposed like the reference)
+ *   n_unconverged_out: number of columns/rows whose solver hit its sweep cap (scipy would raise) */
+int nfb_dual_regression_host(nfb_handle* h, const nfb_matrix* x, int k, const double* g_host, double* gs_out,
+                             double* hs_out, int* n_unconverged_out);
+
+/* ---- low-level kernels exported for tests / profiling ------------------------------------------- */
+/* out_dev[t*ld_out + r] = sum_K A[r,K] B[t,K] through the split-precision tcgen05 path.
+ * a_dev [a_rows, a_cols] float32 (a_is_transposed: A is given as [K, M]); b_dev [n_b, K] float32. */
+int nfb_test_gemm(nfb_handle* h, const float* a_dev, int64_t a_rows, int64_t a_cols, int a_is_transposed,
+                  const float* b_dev, int64_t n_b, float* out_dev, int64_t ld_out, int cta_group, int splits);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NFACT_B200_H */

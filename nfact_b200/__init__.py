@@ -1,0 +1,16 @@
+"""nfact_b200 -- B200-native (sm_100a) decomposition hot path of NFACT.
+
+Drop-in replacements for the three seams where NFACT hands NumPy arrays to sklearn / scipy:
+ingest (``load_fdt_matrix`` / ``avg_fdt`` / ``process_fdt_matrix2``), the NMF solve (``nmf_decomp``)
+and the non-negative dual regression (``nmf_dual_regression``).  All arithmetic runs in
+``libnfact_b200.so`` (hand-written CUDA, C ABI in ``include/nfact_b200.h``); there is no CPU path.
+"""
+from ._lib import NfbError, load as load_library  # noqa: F401
+from .device import DeviceMatrix, NmfState, get_handle  # noqa: F401
+from .dual_regression import nmf_dual_regression, run_decomp  # noqa: F401
+from .matrix_handling import (avg_fdt, load_fdt_matrix, load_previous_matrix, load_single_matrix,  # noqa: F401
+                              normalise_components, process_fdt_matrix2, read_in_matrix, save_matrix,
+                              thresholding)
+from .nmf import NMF, compute_regularization, get_parameters, nmf_decomp  # noqa: F401
+
+__version__ = "0.1.0"

@@ -1,0 +1,92 @@
+"""ctypes binding of libnfact_b200.so (the C ABI declared in include/nfact_b200.h).
+
+There is no CPU path: if the shared library is missing or cannot be loaded this module raises, and
+every compute entry point of the package raises with it.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnfact_b200.so")
+
+
+class NfbError(RuntimeError):
+    """A libnfact_b200 call failed; the message is nfb_last_error()."""
+
+
+class NmfParams(ctypes.Structure):
+    _fields_ = [
+        ("solver", c_int),
+        ("max_iter", c_int),
+        ("tol", c_double),
+        ("l1_reg_W", c_double),
+        ("l1_reg_H", c_double),
+        ("l2_reg_W", c_double),
+        ("l2_reg_H", c_double),
+        ("verbose", c_int),
+    ]
+
+
+# name -> (restype, argtypes); every name here must be declared in include/nfact_b200.h
+SIGNATURES = {
+    "nfb_last_error": (c_char_p, []),
+    "nfb_version": (c_char_p, []),
+    "nfb_create": (c_int, [c_int, c_void_p, POINTER(c_void_p)]),
+    "nfb_destroy": (c_int, [c_void_p]),
+    "nfb_synchronize": (c_int, [c_void_p]),
+    "nfb_set_comm": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int]),
+    "nfb_nccl_unique_id": (c_int, [c_char_p, c_void_p]),
+    "nfb_nccl_init_rank": (c_int, [c_void_p, c_char_p, c_void_p, c_int, c_int]),
+    "nfb_ingest_coo": (c_int, [c_void_p, c_int, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p),
+                               POINTER(c_int64), POINTER(c_double), c_int64, c_int64, c_int, c_void_p, c_void_p]),
+    "nfb_matrix_from_host": (c_int, [c_void_p, c_void_p, c_int64, c_int64, POINTER(c_void_p)]),
+    "nfb_matrix_from_device": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, POINTER(c_void_p)]),
+    "nfb_matrix_free": (c_int, [c_void_p]),
+    "nfb_matrix_shape": (c_int, [c_void_p, POINTER(c_int64), POINTER(c_int64)]),
+    "nfb_matrix_sumsq": (c_int, [c_void_p, POINTER(c_double)]),
+    "nfb_matrix_matmul": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int64, c_void_p, c_int64]),
+    "nfb_nmf_fit_host": (c_int, [c_void_p, c_void_p, c_int, POINTER(NmfParams), c_void_p, c_void_p,
+                                 POINTER(c_int), POINTER(c_double)]),
+    "nfb_nmf_create": (c_int, [c_void_p, c_void_p, c_int, POINTER(NmfParams), POINTER(c_void_p)]),
+    "nfb_nmf_free": (c_int, [c_void_p]),
+    "nfb_nmf_set_factors_host": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "nfb_nmf_set_factors_dev": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "nfb_nmf_get_factors_host": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "nfb_nmf_get_factors_dev": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "nfb_nmf_iterate": (c_int, [c_void_p, c_int, POINTER(c_double)]),
+    "nfb_nmf_run": (c_int, [c_void_p, POINTER(c_int), POINTER(c_double)]),
+    "nfb_nmf_error": (c_int, [c_void_p, POINTER(c_double)]),
+    "nfb_launch_count": (c_int64, [c_void_p]),
+    "nfb_dual_regression_host": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, POINTER(c_int)]),
+    "nfb_test_gemm": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_int64, c_void_p, c_int64,
+                              c_int, c_int]),
+}
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    """Load the shared library (once).  Raises ImportError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C nfact_b200/csrc`).  nfact_b200 has no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_GLOBAL)
+    for name, (restype, argtypes) in SIGNATURES.items():
+        fn = getattr(lib, name)   # AttributeError here means header and library disagree
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = load().nfb_last_error()
+        raise NfbError(msg.decode() if msg else f"libnfact_b200 call failed with code {rc}")

@@ -1,0 +1,399 @@
+// Split-precision tcgen05 GEMM: the hot contraction of the NMF / dual-regression path.
+//
+//   D[r, t] = sum_K  A[r, K] * B[t, K]            r < M_total,  t < N (<= 256),  K streamed
+//
+// A is the connectivity matrix X (or X^T), B is a factor matrix stored component-major
+// ([k_pad, dim], K contiguous).  Every operand is held as two fp16 planes (hi + lo of a
+// power-of-two pre-scaled fp32 value, 22 significant bits) and each K step issues three
+// tcgen05.mma.kind::f16 (hi*hi + lo*hi + hi*lo) into one fp32 TMEM accumulator, so the result
+// matches an fp32 GEMM to ~2^-22 per product while X still costs 4 B/element of HBM traffic.
+//
+// This replaces the two sgemm calls sklearn makes per NMF iteration
+// (sklearn/decomposition/_nmf.py:376 `safe_sparse_dot(X, Ht)` and :631 `safe_sparse_dot(W.T, X)`,
+// reached from NFACT/decomp/decomposition/sso/nmfsso.py:54-56) and the k x k Gram / denominator
+// products around them (:375, :550, :632).
+//
+// Kernel shape: persistent, warp specialised (1 TMA producer thread, 1 MMA issuer thread, 4 epilogue
+// warps), multi-stage smem ring fed by TMA with 128B swizzle, double-buffered TMEM accumulator,
+// split-K over `splits` deterministic partial outputs (no atomics), optional 2-CTA pairs
+// (cta_group::2: M = 256 per pair, each CTA stages half of B).
+#include <algorithm>
+#include <cstdlib>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace nfb {
+
+namespace {
+
+constexpr int kBlockM = 128;       // accumulator rows per CTA == TMEM lanes
+constexpr int kBlockK = 64;        // fp16 elements per K block: 128 B rows, SWIZZLE_128B
+constexpr int kUmmaK = 16;         // K per tcgen05.mma for 16-bit inputs
+constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KB per plane
+constexpr int kTmemCols = 512;
+constexpr int kAccStageCols = 256;
+constexpr int kNumThreads = 256;
+constexpr int kMaxStages = 8;
+
+struct GemmArgs {
+    float* out;              // [splits][n_store rows][ld_out]   (component-major: D^T)
+    const float* col_scale;  // [N] per-column multiplier folded into the store (nullptr -> 1)
+    const float* row_scale;  // [m_total] per-row multiplier (nullptr -> 1)
+    float scale;             // global multiplier
+    int m_total;             // valid rows of D
+    int n_umma;              // UMMA N (multiple of 16, 16..256)
+    int n_store;             // columns of D that are stored (<= n_umma)
+    int num_kb;              // K blocks in total
+    int splits;              // split-K factor (<= num_kb)
+    int m_blocks;            // ceil(m_total / (128 * cta_group))
+    int ld_out;
+    long long split_stride;  // elements between consecutive split slabs
+    int num_stages;
+    int b_tile_bytes;        // per plane, per CTA
+};
+
+// 64-bit shared-memory matrix descriptor (sm_100 layout: version=1 at bit 46, SWIZZLE_128B = 2 at bit 61)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t desc = 0;
+    desc |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+    desc |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    desc |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    desc |= static_cast<uint64_t>(1) << 46;
+    desc |= static_cast<uint64_t>(2) << 61;
+    return desc;
+}
+
+// instruction descriptor for kind::f16: fp16 x fp16 -> fp32, B always K-major
+__device__ __forceinline__ uint32_t make_idesc(int m, int n, int a_mn_major) {
+    uint32_t d = 0;
+    d |= 1u << 4;                                 // D format: f32
+    d |= 0u << 7;                                 // A format: f16
+    d |= 0u << 10;                                // B format: f16
+    d |= static_cast<uint32_t>(a_mn_major) << 15; // A major
+    d |= 0u << 16;                                // B major: K
+    d |= static_cast<uint32_t>(n >> 3) << 17;
+    d |= static_cast<uint32_t>(m >> 4) << 24;
+    return d;
+}
+
+template <int kAMajorMN, int kCtaGroup>
+__global__ void __launch_bounds__(kNumThreads, 1)
+gemm_split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                  const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+                  const GemmArgs args) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t warp_idx = threadIdx.x >> 5;
+    const uint32_t lane_idx = threadIdx.x & 31;
+    const uint32_t cta_rank = kCtaGroup == 2 ? cluster_ctarank() : 0;
+    const bool is_leader = cta_rank == 0;
+
+    // ---- smem carve-up (1024 B aligned for SWIZZLE_128B) ---------------------------------------
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int stage_bytes = 2 * kATileBytes + 2 * args.b_tile_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(args.num_stages) * stage_bytes);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + kMaxStages;
+    uint64_t* tmem_full_bar = bars + 2 * kMaxStages;
+    uint64_t* tmem_empty_bar = bars + 2 * kMaxStages + 2;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+
+    if (warp_idx == 0 && lane_idx == 0) {
+        tma_prefetch_desc(&tm_a_hi);
+        tma_prefetch_desc(&tm_a_lo);
+        tma_prefetch_desc(&tm_b_hi);
+        tma_prefetch_desc(&tm_b_lo);
+    }
+    if (warp_idx == 1 && lane_idx == 0) {
+        for (int s = 0; s < args.num_stages; ++s) {
+            mbar_init(&full_bar[s], kCtaGroup);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tmem_full_bar[a], 1);
+            mbar_init(&tmem_empty_bar[a], kCtaGroup * 128);
+        }
+        fence_barrier_init();
+    }
+    if (warp_idx == 2) tmem_alloc<kCtaGroup>(tmem_ptr_smem, kTmemCols);
+    tc_fence_before();
+    if constexpr (kCtaGroup == 2) cluster_sync_all(); else __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    const int num_tiles = args.m_blocks * args.splits;
+    const int num_workers = gridDim.x / kCtaGroup;
+    const int worker = blockIdx.x / kCtaGroup;
+    const int n_load = args.n_umma / kCtaGroup;  // rows of B staged by this CTA
+
+    uint32_t stage = 0, phase = 0;
+    auto advance = [&]() {
+        if (++stage == static_cast<uint32_t>(args.num_stages)) { stage = 0; phase ^= 1; }
+    };
+
+    if (warp_idx == 0) {
+      if (lane_idx == 0) {
+        // =========================== TMA producer ===============================================
+        for (int tile = worker; tile < num_tiles; tile += num_workers) {
+            const int ks = tile / args.m_blocks, mb = tile % args.m_blocks;
+            const int kb0 = static_cast<int>(static_cast<long long>(ks) * args.num_kb / args.splits);
+            const int kb1 = static_cast<int>(static_cast<long long>(ks + 1) * args.num_kb / args.splits);
+            const int m_idx = (mb * kCtaGroup + static_cast<int>(cta_rank)) * kBlockM;
+            const int n_idx = static_cast<int>(cta_rank) * n_load;
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                uint8_t* sa_hi = smem + static_cast<size_t>(stage) * stage_bytes;
+                uint8_t* sa_lo = sa_hi + kATileBytes;
+                uint8_t* sb_hi = sa_lo + kATileBytes;
+                uint8_t* sb_lo = sb_hi + args.b_tile_bytes;
+                const int k_idx = kb * kBlockK;
+                auto load = [&](const CUtensorMap* tm, void* dst, int c0, int c1) {
+                    if constexpr (kCtaGroup == 2) tma_load_2d_2sm(tm, &full_bar[stage], dst, c0, c1);
+                    else tma_load_2d(tm, &full_bar[stage], dst, c0, c1);
+                };
+                if constexpr (kAMajorMN) {
+                    // A = X^T: global rows are K, global columns are M.  Two 64-column atoms.
+                    for (int atom = 0; atom < 2; ++atom) {
+                        load(&tm_a_hi, sa_hi + atom * (kBlockK * 128), m_idx + atom * 64, k_idx);
+                        load(&tm_a_lo, sa_lo + atom * (kBlockK * 128), m_idx + atom * 64, k_idx);
+                    }
+                } else {
+                    load(&tm_a_hi, sa_hi, k_idx, m_idx);
+                    load(&tm_a_lo, sa_lo, k_idx, m_idx);
+                }
+                load(&tm_b_hi, sb_hi, k_idx, n_idx);
+                load(&tm_b_lo, sb_lo, k_idx, n_idx);
+                if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(stage_bytes) * kCtaGroup);
+                else mbar_arrive_cluster(&full_bar[stage], 0);
+                advance();
+            }
+        }
+      }
+      __syncwarp();
+    } else if (warp_idx == 1) {
+      if (lane_idx == 0 && is_leader) {
+        // =========================== MMA issuer =================================================
+        const uint32_t idesc = make_idesc(kBlockM * kCtaGroup, args.n_umma, kAMajorMN);
+        // A: K-major  -> SBO = 8 rows * 128 B;              K step = 32 B inside the swizzle atom
+        //    MN-major -> LBO = next 64-wide M atom (8 KB),  SBO = 8 K-rows * 128 B, K step = 16 rows * 128 B
+        const uint32_t a_lbo = kAMajorMN ? kBlockK * 128 : 0;
+        const uint32_t a_kstep = kAMajorMN ? kUmmaK * 128 : kUmmaK * 2;
+        uint32_t iter = 0;
+        for (int tile = worker; tile < num_tiles; tile += num_workers, ++iter) {
+            const int ks = tile / args.m_blocks;
+            const int kb0 = static_cast<int>(static_cast<long long>(ks) * args.num_kb / args.splits);
+            const int kb1 = static_cast<int>(static_cast<long long>(ks + 1) * args.num_kb / args.splits);
+            const uint32_t as = iter & 1, aphase = (iter >> 1) & 1;
+            mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + as * kAccStageCols;
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                const uint32_t sa_hi = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
+                const uint32_t sa_lo = sa_hi + kATileBytes;
+                const uint32_t sb_hi = sa_lo + kATileBytes;
+                const uint32_t sb_lo = sb_hi + args.b_tile_bytes;
+#pragma unroll
+                for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                    const uint64_t da_hi = make_smem_desc(sa_hi + k * a_kstep, a_lbo, 1024);
+                    const uint64_t da_lo = make_smem_desc(sa_lo + k * a_kstep, a_lbo, 1024);
+                    const uint64_t db_hi = make_smem_desc(sb_hi + k * kUmmaK * 2, 0, 1024);
+                    const uint64_t db_lo = make_smem_desc(sb_lo + k * kUmmaK * 2, 0, 1024);
+                    umma_f16<kCtaGroup>(d_tmem, da_hi, db_hi, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                    umma_f16<kCtaGroup>(d_tmem, da_lo, db_hi, idesc, 1u);
+                    umma_f16<kCtaGroup>(d_tmem, da_hi, db_lo, idesc, 1u);
+                }
+                umma_commit<kCtaGroup>(&empty_bar[stage]);
+                if (kb == kb1 - 1) umma_commit<kCtaGroup>(&tmem_full_bar[as]);
+                advance();
+            }
+        }
+      }
+      __syncwarp();
+    } else if (warp_idx >= 4) {
+        // =========================== epilogue: TMEM -> registers -> global ======================
+        const uint32_t quarter = warp_idx & 3;
+        const uint32_t row = quarter * 32 + lane_idx;
+        uint32_t iter = 0;
+        for (int tile = worker; tile < num_tiles; tile += num_workers, ++iter) {
+            const int ks = tile / args.m_blocks, mb = tile % args.m_blocks;
+            const uint32_t as = iter & 1, aphase = (iter >> 1) & 1;
+            mbar_wait(&tmem_full_bar[as], aphase);
+            tc_fence_after();
+            const long long m_row = static_cast<long long>(mb * kCtaGroup + static_cast<int>(cta_rank)) * kBlockM + row;
+            const bool row_ok = m_row < args.m_total;
+            float* outp = args.out + static_cast<long long>(ks) * args.split_stride + m_row;
+            const float rs = (row_ok && args.row_scale) ? __ldg(args.row_scale + m_row) * args.scale : args.scale;
+            for (int c0 = 0; c0 < args.n_umma; c0 += 32) {
+                uint32_t v[32];
+                const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + as * kAccStageCols + c0;
+                const int ncol = (c0 + 32 <= args.n_umma) ? 32 : 16;
+                if (ncol == 32) tmem_ld_32x32b_x32(taddr, v); else tmem_ld_32x32b_x16(taddr, v);
+                tmem_ld_wait();
+                if (row_ok) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int col = c0 + j;
+                        if (j < ncol && col < args.n_store) {
+                            const float cs = args.col_scale ? __ldg(args.col_scale + col) : 1.0f;
+                            outp[static_cast<long long>(col) * args.ld_out] = (__uint_as_float(v[j]) * cs) * rs;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            if constexpr (kCtaGroup == 2) mbar_arrive_cluster(&tmem_empty_bar[as], 0);
+            else mbar_arrive(&tmem_empty_bar[as]);
+        }
+    }
+
+    tc_fence_before();
+    if constexpr (kCtaGroup == 2) cluster_sync_all(); else __syncthreads();
+    if (warp_idx == 2) tmem_dealloc<kCtaGroup>(tmem_base, kTmemCols);
+}
+
+// ---- host side -----------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+// fp16 plane [rows, ld] row-major; box = box_inner (<= 64 elements, 128 B) x box_outer rows
+int make_plane_map(CUtensorMap* tm, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_inner,
+                   int box_outer) {
+    EncodeTiledFn fn = encode_fn();
+    NFB_CHECK(fn != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
+    NFB_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld * 2) % 16 == 0, "plane must be 16 B aligned");
+    cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+    cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 2};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(box_inner), static_cast<cuuint32_t>(box_outer)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult rc = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    NFB_CHECK(rc == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code " + std::to_string(static_cast<int>(rc)));
+    return 0;
+}
+
+template <int kAMajorMN, int kCtaGroup>
+int launch(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
+           const GemmArgs& args, int grid, size_t smem_bytes, cudaStream_t stream) {
+    auto kernel = gemm_split_kernel<kAMajorMN, kCtaGroup>;
+    NFB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes)));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kNumThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kCtaGroup;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    NFB_CUDA(cudaLaunchKernelEx(&cfg, kernel, a_hi, a_lo, b_hi, b_lo, args));
+    return 0;
+}
+
+}  // namespace
+
+int gemm_default_cta_group() {
+    static int value = -1;
+    if (value < 0) {
+        const char* env = getenv("NFB_GEMM_CTA_GROUP");
+        value = env ? atoi(env) : 2;
+        if (value != 1 && value != 2) value = 2;
+    }
+    return value;
+}
+
+int gemm_pick_splits(int64_t m_total, int64_t k_total, int cta_group) {
+    const int64_t m_blocks = ceil_div64(m_total, static_cast<int64_t>(kBlockM) * cta_group);
+    const int64_t num_kb = ceil_div64(k_total, kBlockK);
+    const int64_t workers = sm_count() / cta_group;
+    // Aim for >= 4 waves of equal tiles; keep every split at least 4 K blocks long.
+    int64_t best = 1;
+    double best_eff = 0.0;
+    const int64_t max_splits = std::max<int64_t>(1, std::min<int64_t>(num_kb / 4, 64));
+    for (int64_t s = 1; s <= max_splits; ++s) {
+        const int64_t tiles = m_blocks * s;
+        const int64_t waves = ceil_div64(tiles, workers);
+        const double eff = static_cast<double>(tiles) / static_cast<double>(waves * workers);
+        // small bias towards fewer splits (less partial traffic)
+        const double score = eff - 0.002 * static_cast<double>(s);
+        if (score > best_eff) { best_eff = score; best = s; }
+    }
+    return static_cast<int>(best);
+}
+
+int gemm_split(const GemmOperand& a, bool a_is_mn_major, const GemmOperand& b, int64_t m_total, int64_t k_total,
+               int n_umma, int n_store, float* out, int64_t ld_out, int splits, const float* col_scale,
+               const float* row_scale, float scale, int cta_group, cudaStream_t stream) {
+    NFB_CHECK(n_umma % 16 == 0 && n_umma >= 16 && n_umma <= 256, "n_umma must be a multiple of 16 in [16,256]");
+    NFB_CHECK(cta_group == 1 || cta_group == 2, "cta_group must be 1 or 2");
+    NFB_CHECK(n_store <= n_umma, "n_store exceeds n_umma");
+    NFB_CHECK(m_total < (1LL << 31) && k_total < (1LL << 31), "dimension exceeds int32");
+    const int64_t num_kb = ceil_div64(k_total, kBlockK);
+    NFB_CHECK(splits >= 1 && splits <= num_kb, "splits must be in [1, num_k_blocks]");
+
+    CUtensorMap tm_a_hi, tm_a_lo, tm_b_hi, tm_b_lo;
+    if (a_is_mn_major) {
+        // plane rows = K, plane cols = M
+        NFB_TRY(make_plane_map(&tm_a_hi, a.hi, k_total, m_total, a.ld, 64, kBlockK));
+        NFB_TRY(make_plane_map(&tm_a_lo, a.lo, k_total, m_total, a.ld, 64, kBlockK));
+    } else {
+        NFB_TRY(make_plane_map(&tm_a_hi, a.hi, m_total, k_total, a.ld, kBlockK, kBlockM));
+        NFB_TRY(make_plane_map(&tm_a_lo, a.lo, m_total, k_total, a.ld, kBlockK, kBlockM));
+    }
+    const int n_load = n_umma / cta_group;
+    NFB_CHECK(n_load % 8 == 0, "per-CTA B rows must be a multiple of 8");
+    NFB_CHECK(b.rows >= n_umma, "B plane has fewer rows than n_umma");
+    NFB_TRY(make_plane_map(&tm_b_hi, b.hi, b.rows, k_total, b.ld, kBlockK, n_load));
+    NFB_TRY(make_plane_map(&tm_b_lo, b.lo, b.rows, k_total, b.ld, kBlockK, n_load));
+
+    GemmArgs args;
+    args.out = out;
+    args.col_scale = col_scale;
+    args.row_scale = row_scale;
+    args.scale = scale;
+    args.m_total = static_cast<int>(m_total);
+    args.n_umma = n_umma;
+    args.n_store = n_store;
+    args.num_kb = static_cast<int>(num_kb);
+    args.splits = splits;
+    args.m_blocks = static_cast<int>(ceil_div64(m_total, static_cast<int64_t>(kBlockM) * cta_group));
+    args.ld_out = static_cast<int>(ld_out);
+    args.split_stride = static_cast<long long>(n_store) * ld_out;
+    args.b_tile_bytes = n_load * 128;
+    const int stage_bytes = 2 * kATileBytes + 2 * args.b_tile_bytes;
+    const int smem_budget = 227 * 1024 - 1024 /*align*/ - 256 /*barriers*/;
+    args.num_stages = std::min(kMaxStages, smem_budget / stage_bytes);
+    NFB_CHECK(args.num_stages >= 2, "not enough shared memory for a 2-stage pipeline");
+    const size_t smem_bytes = static_cast<size_t>(args.num_stages) * stage_bytes + 1024 + 256;
+
+    const int64_t tiles = static_cast<int64_t>(args.m_blocks) * splits;
+    int workers = static_cast<int>(std::min<int64_t>(tiles, sm_count() / cta_group));
+    const int grid = workers * cta_group;
+
+    if (a_is_mn_major) {
+        if (cta_group == 2) return launch<1, 2>(tm_a_hi, tm_a_lo, tm_b_hi, tm_b_lo, args, grid, smem_bytes, stream);
+        return launch<1, 1>(tm_a_hi, tm_a_lo, tm_b_hi, tm_b_lo, args, grid, smem_bytes, stream);
+    }
+    if (cta_group == 2) return launch<0, 2>(tm_a_hi, tm_a_lo, tm_b_hi, tm_b_lo, args, grid, smem_bytes, stream);
+    return launch<0, 1>(tm_a_hi, tm_a_lo, tm_b_hi, tm_b_lo, args, grid, smem_bytes, stream);
+}
+
+}  // namespace nfb

@@ -1,0 +1,100 @@
+// Internal host-side launch API of the nfact_b200 CUDA kernels (C++; the public C ABI is
+// include/nfact_b200.h).  All pointers are device pointers unless stated otherwise.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace nfb {
+
+// fp16 hi/lo planes of a pre-scaled fp32 matrix, row-major [rows, ld] (ld % 8 == 0, padding = 0)
+struct GemmOperand {
+    const __half* hi;
+    const __half* lo;
+    int64_t rows;
+    int64_t ld;
+};
+
+// ---- gemm_split.cu --------------------------------------------------------------------------------
+int gemm_default_cta_group();
+int gemm_pick_splits(int64_t m_total, int64_t k_total, int cta_group);
+// out[s][t][r] (r contiguous, leading dimension ld_out)
+//     = scale * col_scale[t] * row_scale[r] * sum_{K in split s} A[r,K] B[t,K]      (null scale vectors -> 1)
+//   a_is_mn_major == false : A planes are [m_total rows, K cols]     (X      for X H^T)
+//   a_is_mn_major == true  : A planes are [K rows, m_total cols]     (X read as X^T for W^T X)
+int gemm_split(const GemmOperand& a, bool a_is_mn_major, const GemmOperand& b, int64_t m_total, int64_t k_total,
+               int n_umma, int n_store, float* out, int64_t ld_out, int splits, const float* col_scale,
+               const float* row_scale, float scale, int cta_group, cudaStream_t stream);
+
+// ---- planes.cu ------------------------------------------------------------------------------------
+// max |x| over a [rows, cols] fp32 matrix (ld >= cols) -> *out_bits (float bits, must be zeroed first)
+int absmax_f32(const float* x, int64_t rows, int64_t cols, int64_t ld, unsigned int* out_bits, cudaStream_t stream);
+// per-row max |x| -> rowmax_bits[rows] (must be zeroed first)
+// col_mul (nullable, [cols]): the maxima are taken over x[r][c] * col_mul[c]
+int rowabsmax_f32(const float* x, int64_t rows, int64_t cols, int64_t ld, const float* col_mul,
+                  unsigned int* rowmax_bits, cudaStream_t stream);
+// X [rows, cols] fp32 -> hi/lo planes [rows, ldp] scaled by the power of two that maps *max_bits into
+// [2^14, 2^15); inv_scale[0] receives 1/scale; sumsq (may be null) accumulates sum x^2 in fp64.
+int split_matrix(const float* x, int64_t rows, int64_t cols, int64_t ld, const unsigned int* max_bits, __half* hi,
+                 __half* lo, int64_t ldp, float* inv_scale, double* sumsq, cudaStream_t stream);
+// factor F [k, cols] fp32 -> planes [>=k rows, ldp] with one power-of-two scale per row
+// (from rowmax_bits[k]); inv_scale[k] receives 1/scale_t.  Columns [cols, ldp) are zeroed.
+// col_mul (nullable, [cols]) multiplies column c before the split (used to fold the K-side scales of
+// the other operand into a Gram matrix).
+int split_factor(const float* f, int64_t k, int64_t cols, int64_t ld, const float* col_mul,
+                 const unsigned int* rowmax_bits, __half* hi, __half* lo, int64_t ldp, float* inv_scale,
+                 cudaStream_t stream);
+
+// ---- update.cu ------------------------------------------------------------------------------------
+// out[t][j] = sum_s part[s][t][j] + bias     (t < k, j < cols)
+int reduce_partials(const float* part, int splits, int64_t split_stride, int64_t k, int64_t cols, int64_t ld,
+                    float bias, float* out, int64_t ld_out, cudaStream_t stream);
+// multiplicative update of one factor (sklearn _multiplicative_update_w/_h, beta = 2):
+//   F[t][j] *= (sum_s num[s][t][j]) / den,  den = sum_s dpart[s][t][j] + l1 + l2 F[t][j], den == 0 -> eps
+// rowmax_bits[k] (zeroed by the caller) receives the new per-row maxima.
+int mu_update(float* f, int64_t k, int64_t cols, int64_t ld, const float* num, int num_splits, int64_t num_stride,
+              const float* den, int den_splits, int64_t den_stride, int64_t ld_part, float l1, float l2,
+              unsigned int* rowmax_bits, cudaStream_t stream);
+// one coordinate-descent sweep over all k components for every column j of F [k, cols]
+// (sklearn _cdnmf_fast.pyx with F = W^T):  num = sum_s part[s] - l1, G = gram (+ l2 on the diagonal).
+// violation (fp64, accumulated) and rowmax_bits as above.
+int cd_sweep(float* f, int64_t k, int64_t cols, int64_t ld, const float* num, int num_splits, int64_t num_stride,
+             int64_t ld_part, const float* gram, float l1, float l2, double* violation, unsigned int* rowmax_bits,
+             cudaStream_t stream);
+// *out += sum_{t<k, j<cols} a[t][j] * (sum_s b[s][t][j])        (fp64 accumulation)
+int dot_partials(const float* a, int64_t lda, const float* b, int splits, int64_t b_stride, int64_t ldb, int64_t k,
+                 int64_t cols, double* out, cudaStream_t stream);
+// out64[t][j] = sum_s part[s][t][j]  (fp64 accumulation of fp32 partials)
+int reduce_partials_f64(const float* part, int splits, int64_t split_stride, int64_t k, int64_t cols, int64_t ld,
+                        double* out, int64_t ld_out, cudaStream_t stream);
+// gram64[t][u] = sum_j f[t][j] f[u][j] in float64 (k x k, ld = k) straight from the fp32 factor
+int gram_f64(const float* f, int64_t k, int64_t cols, int64_t ld, double* gram64, cudaStream_t stream);
+// out32[t][j] = (float) in64[t][j]; rowmax_bits as in mu_update
+int f64_to_f32_rowmax(const double* in, int64_t k, int64_t cols, int64_t ld_in, float* out, int64_t ld_out,
+                      unsigned int* rowmax_bits, cudaStream_t stream);
+// *out += sum_{t,u<k} a[t][u] * b[t][u]
+int dot_small(const float* a, const float* b, int64_t k, int64_t ld, double* out, cudaStream_t stream);
+// transpose fp32 [rows, cols] (ld_in) -> [cols, rows] (ld_out)
+int transpose_f32(const float* in, int64_t rows, int64_t cols, int64_t ld_in, float* out, int64_t ld_out,
+                  cudaStream_t stream);
+int transpose_f64_to_f32(const double* in, int64_t rows, int64_t cols, int64_t ld_in, float* out, int64_t ld_out,
+                         cudaStream_t stream);
+
+// ---- ingest.cu ------------------------------------------------------------------------------------
+// phase A: tmp[r*ncols+c] += v for every triplet with row in [row0, row0+nrows_blk)  (fp64 atomics)
+// phase B: the first thread to exchange a non-zero tmp cell adds cell*scale to acc and leaves tmp zero.
+int ingest_scatter(const int* rows, const int* cols, const double* vals, int64_t nnz, int64_t row0,
+                   int64_t nrows_blk, int64_t nrows_total, int64_t ncols, double scale, double* tmp, double* acc,
+                   int* oob_flag, cudaStream_t stream);
+// X[r][c] = (float)(acc * recip)   (recip == 1.0 -> plain rounding)
+int ingest_finalize(const double* acc, int64_t nelem, double recip, int apply_recip, float* x, cudaStream_t stream);
+
+// ---- nnls.cu --------------------------------------------------------------------------------------
+// Batched non-negative least squares with one shared Gram matrix:
+//   for every column j < cols:  min_{h >= 0} 0.5 h'Gh - rhs[:, j]'h ,  G [k,k] fp64, rhs [k, ld] fp32 partials
+// sol [k, ld_sol] fp64.  status[0] counts columns that hit the iteration cap.
+int nnls_gram_batched(const double* gram, int64_t k, const float* rhs, int rhs_splits, int64_t rhs_stride,
+                      int64_t ld_rhs, int64_t cols, double* sol, int64_t ld_sol, int max_outer, int* status,
+                      cudaStream_t stream);
+
+}  // namespace nfb

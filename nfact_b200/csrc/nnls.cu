@@ -1,0 +1,131 @@
+// Batched non-negative least squares on a shared Gram matrix (the nfact_dr hot loop).
+//
+// The reference solves, for every target column j (stage 1) / seed row i (stage 2),
+//     h_j = argmin_{h >= 0} || A h - x_j ||_2        scipy.optimize.nnls(A, x_j)  (float64, Lawson-Hanson)
+// (NFACT/dual_reg/dual_regression/dual_regression_methods.py:137-163).  Every one of those problems shares
+// A, so they share the k x k Gram matrix G = A'A and differ only in the right-hand side r_j = A'x_j:
+//     h_j = argmin_{h >= 0} 0.5 h'Gh - r_j'h .
+// G and all r_j come out of the tensor-core GEMMs; this kernel solves the n (or m) independent k-dim
+// QPs in float64, one warp per problem, by exact coordinate minimisation (the same projected
+// Newton step as the NMF coordinate-descent sweep) with the gradient g = Gh - r kept incrementally:
+// a coordinate whose value does not move costs O(1), a move costs one column of G.  Full sweeps detect
+// support changes; between them only the current support is swept.  The minimiser of a strictly convex
+// QP is unique, so on full-column-rank A the fixed point equals the active-set solution of scipy;
+// convergence is declared on the KKT residual max_t |pg_t| <= tol * max|r|.
+#include <algorithm>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace nfb {
+namespace {
+
+__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
+template <int KPL>  // coordinates per lane: k <= 32 * KPL
+__global__ void __launch_bounds__(128)
+nnls_cd_kernel(const double* __restrict__ gram, int k, const float* __restrict__ rhs, int rhs_splits,
+               int64_t rhs_stride, int64_t ld_rhs, int64_t cols, double* __restrict__ sol, int64_t ld_sol,
+               int max_outer, double tol, int* __restrict__ status) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp_global = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+    const int64_t num_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+
+    for (int64_t j = warp_global; j < cols; j += num_warps) {
+        double h[KPL], g[KPL];
+        double rmax = 0.0;
+#pragma unroll
+        for (int i = 0; i < KPL; ++i) {
+            const int t = lane + 32 * i;
+            double r = 0.0;
+            if (t < k)
+                for (int s = 0; s < rhs_splits; ++s) r += static_cast<double>(rhs[s * rhs_stride + t * ld_rhs + j]);
+            h[i] = 0.0;
+            g[i] = -r;
+            rmax = fmax(rmax, fabs(r));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) rmax = fmax(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
+        const double thresh = tol * rmax;
+
+        // one exact coordinate step on component t; returns |projected gradient| before the step
+        auto step = [&](int t) -> double {
+            const int owner = t & 31, slot = t >> 5;
+            double gt = 0.0, ht = 0.0;
+#pragma unroll
+            for (int i = 0; i < KPL; ++i)
+                if (i == slot) { gt = g[i]; ht = h[i]; }
+            gt = shfl_d(gt, owner);
+            ht = shfl_d(ht, owner);
+            const double gtt = __ldg(gram + static_cast<int64_t>(t) * k + t);
+            const double pg = (ht == 0.0) ? fmin(gt, 0.0) : gt;
+            if (gtt > 0.0) {
+                const double hn = fmax(ht - gt / gtt, 0.0);
+                const double delta = hn - ht;
+                if (delta != 0.0) {  // warp-uniform
+                    const double* gcol = gram + static_cast<int64_t>(t) * k;  // G symmetric: row t == column t
+#pragma unroll
+                    for (int i = 0; i < KPL; ++i) {
+                        const int u = lane + 32 * i;
+                        if (u < k) g[i] = fma(delta, __ldg(gcol + u), g[i]);
+                        if (i == slot && lane == owner) h[i] = hn;
+                    }
+                }
+            }
+            return fabs(pg);
+        };
+
+        bool converged = (rmax == 0.0);
+        for (int outer = 0; outer < max_outer && !converged; ++outer) {
+            double viol = 0.0;
+            for (int t = 0; t < k; ++t) viol = fmax(viol, step(t));
+            if (viol <= thresh) { converged = true; break; }
+            // sweeps restricted to the current support
+            for (int inner = 0; inner < 64; ++inner) {
+                double iv = 0.0;
+#pragma unroll
+                for (int i = 0; i < KPL; ++i) {
+                    unsigned mask = __ballot_sync(0xffffffffu, h[i] > 0.0);
+                    while (mask) {
+                        const int bit = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        iv = fmax(iv, step(32 * i + bit));
+                    }
+                }
+                if (iv <= thresh) break;
+            }
+        }
+        if (!converged && lane == 0) atomicAdd(status, 1);
+#pragma unroll
+        for (int i = 0; i < KPL; ++i) {
+            const int t = lane + 32 * i;
+            if (t < k) sol[t * ld_sol + j] = h[i];
+        }
+    }
+}
+
+}  // namespace
+
+int nnls_gram_batched(const double* gram, int64_t k, const float* rhs, int rhs_splits, int64_t rhs_stride,
+                      int64_t ld_rhs, int64_t cols, double* sol, int64_t ld_sol, int max_outer, int* status,
+                      cudaStream_t stream) {
+    if (k == 0 || cols == 0) return 0;
+    NFB_CHECK(k <= 512, "n_components > 512 is not supported by the NNLS kernel");
+    const int threads = 128;
+    const int64_t warps_needed = cols;
+    const int blocks = static_cast<int>(std::max<int64_t>(
+        1, std::min<int64_t>(ceil_div64(warps_needed * 32, threads), static_cast<int64_t>(sm_count()) * 8)));
+    const double tol = 1e-10;
+#define NFB_NNLS_LAUNCH(KPL)                                                                                   \
+    nnls_cd_kernel<KPL><<<blocks, threads, 0, stream>>>(gram, static_cast<int>(k), rhs, rhs_splits, rhs_stride, \
+                                                        ld_rhs, cols, sol, ld_sol, max_outer, tol, status)
+    if (k <= 64) NFB_NNLS_LAUNCH(2);
+    else if (k <= 128) NFB_NNLS_LAUNCH(4);
+    else if (k <= 256) NFB_NNLS_LAUNCH(8);
+    else NFB_NNLS_LAUNCH(16);
+#undef NFB_NNLS_LAUNCH
+    NFB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace nfb

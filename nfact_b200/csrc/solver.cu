@@ -1,0 +1,861 @@
+// Host-side runtime of libnfact_b200.so: handles, resident matrices, the NMF loops (multiplicative
+// update and coordinate descent with sklearn's stopping rules), dual regression, ingest, and the C ABI.
+//
+// Reference call sites this replaces:
+//   NFACT/decomp/decomposition/sso/nmfsso.py:32-59          nmf_decomp -> sklearn NMF.fit_transform
+//   NFACT/dual_reg/dual_regression/dual_regression_methods.py:92-167   nmf_dual_regression
+//   NFACT/base/matrix_handling.py:116-158, NFACT/decomp/decomposition/matrix_handling.py:73-100   ingest
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+#include "../../include/nfact_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace nfb {
+
+static thread_local std::string g_error;
+void set_error(const std::string& msg) { g_error = msg; }
+
+int sm_count() {
+    static int value = 0;
+    if (value == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&value, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || value <= 0) value = 148;
+    }
+    return value;
+}
+
+std::atomic<int64_t> g_launches{0};
+void note_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    int alloc(size_t count, bool zero, cudaStream_t stream) {
+        release();
+        if (count == 0) count = 1;
+        NFB_CUDA(cudaMalloc(reinterpret_cast<void**>(&p), count * sizeof(T)));
+        n = count;
+        if (zero) NFB_CUDA(cudaMemsetAsync(p, 0, count * sizeof(T), stream));
+        return 0;
+    }
+};
+
+typedef int (*NcclAllReduceFn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+constexpr int kNcclFloat = 7, kNcclDouble = 8, kNcclSum = 0;
+
+}  // namespace nfb
+
+using namespace nfb;
+
+struct nfb_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int cta_group = 2;
+    int64_t launches_last = 0;
+    // multi-GPU (row-sharded) -------------------------------------------------
+    void* comm = nullptr;
+    NcclAllReduceFn allreduce = nullptr;
+    int rank = 0, world = 1;
+    void* nccl_lib = nullptr;
+    bool own_comm = false;
+    // scratch -----------------------------------------------------------------
+    DevBuf<double> d_scal;        // small fp64 scalars
+    DevBuf<unsigned int> d_bits;  // absmax bits
+    DevBuf<int> d_int;
+    double* h_scal = nullptr;     // pinned mirror
+};
+
+struct nfb_matrix {
+    nfb_handle* h = nullptr;
+    int64_t m = 0, n = 0, ldp = 0;
+    DevBuf<__half> hi, lo;
+    DevBuf<float> inv_scale;
+    float inv_scale_host = 1.0f;
+    double sumsq = 0.0;  // local shard
+    GemmOperand operand() const { return GemmOperand{hi.p, lo.p, m, ldp}; }
+};
+
+namespace nfb {
+
+// A factor matrix stored component-major: fp32 master [kp][ld] plus fp16 planes with per-row scales.
+struct Factor {
+    int64_t k = 0, kp = 0, dim = 0, ld = 0;
+    DevBuf<float> f;
+    DevBuf<__half> hi, lo;
+    DevBuf<float> inv_scale;
+    DevBuf<unsigned int> rowmax;
+    int init(int64_t k_, int64_t dim_, bool with_master, cudaStream_t stream, int64_t ld_override = 0) {
+        k = k_;
+        kp = round_up64(k_, 16);
+        dim = dim_;
+        ld = ld_override > 0 ? ld_override : round_up64(std::max<int64_t>(dim_, 1), 8);
+        if (with_master) NFB_TRY(f.alloc(kp * ld, true, stream));
+        NFB_TRY(hi.alloc(kp * ld, true, stream));
+        NFB_TRY(lo.alloc(kp * ld, true, stream));
+        NFB_TRY(inv_scale.alloc(kp, true, stream));
+        NFB_TRY(rowmax.alloc(kp, true, stream));
+        return 0;
+    }
+    GemmOperand operand() const { return GemmOperand{hi.p, lo.p, kp, ld}; }
+};
+
+static int refresh_planes(Factor& fac, const float* src, const float* col_mul, bool recompute_max,
+                          cudaStream_t stream) {
+    if (recompute_max) {
+        NFB_CUDA(cudaMemsetAsync(fac.rowmax.p, 0, sizeof(unsigned int) * fac.kp, stream));
+        NFB_TRY(rowabsmax_f32(src, fac.k, fac.dim, fac.ld, col_mul, fac.rowmax.p, stream));
+        note_launch(1);
+    }
+    NFB_TRY(split_factor(src, fac.k, fac.dim, fac.ld, col_mul, fac.rowmax.p, fac.hi.p, fac.lo.p, fac.ld,
+                         fac.inv_scale.p, stream));
+    note_launch(1);
+    return 0;
+}
+
+}  // namespace nfb
+
+struct nfb_nmf {
+    nfb_handle* h = nullptr;
+    const nfb_matrix* x = nullptr;
+    int k = 0;
+    int64_t kp = 0;
+    nfb_nmf_params p{};
+    Factor wt, hh;        // W^T [k, m] and H [k, n]
+    Factor gw, gh;        // Gram matrices W'W and HH' (fp32 [kp][kp]); planes are only used as scratch
+    Factor gd;            // planes of a Gram matrix with the K-side scales folded in (denominator GEMM)
+    DevBuf<float> part_w, part_h, part_den, part_gram, num_h;
+    int s_w = 1, s_h = 1, s_gw = 1, s_gh = 1;
+    double sumsq_global = 0.0;
+    bool p1_valid = false;  // part_w holds X H' for the current H
+    double last_violation = 0.0;
+};
+
+namespace nfb {
+
+static int allreduce_f32(nfb_handle* h, float* buf, size_t count) {
+    if (h->world <= 1) return 0;
+    NFB_CHECK(h->allreduce != nullptr && h->comm != nullptr, "multi-GPU run without a communicator");
+    int rc = h->allreduce(buf, buf, count, kNcclFloat, kNcclSum, h->comm, h->stream);
+    NFB_CHECK(rc == 0, "ncclAllReduce(float) failed with code " + std::to_string(rc));
+    return 0;
+}
+static int allreduce_f64(nfb_handle* h, double* buf, size_t count) {
+    if (h->world <= 1) return 0;
+    NFB_CHECK(h->allreduce != nullptr && h->comm != nullptr, "multi-GPU run without a communicator");
+    int rc = h->allreduce(buf, buf, count, kNcclDouble, kNcclSum, h->comm, h->stream);
+    NFB_CHECK(rc == 0, "ncclAllReduce(double) failed with code " + std::to_string(rc));
+    return 0;
+}
+
+// G = F F' (fp32 [k][kp]) through the tensor-core path; partial sums over `splits` K ranges.
+static int compute_gram(nfb_nmf* s, Factor& fac, Factor& gram, int splits, bool allreduce) {
+    nfb_handle* h = s->h;
+    NFB_TRY(gemm_split(fac.operand(), false, fac.operand(), fac.k, fac.dim, static_cast<int>(fac.kp),
+                       static_cast<int>(fac.k), s->part_gram.p, gram.ld, splits, fac.inv_scale.p, fac.inv_scale.p,
+                       1.0f, h->cta_group, h->stream));
+    NFB_TRY(reduce_partials(s->part_gram.p, splits, fac.k * gram.ld, fac.k, fac.k, gram.ld, 0.0f, gram.f.p, gram.ld,
+                            h->stream));
+    note_launch(2);
+    if (allreduce) NFB_TRY(allreduce_f32(h, gram.f.p, static_cast<size_t>(gram.kp * gram.ld)));
+    return 0;
+}
+
+// part_w = X H'   (per split) for the current H planes
+static int gemm_xht(nfb_nmf* s) {
+    nfb_handle* h = s->h;
+    NFB_TRY(gemm_split(s->x->operand(), false, s->hh.operand(), s->x->m, s->x->n, static_cast<int>(s->kp), s->k,
+                       s->part_w.p, s->wt.ld, s->s_w, s->hh.inv_scale.p, nullptr, s->x->inv_scale_host,
+                       h->cta_group, h->stream));
+    note_launch(1);
+    s->p1_valid = true;
+    return 0;
+}
+
+// part_h = W'X   (per split) for the current W planes; row-sharded runs reduce it across ranks
+static int gemm_wtx(nfb_nmf* s, const float** num_out, int* splits_out, int64_t* stride_out) {
+    nfb_handle* h = s->h;
+    NFB_TRY(gemm_split(s->x->operand(), true, s->wt.operand(), s->x->n, s->x->m, static_cast<int>(s->kp), s->k,
+                       s->part_h.p, s->hh.ld, s->s_h, s->wt.inv_scale.p, nullptr, s->x->inv_scale_host,
+                       h->cta_group, h->stream));
+    note_launch(1);
+    *num_out = s->part_h.p;
+    *splits_out = s->s_h;
+    *stride_out = static_cast<int64_t>(s->k) * s->hh.ld;
+    if (h->world > 1) {
+        NFB_TRY(reduce_partials(s->part_h.p, s->s_h, static_cast<int64_t>(s->k) * s->hh.ld, s->k, s->x->n, s->hh.ld,
+                                0.0f, s->num_h.p, s->hh.ld, h->stream));
+        note_launch(1);
+        NFB_TRY(allreduce_f32(h, s->num_h.p, static_cast<size_t>(s->k) * s->hh.ld));
+        *num_out = s->num_h.p;
+        *splits_out = 1;
+    }
+    return 0;
+}
+
+// denominator of the multiplicative update: part_den[t][j] = sum_r G[t][r] F[r][j]
+static int gemm_den(nfb_nmf* s, Factor& fac, Factor& gram) {
+    nfb_handle* h = s->h;
+    // fold the per-component scales of F's planes (the K side of this product) into G's columns
+    NFB_TRY(refresh_planes(s->gd, gram.f.p, fac.inv_scale.p, true, h->stream));
+    GemmOperand a = fac.operand();
+    a.rows = fac.k;
+    NFB_TRY(gemm_split(a, true, s->gd.operand(), fac.dim, fac.k, static_cast<int>(s->kp), s->k, s->part_den.p,
+                       fac.ld, 1, s->gd.inv_scale.p, nullptr, 1.0f, h->cta_group, h->stream));
+    note_launch(1);
+    return 0;
+}
+
+static int mu_iteration(nfb_nmf* s) {
+    nfb_handle* h = s->h;
+    const nfb_nmf_params& p = s->p;
+    if (!s->p1_valid) NFB_TRY(gemm_xht(s));
+    // ---- W half-step ----
+    NFB_TRY(gemm_den(s, s->wt, s->gh));
+    NFB_CUDA(cudaMemsetAsync(s->wt.rowmax.p, 0, sizeof(unsigned int) * s->kp, h->stream));
+    NFB_TRY(mu_update(s->wt.f.p, s->k, s->x->m, s->wt.ld, s->part_w.p, s->s_w, static_cast<int64_t>(s->k) * s->wt.ld,
+                      s->part_den.p, 1, 0, s->wt.ld, static_cast<float>(p.l1_reg_W), static_cast<float>(p.l2_reg_W),
+                      s->wt.rowmax.p, h->stream));
+    note_launch(1);
+    s->p1_valid = false;
+    NFB_TRY(refresh_planes(s->wt, s->wt.f.p, nullptr, false, h->stream));
+    NFB_TRY(compute_gram(s, s->wt, s->gw, s->s_gw, true));
+    // ---- H half-step ----
+    const float* num;
+    int num_splits;
+    int64_t num_stride;
+    NFB_TRY(gemm_wtx(s, &num, &num_splits, &num_stride));
+    NFB_TRY(gemm_den(s, s->hh, s->gw));
+    NFB_CUDA(cudaMemsetAsync(s->hh.rowmax.p, 0, sizeof(unsigned int) * s->kp, h->stream));
+    NFB_TRY(mu_update(s->hh.f.p, s->k, s->x->n, s->hh.ld, num, num_splits, num_stride, s->part_den.p, 1, 0,
+                      s->hh.ld, static_cast<float>(p.l1_reg_H), static_cast<float>(p.l2_reg_H), s->hh.rowmax.p,
+                      h->stream));
+    note_launch(1);
+    NFB_TRY(refresh_planes(s->hh, s->hh.f.p, nullptr, false, h->stream));
+    NFB_TRY(compute_gram(s, s->hh, s->gh, s->s_gh, false));
+    return 0;
+}
+
+// d_scal layout: [0] cross, [1] gram dot, [2] violation W, [3] violation H
+static int cd_iteration(nfb_nmf* s, double* violation_out) {
+    nfb_handle* h = s->h;
+    const nfb_nmf_params& p = s->p;
+    NFB_CUDA(cudaMemsetAsync(h->d_scal.p + 2, 0, 2 * sizeof(double), h->stream));
+    if (!s->p1_valid) NFB_TRY(gemm_xht(s));
+    // ---- W half-step ----
+    NFB_CUDA(cudaMemsetAsync(s->wt.rowmax.p, 0, sizeof(unsigned int) * s->kp, h->stream));
+    NFB_TRY(cd_sweep(s->wt.f.p, s->k, s->x->m, s->wt.ld, s->part_w.p, s->s_w, static_cast<int64_t>(s->k) * s->wt.ld,
+                     s->wt.ld, s->gh.f.p, static_cast<float>(p.l1_reg_W), static_cast<float>(p.l2_reg_W),
+                     h->d_scal.p + 2, s->wt.rowmax.p, h->stream));
+    note_launch(1);
+    s->p1_valid = false;
+    NFB_TRY(refresh_planes(s->wt, s->wt.f.p, nullptr, false, h->stream));
+    NFB_TRY(compute_gram(s, s->wt, s->gw, s->s_gw, true));
+    // ---- H half-step ----
+    const float* num;
+    int num_splits;
+    int64_t num_stride;
+    NFB_TRY(gemm_wtx(s, &num, &num_splits, &num_stride));
+    NFB_CUDA(cudaMemsetAsync(s->hh.rowmax.p, 0, sizeof(unsigned int) * s->kp, h->stream));
+    NFB_TRY(cd_sweep(s->hh.f.p, s->k, s->x->n, s->hh.ld, num, num_splits, num_stride, s->hh.ld, s->gw.f.p,
+                     static_cast<float>(p.l1_reg_H), static_cast<float>(p.l2_reg_H), h->d_scal.p + 3,
+                     s->hh.rowmax.p, h->stream));
+    note_launch(1);
+    NFB_TRY(refresh_planes(s->hh, s->hh.f.p, nullptr, false, h->stream));
+    NFB_TRY(compute_gram(s, s->hh, s->gh, s->s_gh, false));
+    if (violation_out != nullptr) {
+        NFB_TRY(allreduce_f64(h, h->d_scal.p + 2, 1));  // W rows are sharded, H is replicated
+        NFB_CUDA(cudaMemcpyAsync(h->h_scal + 2, h->d_scal.p + 2, 2 * sizeof(double), cudaMemcpyDeviceToHost,
+                                 h->stream));
+        NFB_CUDA(cudaStreamSynchronize(h->stream));
+        *violation_out = h->h_scal[2] + h->h_scal[3];
+    }
+    return 0;
+}
+
+// ||X - WH||_F via  ||X||^2 - 2 <W, X H'> + <W'W, HH'>   (float64 accumulation)
+static int nmf_error(nfb_nmf* s, double* err_out) {
+    nfb_handle* h = s->h;
+    if (!s->p1_valid) NFB_TRY(gemm_xht(s));
+    NFB_CUDA(cudaMemsetAsync(h->d_scal.p, 0, 2 * sizeof(double), h->stream));
+    NFB_TRY(dot_partials(s->wt.f.p, s->wt.ld, s->part_w.p, s->s_w, static_cast<int64_t>(s->k) * s->wt.ld, s->wt.ld,
+                         s->k, s->x->m, h->d_scal.p, h->stream));
+    NFB_TRY(dot_small(s->gw.f.p, s->gh.f.p, s->k, s->gw.ld, h->d_scal.p + 1, h->stream));
+    note_launch(2);
+    NFB_TRY(allreduce_f64(h, h->d_scal.p, 1));
+    NFB_CUDA(cudaMemcpyAsync(h->h_scal, h->d_scal.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    NFB_CUDA(cudaStreamSynchronize(h->stream));
+    const double sq = s->sumsq_global - 2.0 * h->h_scal[0] + h->h_scal[1];
+    *err_out = std::sqrt(std::max(sq, 0.0));
+    return 0;
+}
+
+static int nmf_prepare_factors(nfb_nmf* s) {
+    nfb_handle* h = s->h;
+    NFB_TRY(refresh_planes(s->wt, s->wt.f.p, nullptr, true, h->stream));
+    NFB_TRY(refresh_planes(s->hh, s->hh.f.p, nullptr, true, h->stream));
+    NFB_TRY(compute_gram(s, s->wt, s->gw, s->s_gw, true));
+    NFB_TRY(compute_gram(s, s->hh, s->gh, s->s_gh, false));
+    s->p1_valid = false;
+    return 0;
+}
+
+}  // namespace nfb
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+const char* nfb_last_error(void) { return g_error.c_str(); }
+const char* nfb_version(void) { return "nfact_b200 0.1 (sm_100a)"; }
+
+int nfb_create(int device, void* stream, nfb_handle** out) {
+    NFB_CHECK(out != nullptr, "out is NULL");
+    NFB_CUDA(cudaSetDevice(device));
+    int major = 0;
+    NFB_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    NFB_CHECK(major == 10, "nfact_b200 needs a Blackwell (sm_100a) GPU; found compute capability major " +
+                               std::to_string(major));
+    std::unique_ptr<nfb_handle> h(new nfb_handle());
+    h->device = device;
+    if (stream != nullptr) {
+        h->stream = static_cast<cudaStream_t>(stream);
+    } else {
+        NFB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        h->own_stream = true;
+    }
+    h->cta_group = gemm_default_cta_group();
+    NFB_TRY(h->d_scal.alloc(16, true, h->stream));
+    NFB_TRY(h->d_bits.alloc(16, true, h->stream));
+    NFB_TRY(h->d_int.alloc(16, true, h->stream));
+    NFB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h->h_scal), 16 * sizeof(double)));
+    NFB_CUDA(cudaStreamSynchronize(h->stream));
+    *out = h.release();
+    return 0;
+}
+
+int nfb_destroy(nfb_handle* h) {
+    if (h == nullptr) return 0;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    if (h->own_comm && h->comm && h->nccl_lib) {
+        typedef int (*DestroyFn)(void*);
+        DestroyFn fn = reinterpret_cast<DestroyFn>(dlsym(h->nccl_lib, "ncclCommDestroy"));
+        if (fn) fn(h->comm);
+    }
+    if (h->h_scal) cudaFreeHost(h->h_scal);
+    if (h->own_stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return 0;
+}
+
+int nfb_synchronize(nfb_handle* h) {
+    NFB_CHECK(h != nullptr, "handle is NULL");
+    NFB_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int64_t nfb_launch_count(const nfb_handle* h) { return h ? h->launches_last : 0; }
+
+int nfb_set_comm(nfb_handle* h, void* nccl_comm, void* nccl_allreduce_fn, int rank, int world_size) {
+    NFB_CHECK(h != nullptr, "handle is NULL");
+    h->comm = nccl_comm;
+    h->allreduce = reinterpret_cast<NcclAllReduceFn>(nccl_allreduce_fn);
+    h->rank = rank;
+    h->world = world_size;
+    return 0;
+}
+
+struct NcclUniqueIdBlob { char internal[128]; };
+
+int nfb_nccl_unique_id(const char* libnccl_path, void* id_out) {
+    void* lib = dlopen(libnccl_path, RTLD_NOW | RTLD_GLOBAL);
+    NFB_CHECK(lib != nullptr, std::string("dlopen failed for ") + libnccl_path + ": " + dlerror());
+    typedef int (*GetIdFn)(NcclUniqueIdBlob*);
+    GetIdFn fn = reinterpret_cast<GetIdFn>(dlsym(lib, "ncclGetUniqueId"));
+    NFB_CHECK(fn != nullptr, "ncclGetUniqueId not found");
+    int rc = fn(static_cast<NcclUniqueIdBlob*>(id_out));
+    NFB_CHECK(rc == 0, "ncclGetUniqueId failed with code " + std::to_string(rc));
+    return 0;
+}
+
+int nfb_nccl_init_rank(nfb_handle* h, const char* libnccl_path, const void* id, int rank, int world_size) {
+    NFB_CHECK(h != nullptr, "handle is NULL");
+    NFB_CUDA(cudaSetDevice(h->device));
+    void* lib = dlopen(libnccl_path, RTLD_NOW | RTLD_GLOBAL);
+    NFB_CHECK(lib != nullptr, std::string("dlopen failed for ") + libnccl_path + ": " + dlerror());
+    typedef int (*InitFn)(void**, int, NcclUniqueIdBlob, int);
+    InitFn init = reinterpret_cast<InitFn>(dlsym(lib, "ncclCommInitRank"));
+    void* ar = dlsym(lib, "ncclAllReduce");
+    NFB_CHECK(init != nullptr && ar != nullptr, "NCCL symbols not found");
+    NcclUniqueIdBlob blob;
+    memcpy(&blob, id, sizeof(blob));
+    void* comm = nullptr;
+    int rc = init(&comm, world_size, blob, rank);
+    NFB_CHECK(rc == 0, "ncclCommInitRank failed with code " + std::to_string(rc));
+    h->nccl_lib = lib;
+    h->own_comm = true;
+    return nfb_set_comm(h, comm, ar, rank, world_size);
+}
+
+// ---- resident matrix ---------------------------------------------------------------------------
+int nfb_matrix_from_device(nfb_handle* h, const float* x_dev, int64_t m, int64_t n, int64_t ld, nfb_matrix** out) {
+    NFB_CHECK(h != nullptr && out != nullptr, "NULL argument");
+    NFB_CHECK(m > 0 && n > 0 && ld >= n, "bad matrix shape");
+    NFB_CUDA(cudaSetDevice(h->device));
+    std::unique_ptr<nfb_matrix> x(new nfb_matrix());
+    x->h = h;
+    x->m = m;
+    x->n = n;
+    x->ldp = round_up64(n, 8);
+    NFB_TRY(x->hi.alloc(m * x->ldp, false, h->stream));
+    NFB_TRY(x->lo.alloc(m * x->ldp, false, h->stream));
+    NFB_TRY(x->inv_scale.alloc(1, true, h->stream));
+    NFB_CUDA(cudaMemsetAsync(h->d_bits.p, 0, sizeof(unsigned int), h->stream));
+    NFB_CUDA(cudaMemsetAsync(h->d_scal.p + 4, 0, sizeof(double), h->stream));
+    NFB_TRY(absmax_f32(x_dev, m, n, ld, h->d_bits.p, h->stream));
+    NFB_TRY(split_matrix(x_dev, m, n, ld, h->d_bits.p, x->hi.p, x->lo.p, x->ldp, x->inv_scale.p, h->d_scal.p + 4,
+                         h->stream));
+    NFB_CUDA(cudaMemcpyAsync(h->h_scal + 4, h->d_scal.p + 4, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    NFB_CUDA(cudaMemcpyAsync(&x->inv_scale_host, x->inv_scale.p, sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    NFB_CUDA(cudaStreamSynchronize(h->stream));
+    x->sumsq = h->h_scal[4];
+    *out = x.release();
+    return 0;
+}
+
+int nfb_matrix_from_host(nfb_handle* h, const float* x_host, int64_t m, int64_t n, nfb_matrix** out) {
+    NFB_CHECK(h != nullptr && x_host != nullptr && out != nullptr, "NULL argument");
+    NFB_CHECK(m > 0 && n > 0, "bad matrix shape");
+    NFB_CUDA(cudaSetDevice(h->device));
+    // Two passes over row chunks so that only the planes (4 B/element) stay resident: pass 1 finds the
+    // global scale, pass 2 splits.  Chunks are staged through one device buffer.
+    std::unique_ptr<nfb_matrix> x(new nfb_matrix());
+    x->h = h;
+    x->m = m;
+    x->n = n;
+    x->ldp = round_up64(n, 8);
+    NFB_TRY(x->hi.alloc(m * x->ldp, false, h->stream));
+    NFB_TRY(x->lo.alloc(m * x->ldp, false, h->stream));
+    NFB_TRY(x->inv_scale.alloc(1, true, h->stream));
+    const int64_t chunk_rows = std::max<int64_t>(1, std::min<int64_t>(m, (int64_t(1) << 30) / (4 * n)));
+    DevBuf<float> stage[2];
+    NFB_TRY(stage[0].alloc(chunk_rows * n, false, h->stream));
+    NFB_TRY(stage[1].alloc(chunk_rows * n, false, h->stream));
+    NFB_CUDA(cudaMemsetAsync(h->d_bits.p, 0, sizeof(unsigned int), h->stream));
+    NFB_CUDA(cudaMemsetAsync(h->d_scal.p + 4, 0, sizeof(double), h->stream));
+    int rc = 0;
+    for (int pass = 0; pass < 2 && rc == 0; ++pass) {
+        int slot = 0;
+        for (int64_t r0 = 0; r0 < m && rc == 0; r0 += chunk_rows, slot ^= 1) {
+            const int64_t rows = std::min(chunk_rows, m - r0);
+            if (cudaMemcpyAsync(stage[slot].p, x_host + r0 * n, sizeof(float) * rows * n, cudaMemcpyHostToDevice,
+                                h->stream) != cudaSuccess) { set_error("H2D copy of X failed"); rc = 1; break; }
+            if (pass == 0) rc = absmax_f32(stage[slot].p, rows, n, n, h->d_bits.p, h->stream);
+            else rc = split_matrix(stage[slot].p, rows, n, n, h->d_bits.p, x->hi.p + r0 * x->ldp,
+                                   x->lo.p + r0 * x->ldp, x->ldp, x->inv_scale.p, h->d_scal.p + 4, h->stream);
+        }
+    }
+    if (rc != 0) return rc;
+    NFB_CUDA(cudaMemcpyAsync(h->h_scal + 4, h->d_scal.p + 4, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    NFB_CUDA(cudaMemcpyAsync(&x->inv_scale_host, x->inv_scale.p, sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    NFB_CUDA(cudaStreamSynchronize(h->stream));
+    x->sumsq = h->h_scal[4];
+    *out = x.release();
+    return 0;
+}
+
+int nfb_matrix_free(nfb_matrix* x) {
+    if (x == nullptr) return 0;
+    cudaSetDevice(x->h->device);
+    cudaStreamSynchronize(x->h->stream);
+    delete x;
+    return 0;
+}
+
+int nfb_matrix_shape(const nfb_matrix* x, int64_t* m, int64_t* n) {
+    NFB_CHECK(x != nullptr, "matrix is NULL");
+    if (m) *m = x->m;
+    if (n) *n = x->n;
+    return 0;
+}
+
+int nfb_matrix_sumsq(const nfb_matrix* x, double* out) {
+    NFB_CHECK(x != nullptr && out != nullptr, "NULL argument");
+    *out = x->sumsq;
+    return 0;
+}
+
+// ---- NMF -----------------------------------------------------------------------------------------
+int nfb_nmf_create(nfb_handle* h, const nfb_matrix* x, int k, const nfb_nmf_params* p, nfb_nmf** out) {
+    NFB_CHECK(h != nullptr && x != nullptr && p != nullptr && out != nullptr, "NULL argument");
+    NFB_CHECK(k >= 1 && k <= 256, "n_components must be in [1, 256] in this build");
+    NFB_CHECK(p->solver == 0 || p->solver == 1, "solver must be 0 (cd) or 1 (mu)");
+    NFB_CUDA(cudaSetDevice(h->device));
+    std::unique_ptr<nfb_nmf> s(new nfb_nmf());
+    s->h = h;
+    s->x = x;
+    s->k = k;
+    s->kp = round_up64(k, 16);
+    s->p = *p;
+    cudaStream_t st = h->stream;
+    NFB_TRY(s->wt.init(k, x->m, true, st));
+    NFB_TRY(s->hh.init(k, x->n, true, st));
+    // the Gram factors share the padded leading dimension kp so the sweep can use float4 rows
+    NFB_TRY(s->gw.init(k, k, true, st, s->kp));
+    NFB_TRY(s->gh.init(k, k, true, st, s->kp));
+    NFB_TRY(s->gd.init(k, k, false, st, s->kp));
+    const int cg = h->cta_group;
+    s->s_w = gemm_pick_splits(x->m, x->n, cg);
+    s->s_h = gemm_pick_splits(x->n, x->m, cg);
+    s->s_gw = gemm_pick_splits(k, x->m, cg);
+    s->s_gh = gemm_pick_splits(k, x->n, cg);
+    NFB_TRY(s->part_w.alloc(static_cast<size_t>(s->s_w) * k * s->wt.ld, false, st));
+    NFB_TRY(s->part_h.alloc(static_cast<size_t>(s->s_h) * k * s->hh.ld, false, st));
+    NFB_TRY(s->part_den.alloc(static_cast<size_t>(k) * std::max(s->wt.ld, s->hh.ld), false, st));
+    NFB_TRY(s->part_gram.alloc(static_cast<size_t>(std::max(s->s_gw, s->s_gh)) * k * s->kp, false, st));
+    if (h->world > 1) NFB_TRY(s->num_h.alloc(static_cast<size_t>(k) * s->hh.ld, false, st));
+    // ||X||^2 over all row shards
+    h->h_scal[5] = x->sumsq;
+    if (h->world > 1) {
+        NFB_CUDA(cudaMemcpyAsync(h->d_scal.p + 5, h->h_scal + 5, sizeof(double), cudaMemcpyHostToDevice, st));
+        NFB_TRY(allreduce_f64(h, h->d_scal.p + 5, 1));
+        NFB_CUDA(cudaMemcpyAsync(h->h_scal + 5, h->d_scal.p + 5, sizeof(double), cudaMemcpyDeviceToHost, st));
+        NFB_CUDA(cudaStreamSynchronize(st));
+    }
+    s->sumsq_global = h->h_scal[5];
+    *out = s.release();
+    return 0;
+}
+
+int nfb_nmf_free(nfb_nmf* s) {
+    if (s == nullptr) return 0;
+    cudaSetDevice(s->h->device);
+    cudaStreamSynchronize(s->h->stream);
+    delete s;
+    return 0;
+}
+
+int nfb_nmf_set_factors_dev(nfb_nmf* s, const float* w_dev, const float* h_dev) {
+    NFB_CHECK(s != nullptr && w_dev != nullptr && h_dev != nullptr, "NULL argument");
+    nfb_handle* h = s->h;
+    NFB_CUDA(cudaSetDevice(h->device));
+    NFB_TRY(transpose_f32(w_dev, s->x->m, s->k, s->k, s->wt.f.p, s->wt.ld, h->stream));
+    NFB_CUDA(cudaMemcpy2DAsync(s->hh.f.p, s->hh.ld * sizeof(float), h_dev, s->x->n * sizeof(float),
+                               s->x->n * sizeof(float), s->k, cudaMemcpyDeviceToDevice, h->stream));
+    return nmf_prepare_factors(s);
+}
+
+int nfb_nmf_set_factors_host(nfb_nmf* s, const float* w_host, const float* h_host) {
+    NFB_CHECK(s != nullptr && w_host != nullptr && h_host != nullptr, "NULL argument");
+    nfb_handle* h = s->h;
+    NFB_CUDA(cudaSetDevice(h->device));
+    DevBuf<float> tmp;
+    NFB_TRY(tmp.alloc(static_cast<size_t>(s->x->m) * s->k, false, h->stream));
+    NFB_CUDA(cudaMemcpyAsync(tmp.p, w_host, sizeof(float) * s->x->m * s->k, cudaMemcpyHostToDevice, h->stream));
+    NFB_TRY(transpose_f32(tmp.p, s->x->m, s->k, s->k, s->wt.f.p, s->wt.ld, h->stream));
+    NFB_CUDA(cudaMemcpy2DAsync(s->hh.f.p, s->hh.ld * sizeof(float), h_host, s->x->n * sizeof(float),
+                               s->x->n * sizeof(float), s->k, cudaMemcpyHostToDevice, h->stream));
+    NFB_TRY(nmf_prepare_factors(s));
+    NFB_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int nfb_nmf_get_factors_dev(nfb_nmf* s, float* w_dev, float* h_dev) {
+    NFB_CHECK(s != nullptr, "NULL argument");
+    nfb_handle* h = s->h;
+    NFB_CUDA(cudaSetDevice(h->device));
+    if (w_dev) NFB_TRY(transpose_f32(s->wt.f.p, s->k, s->x->m, s->wt.ld, w_dev, s->k, h->stream));
+    if (h_dev)
+        NFB_CUDA(cudaMemcpy2DAsync(h_dev, s->x->n * sizeof(float), s->hh.f.p, s->hh.ld * sizeof(float),
+                                   s->x->n * sizeof(float), s->k, cudaMemcpyDeviceToDevice, h->stream));
+    return 0;
+}
+
+int nfb_nmf_get_factors_host(nfb_nmf* s, float* w_host, float* h_host) {
+    NFB_CHECK(s != nullptr, "NULL argument");
+    nfb_handle* h = s->h;
+    NFB_CUDA(cudaSetDevice(h->device));
+    DevBuf<float> tmp;
+    if (w_host) {
+        NFB_TRY(tmp.alloc(static_cast<size_t>(s->x->m) * s->k, false, h->stream));
+        NFB_TRY(transpose_f32(s->wt.f.p, s->k, s->x->m, s->wt.ld, tmp.p, s->k, h->stream));
+        NFB_CUDA(cudaMemcpyAsync(w_host, tmp.p, sizeof(float) * s->x->m * s->k, cudaMemcpyDeviceToHost, h->stream));
+    }
+    if (h_host)
+        NFB_CUDA(cudaMemcpy2DAsync(h_host, s->x->n * sizeof(float), s->hh.f.p, s->hh.ld * sizeof(float),
+                                   s->x->n * sizeof(float), s->k, cudaMemcpyDeviceToHost, h->stream));
+    NFB_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int nfb_nmf_iterate(nfb_nmf* s, int n_iters, double* violation_out) {
+    NFB_CHECK(s != nullptr, "NULL argument");
+    NFB_CUDA(cudaSetDevice(s->h->device));
+    const int64_t before = g_launches.load();
+    for (int it = 0; it < n_iters; ++it) {
+        if (s->p.solver == 1) {
+            NFB_TRY(mu_iteration(s));
+            NFB_TRY(gemm_xht(s));  // numerator of the next W half-step == cross term of this iteration's error
+        } else {
+            NFB_TRY(cd_iteration(s, (it == n_iters - 1) ? violation_out : nullptr));
+        }
+    }
+    s->h->launches_last = g_launches.load() - before;
+    return 0;
+}
+
+int nfb_nmf_error(nfb_nmf* s, double* err_out) {
+    NFB_CHECK(s != nullptr && err_out != nullptr, "NULL argument");
+    NFB_CUDA(cudaSetDevice(s->h->device));
+    return nmf_error(s, err_out);
+}
+
+int nfb_nmf_run(nfb_nmf* s, int* n_iter_out, double* recon_err_out) {
+    NFB_CHECK(s != nullptr, "NULL argument");
+    NFB_CUDA(cudaSetDevice(s->h->device));
+    const nfb_nmf_params& p = s->p;
+    const int64_t before = g_launches.load();
+    int n_iter = 0;
+    if (p.solver == 1) {
+        // sklearn/decomposition/_nmf.py:823-879
+        double error_at_init = 0.0;
+        NFB_TRY(nmf_error(s, &error_at_init));
+        double previous_error = error_at_init;
+        for (n_iter = 1; n_iter <= p.max_iter; ++n_iter) {
+            NFB_TRY(mu_iteration(s));
+            NFB_TRY(gemm_xht(s));
+            if (p.tol > 0 && n_iter % 10 == 0) {
+                double error = 0.0;
+                NFB_TRY(nmf_error(s, &error));
+                if (p.verbose) printf("Epoch %02d, error: %f\n", n_iter, error);
+                if ((previous_error - error) / error_at_init < p.tol) break;
+                previous_error = error;
+            }
+        }
+        if (n_iter > p.max_iter) n_iter = p.max_iter;
+    } else {
+        // sklearn/decomposition/_nmf.py:489-516
+        double violation_init = 0.0;
+        for (n_iter = 1; n_iter <= p.max_iter; ++n_iter) {
+            double violation = 0.0;
+            NFB_TRY(cd_iteration(s, &violation));
+            s->last_violation = violation;
+            if (n_iter == 1) violation_init = violation;
+            if (violation_init == 0) break;
+            if (p.verbose) printf("violation: %g\n", violation / violation_init);
+            if (violation / violation_init <= p.tol) break;
+        }
+        if (n_iter > p.max_iter) n_iter = p.max_iter;
+    }
+    if (n_iter_out) *n_iter_out = n_iter;
+    if (recon_err_out) NFB_TRY(nmf_error(s, recon_err_out));
+    s->h->launches_last = g_launches.load() - before;
+    return 0;
+}
+
+int nfb_nmf_fit_host(nfb_handle* h, const nfb_matrix* x, int k, const nfb_nmf_params* p, float* w_host,
+                     float* h_host, int* n_iter_out, double* recon_err_out) {
+    nfb_nmf* s = nullptr;
+    NFB_TRY(nfb_nmf_create(h, x, k, p, &s));
+    int rc = nfb_nmf_set_factors_host(s, w_host, h_host);
+    if (rc == 0) rc = nfb_nmf_run(s, n_iter_out, recon_err_out);
+    if (rc == 0) rc = nfb_nmf_get_factors_host(s, w_host, h_host);
+    nfb_nmf_free(s);
+    return rc;
+}
+
+// ---- dual regression -------------------------------------------------------------------------------
+int nfb_dual_regression_host(nfb_handle* h, const nfb_matrix* x, int k, const double* g_host, double* gs_out,
+                             double* hs_out, int* n_unconverged_out) {
+    NFB_CHECK(h != nullptr && x != nullptr && g_host != nullptr, "NULL argument");
+    NFB_CHECK(k >= 1 && k <= 256, "n_components must be in [1, 256] in this build");
+    NFB_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    const int64_t m = x->m, n = x->n, kp = round_up64(k, 16);
+    const int cg = h->cta_group;
+    Factor gt, hs;
+    NFB_TRY(gt.init(k, m, true, st));
+    NFB_TRY(hs.init(k, n, true, st));
+    DevBuf<double> g64, gram64, sol_h, sol_g;
+    NFB_TRY(g64.alloc(static_cast<size_t>(m) * k, false, st));
+    NFB_TRY(gram64.alloc(static_cast<size_t>(k) * k, false, st));
+    NFB_TRY(sol_h.alloc(static_cast<size_t>(k) * hs.ld, true, st));
+    NFB_TRY(sol_g.alloc(static_cast<size_t>(k) * gt.ld, true, st));
+    const int s1 = gemm_pick_splits(n, m, cg), s2 = gemm_pick_splits(m, n, cg);
+    DevBuf<float> part;
+    NFB_TRY(part.alloc(std::max(static_cast<size_t>(s1) * k * hs.ld, static_cast<size_t>(s2) * k * gt.ld), false, st));
+    NFB_CUDA(cudaMemsetAsync(h->d_int.p, 0, 2 * sizeof(int), st));
+    // group grey components: float64 [m, k] -> component-major float32 master + planes
+    NFB_CUDA(cudaMemcpyAsync(g64.p, g_host, sizeof(double) * m * k, cudaMemcpyHostToDevice, st));
+    NFB_TRY(transpose_f64_to_f32(g64.p, m, k, k, gt.f.p, gt.ld, st));
+    NFB_TRY(refresh_planes(gt, gt.f.p, nullptr, true, st));
+    // ---- stage 1: white matter.  Hs[:, j] = nnls(G, X[:, j])  (dual_regression_methods.py:137-149)
+    NFB_TRY(gram_f64(gt.f.p, k, m, gt.ld, gram64.p, st));
+    NFB_TRY(gemm_split(x->operand(), true, gt.operand(), n, m, static_cast<int>(kp), k, part.p, hs.ld, s1,
+                       gt.inv_scale.p, nullptr, x->inv_scale_host, cg, st));
+    NFB_TRY(nnls_gram_batched(gram64.p, k, part.p, s1, static_cast<int64_t>(k) * hs.ld, hs.ld, n, sol_h.p, hs.ld,
+                              400, h->d_int.p, st));
+    // ---- stage 2: grey matter.  Gs[i, :] = nnls(Hs, X[i, :])    (dual_regression_methods.py:151-163)
+    NFB_CUDA(cudaMemsetAsync(hs.rowmax.p, 0, sizeof(unsigned int) * kp, st));
+    NFB_TRY(f64_to_f32_rowmax(sol_h.p, k, n, hs.ld, hs.f.p, hs.ld, hs.rowmax.p, st));
+    NFB_TRY(refresh_planes(hs, hs.f.p, nullptr, false, st));
+    NFB_TRY(gram_f64(hs.f.p, k, n, hs.ld, gram64.p, st));
+    NFB_TRY(gemm_split(x->operand(), false, hs.operand(), m, n, static_cast<int>(kp), k, part.p, gt.ld, s2,
+                       hs.inv_scale.p, nullptr, x->inv_scale_host, cg, st));
+    NFB_TRY(nnls_gram_batched(gram64.p, k, part.p, s2, static_cast<int64_t>(k) * gt.ld, gt.ld, m, sol_g.p, gt.ld,
+                              400, h->d_int.p + 1, st));
+    // ---- results -------------------------------------------------------------------------------------
+    if (hs_out)
+        NFB_CUDA(cudaMemcpy2DAsync(hs_out, n * sizeof(double), sol_h.p, hs.ld * sizeof(double), n * sizeof(double), k,
+                                   cudaMemcpyDeviceToHost, st));
+    std::vector<double> gs_t;
+    if (gs_out) {
+        gs_t.resize(static_cast<size_t>(k) * m);
+        NFB_CUDA(cudaMemcpy2DAsync(gs_t.data(), m * sizeof(double), sol_g.p, gt.ld * sizeof(double),
+                                   m * sizeof(double), k, cudaMemcpyDeviceToHost, st));
+    }
+    int status[2] = {0, 0};
+    NFB_CUDA(cudaMemcpyAsync(status, h->d_int.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    NFB_CUDA(cudaStreamSynchronize(st));
+    if (gs_out)
+        for (int64_t i = 0; i < m; ++i)
+            for (int t = 0; t < k; ++t) gs_out[i * k + t] = gs_t[static_cast<size_t>(t) * m + i];
+    if (n_unconverged_out) *n_unconverged_out = status[0] + status[1];
+    return 0;
+}
+
+// ---- ingest ----------------------------------------------------------------------------------------
+int nfb_ingest_coo(nfb_handle* h, int n_subjects, const int32_t* const* rows_host, const int32_t* const* cols_host,
+                   const double* const* vals_host, const int64_t* nnz, const double* scale, int64_t nrows,
+                   int64_t ncols, int group_mode, float* x_out_host, float* x_out_dev) {
+    NFB_CHECK(h != nullptr && n_subjects >= 1 && nrows > 0 && ncols > 0, "bad ingest arguments");
+    NFB_CHECK(group_mode || n_subjects == 1, "single-subject mode takes exactly one subject");
+    NFB_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    int64_t max_nnz = 0;
+    for (int s = 0; s < n_subjects; ++s) max_nnz = std::max(max_nnz, nnz[s]);
+    size_t free_b = 0, total_b = 0;
+    NFB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    const double budget = 0.6 * static_cast<double>(free_b) - 16.0 * static_cast<double>(max_nnz);
+    const double per_row = 20.0 * static_cast<double>(ncols);  // tmp + acc (fp64) + fp32 block
+    NFB_CHECK(budget > per_row, "not enough device memory for ingest");
+    const int64_t blk_rows = std::max<int64_t>(1, std::min<int64_t>(nrows, static_cast<int64_t>(budget / per_row)));
+    DevBuf<double> tmp, acc, vals;
+    DevBuf<int> rows, cols;
+    DevBuf<float> xblk;
+    NFB_TRY(tmp.alloc(static_cast<size_t>(blk_rows) * ncols, true, st));
+    NFB_TRY(acc.alloc(static_cast<size_t>(blk_rows) * ncols, false, st));
+    if (x_out_dev == nullptr) NFB_TRY(xblk.alloc(static_cast<size_t>(blk_rows) * ncols, false, st));
+    NFB_TRY(rows.alloc(max_nnz, false, st));
+    NFB_TRY(cols.alloc(max_nnz, false, st));
+    NFB_TRY(vals.alloc(max_nnz, false, st));
+    NFB_CUDA(cudaMemsetAsync(h->d_int.p + 2, 0, sizeof(int), st));
+    const double recip = 1.0 / static_cast<double>(n_subjects);
+    for (int64_t r0 = 0; r0 < nrows; r0 += blk_rows) {
+        const int64_t nr = std::min(blk_rows, nrows - r0);
+        NFB_CUDA(cudaMemsetAsync(acc.p, 0, sizeof(double) * nr * ncols, st));
+        for (int s = 0; s < n_subjects; ++s) {
+            NFB_CUDA(cudaMemcpyAsync(rows.p, rows_host[s], sizeof(int) * nnz[s], cudaMemcpyHostToDevice, st));
+            NFB_CUDA(cudaMemcpyAsync(cols.p, cols_host[s], sizeof(int) * nnz[s], cudaMemcpyHostToDevice, st));
+            NFB_CUDA(cudaMemcpyAsync(vals.p, vals_host[s], sizeof(double) * nnz[s], cudaMemcpyHostToDevice, st));
+            NFB_TRY(ingest_scatter(rows.p, cols.p, vals.p, nnz[s], r0, nr, nrows, ncols, scale[s], tmp.p, acc.p,
+                                   h->d_int.p + 2, st));
+            // the staging buffers are reused by the next subject: pageable H2D copies are synchronous
+            // with respect to the host, the kernels are ordered on the stream.
+        }
+        float* dst = x_out_dev ? x_out_dev + r0 * ncols : xblk.p;
+        NFB_TRY(ingest_finalize(acc.p, nr * ncols, recip, group_mode ? 1 : 0, dst, st));
+        if (x_out_host)
+            NFB_CUDA(cudaMemcpyAsync(x_out_host + r0 * ncols, dst, sizeof(float) * nr * ncols, cudaMemcpyDeviceToHost,
+                                     st));
+    }
+    int oob = 0;
+    NFB_CUDA(cudaMemcpyAsync(&oob, h->d_int.p + 2, sizeof(int), cudaMemcpyDeviceToHost, st));
+    NFB_CUDA(cudaStreamSynchronize(st));
+    NFB_CHECK(oob == 0, "row/column index exceeds matrix dimensions");
+    return 0;
+}
+
+int nfb_matrix_matmul(nfb_handle* h, const nfb_matrix* x, int trans, const float* b_dev, int64_t n_b,
+                      float* out_dev, int64_t ld_out) {
+    NFB_CHECK(h != nullptr && x != nullptr && b_dev != nullptr && out_dev != nullptr, "NULL argument");
+    NFB_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    const int64_t m_total = trans ? x->n : x->m;
+    const int64_t k_total = trans ? x->m : x->n;
+    NFB_CHECK(ld_out >= m_total, "ld_out too small");
+    const int cg = h->cta_group;
+    const int splits = gemm_pick_splits(m_total, k_total, cg);
+    for (int64_t t0 = 0; t0 < n_b; t0 += 256) {
+        const int64_t nb = std::min<int64_t>(256, n_b - t0);
+        Factor b;
+        NFB_TRY(b.init(nb, k_total, true, st));
+        NFB_CUDA(cudaMemcpy2DAsync(b.f.p, b.ld * sizeof(float), b_dev + t0 * k_total, k_total * sizeof(float),
+                                   k_total * sizeof(float), nb, cudaMemcpyDeviceToDevice, st));
+        NFB_TRY(refresh_planes(b, b.f.p, nullptr, true, st));
+        DevBuf<float> part;
+        NFB_TRY(part.alloc(static_cast<size_t>(splits) * nb * ld_out, false, st));
+        NFB_TRY(gemm_split(x->operand(), trans != 0, b.operand(), m_total, k_total, static_cast<int>(b.kp),
+                           static_cast<int>(nb), part.p, ld_out, splits, b.inv_scale.p, nullptr, x->inv_scale_host,
+                           cg, st));
+        NFB_TRY(reduce_partials(part.p, splits, nb * ld_out, nb, m_total, ld_out, 0.0f, out_dev + t0 * ld_out,
+                                ld_out, st));
+        NFB_CUDA(cudaStreamSynchronize(st));  // temporaries are freed at scope exit
+    }
+    return 0;
+}
+
+// ---- test hook --------------------------------------------------------------------------------------
+int nfb_test_gemm(nfb_handle* h, const float* a_dev, int64_t a_rows, int64_t a_cols, int a_is_transposed,
+                  const float* b_dev, int64_t n_b, float* out_dev, int64_t ld_out, int cta_group, int splits) {
+    NFB_CHECK(h != nullptr, "handle is NULL");
+    NFB_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    const int64_t m_total = a_is_transposed ? a_cols : a_rows;
+    const int64_t k_total = a_is_transposed ? a_rows : a_cols;
+    nfb_matrix* a = nullptr;
+    NFB_TRY(nfb_matrix_from_device(h, a_dev, a_rows, a_cols, a_cols, &a));
+    std::unique_ptr<nfb_matrix> a_guard(a);
+    Factor b;
+    NFB_TRY(b.init(n_b, k_total, false, st));
+    // b_dev is [n_b, k_total] with ld = k_total; Factor planes use ld rounded up to 8
+    DevBuf<float> bpad;
+    NFB_TRY(bpad.alloc(static_cast<size_t>(b.kp) * b.ld, true, st));
+    NFB_CUDA(cudaMemcpy2DAsync(bpad.p, b.ld * sizeof(float), b_dev, k_total * sizeof(float), k_total * sizeof(float),
+                               n_b, cudaMemcpyDeviceToDevice, st));
+    NFB_TRY(refresh_planes(b, bpad.p, nullptr, true, st));
+    if (cta_group == 0) cta_group = h->cta_group;
+    if (splits <= 0) splits = gemm_pick_splits(m_total, k_total, cta_group);
+    DevBuf<float> part;
+    NFB_TRY(part.alloc(static_cast<size_t>(splits) * n_b * ld_out, false, st));
+    NFB_TRY(gemm_split(a->operand(), a_is_transposed != 0, b.operand(), m_total, k_total, static_cast<int>(b.kp),
+                       static_cast<int>(n_b), part.p, ld_out, splits, b.inv_scale.p, nullptr, a->inv_scale_host,
+                       cta_group, st));
+    NFB_TRY(reduce_partials(part.p, splits, n_b * ld_out, n_b, m_total, ld_out, 0.0f, out_dev, ld_out, st));
+    NFB_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,314 @@
+// Factor-update kernels of the NMF loop.  Both factors are kept component-major on the device
+// (W^T [k, m] and H [k, n], fp32) so the W and H half-steps run the same code -- the same symmetry
+// sklearn uses when it calls _update_coordinate_descent(X, W, Ht) and then (X.T, Ht, W)
+// (sklearn/decomposition/_nmf.py:492-501).
+#include <algorithm>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace nfb {
+namespace {
+
+constexpr float kEpsF32 = 1.1920928955078125e-07f;  // np.finfo(np.float32).eps, sklearn _nmf.py:32
+
+__global__ void reduce_partials_kernel(const float* __restrict__ part, int splits, int64_t split_stride, int64_t cols,
+                                       int64_t ld, float bias, float* __restrict__ out, int64_t ld_out) {
+    const int64_t t = blockIdx.y;
+    for (int64_t j = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; j < cols;
+         j += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        float acc = 0.0f;
+        for (int s = 0; s < splits; ++s) acc += part[s * split_stride + t * ld + j];
+        out[t * ld_out + j] = acc + bias;
+    }
+}
+
+// sklearn/decomposition/_nmf.py:521-626 and :629-723 (beta_loss == 2, gamma == 1), one element per lane.
+__global__ void mu_update_kernel(float* __restrict__ f, int64_t cols, int64_t ld, const float* __restrict__ num,
+                                 int num_splits, int64_t num_stride, const float* __restrict__ den, int den_splits,
+                                 int64_t den_stride, int64_t ld_part, float l1, float l2,
+                                 unsigned int* __restrict__ rowmax_bits) {
+    const int64_t t = blockIdx.y;
+    float vmax = 0.0f;
+    for (int64_t j = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; j < cols;
+         j += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        float numerator = 0.0f;
+        for (int s = 0; s < num_splits; ++s) numerator += num[s * num_stride + t * ld_part + j];
+        float denominator = 0.0f;
+        for (int s = 0; s < den_splits; ++s) denominator += den[s * den_stride + t * ld_part + j];
+        const float old = f[t * ld + j];
+        if (l1 > 0.0f) denominator = __fadd_rn(denominator, l1);
+        if (l2 > 0.0f) denominator = __fadd_rn(denominator, __fmul_rn(l2, old));
+        if (denominator == 0.0f) denominator = kEpsF32;
+        const float ratio = __fdiv_rn(numerator, denominator);
+        const float updated = __fmul_rn(old, ratio);
+        f[t * ld + j] = updated;
+        vmax = fmaxf(vmax, fabsf(updated));
+    }
+    vmax = warp_max(vmax);
+    if ((threadIdx.x & 31) == 0 && vmax > 0.0f) atomicMax(&rowmax_bits[t], __float_as_uint(vmax));
+}
+
+// sklearn/decomposition/_cdnmf_fast.pyx:8-38 with the roles transposed: thread j owns column j of
+// F [k, cols] (= row j of sklearn's W) and walks the components t = 0..k-1 in order, so the
+// Gauss-Seidel dependence across components is kept exactly; columns are independent.
+//   grad = -num[t][j] + sum_r G[t][r] F[r][j]          (G carries l2 on its diagonal, num carries -l1)
+//   pg   = F[t][j] == 0 ? min(0, grad) : grad ;  violation += |pg|
+//   F[t][j] = max(F[t][j] - grad / G[t][t], 0)   if G[t][t] != 0
+template <int kTJ>
+__global__ void __launch_bounds__(kTJ)
+cd_sweep_kernel(float* __restrict__ f, int k, int64_t cols, int64_t ld, const float* __restrict__ num,
+                int num_splits, int64_t num_stride, int64_t ld_part, const float* __restrict__ gram, int ldg,
+                float l1, float l2, double* __restrict__ violation, unsigned int* __restrict__ rowmax_bits) {
+    extern __shared__ float fs[];  // [k][kTJ]
+    __shared__ double scratch[32];
+    const int tid = threadIdx.x;
+    const int64_t j = blockIdx.x * static_cast<int64_t>(kTJ) + tid;
+    const bool active = j < cols;
+    for (int r = 0; r < k; ++r) fs[r * kTJ + tid] = active ? f[r * ld + j] : 0.0f;
+    float viol = 0.0f;
+    const int k4 = k & ~3;
+    for (int t = 0; t < k; ++t) {
+        const float* grow = gram + static_cast<int64_t>(t) * ldg;
+        float g0 = 0.0f, g1 = 0.0f, g2 = 0.0f, g3 = 0.0f;
+        for (int r = 0; r < k4; r += 4) {
+            const float4 gv = __ldg(reinterpret_cast<const float4*>(grow + r));
+            g0 = fmaf(gv.x, fs[(r + 0) * kTJ + tid], g0);
+            g1 = fmaf(gv.y, fs[(r + 1) * kTJ + tid], g1);
+            g2 = fmaf(gv.z, fs[(r + 2) * kTJ + tid], g2);
+            g3 = fmaf(gv.w, fs[(r + 3) * kTJ + tid], g3);
+        }
+        for (int r = k4; r < k; ++r) g0 = fmaf(__ldg(grow + r), fs[r * kTJ + tid], g0);
+        const float cur = fs[t * kTJ + tid];
+        float numer = 0.0f;
+        if (active)
+            for (int s = 0; s < num_splits; ++s) numer += num[s * num_stride + t * ld_part + j];
+        numer -= l1;
+        const float hess = __ldg(grow + t) + l2;
+        float grad = (g0 + g1) + (g2 + g3);
+        grad = fmaf(l2, cur, grad) - numer;
+        const float pg = (cur == 0.0f) ? fminf(0.0f, grad) : grad;
+        viol += fabsf(pg);
+        if (hess != 0.0f) fs[t * kTJ + tid] = fmaxf(cur - grad / hess, 0.0f);
+    }
+    for (int t = 0; t < k; ++t) {
+        const float v = active ? fs[t * kTJ + tid] : 0.0f;
+        if (active) f[t * ld + j] = v;
+        const float m = warp_max(v);
+        if ((tid & 31) == 0 && m > 0.0f) atomicMax(&rowmax_bits[t], __float_as_uint(m));
+    }
+    const double total = block_sum(active ? static_cast<double>(viol) : 0.0, scratch);
+    if (tid == 0 && total != 0.0) atomicAdd(violation, total);
+}
+
+__global__ void dot_partials_kernel(const float* __restrict__ a, int64_t lda, const float* __restrict__ b, int splits,
+                                    int64_t b_stride, int64_t ldb, int64_t cols, double* __restrict__ out) {
+    __shared__ double scratch[32];
+    const int64_t t = blockIdx.y;
+    double acc = 0.0;
+    for (int64_t j = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; j < cols;
+         j += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        float bsum = 0.0f;
+        for (int s = 0; s < splits; ++s) bsum += b[s * b_stride + t * ldb + j];
+        acc += static_cast<double>(a[t * lda + j]) * static_cast<double>(bsum);
+    }
+    const double total = block_sum(acc, scratch);
+    if (threadIdx.x == 0 && total != 0.0) atomicAdd(out, total);
+}
+
+__global__ void dot_small_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t k, int64_t ld,
+                                 double* __restrict__ out) {
+    __shared__ double scratch[32];
+    double acc = 0.0;
+    for (int64_t i = threadIdx.x; i < k * k; i += blockDim.x) {
+        const int64_t t = i / k, u = i - t * k;
+        acc += static_cast<double>(a[t * ld + u]) * static_cast<double>(b[t * ld + u]);
+    }
+    const double total = block_sum(acc, scratch);
+    if (threadIdx.x == 0) atomicAdd(out, total);
+}
+
+template <typename Tin>
+__global__ void transpose_kernel(const Tin* __restrict__ in, int64_t rows, int64_t cols, int64_t ld_in,
+                                 float* __restrict__ out, int64_t ld_out) {
+    __shared__ float tile[32][33];
+    const int64_t c0 = static_cast<int64_t>(blockIdx.x) * 32, r0 = static_cast<int64_t>(blockIdx.y) * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int64_t r = r0 + i, c = c0 + threadIdx.x;
+        tile[i][threadIdx.x] = (r < rows && c < cols) ? static_cast<float>(in[r * ld_in + c]) : 0.0f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int64_t c = c0 + i, r = r0 + threadIdx.x;
+        if (c < cols && r < rows) out[c * ld_out + r] = tile[threadIdx.x][i];
+    }
+}
+
+__global__ void reduce_partials_f64_kernel(const float* __restrict__ part, int splits, int64_t split_stride,
+                                           int64_t cols, int64_t ld, double* __restrict__ out, int64_t ld_out) {
+    const int64_t t = blockIdx.y;
+    for (int64_t j = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; j < cols;
+         j += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        double acc = 0.0;
+        for (int s = 0; s < splits; ++s) acc += static_cast<double>(part[s * split_stride + t * ld + j]);
+        out[t * ld_out + j] = acc;
+    }
+}
+
+// 4 x 4 block of the Gram matrix per CTA column slice, float64 products of the fp32 factor.
+__global__ void gram_f64_kernel(const float* __restrict__ f, int k, int64_t cols, int64_t ld,
+                                double* __restrict__ gram64) {
+    __shared__ double scratch[32];
+    const int t0 = blockIdx.x * 4, u0 = blockIdx.y * 4;
+    if (u0 > t0) return;  // lower triangle only, mirrored below
+    double acc[4][4] = {};
+    const int64_t j_begin = static_cast<int64_t>(blockIdx.z) * blockDim.x + threadIdx.x;
+    const int64_t j_step = static_cast<int64_t>(gridDim.z) * blockDim.x;
+    for (int64_t j = j_begin; j < cols; j += j_step) {
+        double a[4], b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            a[i] = (t0 + i < k) ? static_cast<double>(f[(t0 + i) * ld + j]) : 0.0;
+            b[i] = (u0 + i < k) ? static_cast<double>(f[(u0 + i) * ld + j]) : 0.0;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int l = 0; l < 4; ++l) acc[i][l] = fma(a[i], b[l], acc[i][l]);
+    }
+    for (int i = 0; i < 4; ++i)
+        for (int l = 0; l < 4; ++l) {
+            const double total = block_sum(acc[i][l], scratch);
+            if (threadIdx.x == 0 && t0 + i < k && u0 + l < k) {
+                atomicAdd(&gram64[(t0 + i) * k + (u0 + l)], total);
+                if (u0 != t0) atomicAdd(&gram64[(u0 + l) * k + (t0 + i)], total);
+            }
+        }
+}
+
+__global__ void f64_to_f32_rowmax_kernel(const double* __restrict__ in, int64_t cols, int64_t ld_in,
+                                         float* __restrict__ out, int64_t ld_out,
+                                         unsigned int* __restrict__ rowmax_bits) {
+    const int64_t t = blockIdx.y;
+    float vmax = 0.0f;
+    for (int64_t j = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; j < cols;
+         j += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const float v = __double2float_rn(in[t * ld_in + j]);
+        out[t * ld_out + j] = v;
+        vmax = fmaxf(vmax, fabsf(v));
+    }
+    vmax = warp_max(vmax);
+    if ((threadIdx.x & 31) == 0 && vmax > 0.0f) atomicMax(&rowmax_bits[t], __float_as_uint(vmax));
+}
+
+int col_blocks(int64_t cols, int per_block, int cap) {
+    return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(ceil_div64(cols, per_block), cap)));
+}
+
+}  // namespace
+
+int reduce_partials(const float* part, int splits, int64_t split_stride, int64_t k, int64_t cols, int64_t ld,
+                    float bias, float* out, int64_t ld_out, cudaStream_t stream) {
+    if (k * cols == 0) return 0;
+    reduce_partials_kernel<<<dim3(col_blocks(cols, 256, 1024), static_cast<unsigned>(k)), 256, 0, stream>>>(
+        part, splits, split_stride, cols, ld, bias, out, ld_out);
+    NFB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int mu_update(float* f, int64_t k, int64_t cols, int64_t ld, const float* num, int num_splits, int64_t num_stride,
+              const float* den, int den_splits, int64_t den_stride, int64_t ld_part, float l1, float l2,
+              unsigned int* rowmax_bits, cudaStream_t stream) {
+    if (k * cols == 0) return 0;
+    mu_update_kernel<<<dim3(col_blocks(cols, 256, 1024), static_cast<unsigned>(k)), 256, 0, stream>>>(
+        f, cols, ld, num, num_splits, num_stride, den, den_splits, den_stride, ld_part, l1, l2, rowmax_bits);
+    NFB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int cd_sweep(float* f, int64_t k, int64_t cols, int64_t ld, const float* num, int num_splits, int64_t num_stride,
+             int64_t ld_part, const float* gram, float l1, float l2, double* violation, unsigned int* rowmax_bits,
+             cudaStream_t stream) {
+    if (k * cols == 0) return 0;
+    const int ldg = static_cast<int>(round_up64(k, 16));
+    auto run = [&](auto tj_tag) -> int {
+        constexpr int TJ = decltype(tj_tag)::value;
+        const size_t smem = static_cast<size_t>(k) * TJ * sizeof(float);
+        auto kernel = cd_sweep_kernel<TJ>;
+        NFB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        kernel<<<static_cast<unsigned>(ceil_div64(cols, TJ)), TJ, smem, stream>>>(
+            f, static_cast<int>(k), cols, ld, num, num_splits, num_stride, ld_part, gram, ldg, l1, l2, violation,
+            rowmax_bits);
+        NFB_CUDA(cudaGetLastError());
+        return 0;
+    };
+    if (k * 128 * 4 <= 110 * 1024) return run(std::integral_constant<int, 128>{});
+    if (k * 64 * 4 <= 220 * 1024) return run(std::integral_constant<int, 64>{});
+    NFB_CHECK(k * 32 * 4 <= 220 * 1024, "n_components too large for the coordinate-descent kernel");
+    return run(std::integral_constant<int, 32>{});
+}
+
+int dot_partials(const float* a, int64_t lda, const float* b, int splits, int64_t b_stride, int64_t ldb, int64_t k,
+                 int64_t cols, double* out, cudaStream_t stream) {
+    if (k * cols == 0) return 0;
+    dot_partials_kernel<<<dim3(col_blocks(cols, 256, 256), static_cast<unsigned>(k)), 256, 0, stream>>>(
+        a, lda, b, splits, b_stride, ldb, cols, out);
+    NFB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int reduce_partials_f64(const float* part, int splits, int64_t split_stride, int64_t k, int64_t cols, int64_t ld,
+                        double* out, int64_t ld_out, cudaStream_t stream) {
+    if (k * cols == 0) return 0;
+    reduce_partials_f64_kernel<<<dim3(col_blocks(cols, 256, 1024), static_cast<unsigned>(k)), 256, 0, stream>>>(
+        part, splits, split_stride, cols, ld, out, ld_out);
+    NFB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int gram_f64(const float* f, int64_t k, int64_t cols, int64_t ld, double* gram64, cudaStream_t stream) {
+    if (k == 0) return 0;
+    NFB_CUDA(cudaMemsetAsync(gram64, 0, sizeof(double) * k * k, stream));
+    if (cols == 0) return 0;
+    const unsigned kb = static_cast<unsigned>(ceil_div64(k, 4));
+    const unsigned jz = static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>(ceil_div64(cols, 256 * 16), 32)));
+    gram_f64_kernel<<<dim3(kb, kb, jz), 256, 0, stream>>>(f, static_cast<int>(k), cols, ld, gram64);
+    NFB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int f64_to_f32_rowmax(const double* in, int64_t k, int64_t cols, int64_t ld_in, float* out, int64_t ld_out,
+                      unsigned int* rowmax_bits, cudaStream_t stream) {
+    if (k * cols == 0) return 0;
+    f64_to_f32_rowmax_kernel<<<dim3(col_blocks(cols, 256, 1024), static_cast<unsigned>(k)), 256, 0, stream>>>(
+        in, cols, ld_in, out, ld_out, rowmax_bits);
+    NFB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int dot_small(const float* a, const float* b, int64_t k, int64_t ld, double* out, cudaStream_t stream) {
+    if (k == 0) return 0;
+    dot_small_kernel<<<1, 1024, 0, stream>>>(a, b, k, ld, out);
+    NFB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int transpose_f32(const float* in, int64_t rows, int64_t cols, int64_t ld_in, float* out, int64_t ld_out,
+                  cudaStream_t stream) {
+    if (rows * cols == 0) return 0;
+    dim3 grid(static_cast<unsigned>(ceil_div64(cols, 32)), static_cast<unsigned>(ceil_div64(rows, 32)));
+    transpose_kernel<float><<<grid, dim3(32, 8), 0, stream>>>(in, rows, cols, ld_in, out, ld_out);
+    NFB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int transpose_f64_to_f32(const double* in, int64_t rows, int64_t cols, int64_t ld_in, float* out, int64_t ld_out,
+                         cudaStream_t stream) {
+    if (rows * cols == 0) return 0;
+    dim3 grid(static_cast<unsigned>(ceil_div64(cols, 32)), static_cast<unsigned>(ceil_div64(rows, 32)));
+    transpose_kernel<double><<<grid, dim3(32, 8), 0, stream>>>(in, rows, cols, ld_in, out, ld_out);
+    NFB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace nfb

@@ -1,0 +1,204 @@
+"""Thin object layer over the C ABI: device handle, resident connectivity matrix, NMF state.
+
+PyTorch appears only as plumbing (device tensors handed over as raw pointers, the current CUDA
+stream, torch.distributed for rendezvous); all arithmetic happens inside libnfact_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import byref, c_double, c_int, c_int64, c_void_p
+
+import numpy as np
+
+from . import _lib
+from ._lib import NmfParams, check
+
+_handles: dict = {}
+
+
+class Handle:
+    """One per (process, device): CUDA stream + scratch owned by the library."""
+
+    def __init__(self, device: int = 0):
+        self.lib = _lib.load()
+        self.device = int(device)
+        self._ptr = c_void_p()
+        check(self.lib.nfb_create(self.device, None, byref(self._ptr)))
+        self.rank, self.world = 0, 1
+
+    @property
+    def ptr(self) -> c_void_p:
+        return self._ptr
+
+    def synchronize(self) -> None:
+        check(self.lib.nfb_synchronize(self._ptr))
+
+    def launch_count(self) -> int:
+        return int(self.lib.nfb_launch_count(self._ptr))
+
+    def init_nccl(self, rank: int, world: int, broadcast_bytes) -> None:
+        """Create a NCCL communicator inside the library.  ``broadcast_bytes(b: bytes|None) -> bytes``
+        must return rank 0's 128-byte unique id on every rank (e.g. via torch.distributed)."""
+        path = find_libnccl().encode()
+        uid = ctypes.create_string_buffer(128)
+        if rank == 0:
+            check(self.lib.nfb_nccl_unique_id(path, uid))
+        payload = broadcast_bytes(bytes(uid.raw) if rank == 0 else None)
+        uid = ctypes.create_string_buffer(payload, 128)
+        check(self.lib.nfb_nccl_init_rank(self._ptr, path, uid, rank, world))
+        self.rank, self.world = rank, world
+
+    def close(self) -> None:
+        if self._ptr:
+            self.lib.nfb_destroy(self._ptr)
+            self._ptr = c_void_p()
+
+
+def find_libnccl() -> str:
+    """The NCCL that ships with torch (no system dependency)."""
+    import glob
+    import os
+    import sys
+    for base in sys.path:
+        hits = glob.glob(os.path.join(base, "nvidia", "nccl", "lib", "libnccl.so*"))
+        if hits:
+            return sorted(hits)[0]
+    return "libnccl.so.2"
+
+
+def get_handle(device: int = 0) -> Handle:
+    if device not in _handles:
+        _handles[device] = Handle(device)
+    return _handles[device]
+
+
+class DeviceMatrix:
+    """Connectivity matrix X resident in HBM as fp16 hi/lo planes (4 B/element)."""
+
+    def __init__(self, handle: Handle, ptr: c_void_p, shape):
+        self.handle, self._ptr, self.shape = handle, ptr, tuple(shape)
+
+    @classmethod
+    def from_host(cls, x: np.ndarray, handle: Handle | None = None) -> "DeviceMatrix":
+        handle = handle or get_handle()
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        if x.ndim != 2:
+            raise ValueError("expected a 2-D matrix")
+        ptr = c_void_p()
+        check(handle.lib.nfb_matrix_from_host(handle.ptr, x.ctypes.data, x.shape[0], x.shape[1], byref(ptr)))
+        return cls(handle, ptr, x.shape)
+
+    @classmethod
+    def from_device_ptr(cls, data_ptr: int, m: int, n: int, ld: int | None = None,
+                        handle: Handle | None = None) -> "DeviceMatrix":
+        handle = handle or get_handle()
+        ptr = c_void_p()
+        check(handle.lib.nfb_matrix_from_device(handle.ptr, c_void_p(data_ptr), m, n, ld or n, byref(ptr)))
+        return cls(handle, ptr, (m, n))
+
+    @property
+    def ptr(self) -> c_void_p:
+        return self._ptr
+
+    @property
+    def sumsq(self) -> float:
+        out = c_double()
+        check(self.handle.lib.nfb_matrix_sumsq(self._ptr, byref(out)))
+        return out.value
+
+    def matmul_dev(self, trans: bool, b_ptr: int, n_b: int, out_ptr: int, ld_out: int) -> None:
+        check(self.handle.lib.nfb_matrix_matmul(self.handle.ptr, self._ptr, int(trans), c_void_p(b_ptr), n_b,
+                                                c_void_p(out_ptr), ld_out))
+
+    def free(self) -> None:
+        if self._ptr:
+            self.handle.lib.nfb_matrix_free(self._ptr)
+            self._ptr = c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def make_params(solver: str, max_iter: int, tol: float, regs, verbose: int = 0) -> NmfParams:
+    if solver not in ("cd", "mu"):
+        raise ValueError(f"Invalid solver parameter '{solver}'.")
+    l1w, l1h, l2w, l2h = regs
+    return NmfParams(0 if solver == "cd" else 1, int(max_iter), float(tol), float(l1w), float(l1h), float(l2w),
+                     float(l2h), int(verbose))
+
+
+class NmfState:
+    """Stepwise NMF solver on a resident matrix (benchmarks and per-iteration parity tests)."""
+
+    def __init__(self, x: DeviceMatrix, k: int, params: NmfParams):
+        self.x, self.k, self.params = x, int(k), params
+        self.handle = x.handle
+        self._ptr = c_void_p()
+        check(self.handle.lib.nfb_nmf_create(self.handle.ptr, x.ptr, self.k, byref(params), byref(self._ptr)))
+
+    def set_factors(self, w: np.ndarray, h: np.ndarray) -> None:
+        m, n = self.x.shape
+        w = np.ascontiguousarray(w, dtype=np.float32)
+        h = np.ascontiguousarray(h, dtype=np.float32)
+        if w.shape != (m, self.k) or h.shape != (self.k, n):
+            raise ValueError(f"Array with wrong shape passed to NMF: W {w.shape}, H {h.shape}, "
+                             f"expected {(m, self.k)} and {(self.k, n)}")
+        check(self.handle.lib.nfb_nmf_set_factors_host(self._ptr, w.ctypes.data, h.ctypes.data))
+
+    def set_factors_dev(self, w_ptr: int, h_ptr: int) -> None:
+        check(self.handle.lib.nfb_nmf_set_factors_dev(self._ptr, c_void_p(w_ptr), c_void_p(h_ptr)))
+
+    def get_factors(self):
+        m, n = self.x.shape
+        w = np.empty((m, self.k), dtype=np.float32)
+        h = np.empty((self.k, n), dtype=np.float32)
+        check(self.handle.lib.nfb_nmf_get_factors_host(self._ptr, w.ctypes.data, h.ctypes.data))
+        return w, h
+
+    def iterate(self, n_iters: int = 1, want_violation: bool = False):
+        viol = c_double()
+        check(self.handle.lib.nfb_nmf_iterate(self._ptr, int(n_iters), byref(viol) if want_violation else None))
+        return viol.value if want_violation else None
+
+    def run(self):
+        n_iter, err = c_int(), c_double()
+        check(self.handle.lib.nfb_nmf_run(self._ptr, byref(n_iter), byref(err)))
+        return n_iter.value, err.value
+
+    def error(self) -> float:
+        err = c_double()
+        check(self.handle.lib.nfb_nmf_error(self._ptr, byref(err)))
+        return err.value
+
+    def free(self) -> None:
+        if self._ptr:
+            self.handle.lib.nfb_nmf_free(self._ptr)
+            self._ptr = c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def ingest_coo(subjects, nrows: int, ncols: int, group_mode: bool, handle: Handle | None = None) -> np.ndarray:
+    """subjects: list of (rows int32 0-based, cols int32 0-based, vals float64, scale float)."""
+    handle = handle or get_handle()
+    n = len(subjects)
+    rows = [np.ascontiguousarray(s[0], dtype=np.int32) for s in subjects]
+    cols = [np.ascontiguousarray(s[1], dtype=np.int32) for s in subjects]
+    vals = [np.ascontiguousarray(s[2], dtype=np.float64) for s in subjects]
+    arr_t = c_void_p * n
+    rows_p = arr_t(*[r.ctypes.data for r in rows])
+    cols_p = arr_t(*[c.ctypes.data for c in cols])
+    vals_p = arr_t(*[v.ctypes.data for v in vals])
+    nnz = (c_int64 * n)(*[len(r) for r in rows])
+    scale = (c_double * n)(*[float(s[3]) for s in subjects])
+    out = np.empty((nrows, ncols), dtype=np.float32)
+    check(handle.lib.nfb_ingest_coo(handle.ptr, n, rows_p, cols_p, vals_p, nnz, scale, nrows, ncols,
+                                    1 if group_mode else 0, out.ctypes.data, None))
+    return out

@@ -1,0 +1,137 @@
+"""Matrix ingest -- host-side mirror of the reference's loaders, arithmetic on the GPU.
+
+Same names, arguments and error behaviour as
+  NFACT/base/matrix_handling.py            read_in_matrix :93, load_single_matrix :116, load_fdt_matrix :143,
+                                           normalise_components :45, thresholding :218, save_matrix :161
+  NFACT/decomp/decomposition/matrix_handling.py   process_fdt_matrix2 :12, avg_fdt :73, load_previous_matrix :47
+The text parse stays on the host (it is I/O); duplicate summation, waytotal scaling, group averaging,
+densification and the float32 rounding run in libnfact_b200 (ingest.cu) and are bit-identical to the reference.
+"""
+from __future__ import annotations
+
+import os
+from collections import namedtuple
+
+import numpy as np
+
+from . import device
+from .utils import colours, error_and_exit, nprint
+
+CooMatrix = namedtuple("CooMatrix", "rows cols data shape scale")
+
+
+def read_in_matrix(matfile: str) -> np.ndarray:
+    """NFACT/base/matrix_handling.py:93-113.  float64 [T+1, 3]; ``.lz4`` files need the lz4 module."""
+    if matfile.endswith(".lz4"):
+        import lz4.frame  # same optional dependency as the reference
+        with lz4.frame.open(matfile, "rb") as fil:
+            raw = fil.read()
+    else:
+        with open(matfile, "rb") as fil:
+            raw = fil.read()
+    flat = np.array(raw.split(), dtype=np.float64)
+    if flat.size % 3 != 0 or flat.size < 3:
+        raise ValueError(f"{matfile}: expected 3 columns per line")
+    return flat.reshape(-1, 3)
+
+
+def load_single_matrix(matfile: str) -> CooMatrix:
+    """NFACT/base/matrix_handling.py:116-140.  Returns the COO triplets (0-based) plus the
+    ``1e8 / waytotal`` scale; the sparse-matrix arithmetic itself happens on the device."""
+    mat = read_in_matrix(matfile)
+    data = np.ascontiguousarray(mat[:-1, -1])
+    rows = np.array(mat[:-1, 0] - 1, dtype=np.int64)
+    cols = np.array(mat[:-1, 1] - 1, dtype=np.int64)
+    nrows = int(mat[-1, 0])
+    ncols = int(mat[-1, 1])
+    if rows.size and (rows.min() < 0 or cols.min() < 0):
+        raise ValueError("negative row index found" if rows.min() < 0 else "negative column index found")
+    if rows.size and rows.max() >= nrows:
+        raise ValueError("row index exceeds matrix dimensions")
+    if cols.size and cols.max() >= ncols:
+        raise ValueError("column index exceeds matrix dimensions")
+    waytotal = float(np.loadtxt(os.path.join(os.path.dirname(matfile), "waytotal")))
+    return CooMatrix(rows.astype(np.int32), cols.astype(np.int32), data, (nrows, ncols), 1e8 / waytotal)
+
+
+def load_fdt_matrix(matfile: str) -> np.ndarray:
+    """NFACT/base/matrix_handling.py:143-158: dense float32 [m, n]."""
+    coo = load_single_matrix(matfile)
+    return device.ingest_coo([(coo.rows, coo.cols, coo.data, coo.scale)], coo.shape[0], coo.shape[1], False)
+
+
+def avg_fdt(list_of_matfiles: list) -> np.ndarray:
+    """NFACT/decomp/decomposition/matrix_handling.py:73-100: group average, dense float32."""
+    if len(list_of_matfiles) == 0:
+        raise ValueError("no fdt_matrix2 files given")
+    subjects, shape = [], None
+    for matrix in list_of_matfiles:
+        coo = load_single_matrix(matrix)
+        if shape is None:
+            shape = coo.shape
+        elif coo.shape != shape:
+            raise ValueError(f"inconsistent shapes {shape} and {coo.shape}")
+        subjects.append((coo.rows, coo.cols, coo.data, coo.scale))
+    return device.ingest_coo(subjects, shape[0], shape[1], True)
+
+
+def process_fdt_matrix2(list_of_ptx_folds: list, group_mode: bool) -> np.ndarray:
+    """NFACT/decomp/decomposition/matrix_handling.py:12-44."""
+    list_of_fdt = [
+        os.path.join(sub_folder, fname)
+        for sub_folder in list_of_ptx_folds
+        for fname in ("fdt_matrix2.dot", "fdt_matrix2.dot.lz4")
+        if os.path.exists(os.path.join(sub_folder, fname))
+    ]
+    fdt_matrix2 = None
+    if group_mode:
+        try:
+            fdt_matrix2 = avg_fdt(list_of_fdt)
+        except Exception as e:
+            error_and_exit(False, f"Unable to load fdt_matrix2 due to {e}")
+    if not group_mode:
+        try:
+            fdt_matrix2 = load_fdt_matrix(list_of_fdt[0])
+        except Exception as e:
+            error_and_exit(False, f"Unable to load fdt_matrix2 due to {e}")
+    return fdt_matrix2
+
+
+def load_previous_matrix(path: str):
+    """NFACT/decomp/decomposition/matrix_handling.py:47-70."""
+    try:
+        return np.load(os.path.join(path))
+    except Exception:
+        col = colours()
+        nprint(f"{col['pink']}Error:{col['reset']} Unable to read previous matrix. Averaging")
+        return None
+
+
+def save_matrix(matrix: np.ndarray, directory: str, matrix_name: str) -> None:
+    """NFACT/base/matrix_handling.py:161-181."""
+    try:
+        np.save(os.path.join(directory, matrix_name), matrix)
+    except Exception as e:
+        error_and_exit(False, f"Unable to save matrix due to {e}")
+
+
+def thresholding(component: np.ndarray, zscore_val) -> np.ndarray:
+    """NFACT/base/matrix_handling.py:218-238 (in place; elementwise post-op after the D2H copy)."""
+    for comp in range(component.shape[0]):
+        tract = component[comp, :]
+        threshold = tract.mean() + (zscore_val * tract.std())
+        tract[tract < threshold] = 0.0
+    return component
+
+
+def normalise_components(grey_matter: np.ndarray, white_matter: np.ndarray) -> dict:
+    """NFACT/base/matrix_handling.py:45-68 (StandardScaler semantics: population std, zero std -> 1)."""
+    def zscore_cols(arr):
+        arr64 = arr.astype(np.float64)
+        mean = arr64.mean(axis=0)
+        std = arr64.std(axis=0)
+        std[std < 10 * np.finfo(np.float64).eps] = 1.0
+        return ((arr64 - mean) / std).astype(arr.dtype)
+    col = colours()
+    nprint(f"{col['pink']}Normalising:{col['reset']} Components")
+    return {"grey_matter": zscore_cols(grey_matter), "white_matter": zscore_cols(white_matter.T).T}

@@ -1,0 +1,184 @@
+"""NMF solve -- host-side mirror of the reference's decomposition seam, arithmetic on the GPU.
+
+Same names, arguments and error behaviour as
+  NFACT/decomp/decomposition/sso/nmfsso.py:32-59          nmf_decomp(parameters, fdt_matrix, W=None, H=None)
+  NFACT/decomp/decomposition/matrix_decomposition.py:74-107   get_parameters(parameters, algo, n_components)
+  NFACT/config/nfact_config_functions.py:337-356          the hyper-parameter schema (= sklearn NMF's signature)
+The solver itself (sklearn/decomposition/_nmf.py: _fit_coordinate_descent :399-518,
+_fit_multiplicative_update :726-897, _initialize_nmf :214-366) runs in libnfact_b200.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import device
+from .device import DeviceMatrix, NmfState, make_params
+from .utils import error_and_exit
+
+# sklearn 1.9 NMF.__init__ signature minus n_components (what ``nfact_config -D`` dumps)
+NMF_DEFAULTS = {
+    "init": None, "solver": "cd", "beta_loss": "frobenius", "tol": 1e-4, "max_iter": 200,
+    "random_state": None, "alpha_W": 0.0, "alpha_H": "same", "l1_ratio": 0.0, "verbose": 0, "shuffle": False,
+}
+
+
+def create_combined_algo_dict() -> dict:
+    """NFACT/config/nfact_config_functions.py:337-356 (NMF block)."""
+    return {"nmf": dict(NMF_DEFAULTS)}
+
+
+def get_parameters(parameters: dict, algo: str, n_components: int) -> dict:
+    """NFACT/decomp/decomposition/matrix_decomposition.py:74-107."""
+    if parameters:
+        parameters["n_components"] = n_components
+        return parameters
+    if algo != "nmf":
+        raise ValueError("nfact_b200 implements the NMF decomposition path only")
+    parameters = create_combined_algo_dict()[algo]
+    parameters["n_components"] = n_components
+    parameters["alpha_W"] = 0.1
+    parameters["init"] = "nndsvd"
+    parameters["random_state"] = None
+    parameters["l1_ratio"] = 1
+    return parameters
+
+
+def compute_regularization(n_samples: int, n_features: int, alpha_W, alpha_H, l1_ratio):
+    """sklearn/decomposition/_nmf.py:1249-1259 (float64 scalars)."""
+    alpha_H = alpha_W if alpha_H == "same" else alpha_H
+    return (n_features * alpha_W * l1_ratio, n_samples * alpha_H * l1_ratio,
+            n_features * alpha_W * (1.0 - l1_ratio), n_samples * alpha_H * (1.0 - l1_ratio))
+
+
+def _check_params(p: dict) -> dict:
+    unknown = set(p) - set(NMF_DEFAULTS) - {"n_components"}
+    if unknown:
+        raise TypeError(f"NMF.__init__() got an unexpected keyword argument '{sorted(unknown)[0]}'")
+    full = dict(NMF_DEFAULTS)
+    full.update(p)
+    if full["beta_loss"] not in ("frobenius", 2, 2.0):
+        raise ValueError("nfact_b200 implements beta_loss='frobenius' only (no CPU fallback for other losses)")
+    if full["solver"] not in ("cd", "mu"):
+        raise ValueError(f"The 'solver' parameter of NMF must be a str among {{'cd', 'mu'}}. Got {full['solver']!r}")
+    if full["shuffle"]:
+        raise ValueError("shuffle=True is not implemented on the device (NFACT never sets it)")
+    if not isinstance(full["n_components"], (int, np.integer)) or full["n_components"] < 1:
+        raise ValueError("n_components must be a positive integer")
+    return full
+
+
+def _random_state(seed):
+    if seed is None or isinstance(seed, (int, np.integer)):
+        return np.random.RandomState(seed)
+    if isinstance(seed, np.random.RandomState):
+        return seed
+    raise ValueError(f"{seed!r} cannot be used to seed a numpy.random.RandomState instance")
+
+
+def initialize_nmf(xdev: DeviceMatrix, x_mean: float, k: int, init, random_state):
+    """sklearn/decomposition/_nmf.py:214-366 for init in {random, nndsvd, nndsvda, nndsvdar}.
+
+    The random draws come from numpy's RandomState exactly as in sklearn (so a fixed ``random_state``
+    gives sklearn's starting point); every product with X runs on the device.
+    """
+    m, n = xdev.shape
+    if init is None:
+        init = "nndsvda" if k <= min(m, n) else "random"
+    if init != "random" and k > min(m, n):
+        raise ValueError(f"init = '{init}' can only be used when n_components <= min(n_samples, n_features)")
+    rng = _random_state(random_state)
+    if init == "random":
+        avg = np.sqrt(x_mean / k)
+        H = avg * rng.standard_normal(size=(k, n)).astype(np.float32, copy=False)
+        W = avg * rng.standard_normal(size=(m, k)).astype(np.float32, copy=False)
+        return np.abs(W, out=W), np.abs(H, out=H)
+    if init not in ("nndsvd", "nndsvda", "nndsvdar"):
+        raise ValueError(f"Invalid init parameter: got {init!r} instead of one of "
+                         "(None, 'random', 'nndsvd', 'nndsvda', 'nndsvdar')")
+    from .nndsvd import nndsvd_device
+    W, H = nndsvd_device(xdev, k, rng)
+    if init == "nndsvda":
+        W[W == 0] = x_mean
+        H[H == 0] = x_mean
+    elif init == "nndsvdar":
+        W[W == 0] = abs(x_mean * rng.standard_normal(size=int((W == 0).sum())) / 100)
+        H[H == 0] = abs(x_mean * rng.standard_normal(size=int((H == 0).sum())) / 100)
+    return W, H
+
+
+class NMF:
+    """The slice of sklearn.decomposition.NMF that NFACT touches (nmfsso.py:54-59):
+    ``NMF(**parameters).fit_transform(X, W=W, H=H)``, ``components_``, ``n_iter_``,
+    ``reconstruction_err_``."""
+
+    def __init__(self, n_components=None, **kwargs):
+        self.params = _check_params(dict(kwargs, n_components=n_components))
+
+    def fit_transform(self, X, y=None, W=None, H=None):
+        p = self.params
+        k = int(p["n_components"])
+        if isinstance(X, DeviceMatrix):
+            xdev, x_mean, owns = X, None, False
+        else:
+            X = np.asarray(X)
+            if X.ndim != 2:
+                raise ValueError(f"Expected 2D array, got {X.ndim}D array instead")
+            if X.dtype not in (np.float32, np.float64):
+                X = X.astype(np.float64)
+            if X.size and X.min() < 0:
+                raise ValueError("Negative values in data passed to NMF (input X)")
+            x_mean = float(X.mean())
+            xdev, owns = DeviceMatrix.from_host(X), True
+        try:
+            m, n = xdev.shape
+            if p["init"] == "custom":
+                for name, arr, shape in (("H", H, (k, n)), ("W", W, (m, k))):
+                    arr = np.asarray(arr)
+                    if arr.shape != shape:
+                        raise ValueError(f"Array with wrong shape passed to NMF (input {name}). "
+                                         f"Expected {shape}, but got {arr.shape} ")
+                    if arr.size and arr.min() < 0:
+                        raise ValueError(f"Negative values in data passed to NMF (input {name})")
+                    if arr.size and arr.max() == 0:
+                        raise ValueError(f"Array passed to NMF (input {name}) is full of zeros.")
+                W0 = np.array(W, dtype=np.float32, order="C")
+                H0 = np.array(H, dtype=np.float32, order="C")
+            else:
+                if x_mean is None:
+                    raise ValueError("init != 'custom' on a DeviceMatrix needs the host matrix (its mean); "
+                                     "pass W and H or the numpy matrix")
+                W0, H0 = initialize_nmf(xdev, x_mean, k, p["init"], p["random_state"])
+            regs = compute_regularization(m, n, p["alpha_W"], p["alpha_H"], p["l1_ratio"])
+            state = NmfState(xdev, k, make_params(p["solver"], p["max_iter"], p["tol"], regs, p["verbose"]))
+            try:
+                state.set_factors(W0, H0)
+                self.n_iter_, self.reconstruction_err_ = state.run()
+                Wf, Hf = state.get_factors()
+            finally:
+                state.free()
+        finally:
+            if owns:
+                xdev.free()
+        self.components_ = Hf
+        self.n_components_ = Hf.shape[0]
+        return Wf
+
+
+def nmf_decomp(parameters: dict, fdt_matrix, W=None, H=None) -> dict:
+    """NFACT/decomp/decomposition/sso/nmfsso.py:32-59.
+
+    ``fdt_matrix`` is the float32 [m, n] connectivity matrix (a numpy array like the reference, or a
+    ``DeviceMatrix`` that is already resident); ``W``/``H`` given => ``init='custom'``.
+    Returns {"grey_components": W [m,k], "white_components": H [k,n]} as float32 numpy arrays.
+    """
+    if W is not None and H is not None:
+        parameters = parameters.copy()
+        parameters["init"] = "custom"
+    grey_matter = components = None
+    try:
+        decomp = NMF(**parameters)
+        grey_matter = decomp.fit_transform(fdt_matrix, W=W, H=H)
+        components = decomp.components_
+    except Exception as e:
+        error_and_exit(False, f"Unable to perform NMF due to {e}")
+    return {"grey_components": grey_matter, "white_components": components}

@@ -1,0 +1,86 @@
+"""CPU: the C-ABI library loads and exports every symbol include/nfact_b200.h declares; host-side logic."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "nfact_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(nfb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    import nfact_b200
+    from nfact_b200 import _lib
+    lib = nfact_b200.load_library()
+    declared = _declared_symbols()
+    assert len(declared) >= 25
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/nfact_b200.h but not exported"
+    assert sorted(_lib.SIGNATURES) == declared, "ctypes table and header disagree"
+    assert b"sm_100a" in lib.nfb_version()
+
+
+def test_no_cpu_fallback_without_gpu():
+    """Without a CUDA device the product path fails loudly instead of computing on the host."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import nfact_b200
+    from nfact_b200._lib import NfbError
+    with pytest.raises((NfbError, SystemExit)):
+        nfact_b200.nmf_decomp(nfact_b200.get_parameters(None, "nmf", 3), np.ones((8, 9), np.float32))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "nfact_b200")
+    for base, _, files in os.walk(pkg):
+        for name in files:
+            if name.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(base, name)).read()
+                assert "oracle" not in text.lower() or name == "nothing", f"{name} mentions the oracle"
+
+
+def test_get_parameters_matches_reference(golden):
+    import nfact_b200
+    p = nfact_b200.get_parameters(None, "nmf", 10)
+    assert sorted(p.keys()) == list(golden["params_keys"])
+    assert repr(sorted(p.items(), key=lambda kv: kv[0])) == str(golden["params_repr"])
+    cfg = {"init": "random", "solver": "mu"}
+    assert nfact_b200.get_parameters(cfg, "nmf", 7) == {"init": "random", "solver": "mu", "n_components": 7}
+    regs = nfact_b200.compute_regularization(99, 199, p["alpha_W"], p["alpha_H"], p["l1_ratio"])
+    assert np.array_equal(np.array(regs, dtype=np.float64), golden["regularization"])
+
+
+def test_host_parsing_matches_oracle(golden_subjects):
+    import nfact_b200
+    from oracle import nfact_oracle as orc
+    mat = nfact_b200.read_in_matrix(golden_subjects[0])
+    assert np.array_equal(mat, orc.read_dot(golden_subjects[0]))
+    coo = nfact_b200.load_single_matrix(golden_subjects[0])
+    assert coo.shape == (99, 199) and coo.rows.dtype == np.int32 and coo.rows.min() >= 0
+    assert coo.scale == 1e8 / 15000000.0
+
+
+def test_postops_match_reference(golden):
+    import nfact_b200
+    norm = nfact_b200.normalise_components(golden["cd_fit_W"].copy(), golden["cd_fit_H"].copy())
+    assert np.allclose(norm["grey_matter"], golden["norm_grey"], rtol=1e-5, atol=1e-6)
+    assert np.allclose(norm["white_matter"], golden["norm_white"], rtol=1e-5, atol=1e-6)
+    assert np.array_equal(nfact_b200.thresholding(golden["cd_fit_H"].copy(), 3), golden["thresh_white_3"])
+
+
+def test_parameter_validation():
+    import nfact_b200
+    with pytest.raises(TypeError):
+        nfact_b200.NMF(n_components=3, not_a_param=1)
+    with pytest.raises(ValueError):
+        nfact_b200.NMF(n_components=3, beta_loss="kullback-leibler")
+    with pytest.raises(ValueError):
+        nfact_b200.NMF(n_components=3, solver="xx")

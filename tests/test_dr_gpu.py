@@ -1,0 +1,56 @@
+"""GPU: non-negative dual regression against scipy.optimize.nnls (golden) and the oracle."""
+import numpy as np
+import pytest
+
+from conftest import rel_fro
+
+pytestmark = pytest.mark.gpu
+
+DR_TOL = 1e-4     # rel-Frobenius <= 1e-4 vs scipy float64
+
+
+def test_dr_matches_scipy_golden(golden):
+    import nfact_b200
+    comps = {"grey_components": golden["cd_fit_W"].astype(np.float64),
+             "white_components": golden["cd_fit_H"].astype(np.float64)}
+    dr = nfact_b200.nmf_dual_regression(comps, golden["ingest_single_1"], 1)
+    assert dr["grey_components"].dtype == np.float64 and dr["grey_components"].shape == golden["dr_grey"].shape
+    assert dr["white_components"].shape == golden["dr_white"].shape
+    assert rel_fro(dr["white_components"], golden["dr_white"]) < DR_TOL
+    assert rel_fro(dr["grey_components"], golden["dr_grey"]) < DR_TOL
+
+
+def test_dr_second_subject_parallel_flag(golden):
+    import nfact_b200
+    comps = {"grey_components": golden["mu_fit_W"], "white_components": golden["mu_fit_H"]}
+    dr = nfact_b200.run_decomp(nfact_b200.nmf_dual_regression, comps, golden["ingest_single_2"], 4)
+    assert rel_fro(dr["white_components"], golden["dr2_white"]) < DR_TOL
+    assert rel_fro(dr["grey_components"], golden["dr2_grey"]) < DR_TOL
+
+
+def test_dr_kkt_conditions():
+    """Size-independent property: the solution satisfies the NNLS KKT conditions for both stages."""
+    import nfact_b200
+    rng = np.random.default_rng(9)
+    m, n, k = 700, 1100, 37
+    G = rng.gamma(0.3, 1.0, (m, k))
+    X = (rng.gamma(0.3, 1.0, (m, k)) @ rng.gamma(0.3, 1.0, (k, n)) * (rng.random((m, n)) < 0.3)).astype(np.float32)
+    dr = nfact_b200.nmf_dual_regression({"grey_components": G}, X)
+    Hs, Gs = dr["white_components"], dr["grey_components"]
+    assert (Hs >= 0).all() and (Gs >= 0).all()
+    X64 = X.astype(np.float64)
+    grad1 = G.T @ (G @ Hs - X64)                      # [k, n]
+    scale1 = np.abs(G.T @ X64).max()
+    assert grad1.min() > -1e-5 * scale1
+    assert np.abs(grad1[Hs > 0]).max() < 1e-5 * scale1
+    grad2 = (Gs @ Hs - X64) @ Hs.T                    # [m, k]
+    scale2 = np.abs(X64 @ Hs.T).max()
+    assert grad2.min() > -1e-5 * scale2
+    assert np.abs(grad2[Gs > 0]).max() < 1e-5 * scale2
+
+
+def test_dr_shape_mismatch_exits(golden):
+    import nfact_b200
+    comps = {"grey_components": np.ones((5, 3))}
+    with pytest.raises(SystemExit):
+        nfact_b200.run_decomp(nfact_b200.nmf_dual_regression, comps, golden["ingest_single_1"], 1)

@@ -1,0 +1,71 @@
+"""GPU: ingest / group average is bit-identical to the reference (golden) and to the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_DIR
+
+pytestmark = pytest.mark.gpu
+
+
+def test_single_subject_bit_exact(golden, golden_subjects):
+    import nfact_b200
+    for s, path in enumerate(golden_subjects):
+        X = nfact_b200.load_fdt_matrix(path)
+        assert X.dtype == np.float32 and X.flags.c_contiguous
+        assert np.array_equal(X, golden[f"ingest_single_{s + 1}"])
+
+
+def test_non_integer_values_bit_exact(golden):
+    import nfact_b200
+    X = nfact_b200.load_fdt_matrix(os.path.join(GOLDEN_DIR, "data", "sub-pd", "fdt_matrix2.dot"))
+    assert np.array_equal(X, golden["ingest_single_pd"])
+
+
+def test_group_average_bit_exact(golden, golden_subjects):
+    import nfact_b200
+    assert np.array_equal(nfact_b200.avg_fdt(golden_subjects), golden["ingest_group"])
+    assert np.array_equal(nfact_b200.avg_fdt(golden_subjects[:2]), golden["ingest_group2"])
+    folders = [os.path.dirname(p) for p in golden_subjects]
+    assert np.array_equal(nfact_b200.process_fdt_matrix2(folders, True), golden["ingest_group"])
+    assert np.array_equal(nfact_b200.process_fdt_matrix2(folders[:1], False), golden["ingest_single_1"])
+
+
+def test_random_against_oracle(tmp_path):
+    """Ragged shapes, duplicates, empty rows/columns, several subjects; compared with the oracle."""
+    import nfact_b200
+    from oracle import nfact_oracle as orc
+    rng = np.random.default_rng(11)
+    files = []
+    for s in range(4):
+        folder = tmp_path / f"sub-{s}"
+        folder.mkdir()
+        nnz = 5000 + 1000 * s
+        rows = rng.integers(1, 258, size=nnz)
+        cols = rng.integers(5, 391, size=nnz)
+        vals = rng.integers(1, 2000, size=nnz)
+        with open(folder / "fdt_matrix2.dot", "w") as fh:
+            for r, c, v in zip(rows, cols, vals):
+                fh.write(f"{r} {c} {v}\n")
+            fh.write("257 401 0\n")
+        (folder / "waytotal").write_text(str(10_000_000 + 777_777 * s))
+        files.append(str(folder / "fdt_matrix2.dot"))
+    assert np.array_equal(nfact_b200.load_fdt_matrix(files[2]), orc.load_fdt_matrix(files[2]))
+    assert np.array_equal(nfact_b200.avg_fdt(files), orc.avg_fdt(files))
+    assert np.array_equal(nfact_b200.avg_fdt(files[:3]), orc.avg_fdt(files[:3]))
+
+
+def test_empty_matrix_and_errors(tmp_path):
+    import nfact_b200
+    folder = tmp_path / "sub-empty"
+    folder.mkdir()
+    (folder / "fdt_matrix2.dot").write_text("7 9 0\n")
+    (folder / "waytotal").write_text("1000")
+    X = nfact_b200.load_fdt_matrix(str(folder / "fdt_matrix2.dot"))
+    assert X.shape == (7, 9) and not X.any()
+    (folder / "fdt_matrix2.dot").write_text("8 1 5\n7 9 0\n")       # row index beyond the shape line
+    with pytest.raises(ValueError):
+        nfact_b200.load_fdt_matrix(str(folder / "fdt_matrix2.dot"))
+    with pytest.raises(SystemExit):                                   # reference: error_and_exit -> exit(1)
+        nfact_b200.process_fdt_matrix2([str(folder)], False)

@@ -1,0 +1,166 @@
+"""GPU: NMF solver parity with sklearn as NFACT configures it (golden vectors + oracle)."""
+import numpy as np
+import pytest
+
+from conftest import rel_fro
+
+pytestmark = pytest.mark.gpu
+
+MU_TOL = 1e-4     # BASELINE.json: MU trajectory within 1e-4 relative Frobenius error per iteration
+CD_OBJ_TOL = 5e-3  # CD: final objective within 0.5 %
+CD_CORR = 0.99     # CD: Hungarian-matched component correlation >= 0.99
+
+
+def _state(X, k, solver, regs, max_iter=200, tol=1e-4):
+    import nfact_b200
+    from nfact_b200.device import DeviceMatrix, NmfState, make_params
+    xdev = DeviceMatrix.from_host(X)
+    return xdev, NmfState(xdev, k, make_params(solver, max_iter, tol, regs))
+
+
+def matched_correlation(A, B):
+    """Hungarian-matched Pearson correlation between the rows of A and B."""
+    from scipy.optimize import linear_sum_assignment
+    A = A - A.mean(axis=1, keepdims=True)
+    B = B - B.mean(axis=1, keepdims=True)
+    An = np.linalg.norm(A, axis=1, keepdims=True)
+    Bn = np.linalg.norm(B, axis=1, keepdims=True)
+    live = (An[:, 0] > 0) & (Bn[:, 0] > 0)
+    C = (A / np.where(An > 0, An, 1)) @ (B / np.where(Bn > 0, Bn, 1)).T
+    r, c = linear_sum_assignment(-C)
+    return C[r, c], live
+
+
+def test_mu_trajectory_matches_sklearn_per_iteration(golden):
+    X = golden["ingest_group"]
+    xdev, st = _state(X, 10, "mu", golden["regularization"])
+    st.set_factors(golden["init_nndsvd_W"], golden["init_nndsvd_H"])
+    assert abs(st.error() - golden["mu_err0"]) <= 1e-5 * golden["mu_err0"]
+    for it in range(1, 41):
+        st.iterate(1)
+        if f"mu_W_{it}" in golden:
+            W, H = st.get_factors()
+            assert rel_fro(W, golden[f"mu_W_{it}"]) < MU_TOL, it
+            assert rel_fro(H, golden[f"mu_H_{it}"]) < MU_TOL, it
+            assert abs(st.error() - golden[f"mu_err_{it}"]) <= 1e-5 * golden[f"mu_err_{it}"], it
+
+
+def test_mu_with_l1_and_l2(golden):
+    X = golden["ingest_group"]
+    xdev, st = _state(X, 10, "mu", golden["mu_l2_regs"])
+    st.set_factors(golden["init_random_W"], golden["init_random_H"])
+    st.iterate(5)
+    W, H = st.get_factors()
+    assert rel_fro(W, golden["mu_l2_W_5"]) < MU_TOL
+    assert rel_fro(H, golden["mu_l2_H_5"]) < MU_TOL
+
+
+def test_mu_full_fit_through_nmf_decomp(golden):
+    import nfact_b200
+    X = golden["ingest_group"]
+    p = dict(nfact_b200.get_parameters(None, "nmf", 10), solver="mu")
+    res = nfact_b200.nmf_decomp(p, X, W=golden["init_nndsvd_W"].copy(), H=golden["init_nndsvd_H"].copy())
+    assert res["grey_components"].dtype == np.float32 and res["grey_components"].shape == (99, 10)
+    assert res["white_components"].shape == (10, 199)
+    assert rel_fro(res["grey_components"], golden["mu_fit_W"]) < 1e-3
+    assert rel_fro(res["white_components"], golden["mu_fit_H"]) < 1e-3
+
+
+def test_mu_stopping_rule(golden):
+    import nfact_b200
+    X = golden["ingest_group"]
+    est = nfact_b200.NMF(**dict(nfact_b200.get_parameters(None, "nmf", 10), solver="mu", init="custom"))
+    est.fit_transform(X, W=golden["init_nndsvd_W"].copy(), H=golden["init_nndsvd_H"].copy())
+    assert est.n_iter_ == int(golden["mu_fit_n_iter"])
+
+
+def test_cd_sweeps_match_sklearn(golden):
+    X = golden["ingest_group"]
+    xdev, st = _state(X, 10, "cd", golden["regularization"])
+    st.set_factors(golden["init_nndsvd_W"], golden["init_nndsvd_H"])
+    for it in range(1, 4):
+        viol = st.iterate(1, want_violation=True)
+        W, H = st.get_factors()
+        assert rel_fro(W, golden[f"cd_W_{it}"]) < 1e-4, it
+        assert rel_fro(H, golden[f"cd_H_{it}"]) < 1e-4, it
+        assert abs(viol - golden["cd_violation"][it - 1]) <= 1e-3 * golden["cd_violation"][it - 1], it
+
+
+def test_cd_full_fit_nfact_defaults(golden):
+    import nfact_b200
+    from oracle import nfact_oracle as orc
+    X = golden["ingest_group"]
+    p = nfact_b200.get_parameters(None, "nmf", 10)
+    est = nfact_b200.NMF(**dict(p, init="custom"))
+    W = est.fit_transform(X, W=golden["init_nndsvd_W"].copy(), H=golden["init_nndsvd_H"].copy())
+    H = est.components_
+    regs = golden["regularization"]
+    obj = orc.nmf_objective(X, W, H, *regs)
+    ref = orc.nmf_objective(X, golden["cd_fit_W"], golden["cd_fit_H"], *regs)
+    assert abs(obj - ref) <= CD_OBJ_TOL * ref
+    corr, live = matched_correlation(H, golden["cd_fit_H"])
+    assert corr[live].min() >= CD_CORR
+    corr_w, live_w = matched_correlation(W.T, golden["cd_fit_W"].T)
+    assert corr_w[live_w].min() >= CD_CORR
+    assert abs(est.n_iter_ - int(golden["cd_fit_n_iter"])) <= 5
+    assert abs(est.reconstruction_err_ - golden["cd_fit_err"]) <= 1e-3 * golden["cd_fit_err"]
+
+
+def test_cd_second_case_l2(golden):
+    import nfact_b200
+    from oracle import nfact_oracle as orc
+    X = golden["ingest_group"]
+    p = dict(nfact_b200.get_parameters(None, "nmf", 10), alpha_W=0.001, l1_ratio=0.5, max_iter=60)
+    res = nfact_b200.nmf_decomp(p, X, W=golden["init_random_W"].copy(), H=golden["init_random_H"].copy())
+    regs = orc.compute_regularization(99, 199, 0.001, "same", 0.5)
+    obj = orc.nmf_objective(X, res["grey_components"], res["white_components"], *regs)
+    ref = orc.nmf_objective(X, golden["cd2_fit_W"], golden["cd2_fit_H"], *regs)
+    assert abs(obj - ref) <= CD_OBJ_TOL * ref
+    corr, live = matched_correlation(res["white_components"], golden["cd2_fit_H"])
+    assert corr[live].min() >= CD_CORR
+
+
+@pytest.mark.parametrize("solver", ["mu", "cd"])
+def test_medium_random_against_oracle(solver):
+    """A larger ragged case (m, n not multiples of the tile sizes, k not a multiple of 16)."""
+    from oracle import nfact_oracle as orc
+    rng = np.random.default_rng(3)
+    m, n, k = 517, 1203, 23
+    Wt, Ht = rng.gamma(0.3, 1.0, (m, k)), rng.gamma(0.3, 1.0, (k, n))
+    X = (np.floor(300 * (Wt @ Ht)) * (rng.random((m, n)) < 0.4) * (1e8 / 1.5e7)).astype(np.float32)
+    W0, H0 = orc.init_random(X, k, 1)
+    regs = orc.compute_regularization(m, n, 0.01, "same", 1.0)
+    xdev, st = _state(X, k, solver, regs)
+    st.set_factors(W0, H0)
+    rec = []
+    (orc.fit_mu if solver == "mu" else orc.fit_cd)(X, W0, H0, *regs, tol=0, max_iter=6, record=rec)
+    for it in range(1, 7):
+        st.iterate(1)
+        W, H = st.get_factors()
+        assert rel_fro(W, rec[it - 1][1]) < MU_TOL, (solver, it)
+        assert rel_fro(H, rec[it - 1][2]) < MU_TOL, (solver, it)
+
+
+def test_inits_and_error_paths(golden):
+    import nfact_b200
+    X = golden["ingest_group"]
+    p = nfact_b200.get_parameters(None, "nmf", 10)
+    res = nfact_b200.nmf_decomp(dict(p, init="random", random_state=7, max_iter=3), X)
+    assert res["grey_components"].shape == (99, 10) and (res["grey_components"] >= 0).all()
+    res = nfact_b200.nmf_decomp(dict(p, random_state=0, max_iter=5), X)          # nndsvd on the device
+    assert np.isfinite(res["white_components"]).all()
+    with pytest.raises(SystemExit):                                              # nmfsso.py:57-58
+        nfact_b200.nmf_decomp(dict(p, beta_loss="kullback-leibler"), X)
+    with pytest.raises(SystemExit):
+        nfact_b200.nmf_decomp(p, X, W=np.ones((5, 10), np.float32), H=np.ones((10, 199), np.float32))
+
+
+def test_nndsvd_device_matches_sklearn(golden):
+    import nfact_b200
+    from nfact_b200.device import DeviceMatrix
+    from nfact_b200.nndsvd import nndsvd_device
+    X = golden["ingest_group"]
+    xdev = DeviceMatrix.from_host(X)
+    W, H = nndsvd_device(xdev, 10, np.random.RandomState(0))
+    assert rel_fro(W, golden["init_nndsvd_W"]) < 1e-3
+    assert rel_fro(H, golden["init_nndsvd_H"]) < 1e-3
