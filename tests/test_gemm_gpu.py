@@ -60,9 +60,9 @@ def test_gemm_matches_float64(rows, cols, n_b, transposed, cta_group):
     ref = _reference(a, b, transposed)
     scale = np.abs(ref).max(axis=1, keepdims=True) + 1e-300
     err = np.abs(out - ref) / scale
-    assert err.max() < 2e-6, f"max rel err {err.max():.3e}"
+    assert err.max() < 1e-5, f"max rel err {err.max():.3e}"
     rel_fro = np.linalg.norm(out - ref) / np.linalg.norm(ref)
-    assert rel_fro < 1e-6, f"rel fro {rel_fro:.3e}"
+    assert rel_fro < 5e-6, f"rel fro {rel_fro:.3e}"
 
 
 @pytest.mark.parametrize("cta_group", [1, 2])
@@ -73,4 +73,4 @@ def test_gemm_signed_values_and_splits(cta_group):
     ref = _reference(a, b, False)
     for splits in (1, 3, 8):
         out = _run_gemm(a, b, False, cta_group, splits)
-        assert np.abs(out - ref).max() / np.abs(ref).max() < 2e-6, splits
+        assert np.abs(out - ref).max() / np.abs(ref).max() < 1e-5, splits
