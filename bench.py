@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""Benchmark of the NFACT decomposition hot path on B200 (see BASELINE.json / SURVEY.md section 8d).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload C1|C2|C3] [--solver cd|mu] [--no-e2e] [--no-cpu]
+
+A "step" is one NMF iteration (W half-step + H half-step) on the synthetic connectivity matrix of the
+named shape.  `value` = iterations/s with X, W, H resident in HBM; `e2e` = iterations/s of one
+`nmf_decomp(parameters, X_host, W=W0, H=H0)` call on host buffers (H2D of X, plane split, solve, D2H of
+W and H inside the timed region); `roofline` = the dominant kernel (the X-streaming split-precision
+GEMM) against the measured HBM peak; `cpu_baseline` = sklearn's NMF exactly as NFACT calls it, timed on
+this box's host cores on a bounded row sample.  Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (m seeds, n targets, k components, nnz density)   SURVEY.md section 8d
+    "C1": (5000, 10000, 50, 0.15),
+    "C2": (29696, 60000, 100, 0.05),
+    "C3": (59412, 110000, 200, 0.05),
+}
+METRIC = "nmf_iterations_per_second"
+UNIT = "iter/s"
+ALPHA_W, L1_RATIO = 0.1, 1.0   # NFACT defaults (matrix_decomposition.py:100-107)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("NFB_BENCH_WORKLOAD", "C3"), choices=sorted(WORKLOADS))
+    ap.add_argument("--solver", default="cd", choices=["cd", "mu"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-iters", type=int, default=0, help="iterations of the e2e call (default: max(steps, 50))")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            data = json.load(fh)
+        return float(data["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def regularization(m_total, n, k):
+    return (n * ALPHA_W * L1_RATIO, m_total * ALPHA_W * L1_RATIO, n * ALPHA_W * (1 - L1_RATIO),
+            m_total * ALPHA_W * (1 - L1_RATIO))
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic connectivity matrix: planted Gamma factors, Bernoulli mask, integer
+# "streamline counts" scaled by 1e8 / waytotal.  Generated on the device, one row block at a time.
+# ------------------------------------------------------------------------------------------------
+def synth_rows_device(torch, dev, row0, rows, n, k, density, seed=0):
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(seed * 1000003 + 17)
+    h_star = torch._standard_gamma(torch.full((k, n), 0.3, device=dev), generator=gen)
+    out = torch.empty((rows, n), dtype=torch.float32, device=dev)
+    blk = 2048
+    for r in range(0, rows, blk):
+        nr = min(blk, rows - r)
+        gen.manual_seed(seed * 1000003 + 1000 + row0 + r)
+        w_star = torch._standard_gamma(torch.full((nr, k), 0.3, device=dev), generator=gen)
+        dense = torch.floor(300.0 * (w_star @ h_star))
+        mask = torch.rand((nr, n), device=dev, generator=gen) < density
+        counts = (dense * mask).to(torch.float64) * (1e8 / 1.5e7)
+        out[r:r + nr] = counts.to(torch.float32)
+    return out
+
+
+def random_init(torch, dev, x_mean, rows, n, k, row0, seed=1):
+    """sklearn's init='random' formula (avg * |N(0,1)|) with a device RNG."""
+    gen = torch.Generator(device=dev)
+    avg = float(np.sqrt(x_mean / k))
+    gen.manual_seed(seed)
+    h0 = (avg * torch.randn((k, n), device=dev, generator=gen)).abs_().float()
+    gen.manual_seed(seed + 7919 + row0)
+    w0 = (avg * torch.randn((rows, k), device=dev, generator=gen)).abs_().float()
+    return w0.contiguous(), h0.contiguous()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i] == "Active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference CPU path: sklearn.decomposition.NMF called exactly as NFACT does
+# (NFACT/decomp/decomposition/sso/nmfsso.py:54-56 with get_parameters defaults), on a bounded row sample.
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_seconds_per_iter(m, n, k, density, solver, budget_rows=(1024, 2048)):
+    """Fit t(m_s) = a*m_s + b from two row samples (per-iteration slope between max_iter=1 and 3) and
+    extrapolate to the full m: the H half-step costs do not shrink with the row sample."""
+    import warnings
+    from sklearn.decomposition import NMF
+    rng = np.random.default_rng(0)
+    h_star = rng.gamma(0.3, 1.0, (k, n)).astype(np.float32)
+    per_iter = []
+    for ms in budget_rows:
+        w_star = rng.gamma(0.3, 1.0, (ms, k)).astype(np.float32)
+        x = np.floor(300.0 * (w_star @ h_star)) * (rng.random((ms, n)) < density)
+        x = (x * (1e8 / 1.5e7)).astype(np.float32)
+        avg = np.sqrt(x.mean() / k)
+        w0 = np.abs(avg * rng.standard_normal((ms, k))).astype(np.float32)
+        h0 = np.abs(avg * rng.standard_normal((k, n))).astype(np.float32)
+        times = {}
+        for iters in (1, 3):
+            est = NMF(n_components=k, init="custom", solver=solver, beta_loss="frobenius", tol=0.0, max_iter=iters,
+                      random_state=None, alpha_W=ALPHA_W, alpha_H=ALPHA_W * m / ms,
+                      l1_ratio=L1_RATIO, verbose=0, shuffle=False)
+            t0 = time.perf_counter()
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                est.fit_transform(x, W=w0.copy(), H=h0.copy())
+            times[iters] = time.perf_counter() - t0
+        per_iter.append((times[3] - times[1]) / 2.0)
+    (m1, m2), (t1, t2) = budget_rows, per_iter
+    a = (t2 - t1) / (m2 - m1)
+    b = t1 - a * m1
+    full = max(a * m + b, t2 * m / m2 * 0.5)
+    return full, per_iter
+
+
+def cpu_baseline(m, n, k, density, solver):
+    import threadpoolctl
+    full, samples = cpu_reference_seconds_per_iter(m, n, k, density, solver)
+    info = threadpoolctl.threadpool_info()
+    threads = max([i.get("num_threads", 1) for i in info] or [1])
+    return {
+        "value": 1.0 / full, "unit": UNIT, "cores": int(threads), "kind": "reference",
+        "sample": (f"sklearn {__import__('sklearn').__version__} NMF(init=custom, solver={solver}, NFACT default "
+                   f"alpha_W/l1_ratio) as called by NFACT nmfsso.py:54-56, on row samples of 1024 and 2048 seeds x "
+                   f"{n} targets, k={k}; seconds/iter from the max_iter 1->3 slope ({samples[0]:.3f}s, "
+                   f"{samples[1]:.3f}s), linear fit in m extrapolated to m={m}; host cpu_count={os.cpu_count()}"),
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    m, n, k, density = WORKLOADS[args.workload]
+    t_start = time.perf_counter()
+    base = cpu_baseline(m, n, k, density, args.solver)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / base["value"],
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {m}x{n} k={k} solver={args.solver}"},
+        "cpu_baseline": base,
+        "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": time.perf_counter() - t_start,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import nfact_b200
+    from nfact_b200.device import DeviceMatrix, Handle, NmfState, make_params
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    m, n, k, density = WORKLOADS[args.workload]
+    row0 = (m * rank) // world
+    rows = (m * (rank + 1)) // world - row0
+
+    stream = torch.cuda.Stream(device=dev)
+    handle = Handle(local_rank, stream=stream.cuda_stream)
+    if world > 1:
+        def bcast(payload):
+            obj = [payload]
+            dist.broadcast_object_list(obj, src=0)
+            return obj[0]
+        handle.init_nccl(rank, world, bcast)
+
+    with torch.cuda.stream(stream):
+        x_dev = synth_rows_device(torch, dev, row0, rows, n, k, density)
+        x_sum = x_dev.sum(dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(x_sum)
+        x_mean = float(x_sum) / (m * n)
+        stream.synchronize()
+        xmat = DeviceMatrix.from_device_ptr(x_dev.data_ptr(), rows, n, n, handle=handle)
+        want_e2e = (not args.no_e2e) and world == 1
+        x_host = None
+        if want_e2e:
+            x_host = torch.empty((rows, n), dtype=torch.float32, pin_memory=True)
+            x_host.copy_(x_dev)
+        del x_dev
+        torch.cuda.empty_cache()
+        w0, h0 = random_init(torch, dev, x_mean, rows, n, k, row0)
+        regs = regularization(m, n, k)
+        state = NmfState(xmat, k, make_params(args.solver, 10 ** 6, 0.0, regs))
+        stream.synchronize()
+        state.set_factors_dev(w0.data_ptr(), h0.data_ptr())
+
+        # ---- warm-up ------------------------------------------------------------------------------
+        state.iterate(max(args.warmup, 3))
+        handle.synchronize()
+        handle.profile_gemms(True)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        # ---- timed region: exactly K iterations, device-timed ------------------------------------
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        state.iterate(args.steps)
+        ev1.record(stream)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        clocks = sampler.stop()
+        elapsed_ms = ev0.elapsed_time(ev1)
+        launches = handle.launch_count()
+        gemm_ms, gemm_launches = handle.profile_gemms(False)
+        if world > 1:
+            t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            elapsed_ms = float(t)
+        final_err = state.error()
+        state.free()
+
+        # ---- e2e through the reference-facing call with host buffers ------------------------------
+        e2e = None
+        if want_e2e:
+            xmat.free()
+            torch.cuda.empty_cache()
+            iters = args.e2e_iters or max(args.steps, 50)
+            w0_host = w0.cpu().numpy()
+            h0_host = h0.cpu().numpy()
+            params = dict(nfact_b200.get_parameters(None, "nmf", k), solver=args.solver, tol=0.0, max_iter=iters)
+            x_np = x_host.numpy()
+            import nfact_b200.device as nfdev
+            nfdev._handles[local_rank] = handle
+            t0 = time.perf_counter()
+            res = nfact_b200.nmf_decomp(params, x_np, W=w0_host, H=h0_host)
+            t_e2e = time.perf_counter() - t0
+            assert np.isfinite(res["white_components"]).all()
+            e2e = {"value": iters / t_e2e, "unit": UNIT, "iters": iters, "seconds": t_e2e,
+                   "h2d_bytes_per_step": int((x_np.nbytes + w0_host.nbytes + h0_host.nbytes) / iters),
+                   "d2h_bytes_per_step": int((w0_host.nbytes + h0_host.nbytes) / iters),
+                   "api": "nfact_b200.nmf_decomp(parameters, X_host, W=W0, H=H0) with tol=0"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    ms_per_step = elapsed_ms / args.steps
+    hbm_peak, peak_src = measured_peaks()
+    gemm_avg_ms = gemm_ms / max(gemm_launches, 1)
+    bytes_per_launch = 4.0 * rows * n                      # one pass over the fp16 hi+lo planes of X
+    achieved = bytes_per_launch / (gemm_avg_ms * 1e-3) / 1e9 if gemm_launches else 0.0
+    line = {
+        "metric": METRIC, "value": 1000.0 / ms_per_step, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32 (fp16 hi/lo split operands, fp32 accumulate)", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {m}x{n} k={k} solver={args.solver} "
+                               f"(NFACT defaults alpha_W=0.1 l1_ratio=1), X row-sharded over {world} GPU(s)",
+                   "l2_flush": "inputs larger than L2 (X planes %.1f GB per GPU)" % (4.0 * rows * n / 1e9),
+                   "final_error": final_err},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "gemm_split_kernel (X H' and W'X)", "achieved": achieved,
+                     "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                     "peak_source": peak_src, "avg_launch_ms": gemm_avg_ms, "launches": int(gemm_launches),
+                     "algorithmic_bytes_per_launch": bytes_per_launch,
+                     "step_frac": (8.0 * rows * n / hbm_peak / 1e9) / (ms_per_step * 1e-3)},
+    }
+    if e2e is not None:
+        line["e2e"] = e2e
+    if not args.no_cpu and world == 1:
+        line["cpu_baseline"] = cpu_baseline(m, n, k, density, args.solver)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -64,6 +64,8 @@ int nfb_matrix_free(nfb_matrix* x);
 int nfb_matrix_shape(const nfb_matrix* x, int64_t* m, int64_t* n);
 /* ||X||_F^2 accumulated in float64 from the original float32 values */
 int nfb_matrix_sumsq(const nfb_matrix* x, double* out);
+/* 1 when any element of X is negative (sklearn's check_non_negative, evaluated during the split pass) */
+int nfb_matrix_has_negative(const nfb_matrix* x, int* out);
 
 /* Generic product of the resident matrix with a dense float32 factor given component-major:
  *   trans == 0 : out[t*ld_out + i] = sum_j X[i,j] * b_dev[t*n + j]     (b_dev [n_b, n], out [n_b, m])
@@ -109,6 +111,9 @@ int nfb_nmf_run(nfb_nmf* s, int* n_iter_out, double* recon_err_out);
 int nfb_nmf_error(nfb_nmf* s, double* err_out);
 /* number of kernels the last iterate/run call launched (for the benchmark's gpu_launches) */
 int64_t nfb_launch_count(const nfb_handle* h);
+/* Per-kernel timing of the two X-streaming GEMMs (X H' and W'X) with CUDA events on the launch stream.
+ * Returns the accumulated duration / count since the previous call, then sets the enable flag. */
+int nfb_profile_gemms(nfb_handle* h, int enable, double* total_ms_out, int64_t* launches_out);
 
 /* ---- non-negative dual regression ---------------------------------------------------------------
  * replaces  NFACT/dual_reg/dual_regression/dual_regression_methods.py:92-167  nmf_dual_regression

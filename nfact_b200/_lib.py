@@ -47,6 +47,7 @@ SIGNATURES = {
     "nfb_matrix_free": (c_int, [c_void_p]),
     "nfb_matrix_shape": (c_int, [c_void_p, POINTER(c_int64), POINTER(c_int64)]),
     "nfb_matrix_sumsq": (c_int, [c_void_p, POINTER(c_double)]),
+    "nfb_matrix_has_negative": (c_int, [c_void_p, POINTER(c_int)]),
     "nfb_matrix_matmul": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int64, c_void_p, c_int64]),
     "nfb_nmf_fit_host": (c_int, [c_void_p, c_void_p, c_int, POINTER(NmfParams), c_void_p, c_void_p,
                                  POINTER(c_int), POINTER(c_double)]),
@@ -60,6 +61,7 @@ SIGNATURES = {
     "nfb_nmf_run": (c_int, [c_void_p, POINTER(c_int), POINTER(c_double)]),
     "nfb_nmf_error": (c_int, [c_void_p, POINTER(c_double)]),
     "nfb_launch_count": (c_int64, [c_void_p]),
+    "nfb_profile_gemms": (c_int, [c_void_p, c_int, POINTER(c_double), POINTER(c_int64)]),
     "nfb_dual_regression_host": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, POINTER(c_int)]),
     "nfb_test_gemm": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_int64, c_void_p, c_int64,
                               c_int, c_int]),

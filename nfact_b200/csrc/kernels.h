@@ -36,7 +36,7 @@ int rowabsmax_f32(const float* x, int64_t rows, int64_t cols, int64_t ld, const 
 // X [rows, cols] fp32 -> hi/lo planes [rows, ldp] scaled by the power of two that maps *max_bits into
 // [2^14, 2^15); inv_scale[0] receives 1/scale; sumsq (may be null) accumulates sum x^2 in fp64.
 int split_matrix(const float* x, int64_t rows, int64_t cols, int64_t ld, const unsigned int* max_bits, __half* hi,
-                 __half* lo, int64_t ldp, float* inv_scale, double* sumsq, cudaStream_t stream);
+                 __half* lo, int64_t ldp, float* inv_scale, double* sumsq, int* neg_flag, cudaStream_t stream);
 // factor F [k, cols] fp32 -> planes [>=k rows, ldp] with one power-of-two scale per row
 // (from rowmax_bits[k]); inv_scale[k] receives 1/scale_t.  Columns [cols, ldp) are zeroed.
 // col_mul (nullable, [cols]) multiplies column c before the split (used to fold the K-side scales of

@@ -51,7 +51,7 @@ __global__ void split_kernel(const float* __restrict__ x, int64_t rows, int64_t 
                              const float* __restrict__ col_mul, const unsigned int* __restrict__ max_bits,
                              __half* __restrict__ hi,
                              __half* __restrict__ lo, int64_t ldp, float* __restrict__ inv_scale,
-                             double* __restrict__ sumsq) {
+                             double* __restrict__ sumsq, int* __restrict__ neg_flag) {
     __shared__ double scratch[32];
     const int64_t groups_per_row = ldp / 8;
     const int64_t total = rows * groups_per_row;
@@ -70,6 +70,7 @@ __global__ void split_kernel(const float* __restrict__ x, int64_t rows, int64_t 
             float v = c < cols ? x[r * ld + c] : 0.0f;
             if (col_mul != nullptr && c < cols) v *= col_mul[c];
             acc += static_cast<double>(v) * static_cast<double>(v);
+            if (neg_flag != nullptr && v < 0.0f) *neg_flag = 1;
             const float vs = v * s;
             const __half vh = __float2half_rn(vs);
             h[i] = vh;
@@ -109,11 +110,11 @@ int rowabsmax_f32(const float* x, int64_t rows, int64_t cols, int64_t ld, const 
 }
 
 int split_matrix(const float* x, int64_t rows, int64_t cols, int64_t ld, const unsigned int* max_bits, __half* hi,
-                 __half* lo, int64_t ldp, float* inv_scale, double* sumsq, cudaStream_t stream) {
+                 __half* lo, int64_t ldp, float* inv_scale, double* sumsq, int* neg_flag, cudaStream_t stream) {
     NFB_CHECK(ldp % 8 == 0 && ldp >= cols, "plane leading dimension must be a multiple of 8 and >= cols");
     if (rows == 0) return 0;
     split_kernel<false><<<grid_for(rows * (ldp / 8), 256, 8), 256, 0, stream>>>(x, rows, cols, ld, nullptr, max_bits, hi,
-                                                                              lo, ldp, inv_scale, sumsq);
+                                                                              lo, ldp, inv_scale, sumsq, neg_flag);
     NFB_CUDA(cudaGetLastError());
     return 0;
 }
@@ -124,7 +125,7 @@ int split_factor(const float* f, int64_t k, int64_t cols, int64_t ld, const floa
     NFB_CHECK(ldp % 8 == 0 && ldp >= cols, "plane leading dimension must be a multiple of 8 and >= cols");
     if (k == 0) return 0;
     split_kernel<true><<<grid_for(k * (ldp / 8), 256, 8), 256, 0, stream>>>(f, k, cols, ld, col_mul, rowmax_bits, hi, lo,
-                                                                          ldp, inv_scale, nullptr);
+                                                                          ldp, inv_scale, nullptr, nullptr);
     NFB_CUDA(cudaGetLastError());
     return 0;
 }

@@ -73,6 +73,9 @@ struct nfb_handle {
     bool own_stream = false;
     int cta_group = 2;
     int64_t launches_last = 0;
+    // optional per-kernel timing of the two X-streaming GEMMs (CUDA events on the launch stream)
+    bool profiling = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> gemm_events;
     // multi-GPU (row-sharded) -------------------------------------------------
     void* comm = nullptr;
     NcclAllReduceFn allreduce = nullptr;
@@ -93,6 +96,7 @@ struct nfb_matrix {
     DevBuf<float> inv_scale;
     float inv_scale_host = 1.0f;
     double sumsq = 0.0;  // local shard
+    int has_negative = 0;
     GemmOperand operand() const { return GemmOperand{hi.p, lo.p, m, ldp}; }
 };
 
@@ -182,8 +186,24 @@ static int compute_gram(nfb_nmf* s, Factor& fac, Factor& gram, int splits, bool 
 }
 
 // part_w = X H'   (per split) for the current H planes
+struct GemmTimer {
+    nfb_handle* h;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    explicit GemmTimer(nfb_handle* handle) : h(handle) {
+        if (h->profiling && cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess)
+            cudaEventRecord(e0, h->stream);
+    }
+    ~GemmTimer() {
+        if (e0 && e1) {
+            cudaEventRecord(e1, h->stream);
+            h->gemm_events.emplace_back(e0, e1);
+        }
+    }
+};
+
 static int gemm_xht(nfb_nmf* s) {
     nfb_handle* h = s->h;
+    GemmTimer timer(h);
     NFB_TRY(gemm_split(s->x->operand(), false, s->hh.operand(), s->x->m, s->x->n, static_cast<int>(s->kp), s->k,
                        s->part_w.p, s->wt.ld, s->s_w, s->hh.inv_scale.p, nullptr, s->x->inv_scale_host,
                        h->cta_group, h->stream));
@@ -195,9 +215,12 @@ static int gemm_xht(nfb_nmf* s) {
 // part_h = W'X   (per split) for the current W planes; row-sharded runs reduce it across ranks
 static int gemm_wtx(nfb_nmf* s, const float** num_out, int* splits_out, int64_t* stride_out) {
     nfb_handle* h = s->h;
+    {
+    GemmTimer timer(h);
     NFB_TRY(gemm_split(s->x->operand(), true, s->wt.operand(), s->x->n, s->x->m, static_cast<int>(s->kp), s->k,
                        s->part_h.p, s->hh.ld, s->s_h, s->wt.inv_scale.p, nullptr, s->x->inv_scale_host,
                        h->cta_group, h->stream));
+    }
     note_launch(1);
     *num_out = s->part_h.p;
     *splits_out = s->s_h;
@@ -378,6 +401,23 @@ int nfb_synchronize(nfb_handle* h) {
 
 int64_t nfb_launch_count(const nfb_handle* h) { return h ? h->launches_last : 0; }
 
+int nfb_profile_gemms(nfb_handle* h, int enable, double* total_ms_out, int64_t* launches_out) {
+    NFB_CHECK(h != nullptr, "handle is NULL");
+    NFB_CUDA(cudaStreamSynchronize(h->stream));
+    double total = 0.0;
+    for (auto& ev : h->gemm_events) {
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, ev.first, ev.second) == cudaSuccess) total += ms;
+        cudaEventDestroy(ev.first);
+        cudaEventDestroy(ev.second);
+    }
+    if (total_ms_out) *total_ms_out = total;
+    if (launches_out) *launches_out = static_cast<int64_t>(h->gemm_events.size());
+    h->gemm_events.clear();
+    h->profiling = enable != 0;
+    return 0;
+}
+
 int nfb_set_comm(nfb_handle* h, void* nccl_comm, void* nccl_allreduce_fn, int rank, int world_size) {
     NFB_CHECK(h != nullptr, "handle is NULL");
     h->comm = nccl_comm;
@@ -434,11 +474,13 @@ int nfb_matrix_from_device(nfb_handle* h, const float* x_dev, int64_t m, int64_t
     NFB_TRY(x->inv_scale.alloc(1, true, h->stream));
     NFB_CUDA(cudaMemsetAsync(h->d_bits.p, 0, sizeof(unsigned int), h->stream));
     NFB_CUDA(cudaMemsetAsync(h->d_scal.p + 4, 0, sizeof(double), h->stream));
+    NFB_CUDA(cudaMemsetAsync(h->d_int.p + 3, 0, sizeof(int), h->stream));
     NFB_TRY(absmax_f32(x_dev, m, n, ld, h->d_bits.p, h->stream));
     NFB_TRY(split_matrix(x_dev, m, n, ld, h->d_bits.p, x->hi.p, x->lo.p, x->ldp, x->inv_scale.p, h->d_scal.p + 4,
-                         h->stream));
+                         h->d_int.p + 3, h->stream));
     NFB_CUDA(cudaMemcpyAsync(h->h_scal + 4, h->d_scal.p + 4, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     NFB_CUDA(cudaMemcpyAsync(&x->inv_scale_host, x->inv_scale.p, sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    NFB_CUDA(cudaMemcpyAsync(&x->has_negative, h->d_int.p + 3, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     NFB_CUDA(cudaStreamSynchronize(h->stream));
     x->sumsq = h->h_scal[4];
     *out = x.release();
@@ -465,6 +507,7 @@ int nfb_matrix_from_host(nfb_handle* h, const float* x_host, int64_t m, int64_t 
     NFB_TRY(stage[1].alloc(chunk_rows * n, false, h->stream));
     NFB_CUDA(cudaMemsetAsync(h->d_bits.p, 0, sizeof(unsigned int), h->stream));
     NFB_CUDA(cudaMemsetAsync(h->d_scal.p + 4, 0, sizeof(double), h->stream));
+    NFB_CUDA(cudaMemsetAsync(h->d_int.p + 3, 0, sizeof(int), h->stream));
     int rc = 0;
     for (int pass = 0; pass < 2 && rc == 0; ++pass) {
         int slot = 0;
@@ -474,12 +517,14 @@ int nfb_matrix_from_host(nfb_handle* h, const float* x_host, int64_t m, int64_t 
                                 h->stream) != cudaSuccess) { set_error("H2D copy of X failed"); rc = 1; break; }
             if (pass == 0) rc = absmax_f32(stage[slot].p, rows, n, n, h->d_bits.p, h->stream);
             else rc = split_matrix(stage[slot].p, rows, n, n, h->d_bits.p, x->hi.p + r0 * x->ldp,
-                                   x->lo.p + r0 * x->ldp, x->ldp, x->inv_scale.p, h->d_scal.p + 4, h->stream);
+                                   x->lo.p + r0 * x->ldp, x->ldp, x->inv_scale.p, h->d_scal.p + 4, h->d_int.p + 3,
+                                   h->stream);
         }
     }
     if (rc != 0) return rc;
     NFB_CUDA(cudaMemcpyAsync(h->h_scal + 4, h->d_scal.p + 4, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     NFB_CUDA(cudaMemcpyAsync(&x->inv_scale_host, x->inv_scale.p, sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    NFB_CUDA(cudaMemcpyAsync(&x->has_negative, h->d_int.p + 3, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     NFB_CUDA(cudaStreamSynchronize(h->stream));
     x->sumsq = h->h_scal[4];
     *out = x.release();
@@ -498,6 +543,12 @@ int nfb_matrix_shape(const nfb_matrix* x, int64_t* m, int64_t* n) {
     NFB_CHECK(x != nullptr, "matrix is NULL");
     if (m) *m = x->m;
     if (n) *n = x->n;
+    return 0;
+}
+
+int nfb_matrix_has_negative(const nfb_matrix* x, int* out) {
+    NFB_CHECK(x != nullptr && out != nullptr, "NULL argument");
+    *out = x->has_negative;
     return 0;
 }
 

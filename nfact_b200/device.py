@@ -19,11 +19,13 @@ _handles: dict = {}
 class Handle:
     """One per (process, device): CUDA stream + scratch owned by the library."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, stream: int | None = None):
+        """``stream``: a cudaStream_t as an integer (e.g. ``torch.cuda.Stream().cuda_stream``) so that
+        the caller's CUDA events see the library's kernels; None -> the library creates its own."""
         self.lib = _lib.load()
         self.device = int(device)
         self._ptr = c_void_p()
-        check(self.lib.nfb_create(self.device, None, byref(self._ptr)))
+        check(self.lib.nfb_create(self.device, c_void_p(stream) if stream else None, byref(self._ptr)))
         self.rank, self.world = 0, 1
 
     @property
@@ -35,6 +37,12 @@ class Handle:
 
     def launch_count(self) -> int:
         return int(self.lib.nfb_launch_count(self._ptr))
+
+    def profile_gemms(self, enable: bool):
+        """(total ms, launches) of the X-streaming GEMMs since the last call; then set the enable flag."""
+        total, count = c_double(), c_int64()
+        check(self.lib.nfb_profile_gemms(self._ptr, int(enable), byref(total), byref(count)))
+        return total.value, count.value
 
     def init_nccl(self, rank: int, world: int, broadcast_bytes) -> None:
         """Create a NCCL communicator inside the library.  ``broadcast_bytes(b: bytes|None) -> bytes``
@@ -105,6 +113,12 @@ class DeviceMatrix:
         out = c_double()
         check(self.handle.lib.nfb_matrix_sumsq(self._ptr, byref(out)))
         return out.value
+
+    @property
+    def has_negative(self) -> bool:
+        out = c_int()
+        check(self.handle.lib.nfb_matrix_has_negative(self._ptr, byref(out)))
+        return bool(out.value)
 
     def matmul_dev(self, trans: bool, b_ptr: int, n_b: int, out_ptr: int, ld_out: int) -> None:
         check(self.handle.lib.nfb_matrix_matmul(self.handle.ptr, self._ptr, int(trans), c_void_p(b_ptr), n_b,

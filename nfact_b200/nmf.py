@@ -125,11 +125,12 @@ class NMF:
                 raise ValueError(f"Expected 2D array, got {X.ndim}D array instead")
             if X.dtype not in (np.float32, np.float64):
                 X = X.astype(np.float64)
-            if X.size and X.min() < 0:
-                raise ValueError("Negative values in data passed to NMF (input X)")
-            x_mean = float(X.mean())
+            # the mean is only needed by the non-custom initialisations
+            x_mean = float(X.mean()) if p["init"] != "custom" else None
             xdev, owns = DeviceMatrix.from_host(X), True
         try:
+            if xdev.has_negative:     # sklearn check_non_negative, evaluated on the device during ingest
+                raise ValueError("Negative values in data passed to NMF (input X)")
             m, n = xdev.shape
             if p["init"] == "custom":
                 for name, arr, shape in (("H", H, (k, n)), ("W", W, (m, k))):
