@@ -58,9 +58,10 @@ int mu_update(float* f, int64_t k, int64_t cols, int64_t ld, const float* num, i
 // one coordinate-descent sweep over all k components for every column j of F [k, cols]
 // (sklearn _cdnmf_fast.pyx with F = W^T):  num = sum_s part[s] - l1, G = gram (+ l2 on the diagonal).
 // violation (fp64, accumulated) and rowmax_bits as above.
+// den [k][ld_part] = G F from the tensor-core denominator GEMM seeds the per-column gradient.
 int cd_sweep(float* f, int64_t k, int64_t cols, int64_t ld, const float* num, int num_splits, int64_t num_stride,
-             int64_t ld_part, const float* gram, float l1, float l2, double* violation, unsigned int* rowmax_bits,
-             cudaStream_t stream);
+             const float* den, int64_t ld_part, const float* gram, float l1, float l2, double* violation,
+             unsigned int* rowmax_bits, cudaStream_t stream);
 // *out += sum_{t<k, j<cols} a[t][j] * (sum_s b[s][t][j])        (fp64 accumulation)
 int dot_partials(const float* a, int64_t lda, const float* b, int splits, int64_t b_stride, int64_t ldb, int64_t k,
                  int64_t cols, double* out, cudaStream_t stream);

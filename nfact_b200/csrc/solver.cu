@@ -286,10 +286,11 @@ static int cd_iteration(nfb_nmf* s, double* violation_out) {
     NFB_CUDA(cudaMemsetAsync(h->d_scal.p + 2, 0, 2 * sizeof(double), h->stream));
     if (!s->p1_valid) NFB_TRY(gemm_xht(s));
     // ---- W half-step ----
+    NFB_TRY(gemm_den(s, s->wt, s->gh));  // G_H W^T seeds the per-row gradient
     NFB_CUDA(cudaMemsetAsync(s->wt.rowmax.p, 0, sizeof(unsigned int) * s->kp, h->stream));
     NFB_TRY(cd_sweep(s->wt.f.p, s->k, s->x->m, s->wt.ld, s->part_w.p, s->s_w, static_cast<int64_t>(s->k) * s->wt.ld,
-                     s->wt.ld, s->gh.f.p, static_cast<float>(p.l1_reg_W), static_cast<float>(p.l2_reg_W),
-                     h->d_scal.p + 2, s->wt.rowmax.p, h->stream));
+                     s->part_den.p, s->wt.ld, s->gh.f.p, static_cast<float>(p.l1_reg_W),
+                     static_cast<float>(p.l2_reg_W), h->d_scal.p + 2, s->wt.rowmax.p, h->stream));
     note_launch(1);
     s->p1_valid = false;
     NFB_TRY(refresh_planes(s->wt, s->wt.f.p, nullptr, false, h->stream));
@@ -299,9 +300,10 @@ static int cd_iteration(nfb_nmf* s, double* violation_out) {
     int num_splits;
     int64_t num_stride;
     NFB_TRY(gemm_wtx(s, &num, &num_splits, &num_stride));
+    NFB_TRY(gemm_den(s, s->hh, s->gw));
     NFB_CUDA(cudaMemsetAsync(s->hh.rowmax.p, 0, sizeof(unsigned int) * s->kp, h->stream));
-    NFB_TRY(cd_sweep(s->hh.f.p, s->k, s->x->n, s->hh.ld, num, num_splits, num_stride, s->hh.ld, s->gw.f.p,
-                     static_cast<float>(p.l1_reg_H), static_cast<float>(p.l2_reg_H), h->d_scal.p + 3,
+    NFB_TRY(cd_sweep(s->hh.f.p, s->k, s->x->n, s->hh.ld, num, num_splits, num_stride, s->part_den.p, s->hh.ld,
+                     s->gw.f.p, static_cast<float>(p.l1_reg_H), static_cast<float>(p.l2_reg_H), h->d_scal.p + 3,
                      s->hh.rowmax.p, h->stream));
     note_launch(1);
     NFB_TRY(refresh_planes(s->hh, s->hh.f.p, nullptr, false, h->stream));

@@ -23,82 +23,45 @@ __global__ void reduce_partials_kernel(const float* __restrict__ part, int split
     }
 }
 
-// sklearn/decomposition/_nmf.py:521-626 and :629-723 (beta_loss == 2, gamma == 1), one element per lane.
+// sklearn/decomposition/_nmf.py:521-626 and :629-723 (beta_loss == 2, gamma == 1); four consecutive
+// columns per thread (128-bit loads: every buffer has a leading dimension that is a multiple of 8).
+__device__ __forceinline__ float mu_one(float old, float numerator, float denominator, float l1, float l2) {
+    if (l1 > 0.0f) denominator = __fadd_rn(denominator, l1);
+    if (l2 > 0.0f) denominator = __fadd_rn(denominator, __fmul_rn(l2, old));
+    if (denominator == 0.0f) denominator = kEpsF32;
+    return __fmul_rn(old, __fdiv_rn(numerator, denominator));
+}
+
 __global__ void mu_update_kernel(float* __restrict__ f, int64_t cols, int64_t ld, const float* __restrict__ num,
                                  int num_splits, int64_t num_stride, const float* __restrict__ den, int den_splits,
                                  int64_t den_stride, int64_t ld_part, float l1, float l2,
                                  unsigned int* __restrict__ rowmax_bits) {
     const int64_t t = blockIdx.y;
     float vmax = 0.0f;
-    for (int64_t j = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; j < cols;
-         j += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        float numerator = 0.0f;
-        for (int s = 0; s < num_splits; ++s) numerator += num[s * num_stride + t * ld_part + j];
-        float denominator = 0.0f;
-        for (int s = 0; s < den_splits; ++s) denominator += den[s * den_stride + t * ld_part + j];
-        const float old = f[t * ld + j];
-        if (l1 > 0.0f) denominator = __fadd_rn(denominator, l1);
-        if (l2 > 0.0f) denominator = __fadd_rn(denominator, __fmul_rn(l2, old));
-        if (denominator == 0.0f) denominator = kEpsF32;
-        const float ratio = __fdiv_rn(numerator, denominator);
-        const float updated = __fmul_rn(old, ratio);
-        f[t * ld + j] = updated;
-        vmax = fmaxf(vmax, fabsf(updated));
+    const int64_t groups = (cols + 3) / 4;
+    for (int64_t g = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; g < groups;
+         g += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t j = g * 4;
+        float4 numerator = make_float4(0.f, 0.f, 0.f, 0.f), denominator = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int s = 0; s < num_splits; ++s) {
+            const float4 v = __ldcs(reinterpret_cast<const float4*>(num + s * num_stride + t * ld_part + j));
+            numerator.x += v.x; numerator.y += v.y; numerator.z += v.z; numerator.w += v.w;
+        }
+        for (int s = 0; s < den_splits; ++s) {
+            const float4 v = __ldcs(reinterpret_cast<const float4*>(den + s * den_stride + t * ld_part + j));
+            denominator.x += v.x; denominator.y += v.y; denominator.z += v.z; denominator.w += v.w;
+        }
+        float4 cur = *reinterpret_cast<const float4*>(f + t * ld + j);
+        // columns >= cols are padding: partial buffers are not written there, keep the zeros
+        cur.x = mu_one(cur.x, numerator.x, denominator.x, l1, l2);
+        cur.y = (j + 1 < cols) ? mu_one(cur.y, numerator.y, denominator.y, l1, l2) : 0.0f;
+        cur.z = (j + 2 < cols) ? mu_one(cur.z, numerator.z, denominator.z, l1, l2) : 0.0f;
+        cur.w = (j + 3 < cols) ? mu_one(cur.w, numerator.w, denominator.w, l1, l2) : 0.0f;
+        *reinterpret_cast<float4*>(f + t * ld + j) = cur;
+        vmax = fmaxf(fmaxf(vmax, fmaxf(fabsf(cur.x), fabsf(cur.y))), fmaxf(fabsf(cur.z), fabsf(cur.w)));
     }
     vmax = warp_max(vmax);
     if ((threadIdx.x & 31) == 0 && vmax > 0.0f) atomicMax(&rowmax_bits[t], __float_as_uint(vmax));
-}
-
-// sklearn/decomposition/_cdnmf_fast.pyx:8-38 with the roles transposed: thread j owns column j of
-// F [k, cols] (= row j of sklearn's W) and walks the components t = 0..k-1 in order, so the
-// Gauss-Seidel dependence across components is kept exactly; columns are independent.
-//   grad = -num[t][j] + sum_r G[t][r] F[r][j]          (G carries l2 on its diagonal, num carries -l1)
-//   pg   = F[t][j] == 0 ? min(0, grad) : grad ;  violation += |pg|
-//   F[t][j] = max(F[t][j] - grad / G[t][t], 0)   if G[t][t] != 0
-template <int kTJ>
-__global__ void __launch_bounds__(kTJ)
-cd_sweep_kernel(float* __restrict__ f, int k, int64_t cols, int64_t ld, const float* __restrict__ num,
-                int num_splits, int64_t num_stride, int64_t ld_part, const float* __restrict__ gram, int ldg,
-                float l1, float l2, double* __restrict__ violation, unsigned int* __restrict__ rowmax_bits) {
-    extern __shared__ float fs[];  // [k][kTJ]
-    __shared__ double scratch[32];
-    const int tid = threadIdx.x;
-    const int64_t j = blockIdx.x * static_cast<int64_t>(kTJ) + tid;
-    const bool active = j < cols;
-    for (int r = 0; r < k; ++r) fs[r * kTJ + tid] = active ? f[r * ld + j] : 0.0f;
-    float viol = 0.0f;
-    const int k4 = k & ~3;
-    for (int t = 0; t < k; ++t) {
-        const float* grow = gram + static_cast<int64_t>(t) * ldg;
-        float g0 = 0.0f, g1 = 0.0f, g2 = 0.0f, g3 = 0.0f;
-        for (int r = 0; r < k4; r += 4) {
-            const float4 gv = __ldg(reinterpret_cast<const float4*>(grow + r));
-            g0 = fmaf(gv.x, fs[(r + 0) * kTJ + tid], g0);
-            g1 = fmaf(gv.y, fs[(r + 1) * kTJ + tid], g1);
-            g2 = fmaf(gv.z, fs[(r + 2) * kTJ + tid], g2);
-            g3 = fmaf(gv.w, fs[(r + 3) * kTJ + tid], g3);
-        }
-        for (int r = k4; r < k; ++r) g0 = fmaf(__ldg(grow + r), fs[r * kTJ + tid], g0);
-        const float cur = fs[t * kTJ + tid];
-        float numer = 0.0f;
-        if (active)
-            for (int s = 0; s < num_splits; ++s) numer += num[s * num_stride + t * ld_part + j];
-        numer -= l1;
-        const float hess = __ldg(grow + t) + l2;
-        float grad = (g0 + g1) + (g2 + g3);
-        grad = fmaf(l2, cur, grad) - numer;
-        const float pg = (cur == 0.0f) ? fminf(0.0f, grad) : grad;
-        viol += fabsf(pg);
-        if (hess != 0.0f) fs[t * kTJ + tid] = fmaxf(cur - grad / hess, 0.0f);
-    }
-    for (int t = 0; t < k; ++t) {
-        const float v = active ? fs[t * kTJ + tid] : 0.0f;
-        if (active) f[t * ld + j] = v;
-        const float m = warp_max(v);
-        if ((tid & 31) == 0 && m > 0.0f) atomicMax(&rowmax_bits[t], __float_as_uint(m));
-    }
-    const double total = block_sum(active ? static_cast<double>(viol) : 0.0, scratch);
-    if (tid == 0 && total != 0.0) atomicAdd(violation, total);
 }
 
 __global__ void dot_partials_kernel(const float* __restrict__ a, int64_t lda, const float* __restrict__ b, int splits,
@@ -220,32 +183,10 @@ int mu_update(float* f, int64_t k, int64_t cols, int64_t ld, const float* num, i
               const float* den, int den_splits, int64_t den_stride, int64_t ld_part, float l1, float l2,
               unsigned int* rowmax_bits, cudaStream_t stream) {
     if (k * cols == 0) return 0;
-    mu_update_kernel<<<dim3(col_blocks(cols, 256, 1024), static_cast<unsigned>(k)), 256, 0, stream>>>(
+    mu_update_kernel<<<dim3(col_blocks(cols, 256 * 4, 1024), static_cast<unsigned>(k)), 256, 0, stream>>>(
         f, cols, ld, num, num_splits, num_stride, den, den_splits, den_stride, ld_part, l1, l2, rowmax_bits);
     NFB_CUDA(cudaGetLastError());
     return 0;
-}
-
-int cd_sweep(float* f, int64_t k, int64_t cols, int64_t ld, const float* num, int num_splits, int64_t num_stride,
-             int64_t ld_part, const float* gram, float l1, float l2, double* violation, unsigned int* rowmax_bits,
-             cudaStream_t stream) {
-    if (k * cols == 0) return 0;
-    const int ldg = static_cast<int>(round_up64(k, 16));
-    auto run = [&](auto tj_tag) -> int {
-        constexpr int TJ = decltype(tj_tag)::value;
-        const size_t smem = static_cast<size_t>(k) * TJ * sizeof(float);
-        auto kernel = cd_sweep_kernel<TJ>;
-        NFB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        kernel<<<static_cast<unsigned>(ceil_div64(cols, TJ)), TJ, smem, stream>>>(
-            f, static_cast<int>(k), cols, ld, num, num_splits, num_stride, ld_part, gram, ldg, l1, l2, violation,
-            rowmax_bits);
-        NFB_CUDA(cudaGetLastError());
-        return 0;
-    };
-    if (k * 128 * 4 <= 110 * 1024) return run(std::integral_constant<int, 128>{});
-    if (k * 64 * 4 <= 220 * 1024) return run(std::integral_constant<int, 64>{});
-    NFB_CHECK(k * 32 * 4 <= 220 * 1024, "n_components too large for the coordinate-descent kernel");
-    return run(std::integral_constant<int, 32>{});
 }
 
 int dot_partials(const float* a, int64_t lda, const float* b, int splits, int64_t b_stride, int64_t ldb, int64_t k,
