@@ -117,6 +117,123 @@ cd_sweep_warp_kernel(float* __restrict__ f, int k, int64_t cols, int64_t ld, con
     if (threadIdx.x == 0 && total != 0.0) atomicAdd(violation, total);
 }
 
+
+// ---- fast path: Gram matrix resident in shared memory (k <= ~216) ----------------------------------
+// One CTA per SM, 16 warps, one column per warp at a time.  Per component step the dependent chain is
+// shfl -> multiply by the precomputed 1/hess -> clamp -> rank-1 update from smem, ~20 instructions.
+constexpr int kFastWarps = 16;
+constexpr int kFastTile = 16;
+
+template <int KPL>
+__global__ void __launch_bounds__(kFastWarps * 32, 1)
+cd_sweep_smem_kernel(float* __restrict__ f, int k, int64_t cols, int64_t ld, const float* __restrict__ num,
+                     int num_splits, int64_t num_stride, const float* __restrict__ den, int64_t ld_part,
+                     const float* __restrict__ gram, int ldg, float l1, float l2, double* __restrict__ violation,
+                     unsigned int* __restrict__ rowmax_bits) {
+    extern __shared__ float sm[];
+    __shared__ double scratch[32];
+    const int kpad = k | 1;
+    constexpr int kRow = 32 * KPL;                        // zero-padded Gram row: no bounds predicate
+    float* gram_s = sm;                                   // [k][kRow]
+    float* invh_s = gram_s + k * kRow;                    // [k]  1 / (G[t][t] + l2), 0 when the hessian is 0
+    float* g_s = invh_s + k;                              // [kFastTile][kpad]
+    float* f_s = g_s + kFastTile * kpad;                  // [kFastTile][kpad]
+    unsigned int* max_s = reinterpret_cast<unsigned int*>(f_s + kFastTile * kpad);  // [k]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int idx = threadIdx.x; idx < k * kRow; idx += blockDim.x) {
+        const int t = idx / kRow, u = idx - t * kRow;
+        gram_s[idx] = u < k ? gram[static_cast<int64_t>(t) * ldg + u] : 0.0f;
+    }
+    for (int u = threadIdx.x; u < k; u += blockDim.x) {
+        const float hess = gram[static_cast<int64_t>(u) * ldg + u] + l2;
+        invh_s[u] = hess != 0.0f ? 1.0f / hess : 0.0f;
+        max_s[u] = 0u;
+    }
+    float viol = 0.0f;
+    const int64_t ntiles = (cols + kFastTile - 1) / kFastTile;
+
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t j0 = tile * kFastTile;
+        __syncthreads();
+        // ---- phase 1: half-warps read 16 consecutive columns of one component row ---------------------
+        {
+            const int half = lane >> 4, c = lane & 15;
+            const int64_t j = j0 + c;
+            const bool active = j < cols;
+#pragma unroll 4
+            for (int u = warp * 2 + half; u < k; u += kFastWarps * 2) {
+                float fv = 0.0f, gv = 0.0f;
+                if (active) {
+                    fv = f[static_cast<int64_t>(u) * ld + j];
+                    float nv = 0.0f;
+                    for (int s = 0; s < num_splits; ++s)
+                        nv += __ldcs(num + s * num_stride + static_cast<int64_t>(u) * ld_part + j);
+                    const float dv = __ldcs(den + static_cast<int64_t>(u) * ld_part + j);
+                    gv = fmaf(l2, fv, dv) - (nv - l1);
+                }
+                g_s[c * kpad + u] = gv;
+                f_s[c * kpad + u] = fv;
+            }
+        }
+        __syncthreads();
+        // ---- phase 2: one warp = one column ------------------------------------------------------------
+        if (j0 + warp < cols) {
+            float g[KPL], fv[KPL];
+#pragma unroll
+            for (int i = 0; i < KPL; ++i) {
+                const int u = lane + 32 * i;
+                g[i] = u < k ? g_s[warp * kpad + u] : 0.0f;
+                fv[i] = u < k ? f_s[warp * kpad + u] : 0.0f;
+            }
+#pragma unroll
+            for (int i = 0; i < KPL; ++i) {
+                const int t_end = min(32, k - 32 * i);
+                for (int o = 0; o < t_end; ++o) {
+                    const int t = 32 * i + o;
+                    const float gt = __shfl_sync(0xffffffffu, g[i], o);
+                    const float ft = __shfl_sync(0xffffffffu, fv[i], o);
+                    const float inv = invh_s[t];
+                    viol += fabsf((ft == 0.0f) ? fminf(0.0f, gt) : gt);
+                    const float fn = fmaxf(fmaf(-gt, inv, ft), 0.0f);
+                    const float delta = (inv != 0.0f) ? fn - ft : 0.0f;
+                    if (delta != 0.0f) {  // warp-uniform
+                        const float* grow = gram_s + t * kRow + lane;
+#pragma unroll
+                        for (int i2 = i; i2 < KPL; ++i2) g[i2] = fmaf(delta, grow[32 * i2], g[i2]);
+                        if (lane == o) fv[i] = fn;
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < KPL; ++i) {
+                const int u = lane + 32 * i;
+                if (u < k) f_s[warp * kpad + u] = fv[i];
+            }
+        }
+        __syncthreads();
+        // ---- phase 3: store + per-row maxima --------------------------------------------------------------
+        {
+            const int half = lane >> 4, c = lane & 15;
+            const int64_t j = j0 + c;
+            const bool active = j < cols;
+            for (int u = warp * 2 + half; u < k; u += kFastWarps * 2) {
+                const float v = active ? f_s[c * kpad + u] : 0.0f;
+                if (active) f[static_cast<int64_t>(u) * ld + j] = v;
+                float m = v;
+                const unsigned half_mask = 0xFFFFu << (16 * half);
+#pragma unroll
+                for (int off = 8; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(half_mask, m, off));
+                if (c == 0 && m > 0.0f) atomicMax(&max_s[u], __float_as_uint(m));
+            }
+        }
+    }
+    __syncthreads();
+    for (int u = threadIdx.x; u < k; u += blockDim.x)
+        if (max_s[u] != 0u) atomicMax(&rowmax_bits[u], max_s[u]);
+    const double total = block_sum(lane == 0 ? static_cast<double>(viol) : 0.0, scratch);
+    if (threadIdx.x == 0 && total != 0.0) atomicAdd(violation, total);
+}
+
 }  // namespace
 
 int cd_sweep(float* f, int64_t k, int64_t cols, int64_t ld, const float* num, int num_splits, int64_t num_stride,
@@ -126,6 +243,29 @@ int cd_sweep(float* f, int64_t k, int64_t cols, int64_t ld, const float* num, in
     NFB_CHECK(k <= 256, "n_components > 256 is not supported by the coordinate-descent kernel");
     const int ldg = static_cast<int>(round_up64(k, 16));
     const int kpad = static_cast<int>(k) | 1;
+    const int kpl_fast = k <= 32 ? 1 : k <= 64 ? 2 : k <= 128 ? 4 : 7;
+    const size_t smem_fast = (static_cast<size_t>(k) * 32 * kpl_fast + 2 * k +
+                              static_cast<size_t>(2) * kFastTile * kpad) * sizeof(float);
+    if (k <= 32 * kpl_fast && smem_fast <= 224 * 1024) {
+        const int64_t ntiles_fast = ceil_div64(cols, kFastTile);
+        const int grid_fast = static_cast<int>(std::min<int64_t>(ntiles_fast, sm_count()));
+#define NFB_CD_FAST(KPL)                                                                                         \
+    do {                                                                                                         \
+        auto kernel = cd_sweep_smem_kernel<KPL>;                                                                 \
+        NFB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,                       \
+                                      static_cast<int>(smem_fast)));                                             \
+        kernel<<<grid_fast, kFastWarps * 32, smem_fast, stream>>>(f, static_cast<int>(k), cols, ld, num,         \
+                                                                  num_splits, num_stride, den, ld_part, gram,    \
+                                                                  ldg, l1, l2, violation, rowmax_bits);          \
+    } while (0)
+        if (k <= 32) NFB_CD_FAST(1);
+        else if (k <= 64) NFB_CD_FAST(2);
+        else if (k <= 128) NFB_CD_FAST(4);
+        else NFB_CD_FAST(7);
+#undef NFB_CD_FAST
+        NFB_CUDA(cudaGetLastError());
+        return 0;
+    }
     const size_t smem = (static_cast<size_t>(2) * kTileCols * kpad + k) * sizeof(float);
     const int64_t ntiles = ceil_div64(cols, kTileCols);
     const int blocks_per_sm = std::max<int>(1, std::min<int>(4, static_cast<int>((200 * 1024) / (smem + 1024))));
