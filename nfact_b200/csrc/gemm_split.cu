@@ -13,10 +13,16 @@
 // reached from NFACT/decomp/decomposition/sso/nmfsso.py:54-56) and the k x k Gram / denominator
 // products around them (:375, :550, :632).
 //
-// Kernel shape: persistent, warp specialised (1 TMA producer thread, 1 MMA issuer thread, 4 epilogue
-// warps), multi-stage smem ring fed by TMA with 128B swizzle, double-buffered TMEM accumulator,
+// Kernel shape: persistent, warp specialised (1 TMA producer thread, 1 MMA issuer thread, 8 epilogue
+// warps), multi-stage smem ring fed by TMA with 128B swizzle, two TMEM accumulator stages,
 // split-K over `splits` deterministic partial outputs (no atomics), optional 2-CTA pairs
 // (cta_group::2: M = 256 per pair, each CTA stages half of B).
+//
+// Accumulation promotion: the tensor core truncates when it adds into the fp32 TMEM accumulator
+// (measured on B200: about -7e-8 relative per 64-wide K block of chain length for non-negative data,
+// -1.3e-4 over K = 110k), so a TMEM chain is at most kChunkKB K blocks long; the epilogue warps drain
+// every finished chain into fp32 registers with round-to-nearest adds while the issuer fills the other
+// TMEM stage (the FP8-style "promotion" scheme, applied here to keep fp32-faithful sums).
 #include <algorithm>
 #include <cstdlib>
 
@@ -33,8 +39,10 @@ constexpr int kUmmaK = 16;         // K per tcgen05.mma for 16-bit inputs
 constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KB per plane
 constexpr int kTmemCols = 512;
 constexpr int kAccStageCols = 256;
-constexpr int kNumThreads = 256;
+constexpr int kNumEpilogueWarps = 8;
+constexpr int kNumThreads = 128 + kNumEpilogueWarps * 32;
 constexpr int kMaxStages = 8;
+constexpr int kChunkKB = 8;        // K blocks per TMEM accumulation chain (512 K elements)
 
 struct GemmArgs {
     float* out;              // [splits][n_store rows][ld_out]   (component-major: D^T)
@@ -77,7 +85,9 @@ __device__ __forceinline__ uint32_t make_idesc(int m, int n, int a_mn_major) {
     return d;
 }
 
-template <int kAMajorMN, int kCtaGroup>
+// kNch = 16-column accumulator chunks owned by one epilogue thread (two warps share a TMEM lane quarter
+// and split the N columns between them): N <= 32 * kNch.
+template <int kAMajorMN, int kCtaGroup, int kNch>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                   const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
@@ -111,7 +121,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tmem_full_bar[a], 1);
-            mbar_init(&tmem_empty_bar[a], kCtaGroup * 128);
+            mbar_init(&tmem_empty_bar[a], kCtaGroup * kNumEpilogueWarps * 32);
         }
         fence_barrier_init();
     }
@@ -178,73 +188,97 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
         //    MN-major -> LBO = next 64-wide M atom (8 KB),  SBO = 8 K-rows * 128 B, K step = 16 rows * 128 B
         const uint32_t a_lbo = kAMajorMN ? kBlockK * 128 : 0;
         const uint32_t a_kstep = kAMajorMN ? kUmmaK * 128 : kUmmaK * 2;
-        uint32_t iter = 0;
-        for (int tile = worker; tile < num_tiles; tile += num_workers, ++iter) {
+        uint32_t chain = 0;  // running index of TMEM accumulation chains (stage = chain & 1)
+        for (int tile = worker; tile < num_tiles; tile += num_workers) {
             const int ks = tile / args.m_blocks;
             const int kb0 = static_cast<int>(static_cast<long long>(ks) * args.num_kb / args.splits);
             const int kb1 = static_cast<int>(static_cast<long long>(ks + 1) * args.num_kb / args.splits);
-            const uint32_t as = iter & 1, aphase = (iter >> 1) & 1;
-            mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + as * kAccStageCols;
-            for (int kb = kb0; kb < kb1; ++kb) {
-                mbar_wait(&full_bar[stage], phase);
+            for (int kc0 = kb0; kc0 < kb1; kc0 += kChunkKB, ++chain) {
+                const int kc1 = min(kc0 + kChunkKB, kb1);
+                const uint32_t as = chain & 1, aphase = (chain >> 1) & 1;
+                mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
                 tc_fence_after();
-                const uint32_t sa_hi = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
-                const uint32_t sa_lo = sa_hi + kATileBytes;
-                const uint32_t sb_hi = sa_lo + kATileBytes;
-                const uint32_t sb_lo = sb_hi + args.b_tile_bytes;
+                const uint32_t d_tmem = tmem_base + as * kAccStageCols;
+                for (int kb = kc0; kb < kc1; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa_hi = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
+                    const uint32_t sa_lo = sa_hi + kATileBytes;
+                    const uint32_t sb_hi = sa_lo + kATileBytes;
+                    const uint32_t sb_lo = sb_hi + args.b_tile_bytes;
 #pragma unroll
-                for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-                    const uint64_t da_hi = make_smem_desc(sa_hi + k * a_kstep, a_lbo, 1024);
-                    const uint64_t da_lo = make_smem_desc(sa_lo + k * a_kstep, a_lbo, 1024);
-                    const uint64_t db_hi = make_smem_desc(sb_hi + k * kUmmaK * 2, 0, 1024);
-                    const uint64_t db_lo = make_smem_desc(sb_lo + k * kUmmaK * 2, 0, 1024);
-                    umma_f16<kCtaGroup>(d_tmem, da_hi, db_hi, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-                    umma_f16<kCtaGroup>(d_tmem, da_lo, db_hi, idesc, 1u);
-                    umma_f16<kCtaGroup>(d_tmem, da_hi, db_lo, idesc, 1u);
+                    for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                        const uint64_t da_hi = make_smem_desc(sa_hi + k * a_kstep, a_lbo, 1024);
+                        const uint64_t da_lo = make_smem_desc(sa_lo + k * a_kstep, a_lbo, 1024);
+                        const uint64_t db_hi = make_smem_desc(sb_hi + k * kUmmaK * 2, 0, 1024);
+                        const uint64_t db_lo = make_smem_desc(sb_lo + k * kUmmaK * 2, 0, 1024);
+                        umma_f16<kCtaGroup>(d_tmem, da_hi, db_hi, idesc, (kb > kc0 || k > 0) ? 1u : 0u);
+                        umma_f16<kCtaGroup>(d_tmem, da_lo, db_hi, idesc, 1u);
+                        umma_f16<kCtaGroup>(d_tmem, da_hi, db_lo, idesc, 1u);
+                    }
+                    umma_commit<kCtaGroup>(&empty_bar[stage]);
+                    if (kb == kc1 - 1) umma_commit<kCtaGroup>(&tmem_full_bar[as]);
+                    advance();
                 }
-                umma_commit<kCtaGroup>(&empty_bar[stage]);
-                if (kb == kb1 - 1) umma_commit<kCtaGroup>(&tmem_full_bar[as]);
-                advance();
             }
         }
       }
       __syncwarp();
     } else if (warp_idx >= 4) {
-        // =========================== epilogue: TMEM -> registers -> global ======================
-        const uint32_t quarter = warp_idx & 3;
+        // ====== epilogue: drain every chain TMEM -> fp32 registers (RN adds), store once per tile ======
+        const uint32_t ewarp = warp_idx - 4;
+        const uint32_t quarter = warp_idx & 3;          // TMEM lanes this warp may touch
+        const uint32_t col_half = ewarp >> 2;           // which half of the N columns
         const uint32_t row = quarter * 32 + lane_idx;
-        uint32_t iter = 0;
-        for (int tile = worker; tile < num_tiles; tile += num_workers, ++iter) {
+        const int nch_total = args.n_umma >> 4;
+        const int nch_first = (nch_total + 1) >> 1;
+        const int ch0 = col_half == 0 ? 0 : nch_first;                       // first 16-col chunk
+        const int nch = col_half == 0 ? nch_first : nch_total - nch_first;   // chunks owned (<= kNch)
+        uint32_t chain = 0;
+        for (int tile = worker; tile < num_tiles; tile += num_workers) {
             const int ks = tile / args.m_blocks, mb = tile % args.m_blocks;
-            const uint32_t as = iter & 1, aphase = (iter >> 1) & 1;
-            mbar_wait(&tmem_full_bar[as], aphase);
-            tc_fence_after();
-            const long long m_row = static_cast<long long>(mb * kCtaGroup + static_cast<int>(cta_rank)) * kBlockM + row;
-            const bool row_ok = m_row < args.m_total;
-            float* outp = args.out + static_cast<long long>(ks) * args.split_stride + m_row;
-            const float rs = (row_ok && args.row_scale) ? __ldg(args.row_scale + m_row) * args.scale : args.scale;
-            for (int c0 = 0; c0 < args.n_umma; c0 += 32) {
-                uint32_t v[32];
-                const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + as * kAccStageCols + c0;
-                const int ncol = (c0 + 32 <= args.n_umma) ? 32 : 16;
-                if (ncol == 32) tmem_ld_32x32b_x32(taddr, v); else tmem_ld_32x32b_x16(taddr, v);
-                tmem_ld_wait();
-                if (row_ok) {
+            const int kb0 = static_cast<int>(static_cast<long long>(ks) * args.num_kb / args.splits);
+            const int kb1 = static_cast<int>(static_cast<long long>(ks + 1) * args.num_kb / args.splits);
+            float acc[kNch * 16];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int col = c0 + j;
-                        if (j < ncol && col < args.n_store) {
-                            const float cs = args.col_scale ? __ldg(args.col_scale + col) : 1.0f;
-                            outp[static_cast<long long>(col) * args.ld_out] = (__uint_as_float(v[j]) * cs) * rs;
+            for (int i = 0; i < kNch * 16; ++i) acc[i] = 0.0f;
+            for (int kc0 = kb0; kc0 < kb1; kc0 += kChunkKB, ++chain) {
+                const uint32_t as = chain & 1, aphase = (chain >> 1) & 1;
+                mbar_wait(&tmem_full_bar[as], aphase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + as * kAccStageCols + ch0 * 16;
+#pragma unroll
+                for (int c = 0; c < kNch; ++c) {
+                    if (c < nch) {  // warp-uniform
+                        uint32_t v[32];
+                        tmem_ld_32x32b_x16(taddr + c * 16, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) acc[c * 16 + j] = __fadd_rn(acc[c * 16 + j], __uint_as_float(v[j]));
+                    }
+                }
+                tc_fence_before();
+                if constexpr (kCtaGroup == 2) mbar_arrive_cluster(&tmem_empty_bar[as], 0);
+                else mbar_arrive(&tmem_empty_bar[as]);
+            }
+            const long long m_row = static_cast<long long>(mb * kCtaGroup + static_cast<int>(cta_rank)) * kBlockM + row;
+            if (m_row < args.m_total) {
+                float* outp = args.out + static_cast<long long>(ks) * args.split_stride + m_row;
+                const float rs = args.row_scale ? __ldg(args.row_scale + m_row) * args.scale : args.scale;
+#pragma unroll
+                for (int c = 0; c < kNch; ++c) {
+                    if (c < nch) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const int col = (ch0 + c) * 16 + j;
+                            if (col < args.n_store) {
+                                const float cs = args.col_scale ? __ldg(args.col_scale + col) : 1.0f;
+                                outp[static_cast<long long>(col) * args.ld_out] = (acc[c * 16 + j] * cs) * rs;
+                            }
                         }
                     }
                 }
             }
-            tc_fence_before();
-            if constexpr (kCtaGroup == 2) mbar_arrive_cluster(&tmem_empty_bar[as], 0);
-            else mbar_arrive(&tmem_empty_bar[as]);
         }
     }
 
@@ -287,16 +321,23 @@ int make_plane_map(CUtensorMap* tm, const void* base, int64_t rows, int64_t cols
     return 0;
 }
 
-template <int kAMajorMN, int kCtaGroup>
-int launch(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
-           const GemmArgs& args, int grid, size_t smem_bytes, cudaStream_t stream) {
-    auto kernel = gemm_split_kernel<kAMajorMN, kCtaGroup>;
-    NFB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes)));
+struct Launch {
+    const CUtensorMap *a_hi, *a_lo, *b_hi, *b_lo;
+    const GemmArgs* args;
+    int grid;
+    size_t smem_bytes;
+    cudaStream_t stream;
+};
+
+template <int kAMajorMN, int kCtaGroup, int kNch>
+int launch(const Launch& l) {
+    auto kernel = gemm_split_kernel<kAMajorMN, kCtaGroup, kNch>;
+    NFB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(l.smem_bytes)));
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid);
+    cfg.gridDim = dim3(l.grid);
     cfg.blockDim = dim3(kNumThreads);
-    cfg.dynamicSmemBytes = smem_bytes;
-    cfg.stream = stream;
+    cfg.dynamicSmemBytes = l.smem_bytes;
+    cfg.stream = l.stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = kCtaGroup;
@@ -304,8 +345,16 @@ int launch(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    NFB_CUDA(cudaLaunchKernelEx(&cfg, kernel, a_hi, a_lo, b_hi, b_lo, args));
+    NFB_CUDA(cudaLaunchKernelEx(&cfg, kernel, *l.a_hi, *l.a_lo, *l.b_hi, *l.b_lo, *l.args));
     return 0;
+}
+
+template <int kAMajorMN, int kCtaGroup>
+int launch_nch(const Launch& l, int nch_per_thread) {
+    if (nch_per_thread <= 2) return launch<kAMajorMN, kCtaGroup, 2>(l);
+    if (nch_per_thread <= 4) return launch<kAMajorMN, kCtaGroup, 4>(l);
+    if (nch_per_thread <= 7) return launch<kAMajorMN, kCtaGroup, 7>(l);
+    return launch<kAMajorMN, kCtaGroup, 8>(l);
 }
 
 }  // namespace
@@ -324,7 +373,7 @@ int gemm_pick_splits(int64_t m_total, int64_t k_total, int cta_group) {
     const int64_t m_blocks = ceil_div64(m_total, static_cast<int64_t>(kBlockM) * cta_group);
     const int64_t num_kb = ceil_div64(k_total, kBlockK);
     const int64_t workers = sm_count() / cta_group;
-    // Aim for >= 4 waves of equal tiles; keep every split at least 4 K blocks long.
+    // Aim for full waves of equal tiles; keep every split at least 4 K blocks long.
     int64_t best = 1;
     double best_eff = 0.0;
     const int64_t max_splits = std::max<int64_t>(1, std::min<int64_t>(num_kb / 4, 64));
@@ -386,14 +435,15 @@ int gemm_split(const GemmOperand& a, bool a_is_mn_major, const GemmOperand& b, i
 
     const int64_t tiles = static_cast<int64_t>(args.m_blocks) * splits;
     int workers = static_cast<int>(std::min<int64_t>(tiles, sm_count() / cta_group));
-    const int grid = workers * cta_group;
 
+    Launch l{&tm_a_hi, &tm_a_lo, &tm_b_hi, &tm_b_lo, &args, workers * cta_group, smem_bytes, stream};
+    const int nch_per_thread = ((n_umma >> 4) + 1) >> 1;
     if (a_is_mn_major) {
-        if (cta_group == 2) return launch<1, 2>(tm_a_hi, tm_a_lo, tm_b_hi, tm_b_lo, args, grid, smem_bytes, stream);
-        return launch<1, 1>(tm_a_hi, tm_a_lo, tm_b_hi, tm_b_lo, args, grid, smem_bytes, stream);
+        if (cta_group == 2) return launch_nch<1, 2>(l, nch_per_thread);
+        return launch_nch<1, 1>(l, nch_per_thread);
     }
-    if (cta_group == 2) return launch<0, 2>(tm_a_hi, tm_a_lo, tm_b_hi, tm_b_lo, args, grid, smem_bytes, stream);
-    return launch<0, 1>(tm_a_hi, tm_a_lo, tm_b_hi, tm_b_lo, args, grid, smem_bytes, stream);
+    if (cta_group == 2) return launch_nch<0, 2>(l, nch_per_thread);
+    return launch_nch<0, 1>(l, nch_per_thread);
 }
 
 }  // namespace nfb
