@@ -32,6 +32,9 @@ WORKLOADS = {
     "C2": (29696, 60000, 100, 0.05),
     "C3": (59412, 110000, 200, 0.05),
 }
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of gemm_split_kernel from the ncu --set full capture
+# of this same command (profiles/r01_ncu_full_gemm_split_C3.csv: X H' 26.63+0.28 GB, W'X 26.60+0.52 GB)
+NCU_TRAFFIC_PER_LAUNCH = {"C3": 27.0e9}
 METRIC = "nmf_iterations_per_second"
 UNIT = "iter/s"
 ALPHA_W, L1_RATIO = 0.1, 1.0   # NFACT defaults (matrix_decomposition.py:100-107)
@@ -47,7 +50,9 @@ def parse_args():
     ap.add_argument("--solver", default="cd", choices=["cd", "mu"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--e2e-iters", type=int, default=0, help="iterations of the e2e call (default: max(steps, 50))")
+    ap.add_argument("--no-dr", action="store_true", help="skip the dual-regression subject after the e2e solve")
+    ap.add_argument("--e2e-iters", type=int, default=0,
+                    help="iterations of the e2e call (default: NFACT's max_iter=200)")
     return ap.parse_args()
 
 
@@ -219,17 +224,14 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
 
     m, n, k, density = WORKLOADS[args.workload]
-    row0 = (m * rank) // world
-    rows = (m * (rank + 1)) // world - row0
+    from nfact_b200.sharding import init_nccl_from_torch, row_range
+    row0, row1 = row_range(m, rank, world)
+    rows = row1 - row0
 
     stream = torch.cuda.Stream(device=dev)
     handle = Handle(local_rank, stream=stream.cuda_stream)
     if world > 1:
-        def bcast(payload):
-            obj = [payload]
-            dist.broadcast_object_list(obj, src=0)
-            return obj[0]
-        handle.init_nccl(rank, world, bcast)
+        init_nccl_from_torch(handle)
 
     with torch.cuda.stream(stream):
         x_dev = synth_rows_device(torch, dev, row0, rows, n, k, density)
@@ -281,11 +283,11 @@ def run_ours(args):
         state.free()
 
         # ---- e2e through the reference-facing call with host buffers ------------------------------
-        e2e = None
+        e2e = dr_info = None
         if want_e2e:
             xmat.free()
             torch.cuda.empty_cache()
-            iters = args.e2e_iters or max(args.steps, 50)
+            iters = args.e2e_iters or 200
             w0_host = w0.cpu().numpy()
             h0_host = h0.cpu().numpy()
             params = dict(nfact_b200.get_parameters(None, "nmf", k), solver=args.solver, tol=0.0, max_iter=iters)
@@ -296,6 +298,22 @@ def run_ours(args):
             res = nfact_b200.nmf_decomp(params, x_np, W=w0_host, H=h0_host)
             t_e2e = time.perf_counter() - t0
             assert np.isfinite(res["white_components"]).all()
+            dr_info = None
+            if not args.no_dr:
+                # nfact_dr on one subject of the same shape (C4 is 100 such subjects): regress the matrix onto
+                # the grey components the solve just produced, through the reference-facing call.
+                from nfact_b200.device import DeviceMatrix as _DM
+                t0 = time.perf_counter()
+                xsub = _DM.from_host(x_np, handle)
+                t_up = time.perf_counter() - t0
+                dr = nfact_b200.nmf_dual_regression({"grey_components": res["grey_components"]}, xsub)
+                t_dr = time.perf_counter() - t0
+                xsub.free()
+                assert np.isfinite(dr["white_components"]).all() and (dr["grey_components"] >= 0).all()
+                dr_info = {"value": 1.0 / t_dr, "unit": "subjects/s", "seconds": t_dr, "upload_seconds": t_up,
+                           "solve_seconds": t_dr - t_up, "shape": [int(rows), int(n), int(k)],
+                           "white_nnz_frac": float(np.mean(dr["white_components"] > 0)),
+                           "api": "nfact_b200.nmf_dual_regression(components, X_host) per subject"}
             e2e = {"value": iters / t_e2e, "unit": UNIT, "iters": iters, "seconds": t_e2e,
                    "h2d_bytes_per_step": int((x_np.nbytes + w0_host.nbytes + h0_host.nbytes) / iters),
                    "d2h_bytes_per_step": int((w0_host.nbytes + h0_host.nbytes) / iters),
@@ -322,13 +340,17 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "gemm_split_kernel (X H' and W'X)", "achieved": achieved,
-                     "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                     "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                     "traffic": NCU_TRAFFIC_PER_LAUNCH.get(args.workload) if world == 1 else None,
+                     "tensor_pipe_active_ncu": 0.92 if args.workload == "C3" else None,
                      "peak_source": peak_src, "avg_launch_ms": gemm_avg_ms, "launches": int(gemm_launches),
                      "algorithmic_bytes_per_launch": bytes_per_launch,
                      "step_frac": (8.0 * rows * n / hbm_peak / 1e9) / (ms_per_step * 1e-3)},
     }
     if e2e is not None:
         line["e2e"] = e2e
+        if dr_info is not None:
+            line["dual_regression"] = dr_info
     if not args.no_cpu and world == 1:
         line["cpu_baseline"] = cpu_baseline(m, n, k, density, args.solver)
     print(json.dumps(line), flush=True)

@@ -25,10 +25,16 @@ __global__ void absmax_kernel(const float* __restrict__ x, int64_t rows, int64_t
                               unsigned int* __restrict__ out_bits) {
     float m = 0.0f;
     const int64_t total = rows * cols;
-    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
-         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        const int64_t r = i / cols, c = i - r * cols;
-        m = fmaxf(m, fabsf(x[r * ld + c]));
+    if (ld == cols) {  // contiguous: no index arithmetic
+        for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+             i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+            m = fmaxf(m, fabsf(x[i]));
+    } else {
+        for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+             i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+            const int64_t r = i / cols, c = i - r * cols;
+            m = fmaxf(m, fabsf(x[r * ld + c]));
+        }
     }
     m = warp_max(m);
     if ((threadIdx.x & 31) == 0) atomicMax(out_bits, __float_as_uint(m));

@@ -493,8 +493,9 @@ int nfb_matrix_from_host(nfb_handle* h, const float* x_host, int64_t m, int64_t 
     NFB_CHECK(h != nullptr && x_host != nullptr && out != nullptr, "NULL argument");
     NFB_CHECK(m > 0 && n > 0, "bad matrix shape");
     NFB_CUDA(cudaSetDevice(h->device));
-    // Two passes over row chunks so that only the planes (4 B/element) stay resident: pass 1 finds the
-    // global scale, pass 2 splits.  Chunks are staged through one device buffer.
+    // Preferred: one H2D pass into a temporary fp32 copy (max scan + split then run at HBM speed on the
+    // device).  When the temporary does not fit, two passes over row chunks through a staging buffer: pass 1
+    // finds the global scale, pass 2 splits -- only the planes (4 B/element) ever stay resident.
     std::unique_ptr<nfb_matrix> x(new nfb_matrix());
     x->h = h;
     x->m = m;
@@ -503,25 +504,43 @@ int nfb_matrix_from_host(nfb_handle* h, const float* x_host, int64_t m, int64_t 
     NFB_TRY(x->hi.alloc(m * x->ldp, false, h->stream));
     NFB_TRY(x->lo.alloc(m * x->ldp, false, h->stream));
     NFB_TRY(x->inv_scale.alloc(1, true, h->stream));
-    const int64_t chunk_rows = std::max<int64_t>(1, std::min<int64_t>(m, (int64_t(1) << 30) / (4 * n)));
-    DevBuf<float> stage[2];
-    NFB_TRY(stage[0].alloc(chunk_rows * n, false, h->stream));
-    NFB_TRY(stage[1].alloc(chunk_rows * n, false, h->stream));
     NFB_CUDA(cudaMemsetAsync(h->d_bits.p, 0, sizeof(unsigned int), h->stream));
     NFB_CUDA(cudaMemsetAsync(h->d_scal.p + 4, 0, sizeof(double), h->stream));
     NFB_CUDA(cudaMemsetAsync(h->d_int.p + 3, 0, sizeof(int), h->stream));
+    size_t free_b = 0, total_b = 0;
+    NFB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    const size_t full_bytes = sizeof(float) * static_cast<size_t>(m) * n;
     int rc = 0;
-    for (int pass = 0; pass < 2 && rc == 0; ++pass) {
-        int slot = 0;
-        for (int64_t r0 = 0; r0 < m && rc == 0; r0 += chunk_rows, slot ^= 1) {
-            const int64_t rows = std::min(chunk_rows, m - r0);
-            if (cudaMemcpyAsync(stage[slot].p, x_host + r0 * n, sizeof(float) * rows * n, cudaMemcpyHostToDevice,
-                                h->stream) != cudaSuccess) { set_error("H2D copy of X failed"); rc = 1; break; }
-            if (pass == 0) rc = absmax_f32(stage[slot].p, rows, n, n, h->d_bits.p, h->stream);
-            else rc = split_matrix(stage[slot].p, rows, n, n, h->d_bits.p, x->hi.p + r0 * x->ldp,
-                                   x->lo.p + r0 * x->ldp, x->ldp, x->inv_scale.p, h->d_scal.p + 4, h->d_int.p + 3,
-                                   h->stream);
+    if (full_bytes + (static_cast<size_t>(2) << 30) < free_b / 2) {
+        DevBuf<float> full;
+        NFB_TRY(full.alloc(static_cast<size_t>(m) * n, false, h->stream));
+        // 1 GiB pieces keep the driver's pageable staging pipeline busy and let the max scan overlap the copies
+        const int64_t piece_rows = std::max<int64_t>(1, std::min<int64_t>(m, (int64_t(1) << 30) / (4 * n)));
+        for (int64_t r0 = 0; r0 < m; r0 += piece_rows) {
+            const int64_t rows = std::min(piece_rows, m - r0);
+            NFB_CUDA(cudaMemcpyAsync(full.p + r0 * n, x_host + r0 * n, sizeof(float) * rows * n,
+                                     cudaMemcpyHostToDevice, h->stream));
+            NFB_TRY(absmax_f32(full.p + r0 * n, rows, n, n, h->d_bits.p, h->stream));
         }
+        NFB_TRY(split_matrix(full.p, m, n, n, h->d_bits.p, x->hi.p, x->lo.p, x->ldp, x->inv_scale.p,
+                             h->d_scal.p + 4, h->d_int.p + 3, h->stream));
+        NFB_CUDA(cudaStreamSynchronize(h->stream));
+    } else {
+        const int64_t chunk_rows = std::max<int64_t>(1, std::min<int64_t>(m, (int64_t(1) << 30) / (4 * n)));
+        DevBuf<float> stage;
+        NFB_TRY(stage.alloc(chunk_rows * n, false, h->stream));
+        for (int pass = 0; pass < 2 && rc == 0; ++pass) {
+            for (int64_t r0 = 0; r0 < m && rc == 0; r0 += chunk_rows) {
+                const int64_t rows = std::min(chunk_rows, m - r0);
+                if (cudaMemcpyAsync(stage.p, x_host + r0 * n, sizeof(float) * rows * n, cudaMemcpyHostToDevice,
+                                    h->stream) != cudaSuccess) { set_error("H2D copy of X failed"); rc = 1; break; }
+                if (pass == 0) rc = absmax_f32(stage.p, rows, n, n, h->d_bits.p, h->stream);
+                else rc = split_matrix(stage.p, rows, n, n, h->d_bits.p, x->hi.p + r0 * x->ldp,
+                                       x->lo.p + r0 * x->ldp, x->ldp, x->inv_scale.p, h->d_scal.p + 4,
+                                       h->d_int.p + 3, h->stream);
+            }
+        }
+        NFB_CUDA(cudaStreamSynchronize(h->stream));
     }
     if (rc != 0) return rc;
     NFB_CUDA(cudaMemcpyAsync(h->h_scal + 4, h->d_scal.p + 4, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
