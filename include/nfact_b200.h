@@ -64,6 +64,8 @@ int nfb_matrix_free(nfb_matrix* x);
 int nfb_matrix_shape(const nfb_matrix* x, int64_t* m, int64_t* n);
 /* ||X||_F^2 accumulated in float64 from the original float32 values */
 int nfb_matrix_sumsq(const nfb_matrix* x, double* out);
+/* sum of all elements in float64 (X.mean() * m * n; needed by sklearn's init='random' / nndsvda scaling) */
+int nfb_matrix_sum(const nfb_matrix* x, double* out);
 /* 1 when any element of X is negative (sklearn's check_non_negative, evaluated during the split pass) */
 int nfb_matrix_has_negative(const nfb_matrix* x, int* out);
 

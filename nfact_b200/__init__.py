@@ -7,10 +7,11 @@ and the non-negative dual regression (``nmf_dual_regression``).  All arithmetic 
 """
 from ._lib import NfbError, load as load_library  # noqa: F401
 from .device import DeviceMatrix, NmfState, get_handle  # noqa: F401
-from .dual_regression import nmf_dual_regression, run_decomp  # noqa: F401
+from .dual_regression import dual_regression_subject, nmf_dual_regression, run_decomp, run_locally  # noqa: F401
 from .matrix_handling import (avg_fdt, load_fdt_matrix, load_previous_matrix, load_single_matrix,  # noqa: F401
                               normalise_components, process_fdt_matrix2, read_in_matrix, save_matrix,
-                              thresholding)
+                              threshold_grey_components, thresholding, thresholding_components)
 from .nmf import NMF, compute_regularization, get_parameters, nmf_decomp  # noqa: F401
+from .nmfsso import NMFsso, nmf_sso  # noqa: F401
 
 __version__ = "0.1.0"

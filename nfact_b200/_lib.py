@@ -47,6 +47,7 @@ SIGNATURES = {
     "nfb_matrix_free": (c_int, [c_void_p]),
     "nfb_matrix_shape": (c_int, [c_void_p, POINTER(c_int64), POINTER(c_int64)]),
     "nfb_matrix_sumsq": (c_int, [c_void_p, POINTER(c_double)]),
+    "nfb_matrix_sum": (c_int, [c_void_p, POINTER(c_double)]),
     "nfb_matrix_has_negative": (c_int, [c_void_p, POINTER(c_int)]),
     "nfb_matrix_matmul": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int64, c_void_p, c_int64]),
     "nfb_nmf_fit_host": (c_int, [c_void_p, c_void_p, c_int, POINTER(NmfParams), c_void_p, c_void_p,

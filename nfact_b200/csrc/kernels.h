@@ -34,7 +34,8 @@ int absmax_f32(const float* x, int64_t rows, int64_t cols, int64_t ld, unsigned 
 int rowabsmax_f32(const float* x, int64_t rows, int64_t cols, int64_t ld, const float* col_mul,
                   unsigned int* rowmax_bits, cudaStream_t stream);
 // X [rows, cols] fp32 -> hi/lo planes [rows, ldp] scaled by the power of two that maps *max_bits into
-// [2^14, 2^15); inv_scale[0] receives 1/scale; sumsq (may be null) accumulates sum x^2 in fp64.
+// [2^14, 2^15); inv_scale[0] receives 1/scale; sumsq (may be null) points at two doubles that
+// accumulate sum x^2 and sum x in fp64.
 int split_matrix(const float* x, int64_t rows, int64_t cols, int64_t ld, const unsigned int* max_bits, __half* hi,
                  __half* lo, int64_t ldp, float* inv_scale, double* sumsq, int* neg_flag, cudaStream_t stream);
 // factor F [k, cols] fp32 -> planes [>=k rows, ldp] with one power-of-two scale per row
@@ -96,6 +97,6 @@ int ingest_finalize(const double* acc, int64_t nelem, double recip, int apply_re
 // sol [k, ld_sol] fp64.  status[0] counts columns that hit the iteration cap.
 int nnls_gram_batched(const double* gram, int64_t k, const float* rhs, int rhs_splits, int64_t rhs_stride,
                       int64_t ld_rhs, int64_t cols, double* sol, int64_t ld_sol, int max_outer, int* status,
-                      cudaStream_t stream);
+                      cudaStream_t stream, unsigned long long* steps_total = nullptr);
 
 }  // namespace nfb

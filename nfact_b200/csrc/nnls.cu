@@ -26,7 +26,7 @@ template <int KPL>  // coordinates per lane: k <= 32 * KPL
 __global__ void __launch_bounds__(128)
 nnls_cd_kernel(const double* __restrict__ gram, int k, const float* __restrict__ rhs, int rhs_splits,
                int64_t rhs_stride, int64_t ld_rhs, int64_t cols, double* __restrict__ sol, int64_t ld_sol,
-               int max_outer, double tol, int* __restrict__ status) {
+               int max_outer, double tol, int* __restrict__ status, unsigned long long* __restrict__ steps_total) {
     const int lane = threadIdx.x & 31;
     const int64_t warp_global = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
     const int64_t num_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
@@ -76,9 +76,11 @@ nnls_cd_kernel(const double* __restrict__ gram, int k, const float* __restrict__
         };
 
         bool converged = (rmax == 0.0);
+        unsigned long long nsteps = 0;
         for (int outer = 0; outer < max_outer && !converged; ++outer) {
             double viol = 0.0;
             for (int t = 0; t < k; ++t) viol = fmax(viol, step(t));
+            nsteps += k;
             if (viol <= thresh) { converged = true; break; }
             // sweeps restricted to the current support
             for (int inner = 0; inner < 64; ++inner) {
@@ -90,12 +92,14 @@ nnls_cd_kernel(const double* __restrict__ gram, int k, const float* __restrict__
                         const int bit = __ffs(mask) - 1;
                         mask &= mask - 1;
                         iv = fmax(iv, step(32 * i + bit));
+                        ++nsteps;
                     }
                 }
                 if (iv <= thresh) break;
             }
         }
         if (!converged && lane == 0) atomicAdd(status, 1);
+        if (lane == 0 && steps_total != nullptr) atomicAdd(steps_total, nsteps);
 #pragma unroll
         for (int i = 0; i < KPL; ++i) {
             const int t = lane + 32 * i;
@@ -108,7 +112,7 @@ nnls_cd_kernel(const double* __restrict__ gram, int k, const float* __restrict__
 
 int nnls_gram_batched(const double* gram, int64_t k, const float* rhs, int rhs_splits, int64_t rhs_stride,
                       int64_t ld_rhs, int64_t cols, double* sol, int64_t ld_sol, int max_outer, int* status,
-                      cudaStream_t stream) {
+                      cudaStream_t stream, unsigned long long* steps_total) {
     if (k == 0 || cols == 0) return 0;
     NFB_CHECK(k <= 512, "n_components > 512 is not supported by the NNLS kernel");
     const int threads = 128;
@@ -118,7 +122,7 @@ int nnls_gram_batched(const double* gram, int64_t k, const float* rhs, int rhs_s
     const double tol = 1e-10;
 #define NFB_NNLS_LAUNCH(KPL)                                                                                   \
     nnls_cd_kernel<KPL><<<blocks, threads, 0, stream>>>(gram, static_cast<int>(k), rhs, rhs_splits, rhs_stride, \
-                                                        ld_rhs, cols, sol, ld_sol, max_outer, tol, status)
+                                                        ld_rhs, cols, sol, ld_sol, max_outer, tol, status, steps_total)
     if (k <= 64) NFB_NNLS_LAUNCH(2);
     else if (k <= 128) NFB_NNLS_LAUNCH(4);
     else if (k <= 256) NFB_NNLS_LAUNCH(8);

@@ -61,7 +61,7 @@ __global__ void split_kernel(const float* __restrict__ x, int64_t rows, int64_t 
     __shared__ double scratch[32];
     const int64_t groups_per_row = ldp / 8;
     const int64_t total = rows * groups_per_row;
-    double acc = 0.0;
+    double acc = 0.0, acc_sum = 0.0;
     for (int64_t g = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; g < total;
          g += static_cast<int64_t>(gridDim.x) * blockDim.x) {
         const int64_t r = g / groups_per_row;
@@ -76,6 +76,7 @@ __global__ void split_kernel(const float* __restrict__ x, int64_t rows, int64_t 
             float v = c < cols ? x[r * ld + c] : 0.0f;
             if (col_mul != nullptr && c < cols) v *= col_mul[c];
             acc += static_cast<double>(v) * static_cast<double>(v);
+            acc_sum += static_cast<double>(v);
             if (neg_flag != nullptr && v < 0.0f) *neg_flag = 1;
             const float vs = v * s;
             const __half vh = __float2half_rn(vs);
@@ -88,6 +89,8 @@ __global__ void split_kernel(const float* __restrict__ x, int64_t rows, int64_t 
     if (sumsq != nullptr) {
         const double total_sq = block_sum(acc, scratch);
         if (threadIdx.x == 0) atomicAdd(sumsq, total_sq);
+        const double total_sum = block_sum(acc_sum, scratch);
+        if (threadIdx.x == 0) atomicAdd(sumsq + 1, total_sum);   // sumsq[1] = plain sum
     }
 }
 

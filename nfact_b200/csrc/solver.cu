@@ -96,6 +96,7 @@ struct nfb_matrix {
     DevBuf<float> inv_scale;
     float inv_scale_host = 1.0f;
     double sumsq = 0.0;  // local shard
+    double sum = 0.0;
     int has_negative = 0;
     GemmOperand operand() const { return GemmOperand{hi.p, lo.p, m, ldp}; }
 };
@@ -475,16 +476,18 @@ int nfb_matrix_from_device(nfb_handle* h, const float* x_dev, int64_t m, int64_t
     NFB_TRY(x->lo.alloc(m * x->ldp, false, h->stream));
     NFB_TRY(x->inv_scale.alloc(1, true, h->stream));
     NFB_CUDA(cudaMemsetAsync(h->d_bits.p, 0, sizeof(unsigned int), h->stream));
-    NFB_CUDA(cudaMemsetAsync(h->d_scal.p + 4, 0, sizeof(double), h->stream));
+    NFB_CUDA(cudaMemsetAsync(h->d_scal.p + 6, 0, 2 * sizeof(double), h->stream));
     NFB_CUDA(cudaMemsetAsync(h->d_int.p + 3, 0, sizeof(int), h->stream));
     NFB_TRY(absmax_f32(x_dev, m, n, ld, h->d_bits.p, h->stream));
-    NFB_TRY(split_matrix(x_dev, m, n, ld, h->d_bits.p, x->hi.p, x->lo.p, x->ldp, x->inv_scale.p, h->d_scal.p + 4,
+    NFB_TRY(split_matrix(x_dev, m, n, ld, h->d_bits.p, x->hi.p, x->lo.p, x->ldp, x->inv_scale.p, h->d_scal.p + 6,
                          h->d_int.p + 3, h->stream));
-    NFB_CUDA(cudaMemcpyAsync(h->h_scal + 4, h->d_scal.p + 4, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    NFB_CUDA(cudaMemcpyAsync(h->h_scal + 6, h->d_scal.p + 6, 2 * sizeof(double), cudaMemcpyDeviceToHost,
+                             h->stream));
     NFB_CUDA(cudaMemcpyAsync(&x->inv_scale_host, x->inv_scale.p, sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     NFB_CUDA(cudaMemcpyAsync(&x->has_negative, h->d_int.p + 3, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     NFB_CUDA(cudaStreamSynchronize(h->stream));
-    x->sumsq = h->h_scal[4];
+    x->sumsq = h->h_scal[6];
+    x->sum = h->h_scal[7];
     *out = x.release();
     return 0;
 }
@@ -505,7 +508,7 @@ int nfb_matrix_from_host(nfb_handle* h, const float* x_host, int64_t m, int64_t 
     NFB_TRY(x->lo.alloc(m * x->ldp, false, h->stream));
     NFB_TRY(x->inv_scale.alloc(1, true, h->stream));
     NFB_CUDA(cudaMemsetAsync(h->d_bits.p, 0, sizeof(unsigned int), h->stream));
-    NFB_CUDA(cudaMemsetAsync(h->d_scal.p + 4, 0, sizeof(double), h->stream));
+    NFB_CUDA(cudaMemsetAsync(h->d_scal.p + 6, 0, 2 * sizeof(double), h->stream));
     NFB_CUDA(cudaMemsetAsync(h->d_int.p + 3, 0, sizeof(int), h->stream));
     size_t free_b = 0, total_b = 0;
     NFB_CUDA(cudaMemGetInfo(&free_b, &total_b));
@@ -523,7 +526,7 @@ int nfb_matrix_from_host(nfb_handle* h, const float* x_host, int64_t m, int64_t 
             NFB_TRY(absmax_f32(full.p + r0 * n, rows, n, n, h->d_bits.p, h->stream));
         }
         NFB_TRY(split_matrix(full.p, m, n, n, h->d_bits.p, x->hi.p, x->lo.p, x->ldp, x->inv_scale.p,
-                             h->d_scal.p + 4, h->d_int.p + 3, h->stream));
+                             h->d_scal.p + 6, h->d_int.p + 3, h->stream));
         NFB_CUDA(cudaStreamSynchronize(h->stream));
     } else {
         const int64_t chunk_rows = std::max<int64_t>(1, std::min<int64_t>(m, (int64_t(1) << 30) / (4 * n)));
@@ -536,18 +539,20 @@ int nfb_matrix_from_host(nfb_handle* h, const float* x_host, int64_t m, int64_t 
                                     h->stream) != cudaSuccess) { set_error("H2D copy of X failed"); rc = 1; break; }
                 if (pass == 0) rc = absmax_f32(stage.p, rows, n, n, h->d_bits.p, h->stream);
                 else rc = split_matrix(stage.p, rows, n, n, h->d_bits.p, x->hi.p + r0 * x->ldp,
-                                       x->lo.p + r0 * x->ldp, x->ldp, x->inv_scale.p, h->d_scal.p + 4,
+                                       x->lo.p + r0 * x->ldp, x->ldp, x->inv_scale.p, h->d_scal.p + 6,
                                        h->d_int.p + 3, h->stream);
             }
         }
         NFB_CUDA(cudaStreamSynchronize(h->stream));
     }
     if (rc != 0) return rc;
-    NFB_CUDA(cudaMemcpyAsync(h->h_scal + 4, h->d_scal.p + 4, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    NFB_CUDA(cudaMemcpyAsync(h->h_scal + 6, h->d_scal.p + 6, 2 * sizeof(double), cudaMemcpyDeviceToHost,
+                             h->stream));
     NFB_CUDA(cudaMemcpyAsync(&x->inv_scale_host, x->inv_scale.p, sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     NFB_CUDA(cudaMemcpyAsync(&x->has_negative, h->d_int.p + 3, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     NFB_CUDA(cudaStreamSynchronize(h->stream));
-    x->sumsq = h->h_scal[4];
+    x->sumsq = h->h_scal[6];
+    x->sum = h->h_scal[7];
     *out = x.release();
     return 0;
 }
@@ -564,6 +569,12 @@ int nfb_matrix_shape(const nfb_matrix* x, int64_t* m, int64_t* n) {
     NFB_CHECK(x != nullptr, "matrix is NULL");
     if (m) *m = x->m;
     if (n) *n = x->n;
+    return 0;
+}
+
+int nfb_matrix_sum(const nfb_matrix* x, double* out) {
+    NFB_CHECK(x != nullptr && out != nullptr, "NULL argument");
+    *out = x->sum;
     return 0;
 }
 
@@ -779,6 +790,7 @@ int nfb_dual_regression_host(nfb_handle* h, const nfb_matrix* x, int k, const do
     DevBuf<float> part;
     NFB_TRY(part.alloc(std::max(static_cast<size_t>(s1) * k * hs.ld, static_cast<size_t>(s2) * k * gt.ld), false, st));
     NFB_CUDA(cudaMemsetAsync(h->d_int.p, 0, 2 * sizeof(int), st));
+    NFB_CUDA(cudaMemsetAsync(h->d_scal.p + 8, 0, 2 * sizeof(double), st));
     // group grey components: float64 [m, k] -> component-major float32 master + planes
     NFB_CUDA(cudaMemcpyAsync(g64.p, g_host, sizeof(double) * m * k, cudaMemcpyHostToDevice, st));
     NFB_TRY(transpose_f64_to_f32(g64.p, m, k, k, gt.f.p, gt.ld, st));
@@ -788,7 +800,7 @@ int nfb_dual_regression_host(nfb_handle* h, const nfb_matrix* x, int k, const do
     NFB_TRY(gemm_split(x->operand(), true, gt.operand(), n, m, static_cast<int>(kp), k, part.p, hs.ld, s1,
                        gt.inv_scale.p, nullptr, x->inv_scale_host, cg, st));
     NFB_TRY(nnls_gram_batched(gram64.p, k, part.p, s1, static_cast<int64_t>(k) * hs.ld, hs.ld, n, sol_h.p, hs.ld,
-                              400, h->d_int.p, st));
+                              400, h->d_int.p, st, reinterpret_cast<unsigned long long*>(h->d_scal.p + 8)));
     // ---- stage 2: grey matter.  Gs[i, :] = nnls(Hs, X[i, :])    (dual_regression_methods.py:151-163)
     NFB_CUDA(cudaMemsetAsync(hs.rowmax.p, 0, sizeof(unsigned int) * kp, st));
     NFB_TRY(f64_to_f32_rowmax(sol_h.p, k, n, hs.ld, hs.f.p, hs.ld, hs.rowmax.p, st));
@@ -797,7 +809,7 @@ int nfb_dual_regression_host(nfb_handle* h, const nfb_matrix* x, int k, const do
     NFB_TRY(gemm_split(x->operand(), false, hs.operand(), m, n, static_cast<int>(kp), k, part.p, gt.ld, s2,
                        hs.inv_scale.p, nullptr, x->inv_scale_host, cg, st));
     NFB_TRY(nnls_gram_batched(gram64.p, k, part.p, s2, static_cast<int64_t>(k) * gt.ld, gt.ld, m, sol_g.p, gt.ld,
-                              400, h->d_int.p + 1, st));
+                              400, h->d_int.p + 1, st, reinterpret_cast<unsigned long long*>(h->d_scal.p + 9)));
     // ---- results -------------------------------------------------------------------------------------
     if (hs_out)
         NFB_CUDA(cudaMemcpy2DAsync(hs_out, n * sizeof(double), sol_h.p, hs.ld * sizeof(double), n * sizeof(double), k,
@@ -815,6 +827,13 @@ int nfb_dual_regression_host(nfb_handle* h, const nfb_matrix* x, int k, const do
         for (int64_t i = 0; i < m; ++i)
             for (int t = 0; t < k; ++t) gs_out[i * k + t] = gs_t[static_cast<size_t>(t) * m + i];
     if (n_unconverged_out) *n_unconverged_out = status[0] + status[1];
+    if (getenv("NFB_DR_STATS")) {
+        unsigned long long steps[2] = {0, 0};
+        cudaMemcpy(steps, h->d_scal.p + 8, sizeof(steps), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "nfact_b200 DR: stage1 %.1f coordinate steps/column (n=%lld), stage2 %.1f steps/row (m=%lld), k=%d\n",
+                static_cast<double>(steps[0]) / n, static_cast<long long>(n), static_cast<double>(steps[1]) / m,
+                static_cast<long long>(m), k);
+    }
     return 0;
 }
 

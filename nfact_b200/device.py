@@ -115,6 +115,12 @@ class DeviceMatrix:
         return out.value
 
     @property
+    def mean(self) -> float:
+        out = c_double()
+        check(self.handle.lib.nfb_matrix_sum(self._ptr, byref(out)))
+        return out.value / (self.shape[0] * self.shape[1])
+
+    @property
     def has_negative(self) -> bool:
         out = c_int()
         check(self.handle.lib.nfb_matrix_has_negative(self._ptr, byref(out)))

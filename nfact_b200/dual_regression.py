@@ -63,3 +63,44 @@ def run_decomp(decomp, components: dict, connectivity_matrix, parallel: int = No
     except Exception as e:
         error_and_exit(False, f"Unable to perform dual regression due to {e}")
     return components
+
+
+def dual_regression_subject(fdt_path: str, components: dict, seeds: list, threshold: int = 3,
+                            normalise: bool = False, parallel: int = 1) -> dict:
+    """Compute part of NFACT/dual_reg/dual_regression/run_dual_regression.py:66-199 for one subject:
+    load the subject's fdt_matrix2 -> dual regression -> z-threshold -> optional z-score normalisation.
+    Saving the images stays with the reference's ``save_dual_regression_images``."""
+    import os
+    from .matrix_handling import load_fdt_matrix, normalise_components, thresholding_components
+    matrix = None
+    try:
+        matrix_file = next((os.path.join(fdt_path, fname) for fname in ("fdt_matrix2.dot.lz4", "fdt_matrix2.dot")
+                            if os.path.exists(os.path.join(fdt_path, fname))), None)
+        matrix = load_fdt_matrix(matrix_file)
+    except Exception:
+        error_and_exit(False, f"Unable to load {os.path.basename(os.path.normpath(fdt_path))} fdt matrix")
+    dr_results = run_decomp(nmf_dual_regression, components, matrix, parallel)
+    dr_results = thresholding_components(int(threshold), os.path.join(fdt_path, "coords_for_fdt_matrix2"), seeds,
+                                         dr_results)
+    if normalise:
+        normalised = normalise_components(dr_results["grey_components"], dr_results["white_components"])
+        dr_results["normalised_white"] = normalised["white_matter"]
+        dr_results["normalised_grey"] = normalised["grey_matter"]
+    return dr_results
+
+
+def run_locally(list_of_subject_dirs: list, components: dict, seeds: list, threshold: int = 3,
+                normalise: bool = False, rank: int = 0, world: int = 1, save=None) -> dict:
+    """Subject loop of NFACT/dual_reg/dual_regression/set_up_dual_regression.py:186-235.  Subjects are
+    independent: with ``world`` processes (one per GPU) rank r takes subjects r, r+world, ... and no
+    collective is needed.  ``save(subject_dir, dr_results)`` receives each result (the reference's image
+    writer); the results of this rank are also returned keyed by subject directory."""
+    out = {}
+    for idx, subject_dir in enumerate(list_of_subject_dirs):
+        if idx % world != rank:
+            continue
+        dr_results = dual_regression_subject(subject_dir, components, seeds, threshold, normalise)
+        if save is not None:
+            save(subject_dir, dr_results)
+        out[subject_dir] = dr_results
+    return out

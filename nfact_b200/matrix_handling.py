@@ -135,3 +135,27 @@ def normalise_components(grey_matter: np.ndarray, white_matter: np.ndarray) -> d
     col = colours()
     nprint(f"{col['pink']}Normalising:{col['reset']} Components")
     return {"grey_matter": zscore_cols(grey_matter), "white_matter": zscore_cols(white_matter.T).T}
+
+
+def threshold_grey_components(components: np.ndarray, coord_path: str, seeds: list, zscore_val) -> np.ndarray:
+    """NFACT/base/matrix_handling.py:184-215: z-threshold the grey components separately for every seed
+    (the seed index of each row is the second-to-last column of ``coords_for_fdt_matrix2``)."""
+    seeds_id = np.loadtxt(coord_path, dtype=int)[:, -2]
+    for idx, _ in enumerate(seeds):
+        rows_of_seed = seeds_id == idx
+        per_seed = components[rows_of_seed, :].T
+        thresholding(per_seed, zscore_val)
+        components[rows_of_seed, :] = per_seed.T
+    return components
+
+
+def thresholding_components(threshold_val: int, path_to_coords: str, seeds: list, components: dict) -> dict:
+    """NFACT/base/matrix_handling.py:241-277."""
+    col = colours()
+    shown = threshold_val if threshold_val != 0 else "Not thresholding"
+    nprint(f"{col['pink']}Thresholding value:{col['reset']} {shown}\n")
+    if threshold_val != 0:
+        components["white_components"] = thresholding(components["white_components"], threshold_val)
+        components["grey_components"] = threshold_grey_components(components["grey_components"], path_to_coords,
+                                                                  seeds, threshold_val)
+    return components

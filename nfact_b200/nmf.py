@@ -145,9 +145,8 @@ class NMF:
                 W0 = np.array(W, dtype=np.float32, order="C")
                 H0 = np.array(H, dtype=np.float32, order="C")
             else:
-                if x_mean is None:
-                    raise ValueError("init != 'custom' on a DeviceMatrix needs the host matrix (its mean); "
-                                     "pass W and H or the numpy matrix")
+                if x_mean is None:      # resident matrix: float64 mean accumulated during the split
+                    x_mean = xdev.mean
                 W0, H0 = initialize_nmf(xdev, x_mean, k, p["init"], p["random_state"])
             regs = compute_regularization(m, n, p["alpha_W"], p["alpha_H"], p["l1_ratio"])
             state = NmfState(xdev, k, make_params(p["solver"], p["max_iter"], p["tol"], regs, p["verbose"]))

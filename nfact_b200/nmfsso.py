@@ -1,0 +1,139 @@
+"""NMF-sso orchestration on a resident matrix.
+
+Mirrors NFACT/decomp/decomposition/sso/nmfsso.py (``NMFsso`` :62-238, ``nmf_sso`` :322-360) and the
+clustering glue of sso_functions.py (``compute_similairty_matrix`` :49, ``sim2dis`` :71,
+``clustering_components`` :359, ``idx2centrotype`` :426): N random-init solves -> per-run z-threshold of H
+-> similarity of all N*k white-matter components -> average-linkage clustering cut at the elbow -> one
+centrotype per cluster -> final ``init='custom'`` solve.
+
+Difference by design: the reference copies X into POSIX shared memory and forks ``n_cores`` joblib workers;
+here X is uploaded to HBM once (``DeviceMatrix``) and the N+1 solves reuse it, so ``n_cores`` only keeps its
+meaning as "run the sso loop" and the single-run path does not inherit the reference's ``range(colours)``
+TypeError (nmfsso.py:207).  Plots / csv (sso_plotting.py) are out of scope.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .device import DeviceMatrix
+from .matrix_handling import thresholding
+from .nmf import nmf_decomp
+from .utils import colours, error_and_exit, nprint
+
+
+def rownorm(nmf_mat: np.ndarray) -> np.ndarray:
+    norms = np.linalg.norm(nmf_mat, axis=1, keepdims=True)
+    norms[norms == 0] = 1
+    return nmf_mat / norms
+
+
+def compute_similairty_matrix(components: np.ndarray) -> np.ndarray:
+    """sso_functions.py:49-68: correlation between the row-normalised components, clipped to [0, 1]."""
+    sim = np.corrcoef(rownorm(components))
+    np.clip(sim, 0, 1, out=sim)
+    return sim
+
+
+def sim2dis(sim: np.ndarray) -> np.ndarray:
+    return 1 - sim
+
+
+def calculate_elbow(merge_dist: np.ndarray) -> float:
+    """sso_functions.py:268-300: merge height farthest from the chord between the first and last merge."""
+    xs = np.asarray(merge_dist, dtype=np.float64)
+    ys = np.arange(xs.shape[0], dtype=np.float64)
+    dx, dy = xs[-1] - xs[0], ys[-1] - ys[0]
+    chord = np.hypot(dx, dy)
+    dist = np.abs(dx * (ys - ys[0]) - dy * (xs - xs[0])) / chord
+    return xs[int(np.argmax(dist))]
+
+
+def cluster_valid(cluster_partition: np.ndarray, dim: int) -> bool:
+    clusters, counts = np.unique(cluster_partition, return_counts=True)
+    if np.any(counts == 1) or len(clusters) == 1:
+        return False
+    return clusters.max() <= dim
+
+
+def clustering_components(dis: np.ndarray, dim: int):
+    """sso_functions.py:249-377: average linkage, cut at the elbow, raised until the partition is valid."""
+    from scipy.cluster.hierarchy import fcluster, linkage
+    from scipy.spatial.distance import squareform
+    zlink = linkage(squareform(dis, checks=False), method="average")
+    elbow = calculate_elbow(zlink[:, 2])
+    first = fcluster(zlink, t=elbow, criterion="distance")
+    if cluster_valid(first, dim):
+        return first
+    heights = np.sort(np.unique(zlink))
+    for height in heights[np.searchsorted(heights, elbow):]:
+        part = fcluster(zlink, t=height, criterion="distance")
+        if cluster_valid(part, dim):
+            return part
+    return None
+
+
+def idx2centrotype(sim: np.ndarray, partition: np.ndarray) -> np.ndarray:
+    """sso_functions.py:405-453: per cluster, the member with the largest summed similarity to the others."""
+    n_cluster = int(partition.max())
+    out = np.zeros(n_cluster, dtype=int)
+    for cluster in range(1, n_cluster + 1):
+        members = np.where(partition == cluster)[0]
+        sub = sim[np.ix_(members, members)]
+        out[cluster - 1] = members[int(np.argmax(sub.sum(axis=0)))]
+    return out
+
+
+class NMFsso:
+    """est = NMFsso(fdt_mat, num_int, nmf_params, n_jobs); results = est.run()  (nmfsso.py:62-238)."""
+
+    def __init__(self, fdt_mat, num_int: int, nmf_params: dict, n_jobs: int) -> None:
+        self.num_int = num_int
+        self.nmf_params = nmf_params.copy()
+        self.n_jobs = n_jobs
+        self.fdt_mat = fdt_mat
+        self.nmf_params["init"] = "random"
+        self.col = colours()
+
+    def run(self) -> dict:
+        nprint(f"{self.col['pink']}NMF iterations: {self.col['reset']}{self.num_int}")
+        owns = not isinstance(self.fdt_mat, DeviceMatrix)
+        xdev = DeviceMatrix.from_host(np.asarray(self.fdt_mat)) if owns else self.fdt_mat
+        results = {"grey": [], "white": []}
+        try:
+            for iterat in range(self.num_int):
+                nprint(f"{self.col['pink']}Run: {self.col['reset']}{iterat + 1}/{self.num_int}")
+                self.nmf_params["random_state"] = None
+                state = nmf_decomp(self.nmf_params, xdev)
+                results["grey"].append(state["grey_components"])
+                results["white"].append(thresholding(state["white_components"], 3))   # nmfsso.py:137
+        finally:
+            if owns:
+                xdev.free()
+        return results
+
+
+def nmf_sso(fdt_matrix, parameters: dict, args: dict) -> dict:
+    """NFACT/decomp/decomposition/sso/nmfsso.py:322-360."""
+    if args["no_sso"]:
+        return nmf_decomp(parameters, fdt_matrix)
+    owns = not isinstance(fdt_matrix, DeviceMatrix)
+    xdev = DeviceMatrix.from_host(np.asarray(fdt_matrix)) if owns else fdt_matrix
+    try:
+        results = NMFsso(xdev, args["iterations"], parameters, args.get("n_cores", 1)).run()
+        w_components = np.vstack(results["white"])
+        g_components = np.hstack(results["grey"])
+        sim = compute_similairty_matrix(w_components)
+        dis = sim2dis(sim)
+        partitions = clustering_components(dis, args["dim"])
+        error_and_exit(partitions is not None and partitions.size != 0,
+                       "Clustering Failed. Please check Num of dims")
+        centroids = idx2centrotype(sim, partitions)
+        parameters["random_state"] = None
+        parameters["init"] = "custom"
+        parameters["n_components"] = centroids.shape[0]
+        w_mat = np.ascontiguousarray(g_components[:, centroids])
+        h_mat = np.ascontiguousarray(w_components[centroids, :])
+        return nmf_decomp(parameters, xdev, W=w_mat, H=h_mat)
+    finally:
+        if owns:
+            xdev.free()

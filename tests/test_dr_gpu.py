@@ -54,3 +54,23 @@ def test_dr_shape_mismatch_exits(golden):
     comps = {"grey_components": np.ones((5, 3))}
     with pytest.raises(SystemExit):
         nfact_b200.run_decomp(nfact_b200.nmf_dual_regression, comps, golden["ingest_single_1"], 1)
+
+
+def test_dr_subject_pipeline(golden, tmp_path):
+    """dual_regression_pipeline compute part: ingest -> DR -> per-seed threshold -> normalise."""
+    import os
+    import shutil
+    import nfact_b200
+    from conftest import GOLDEN_DIR
+    sub = tmp_path / "sub-1"
+    shutil.copytree(os.path.join(GOLDEN_DIR, "data", "sub-1"), sub)
+    coords = np.zeros((99, 5), dtype=int)
+    coords[50:, -2] = 1                                   # two seeds: rows 0-49 and 50-98
+    np.savetxt(sub / "coords_for_fdt_matrix2", coords, fmt="%d")
+    comps = {"grey_components": golden["cd_fit_W"].astype(np.float64)}
+    out = nfact_b200.run_locally([str(sub)], comps, ["L", "R"], threshold=1, normalise=True)
+    res = out[str(sub)]
+    assert res["grey_components"].shape == (99, 10) and res["white_components"].shape == (10, 199)
+    assert res["normalised_white"].shape == (10, 199)
+    ref_white = nfact_b200.thresholding(golden["dr_white"].copy(), 1)
+    assert np.abs(res["white_components"] - ref_white).max() <= 1e-3 * np.abs(ref_white).max()

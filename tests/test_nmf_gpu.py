@@ -164,3 +164,16 @@ def test_nndsvd_device_matches_sklearn(golden):
     W, H = nndsvd_device(xdev, 10, np.random.RandomState(0))
     assert rel_fro(W, golden["init_nndsvd_W"]) < 1e-3
     assert rel_fro(H, golden["init_nndsvd_H"]) < 1e-3
+
+
+def test_nmf_sso_runs_on_resident_matrix(golden):
+    """NMF-sso orchestration: N random solves share one resident X, clustering, final custom solve."""
+    import nfact_b200
+    X = golden["ingest_group"]
+    p = dict(nfact_b200.get_parameters(None, "nmf", 6), max_iter=40)
+    res = nfact_b200.nmf_sso(X, p, {"no_sso": False, "iterations": 5, "n_cores": 1, "dim": 6, "outdir": "."})
+    kf = res["white_components"].shape[0]
+    assert 2 <= kf <= 6 and res["grey_components"].shape == (99, kf)
+    assert np.isfinite(res["white_components"]).all() and (res["grey_components"] >= 0).all()
+    single = nfact_b200.nmf_sso(X, dict(p, random_state=0), {"no_sso": True})
+    assert single["white_components"].shape == (6, 199)
