@@ -240,7 +240,7 @@ int cd_sweep(float* f, int64_t k, int64_t cols, int64_t ld, const float* num, in
              const float* den, int64_t ld_part, const float* gram, float l1, float l2, double* violation,
              unsigned int* rowmax_bits, cudaStream_t stream) {
     if (k * cols == 0) return 0;
-    NFB_CHECK(k <= 256, "n_components > 256 is not supported by the coordinate-descent kernel");
+    NFB_CHECK(k <= 512, "n_components > 512 is not supported by the coordinate-descent kernel");
     const int ldg = static_cast<int>(round_up64(k, 16));
     const int kpad = static_cast<int>(k) | 1;
     const int kpl_fast = k <= 32 ? 1 : k <= 64 ? 2 : k <= 128 ? 4 : 7;
@@ -268,6 +268,7 @@ int cd_sweep(float* f, int64_t k, int64_t cols, int64_t ld, const float* num, in
     }
     const size_t smem = (static_cast<size_t>(2) * kTileCols * kpad + k) * sizeof(float);
     const int64_t ntiles = ceil_div64(cols, kTileCols);
+    NFB_CHECK(smem <= 220 * 1024, "n_components too large for the coordinate-descent kernel");
     const int blocks_per_sm = std::max<int>(1, std::min<int>(4, static_cast<int>((200 * 1024) / (smem + 1024))));
     const int grid = static_cast<int>(std::min<int64_t>(ntiles, static_cast<int64_t>(sm_count()) * blocks_per_sm));
 #define NFB_CD_LAUNCH(KPL)                                                                                       \
@@ -280,7 +281,8 @@ int cd_sweep(float* f, int64_t k, int64_t cols, int64_t ld, const float* num, in
     if (k <= 32) NFB_CD_LAUNCH(1);
     else if (k <= 64) NFB_CD_LAUNCH(2);
     else if (k <= 128) NFB_CD_LAUNCH(4);
-    else NFB_CD_LAUNCH(8);
+    else if (k <= 256) NFB_CD_LAUNCH(8);
+    else NFB_CD_LAUNCH(16);
 #undef NFB_CD_LAUNCH
     NFB_CUDA(cudaGetLastError());
     return 0;

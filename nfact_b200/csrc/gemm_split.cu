@@ -388,9 +388,10 @@ int gemm_pick_splits(int64_t m_total, int64_t k_total, int cta_group) {
     return static_cast<int>(best);
 }
 
-int gemm_split(const GemmOperand& a, bool a_is_mn_major, const GemmOperand& b, int64_t m_total, int64_t k_total,
-               int n_umma, int n_store, float* out, int64_t ld_out, int splits, const float* col_scale,
-               const float* row_scale, float scale, int cta_group, cudaStream_t stream) {
+static int gemm_split_tile(const GemmOperand& a, bool a_is_mn_major, const GemmOperand& b, int64_t m_total,
+                           int64_t k_total, int n_umma, int n_store, float* out, int64_t ld_out,
+                           long long split_stride, int splits, const float* col_scale, const float* row_scale,
+                           float scale, int cta_group, cudaStream_t stream) {
     NFB_CHECK(n_umma % 16 == 0 && n_umma >= 16 && n_umma <= 256, "n_umma must be a multiple of 16 in [16,256]");
     NFB_CHECK(cta_group == 1 || cta_group == 2, "cta_group must be 1 or 2");
     NFB_CHECK(n_store <= n_umma, "n_store exceeds n_umma");
@@ -425,7 +426,7 @@ int gemm_split(const GemmOperand& a, bool a_is_mn_major, const GemmOperand& b, i
     args.splits = splits;
     args.m_blocks = static_cast<int>(ceil_div64(m_total, static_cast<int64_t>(kBlockM) * cta_group));
     args.ld_out = static_cast<int>(ld_out);
-    args.split_stride = static_cast<long long>(n_store) * ld_out;
+    args.split_stride = split_stride;
     args.b_tile_bytes = n_load * 128;
     const int stage_bytes = 2 * kATileBytes + 2 * args.b_tile_bytes;
     const int smem_budget = 227 * 1024 - 1024 /*align*/ - 256 /*barriers*/;
@@ -444,6 +445,23 @@ int gemm_split(const GemmOperand& a, bool a_is_mn_major, const GemmOperand& b, i
     }
     if (cta_group == 2) return launch_nch<0, 2>(l, nch_per_thread);
     return launch_nch<0, 1>(l, nch_per_thread);
+}
+
+// N (the component dimension) is tiled in slabs of <= 256 columns: one launch per slab, each streaming A once.
+int gemm_split(const GemmOperand& a, bool a_is_mn_major, const GemmOperand& b, int64_t m_total, int64_t k_total,
+               int n_umma, int n_store, float* out, int64_t ld_out, int splits, const float* col_scale,
+               const float* row_scale, float scale, int cta_group, cudaStream_t stream) {
+    NFB_CHECK(n_umma % 16 == 0 && n_umma >= 16, "n_umma must be a positive multiple of 16");
+    const long long split_stride = static_cast<long long>(n_store) * ld_out;
+    for (int t0 = 0; t0 < n_umma && t0 < n_store; t0 += 256) {
+        const int n_tile = std::min(256, n_umma - t0);
+        GemmOperand bt{b.hi + static_cast<int64_t>(t0) * b.ld, b.lo + static_cast<int64_t>(t0) * b.ld, b.rows - t0,
+                       b.ld};
+        NFB_TRY(gemm_split_tile(a, a_is_mn_major, bt, m_total, k_total, n_tile, std::min(n_tile, n_store - t0),
+                                out + static_cast<int64_t>(t0) * ld_out, ld_out, split_stride, splits,
+                                col_scale ? col_scale + t0 : nullptr, row_scale, scale, cta_group, stream));
+    }
+    return 0;
 }
 
 }  // namespace nfb

@@ -593,7 +593,7 @@ int nfb_matrix_sumsq(const nfb_matrix* x, double* out) {
 // ---- NMF -----------------------------------------------------------------------------------------
 int nfb_nmf_create(nfb_handle* h, const nfb_matrix* x, int k, const nfb_nmf_params* p, nfb_nmf** out) {
     NFB_CHECK(h != nullptr && x != nullptr && p != nullptr && out != nullptr, "NULL argument");
-    NFB_CHECK(k >= 1 && k <= 256, "n_components must be in [1, 256] in this build");
+    NFB_CHECK(k >= 1 && k <= 512, "n_components must be in [1, 512] in this build");
     NFB_CHECK(p->solver == 0 || p->solver == 1, "solver must be 0 (cd) or 1 (mu)");
     NFB_CUDA(cudaSetDevice(h->device));
     std::unique_ptr<nfb_nmf> s(new nfb_nmf());
@@ -773,7 +773,7 @@ int nfb_nmf_fit_host(nfb_handle* h, const nfb_matrix* x, int k, const nfb_nmf_pa
 int nfb_dual_regression_host(nfb_handle* h, const nfb_matrix* x, int k, const double* g_host, double* gs_out,
                              double* hs_out, int* n_unconverged_out) {
     NFB_CHECK(h != nullptr && x != nullptr && g_host != nullptr, "NULL argument");
-    NFB_CHECK(k >= 1 && k <= 256, "n_components must be in [1, 256] in this build");
+    NFB_CHECK(k >= 1 && k <= 512, "n_components must be in [1, 512] in this build");
     NFB_CUDA(cudaSetDevice(h->device));
     cudaStream_t st = h->stream;
     const int64_t m = x->m, n = x->n, kp = round_up64(k, 16);
@@ -899,8 +899,8 @@ int nfb_matrix_matmul(nfb_handle* h, const nfb_matrix* x, int trans, const float
     NFB_CHECK(ld_out >= m_total, "ld_out too small");
     const int cg = h->cta_group;
     const int splits = gemm_pick_splits(m_total, k_total, cg);
-    for (int64_t t0 = 0; t0 < n_b; t0 += 256) {
-        const int64_t nb = std::min<int64_t>(256, n_b - t0);
+    for (int64_t t0 = 0; t0 < n_b; t0 += 512) {
+        const int64_t nb = std::min<int64_t>(512, n_b - t0);
         Factor b;
         NFB_TRY(b.init(nb, k_total, true, st));
         NFB_CUDA(cudaMemcpy2DAsync(b.f.p, b.ld * sizeof(float), b_dev + t0 * k_total, k_total * sizeof(float),

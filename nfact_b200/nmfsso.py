@@ -29,7 +29,14 @@ def rownorm(nmf_mat: np.ndarray) -> np.ndarray:
 
 def compute_similairty_matrix(components: np.ndarray) -> np.ndarray:
     """sso_functions.py:49-68: correlation between the row-normalised components, clipped to [0, 1]."""
-    sim = np.corrcoef(rownorm(components))
+    with np.errstate(invalid="ignore", divide="ignore"):
+        sim = np.corrcoef(rownorm(components))
+    # A component that a run drove to all-zero has no variance: corrcoef gives NaN there and scipy's
+    # linkage rejects the matrix (the reference crashes).  Treat it as dissimilar to everything.
+    dead = ~np.isfinite(sim)
+    if dead.any():
+        sim[dead] = 0.0
+        np.fill_diagonal(sim, 1.0)
     np.clip(sim, 0, 1, out=sim)
     return sim
 

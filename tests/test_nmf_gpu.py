@@ -177,3 +177,22 @@ def test_nmf_sso_runs_on_resident_matrix(golden):
     assert np.isfinite(res["white_components"]).all() and (res["grey_components"] >= 0).all()
     single = nfact_b200.nmf_sso(X, dict(p, random_state=0), {"no_sso": True})
     assert single["white_components"].shape == (6, 199)
+
+
+@pytest.mark.parametrize("solver", ["mu", "cd"])
+def test_more_than_256_components(solver):
+    """k > 256 (configs[4] uses k = 500): the component dimension is tiled over several GEMM launches."""
+    from oracle import nfact_oracle as orc
+    rng = np.random.default_rng(8)
+    m, n, k = 640, 901, 300
+    X = (rng.gamma(0.3, 1.0, (m, 40)) @ rng.gamma(0.3, 1.0, (40, n)) * (rng.random((m, n)) < 0.5) * 50).astype(np.float32)
+    W0, H0 = orc.init_random(X, k, 2)
+    regs = orc.compute_regularization(m, n, 0.001, "same", 1.0)
+    xdev, st = _state(X, k, solver, regs)
+    st.set_factors(W0, H0)
+    rec = []
+    (orc.fit_mu if solver == "mu" else orc.fit_cd)(X, W0, H0, *regs, tol=0, max_iter=3, record=rec)
+    st.iterate(3)
+    W, H = st.get_factors()
+    assert rel_fro(W, rec[-1][1]) < MU_TOL
+    assert rel_fro(H, rec[-1][2]) < MU_TOL
