@@ -121,8 +121,8 @@ cd_sweep_warp_kernel(float* __restrict__ f, int k, int64_t cols, int64_t ld, con
 // ---- fast path: Gram matrix resident in shared memory (k <= ~216) ----------------------------------
 // One CTA per SM, 16 warps, one column per warp at a time.  Per component step the dependent chain is
 // shfl -> multiply by the precomputed 1/hess -> clamp -> rank-1 update from smem, ~20 instructions.
-constexpr int kFastWarps = 16;
-constexpr int kFastTile = 16;
+constexpr int kFastWarps = 24;   // 6 warps per scheduler hide the per-step dependency chain
+constexpr int kFastTile = 24;    // one column per warp
 
 template <int KPL>
 __global__ void __launch_bounds__(kFastWarps * 32, 1)
@@ -155,25 +155,22 @@ cd_sweep_smem_kernel(float* __restrict__ f, int k, int64_t cols, int64_t ld, con
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t j0 = tile * kFastTile;
         __syncthreads();
-        // ---- phase 1: half-warps read 16 consecutive columns of one component row ---------------------
-        {
-            const int half = lane >> 4, c = lane & 15;
-            const int64_t j = j0 + c;
-            const bool active = j < cols;
+        // ---- phase 1: consecutive threads read consecutive columns of one component row ------------------
 #pragma unroll 4
-            for (int u = warp * 2 + half; u < k; u += kFastWarps * 2) {
-                float fv = 0.0f, gv = 0.0f;
-                if (active) {
-                    fv = f[static_cast<int64_t>(u) * ld + j];
-                    float nv = 0.0f;
-                    for (int s = 0; s < num_splits; ++s)
-                        nv += __ldcs(num + s * num_stride + static_cast<int64_t>(u) * ld_part + j);
-                    const float dv = __ldcs(den + static_cast<int64_t>(u) * ld_part + j);
-                    gv = fmaf(l2, fv, dv) - (nv - l1);
-                }
-                g_s[c * kpad + u] = gv;
-                f_s[c * kpad + u] = fv;
+        for (int idx = threadIdx.x; idx < k * kFastTile; idx += kFastWarps * 32) {
+            const int u = idx / kFastTile, c = idx - u * kFastTile;
+            const int64_t j = j0 + c;
+            float fv = 0.0f, gv = 0.0f;
+            if (j < cols) {
+                fv = f[static_cast<int64_t>(u) * ld + j];
+                float nv = 0.0f;
+                for (int s = 0; s < num_splits; ++s)
+                    nv += __ldcs(num + s * num_stride + static_cast<int64_t>(u) * ld_part + j);
+                const float dv = __ldcs(den + static_cast<int64_t>(u) * ld_part + j);
+                gv = fmaf(l2, fv, dv) - (nv - l1);
             }
+            g_s[c * kpad + u] = gv;
+            f_s[c * kpad + u] = fv;
         }
         __syncthreads();
         // ---- phase 2: one warp = one column ------------------------------------------------------------
@@ -212,18 +209,14 @@ cd_sweep_smem_kernel(float* __restrict__ f, int k, int64_t cols, int64_t ld, con
         }
         __syncthreads();
         // ---- phase 3: store + per-row maxima --------------------------------------------------------------
-        {
-            const int half = lane >> 4, c = lane & 15;
+        for (int idx = threadIdx.x; idx < k * kFastTile; idx += kFastWarps * 32) {
+            const int u = idx / kFastTile, c = idx - u * kFastTile;
             const int64_t j = j0 + c;
-            const bool active = j < cols;
-            for (int u = warp * 2 + half; u < k; u += kFastWarps * 2) {
-                const float v = active ? f_s[c * kpad + u] : 0.0f;
-                if (active) f[static_cast<int64_t>(u) * ld + j] = v;
-                float m = v;
-                const unsigned half_mask = 0xFFFFu << (16 * half);
-#pragma unroll
-                for (int off = 8; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(half_mask, m, off));
-                if (c == 0 && m > 0.0f) atomicMax(&max_s[u], __float_as_uint(m));
+            if (j < cols) {
+                const float v = f_s[c * kpad + u];
+                f[static_cast<int64_t>(u) * ld + j] = v;
+                const unsigned int bits = __float_as_uint(v);
+                if (bits > max_s[u]) atomicMax(&max_s[u], bits);   // v >= 0: float order == uint order
             }
         }
     }

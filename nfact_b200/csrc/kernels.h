@@ -50,6 +50,9 @@ int split_factor(const float* f, int64_t k, int64_t cols, int64_t ld, const floa
 // out[t][j] = sum_s part[s][t][j] + bias     (t < k, j < cols)
 int reduce_partials(const float* part, int splits, int64_t split_stride, int64_t k, int64_t cols, int64_t ld,
                     float bias, float* out, int64_t ld_out, cudaStream_t stream);
+// out[j / slice_cols][t][j % slice_cols] = sum_s part[s][t][j]  (contiguous per-rank chunks for reduce-scatter)
+int reduce_partials_sliced(const float* part, int splits, int64_t split_stride, int64_t k, int64_t cols, int64_t ld,
+                           float* out, int64_t slice_cols, cudaStream_t stream);
 // multiplicative update of one factor (sklearn _multiplicative_update_w/_h, beta = 2):
 //   F[t][j] *= (sum_s num[s][t][j]) / den,  den = sum_s dpart[s][t][j] + l1 + l2 F[t][j], den == 0 -> eps
 // rowmax_bits[k] (zeroed by the caller) receives the new per-row maxima.

@@ -61,6 +61,8 @@ struct DevBuf {
 };
 
 typedef int (*NcclAllReduceFn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*NcclReduceScatterFn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*NcclAllGatherFn)(const void*, void*, size_t, int, void*, cudaStream_t);
 constexpr int kNcclFloat = 7, kNcclDouble = 8, kNcclSum = 0;
 
 }  // namespace nfb
@@ -79,6 +81,8 @@ struct nfb_handle {
     // multi-GPU (row-sharded) -------------------------------------------------
     void* comm = nullptr;
     NcclAllReduceFn allreduce = nullptr;
+    NcclReduceScatterFn reduce_scatter = nullptr;
+    NcclAllGatherFn all_gather = nullptr;
     int rank = 0, world = 1;
     void* nccl_lib = nullptr;
     bool own_comm = false;
@@ -150,6 +154,8 @@ struct nfb_nmf {
     Factor gw, gh;        // Gram matrices W'W and HH' (fp32 [kp][kp]); planes are only used as scratch
     Factor gd;            // planes of a Gram matrix with the K-side scales folded in (denominator GEMM)
     DevBuf<float> part_w, part_h, part_den, part_gram, num_h;
+    DevBuf<float> num_sl, pack;   // sharded runs: slice-major numerator / gather buffer [P][k][ns], packed slice
+    int64_t slice_cols = 0;       // ns: H columns per rank (multiple of 8)
     int s_w = 1, s_h = 1, s_gw = 1, s_gh = 1;
     double sumsq_global = 0.0;
     bool p1_valid = false;  // part_w holds X H' for the current H
@@ -213,8 +219,19 @@ static int gemm_xht(nfb_nmf* s) {
     return 0;
 }
 
-// part_h = W'X   (per split) for the current W planes; row-sharded runs reduce it across ranks
-static int gemm_wtx(nfb_nmf* s, const float** num_out, int* splits_out, int64_t* stride_out) {
+// part_h = W'X   (per split) for the current W planes.  Single GPU: the consumer sums the split slabs.
+// Row-sharded runs: the slabs are summed into a slice-major buffer [P][k][ns] and reduce-scattered, so
+// that rank r receives only the numerator of the H columns it will update (its slice).
+struct HNumerator {
+    const float* num;   // [splits][k][ld_part]
+    int splits;
+    int64_t stride;
+    int64_t ld_part;
+    int64_t col0;       // first H column this rank updates
+    int64_t width;      // number of H columns this rank updates
+};
+
+static int gemm_wtx(nfb_nmf* s, HNumerator* out) {
     nfb_handle* h = s->h;
     {
     GemmTimer timer(h);
@@ -223,30 +240,74 @@ static int gemm_wtx(nfb_nmf* s, const float** num_out, int* splits_out, int64_t*
                        h->cta_group, h->stream));
     }
     note_launch(1);
-    *num_out = s->part_h.p;
-    *splits_out = s->s_h;
-    *stride_out = static_cast<int64_t>(s->k) * s->hh.ld;
-    if (h->world > 1) {
-        NFB_TRY(reduce_partials(s->part_h.p, s->s_h, static_cast<int64_t>(s->k) * s->hh.ld, s->k, s->x->n, s->hh.ld,
-                                0.0f, s->num_h.p, s->hh.ld, h->stream));
+    const int64_t n = s->x->n;
+    if (h->world <= 1) {
+        *out = HNumerator{s->part_h.p, s->s_h, static_cast<int64_t>(s->k) * s->hh.ld, s->hh.ld, 0, n};
+        return 0;
+    }
+    if (h->reduce_scatter != nullptr && h->all_gather != nullptr) {
+        const int64_t ns = s->slice_cols;
+        NFB_TRY(reduce_partials_sliced(s->part_h.p, s->s_h, static_cast<int64_t>(s->k) * s->hh.ld, s->k, n, s->hh.ld,
+                                       s->num_sl.p, ns, h->stream));
         note_launch(1);
-        NFB_TRY(allreduce_f32(h, s->num_h.p, static_cast<size_t>(s->k) * s->hh.ld));
-        *num_out = s->num_h.p;
-        *splits_out = 1;
+        int rc = h->reduce_scatter(s->num_sl.p, s->num_h.p, static_cast<size_t>(s->k) * ns, kNcclFloat, kNcclSum,
+                                   h->comm, h->stream);
+        NFB_CHECK(rc == 0, "ncclReduceScatter failed with code " + std::to_string(rc));
+        const int64_t c0 = std::min<int64_t>(n, h->rank * ns);
+        *out = HNumerator{s->num_h.p, 1, 0, ns, c0, std::min<int64_t>(ns, n - c0)};
+        return 0;
+    }
+    // communicator without reduce-scatter / all-gather: replicate the H update on every rank
+    NFB_TRY(reduce_partials(s->part_h.p, s->s_h, static_cast<int64_t>(s->k) * s->hh.ld, s->k, n, s->hh.ld, 0.0f,
+                            s->num_h.p, s->hh.ld, h->stream));
+    note_launch(1);
+    NFB_TRY(allreduce_f32(h, s->num_h.p, static_cast<size_t>(s->k) * s->hh.ld));
+    *out = HNumerator{s->num_h.p, 1, 0, s->hh.ld, 0, n};
+    return 0;
+}
+
+// after a sliced H update: every rank contributes its columns, everyone ends up with the full H
+static int gather_h_slices(nfb_nmf* s, const HNumerator& hn) {
+    nfb_handle* h = s->h;
+    if (h->world <= 1 || hn.width == s->x->n) return 0;
+    const int64_t ns = s->slice_cols, n = s->x->n;
+    if (hn.width > 0)
+        NFB_CUDA(cudaMemcpy2DAsync(s->pack.p, ns * sizeof(float), s->hh.f.p + hn.col0, s->hh.ld * sizeof(float),
+                                   hn.width * sizeof(float), s->k, cudaMemcpyDeviceToDevice, h->stream));
+    int rc = h->all_gather(s->pack.p, s->num_sl.p, static_cast<size_t>(s->k) * ns, kNcclFloat, h->comm, h->stream);
+    NFB_CHECK(rc == 0, "ncclAllGather failed with code " + std::to_string(rc));
+    for (int r = 0; r < h->world; ++r) {
+        if (r == h->rank) continue;
+        const int64_t c0 = std::min<int64_t>(n, r * ns), width = std::min<int64_t>(ns, n - c0);
+        if (width <= 0) continue;
+        NFB_CUDA(cudaMemcpy2DAsync(s->hh.f.p + c0, s->hh.ld * sizeof(float),
+                                   s->num_sl.p + static_cast<int64_t>(r) * s->k * ns, ns * sizeof(float),
+                                   width * sizeof(float), s->k, cudaMemcpyDeviceToDevice, h->stream));
     }
     return 0;
 }
 
-// denominator of the multiplicative update: part_den[t][j] = sum_r G[t][r] F[r][j]
-static int gemm_den(nfb_nmf* s, Factor& fac, Factor& gram) {
+// G F for the columns [col0, col0 + width) of F:  part_den[t][j] = sum_r G[t][r] F[r][col0 + j]
+// (denominator of the multiplicative update; seed of the coordinate-descent gradient)
+static int gemm_den(nfb_nmf* s, Factor& fac, Factor& gram, int64_t col0, int64_t width, int64_t ld_out) {
     nfb_handle* h = s->h;
     // fold the per-component scales of F's planes (the K side of this product) into G's columns
     NFB_TRY(refresh_planes(s->gd, gram.f.p, fac.inv_scale.p, true, h->stream));
-    GemmOperand a = fac.operand();
-    a.rows = fac.k;
-    NFB_TRY(gemm_split(a, true, s->gd.operand(), fac.dim, fac.k, static_cast<int>(s->kp), s->k, s->part_den.p,
-                       fac.ld, 1, s->gd.inv_scale.p, nullptr, 1.0f, h->cta_group, h->stream));
+    if (width <= 0) return 0;
+    GemmOperand a{fac.hi.p + col0, fac.lo.p + col0, fac.k, fac.ld};
+    NFB_TRY(gemm_split(a, true, s->gd.operand(), width, fac.k, static_cast<int>(s->kp), s->k, s->part_den.p, ld_out,
+                       1, s->gd.inv_scale.p, nullptr, 1.0f, h->cta_group, h->stream));
     note_launch(1);
+    return 0;
+}
+
+// refresh planes + Gram of H after its update (slices gathered first in sharded runs)
+static int finish_h(nfb_nmf* s, const HNumerator& hn) {
+    nfb_handle* h = s->h;
+    const bool sliced = hn.width != s->x->n;
+    NFB_TRY(gather_h_slices(s, hn));
+    NFB_TRY(refresh_planes(s->hh, s->hh.f.p, nullptr, sliced, h->stream));
+    NFB_TRY(compute_gram(s, s->hh, s->gh, s->s_gh, false));
     return 0;
 }
 
@@ -255,7 +316,7 @@ static int mu_iteration(nfb_nmf* s) {
     const nfb_nmf_params& p = s->p;
     if (!s->p1_valid) NFB_TRY(gemm_xht(s));
     // ---- W half-step ----
-    NFB_TRY(gemm_den(s, s->wt, s->gh));
+    NFB_TRY(gemm_den(s, s->wt, s->gh, 0, s->x->m, s->wt.ld));
     NFB_CUDA(cudaMemsetAsync(s->wt.rowmax.p, 0, sizeof(unsigned int) * s->kp, h->stream));
     NFB_TRY(mu_update(s->wt.f.p, s->k, s->x->m, s->wt.ld, s->part_w.p, s->s_w, static_cast<int64_t>(s->k) * s->wt.ld,
                       s->part_den.p, 1, 0, s->wt.ld, static_cast<float>(p.l1_reg_W), static_cast<float>(p.l2_reg_W),
@@ -265,18 +326,17 @@ static int mu_iteration(nfb_nmf* s) {
     NFB_TRY(refresh_planes(s->wt, s->wt.f.p, nullptr, false, h->stream));
     NFB_TRY(compute_gram(s, s->wt, s->gw, s->s_gw, true));
     // ---- H half-step ----
-    const float* num;
-    int num_splits;
-    int64_t num_stride;
-    NFB_TRY(gemm_wtx(s, &num, &num_splits, &num_stride));
-    NFB_TRY(gemm_den(s, s->hh, s->gw));
+    HNumerator hn;
+    NFB_TRY(gemm_wtx(s, &hn));
+    NFB_TRY(gemm_den(s, s->hh, s->gw, hn.col0, hn.width, hn.ld_part));
     NFB_CUDA(cudaMemsetAsync(s->hh.rowmax.p, 0, sizeof(unsigned int) * s->kp, h->stream));
-    NFB_TRY(mu_update(s->hh.f.p, s->k, s->x->n, s->hh.ld, num, num_splits, num_stride, s->part_den.p, 1, 0,
-                      s->hh.ld, static_cast<float>(p.l1_reg_H), static_cast<float>(p.l2_reg_H), s->hh.rowmax.p,
-                      h->stream));
-    note_launch(1);
-    NFB_TRY(refresh_planes(s->hh, s->hh.f.p, nullptr, false, h->stream));
-    NFB_TRY(compute_gram(s, s->hh, s->gh, s->s_gh, false));
+    if (hn.width > 0) {
+        NFB_TRY(mu_update(s->hh.f.p + hn.col0, s->k, hn.width, s->hh.ld, hn.num, hn.splits, hn.stride, s->part_den.p,
+                          1, 0, hn.ld_part, static_cast<float>(p.l1_reg_H), static_cast<float>(p.l2_reg_H),
+                          s->hh.rowmax.p, h->stream));
+        note_launch(1);
+    }
+    NFB_TRY(finish_h(s, hn));
     return 0;
 }
 
@@ -287,7 +347,7 @@ static int cd_iteration(nfb_nmf* s, double* violation_out) {
     NFB_CUDA(cudaMemsetAsync(h->d_scal.p + 2, 0, 2 * sizeof(double), h->stream));
     if (!s->p1_valid) NFB_TRY(gemm_xht(s));
     // ---- W half-step ----
-    NFB_TRY(gemm_den(s, s->wt, s->gh));  // G_H W^T seeds the per-row gradient
+    NFB_TRY(gemm_den(s, s->wt, s->gh, 0, s->x->m, s->wt.ld));  // G_H W^T seeds the per-row gradient
     NFB_CUDA(cudaMemsetAsync(s->wt.rowmax.p, 0, sizeof(unsigned int) * s->kp, h->stream));
     NFB_TRY(cd_sweep(s->wt.f.p, s->k, s->x->m, s->wt.ld, s->part_w.p, s->s_w, static_cast<int64_t>(s->k) * s->wt.ld,
                      s->part_den.p, s->wt.ld, s->gh.f.p, static_cast<float>(p.l1_reg_W),
@@ -297,20 +357,21 @@ static int cd_iteration(nfb_nmf* s, double* violation_out) {
     NFB_TRY(refresh_planes(s->wt, s->wt.f.p, nullptr, false, h->stream));
     NFB_TRY(compute_gram(s, s->wt, s->gw, s->s_gw, true));
     // ---- H half-step ----
-    const float* num;
-    int num_splits;
-    int64_t num_stride;
-    NFB_TRY(gemm_wtx(s, &num, &num_splits, &num_stride));
-    NFB_TRY(gemm_den(s, s->hh, s->gw));
+    HNumerator hn;
+    NFB_TRY(gemm_wtx(s, &hn));
+    NFB_TRY(gemm_den(s, s->hh, s->gw, hn.col0, hn.width, hn.ld_part));
     NFB_CUDA(cudaMemsetAsync(s->hh.rowmax.p, 0, sizeof(unsigned int) * s->kp, h->stream));
-    NFB_TRY(cd_sweep(s->hh.f.p, s->k, s->x->n, s->hh.ld, num, num_splits, num_stride, s->part_den.p, s->hh.ld,
-                     s->gw.f.p, static_cast<float>(p.l1_reg_H), static_cast<float>(p.l2_reg_H), h->d_scal.p + 3,
-                     s->hh.rowmax.p, h->stream));
-    note_launch(1);
-    NFB_TRY(refresh_planes(s->hh, s->hh.f.p, nullptr, false, h->stream));
-    NFB_TRY(compute_gram(s, s->hh, s->gh, s->s_gh, false));
+    if (hn.width > 0) {
+        NFB_TRY(cd_sweep(s->hh.f.p + hn.col0, s->k, hn.width, s->hh.ld, hn.num, hn.splits, hn.stride, s->part_den.p,
+                         hn.ld_part, s->gw.f.p, static_cast<float>(p.l1_reg_H), static_cast<float>(p.l2_reg_H),
+                         h->d_scal.p + 3, s->hh.rowmax.p, h->stream));
+        note_launch(1);
+    }
+    NFB_TRY(finish_h(s, hn));
     if (violation_out != nullptr) {
-        NFB_TRY(allreduce_f64(h, h->d_scal.p + 2, 1));  // W rows are sharded, H is replicated
+        // W rows are sharded; H columns are sharded too when the update was sliced, replicated otherwise
+        const bool h_sliced = hn.width != s->x->n;
+        NFB_TRY(allreduce_f64(h, h->d_scal.p + 2, h_sliced ? 2 : 1));
         NFB_CUDA(cudaMemcpyAsync(h->h_scal + 2, h->d_scal.p + 2, 2 * sizeof(double), cudaMemcpyDeviceToHost,
                                  h->stream));
         NFB_CUDA(cudaStreamSynchronize(h->stream));
@@ -459,6 +520,8 @@ int nfb_nccl_init_rank(nfb_handle* h, const char* libnccl_path, const void* id, 
     NFB_CHECK(rc == 0, "ncclCommInitRank failed with code " + std::to_string(rc));
     h->nccl_lib = lib;
     h->own_comm = true;
+    h->reduce_scatter = reinterpret_cast<NcclReduceScatterFn>(dlsym(lib, "ncclReduceScatter"));
+    h->all_gather = reinterpret_cast<NcclAllGatherFn>(dlsym(lib, "ncclAllGather"));
     return nfb_set_comm(h, comm, ar, rank, world_size);
 }
 
@@ -618,7 +681,12 @@ int nfb_nmf_create(nfb_handle* h, const nfb_matrix* x, int k, const nfb_nmf_para
     NFB_TRY(s->part_h.alloc(static_cast<size_t>(s->s_h) * k * s->hh.ld, false, st));
     NFB_TRY(s->part_den.alloc(static_cast<size_t>(k) * std::max(s->wt.ld, s->hh.ld), false, st));
     NFB_TRY(s->part_gram.alloc(static_cast<size_t>(std::max(s->s_gw, s->s_gh)) * k * s->kp, false, st));
-    if (h->world > 1) NFB_TRY(s->num_h.alloc(static_cast<size_t>(k) * s->hh.ld, false, st));
+    if (h->world > 1) {
+        s->slice_cols = round_up64(ceil_div64(x->n, h->world), 8);
+        NFB_TRY(s->num_h.alloc(static_cast<size_t>(k) * std::max<int64_t>(s->hh.ld, s->slice_cols), true, st));
+        NFB_TRY(s->num_sl.alloc(static_cast<size_t>(h->world) * k * s->slice_cols, true, st));
+        NFB_TRY(s->pack.alloc(static_cast<size_t>(k) * s->slice_cols, true, st));
+    }
     // ||X||^2 over all row shards
     h->h_scal[5] = x->sumsq;
     if (h->world > 1) {

@@ -23,6 +23,20 @@ __global__ void reduce_partials_kernel(const float* __restrict__ part, int split
     }
 }
 
+// out[(j / slice_cols)][t][j % slice_cols] = sum_s part[s][t][j]   (slice-major layout for reduce-scatter)
+__global__ void reduce_partials_sliced_kernel(const float* __restrict__ part, int splits, int64_t split_stride,
+                                              int64_t k, int64_t cols, int64_t ld, float* __restrict__ out,
+                                              int64_t slice_cols) {
+    const int64_t t = blockIdx.y;
+    for (int64_t j = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; j < cols;
+         j += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        float acc = 0.0f;
+        for (int s = 0; s < splits; ++s) acc += part[s * split_stride + t * ld + j];
+        const int64_t slice = j / slice_cols;
+        out[(slice * k + t) * slice_cols + (j - slice * slice_cols)] = acc;
+    }
+}
+
 // sklearn/decomposition/_nmf.py:521-626 and :629-723 (beta_loss == 2, gamma == 1); four consecutive
 // columns per thread (128-bit loads: every buffer has a leading dimension that is a multiple of 8).
 __device__ __forceinline__ float mu_one(float old, float numerator, float denominator, float l1, float l2) {
@@ -175,6 +189,15 @@ int reduce_partials(const float* part, int splits, int64_t split_stride, int64_t
     if (k * cols == 0) return 0;
     reduce_partials_kernel<<<dim3(col_blocks(cols, 256, 1024), static_cast<unsigned>(k)), 256, 0, stream>>>(
         part, splits, split_stride, cols, ld, bias, out, ld_out);
+    NFB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int reduce_partials_sliced(const float* part, int splits, int64_t split_stride, int64_t k, int64_t cols, int64_t ld,
+                           float* out, int64_t slice_cols, cudaStream_t stream) {
+    if (k * cols == 0) return 0;
+    reduce_partials_sliced_kernel<<<dim3(col_blocks(cols, 256, 1024), static_cast<unsigned>(k)), 256, 0, stream>>>(
+        part, splits, split_stride, k, cols, ld, out, slice_cols);
     NFB_CUDA(cudaGetLastError());
     return 0;
 }

@@ -1,0 +1,65 @@
+"""Multi-GPU parity (run under torchrun, one rank per GPU):
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tests/dist_parity_gpu.py
+Row-sharded MU and CD iterations (W shards local, H columns sliced over ranks, NCCL reduce-scatter /
+all-gather inside libnfact_b200) against the unsharded CPU oracle."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+from nfact_b200.device import DeviceMatrix, Handle, NmfState, make_params  # noqa: E402
+from nfact_b200.sharding import init_nccl_from_torch, row_range  # noqa: E402
+from oracle import nfact_oracle as orc  # noqa: E402
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    handle = Handle(local)
+    init_nccl_from_torch(handle)
+    rng = np.random.default_rng(3)
+    ok = True
+    for (m, n, k) in [(517, 1203, 23), (300, 77, 5)]:
+        Wt, Ht = rng.gamma(0.3, 1.0, (m, k)), rng.gamma(0.3, 1.0, (k, n))
+        X = (np.floor(300 * (Wt @ Ht)) * (rng.random((m, n)) < 0.4) * (1e8 / 1.5e7)).astype(np.float32)
+        W0, H0 = orc.init_random(X, k, 1)
+        regs = orc.compute_regularization(m, n, 0.01, "same", 0.7)
+        r0, r1 = row_range(m, rank, world)
+        xdev = DeviceMatrix.from_host(X[r0:r1], handle)
+        for solver in ("mu", "cd"):
+            st = NmfState(xdev, k, make_params(solver, 200, 0.0, regs))
+            st.set_factors(W0[r0:r1], H0)
+            viol = st.iterate(4, want_violation=(solver == "cd"))
+            err = st.error()
+            W, H = st.get_factors()
+            st.free()
+            rec = []
+            (orc.fit_mu if solver == "mu" else orc.fit_cd)(X, W0, H0, *regs, tol=0, max_iter=4, record=rec)
+            Wr, Hr = rec[-1][1], rec[-1][2]
+            ew = np.linalg.norm(W - Wr[r0:r1]) / np.linalg.norm(Wr[r0:r1])
+            eh = np.linalg.norm(H - Hr) / np.linalg.norm(Hr)
+            eref = orc.frob_error(X, Wr, Hr)
+            line = f"rank {rank} {m}x{n} k={k} {solver}: relW={ew:.2e} relH={eh:.2e} err={err:.6g} (oracle {eref:.6g})"
+            if solver == "cd":
+                line += f" violation={viol:.6g} (oracle {rec[-1][3]:.6g})"
+                ok &= abs(viol - rec[-1][3]) <= 1e-3 * rec[-1][3]
+            print(line, flush=True)
+            ok &= ew < 1e-4 and eh < 1e-4 and abs(err - eref) <= 1e-4 * eref
+        xdev.free()
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("DIST PARITY", "OK" if int(flag) == 1 else "FAILED", flush=True)
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()

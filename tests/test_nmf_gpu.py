@@ -166,17 +166,23 @@ def test_nndsvd_device_matches_sklearn(golden):
     assert rel_fro(H, golden["init_nndsvd_H"]) < 1e-3
 
 
-def test_nmf_sso_runs_on_resident_matrix(golden):
+def test_nmf_sso_runs_on_resident_matrix():
     """NMF-sso orchestration: N random solves share one resident X, clustering, final custom solve."""
     import nfact_b200
-    X = golden["ingest_group"]
-    p = dict(nfact_b200.get_parameters(None, "nmf", 6), max_iter=40)
-    res = nfact_b200.nmf_sso(X, p, {"no_sso": False, "iterations": 5, "n_cores": 1, "dim": 6, "outdir": "."})
+    rng = np.random.default_rng(12)
+    k = 4
+    Wp = rng.gamma(0.4, 1.0, (120, k)) * (rng.random((120, k)) < 0.4)
+    Hp = rng.gamma(0.4, 1.0, (k, 210)) * (rng.random((k, 210)) < 0.4)
+    X = (Wp @ Hp * 100 + 0.01 * rng.random((120, 210))).astype(np.float32)
+    p = dict(nfact_b200.get_parameters(None, "nmf", k), alpha_W=1e-4, max_iter=150)
+    res = nfact_b200.nmf_sso(X, p, {"no_sso": False, "iterations": 6, "n_cores": 1, "dim": k, "outdir": "."})
     kf = res["white_components"].shape[0]
-    assert 2 <= kf <= 6 and res["grey_components"].shape == (99, kf)
+    assert 2 <= kf <= k and res["grey_components"].shape == (120, kf)
     assert np.isfinite(res["white_components"]).all() and (res["grey_components"] >= 0).all()
+    rel = np.linalg.norm(X - res["grey_components"] @ res["white_components"]) / np.linalg.norm(X)
+    assert rel < 0.35
     single = nfact_b200.nmf_sso(X, dict(p, random_state=0), {"no_sso": True})
-    assert single["white_components"].shape == (6, 199)
+    assert single["white_components"].shape == (k, 210)
 
 
 @pytest.mark.parametrize("solver", ["mu", "cd"])
