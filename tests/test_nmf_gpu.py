@@ -181,7 +181,9 @@ def test_nmf_sso_runs_on_resident_matrix():
     assert np.isfinite(res["white_components"]).all() and (res["grey_components"] >= 0).all()
     rel = np.linalg.norm(X - res["grey_components"] @ res["white_components"]) / np.linalg.norm(X)
     assert rel < 0.35
-    single = nfact_b200.nmf_sso(X, dict(p, random_state=0), {"no_sso": True})
+    # nmf_sso mutates its parameter dict like the reference does (init -> custom): start from fresh ones
+    fresh = dict(nfact_b200.get_parameters(None, "nmf", k), alpha_W=1e-4, max_iter=50, random_state=0)
+    single = nfact_b200.nmf_sso(X, fresh, {"no_sso": True})
     assert single["white_components"].shape == (k, 210)
 
 
