@@ -100,6 +100,7 @@ int ingest_finalize(const double* acc, int64_t nelem, double recip, int apply_re
 // sol [k, ld_sol] fp64.  status[0] counts columns that hit the iteration cap.
 int nnls_gram_batched(const double* gram, int64_t k, const float* rhs, int rhs_splits, int64_t rhs_stride,
                       int64_t ld_rhs, int64_t cols, double* sol, int64_t ld_sol, int max_outer, int* status,
-                      cudaStream_t stream, unsigned long long* steps_total = nullptr);
+                      cudaStream_t stream, unsigned long long* steps_total = nullptr,
+                      unsigned long long* counter = nullptr);   // counter: device scratch for dynamic scheduling
 
 }  // namespace nfb

@@ -13,6 +13,7 @@
 // QP is unique, so on full-column-rank A the fixed point equals the active-set solution of scipy;
 // convergence is declared on the KKT residual max_t |pg_t| <= tol * max|r|.
 #include <algorithm>
+#include <utility>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -108,13 +109,149 @@ nnls_cd_kernel(const double* __restrict__ gram, int k, const float* __restrict__
     }
 }
 
+
+// ---- fast path: packed lower triangle of G (float64) resident in shared memory ----------------------
+// One CTA per SM, 24 warps, columns handed out dynamically (their sweep counts differ widely).  The
+// coordinate step has its slot (register index) as a compile-time constant, multiplies by a precomputed
+// 1/G[t][t] and reads row/column t of G from shared memory.
+constexpr int kNnlsWarps = 24;
+
+__device__ __forceinline__ int tri(int r, int c) { return r >= c ? r * (r + 1) / 2 + c : c * (c + 1) / 2 + r; }
+
+template <int KPL>
+__global__ void __launch_bounds__(kNnlsWarps * 32, 1)
+nnls_smem_kernel(const double* __restrict__ gram, int k, const float* __restrict__ rhs, int rhs_splits,
+                 int64_t rhs_stride, int64_t ld_rhs, int64_t cols, double* __restrict__ sol, int64_t ld_sol,
+                 int max_outer, double tol, int* __restrict__ status, unsigned long long* __restrict__ steps_total,
+                 unsigned long long* __restrict__ next_col) {
+    extern __shared__ double smd[];
+    double* g_tri = smd;                                 // k (k + 1) / 2
+    double* inv_diag = smd + k * (k + 1) / 2;            // k  (0 where G[t][t] <= 0)
+    const int lane = threadIdx.x & 31;
+    for (int idx = threadIdx.x; idx < k * k; idx += blockDim.x) {
+        const int r = idx / k, c = idx - r * k;
+        if (c <= r) g_tri[r * (r + 1) / 2 + c] = gram[idx];
+    }
+    for (int t = threadIdx.x; t < k; t += blockDim.x) {
+        const double d = gram[static_cast<int64_t>(t) * k + t];
+        inv_diag[t] = d > 0.0 ? 1.0 / d : 0.0;
+    }
+    __syncthreads();
+
+    for (;;) {
+        unsigned long long j = 0;
+        if (lane == 0) j = atomicAdd(next_col, 1ULL);
+        j = __shfl_sync(0xffffffffu, j, 0);
+        if (j >= static_cast<unsigned long long>(cols)) break;
+        double h[KPL], g[KPL];
+        double rmax = 0.0;
+#pragma unroll
+        for (int i = 0; i < KPL; ++i) {
+            const int t = lane + 32 * i;
+            double r = 0.0;
+            if (t < k)
+                for (int s = 0; s < rhs_splits; ++s) r += static_cast<double>(rhs[s * rhs_stride + t * ld_rhs + j]);
+            h[i] = 0.0;
+            g[i] = -r;
+            rmax = fmax(rmax, fabs(r));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) rmax = fmax(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
+        const double thresh = tol * rmax;
+        unsigned long long nsteps = 0;
+
+        // exact coordinate step on component t = 32 * I + o (I compile-time); returns |projected gradient|
+        auto step = [&](auto slot_tag, int o) -> double {
+            constexpr int I = decltype(slot_tag)::value;
+            const int t = 32 * I + o;
+            const double gt = shfl_d(g[I], o);
+            const double ht = shfl_d(h[I], o);
+            const double inv = inv_diag[t];
+            const double pg = (ht == 0.0) ? fmin(gt, 0.0) : gt;
+            const double hn = fmax(fma(-gt, inv, ht), 0.0);
+            const double delta = inv != 0.0 ? hn - ht : 0.0;
+            if (delta != 0.0) {  // warp-uniform
+#pragma unroll
+                for (int i = 0; i < KPL; ++i) {
+                    const int u = lane + 32 * i;
+                    if (u < k) g[i] = fma(delta, g_tri[tri(u, t)], g[i]);
+                }
+                if (lane == o) h[I] = hn;
+            }
+            return fabs(pg);
+        };
+
+        bool converged = (rmax == 0.0);
+        for (int outer = 0; outer < max_outer && !converged; ++outer) {
+            double viol = 0.0;
+            // full sweep: detects support changes
+            auto full = [&](auto slot_tag) {
+                constexpr int I = decltype(slot_tag)::value;
+                const int t_end = min(32, k - 32 * I);
+                for (int o = 0; o < t_end; ++o) viol = fmax(viol, step(slot_tag, o));
+            };
+            [&]<int... Is>(std::integer_sequence<int, Is...>) {
+                (full(std::integral_constant<int, Is>{}), ...);
+            }(std::make_integer_sequence<int, KPL>{});
+            nsteps += k;
+            if (viol <= thresh) { converged = true; break; }
+            // sweeps restricted to the current support
+            for (int inner = 0; inner < 64; ++inner) {
+                double iv = 0.0;
+                auto support = [&](auto slot_tag) {
+                    constexpr int I = decltype(slot_tag)::value;
+                    unsigned mask = __ballot_sync(0xffffffffu, h[I] > 0.0);
+                    nsteps += __popc(mask);
+                    while (mask) {
+                        const int o = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        iv = fmax(iv, step(slot_tag, o));
+                    }
+                };
+                [&]<int... Is>(std::integer_sequence<int, Is...>) {
+                    (support(std::integral_constant<int, Is>{}), ...);
+                }(std::make_integer_sequence<int, KPL>{});
+                if (iv <= thresh) break;
+            }
+        }
+        if (!converged && lane == 0) atomicAdd(status, 1);
+        if (lane == 0 && steps_total != nullptr) atomicAdd(steps_total, nsteps);
+#pragma unroll
+        for (int i = 0; i < KPL; ++i) {
+            const int t = lane + 32 * i;
+            if (t < k) sol[t * ld_sol + j] = h[i];
+        }
+    }
+}
+
 }  // namespace
 
 int nnls_gram_batched(const double* gram, int64_t k, const float* rhs, int rhs_splits, int64_t rhs_stride,
                       int64_t ld_rhs, int64_t cols, double* sol, int64_t ld_sol, int max_outer, int* status,
-                      cudaStream_t stream, unsigned long long* steps_total) {
+                      cudaStream_t stream, unsigned long long* steps_total, unsigned long long* counter) {
     if (k == 0 || cols == 0) return 0;
     NFB_CHECK(k <= 512, "n_components > 512 is not supported by the NNLS kernel");
+    const size_t smem_fast = (static_cast<size_t>(k) * (k + 1) / 2 + k) * sizeof(double);
+    if (smem_fast <= 220 * 1024 && k <= 224 && counter != nullptr) {
+        NFB_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream));
+        const int grid = static_cast<int>(std::min<int64_t>(ceil_div64(cols, kNnlsWarps), sm_count()));
+#define NFB_NNLS_FAST(KPL)                                                                                       \
+    do {                                                                                                         \
+        auto kernel = nnls_smem_kernel<KPL>;                                                                     \
+        NFB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,                       \
+                                      static_cast<int>(smem_fast)));                                             \
+        kernel<<<grid, kNnlsWarps * 32, smem_fast, stream>>>(gram, static_cast<int>(k), rhs, rhs_splits,         \
+                                                             rhs_stride, ld_rhs, cols, sol, ld_sol, max_outer,   \
+                                                             1e-10, status, steps_total, counter);               \
+    } while (0)
+        if (k <= 32) NFB_NNLS_FAST(1);
+        else if (k <= 64) NFB_NNLS_FAST(2);
+        else if (k <= 128) NFB_NNLS_FAST(4);
+        else NFB_NNLS_FAST(7);
+#undef NFB_NNLS_FAST
+        NFB_CUDA(cudaGetLastError());
+        return 0;
+    }
     const int threads = 128;
     const int64_t warps_needed = cols;
     const int blocks = static_cast<int>(std::max<int64_t>(

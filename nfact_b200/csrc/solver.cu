@@ -868,7 +868,8 @@ int nfb_dual_regression_host(nfb_handle* h, const nfb_matrix* x, int k, const do
     NFB_TRY(gemm_split(x->operand(), true, gt.operand(), n, m, static_cast<int>(kp), k, part.p, hs.ld, s1,
                        gt.inv_scale.p, nullptr, x->inv_scale_host, cg, st));
     NFB_TRY(nnls_gram_batched(gram64.p, k, part.p, s1, static_cast<int64_t>(k) * hs.ld, hs.ld, n, sol_h.p, hs.ld,
-                              400, h->d_int.p, st, reinterpret_cast<unsigned long long*>(h->d_scal.p + 8)));
+                              400, h->d_int.p, st, reinterpret_cast<unsigned long long*>(h->d_scal.p + 8),
+                              reinterpret_cast<unsigned long long*>(h->d_scal.p + 10)));
     // ---- stage 2: grey matter.  Gs[i, :] = nnls(Hs, X[i, :])    (dual_regression_methods.py:151-163)
     NFB_CUDA(cudaMemsetAsync(hs.rowmax.p, 0, sizeof(unsigned int) * kp, st));
     NFB_TRY(f64_to_f32_rowmax(sol_h.p, k, n, hs.ld, hs.f.p, hs.ld, hs.rowmax.p, st));
@@ -877,7 +878,8 @@ int nfb_dual_regression_host(nfb_handle* h, const nfb_matrix* x, int k, const do
     NFB_TRY(gemm_split(x->operand(), false, hs.operand(), m, n, static_cast<int>(kp), k, part.p, gt.ld, s2,
                        hs.inv_scale.p, nullptr, x->inv_scale_host, cg, st));
     NFB_TRY(nnls_gram_batched(gram64.p, k, part.p, s2, static_cast<int64_t>(k) * gt.ld, gt.ld, m, sol_g.p, gt.ld,
-                              400, h->d_int.p + 1, st, reinterpret_cast<unsigned long long*>(h->d_scal.p + 9)));
+                              400, h->d_int.p + 1, st, reinterpret_cast<unsigned long long*>(h->d_scal.p + 9),
+                              reinterpret_cast<unsigned long long*>(h->d_scal.p + 10)));
     // ---- results -------------------------------------------------------------------------------------
     if (hs_out)
         NFB_CUDA(cudaMemcpy2DAsync(hs_out, n * sizeof(double), sol_h.p, hs.ld * sizeof(double), n * sizeof(double), k,
