@@ -140,7 +140,7 @@ class ClockSampler:
 # reference CPU path: sklearn.decomposition.NMF called exactly as NFACT does
 # (NFACT/decomp/decomposition/sso/nmfsso.py:54-56 with get_parameters defaults), on a bounded row sample.
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_seconds_per_iter(m, n, k, density, solver, budget_rows=(1024, 4096)):
+def cpu_reference_seconds_per_iter(m, n, k, density, solver, budget_rows=(512, 8192)):
     """Fit t(m_s) = a*m_s + b from two row samples (per-iteration slope between max_iter=1 and 3) and
     extrapolate to the full m: the H half-step costs do not shrink with the row sample."""
     import warnings
@@ -149,9 +149,11 @@ def cpu_reference_seconds_per_iter(m, n, k, density, solver, budget_rows=(1024, 
     h_star = rng.gamma(0.3, 1.0, (k, n)).astype(np.float32)
     per_iter = []
     for ms in budget_rows:
+        ms = min(ms, m)
         w_star = rng.gamma(0.3, 1.0, (ms, k)).astype(np.float32)
-        x = np.floor(300.0 * (w_star @ h_star)) * (rng.random((ms, n)) < density)
-        x = (x * (1e8 / 1.5e7)).astype(np.float32)
+        x = np.floor(300.0 * (w_star @ h_star))
+        x *= rng.random((ms, n), dtype=np.float32) < density
+        x *= np.float32(1e8 / 1.5e7)
         avg = np.sqrt(x.mean() / k)
         w0 = np.abs(avg * rng.standard_normal((ms, k))).astype(np.float32)
         h0 = np.abs(avg * rng.standard_normal((k, n))).astype(np.float32)
@@ -166,7 +168,9 @@ def cpu_reference_seconds_per_iter(m, n, k, density, solver, budget_rows=(1024, 
                 est.fit_transform(x, W=w0.copy(), H=h0.copy())
             times[iters] = time.perf_counter() - t0
         per_iter.append((times[3] - times[1]) / 2.0)
-    (m1, m2), (t1, t2) = budget_rows, per_iter
+    (m1, m2), (t1, t2) = (min(budget_rows[0], m), min(budget_rows[1], m)), per_iter
+    if m2 == m1:
+        return t2, per_iter
     a = (t2 - t1) / (m2 - m1)
     b = t1 - a * m1
     if a <= 0:   # noise swamped the slope: fall back to the m-independent part only (favours the CPU)
@@ -183,10 +187,43 @@ def cpu_baseline(m, n, k, density, solver):
     return {
         "value": 1.0 / full, "unit": UNIT, "cores": int(threads), "kind": "reference",
         "sample": (f"sklearn {__import__('sklearn').__version__} NMF(init=custom, solver={solver}, NFACT default "
-                   f"alpha_W/l1_ratio) as called by NFACT nmfsso.py:54-56, on row samples of 1024 and 4096 seeds x "
+                   f"alpha_W/l1_ratio) as called by NFACT nmfsso.py:54-56, on row samples of 512 and 8192 seeds x "
                    f"{n} targets, k={k}; seconds/iter from the max_iter 1->3 slope ({samples[0]:.3f}s, "
                    f"{samples[1]:.3f}s), linear fit in m extrapolated to m={m}; host cpu_count={os.cpu_count()}"),
     }
+
+
+def ingest_benchmark(handle):
+    """Group-average ingest (a2-a5) of 3 synthetic C1-shaped subjects (5000 x 10000, 15 % nnz, integer counts
+    with duplicates): host COO triplets -> dense float32 on the host, through nfb_ingest_coo; beside it the
+    reference arithmetic (scipy csc build + sparse adds + toarray, NFACT avg_fdt) on the host cores."""
+    import scipy.sparse as sps
+    from nfact_b200.device import ingest_coo
+    rng = np.random.default_rng(5)
+    nrows, ncols, nnz = 5000, 10000, int(5000 * 10000 * 0.15)
+    subjects = []
+    for sub in range(3):
+        rows = rng.integers(0, nrows, nnz, dtype=np.int32)
+        cols = rng.integers(0, ncols, nnz, dtype=np.int32)
+        vals = rng.integers(1, 500, nnz).astype(np.float64)
+        subjects.append((rows, cols, vals, 1e8 / (1.0e7 + 1.25e5 * sub)))
+    ingest_coo(subjects[:1], nrows, ncols, False, handle)          # warm-up
+    t0 = time.perf_counter()
+    x_gpu = ingest_coo(subjects, nrows, ncols, True, handle)
+    t_gpu = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    acc = None
+    for rows, cols, vals, scale in subjects:
+        mat = sps.csc_matrix((vals, (rows, cols)), shape=(nrows, ncols)).multiply(scale)
+        acc = mat.copy() if acc is None else acc + mat
+    acc /= len(subjects)
+    x_ref = acc.toarray().astype(np.float32)
+    t_ref = time.perf_counter() - t0
+    total = 3 * nnz
+    return {"triplets": total, "shape": [nrows, ncols], "subjects": 3, "seconds": t_gpu,
+            "value": total / t_gpu, "unit": "triplets/s", "bit_exact_vs_scipy": bool(np.array_equal(x_gpu, x_ref)),
+            "reference_seconds": t_ref, "reference_value": total / t_ref,
+            "api": "nfb_ingest_coo (host triplets in, host float32 matrix out)"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -351,6 +388,8 @@ def run_ours(args):
         line["e2e"] = e2e
         if dr_info is not None:
             line["dual_regression"] = dr_info
+    if world == 1 and not args.no_e2e:
+        line["ingest"] = ingest_benchmark(handle)
     if not args.no_cpu and world == 1:
         line["cpu_baseline"] = cpu_baseline(m, n, k, density, args.solver)
     print(json.dumps(line), flush=True)
