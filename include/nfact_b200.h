@@ -56,6 +56,15 @@ int nfb_ingest_coo(nfb_handle* h, int n_subjects, const int32_t* const* rows_hos
                    const double* const* vals_host, const int64_t* nnz, const double* scale, int64_t nrows,
                    int64_t ncols, int group_mode, float* x_out_host, float* x_out_dev);
 
+/* Text parser for fdt_matrix2.dot (replaces np.loadtxt at NFACT/base/matrix_handling.py:93-113).
+ * `buf` is the (decompressed) file content.  Two calls: count the non-empty lines, then fill three
+ * float64 arrays of that length with the row / column / value columns (the last line is the matrix
+ * shape, exactly as in the file).  Parsing is correctly rounded (std::from_chars) and multi-threaded;
+ * nthreads <= 0 uses all host cores.  A malformed line is an error, like loadtxt's ValueError. */
+int nfb_dot_count_lines(const char* buf, int64_t len, int nthreads, int64_t* n_lines_out);
+int nfb_dot_parse(const char* buf, int64_t len, int nthreads, int64_t n_lines, double* rows, double* cols,
+                  double* vals);
+
 /* ---- resident matrix --------------------------------------------------------------------------
  * X float32 [m, n] -> fp16 hi/lo planes in HBM (4 B/element, read by both X H' and W'X). */
 int nfb_matrix_from_host(nfb_handle* h, const float* x_host, int64_t m, int64_t n, nfb_matrix** out);

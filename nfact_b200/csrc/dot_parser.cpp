@@ -1,0 +1,142 @@
+// Multi-threaded parser for probtrackx `fdt_matrix2.dot` text (host code, part of libnfact_b200.so).
+//
+// Replaces the `np.loadtxt` call of NFACT/base/matrix_handling.py:93-113 (single-threaded, minutes per
+// subject).  Every line is `row col value` separated by blanks; numbers are parsed with
+// std::from_chars(double), which is correctly rounded like strtod / Python float(), so the float64 triplets
+// -- and therefore the bit-exact ingest downstream -- are identical to what np.loadtxt returns.
+#include <algorithm>
+#include <charconv>
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/nfact_b200.h"
+
+namespace nfb {
+void set_error(const std::string& msg);
+}
+
+namespace {
+
+inline bool is_blank(char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\v' || c == '\f'; }
+
+// number of non-empty lines in [begin, end)
+int64_t count_lines(const char* begin, const char* end) {
+    int64_t lines = 0;
+    bool content = false;
+    for (const char* p = begin; p < end; ++p) {
+        if (*p == '\n') {
+            lines += content;
+            content = false;
+        } else if (!is_blank(*p)) {
+            content = true;
+        }
+    }
+    return lines + (content ? 1 : 0);
+}
+
+// parse the lines of [begin, end) into out arrays starting at index `first`; returns lines parsed or -1
+int64_t parse_range(const char* begin, const char* end, int64_t first, double* rows, double* cols, double* vals) {
+    int64_t idx = first;
+    const char* p = begin;
+    while (p < end) {
+        while (p < end && (is_blank(*p) || *p == '\n')) ++p;
+        if (p >= end) break;
+        double field[3];
+        for (int f = 0; f < 3; ++f) {
+            while (p < end && is_blank(*p)) ++p;
+            if (p < end && *p == '+') ++p;  // from_chars rejects a leading '+', loadtxt accepts it
+            auto res = std::from_chars(p, end, field[f]);
+            if (res.ec != std::errc()) return -1;
+            p = res.ptr;
+        }
+        while (p < end && is_blank(*p)) ++p;
+        if (p < end && *p != '\n') return -1;  // more than three columns
+        rows[idx] = field[0];
+        cols[idx] = field[1];
+        vals[idx] = field[2];
+        ++idx;
+    }
+    return idx - first;
+}
+
+std::vector<const char*> chunk_starts(const char* buf, int64_t len, int nthreads) {
+    std::vector<const char*> starts;
+    starts.push_back(buf);
+    for (int t = 1; t < nthreads; ++t) {
+        const char* p = buf + len * t / nthreads;
+        const char* nl = static_cast<const char*>(memchr(p, '\n', static_cast<size_t>(buf + len - p)));
+        const char* s = nl ? nl + 1 : buf + len;
+        if (s > starts.back()) starts.push_back(s);
+    }
+    starts.push_back(buf + len);
+    return starts;
+}
+
+int pick_threads(int64_t len, int nthreads) {
+    if (nthreads <= 0) nthreads = static_cast<int>(std::thread::hardware_concurrency());
+    nthreads = std::max(1, std::min(nthreads, 64));
+    return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(nthreads, len / (1 << 20) + 1)));
+}
+
+}  // namespace
+
+extern "C" {
+
+int nfb_dot_count_lines(const char* buf, int64_t len, int nthreads, int64_t* n_lines_out) {
+    if (buf == nullptr || n_lines_out == nullptr || len < 0) {
+        nfb::set_error("nfb_dot_count_lines: bad arguments");
+        return 2;
+    }
+    nthreads = pick_threads(len, nthreads);
+    auto starts = chunk_starts(buf, len, nthreads);
+    std::vector<int64_t> counts(starts.size() - 1, 0);
+    std::vector<std::thread> pool;
+    for (size_t c = 0; c + 1 < starts.size(); ++c)
+        pool.emplace_back([&, c] { counts[c] = count_lines(starts[c], starts[c + 1]); });
+    for (auto& th : pool) th.join();
+    int64_t total = 0;
+    for (int64_t v : counts) total += v;
+    *n_lines_out = total;
+    return 0;
+}
+
+int nfb_dot_parse(const char* buf, int64_t len, int nthreads, int64_t n_lines, double* rows, double* cols,
+                  double* vals) {
+    if (buf == nullptr || rows == nullptr || cols == nullptr || vals == nullptr || len < 0) {
+        nfb::set_error("nfb_dot_parse: bad arguments");
+        return 2;
+    }
+    nthreads = pick_threads(len, nthreads);
+    auto starts = chunk_starts(buf, len, nthreads);
+    const size_t nchunks = starts.size() - 1;
+    std::vector<int64_t> counts(nchunks, 0), parsed(nchunks, 0);
+    {
+        std::vector<std::thread> pool;
+        for (size_t c = 0; c < nchunks; ++c)
+            pool.emplace_back([&, c] { counts[c] = count_lines(starts[c], starts[c + 1]); });
+        for (auto& th : pool) th.join();
+    }
+    std::vector<int64_t> first(nchunks + 1, 0);
+    for (size_t c = 0; c < nchunks; ++c) first[c + 1] = first[c] + counts[c];
+    if (first[nchunks] != n_lines) {
+        nfb::set_error("nfb_dot_parse: line count changed between the two passes");
+        return 2;
+    }
+    {
+        std::vector<std::thread> pool;
+        for (size_t c = 0; c < nchunks; ++c)
+            pool.emplace_back([&, c] { parsed[c] = parse_range(starts[c], starts[c + 1], first[c], rows, cols, vals); });
+        for (auto& th : pool) th.join();
+    }
+    for (size_t c = 0; c < nchunks; ++c)
+        if (parsed[c] != counts[c]) {
+            nfb::set_error("could not convert string to float: malformed line in fdt_matrix2.dot (expected 3 columns)");
+            return 2;
+        }
+    return 0;
+}
+
+}  // extern "C"

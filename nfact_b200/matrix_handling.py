@@ -22,28 +22,47 @@ CooMatrix = namedtuple("CooMatrix", "rows cols data shape scale")
 
 def read_in_matrix(matfile: str) -> np.ndarray:
     """NFACT/base/matrix_handling.py:93-113.  float64 [T+1, 3]; ``.lz4`` files need the lz4 module."""
+    return np.ascontiguousarray(parse_dot_bytes(_read_bytes(matfile), matfile).T)
+
+
+def _read_bytes(matfile: str) -> bytes:
     if matfile.endswith(".lz4"):
         import lz4.frame  # same optional dependency as the reference
         with lz4.frame.open(matfile, "rb") as fil:
-            raw = fil.read()
-    else:
-        with open(matfile, "rb") as fil:
-            raw = fil.read()
-    flat = np.array(raw.split(), dtype=np.float64)
-    if flat.size % 3 != 0 or flat.size < 3:
-        raise ValueError(f"{matfile}: expected 3 columns per line")
-    return flat.reshape(-1, 3)
+            return fil.read()
+    with open(matfile, "rb") as fil:
+        return fil.read()
+
+
+def parse_dot_bytes(raw: bytes, name: str = "<buffer>") -> np.ndarray:
+    """Native multi-threaded parse (libnfact_b200 ``nfb_dot_parse``): float64 [3, lines] = the row, column
+    and value columns of the file (``np.loadtxt(...).T``)."""
+    import ctypes
+    from . import _lib
+    lib = _lib.load()
+    buf = ctypes.c_char_p(raw)
+    n_lines = ctypes.c_int64()
+    _lib.check(lib.nfb_dot_count_lines(buf, len(raw), 0, ctypes.byref(n_lines)))
+    if n_lines.value == 0:
+        raise ValueError(f"{name}: file is empty")
+    cols3 = np.empty((3, n_lines.value), dtype=np.float64)
+    try:
+        _lib.check(lib.nfb_dot_parse(buf, len(raw), 0, n_lines.value, cols3[0].ctypes.data, cols3[1].ctypes.data,
+                                     cols3[2].ctypes.data))
+    except _lib.NfbError as e:
+        raise ValueError(f"{name}: {e}") from None
+    return cols3
 
 
 def load_single_matrix(matfile: str) -> CooMatrix:
     """NFACT/base/matrix_handling.py:116-140.  Returns the COO triplets (0-based) plus the
     ``1e8 / waytotal`` scale; the sparse-matrix arithmetic itself happens on the device."""
-    mat = read_in_matrix(matfile)
-    data = np.ascontiguousarray(mat[:-1, -1])
-    rows = np.array(mat[:-1, 0] - 1, dtype=np.int64)
-    cols = np.array(mat[:-1, 1] - 1, dtype=np.int64)
-    nrows = int(mat[-1, 0])
-    ncols = int(mat[-1, 1])
+    col_r, col_c, col_v = parse_dot_bytes(_read_bytes(matfile), matfile)   # column-wise: no [T,3] copy
+    data = np.ascontiguousarray(col_v[:-1])
+    rows = np.array(col_r[:-1] - 1, dtype=np.int64)
+    cols = np.array(col_c[:-1] - 1, dtype=np.int64)
+    nrows = int(col_r[-1])
+    ncols = int(col_c[-1])
     if rows.size and (rows.min() < 0 or cols.min() < 0):
         raise ValueError("negative row index found" if rows.min() < 0 else "negative column index found")
     if rows.size and rows.max() >= nrows:

@@ -84,3 +84,36 @@ def test_parameter_validation():
         nfact_b200.NMF(n_components=3, beta_loss="kullback-leibler")
     with pytest.raises(ValueError):
         nfact_b200.NMF(n_components=3, solver="xx")
+
+
+def test_native_dot_parser_matches_loadtxt(tmp_path):
+    """nfb_dot_parse == np.loadtxt on awkward but legal text; malformed input raises like loadtxt."""
+    import nfact_b200
+    text = ("1 101 117\n  2\t106   234.5  \n3 107 9.6e1\r\n\n4 5 +7\n5 6 1e-3\n6 7 0.1\n"
+            "7 8 12345678901234567890\n99 199 438")      # no trailing newline, a blank line, CRLF, tabs
+    path = tmp_path / "fdt_matrix2.dot"
+    path.write_text(text)
+    got = nfact_b200.read_in_matrix(str(path))
+    ref = np.loadtxt(str(path))
+    assert got.shape == ref.shape and np.array_equal(got, ref)
+    rng = np.random.default_rng(0)
+    big = tmp_path / "big.dot"
+    rows = rng.integers(1, 5000, 300000)
+    vals = rng.uniform(0, 1e6, 300000)
+    with open(big, "w") as fh:
+        for r, v in zip(rows, vals):
+            fh.write(f"{r} {r + 1} {float(v)!r}\n")
+        fh.write("5000 5001 0\n")
+    got = nfact_b200.read_in_matrix(str(big))
+    assert got.shape == (300001, 3)
+    assert np.array_equal(got[:-1, 2], vals) and np.array_equal(got[:-1, 0], rows.astype(np.float64))
+    bad = tmp_path / "bad.dot"
+    bad.write_text("1 2 3\n4 5\n6 7 8\n")
+    with pytest.raises(ValueError):
+        nfact_b200.read_in_matrix(str(bad))
+    bad.write_text("1 2 x\n")
+    with pytest.raises(ValueError):
+        nfact_b200.read_in_matrix(str(bad))
+    bad.write_text("")
+    with pytest.raises(ValueError):
+        nfact_b200.read_in_matrix(str(bad))
