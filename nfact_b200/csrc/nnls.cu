@@ -114,7 +114,7 @@ nnls_cd_kernel(const double* __restrict__ gram, int k, const float* __restrict__
 // One CTA per SM, 24 warps, columns handed out dynamically (their sweep counts differ widely).  The
 // coordinate step has its slot (register index) as a compile-time constant, multiplies by a precomputed
 // 1/G[t][t] and reads row/column t of G from shared memory.
-constexpr int kNnlsWarps = 24;
+constexpr int kNnlsWarps = 16;
 
 __device__ __forceinline__ int tri(int r, int c) { return r >= c ? r * (r + 1) / 2 + c : c * (c + 1) / 2 + r; }
 
@@ -195,23 +195,73 @@ nnls_smem_kernel(const double* __restrict__ gram, int k, const float* __restrict
             }(std::make_integer_sequence<int, KPL>{});
             nsteps += k;
             if (viol <= thresh) { converged = true; break; }
-            // sweeps restricted to the current support
-            for (int inner = 0; inner < 64; ++inner) {
-                double iv = 0.0;
-                auto support = [&](auto slot_tag) {
+            // ---- conjugate gradients on the current support P = {h > 0} --------------------------------
+            // Between two full sweeps the support is fixed and the problem is the linear system
+            // G_PP z = r_P: CG needs O(sqrt(cond)) products with G where coordinate sweeps need O(cond).
+            // The step is cut at the first component that would turn negative; that component leaves P
+            // and the outer loop (full sweep) re-examines the support.
+            double d[KPL], q[KPL];
+            bool in_p[KPL];
+            double rr = 0.0;
+#pragma unroll
+            for (int i = 0; i < KPL; ++i) {
+                in_p[i] = h[i] > 0.0;
+                d[i] = in_p[i] ? -g[i] : 0.0;
+                rr = fma(d[i], d[i], rr);
+            }
+            rr = warp_sum(rr);
+            const double rr_stop = 0.01 * thresh * thresh;
+            for (int it = 0; it < 2 * k && rr > rr_stop; ++it) {
+#pragma unroll
+                for (int i = 0; i < KPL; ++i) q[i] = 0.0;
+                auto accumulate = [&](auto slot_tag) {
                     constexpr int I = decltype(slot_tag)::value;
-                    unsigned mask = __ballot_sync(0xffffffffu, h[I] > 0.0);
+                    unsigned mask = __ballot_sync(0xffffffffu, d[I] != 0.0);
                     nsteps += __popc(mask);
                     while (mask) {
                         const int o = __ffs(mask) - 1;
                         mask &= mask - 1;
-                        iv = fmax(iv, step(slot_tag, o));
+                        const double dt = shfl_d(d[I], o);
+                        const int t = 32 * I + o;
+#pragma unroll
+                        for (int i = 0; i < KPL; ++i) {
+                            const int u = lane + 32 * i;
+                            if (u < k) q[i] = fma(dt, g_tri[tri(u, t)], q[i]);
+                        }
                     }
                 };
                 [&]<int... Is>(std::integer_sequence<int, Is...>) {
-                    (support(std::integral_constant<int, Is>{}), ...);
+                    (accumulate(std::integral_constant<int, Is>{}), ...);
                 }(std::make_integer_sequence<int, KPL>{});
-                if (iv <= thresh) break;
+                double dq = 0.0, amax = 1.0e300;
+#pragma unroll
+                for (int i = 0; i < KPL; ++i) {
+                    dq = fma(d[i], q[i], dq);
+                    if (in_p[i] && d[i] < 0.0) amax = fmin(amax, -h[i] / d[i]);
+                }
+                dq = warp_sum(dq);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) amax = fmin(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+                if (!(dq > 0.0)) break;                       // direction in the null space: leave it to the sweeps
+                double alpha = rr / dq;
+                const bool hit = alpha >= amax;
+                if (hit) alpha = amax;
+                double rr_new = 0.0;
+#pragma unroll
+                for (int i = 0; i < KPL; ++i) {
+                    const double h_new = fma(alpha, d[i], h[i]);
+                    g[i] = fma(alpha, q[i], g[i]);
+                    // a component that reached the bound (exactly, or within rounding of the cut step) leaves P
+                    const bool blocked = in_p[i] && d[i] < 0.0 && (h_new <= 0.0 || (hit && -h[i] / d[i] <= amax));
+                    h[i] = blocked ? 0.0 : h_new;
+                    if (in_p[i]) rr_new = fma(g[i], g[i], rr_new);
+                }
+                if (hit) break;
+                rr_new = warp_sum(rr_new);
+                const double beta = rr_new / rr;
+#pragma unroll
+                for (int i = 0; i < KPL; ++i) d[i] = in_p[i] ? fma(beta, d[i], -g[i]) : 0.0;
+                rr = rr_new;
             }
         }
         if (!converged && lane == 0) atomicAdd(status, 1);
