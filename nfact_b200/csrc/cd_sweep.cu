@@ -12,6 +12,7 @@
 // NFACT's L1 penalty produces are swept in ~k*nnz instead of k^2 operations, with the Gauss-Seidel
 // order of the reference kept exactly.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -227,6 +228,97 @@ cd_sweep_smem_kernel(float* __restrict__ f, int k, int64_t cols, int64_t ld, con
     if (threadIdx.x == 0 && total != 0.0) atomicAdd(violation, total);
 }
 
+
+// ---- thread-per-sample blocked sweep ------------------------------------------------------------------
+// One THREAD owns one sample (column j of F).  Its gradient vector lives in shared memory as gs[u][tid]
+// (conflict-free), components are processed in blocks of 16: the 16 coordinate steps of a block run in
+// registers against the 16 x 16 diagonal block of G, then the block's 16 deltas are applied to the rest of
+// the gradient, g[u] += sum_i delta_i G[t0+i][u], as 16 FMAs per entry with G broadcast from shared memory.
+// Same arithmetic as the rank-1 formulation above (exact Gauss-Seidel order), but the per-coordinate
+// bookkeeping is paid per thread instead of per warp: ~k^2/2 FMAs per sample at FMA-pipe throughput.
+constexpr int kBlk = 16;
+
+template <int TJ>
+__global__ void __launch_bounds__(TJ)
+cd_sweep_rows_kernel(float* __restrict__ f, int k, int64_t cols, int64_t ld, const float* __restrict__ num,
+                     int num_splits, int64_t num_stride, const float* __restrict__ den, int64_t ld_part,
+                     const float* __restrict__ gram, int ldg, float l1, float l2, double* __restrict__ violation,
+                     unsigned int* __restrict__ rowmax_bits) {
+    extern __shared__ float sm[];
+    __shared__ double scratch[32];
+    __shared__ float invh[kBlk];
+    float* gs = sm;                                   // [k][TJ]
+    float* gb = sm + static_cast<size_t>(k) * TJ;     // [k][kBlk]: gb[u][i] = G[t0 + i][u]
+    const int tid = threadIdx.x;
+    const int64_t j = static_cast<int64_t>(blockIdx.x) * TJ + tid;
+    const bool active = j < cols;
+    // ---- gradient seed: g = G F[:, j] + l2 F[:, j] - (num[:, j] - l1) ------------------------------------
+#pragma unroll 4
+    for (int u = 0; u < k; ++u) {
+        float gv = 0.0f;
+        if (active) {
+            const float fv = f[static_cast<int64_t>(u) * ld + j];
+            float nv = 0.0f;
+            for (int s = 0; s < num_splits; ++s) nv += __ldcs(num + s * num_stride + static_cast<int64_t>(u) * ld_part + j);
+            gv = fmaf(l2, fv, __ldcs(den + static_cast<int64_t>(u) * ld_part + j)) - (nv - l1);
+        }
+        gs[u * TJ + tid] = gv;
+    }
+    float viol = 0.0f;
+    for (int t0 = 0; t0 < k; t0 += kBlk) {
+        const int nb = min(kBlk, k - t0);
+        __syncthreads();   // previous block's readers of gb / invh are done
+        for (int e = tid; e < kBlk * k; e += TJ) {
+            const int i = e / k, u = e - i * k;
+            gb[u * kBlk + i] = i < nb ? gram[static_cast<int64_t>(t0 + i) * ldg + u] : 0.0f;
+        }
+        if (tid < kBlk) {
+            const float hess = tid < nb ? gram[static_cast<int64_t>(t0 + tid) * ldg + t0 + tid] + l2 : 0.0f;
+            invh[tid] = hess != 0.0f ? 1.0f / hess : 0.0f;
+        }
+        __syncthreads();
+        // ---- the 16 coordinate steps of this block, in registers -----------------------------------------
+        float gl[kBlk], dl[kBlk], fl[kBlk];
+#pragma unroll
+        for (int i = 0; i < kBlk; ++i) {
+            gl[i] = i < nb ? gs[(t0 + i) * TJ + tid] : 0.0f;
+            fl[i] = (i < nb && active) ? f[static_cast<int64_t>(t0 + i) * ld + j] : 0.0f;   // 16 loads in flight
+        }
+#pragma unroll
+        for (int i = 0; i < kBlk; ++i) {
+            float delta = 0.0f;
+            if (i < nb) {
+                const float ft = fl[i];
+                const float gt = gl[i];
+                viol += fabsf((ft == 0.0f) ? fminf(0.0f, gt) : gt);
+                const float inv = invh[i];
+                const float fn = fmaxf(fmaf(-gt, inv, ft), 0.0f);
+                delta = inv != 0.0f ? fn - ft : 0.0f;
+                if (active && delta != 0.0f) f[static_cast<int64_t>(t0 + i) * ld + j] = fn;
+                const float vmax = warp_max(active ? ft + delta : 0.0f);
+                if ((tid & 31) == 0 && vmax > 0.0f) atomicMax(&rowmax_bits[t0 + i], __float_as_uint(vmax));
+#pragma unroll
+                for (int i2 = i + 1; i2 < kBlk; ++i2) gl[i2] = fmaf(delta, gb[(t0 + i2) * kBlk + i], gl[i2]);
+            }
+            dl[i] = delta;
+        }
+        // ---- apply the block's deltas to the components still to come ------------------------------------
+#pragma unroll 4
+        for (int u = t0 + nb; u < k; ++u) {
+            const float4* grow = reinterpret_cast<const float4*>(gb + u * kBlk);
+            const float4 a = grow[0], b = grow[1], c = grow[2], d = grow[3];
+            float acc = gs[u * TJ + tid];
+            acc = fmaf(dl[0], a.x, acc);  acc = fmaf(dl[1], a.y, acc);  acc = fmaf(dl[2], a.z, acc);  acc = fmaf(dl[3], a.w, acc);
+            acc = fmaf(dl[4], b.x, acc);  acc = fmaf(dl[5], b.y, acc);  acc = fmaf(dl[6], b.z, acc);  acc = fmaf(dl[7], b.w, acc);
+            acc = fmaf(dl[8], c.x, acc);  acc = fmaf(dl[9], c.y, acc);  acc = fmaf(dl[10], c.z, acc); acc = fmaf(dl[11], c.w, acc);
+            acc = fmaf(dl[12], d.x, acc); acc = fmaf(dl[13], d.y, acc); acc = fmaf(dl[14], d.z, acc); acc = fmaf(dl[15], d.w, acc);
+            gs[u * TJ + tid] = acc;
+        }
+    }
+    const double total = block_sum(active ? static_cast<double>(viol) : 0.0, scratch);
+    if (tid == 0 && total != 0.0) atomicAdd(violation, total);
+}
+
 }  // namespace
 
 int cd_sweep(float* f, int64_t k, int64_t cols, int64_t ld, const float* num, int num_splits, int64_t num_stride,
@@ -236,6 +328,27 @@ int cd_sweep(float* f, int64_t k, int64_t cols, int64_t ld, const float* num, in
     NFB_CHECK(k <= 512, "n_components > 512 is not supported by the coordinate-descent kernel");
     const int ldg = static_cast<int>(round_up64(k, 16));
     const int kpad = static_cast<int>(k) | 1;
+    // preferred: thread-per-sample blocked sweep (largest tile whose gradient block fits in shared memory)
+    if (getenv("NFB_CD_KERNEL") == nullptr || atoi(getenv("NFB_CD_KERNEL")) == 0) {
+        auto smem_rows = [&](int tj) { return (static_cast<size_t>(k) * tj + static_cast<size_t>(k) * kBlk) * sizeof(float); };
+        auto run_rows = [&](auto tj_tag) -> int {
+            constexpr int TJ = decltype(tj_tag)::value;
+            auto kernel = cd_sweep_rows_kernel<TJ>;
+            const size_t smem = smem_rows(TJ);
+            NFB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+            kernel<<<static_cast<unsigned>(ceil_div64(cols, TJ)), TJ, smem, stream>>>(
+                f, static_cast<int>(k), cols, ld, num, num_splits, num_stride, den, ld_part, gram, ldg, l1, l2,
+                violation, rowmax_bits);
+            NFB_CUDA(cudaGetLastError());
+            return 0;
+        };
+        if (smem_rows(256) <= 224 * 1024 && cols >= 256 * static_cast<int64_t>(sm_count()))
+            return run_rows(std::integral_constant<int, 256>{});
+        if (smem_rows(128) <= 110 * 1024) return run_rows(std::integral_constant<int, 128>{});
+        if (smem_rows(256) <= 224 * 1024) return run_rows(std::integral_constant<int, 256>{});
+        if (smem_rows(128) <= 224 * 1024) return run_rows(std::integral_constant<int, 128>{});
+        if (smem_rows(64) <= 224 * 1024) return run_rows(std::integral_constant<int, 64>{});
+    }
     const int kpl_fast = k <= 32 ? 1 : k <= 64 ? 2 : k <= 128 ? 4 : 7;
     const size_t smem_fast = (static_cast<size_t>(k) * 32 * kpl_fast + 2 * k +
                               static_cast<size_t>(2) * kFastTile * kpad) * sizeof(float);

@@ -78,6 +78,9 @@ struct nfb_handle {
     // optional per-kernel timing of the two X-streaming GEMMs (CUDA events on the launch stream)
     bool profiling = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> gemm_events;
+    // NFB_PHASE_TIMING=1: CUDA events around every phase of an iteration (debug aid, printed by nfb_nmf_iterate)
+    bool phase_timing = false;
+    std::vector<std::pair<const char*, std::pair<cudaEvent_t, cudaEvent_t>>> phase_events;
     // multi-GPU (row-sharded) -------------------------------------------------
     void* comm = nullptr;
     NcclAllReduceFn allreduce = nullptr;
@@ -193,6 +196,45 @@ static int compute_gram(nfb_nmf* s, Factor& fac, Factor& gram, int splits, bool 
 }
 
 // part_w = X H'   (per split) for the current H planes
+struct PhaseTimer {
+    nfb_handle* h;
+    const char* name;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    PhaseTimer(nfb_handle* handle, const char* phase) : h(handle), name(phase) {
+        if (h->phase_timing && cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess)
+            cudaEventRecord(e0, h->stream);
+    }
+    ~PhaseTimer() {
+        if (e0 && e1) {
+            cudaEventRecord(e1, h->stream);
+            h->phase_events.push_back({name, {e0, e1}});
+        }
+    }
+};
+#define NFB_PHASE(handle, name) PhaseTimer phase_timer_##__LINE__(handle, name)
+
+static void report_phases(nfb_handle* h, int iters) {
+    if (!h->phase_timing || h->phase_events.empty()) return;
+    cudaStreamSynchronize(h->stream);
+    std::vector<std::pair<std::string, double>> totals;
+    for (auto& ev : h->phase_events) {
+        float ms = 0.0f;
+        cudaEventElapsedTime(&ms, ev.second.first, ev.second.second);
+        cudaEventDestroy(ev.second.first);
+        cudaEventDestroy(ev.second.second);
+        bool found = false;
+        for (auto& t : totals)
+            if (t.first == ev.first) { t.second += ms; found = true; }
+        if (!found) totals.push_back({ev.first, ms});
+    }
+    h->phase_events.clear();
+    double sum = 0.0;
+    for (auto& t : totals) sum += t.second;
+    fprintf(stderr, "nfact_b200 phases over %d iteration(s): ", iters);
+    for (auto& t : totals) fprintf(stderr, "%s=%.3f ms  ", t.first.c_str(), t.second / iters);
+    fprintf(stderr, "| sum=%.3f ms/iter\n", sum / iters);
+}
+
 struct GemmTimer {
     nfb_handle* h;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -314,29 +356,32 @@ static int finish_h(nfb_nmf* s, const HNumerator& hn) {
 static int mu_iteration(nfb_nmf* s) {
     nfb_handle* h = s->h;
     const nfb_nmf_params& p = s->p;
-    if (!s->p1_valid) NFB_TRY(gemm_xht(s));
+    if (!s->p1_valid) { NFB_PHASE(h, "gemm_xht"); NFB_TRY(gemm_xht(s)); }
     // ---- W half-step ----
-    NFB_TRY(gemm_den(s, s->wt, s->gh, 0, s->x->m, s->wt.ld));
+    { NFB_PHASE(h, "den_w"); NFB_TRY(gemm_den(s, s->wt, s->gh, 0, s->x->m, s->wt.ld)); }
     NFB_CUDA(cudaMemsetAsync(s->wt.rowmax.p, 0, sizeof(unsigned int) * s->kp, h->stream));
+    { NFB_PHASE(h, "update_w");
     NFB_TRY(mu_update(s->wt.f.p, s->k, s->x->m, s->wt.ld, s->part_w.p, s->s_w, static_cast<int64_t>(s->k) * s->wt.ld,
                       s->part_den.p, 1, 0, s->wt.ld, static_cast<float>(p.l1_reg_W), static_cast<float>(p.l2_reg_W),
                       s->wt.rowmax.p, h->stream));
+    }
     note_launch(1);
     s->p1_valid = false;
-    NFB_TRY(refresh_planes(s->wt, s->wt.f.p, nullptr, false, h->stream));
-    NFB_TRY(compute_gram(s, s->wt, s->gw, s->s_gw, true));
+    { NFB_PHASE(h, "split_w"); NFB_TRY(refresh_planes(s->wt, s->wt.f.p, nullptr, false, h->stream)); }
+    { NFB_PHASE(h, "gram_w"); NFB_TRY(compute_gram(s, s->wt, s->gw, s->s_gw, true)); }
     // ---- H half-step ----
     HNumerator hn;
-    NFB_TRY(gemm_wtx(s, &hn));
-    NFB_TRY(gemm_den(s, s->hh, s->gw, hn.col0, hn.width, hn.ld_part));
+    { NFB_PHASE(h, "gemm_wtx"); NFB_TRY(gemm_wtx(s, &hn)); }
+    { NFB_PHASE(h, "den_h"); NFB_TRY(gemm_den(s, s->hh, s->gw, hn.col0, hn.width, hn.ld_part)); }
     NFB_CUDA(cudaMemsetAsync(s->hh.rowmax.p, 0, sizeof(unsigned int) * s->kp, h->stream));
     if (hn.width > 0) {
+        NFB_PHASE(h, "update_h");
         NFB_TRY(mu_update(s->hh.f.p + hn.col0, s->k, hn.width, s->hh.ld, hn.num, hn.splits, hn.stride, s->part_den.p,
                           1, 0, hn.ld_part, static_cast<float>(p.l1_reg_H), static_cast<float>(p.l2_reg_H),
                           s->hh.rowmax.p, h->stream));
         note_launch(1);
     }
-    NFB_TRY(finish_h(s, hn));
+    { NFB_PHASE(h, "finish_h"); NFB_TRY(finish_h(s, hn)); }
     return 0;
 }
 
@@ -345,29 +390,32 @@ static int cd_iteration(nfb_nmf* s, double* violation_out) {
     nfb_handle* h = s->h;
     const nfb_nmf_params& p = s->p;
     NFB_CUDA(cudaMemsetAsync(h->d_scal.p + 2, 0, 2 * sizeof(double), h->stream));
-    if (!s->p1_valid) NFB_TRY(gemm_xht(s));
+    if (!s->p1_valid) { NFB_PHASE(h, "gemm_xht"); NFB_TRY(gemm_xht(s)); }
     // ---- W half-step ----
-    NFB_TRY(gemm_den(s, s->wt, s->gh, 0, s->x->m, s->wt.ld));  // G_H W^T seeds the per-row gradient
+    { NFB_PHASE(h, "den_w"); NFB_TRY(gemm_den(s, s->wt, s->gh, 0, s->x->m, s->wt.ld)); }  // seeds the gradient
     NFB_CUDA(cudaMemsetAsync(s->wt.rowmax.p, 0, sizeof(unsigned int) * s->kp, h->stream));
+    { NFB_PHASE(h, "update_w");
     NFB_TRY(cd_sweep(s->wt.f.p, s->k, s->x->m, s->wt.ld, s->part_w.p, s->s_w, static_cast<int64_t>(s->k) * s->wt.ld,
                      s->part_den.p, s->wt.ld, s->gh.f.p, static_cast<float>(p.l1_reg_W),
                      static_cast<float>(p.l2_reg_W), h->d_scal.p + 2, s->wt.rowmax.p, h->stream));
+    }
     note_launch(1);
     s->p1_valid = false;
-    NFB_TRY(refresh_planes(s->wt, s->wt.f.p, nullptr, false, h->stream));
-    NFB_TRY(compute_gram(s, s->wt, s->gw, s->s_gw, true));
+    { NFB_PHASE(h, "split_w"); NFB_TRY(refresh_planes(s->wt, s->wt.f.p, nullptr, false, h->stream)); }
+    { NFB_PHASE(h, "gram_w"); NFB_TRY(compute_gram(s, s->wt, s->gw, s->s_gw, true)); }
     // ---- H half-step ----
     HNumerator hn;
-    NFB_TRY(gemm_wtx(s, &hn));
-    NFB_TRY(gemm_den(s, s->hh, s->gw, hn.col0, hn.width, hn.ld_part));
+    { NFB_PHASE(h, "gemm_wtx"); NFB_TRY(gemm_wtx(s, &hn)); }
+    { NFB_PHASE(h, "den_h"); NFB_TRY(gemm_den(s, s->hh, s->gw, hn.col0, hn.width, hn.ld_part)); }
     NFB_CUDA(cudaMemsetAsync(s->hh.rowmax.p, 0, sizeof(unsigned int) * s->kp, h->stream));
     if (hn.width > 0) {
+        NFB_PHASE(h, "update_h");
         NFB_TRY(cd_sweep(s->hh.f.p + hn.col0, s->k, hn.width, s->hh.ld, hn.num, hn.splits, hn.stride, s->part_den.p,
                          hn.ld_part, s->gw.f.p, static_cast<float>(p.l1_reg_H), static_cast<float>(p.l2_reg_H),
                          h->d_scal.p + 3, s->hh.rowmax.p, h->stream));
         note_launch(1);
     }
-    NFB_TRY(finish_h(s, hn));
+    { NFB_PHASE(h, "finish_h"); NFB_TRY(finish_h(s, hn)); }
     if (violation_out != nullptr) {
         // W rows are sharded; H columns are sharded too when the update was sliced, replicated otherwise
         const bool h_sliced = hn.width != s->x->n;
@@ -433,6 +481,7 @@ int nfb_create(int device, void* stream, nfb_handle** out) {
         h->own_stream = true;
     }
     h->cta_group = gemm_default_cta_group();
+    h->phase_timing = getenv("NFB_PHASE_TIMING") != nullptr;
     NFB_TRY(h->d_scal.alloc(16, true, h->stream));
     NFB_TRY(h->d_bits.alloc(16, true, h->stream));
     NFB_TRY(h->d_int.alloc(16, true, h->stream));
@@ -768,12 +817,13 @@ int nfb_nmf_iterate(nfb_nmf* s, int n_iters, double* violation_out) {
     for (int it = 0; it < n_iters; ++it) {
         if (s->p.solver == 1) {
             NFB_TRY(mu_iteration(s));
-            NFB_TRY(gemm_xht(s));  // numerator of the next W half-step == cross term of this iteration's error
+            { NFB_PHASE(s->h, "gemm_xht"); NFB_TRY(gemm_xht(s)); }  // numerator of the next W half-step
         } else {
             NFB_TRY(cd_iteration(s, (it == n_iters - 1) ? violation_out : nullptr));
         }
     }
     s->h->launches_last = g_launches.load() - before;
+    report_phases(s->h, n_iters);
     return 0;
 }
 
