@@ -229,91 +229,192 @@ cd_sweep_smem_kernel(float* __restrict__ f, int k, int64_t cols, int64_t ld, con
 }
 
 
-// ---- thread-per-sample blocked sweep ------------------------------------------------------------------
-// One THREAD owns one sample (column j of F).  Its gradient vector lives in shared memory as gs[u][tid]
-// (conflict-free), components are processed in blocks of 16: the 16 coordinate steps of a block run in
-// registers against the 16 x 16 diagonal block of G, then the block's 16 deltas are applied to the rest of
-// the gradient, g[u] += sum_i delta_i G[t0+i][u], as 16 FMAs per entry with G broadcast from shared memory.
-// Same arithmetic as the rank-1 formulation above (exact Gauss-Seidel order), but the per-coordinate
-// bookkeeping is paid per thread instead of per warp: ~k^2/2 FMAs per sample at FMA-pipe throughput.
+// ---- blocked sweep: thread-per-sample steps + register-tiled rank-16 updates -----------------------------
+// A CTA owns TJ samples (columns j of F).  Their gradient vectors live in shared memory as gs[u][c]
+// (component-major, conflict-free for a thread-per-sample walk).  Components are processed in blocks of 16:
+//   step phase  : thread c runs the 16 coordinate steps of sample c in registers against the 16 x 16 diagonal
+//                 block of G (exact Gauss-Seidel order) and leaves its 16 deltas in the - now dead - gradient
+//                 rows of the block;
+//   apply phase : gs[u][c] += sum_i delta_i[c] G[t0+i][u] for the components still to come, as a register-tiled
+//                 FMA GEMM: every thread owns 4 samples x 4 components, keeps its 64 deltas in registers and
+//                 reads G as one broadcast 128-bit load per 16 FMAs.
+// The FMA order per gradient entry (i = 0..15 within a block, blocks in order) is that of the rank-1
+// formulation above, so results are bit-identical to it; the cost is ~k^2/2 FMAs per sample at FMA-pipe rate.
+// The next block's G rows, hessians and factor values are prefetched into registers across the apply phase.
 constexpr int kBlk = 16;
 
-template <int TJ>
-__global__ void __launch_bounds__(TJ)
-cd_sweep_rows_kernel(float* __restrict__ f, int k, int64_t cols, int64_t ld, const float* __restrict__ num,
+template <int TJ, int NT>
+__global__ void __launch_bounds__(NT, 1)
+cd_sweep_tile_kernel(float* __restrict__ f, int k, int64_t cols, int64_t ld, const float* __restrict__ num,
                      int num_splits, int64_t num_stride, const float* __restrict__ den, int64_t ld_part,
                      const float* __restrict__ gram, int ldg, float l1, float l2, double* __restrict__ violation,
-                     unsigned int* __restrict__ rowmax_bits) {
-    extern __shared__ float sm[];
+                     unsigned int* __restrict__ rowmax_bits, bool vec) {
+    constexpr int JG = TJ / 4;        // groups of 4 samples
+    constexpr int UG = NT / JG;       // groups of 4 components updated concurrently in the apply phase
+    static_assert(TJ % 32 == 0 && NT % TJ == 0 && NT % JG == 0, "tile shape");
+    extern __shared__ __align__(16) float sm[];
     __shared__ double scratch[32];
     __shared__ float invh[kBlk];
-    float* gs = sm;                                   // [k][TJ]
-    float* gb = sm + static_cast<size_t>(k) * TJ;     // [k][kBlk]: gb[u][i] = G[t0 + i][u]
+    __shared__ unsigned int max_s[kBlk];
+    const int kp4 = (k + 3) & ~3;
+    float* gs = sm;                                        // [kp4][TJ] gradient (rows >= k stay zero)
+    float* gb = sm + static_cast<size_t>(kp4) * TJ;        // [kBlk][kp4]: gb[i][u] = G[t0 + i][u], 0 for u >= k
     const int tid = threadIdx.x;
     const int64_t j = static_cast<int64_t>(blockIdx.x) * TJ + tid;
-    const bool active = j < cols;
-    // ---- gradient seed: g = G F[:, j] + l2 F[:, j] - (num[:, j] - l1) ------------------------------------
+    const bool stepper = tid < TJ;
+    const bool active = stepper && j < cols;
+
+    auto load_g = [&](int t, int u) -> float {             // G[t][u], zero outside the k x k matrix
+        return (t < k && u < k) ? __ldg(gram + static_cast<int64_t>(t) * ldg + u) : 0.0f;
+    };
+    auto load_hess = [&](int t0) -> float {
+        return (tid < kBlk && t0 + tid < k) ? __ldg(gram + static_cast<int64_t>(t0 + tid) * ldg + t0 + tid) + l2 : 0.0f;
+    };
+
+    // ---- block 0 operands, then the gradient seed g = G F[:, j] + l2 F[:, j] - (num[:, j] - l1) -----------
 #pragma unroll 4
-    for (int u = 0; u < k; ++u) {
-        float gv = 0.0f;
-        if (active) {
-            const float fv = f[static_cast<int64_t>(u) * ld + j];
-            float nv = 0.0f;
-            for (int s = 0; s < num_splits; ++s) nv += __ldcs(num + s * num_stride + static_cast<int64_t>(u) * ld_part + j);
-            gv = fmaf(l2, fv, __ldcs(den + static_cast<int64_t>(u) * ld_part + j)) - (nv - l1);
-        }
-        gs[u * TJ + tid] = gv;
+    for (int i = 0; i < kBlk; ++i)
+        for (int u = tid; u < kp4; u += NT) gb[i * kp4 + u] = load_g(i, u);
+    if (tid < kBlk) {
+        const float hess = load_hess(0);
+        invh[tid] = hess != 0.0f ? 1.0f / hess : 0.0f;
+        max_s[tid] = 0u;
     }
+    {
+        // every thread owns 4 consecutive samples of one component row per pass; all (splits + 2) 128-bit loads
+        // of a pass are issued before the first use so the phase runs at memory bandwidth, not latency
+        constexpr int kSeedBatch = 8;
+        const int c4 = tid % JG;
+        const int64_t jc = static_cast<int64_t>(blockIdx.x) * TJ + 4 * c4;
+        const bool full = vec && jc + 3 < cols;
+        for (int u = tid / JG; u < kp4; u += UG) {
+            float4 gv = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            if (u < k && full) {
+                const float4 fv = *reinterpret_cast<const float4*>(f + static_cast<int64_t>(u) * ld + jc);
+                const float4 dv = __ldcs(reinterpret_cast<const float4*>(den + static_cast<int64_t>(u) * ld_part + jc));
+                const float* np = num + static_cast<int64_t>(u) * ld_part + jc;
+                float4 nv = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                for (int s0 = 0; s0 < num_splits; s0 += kSeedBatch) {
+                    float4 b[kSeedBatch];
+#pragma unroll
+                    for (int q = 0; q < kSeedBatch; ++q)
+                        b[q] = (s0 + q < num_splits) ? __ldcs(reinterpret_cast<const float4*>(np + (s0 + q) * num_stride))
+                                                     : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#pragma unroll
+                    for (int q = 0; q < kSeedBatch; ++q) {
+                        nv.x += b[q].x; nv.y += b[q].y; nv.z += b[q].z; nv.w += b[q].w;
+                    }
+                }
+                gv.x = fmaf(l2, fv.x, dv.x) - (nv.x - l1);
+                gv.y = fmaf(l2, fv.y, dv.y) - (nv.y - l1);
+                gv.z = fmaf(l2, fv.z, dv.z) - (nv.z - l1);
+                gv.w = fmaf(l2, fv.w, dv.w) - (nv.w - l1);
+            } else if (u < k) {
+                float out[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    out[q] = 0.0f;
+                    if (jc + q < cols) {
+                        const float fv = f[static_cast<int64_t>(u) * ld + jc + q];
+                        float nv = 0.0f;
+                        for (int sp = 0; sp < num_splits; ++sp)
+                            nv += __ldcs(num + sp * num_stride + static_cast<int64_t>(u) * ld_part + jc + q);
+                        out[q] = fmaf(l2, fv, __ldcs(den + static_cast<int64_t>(u) * ld_part + jc + q)) - (nv - l1);
+                    }
+                }
+                gv = make_float4(out[0], out[1], out[2], out[3]);
+            }
+            *reinterpret_cast<float4*>(gs + u * TJ + 4 * c4) = gv;
+        }
+    }
+    float fl[kBlk];
+#pragma unroll
+    for (int i = 0; i < kBlk; ++i) fl[i] = (active && i < k) ? f[static_cast<int64_t>(i) * ld + j] : 0.0f;
+    __syncthreads();
+
     float viol = 0.0f;
+    const int jg = tid % JG, ug = tid / JG;
     for (int t0 = 0; t0 < k; t0 += kBlk) {
         const int nb = min(kBlk, k - t0);
-        __syncthreads();   // previous block's readers of gb / invh are done
-        for (int e = tid; e < kBlk * k; e += TJ) {
-            const int i = e / k, u = e - i * k;
-            gb[u * kBlk + i] = i < nb ? gram[static_cast<int64_t>(t0 + i) * ldg + u] : 0.0f;
+        const bool more = t0 + kBlk < k;                   // components after this block exist (then nb == 16)
+        // ---- step phase: the block's coordinate steps for sample `tid`, in registers ---------------------
+        if (stepper) {
+            float gl[kBlk];
+#pragma unroll
+            for (int i = 0; i < kBlk; ++i) gl[i] = i < nb ? gs[(t0 + i) * TJ + tid] : 0.0f;
+#pragma unroll
+            for (int i = 0; i < kBlk; ++i) {
+                if (i < nb) {
+                    const float ft = fl[i];
+                    const float gt = gl[i];
+                    viol += fabsf((ft == 0.0f) ? fminf(0.0f, gt) : gt);
+                    const float inv = invh[i];
+                    const float fn = fmaxf(fmaf(-gt, inv, ft), 0.0f);
+                    const float delta = inv != 0.0f ? fn - ft : 0.0f;
+                    if (active && delta != 0.0f) f[static_cast<int64_t>(t0 + i) * ld + j] = fn;
+                    // values are >= 0, so unsigned order == float order
+                    const unsigned int vmax = __reduce_max_sync(0xffffffffu, active ? __float_as_uint(ft + delta) : 0u);
+                    if ((tid & 31) == 0 && vmax != 0u) atomicMax(&max_s[i], vmax);
+                    const float* grow = gb + i * kp4 + t0;
+#pragma unroll
+                    for (int i2 = i + 1; i2 < kBlk; ++i2)
+                        if (i2 < nb) gl[i2] = fmaf(delta, grow[i2], gl[i2]);
+                    gs[(t0 + i) * TJ + tid] = delta;       // the gradient row is dead: it now carries the deltas
+                }
+            }
         }
-        if (tid < kBlk) {
-            const float hess = tid < nb ? gram[static_cast<int64_t>(t0 + tid) * ldg + t0 + tid] + l2 : 0.0f;
-            invh[tid] = hess != 0.0f ? 1.0f / hess : 0.0f;
+        // ---- prefetch the next block's operands across the apply phase --------------------------------------
+        float pre[kBlk];                                   // column `tid` of the next block's G rows
+        float hess_next = 0.0f;
+        if (more) {
+#pragma unroll
+            for (int i = 0; i < kBlk; ++i) pre[i] = tid < kp4 ? load_g(t0 + kBlk + i, tid) : 0.0f;
+            hess_next = load_hess(t0 + kBlk);
+#pragma unroll
+            for (int i = 0; i < kBlk; ++i)
+                fl[i] = (active && t0 + kBlk + i < k) ? f[static_cast<int64_t>(t0 + kBlk + i) * ld + j] : 0.0f;
         }
         __syncthreads();
-        // ---- the 16 coordinate steps of this block, in registers -----------------------------------------
-        float gl[kBlk], dl[kBlk], fl[kBlk];
-#pragma unroll
-        for (int i = 0; i < kBlk; ++i) {
-            gl[i] = i < nb ? gs[(t0 + i) * TJ + tid] : 0.0f;
-            fl[i] = (i < nb && active) ? f[static_cast<int64_t>(t0 + i) * ld + j] : 0.0f;   // 16 loads in flight
+        if (tid < kBlk) {
+            if (t0 + tid < k && max_s[tid] != 0u) atomicMax(&rowmax_bits[t0 + tid], max_s[tid]);
+            max_s[tid] = 0u;
         }
+        if (!more) break;
+        // ---- apply phase: gs[u][4 samples] += sum_i delta_i G[t0+i][u], 4 x 4 register tiles ---------------
+        {
+            float4 d[kBlk];
 #pragma unroll
-        for (int i = 0; i < kBlk; ++i) {
-            float delta = 0.0f;
-            if (i < nb) {
-                const float ft = fl[i];
-                const float gt = gl[i];
-                viol += fabsf((ft == 0.0f) ? fminf(0.0f, gt) : gt);
-                const float inv = invh[i];
-                const float fn = fmaxf(fmaf(-gt, inv, ft), 0.0f);
-                delta = inv != 0.0f ? fn - ft : 0.0f;
-                if (active && delta != 0.0f) f[static_cast<int64_t>(t0 + i) * ld + j] = fn;
-                const float vmax = warp_max(active ? ft + delta : 0.0f);
-                if ((tid & 31) == 0 && vmax > 0.0f) atomicMax(&rowmax_bits[t0 + i], __float_as_uint(vmax));
+            for (int i = 0; i < kBlk; ++i) d[i] = *reinterpret_cast<const float4*>(gs + (t0 + i) * TJ + 4 * jg);
+            for (int ub = t0 + kBlk + 4 * ug; ub < kp4; ub += 4 * UG) {
+                float4* grow = reinterpret_cast<float4*>(gs + ub * TJ + 4 * jg);
+                float4 a0 = grow[0], a1 = grow[TJ / 4], a2 = grow[2 * (TJ / 4)], a3 = grow[3 * (TJ / 4)];
 #pragma unroll
-                for (int i2 = i + 1; i2 < kBlk; ++i2) gl[i2] = fmaf(delta, gb[(t0 + i2) * kBlk + i], gl[i2]);
+                for (int i = 0; i < kBlk; ++i) {
+                    const float4 g = *reinterpret_cast<const float4*>(gb + i * kp4 + ub);
+                    a0.x = fmaf(d[i].x, g.x, a0.x); a0.y = fmaf(d[i].y, g.x, a0.y);
+                    a0.z = fmaf(d[i].z, g.x, a0.z); a0.w = fmaf(d[i].w, g.x, a0.w);
+                    a1.x = fmaf(d[i].x, g.y, a1.x); a1.y = fmaf(d[i].y, g.y, a1.y);
+                    a1.z = fmaf(d[i].z, g.y, a1.z); a1.w = fmaf(d[i].w, g.y, a1.w);
+                    a2.x = fmaf(d[i].x, g.z, a2.x); a2.y = fmaf(d[i].y, g.z, a2.y);
+                    a2.z = fmaf(d[i].z, g.z, a2.z); a2.w = fmaf(d[i].w, g.z, a2.w);
+                    a3.x = fmaf(d[i].x, g.w, a3.x); a3.y = fmaf(d[i].y, g.w, a3.y);
+                    a3.z = fmaf(d[i].z, g.w, a3.z); a3.w = fmaf(d[i].w, g.w, a3.w);
+                }
+                grow[0] = a0; grow[TJ / 4] = a1; grow[2 * (TJ / 4)] = a2; grow[3 * (TJ / 4)] = a3;
             }
-            dl[i] = delta;
         }
-        // ---- apply the block's deltas to the components still to come ------------------------------------
-#pragma unroll 4
-        for (int u = t0 + nb; u < k; ++u) {
-            const float4* grow = reinterpret_cast<const float4*>(gb + u * kBlk);
-            const float4 a = grow[0], b = grow[1], c = grow[2], d = grow[3];
-            float acc = gs[u * TJ + tid];
-            acc = fmaf(dl[0], a.x, acc);  acc = fmaf(dl[1], a.y, acc);  acc = fmaf(dl[2], a.z, acc);  acc = fmaf(dl[3], a.w, acc);
-            acc = fmaf(dl[4], b.x, acc);  acc = fmaf(dl[5], b.y, acc);  acc = fmaf(dl[6], b.z, acc);  acc = fmaf(dl[7], b.w, acc);
-            acc = fmaf(dl[8], c.x, acc);  acc = fmaf(dl[9], c.y, acc);  acc = fmaf(dl[10], c.z, acc); acc = fmaf(dl[11], c.w, acc);
-            acc = fmaf(dl[12], d.x, acc); acc = fmaf(dl[13], d.y, acc); acc = fmaf(dl[14], d.z, acc); acc = fmaf(dl[15], d.w, acc);
-            gs[u * TJ + tid] = acc;
+        __syncthreads();
+        // ---- next block's G rows / hessians into shared memory --------------------------------------------
+        if (tid < kp4) {
+#pragma unroll
+            for (int i = 0; i < kBlk; ++i) gb[i * kp4 + tid] = pre[i];
         }
+        if (kp4 > NT) {                                    // columns the register prefetch does not cover
+            for (int i = 0; i < kBlk; ++i)
+                for (int u = tid + NT; u < kp4; u += NT) gb[i * kp4 + u] = load_g(t0 + kBlk + i, u);
+        }
+        if (tid < kBlk) invh[tid] = hess_next != 0.0f ? 1.0f / hess_next : 0.0f;
+        __syncthreads();
     }
     const double total = block_sum(active ? static_cast<double>(viol) : 0.0, scratch);
     if (tid == 0 && total != 0.0) atomicAdd(violation, total);
@@ -328,26 +429,47 @@ int cd_sweep(float* f, int64_t k, int64_t cols, int64_t ld, const float* num, in
     NFB_CHECK(k <= 512, "n_components > 512 is not supported by the coordinate-descent kernel");
     const int ldg = static_cast<int>(round_up64(k, 16));
     const int kpad = static_cast<int>(k) | 1;
-    // preferred: thread-per-sample blocked sweep (largest tile whose gradient block fits in shared memory)
+    // preferred: blocked sweep.  Pick the sample tile that minimises waves x tile (one CTA per SM).
     if (getenv("NFB_CD_KERNEL") == nullptr || atoi(getenv("NFB_CD_KERNEL")) == 0) {
-        auto smem_rows = [&](int tj) { return (static_cast<size_t>(k) * tj + static_cast<size_t>(k) * kBlk) * sizeof(float); };
-        auto run_rows = [&](auto tj_tag) -> int {
+        const int64_t kp4 = round_up64(k, 4);
+        // 128-bit seed loads need 16-byte aligned rows in all three operands
+        const bool vec = ((ld | ld_part | num_stride) % 4 == 0) &&
+                         ((reinterpret_cast<uintptr_t>(f) | reinterpret_cast<uintptr_t>(num) |
+                           reinterpret_cast<uintptr_t>(den)) % 16 == 0);
+        auto smem_tile = [&](int tj) { return static_cast<size_t>(kp4) * (tj + kBlk) * sizeof(float); };
+        auto run_tile = [&](auto tj_tag, auto nt_tag) -> int {
             constexpr int TJ = decltype(tj_tag)::value;
-            auto kernel = cd_sweep_rows_kernel<TJ>;
-            const size_t smem = smem_rows(TJ);
+            constexpr int NT = decltype(nt_tag)::value;
+            auto kernel = cd_sweep_tile_kernel<TJ, NT>;
+            const size_t smem = smem_tile(TJ);
             NFB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-            kernel<<<static_cast<unsigned>(ceil_div64(cols, TJ)), TJ, smem, stream>>>(
+            kernel<<<static_cast<unsigned>(ceil_div64(cols, TJ)), NT, smem, stream>>>(
                 f, static_cast<int>(k), cols, ld, num, num_splits, num_stride, den, ld_part, gram, ldg, l1, l2,
-                violation, rowmax_bits);
+                violation, rowmax_bits, vec);
             NFB_CUDA(cudaGetLastError());
             return 0;
         };
-        if (smem_rows(256) <= 224 * 1024 && cols >= 256 * static_cast<int64_t>(sm_count()))
-            return run_rows(std::integral_constant<int, 256>{});
-        if (smem_rows(128) <= 110 * 1024) return run_rows(std::integral_constant<int, 128>{});
-        if (smem_rows(256) <= 224 * 1024) return run_rows(std::integral_constant<int, 256>{});
-        if (smem_rows(128) <= 224 * 1024) return run_rows(std::integral_constant<int, 128>{});
-        if (smem_rows(64) <= 224 * 1024) return run_rows(std::integral_constant<int, 64>{});
+        static const int tiles[] = {256, 224, 192, 160, 128, 96, 64, 32};
+        const size_t smem_cap = 227 * 1024 - 1024;
+        int best = 0;
+        int64_t best_cost = 0;
+        for (int tj : tiles) {
+            if (smem_tile(tj) > smem_cap) continue;
+            const int64_t waves = ceil_div64(ceil_div64(cols, tj), sm_count());
+            const int64_t cost = waves * (tj + 48);        // + the per-CTA latency-bound part
+            if (best == 0 || cost < best_cost) { best = tj; best_cost = cost; }
+        }
+        switch (best) {
+            case 256: return run_tile(std::integral_constant<int, 256>{}, std::integral_constant<int, 256>{});
+            case 224: return run_tile(std::integral_constant<int, 224>{}, std::integral_constant<int, 224>{});
+            case 192: return run_tile(std::integral_constant<int, 192>{}, std::integral_constant<int, 192>{});
+            case 160: return run_tile(std::integral_constant<int, 160>{}, std::integral_constant<int, 160>{});
+            case 128: return run_tile(std::integral_constant<int, 128>{}, std::integral_constant<int, 256>{});
+            case 96: return run_tile(std::integral_constant<int, 96>{}, std::integral_constant<int, 192>{});
+            case 64: return run_tile(std::integral_constant<int, 64>{}, std::integral_constant<int, 256>{});
+            case 32: return run_tile(std::integral_constant<int, 32>{}, std::integral_constant<int, 256>{});
+            default: break;
+        }
     }
     const int kpl_fast = k <= 32 ? 1 : k <= 64 ? 2 : k <= 128 ? 4 : 7;
     const size_t smem_fast = (static_cast<size_t>(k) * 32 * kpl_fast + 2 * k +
