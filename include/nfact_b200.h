@@ -129,12 +129,21 @@ int nfb_profile_gemms(nfb_handle* h, int enable, double* total_ms_out, int64_t* 
 /* ---- non-negative dual regression ---------------------------------------------------------------
  * replaces  NFACT/dual_reg/dual_regression/dual_regression_methods.py:92-167  nmf_dual_regression
  *           (scipy.optimize.nnls per column / per row).
- *   g_host   [m, k] float64  group grey-matter components
+ *   g_host   [m, k] group grey-matter components, float64 (NIfTI get_fdata) or float32 (GIFTI / CIFTI
+ *            loaders, NFACT/dual_reg/nfact_dr_functions.py:296-353) as said by g_is_f32
  *   gs_out   [m, k] float64  subject grey components      (stage 2)
  *   hs_out   [k, n] float64  subject white components     (stage 1, already transposed like the reference)
- *   n_unconverged_out: number of columns/rows whose solver hit its sweep cap (scipy would raise) */
-int nfb_dual_regression_host(nfb_handle* h, const nfb_matrix* x, int k, const double* g_host, double* gs_out,
-                             double* hs_out, int* n_unconverged_out);
+ *   n_unconverged_out: number of columns/rows whose solver hit its sweep cap (scipy would raise)
+ *   g_nonfinite_out:   1 when g_host holds an inf / NaN (scipy raises ValueError; the outputs are then garbage) */
+int nfb_dual_regression_host(nfb_handle* h, const nfb_matrix* x, int k, const void* g_host, int g_is_f32,
+                             double* gs_out, double* hs_out, int* n_unconverged_out, int* g_nonfinite_out);
+
+/* ---- page-locked host buffers ------------------------------------------------------------------------
+ * Result arrays are hundreds of MB; device-to-host copies into pageable memory run at a few GB/s, into
+ * page-locked memory at PCIe speed.  The host layer allocates the arrays it returns (W, H, DR outputs)
+ * here; blocks are recycled by size.  Any *_host entry point also accepts ordinary pageable pointers. */
+int nfb_host_alloc(int64_t bytes, void** out);
+int nfb_host_free(void* p);
 
 /* ---- low-level kernels exported for tests / profiling ------------------------------------------- */
 /* out_dev[t*ld_out + r] = sum_K A[r,K] B[t,K] through the split-precision tcgen05 path.

@@ -65,7 +65,10 @@ SIGNATURES = {
     "nfb_nmf_error": (c_int, [c_void_p, POINTER(c_double)]),
     "nfb_launch_count": (c_int64, [c_void_p]),
     "nfb_profile_gemms": (c_int, [c_void_p, c_int, POINTER(c_double), POINTER(c_int64)]),
-    "nfb_dual_regression_host": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, POINTER(c_int)]),
+    "nfb_dual_regression_host": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p,
+                                         POINTER(c_int), POINTER(c_int)]),
+    "nfb_host_alloc": (c_int, [c_int64, POINTER(c_void_p)]),
+    "nfb_host_free": (c_int, [c_void_p]),
     "nfb_test_gemm": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_int64, c_void_p, c_int64,
                               c_int, c_int]),
 }
@@ -89,6 +92,23 @@ def load() -> ctypes.CDLL:
         fn.argtypes = argtypes
     _lib = lib
     return lib
+
+
+def pinned_empty(shape, dtype):
+    """``np.empty(shape, dtype)`` on page-locked memory from the library's pool (nfb_host_alloc): device-to-host
+    copies into it run at PCIe speed.  The block goes back to the pool when the array (and every view of it)
+    is garbage-collected."""
+    import weakref
+
+    import numpy as np
+    lib = load()
+    dtype = np.dtype(dtype)
+    nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
+    ptr = c_void_p()
+    check(lib.nfb_host_alloc(nbytes, ctypes.byref(ptr)))
+    raw = (ctypes.c_byte * max(nbytes, 1)).from_address(ptr.value)
+    weakref.finalize(raw, lib.nfb_host_free, c_void_p(ptr.value))
+    return np.frombuffer(raw, dtype=dtype, count=nbytes // dtype.itemsize).reshape(shape)
 
 
 def check(rc: int) -> None:

@@ -79,11 +79,14 @@ int f64_to_f32_rowmax(const double* in, int64_t k, int64_t cols, int64_t ld_in, 
                       unsigned int* rowmax_bits, cudaStream_t stream);
 // *out += sum_{t,u<k} a[t][u] * b[t][u]
 int dot_small(const float* a, const float* b, int64_t k, int64_t ld, double* out, cudaStream_t stream);
-// transpose fp32 [rows, cols] (ld_in) -> [cols, rows] (ld_out)
+// transpose [rows, cols] (ld_in) -> [cols, rows] (ld_out); *nonfinite (nullable) is set to 1 when an input
+// element is inf or NaN
 int transpose_f32(const float* in, int64_t rows, int64_t cols, int64_t ld_in, float* out, int64_t ld_out,
-                  cudaStream_t stream);
+                  cudaStream_t stream, int* nonfinite = nullptr);
 int transpose_f64_to_f32(const double* in, int64_t rows, int64_t cols, int64_t ld_in, float* out, int64_t ld_out,
-                         cudaStream_t stream);
+                         cudaStream_t stream, int* nonfinite = nullptr);
+int transpose_f64(const double* in, int64_t rows, int64_t cols, int64_t ld_in, double* out, int64_t ld_out,
+                  cudaStream_t stream);
 
 // ---- ingest.cu ------------------------------------------------------------------------------------
 // phase A: tmp[r*ncols+c] += v for every triplet with row in [row0, row0+nrows_blk)  (fp64 atomics)

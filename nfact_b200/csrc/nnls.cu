@@ -13,6 +13,7 @@
 // QP is unique, so on full-column-rank A the fixed point equals the active-set solution of scipy;
 // convergence is declared on the KKT residual max_t |pg_t| <= tol * max|r|.
 #include <algorithm>
+#include <cstdlib>
 #include <utility>
 
 #include "common.cuh"
@@ -114,19 +115,18 @@ nnls_cd_kernel(const double* __restrict__ gram, int k, const float* __restrict__
 // One CTA per SM, 24 warps, columns handed out dynamically (their sweep counts differ widely).  The
 // coordinate step has its slot (register index) as a compile-time constant, multiplies by a precomputed
 // 1/G[t][t] and reads row/column t of G from shared memory.
-constexpr int kNnlsWarps = 16;
 
-__device__ __forceinline__ int tri(int r, int c) { return r >= c ? r * (r + 1) / 2 + c : c * (c + 1) / 2 + r; }
-
-template <int KPL>
+template <int KPL, int kNnlsWarps>
 __global__ void __launch_bounds__(kNnlsWarps * 32, 1)
 nnls_smem_kernel(const double* __restrict__ gram, int k, const float* __restrict__ rhs, int rhs_splits,
                  int64_t rhs_stride, int64_t ld_rhs, int64_t cols, double* __restrict__ sol, int64_t ld_sol,
                  int max_outer, double tol, int* __restrict__ status, unsigned long long* __restrict__ steps_total,
                  unsigned long long* __restrict__ next_col) {
     extern __shared__ double smd[];
-    double* g_tri = smd;                                 // k (k + 1) / 2
-    double* inv_diag = smd + k * (k + 1) / 2;            // k  (0 where G[t][t] <= 0)
+    const int ntri = k * (k + 1) / 2;
+    double* g_tri = smd;                                 // k (k + 1) / 2 packed lower triangle, row-major
+    double* zeros = smd + ntri;                          // k zeros: "column t" of the padding rows u >= k
+    double* inv_diag = zeros + k;                        // k  (0 where G[t][t] <= 0)
     const int lane = threadIdx.x & 31;
     for (int idx = threadIdx.x; idx < k * k; idx += blockDim.x) {
         const int r = idx / k, c = idx - r * k;
@@ -135,7 +135,29 @@ nnls_smem_kernel(const double* __restrict__ gram, int k, const float* __restrict
     for (int t = threadIdx.x; t < k; t += blockDim.x) {
         const double d = gram[static_cast<int64_t>(t) * k + t];
         inv_diag[t] = d > 0.0 ? 1.0 / d : 0.0;
+        zeros[t] = 0.0;
     }
+    // G[u][t] for this lane's coordinates u = lane + 32 i:
+    //   u >= t : g_tri[ro[i] + t]  with ro[i] = u (u + 1) / 2  (padding rows point at the zero region)
+    //   u <  t : g_tri[t (t + 1) / 2 + u]  -- a contiguous run of row t, addressed with immediate offsets
+    int ro[KPL];
+#pragma unroll
+    for (int i = 0; i < KPL; ++i) {
+        const int u = lane + 32 * i;
+        ro[i] = u < k ? u * (u + 1) / 2 : ntri;
+    }
+    // q[i] += dt * G[lane + 32 i][t] for all i, t = 32 I + o
+    auto axpy_col = [&](auto slot_tag, int o, double dt, double (&q)[KPL]) {
+        constexpr int I = decltype(slot_tag)::value;
+        const int t = 32 * I + o;
+        const double* rowt = g_tri + t * (t + 1) / 2 + lane;
+#pragma unroll
+        for (int i = 0; i < KPL; ++i) {
+            if (i < I) q[i] = fma(dt, rowt[32 * i], q[i]);
+            else if (i == I) q[i] = fma(dt, lane < o ? rowt[32 * i] : g_tri[ro[i] + t], q[i]);
+            else q[i] = fma(dt, g_tri[ro[i] + t], q[i]);
+        }
+    };
     __syncthreads();
 
     for (;;) {
@@ -171,11 +193,7 @@ nnls_smem_kernel(const double* __restrict__ gram, int k, const float* __restrict
             const double hn = fmax(fma(-gt, inv, ht), 0.0);
             const double delta = inv != 0.0 ? hn - ht : 0.0;
             if (delta != 0.0) {  // warp-uniform
-#pragma unroll
-                for (int i = 0; i < KPL; ++i) {
-                    const int u = lane + 32 * i;
-                    if (u < k) g[i] = fma(delta, g_tri[tri(u, t)], g[i]);
-                }
+                axpy_col(slot_tag, o, delta, g);
                 if (lane == o) h[I] = hn;
             }
             return fabs(pg);
@@ -221,13 +239,7 @@ nnls_smem_kernel(const double* __restrict__ gram, int k, const float* __restrict
                     while (mask) {
                         const int o = __ffs(mask) - 1;
                         mask &= mask - 1;
-                        const double dt = shfl_d(d[I], o);
-                        const int t = 32 * I + o;
-#pragma unroll
-                        for (int i = 0; i < KPL; ++i) {
-                            const int u = lane + 32 * i;
-                            if (u < k) q[i] = fma(dt, g_tri[tri(u, t)], q[i]);
-                        }
+                        axpy_col(slot_tag, o, shfl_d(d[I], o), q);
                     }
                 };
                 [&]<int... Is>(std::integer_sequence<int, Is...>) {
@@ -281,13 +293,17 @@ int nnls_gram_batched(const double* gram, int64_t k, const float* rhs, int rhs_s
                       cudaStream_t stream, unsigned long long* steps_total, unsigned long long* counter) {
     if (k == 0 || cols == 0) return 0;
     NFB_CHECK(k <= 512, "n_components > 512 is not supported by the NNLS kernel");
-    const size_t smem_fast = (static_cast<size_t>(k) * (k + 1) / 2 + k) * sizeof(double);
+    const size_t smem_fast = (static_cast<size_t>(k) * (k + 1) / 2 + 2 * k) * sizeof(double);
     if (smem_fast <= 220 * 1024 && k <= 224 && counter != nullptr) {
         NFB_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream));
+        // 16 warps per SM (128 registers, a few spilled values at k > 192) measured faster than 12 spill-free ones
+        static const int warps_env = getenv("NFB_NNLS_WARPS") ? atoi(getenv("NFB_NNLS_WARPS")) : 0;
+        const bool wide = warps_env ? warps_env >= 16 : true;
+        const int kNnlsWarps = wide ? 16 : 12;
         const int grid = static_cast<int>(std::min<int64_t>(ceil_div64(cols, kNnlsWarps), sm_count()));
 #define NFB_NNLS_FAST(KPL)                                                                                       \
     do {                                                                                                         \
-        auto kernel = nnls_smem_kernel<KPL>;                                                                     \
+        auto kernel = wide ? nnls_smem_kernel<KPL, 16> : nnls_smem_kernel<KPL, 12>;                              \
         NFB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,                       \
                                       static_cast<int>(smem_fast)));                                             \
         kernel<<<grid, kNnlsWarps * 32, smem_fast, stream>>>(gram, static_cast<int>(k), rhs, rhs_splits,         \

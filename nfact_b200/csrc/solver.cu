@@ -12,7 +12,11 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <memory>
+#include <mutex>
+#include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/nfact_b200.h"
@@ -94,6 +98,7 @@ struct nfb_handle {
     DevBuf<unsigned int> d_bits;  // absmax bits
     DevBuf<int> d_int;
     double* h_scal = nullptr;     // pinned mirror
+    cudaStream_t copy_stream = nullptr;   // D2H of finished results while the compute stream carries on
 };
 
 struct nfb_matrix {
@@ -486,6 +491,7 @@ int nfb_create(int device, void* stream, nfb_handle** out) {
     NFB_TRY(h->d_bits.alloc(16, true, h->stream));
     NFB_TRY(h->d_int.alloc(16, true, h->stream));
     NFB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h->h_scal), 16 * sizeof(double)));
+    NFB_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     NFB_CUDA(cudaStreamSynchronize(h->stream));
     *out = h.release();
     return 0;
@@ -501,6 +507,7 @@ int nfb_destroy(nfb_handle* h) {
         if (fn) fn(h->comm);
     }
     if (h->h_scal) cudaFreeHost(h->h_scal);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
     return 0;
@@ -888,8 +895,63 @@ int nfb_nmf_fit_host(nfb_handle* h, const nfb_matrix* x, int k, const nfb_nmf_pa
 }
 
 // ---- dual regression -------------------------------------------------------------------------------
-int nfb_dual_regression_host(nfb_handle* h, const nfb_matrix* x, int k, const double* g_host, double* gs_out,
-                             double* hs_out, int* n_unconverged_out) {
+// ---- pinned host memory pool ----------------------------------------------------------------------------
+// Result arrays handed to the caller (W, H, the float64 DR outputs) are hundreds of MB; a pageable
+// destination makes the D2H copy run at a few GB/s.  The host layer allocates them here instead: page-locked
+// blocks, recycled by exact size (cudaHostAlloc itself costs ~0.1 s per GB).
+namespace {
+std::mutex g_pin_mutex;
+std::multimap<size_t, void*> g_pin_free;           // size -> idle block
+std::unordered_map<void*, size_t> g_pin_live;      // block -> size
+size_t g_pin_idle_bytes = 0;
+constexpr size_t kPinIdleCap = size_t(8) << 30;    // idle blocks kept for reuse
+}  // namespace
+
+int nfb_host_alloc(int64_t bytes, void** out) {
+    NFB_CHECK(out != nullptr && bytes >= 0, "bad nfb_host_alloc arguments");
+    const size_t size = std::max<size_t>(static_cast<size_t>(bytes), 64);
+    {
+        std::lock_guard<std::mutex> lock(g_pin_mutex);
+        auto it = g_pin_free.find(size);
+        if (it != g_pin_free.end()) {
+            *out = it->second;
+            g_pin_idle_bytes -= size;
+            g_pin_free.erase(it);
+            g_pin_live[*out] = size;
+            return 0;
+        }
+    }
+    void* p = nullptr;
+    NFB_CUDA(cudaHostAlloc(&p, size, cudaHostAllocPortable));
+    std::lock_guard<std::mutex> lock(g_pin_mutex);
+    g_pin_live[p] = size;
+    *out = p;
+    return 0;
+}
+
+int nfb_host_free(void* p) {
+    if (p == nullptr) return 0;
+    size_t size = 0;
+    bool release = false;
+    {
+        std::lock_guard<std::mutex> lock(g_pin_mutex);
+        auto it = g_pin_live.find(p);
+        NFB_CHECK(it != g_pin_live.end(), "nfb_host_free: pointer was not allocated by nfb_host_alloc");
+        size = it->second;
+        g_pin_live.erase(it);
+        if (g_pin_idle_bytes + size <= kPinIdleCap) {
+            g_pin_free.emplace(size, p);
+            g_pin_idle_bytes += size;
+        } else {
+            release = true;
+        }
+    }
+    if (release) cudaFreeHost(p);
+    return 0;
+}
+
+int nfb_dual_regression_host(nfb_handle* h, const nfb_matrix* x, int k, const void* g_host, int g_is_f32,
+                             double* gs_out, double* hs_out, int* n_unconverged_out, int* g_nonfinite_out) {
     NFB_CHECK(h != nullptr && x != nullptr && g_host != nullptr, "NULL argument");
     NFB_CHECK(k >= 1 && k <= 512, "n_components must be in [1, 512] in this build");
     NFB_CUDA(cudaSetDevice(h->device));
@@ -900,6 +962,7 @@ int nfb_dual_regression_host(nfb_handle* h, const nfb_matrix* x, int k, const do
     NFB_TRY(gt.init(k, m, true, st));
     NFB_TRY(hs.init(k, n, true, st));
     DevBuf<double> g64, gram64, sol_h, sol_g;
+    // g64 holds the uploaded group components first and the transposed stage-2 solution [m, k] at the end
     NFB_TRY(g64.alloc(static_cast<size_t>(m) * k, false, st));
     NFB_TRY(gram64.alloc(static_cast<size_t>(k) * k, false, st));
     NFB_TRY(sol_h.alloc(static_cast<size_t>(k) * hs.ld, true, st));
@@ -907,46 +970,74 @@ int nfb_dual_regression_host(nfb_handle* h, const nfb_matrix* x, int k, const do
     const int s1 = gemm_pick_splits(n, m, cg), s2 = gemm_pick_splits(m, n, cg);
     DevBuf<float> part;
     NFB_TRY(part.alloc(std::max(static_cast<size_t>(s1) * k * hs.ld, static_cast<size_t>(s2) * k * gt.ld), false, st));
-    NFB_CUDA(cudaMemsetAsync(h->d_int.p, 0, 2 * sizeof(int), st));
+    NFB_CUDA(cudaMemsetAsync(h->d_int.p, 0, 3 * sizeof(int), st));
     NFB_CUDA(cudaMemsetAsync(h->d_scal.p + 8, 0, 2 * sizeof(double), st));
-    // group grey components: float64 [m, k] -> component-major float32 master + planes
-    NFB_CUDA(cudaMemcpyAsync(g64.p, g_host, sizeof(double) * m * k, cudaMemcpyHostToDevice, st));
-    NFB_TRY(transpose_f64_to_f32(g64.p, m, k, k, gt.f.p, gt.ld, st));
+    // group grey components: [m, k] float64 or float32 -> component-major float32 master + planes
+    // (scipy's nnls casts to float64; the product G'X runs on the float32 value either way)
+    { NFB_PHASE(h, "g_upload");
+    if (g_is_f32) {
+        float* g32 = reinterpret_cast<float*>(g64.p);
+        NFB_CUDA(cudaMemcpyAsync(g32, g_host, sizeof(float) * m * k, cudaMemcpyHostToDevice, st));
+        NFB_TRY(transpose_f32(g32, m, k, k, gt.f.p, gt.ld, st, h->d_int.p + 2));
+    } else {
+        NFB_CUDA(cudaMemcpyAsync(g64.p, g_host, sizeof(double) * m * k, cudaMemcpyHostToDevice, st));
+        NFB_TRY(transpose_f64_to_f32(g64.p, m, k, k, gt.f.p, gt.ld, st, h->d_int.p + 2));
+    }
     NFB_TRY(refresh_planes(gt, gt.f.p, nullptr, true, st));
+    }
     // ---- stage 1: white matter.  Hs[:, j] = nnls(G, X[:, j])  (dual_regression_methods.py:137-149)
-    NFB_TRY(gram_f64(gt.f.p, k, m, gt.ld, gram64.p, st));
+    { NFB_PHASE(h, "gram1"); NFB_TRY(gram_f64(gt.f.p, k, m, gt.ld, gram64.p, st)); }
+    { NFB_PHASE(h, "gemm_gtx");
     NFB_TRY(gemm_split(x->operand(), true, gt.operand(), n, m, static_cast<int>(kp), k, part.p, hs.ld, s1,
                        gt.inv_scale.p, nullptr, x->inv_scale_host, cg, st));
+    }
+    { NFB_PHASE(h, "nnls1");
     NFB_TRY(nnls_gram_batched(gram64.p, k, part.p, s1, static_cast<int64_t>(k) * hs.ld, hs.ld, n, sol_h.p, hs.ld,
                               400, h->d_int.p, st, reinterpret_cast<unsigned long long*>(h->d_scal.p + 8),
                               reinterpret_cast<unsigned long long*>(h->d_scal.p + 10)));
+    }
+    // the white components can travel while stage 2 runs
+    cudaEvent_t hs_ready = nullptr;
+    if (hs_out) {
+        NFB_CUDA(cudaEventCreateWithFlags(&hs_ready, cudaEventDisableTiming));
+        NFB_CUDA(cudaEventRecord(hs_ready, st));
+        NFB_CUDA(cudaStreamWaitEvent(h->copy_stream, hs_ready, 0));
+        NFB_CUDA(cudaMemcpy2DAsync(hs_out, n * sizeof(double), sol_h.p, hs.ld * sizeof(double), n * sizeof(double), k,
+                                   cudaMemcpyDeviceToHost, h->copy_stream));
+    }
     // ---- stage 2: grey matter.  Gs[i, :] = nnls(Hs, X[i, :])    (dual_regression_methods.py:151-163)
+    { NFB_PHASE(h, "planes2");
     NFB_CUDA(cudaMemsetAsync(hs.rowmax.p, 0, sizeof(unsigned int) * kp, st));
     NFB_TRY(f64_to_f32_rowmax(sol_h.p, k, n, hs.ld, hs.f.p, hs.ld, hs.rowmax.p, st));
     NFB_TRY(refresh_planes(hs, hs.f.p, nullptr, false, st));
-    NFB_TRY(gram_f64(hs.f.p, k, n, hs.ld, gram64.p, st));
+    }
+    { NFB_PHASE(h, "gram2"); NFB_TRY(gram_f64(hs.f.p, k, n, hs.ld, gram64.p, st)); }
+    { NFB_PHASE(h, "gemm_xhst");
     NFB_TRY(gemm_split(x->operand(), false, hs.operand(), m, n, static_cast<int>(kp), k, part.p, gt.ld, s2,
                        hs.inv_scale.p, nullptr, x->inv_scale_host, cg, st));
+    }
+    { NFB_PHASE(h, "nnls2");
     NFB_TRY(nnls_gram_batched(gram64.p, k, part.p, s2, static_cast<int64_t>(k) * gt.ld, gt.ld, m, sol_g.p, gt.ld,
                               400, h->d_int.p + 1, st, reinterpret_cast<unsigned long long*>(h->d_scal.p + 9),
                               reinterpret_cast<unsigned long long*>(h->d_scal.p + 10)));
-    // ---- results -------------------------------------------------------------------------------------
-    if (hs_out)
-        NFB_CUDA(cudaMemcpy2DAsync(hs_out, n * sizeof(double), sol_h.p, hs.ld * sizeof(double), n * sizeof(double), k,
-                                   cudaMemcpyDeviceToHost, st));
-    std::vector<double> gs_t;
-    if (gs_out) {
-        gs_t.resize(static_cast<size_t>(k) * m);
-        NFB_CUDA(cudaMemcpy2DAsync(gs_t.data(), m * sizeof(double), sol_g.p, gt.ld * sizeof(double),
-                                   m * sizeof(double), k, cudaMemcpyDeviceToHost, st));
     }
-    int status[2] = {0, 0};
-    NFB_CUDA(cudaMemcpyAsync(status, h->d_int.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    // ---- results -------------------------------------------------------------------------------------
+    { NFB_PHASE(h, "d2h");
+    if (gs_out) {
+        NFB_TRY(transpose_f64(sol_g.p, k, m, gt.ld, g64.p, k, st));
+        NFB_CUDA(cudaMemcpyAsync(gs_out, g64.p, sizeof(double) * m * k, cudaMemcpyDeviceToHost, st));
+    }
+    }
+    int status[3] = {0, 0, 0};
+    NFB_CUDA(cudaMemcpyAsync(status, h->d_int.p, 3 * sizeof(int), cudaMemcpyDeviceToHost, st));
     NFB_CUDA(cudaStreamSynchronize(st));
-    if (gs_out)
-        for (int64_t i = 0; i < m; ++i)
-            for (int t = 0; t < k; ++t) gs_out[i * k + t] = gs_t[static_cast<size_t>(t) * m + i];
+    if (hs_ready) {
+        NFB_CUDA(cudaStreamSynchronize(h->copy_stream));
+        cudaEventDestroy(hs_ready);
+    }
     if (n_unconverged_out) *n_unconverged_out = status[0] + status[1];
+    if (g_nonfinite_out) *g_nonfinite_out = status[2];
+    report_phases(h, 1);
     if (getenv("NFB_DR_STATS")) {
         unsigned long long steps[2] = {0, 0};
         cudaMemcpy(steps, h->d_scal.p + 8, sizeof(steps), cudaMemcpyDeviceToHost);

@@ -105,15 +105,20 @@ __global__ void dot_small_kernel(const float* __restrict__ a, const float* __res
     if (threadIdx.x == 0) atomicAdd(out, total);
 }
 
-template <typename Tin>
+template <typename Tin, typename Tout>
 __global__ void transpose_kernel(const Tin* __restrict__ in, int64_t rows, int64_t cols, int64_t ld_in,
-                                 float* __restrict__ out, int64_t ld_out) {
-    __shared__ float tile[32][33];
+                                 Tout* __restrict__ out, int64_t ld_out, int* __restrict__ nonfinite) {
+    __shared__ Tout tile[32][33];
     const int64_t c0 = static_cast<int64_t>(blockIdx.x) * 32, r0 = static_cast<int64_t>(blockIdx.y) * 32;
+    bool bad = false;
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
         const int64_t r = r0 + i, c = c0 + threadIdx.x;
-        tile[i][threadIdx.x] = (r < rows && c < cols) ? static_cast<float>(in[r * ld_in + c]) : 0.0f;
+        Tin v = Tin(0);
+        if (r < rows && c < cols) v = in[r * ld_in + c];
+        bad |= !isfinite(v);
+        tile[i][threadIdx.x] = static_cast<Tout>(v);
     }
+    if (nonfinite != nullptr && bad) *nonfinite = 1;
     __syncthreads();
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
         const int64_t c = c0 + i, r = r0 + threadIdx.x;
@@ -258,19 +263,28 @@ int dot_small(const float* a, const float* b, int64_t k, int64_t ld, double* out
 }
 
 int transpose_f32(const float* in, int64_t rows, int64_t cols, int64_t ld_in, float* out, int64_t ld_out,
-                  cudaStream_t stream) {
+                  cudaStream_t stream, int* nonfinite) {
     if (rows * cols == 0) return 0;
     dim3 grid(static_cast<unsigned>(ceil_div64(cols, 32)), static_cast<unsigned>(ceil_div64(rows, 32)));
-    transpose_kernel<float><<<grid, dim3(32, 8), 0, stream>>>(in, rows, cols, ld_in, out, ld_out);
+    transpose_kernel<float, float><<<grid, dim3(32, 8), 0, stream>>>(in, rows, cols, ld_in, out, ld_out, nonfinite);
     NFB_CUDA(cudaGetLastError());
     return 0;
 }
 
 int transpose_f64_to_f32(const double* in, int64_t rows, int64_t cols, int64_t ld_in, float* out, int64_t ld_out,
-                         cudaStream_t stream) {
+                         cudaStream_t stream, int* nonfinite) {
     if (rows * cols == 0) return 0;
     dim3 grid(static_cast<unsigned>(ceil_div64(cols, 32)), static_cast<unsigned>(ceil_div64(rows, 32)));
-    transpose_kernel<double><<<grid, dim3(32, 8), 0, stream>>>(in, rows, cols, ld_in, out, ld_out);
+    transpose_kernel<double, float><<<grid, dim3(32, 8), 0, stream>>>(in, rows, cols, ld_in, out, ld_out, nonfinite);
+    NFB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int transpose_f64(const double* in, int64_t rows, int64_t cols, int64_t ld_in, double* out, int64_t ld_out,
+                  cudaStream_t stream) {
+    if (rows * cols == 0) return 0;
+    dim3 grid(static_cast<unsigned>(ceil_div64(cols, 32)), static_cast<unsigned>(ceil_div64(rows, 32)));
+    transpose_kernel<double, double><<<grid, dim3(32, 8), 0, stream>>>(in, rows, cols, ld_in, out, ld_out, nullptr);
     NFB_CUDA(cudaGetLastError());
     return 0;
 }

@@ -126,6 +126,12 @@ class DeviceMatrix:
         check(self.handle.lib.nfb_matrix_has_negative(self._ptr, byref(out)))
         return bool(out.value)
 
+    @property
+    def has_nonfinite(self) -> bool:
+        """inf / NaN anywhere in X (the float64 sum of squares accumulated during the split pass overflows
+        or turns NaN exactly then) -- sklearn's / scipy's finiteness check without a host pass over X."""
+        return not np.isfinite(self.sumsq)
+
     def matmul_dev(self, trans: bool, b_ptr: int, n_b: int, out_ptr: int, ld_out: int) -> None:
         check(self.handle.lib.nfb_matrix_matmul(self.handle.ptr, self._ptr, int(trans), c_void_p(b_ptr), n_b,
                                                 c_void_p(out_ptr), ld_out))
@@ -173,8 +179,8 @@ class NmfState:
 
     def get_factors(self):
         m, n = self.x.shape
-        w = np.empty((m, self.k), dtype=np.float32)
-        h = np.empty((self.k, n), dtype=np.float32)
+        w = _lib.pinned_empty((m, self.k), np.float32)
+        h = _lib.pinned_empty((self.k, n), np.float32)
         check(self.handle.lib.nfb_nmf_get_factors_host(self._ptr, w.ctypes.data, h.ctypes.data))
         return w, h
 

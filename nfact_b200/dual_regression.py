@@ -11,7 +11,7 @@ from ctypes import byref, c_int
 
 import numpy as np
 
-from ._lib import check
+from ._lib import check, pinned_empty
 from .device import DeviceMatrix
 from .utils import error_and_exit
 
@@ -22,30 +22,32 @@ def nmf_dual_regression(components: dict, connectivity_matrix, n_jobs: int = 1) 
     ``n_jobs`` is accepted for signature compatibility; the device solves all columns at once.
     Returns float64 arrays {"grey_components": [m,k], "white_components": [k,n]} like the reference.
     """
-    grey = np.ascontiguousarray(components["grey_components"], dtype=np.float64)
+    grey = np.asarray(components["grey_components"])
+    if grey.dtype != np.float32:          # scipy's nnls casts everything else to float64
+        grey = grey.astype(np.float64, copy=False)
+    grey = np.ascontiguousarray(grey)
     if grey.ndim != 2:
         raise ValueError(f"Expected a 2D array, but the shape of A is {grey.shape}")
-    if not np.isfinite(grey).all():
-        raise ValueError("array must not contain infs or NaNs")
     if isinstance(connectivity_matrix, DeviceMatrix):
         xdev, owns = connectivity_matrix, False
     else:
-        xhost = np.asarray(connectivity_matrix)
-        if not np.isfinite(xhost).all():
-            raise ValueError("array must not contain infs or NaNs")
-        xdev, owns = DeviceMatrix.from_host(xhost), True
+        xdev, owns = DeviceMatrix.from_host(np.asarray(connectivity_matrix)), True
     try:
+        if xdev.has_nonfinite:
+            raise ValueError("array must not contain infs or NaNs")
         m, n = xdev.shape
         if grey.shape[0] != m:
             raise ValueError("Incompatible dimensions. The first dimension of "
                              f"A is {grey.shape[0]}, while the shape of b is {(m,)}")
         k = grey.shape[1]
-        gs = np.empty((m, k), dtype=np.float64)
-        hs = np.empty((k, n), dtype=np.float64)
-        bad = c_int()
+        gs = pinned_empty((m, k), np.float64)
+        hs = pinned_empty((k, n), np.float64)
+        bad, nonfinite = c_int(), c_int()
         h = xdev.handle
-        check(h.lib.nfb_dual_regression_host(h.ptr, xdev.ptr, k, grey.ctypes.data, gs.ctypes.data, hs.ctypes.data,
-                                             byref(bad)))
+        check(h.lib.nfb_dual_regression_host(h.ptr, xdev.ptr, k, grey.ctypes.data, int(grey.dtype == np.float32),
+                                             gs.ctypes.data, hs.ctypes.data, byref(bad), byref(nonfinite)))
+        if nonfinite.value:               # checked on the device while G is transposed
+            raise ValueError("array must not contain infs or NaNs")
         if bad.value:
             raise RuntimeError("Maximum number of iterations reached.")
     finally:

@@ -19,7 +19,7 @@ xmat = DeviceMatrix.from_device_ptr(x.data_ptr(), m, n, n)
 del x
 rng = np.random.default_rng(0)
 G = rng.gamma(0.3, 1.0, (m, k)) * (rng.random((m, k)) < 0.3)        # sparse-ish group components
-for rep in range(2):
+for rep in range(int(sys.argv[2]) if len(sys.argv) > 2 else 2):
     t0 = time.perf_counter()
     dr = nfact_b200.nmf_dual_regression({"grey_components": G}, xmat)
     dt = time.perf_counter() - t0
