@@ -107,13 +107,20 @@ class ClockSampler:
 
     def __init__(self, index):
         self.rows, self.proc, self.index = [], None, index
+        self.t0 = self.t1 = None
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def start(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -121,19 +128,30 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append([time.time()] + [c.strip() for c in line.split(",")])
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        valid = [r for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        # samples stamped inside the timed region; a region shorter than one sampling period takes the
+        # samples that bracket it (the GPU was under the same load during the warm-up just before)
+        rows = [r[1:] for r in valid if self.t0 is not None and self.t0 <= r[0] <= self.t1 + 0.02]
+        window = "timed region"
+        if not rows and valid and self.t0 is not None:
+            mid = 0.5 * (self.t0 + self.t1)
+            rows = [r[1:] for r in sorted(valid, key=lambda r: abs(r[0] - mid))[:3]]
+            window = "nearest samples (timed region shorter than the sampling period)"
+        elif not rows:
+            rows = [r[1:] for r in valid]
+        sm = [float(r[0]) for r in rows]
+        mx = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i] == "Active"})
+        reasons = sorted({names[i] for r in rows for i in range(4) if r[2 + i] == "Active"})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "window": window}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -278,7 +296,7 @@ def run_ours(args):
         x_mean = float(x_sum) / (m * n)
         stream.synchronize()
         xmat = DeviceMatrix.from_device_ptr(x_dev.data_ptr(), rows, n, n, handle=handle)
-        want_e2e = (not args.no_e2e) and world == 1
+        want_e2e = not args.no_e2e
         x_host = None
         if want_e2e:
             x_host = torch.empty((rows, n), dtype=torch.float32, pin_memory=True)
@@ -292,6 +310,8 @@ def run_ours(args):
         state.set_factors_dev(w0.data_ptr(), h0.data_ptr())
 
         # ---- warm-up ------------------------------------------------------------------------------
+        sampler = ClockSampler(local_rank)
+        sampler.start()
         state.iterate(max(args.warmup, 3))
         handle.synchronize()
         handle.profile_gemms(True)
@@ -299,13 +319,13 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
         # ---- timed region: exactly K iterations, device-timed ------------------------------------
-        sampler = ClockSampler(local_rank)
-        sampler.start()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler.mark_begin()
         ev0.record(stream)
         state.iterate(args.steps)
         ev1.record(stream)
         torch.cuda.synchronize()
+        sampler.mark_end()
         if world > 1:
             dist.barrier()
         clocks = sampler.stop()
@@ -320,6 +340,9 @@ def run_ours(args):
         state.free()
 
         # ---- e2e through the reference-facing call with host buffers ------------------------------
+        # Every rank holds its seed rows of X (and of W0) in pinned host memory and calls
+        # nmf_decomp(parameters, X_rows, W=W0_rows, H=H0): H2D of X, plane split, `iters` iterations
+        # (NCCL inside when row-sharded), D2H of W rows and H -- all inside the timed region.
         e2e = dr_info = None
         if want_e2e:
             xmat.free()
@@ -330,31 +353,49 @@ def run_ours(args):
             params = dict(nfact_b200.get_parameters(None, "nmf", k), solver=args.solver, tol=0.0, max_iter=iters)
             x_np = x_host.numpy()
             import nfact_b200.device as nfdev
-            nfdev._handles[local_rank] = handle
+            nfdev.set_default_handle(handle)
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
             t0 = time.perf_counter()
             res = nfact_b200.nmf_decomp(params, x_np, W=w0_host, H=h0_host)
+            torch.cuda.synchronize()
             t_e2e = time.perf_counter() - t0
+            if world > 1:
+                t = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                t_e2e = float(t)
             assert np.isfinite(res["white_components"]).all()
-            dr_info = None
-            if not args.no_dr:
-                # nfact_dr on one subject of the same shape (C4 is 100 such subjects): regress the matrix onto
-                # the grey components the solve just produced, through the reference-facing call.
+            if not args.no_dr and world == 1:
+                # nfact_dr on one subject of the same shape (C4 is 100 such subjects; subjects are independent,
+                # so N GPUs run N of these side by side): regress the matrix onto the grey components the
+                # solve just produced, through the reference-facing call -- once with the subject's matrix
+                # in (pinned) host memory, once with it already resident.
                 from nfact_b200.device import DeviceMatrix as _DM
+                comps = {"grey_components": res["grey_components"]}
                 t0 = time.perf_counter()
-                xsub = _DM.from_host(x_np, handle)
-                t_up = time.perf_counter() - t0
-                dr = nfact_b200.nmf_dual_regression({"grey_components": res["grey_components"]}, xsub)
-                t_dr = time.perf_counter() - t0
-                xsub.free()
+                dr = nfact_b200.nmf_dual_regression(comps, x_np)
+                t_host = time.perf_counter() - t0
                 assert np.isfinite(dr["white_components"]).all() and (dr["grey_components"] >= 0).all()
-                dr_info = {"value": 1.0 / t_dr, "unit": "subjects/s", "seconds": t_dr, "upload_seconds": t_up,
-                           "solve_seconds": t_dr - t_up, "shape": [int(rows), int(n), int(k)],
-                           "white_nnz_frac": float(np.mean(dr["white_components"] > 0)),
-                           "api": "nfact_b200.nmf_dual_regression(components, X_host) per subject"}
+                nnz = float(np.mean(dr["white_components"] > 0))
+                xsub = _DM.from_host(x_np, handle)
+                times = []
+                for _ in range(3):
+                    del dr
+                    t0 = time.perf_counter()
+                    dr = nfact_b200.nmf_dual_regression(comps, xsub)
+                    times.append(time.perf_counter() - t0)
+                xsub.free()
+                dr_info = {"value": 1.0 / min(times), "unit": "subjects/s", "seconds": min(times),
+                           "e2e_value": 1.0 / t_host, "e2e_seconds": t_host, "shape": [int(rows), int(n), int(k)],
+                           "white_nnz_frac": nnz,
+                           "api": "nfact_b200.nmf_dual_regression(components, X): value = X resident in HBM "
+                                  "(best of 3, float64 results copied to the host), e2e_value = X passed as a host array"}
             e2e = {"value": iters / t_e2e, "unit": UNIT, "iters": iters, "seconds": t_e2e,
-                   "h2d_bytes_per_step": int((x_np.nbytes + w0_host.nbytes + h0_host.nbytes) / iters),
-                   "d2h_bytes_per_step": int((w0_host.nbytes + h0_host.nbytes) / iters),
-                   "api": "nfact_b200.nmf_decomp(parameters, X_host, W=W0, H=H0) with tol=0"}
+                   "h2d_bytes_per_step": int(world * (x_np.nbytes + w0_host.nbytes + h0_host.nbytes) / iters),
+                   "d2h_bytes_per_step": int(world * (w0_host.nbytes + h0_host.nbytes) / iters),
+                   "api": "nfact_b200.nmf_decomp(parameters, X_host, W=W0, H=H0) with tol=0" +
+                          (f", one call per rank on its {rows} seed rows" if world > 1 else "")}
 
     if rank != 0:
         if world > 1:

@@ -74,7 +74,19 @@ def find_libnccl() -> str:
     return "libnccl.so.2"
 
 
-def get_handle(device: int = 0) -> Handle:
+_default_device = 0
+
+
+def set_default_handle(handle: Handle) -> None:
+    """Make ``handle`` (its device, stream and - in row-sharded runs - NCCL communicator) the one the
+    reference-facing entry points (``nmf_decomp``, ``nmf_dual_regression``, the loaders) use in this process."""
+    global _default_device
+    _handles[handle.device] = handle
+    _default_device = handle.device
+
+
+def get_handle(device: int | None = None) -> Handle:
+    device = _default_device if device is None else device
     if device not in _handles:
         _handles[device] = Handle(device)
     return _handles[device]

@@ -50,6 +50,18 @@ def compute_regularization(n_samples: int, n_features: int, alpha_W, alpha_H, l1
             n_features * alpha_W * (1.0 - l1_ratio), n_samples * alpha_H * (1.0 - l1_ratio))
 
 
+def global_rows(handle, m_local: int) -> int:
+    """Seed rows of the whole matrix when X is row-sharded over the handle's NCCL world (one process per
+    GPU, torch.distributed as the rendezvous); the local count otherwise."""
+    if getattr(handle, "world", 1) <= 1:
+        return int(m_local)
+    import torch
+    import torch.distributed as dist
+    total = torch.tensor([int(m_local)], dtype=torch.int64, device=torch.device("cuda", handle.device))
+    dist.all_reduce(total)
+    return int(total.item())
+
+
 def _check_params(p: dict) -> dict:
     unknown = set(p) - set(NMF_DEFAULTS) - {"n_components"}
     if unknown:
@@ -148,7 +160,8 @@ class NMF:
                 if x_mean is None:      # resident matrix: float64 mean accumulated during the split
                     x_mean = xdev.mean
                 W0, H0 = initialize_nmf(xdev, x_mean, k, p["init"], p["random_state"])
-            regs = compute_regularization(m, n, p["alpha_W"], p["alpha_H"], p["l1_ratio"])
+            # row-sharded runs: sklearn's n_samples is the number of seeds of the whole matrix
+            regs = compute_regularization(global_rows(xdev.handle, m), n, p["alpha_W"], p["alpha_H"], p["l1_ratio"])
             state = NmfState(xdev, k, make_params(p["solver"], p["max_iter"], p["tol"], regs, p["verbose"]))
             try:
                 state.set_factors(W0, H0)
