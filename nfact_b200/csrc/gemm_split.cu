@@ -369,21 +369,24 @@ int gemm_default_cta_group() {
     return value;
 }
 
-int gemm_pick_splits(int64_t m_total, int64_t k_total, int cta_group) {
+int gemm_pick_splits(int64_t m_total, int64_t k_total, int cta_group, int64_t n_out) {
     const int64_t m_blocks = ceil_div64(m_total, static_cast<int64_t>(kBlockM) * cta_group);
     const int64_t num_kb = ceil_div64(k_total, kBlockK);
     const int64_t workers = sm_count() / cta_group;
-    // Aim for full waves of equal tiles; keep every split at least 4 K blocks long.
+    // Cost in bytes of HBM time: the operand stream (4 B per element of A, at ~80 % of peak when the waves are
+    // full) divided by the wave efficiency, plus every split slab written once and read once by the consumer.
+    // Every split stays at least 4 K blocks long.
     int64_t best = 1;
-    double best_eff = 0.0;
+    double best_cost = 0.0;
     const int64_t max_splits = std::max<int64_t>(1, std::min<int64_t>(num_kb / 4, 64));
     for (int64_t s = 1; s <= max_splits; ++s) {
         const int64_t tiles = m_blocks * s;
         const int64_t waves = ceil_div64(tiles, workers);
         const double eff = static_cast<double>(tiles) / static_cast<double>(waves * workers);
-        // small bias towards fewer splits (less partial traffic)
-        const double score = eff - 0.002 * static_cast<double>(s);
-        if (score > best_eff) { best_eff = score; best = s; }
+        const double stream = 4.0 * static_cast<double>(m_total) * static_cast<double>(k_total) / (0.8 * eff);
+        const double slabs = s > 1 ? 8.0 * static_cast<double>(s) * static_cast<double>(n_out) * static_cast<double>(m_total) : 0.0;
+        const double cost = stream + slabs;
+        if (s == 1 || cost < best_cost) { best_cost = cost; best = s; }
     }
     return static_cast<int>(best);
 }

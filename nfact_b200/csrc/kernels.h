@@ -17,7 +17,8 @@ struct GemmOperand {
 
 // ---- gemm_split.cu --------------------------------------------------------------------------------
 int gemm_default_cta_group();
-int gemm_pick_splits(int64_t m_total, int64_t k_total, int cta_group);
+// n_out: output columns per row of A (components); weighs the split-slab traffic against the wave efficiency
+int gemm_pick_splits(int64_t m_total, int64_t k_total, int cta_group, int64_t n_out);
 // out[s][t][r] (r contiguous, leading dimension ld_out)
 //     = scale * col_scale[t] * row_scale[r] * sum_{K in split s} A[r,K] B[t,K]      (null scale vectors -> 1)
 //   a_is_mn_major == false : A planes are [m_total rows, K cols]     (X      for X H^T)
@@ -87,6 +88,30 @@ int transpose_f64_to_f32(const double* in, int64_t rows, int64_t cols, int64_t l
                          cudaStream_t stream, int* nonfinite = nullptr);
 int transpose_f64(const double* in, int64_t rows, int64_t cols, int64_t ld_in, double* out, int64_t ld_out,
                   cudaStream_t stream);
+
+// ---- p2p.cu ---------------------------------------------------------------------------------------
+// Row-sharded H half-step over NVLink peer memory (CUDA IPC mappings of every rank's arena and H master).
+constexpr int kP2pMaxWorld = 8;
+constexpr int kP2pRsFlag = 0, kP2pAgFlag = 16, kP2pError = 32;   // int offsets into the arena header
+constexpr int64_t kP2pScalOffset = 256;                          // byte offset of double scal[16][2]
+constexpr int64_t kP2pGramOffset = 512;                          // byte offset of float gram[kp * kp]
+struct P2pPeers {
+    void* arena[kP2pMaxWorld];
+    void* hmaster[kP2pMaxWorld];
+};
+// arena_p.flag[flag_offset + rank] = epoch on every rank p (system-scope release after a fence)
+int p2p_post(const P2pPeers& peers, int world, int rank, int flag_offset, int epoch, cudaStream_t stream);
+// wait for every rank's numerator of `epoch`; out[t][j] = sum_p arena_p.num[t][c0 + j] for j < width (0 up to ns),
+// gram_out = sum_p arena_p.gram.  arena num is [k][ld]; c0, ns, ld are multiples of 8.
+int p2p_pull(const P2pPeers& peers, int world, int rank, int epoch, int k, int64_t ns, int64_t ld, int64_t c0,
+             int64_t num_offset, int64_t gram_offset, int gram_elems, float* out, float* gram_out,
+             cudaStream_t stream);
+// own H columns [c0, c0 + width) -> every peer's H master; scal_src[2] (nullable) -> slot `rank` of every arena
+int p2p_push(const P2pPeers& peers, int world, int rank, int k, int64_t ld, int64_t c0, int64_t width,
+             const double* scal_src, int64_t scal_offset, cudaStream_t stream);
+// wait for every rank's slice of `epoch`; scal_out[i] (nullable) = sum_p scal[p][i]
+int p2p_gather_wait(const P2pPeers& peers, int world, int rank, int epoch, int64_t scal_offset, double* scal_out,
+                    cudaStream_t stream);
 
 // ---- ingest.cu ------------------------------------------------------------------------------------
 // phase A: tmp[r*ncols+c] += v for every triplet with row in [row0, row0+nrows_blk)  (fp64 atomics)

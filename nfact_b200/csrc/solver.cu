@@ -164,6 +164,15 @@ struct nfb_nmf {
     DevBuf<float> part_w, part_h, part_den, part_gram, num_h;
     DevBuf<float> num_sl, pack;   // sharded runs: slice-major numerator / gather buffer [P][k][ns], packed slice
     int64_t slice_cols = 0;       // ns: H columns per rank (multiple of 8)
+    // NVLink peer-memory path (p2p.cu): arena + H master of every rank mapped through CUDA IPC
+    bool p2p = false;
+    DevBuf<char> arena;
+    P2pPeers peers{};
+    std::vector<void*> ipc_opened;
+    int epoch = 0;
+    int64_t arena_num_off = 0;    // float offset of num[k][ld] inside the arena
+    float* arena_num() const { return reinterpret_cast<float*>(arena.p) + arena_num_off; }
+    float* arena_gram() const { return reinterpret_cast<float*>(arena.p + kP2pGramOffset); }
     int s_w = 1, s_h = 1, s_gw = 1, s_gh = 1;
     double sumsq_global = 0.0;
     bool p1_valid = false;  // part_w holds X H' for the current H
@@ -188,15 +197,16 @@ static int allreduce_f64(nfb_handle* h, double* buf, size_t count) {
 }
 
 // G = F F' (fp32 [k][kp]) through the tensor-core path; partial sums over `splits` K ranges.
-static int compute_gram(nfb_nmf* s, Factor& fac, Factor& gram, int splits, bool allreduce) {
+// to_arena: leave the local Gram in the peer-visible arena; the pull kernel of the H half-step sums all ranks'
+static int compute_gram(nfb_nmf* s, Factor& fac, Factor& gram, int splits, bool allreduce, bool to_arena = false) {
     nfb_handle* h = s->h;
     NFB_TRY(gemm_split(fac.operand(), false, fac.operand(), fac.k, fac.dim, static_cast<int>(fac.kp),
                        static_cast<int>(fac.k), s->part_gram.p, gram.ld, splits, fac.inv_scale.p, fac.inv_scale.p,
                        1.0f, h->cta_group, h->stream));
-    NFB_TRY(reduce_partials(s->part_gram.p, splits, fac.k * gram.ld, fac.k, fac.k, gram.ld, 0.0f, gram.f.p, gram.ld,
-                            h->stream));
+    NFB_TRY(reduce_partials(s->part_gram.p, splits, fac.k * gram.ld, fac.k, fac.k, gram.ld, 0.0f,
+                            to_arena ? s->arena_gram() : gram.f.p, gram.ld, h->stream));
     note_launch(2);
-    if (allreduce) NFB_TRY(allreduce_f32(h, gram.f.p, static_cast<size_t>(gram.kp * gram.ld)));
+    if (allreduce && !to_arena) NFB_TRY(allreduce_f32(h, gram.f.p, static_cast<size_t>(gram.kp * gram.ld)));
     return 0;
 }
 
@@ -280,16 +290,37 @@ struct HNumerator {
 
 static int gemm_wtx(nfb_nmf* s, HNumerator* out) {
     nfb_handle* h = s->h;
+    // peer-memory path, unsplit GEMM: the epilogue writes the local numerator straight into the arena
+    const bool direct = s->p2p && s->s_h == 1;
     {
     GemmTimer timer(h);
     NFB_TRY(gemm_split(s->x->operand(), true, s->wt.operand(), s->x->n, s->x->m, static_cast<int>(s->kp), s->k,
-                       s->part_h.p, s->hh.ld, s->s_h, s->wt.inv_scale.p, nullptr, s->x->inv_scale_host,
-                       h->cta_group, h->stream));
+                       direct ? s->arena_num() : s->part_h.p, s->hh.ld, s->s_h, s->wt.inv_scale.p, nullptr,
+                       s->x->inv_scale_host, h->cta_group, h->stream));
     }
     note_launch(1);
     const int64_t n = s->x->n;
     if (h->world <= 1) {
         *out = HNumerator{s->part_h.p, s->s_h, static_cast<int64_t>(s->k) * s->hh.ld, s->hh.ld, 0, n};
+        return 0;
+    }
+    if (s->p2p) {
+        // (split-K sum into the peer-visible arena,) post, then pull this rank's column slice from everybody
+        const int64_t ns = s->slice_cols;
+        if (!direct) {
+            NFB_PHASE(h, "rs_local");
+            NFB_TRY(reduce_partials(s->part_h.p, s->s_h, static_cast<int64_t>(s->k) * s->hh.ld, s->k, n, s->hh.ld, 0.0f,
+                                    s->arena_num(), s->hh.ld, h->stream));
+            note_launch(1);
+        }
+        ++s->epoch;
+        NFB_PHASE(h, "rs_pull");
+        const int64_t c0 = std::min<int64_t>(n, h->rank * ns);
+        NFB_TRY(p2p_post(s->peers, h->world, h->rank, kP2pRsFlag, s->epoch, h->stream));
+        NFB_TRY(p2p_pull(s->peers, h->world, h->rank, s->epoch, s->k, ns, s->hh.ld, h->rank * ns, s->arena_num_off,
+                         kP2pGramOffset / 4, static_cast<int>(s->kp * s->kp), s->num_h.p, s->gw.f.p, h->stream));
+        note_launch(2);
+        *out = HNumerator{s->num_h.p, 1, 0, ns, c0, std::min<int64_t>(ns, n - c0)};
         return 0;
     }
     if (h->reduce_scatter != nullptr && h->all_gather != nullptr) {
@@ -318,6 +349,17 @@ static int gather_h_slices(nfb_nmf* s, const HNumerator& hn) {
     nfb_handle* h = s->h;
     if (h->world <= 1 || hn.width == s->x->n) return 0;
     const int64_t ns = s->slice_cols, n = s->x->n;
+    if (s->p2p) {
+        // CD: the two violation partial sums travel with the slice and come back summed over ranks
+        double* scal = s->p.solver == 0 ? h->d_scal.p + 2 : nullptr;
+        NFB_PHASE(h, "ag_push");
+        NFB_TRY(p2p_push(s->peers, h->world, h->rank, s->k, s->hh.ld, hn.col0, std::max<int64_t>(hn.width, 0), scal,
+                         kP2pScalOffset, h->stream));
+        NFB_TRY(p2p_post(s->peers, h->world, h->rank, kP2pAgFlag, s->epoch, h->stream));
+        NFB_TRY(p2p_gather_wait(s->peers, h->world, h->rank, s->epoch, kP2pScalOffset, scal, h->stream));
+        note_launch(3);
+        return 0;
+    }
     if (hn.width > 0)
         NFB_CUDA(cudaMemcpy2DAsync(s->pack.p, ns * sizeof(float), s->hh.f.p + hn.col0, s->hh.ld * sizeof(float),
                                    hn.width * sizeof(float), s->k, cudaMemcpyDeviceToDevice, h->stream));
@@ -373,7 +415,7 @@ static int mu_iteration(nfb_nmf* s) {
     note_launch(1);
     s->p1_valid = false;
     { NFB_PHASE(h, "split_w"); NFB_TRY(refresh_planes(s->wt, s->wt.f.p, nullptr, false, h->stream)); }
-    { NFB_PHASE(h, "gram_w"); NFB_TRY(compute_gram(s, s->wt, s->gw, s->s_gw, true)); }
+    { NFB_PHASE(h, "gram_w"); NFB_TRY(compute_gram(s, s->wt, s->gw, s->s_gw, true, s->p2p)); }
     // ---- H half-step ----
     HNumerator hn;
     { NFB_PHASE(h, "gemm_wtx"); NFB_TRY(gemm_wtx(s, &hn)); }
@@ -407,7 +449,7 @@ static int cd_iteration(nfb_nmf* s, double* violation_out) {
     note_launch(1);
     s->p1_valid = false;
     { NFB_PHASE(h, "split_w"); NFB_TRY(refresh_planes(s->wt, s->wt.f.p, nullptr, false, h->stream)); }
-    { NFB_PHASE(h, "gram_w"); NFB_TRY(compute_gram(s, s->wt, s->gw, s->s_gw, true)); }
+    { NFB_PHASE(h, "gram_w"); NFB_TRY(compute_gram(s, s->wt, s->gw, s->s_gw, true, s->p2p)); }
     // ---- H half-step ----
     HNumerator hn;
     { NFB_PHASE(h, "gemm_wtx"); NFB_TRY(gemm_wtx(s, &hn)); }
@@ -424,7 +466,7 @@ static int cd_iteration(nfb_nmf* s, double* violation_out) {
     if (violation_out != nullptr) {
         // W rows are sharded; H columns are sharded too when the update was sliced, replicated otherwise
         const bool h_sliced = hn.width != s->x->n;
-        NFB_TRY(allreduce_f64(h, h->d_scal.p + 2, h_sliced ? 2 : 1));
+        if (!s->p2p) NFB_TRY(allreduce_f64(h, h->d_scal.p + 2, h_sliced ? 2 : 1));   // p2p: summed with the gather
         NFB_CUDA(cudaMemcpyAsync(h->h_scal + 2, h->d_scal.p + 2, 2 * sizeof(double), cudaMemcpyDeviceToHost,
                                  h->stream));
         NFB_CUDA(cudaStreamSynchronize(h->stream));
@@ -457,6 +499,91 @@ static int nmf_prepare_factors(nfb_nmf* s) {
     NFB_TRY(compute_gram(s, s->wt, s->gw, s->s_gw, true));
     NFB_TRY(compute_gram(s, s->hh, s->gh, s->s_gh, false));
     s->p1_valid = false;
+    return 0;
+}
+
+
+// Map every rank's arena and H master into this process (CUDA IPC; the 2 x 64-byte handles are exchanged with
+// ncclAllGather so the C ABI needs no help from the host language).  Any failure on any rank -- IPC not
+// permitted in the container, no peer access, more than kP2pMaxWorld ranks, NFB_P2P=0 -- leaves p2p off on
+// ALL ranks and the NCCL reduce-scatter / all-gather path in charge.
+static int p2p_setup(nfb_nmf* s) {
+    nfb_handle* h = s->h;
+    cudaStream_t st = h->stream;
+    const char* env = getenv("NFB_P2P");
+    const bool want = h->world <= kP2pMaxWorld && h->all_gather != nullptr && !(env != nullptr && atoi(env) == 0);
+    const int64_t gram_bytes = round_up64(s->kp * s->kp * 4, 256);
+    s->arena_num_off = (kP2pGramOffset + gram_bytes) / 4;
+    const size_t arena_bytes = static_cast<size_t>(s->arena_num_off) * 4 + sizeof(float) * s->k * s->hh.ld;
+    int failed = want ? 0 : 1;
+    cudaIpcMemHandle_t mine[2];
+    memset(mine, 0, sizeof(mine));
+    if (!failed) {
+        if (s->arena.alloc(arena_bytes, true, st) != 0) failed = 1;
+    }
+    if (!failed) {
+        cudaStreamSynchronize(st);   // the zeroed flags must be in place before any peer can post
+        if (cudaIpcGetMemHandle(&mine[0], s->arena.p) != cudaSuccess ||
+            cudaIpcGetMemHandle(&mine[1], s->hh.f.p) != cudaSuccess) {
+            cudaGetLastError();
+            failed = 1;
+        }
+    }
+    // exchange handles (every rank takes part, also the ones that already failed)
+    DevBuf<char> send, recv;
+    NFB_TRY(send.alloc(sizeof(mine), false, st));
+    NFB_TRY(recv.alloc(sizeof(mine) * h->world, false, st));
+    NFB_CUDA(cudaMemcpyAsync(send.p, mine, sizeof(mine), cudaMemcpyHostToDevice, st));
+    if (h->all_gather != nullptr) {
+        int rc = h->all_gather(send.p, recv.p, sizeof(mine), /*ncclInt8*/ 0, h->comm, st);
+        NFB_CHECK(rc == 0, "ncclAllGather(ipc handles) failed with code " + std::to_string(rc));
+    }
+    std::vector<cudaIpcMemHandle_t> all(2 * h->world);
+    NFB_CUDA(cudaMemcpyAsync(all.data(), recv.p, sizeof(mine) * h->world, cudaMemcpyDeviceToHost, st));
+    NFB_CUDA(cudaStreamSynchronize(st));
+    if (!failed) {
+        for (int p = 0; p < h->world && !failed; ++p) {
+            if (p == h->rank) {
+                s->peers.arena[p] = s->arena.p;
+                s->peers.hmaster[p] = s->hh.f.p;
+                continue;
+            }
+            for (int which = 0; which < 2 && !failed; ++which) {
+                void* ptr = nullptr;
+                if (cudaIpcOpenMemHandle(&ptr, all[2 * p + which], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                    cudaGetLastError();
+                    failed = 1;
+                    break;
+                }
+                s->ipc_opened.push_back(ptr);
+                (which == 0 ? s->peers.arena[p] : s->peers.hmaster[p]) = ptr;
+            }
+        }
+    }
+    // agree: one failure anywhere turns the path off everywhere
+    h->h_scal[14] = failed ? 1.0 : 0.0;
+    NFB_CUDA(cudaMemcpyAsync(h->d_scal.p + 14, h->h_scal + 14, sizeof(double), cudaMemcpyHostToDevice, st));
+    NFB_TRY(allreduce_f64(h, h->d_scal.p + 14, 1));
+    NFB_CUDA(cudaMemcpyAsync(h->h_scal + 14, h->d_scal.p + 14, sizeof(double), cudaMemcpyDeviceToHost, st));
+    NFB_CUDA(cudaStreamSynchronize(st));
+    s->p2p = h->h_scal[14] == 0.0;
+    if (!s->p2p) {
+        for (void* ptr : s->ipc_opened) cudaIpcCloseMemHandle(ptr);
+        s->ipc_opened.clear();
+        if (getenv("NFB_P2P_VERBOSE") && !(env != nullptr && atoi(env) == 0))
+            fprintf(stderr, "nfact_b200 rank %d: peer-memory path unavailable, using NCCL collectives\n", h->rank);
+    }
+    return 0;
+}
+
+// a wait that timed out (a peer died or fell out of step) poisons the results: tell the caller
+static int p2p_check(nfb_nmf* s) {
+    if (!s->p2p) return 0;
+    int err = 0;
+    NFB_CUDA(cudaMemcpyAsync(&err, reinterpret_cast<int*>(s->arena.p) + kP2pError, sizeof(int), cudaMemcpyDeviceToHost,
+                             s->h->stream));
+    NFB_CUDA(cudaStreamSynchronize(s->h->stream));
+    NFB_CHECK(err == 0, "peer-memory exchange timed out waiting for another rank");
     return 0;
 }
 
@@ -729,10 +856,10 @@ int nfb_nmf_create(nfb_handle* h, const nfb_matrix* x, int k, const nfb_nmf_para
     NFB_TRY(s->gh.init(k, k, true, st, s->kp));
     NFB_TRY(s->gd.init(k, k, false, st, s->kp));
     const int cg = h->cta_group;
-    s->s_w = gemm_pick_splits(x->m, x->n, cg);
-    s->s_h = gemm_pick_splits(x->n, x->m, cg);
-    s->s_gw = gemm_pick_splits(k, x->m, cg);
-    s->s_gh = gemm_pick_splits(k, x->n, cg);
+    s->s_w = gemm_pick_splits(x->m, x->n, cg, k);
+    s->s_h = gemm_pick_splits(x->n, x->m, cg, k);
+    s->s_gw = gemm_pick_splits(k, x->m, cg, k);
+    s->s_gh = gemm_pick_splits(k, x->n, cg, k);
     NFB_TRY(s->part_w.alloc(static_cast<size_t>(s->s_w) * k * s->wt.ld, false, st));
     NFB_TRY(s->part_h.alloc(static_cast<size_t>(s->s_h) * k * s->hh.ld, false, st));
     NFB_TRY(s->part_den.alloc(static_cast<size_t>(k) * std::max(s->wt.ld, s->hh.ld), false, st));
@@ -743,6 +870,7 @@ int nfb_nmf_create(nfb_handle* h, const nfb_matrix* x, int k, const nfb_nmf_para
         NFB_TRY(s->num_sl.alloc(static_cast<size_t>(h->world) * k * s->slice_cols, true, st));
         NFB_TRY(s->pack.alloc(static_cast<size_t>(k) * s->slice_cols, true, st));
     }
+    if (h->world > 1) NFB_TRY(p2p_setup(s.get()));
     // ||X||^2 over all row shards
     h->h_scal[5] = x->sumsq;
     if (h->world > 1) {
@@ -759,6 +887,12 @@ int nfb_nmf_create(nfb_handle* h, const nfb_matrix* x, int k, const nfb_nmf_para
 int nfb_nmf_free(nfb_nmf* s) {
     if (s == nullptr) return 0;
     cudaSetDevice(s->h->device);
+    if (s->p2p) {
+        // collective: nobody unmaps / frees an arena while a peer's kernels may still touch it
+        allreduce_f64(s->h, s->h->d_scal.p + 15, 1);
+        cudaStreamSynchronize(s->h->stream);
+        for (void* ptr : s->ipc_opened) cudaIpcCloseMemHandle(ptr);
+    }
     cudaStreamSynchronize(s->h->stream);
     delete s;
     return 0;
@@ -831,6 +965,7 @@ int nfb_nmf_iterate(nfb_nmf* s, int n_iters, double* violation_out) {
     }
     s->h->launches_last = g_launches.load() - before;
     report_phases(s->h, n_iters);
+    NFB_TRY(p2p_check(s));
     return 0;
 }
 
@@ -880,6 +1015,7 @@ int nfb_nmf_run(nfb_nmf* s, int* n_iter_out, double* recon_err_out) {
     if (n_iter_out) *n_iter_out = n_iter;
     if (recon_err_out) NFB_TRY(nmf_error(s, recon_err_out));
     s->h->launches_last = g_launches.load() - before;
+    NFB_TRY(p2p_check(s));
     return 0;
 }
 
@@ -967,7 +1103,7 @@ int nfb_dual_regression_host(nfb_handle* h, const nfb_matrix* x, int k, const vo
     NFB_TRY(gram64.alloc(static_cast<size_t>(k) * k, false, st));
     NFB_TRY(sol_h.alloc(static_cast<size_t>(k) * hs.ld, true, st));
     NFB_TRY(sol_g.alloc(static_cast<size_t>(k) * gt.ld, true, st));
-    const int s1 = gemm_pick_splits(n, m, cg), s2 = gemm_pick_splits(m, n, cg);
+    const int s1 = gemm_pick_splits(n, m, cg, k), s2 = gemm_pick_splits(m, n, cg, k);
     DevBuf<float> part;
     NFB_TRY(part.alloc(std::max(static_cast<size_t>(s1) * k * hs.ld, static_cast<size_t>(s2) * k * gt.ld), false, st));
     NFB_CUDA(cudaMemsetAsync(h->d_int.p, 0, 3 * sizeof(int), st));
@@ -1109,7 +1245,7 @@ int nfb_matrix_matmul(nfb_handle* h, const nfb_matrix* x, int trans, const float
     const int64_t k_total = trans ? x->m : x->n;
     NFB_CHECK(ld_out >= m_total, "ld_out too small");
     const int cg = h->cta_group;
-    const int splits = gemm_pick_splits(m_total, k_total, cg);
+    const int splits = gemm_pick_splits(m_total, k_total, cg, std::min<int64_t>(n_b, 512));
     for (int64_t t0 = 0; t0 < n_b; t0 += 512) {
         const int64_t nb = std::min<int64_t>(512, n_b - t0);
         Factor b;
@@ -1149,7 +1285,7 @@ int nfb_test_gemm(nfb_handle* h, const float* a_dev, int64_t a_rows, int64_t a_c
                                n_b, cudaMemcpyDeviceToDevice, st));
     NFB_TRY(refresh_planes(b, bpad.p, nullptr, true, st));
     if (cta_group == 0) cta_group = h->cta_group;
-    if (splits <= 0) splits = gemm_pick_splits(m_total, k_total, cta_group);
+    if (splits <= 0) splits = gemm_pick_splits(m_total, k_total, cta_group, n_b);
     DevBuf<float> part;
     NFB_TRY(part.alloc(static_cast<size_t>(splits) * n_b * ld_out, false, st));
     NFB_TRY(gemm_split(a->operand(), a_is_transposed != 0, b.operand(), m_total, k_total, static_cast<int>(b.kp),
