@@ -13,6 +13,7 @@
 // order of the reference kept exactly.
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -327,52 +328,81 @@ cd_sweep_tile_kernel(float* __restrict__ f, int k, int64_t cols, int64_t ld, con
             *reinterpret_cast<float4*>(gs + u * TJ + 4 * c4) = gv;
         }
     }
+    // factor values of the block in flight; loads are unconditional (clamped indices) and zeroed afterwards so
+    // that the 16 of them are independent straight-line loads
+    const int64_t jc_own = active ? j : 0;
+    const int u_own = min(tid, k - 1);
     float fl[kBlk];
 #pragma unroll
-    for (int i = 0; i < kBlk; ++i) fl[i] = (active && i < k) ? f[static_cast<int64_t>(i) * ld + j] : 0.0f;
+    for (int i = 0; i < kBlk; ++i) {
+        const float v = f[static_cast<int64_t>(min(i, k - 1)) * ld + jc_own];
+        fl[i] = (active && i < k) ? v : 0.0f;
+    }
     __syncthreads();
 
     float viol = 0.0f;
     const int jg = tid % JG, ug = tid / JG;
+    // one block of coordinate steps for sample `tid`; kFull: all 16 components exist (no bounds predicates)
+    auto step_block = [&](auto full_tag, int t0, int nb) {
+        constexpr bool kFull = decltype(full_tag)::value;
+        float gl[kBlk];
+#pragma unroll
+        for (int i = 0; i < kBlk; ++i) gl[i] = (kFull || i < nb) ? gs[(t0 + i) * TJ + tid] : 0.0f;
+        float* fp = f + static_cast<int64_t>(t0) * ld + jc_own;
+#pragma unroll
+        for (int i = 0; i < kBlk; ++i) {
+            if (kFull || i < nb) {
+                const float ft = fl[i];
+                const float gt = gl[i];
+                viol += fabsf((ft == 0.0f) ? fminf(0.0f, gt) : gt);
+                const float inv = invh[i];
+                const float fn = fmaxf(fmaf(-gt, inv, ft), 0.0f);
+                const float delta = inv != 0.0f ? fn - ft : 0.0f;
+                if (active && delta != 0.0f) *fp = fn;
+                fp += ld;
+                // values are >= 0, so unsigned order == float order
+                const unsigned int vmax = __reduce_max_sync(0xffffffffu, active ? __float_as_uint(ft + delta) : 0u);
+                if ((tid & 31) == 0 && vmax != 0u) atomicMax(&max_s[i], vmax);
+                // row i of the diagonal block of G, columns i+1..15, as 128-bit broadcast loads
+                const float4* grow4 = reinterpret_cast<const float4*>(gb + i * kp4 + t0);
+                float grow[kBlk];
+#pragma unroll
+                for (int c = (i + 1) / 4; c < kBlk / 4; ++c) {
+                    const float4 q = grow4[c];
+                    grow[4 * c] = q.x; grow[4 * c + 1] = q.y; grow[4 * c + 2] = q.z; grow[4 * c + 3] = q.w;
+                }
+#pragma unroll
+                for (int i2 = i + 1; i2 < kBlk; ++i2)
+                    if (kFull || i2 < nb) gl[i2] = fmaf(delta, grow[i2], gl[i2]);
+                gs[(t0 + i) * TJ + tid] = delta;           // the gradient row is dead: it now carries the deltas
+            }
+        }
+    };
     for (int t0 = 0; t0 < k; t0 += kBlk) {
         const int nb = min(kBlk, k - t0);
         const bool more = t0 + kBlk < k;                   // components after this block exist (then nb == 16)
         // ---- step phase: the block's coordinate steps for sample `tid`, in registers ---------------------
         if (stepper) {
-            float gl[kBlk];
-#pragma unroll
-            for (int i = 0; i < kBlk; ++i) gl[i] = i < nb ? gs[(t0 + i) * TJ + tid] : 0.0f;
-#pragma unroll
-            for (int i = 0; i < kBlk; ++i) {
-                if (i < nb) {
-                    const float ft = fl[i];
-                    const float gt = gl[i];
-                    viol += fabsf((ft == 0.0f) ? fminf(0.0f, gt) : gt);
-                    const float inv = invh[i];
-                    const float fn = fmaxf(fmaf(-gt, inv, ft), 0.0f);
-                    const float delta = inv != 0.0f ? fn - ft : 0.0f;
-                    if (active && delta != 0.0f) f[static_cast<int64_t>(t0 + i) * ld + j] = fn;
-                    // values are >= 0, so unsigned order == float order
-                    const unsigned int vmax = __reduce_max_sync(0xffffffffu, active ? __float_as_uint(ft + delta) : 0u);
-                    if ((tid & 31) == 0 && vmax != 0u) atomicMax(&max_s[i], vmax);
-                    const float* grow = gb + i * kp4 + t0;
-#pragma unroll
-                    for (int i2 = i + 1; i2 < kBlk; ++i2)
-                        if (i2 < nb) gl[i2] = fmaf(delta, grow[i2], gl[i2]);
-                    gs[(t0 + i) * TJ + tid] = delta;       // the gradient row is dead: it now carries the deltas
-                }
-            }
+            if (nb == kBlk) step_block(std::true_type{}, t0, nb);
+            else step_block(std::false_type{}, t0, nb);
         }
         // ---- prefetch the next block's operands across the apply phase --------------------------------------
         float pre[kBlk];                                   // column `tid` of the next block's G rows
         float hess_next = 0.0f;
         if (more) {
 #pragma unroll
-            for (int i = 0; i < kBlk; ++i) pre[i] = tid < kp4 ? load_g(t0 + kBlk + i, tid) : 0.0f;
+            for (int i = 0; i < kBlk; ++i) {
+                const int t = t0 + kBlk + i;
+                const float v = __ldg(gram + static_cast<int64_t>(min(t, k - 1)) * ldg + u_own);
+                pre[i] = (t < k && tid < k) ? v : 0.0f;
+            }
             hess_next = load_hess(t0 + kBlk);
 #pragma unroll
-            for (int i = 0; i < kBlk; ++i)
-                fl[i] = (active && t0 + kBlk + i < k) ? f[static_cast<int64_t>(t0 + kBlk + i) * ld + j] : 0.0f;
+            for (int i = 0; i < kBlk; ++i) {
+                const int t = t0 + kBlk + i;
+                const float v = f[static_cast<int64_t>(min(t, k - 1)) * ld + jc_own];
+                fl[i] = (active && t < k) ? v : 0.0f;
+            }
         }
         __syncthreads();
         if (tid < kBlk) {
