@@ -31,10 +31,13 @@ WORKLOADS = {
     "C1": (5000, 10000, 50, 0.15),
     "C2": (29696, 60000, 100, 0.05),
     "C3": (59412, 110000, 200, 0.05),
+    "C5": (59412, 230000, 500, 0.05),   # 54.7 GB of planes; run with --no-e2e (the host copy would need as much RAM)
 }
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of gemm_split_kernel from the ncu --set full capture
-# of this same command (profiles/r01_ncu_full_gemm_split_C3.csv: X H' 26.63+0.28 GB, W'X 26.60+0.52 GB)
-NCU_TRAFFIC_PER_LAUNCH = {"C3": 27.0e9}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of gemm_split_kernel from the ncu --set full captures
+# of this same command (profiles/r01_ncu_full_gemm_split_C3.csv: X H' 26.63+0.28 GB with 6 split slabs;
+# profiles/r01_ncu_full_final_C3.csv: W'X 26.55+0.08 GB unsplit) -> mean of the two launches of an iteration
+NCU_TRAFFIC_PER_LAUNCH = {"C3": 26.77e9}
+NCU_TENSOR_PIPE_ACTIVE = {"C3": 0.86}    # sm__pipe_tensor_cycles_active of the W'X launch, same capture
 METRIC = "nmf_iterations_per_second"
 UNIT = "iter/s"
 ALPHA_W, L1_RATIO = 0.1, 1.0   # NFACT defaults (matrix_decomposition.py:100-107)
@@ -57,12 +60,14 @@ def parse_args():
 
 
 def measured_peaks():
+    """(HBM GB/s, dense bf16 TFLOP/s sustained, source)."""
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         with open(path) as fh:
             data = json.load(fh)
-        return float(data["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
-    return 6650.0, "fallback (B200_PROFILING.md)"
+        return (float(data["hbm_gbs"]), float(data.get("bf16_tflops_sustained", data.get("bf16_tflops", 1418.0))),
+                "measured (MEASURED_PEAKS.json; the sustained bf16 figure: the kernel is timed inside a long step)")
+    return 6650.0, 2250.0, "fallback (B200_PROFILING.md)"
 
 
 def regularization(m_total, n, k):
@@ -295,6 +300,7 @@ def run_ours(args):
             dist.all_reduce(x_sum)
         x_mean = float(x_sum) / (m * n)
         stream.synchronize()
+        torch.cuda.empty_cache()      # hand the generator's scratch back before the library allocates the planes
         xmat = DeviceMatrix.from_device_ptr(x_dev.data_ptr(), rows, n, n, handle=handle)
         want_e2e = not args.no_e2e
         x_host = None
@@ -403,10 +409,21 @@ def run_ours(args):
         return
 
     ms_per_step = elapsed_ms / args.steps
-    hbm_peak, peak_src = measured_peaks()
+    hbm_peak, tc_peak, peak_src = measured_peaks()
     gemm_avg_ms = gemm_ms / max(gemm_launches, 1)
-    bytes_per_launch = 4.0 * rows * n                      # one pass over the fp16 hi+lo planes of X
-    achieved = bytes_per_launch / (gemm_avg_ms * 1e-3) / 1e9 if gemm_launches else 0.0
+    # dominant kernel = gemm_split_kernel, one pass over the fp16 hi+lo planes of X per launch:
+    # algorithmic bytes 4 m n, algorithmic flops 2 m n k; the roofline that bounds it
+    # is the slower of the two at the measured peaks
+    bytes_per_launch = 4.0 * rows * n
+    flops_per_launch = 2.0 * rows * n * k
+    t_hbm, t_tc = bytes_per_launch / (hbm_peak * 1e9), flops_per_launch / (tc_peak * 1e12)
+    if t_hbm >= t_tc:
+        bound, unit, peak = "hbm", "GB/s", hbm_peak
+        achieved = bytes_per_launch / (gemm_avg_ms * 1e-3) / 1e9 if gemm_launches else 0.0
+    else:
+        bound, unit, peak = "tensor", "TFLOP/s", tc_peak
+        achieved = flops_per_launch / (gemm_avg_ms * 1e-3) / 1e12 if gemm_launches else 0.0
+    t_step_roof = 2.0 * max(t_hbm, t_tc)
     line = {
         "metric": METRIC, "value": 1000.0 / ms_per_step, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
@@ -417,13 +434,15 @@ def run_ours(args):
                    "final_error": final_err},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "gemm_split_kernel (X H' and W'X)", "achieved": achieved,
-                     "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+        "roofline": {"bound": bound, "kernel": "gemm_split_kernel (X H' and W'X)", "achieved": achieved,
+                     "peak": peak, "unit": unit, "frac": achieved / peak,
                      "traffic": NCU_TRAFFIC_PER_LAUNCH.get(args.workload) if world == 1 else None,
-                     "tensor_pipe_active_ncu": 0.92 if args.workload == "C3" else None,
+                     "tensor_pipe_active_ncu": NCU_TENSOR_PIPE_ACTIVE.get(args.workload),
                      "peak_source": peak_src, "avg_launch_ms": gemm_avg_ms, "launches": int(gemm_launches),
                      "algorithmic_bytes_per_launch": bytes_per_launch,
-                     "step_frac": (8.0 * rows * n / hbm_peak / 1e9) / (ms_per_step * 1e-3)},
+                     "algorithmic_flops_per_launch": flops_per_launch,
+                     "mma_flops_per_launch": 3.0 * 2.0 * rows * n * (16 * ((k + 15) // 16)),
+                     "step_frac": t_step_roof / (ms_per_step * 1e-3)},
     }
     if e2e is not None:
         line["e2e"] = e2e
