@@ -483,8 +483,10 @@ int cd_sweep(float* f, int64_t k, int64_t cols, int64_t ld, const float* num, in
         const size_t smem_cap = 227 * 1024 - 1024;
         int best = 0;
         int64_t best_cost = 0;
+        const int forced = getenv("NFB_CD_TILE") ? atoi(getenv("NFB_CD_TILE")) : 0;   // tests: pin the tile size
         for (int tj : tiles) {
             if (smem_tile(tj) > smem_cap) continue;
+            if (forced != 0 && tj != forced) continue;
             const int64_t waves = ceil_div64(ceil_div64(cols, tj), sm_count());
             const int64_t cost = waves * (tj + 48);        // + the per-CTA latency-bound part
             if (best == 0 || cost < best_cost) { best = tj; best_cost = cost; }

@@ -74,3 +74,23 @@ def test_dr_subject_pipeline(golden, tmp_path):
     assert res["normalised_white"].shape == (10, 199)
     ref_white = nfact_b200.thresholding(golden["dr_white"].copy(), 1)
     assert np.abs(res["white_components"] - ref_white).max() <= 1e-3 * np.abs(ref_white).max()
+
+
+def test_dr_float32_components_and_nonfinite(golden):
+    """GIFTI / CIFTI loaders hand float32 group components (nfact_dr_functions.py:296-353): same result as the
+    float64 copy of the same values; inf / NaN anywhere is rejected like scipy does (checked on the device)."""
+    import nfact_b200
+    g32 = golden["cd_fit_W"].astype(np.float32)
+    dr32 = nfact_b200.nmf_dual_regression({"grey_components": g32}, golden["ingest_single_1"])
+    dr64 = nfact_b200.nmf_dual_regression({"grey_components": g32.astype(np.float64)}, golden["ingest_single_1"])
+    assert dr32["grey_components"].dtype == np.float64
+    assert np.array_equal(dr32["white_components"], dr64["white_components"])
+    assert np.array_equal(dr32["grey_components"], dr64["grey_components"])
+    bad = g32.copy()
+    bad[7, 3] = np.nan
+    with pytest.raises(ValueError):
+        nfact_b200.nmf_dual_regression({"grey_components": bad}, golden["ingest_single_1"])
+    xbad = golden["ingest_single_1"].copy()
+    xbad[5, 60] = np.inf
+    with pytest.raises(ValueError):
+        nfact_b200.nmf_dual_regression({"grey_components": g32}, xbad)

@@ -87,3 +87,37 @@ def test_dr_tiny_and_zero_component(golden):
     assert rel_fro(dr["white_components"], ref["white_components"]) < 1e-4
     assert rel_fro(dr["grey_components"], ref["grey_components"]) < 1e-4
     assert not dr["white_components"][2].any()
+
+
+@pytest.mark.parametrize("tile", [32, 64, 96, 128, 160, 192, 224, 256])
+@pytest.mark.parametrize("k", [16, 37, 50])
+def test_cd_sweep_every_tile_size(tile, k, monkeypatch):
+    """Every instantiation of the blocked sweep (sample tile x thread count) against the oracle, with k a
+    multiple of the 16-wide component block, one component past it, and a ragged last block; the column
+    count leaves a partial tile and is not a multiple of 4 (scalar seed path)."""
+    monkeypatch.setenv("NFB_CD_TILE", str(tile))
+    rng = np.random.default_rng(tile + k)
+    m, n = 611, 1030
+    X = (rng.gamma(0.5, 1.0, (m, n)) * (rng.random((m, n)) < 0.5) * 40).astype(np.float32)
+    W, H, Wr, Hr = _run(X, k, "cd", 3)
+    assert rel_fro(W, Wr) < 1e-4 and rel_fro(H, Hr) < 1e-4
+
+
+def test_results_are_page_locked_numpy_arrays(golden):
+    """W / H come back as ordinary writable float32 arrays (page-locked underneath, recycled by size)."""
+    import gc
+    import nfact_b200
+    p = dict(nfact_b200.get_parameters(None, "nmf", 10), max_iter=2)
+    res = nfact_b200.nmf_decomp(p, golden["ingest_group"], W=golden["init_nndsvd_W"].copy(),
+                                H=golden["init_nndsvd_H"].copy())
+    W, H = res["grey_components"], res["white_components"]
+    assert isinstance(W, np.ndarray) and W.dtype == np.float32 and W.flags.writeable and W.flags.c_contiguous
+    addr = W.ctypes.data
+    nfact_b200.thresholding(H, 1)          # downstream code mutates the arrays in place
+    keep = W.copy()
+    del res, W, H
+    gc.collect()
+    res2 = nfact_b200.nmf_decomp(p, golden["ingest_group"], W=golden["init_nndsvd_W"].copy(),
+                                 H=golden["init_nndsvd_H"].copy())
+    assert np.array_equal(res2["grey_components"], keep)            # deterministic, and not clobbered
+    assert res2["grey_components"].ctypes.data == addr              # the block was recycled
