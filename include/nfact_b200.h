@@ -56,6 +56,13 @@ int nfb_ingest_coo(nfb_handle* h, int n_subjects, const int32_t* const* rows_hos
                    const double* const* vals_host, const int64_t* nnz, const double* scale, int64_t nrows,
                    int64_t ncols, int group_mode, float* x_out_host, float* x_out_dev);
 
+/* Same ingest, but the result stays on the device as a resident nfb_matrix (no 4mn-byte round trip through the
+ * host): what the per-subject dual-regression pipeline (NFACT/dual_reg/dual_regression/run_dual_regression.py:
+ * 150-164, load_fdt_matrix -> run_decomp) needs. */
+int nfb_ingest_coo_matrix(nfb_handle* h, int n_subjects, const int32_t* const* rows_host,
+                          const int32_t* const* cols_host, const double* const* vals_host, const int64_t* nnz,
+                          const double* scale, int64_t nrows, int64_t ncols, int group_mode, nfb_matrix** out);
+
 /* Text parser for fdt_matrix2.dot (replaces np.loadtxt at NFACT/base/matrix_handling.py:93-113).
  * `buf` is the (decompressed) file content.  Two calls: count the non-empty lines, then fill three
  * float64 arrays of that length with the row / column / value columns (the last line is the matrix

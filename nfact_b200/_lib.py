@@ -42,6 +42,9 @@ SIGNATURES = {
     "nfb_nccl_init_rank": (c_int, [c_void_p, c_char_p, c_void_p, c_int, c_int]),
     "nfb_ingest_coo": (c_int, [c_void_p, c_int, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p),
                                POINTER(c_int64), POINTER(c_double), c_int64, c_int64, c_int, c_void_p, c_void_p]),
+    "nfb_ingest_coo_matrix": (c_int, [c_void_p, c_int, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p),
+                                      POINTER(c_int64), POINTER(c_double), c_int64, c_int64, c_int,
+                                      POINTER(c_void_p)]),
     "nfb_dot_count_lines": (c_int, [c_void_p, c_int64, c_int, POINTER(c_int64)]),
     "nfb_dot_parse": (c_int, [c_void_p, c_int64, c_int, c_int64, c_void_p, c_void_p, c_void_p]),
     "nfb_matrix_from_host": (c_int, [c_void_p, c_void_p, c_int64, c_int64, POINTER(c_void_p)]),

@@ -70,6 +70,7 @@ int ingest_scatter(const int* rows, const int* cols, const double* vals, int64_t
     scatter_add_kernel<<<blocks_for(nnz), 256, 0, stream>>>(rows, cols, vals, nnz, row0, nrows_blk, nrows_total,
                                                            ncols, tmp, oob_flag);
     NFB_CUDA(cudaGetLastError());
+    if (acc == nullptr) return 0;   // single subject: the caller finalises tmp * scale directly
     scatter_commit_kernel<<<blocks_for(nnz), 256, 0, stream>>>(rows, cols, nnz, row0, nrows_blk, ncols, scale, tmp,
                                                               acc);
     NFB_CUDA(cudaGetLastError());

@@ -115,7 +115,8 @@ int p2p_gather_wait(const P2pPeers& peers, int world, int rank, int epoch, int64
 
 // ---- ingest.cu ------------------------------------------------------------------------------------
 // phase A: tmp[r*ncols+c] += v for every triplet with row in [row0, row0+nrows_blk)  (fp64 atomics)
-// phase B: the first thread to exchange a non-zero tmp cell adds cell*scale to acc and leaves tmp zero.
+// phase B: the first thread to exchange a non-zero tmp cell adds cell*scale to acc and leaves tmp zero
+//          (skipped when acc == nullptr: single-subject ingest finalises tmp * scale itself).
 int ingest_scatter(const int* rows, const int* cols, const double* vals, int64_t nnz, int64_t row0,
                    int64_t nrows_blk, int64_t nrows_total, int64_t ncols, double scale, double* tmp, double* acc,
                    int* oob_flag, cudaStream_t stream);

@@ -1197,34 +1197,44 @@ int nfb_ingest_coo(nfb_handle* h, int n_subjects, const int32_t* const* rows_hos
     size_t free_b = 0, total_b = 0;
     NFB_CUDA(cudaMemGetInfo(&free_b, &total_b));
     const double budget = 0.6 * static_cast<double>(free_b) - 16.0 * static_cast<double>(max_nnz);
-    const double per_row = 20.0 * static_cast<double>(ncols);  // tmp + acc (fp64) + fp32 block
+    // group mode: scratch + accumulator (fp64) per cell; single subject: X = float32(scratch * scale) needs no
+    // accumulator (0 + d * scale == d * scale), so a C3-sized subject is ingested in one row block
+    const bool single = !group_mode;
+    const double per_row = ((single ? 8.0 : 16.0) + (x_out_dev == nullptr ? 4.0 : 0.0)) * static_cast<double>(ncols);
     NFB_CHECK(budget > per_row, "not enough device memory for ingest");
     const int64_t blk_rows = std::max<int64_t>(1, std::min<int64_t>(nrows, static_cast<int64_t>(budget / per_row)));
     DevBuf<double> tmp, acc, vals;
     DevBuf<int> rows, cols;
     DevBuf<float> xblk;
     NFB_TRY(tmp.alloc(static_cast<size_t>(blk_rows) * ncols, true, st));
-    NFB_TRY(acc.alloc(static_cast<size_t>(blk_rows) * ncols, false, st));
+    if (!single) NFB_TRY(acc.alloc(static_cast<size_t>(blk_rows) * ncols, false, st));
     if (x_out_dev == nullptr) NFB_TRY(xblk.alloc(static_cast<size_t>(blk_rows) * ncols, false, st));
     NFB_TRY(rows.alloc(max_nnz, false, st));
     NFB_TRY(cols.alloc(max_nnz, false, st));
     NFB_TRY(vals.alloc(max_nnz, false, st));
     NFB_CUDA(cudaMemsetAsync(h->d_int.p + 2, 0, sizeof(int), st));
     const double recip = 1.0 / static_cast<double>(n_subjects);
+    auto upload = [&](int s) -> int {
+        NFB_CUDA(cudaMemcpyAsync(rows.p, rows_host[s], sizeof(int) * nnz[s], cudaMemcpyHostToDevice, st));
+        NFB_CUDA(cudaMemcpyAsync(cols.p, cols_host[s], sizeof(int) * nnz[s], cudaMemcpyHostToDevice, st));
+        NFB_CUDA(cudaMemcpyAsync(vals.p, vals_host[s], sizeof(double) * nnz[s], cudaMemcpyHostToDevice, st));
+        return 0;
+    };
+    if (n_subjects == 1) NFB_TRY(upload(0));   // one subject: its triplets are uploaded once for all row blocks
     for (int64_t r0 = 0; r0 < nrows; r0 += blk_rows) {
         const int64_t nr = std::min(blk_rows, nrows - r0);
-        NFB_CUDA(cudaMemsetAsync(acc.p, 0, sizeof(double) * nr * ncols, st));
+        if (!single) NFB_CUDA(cudaMemsetAsync(acc.p, 0, sizeof(double) * nr * ncols, st));
+        if (r0 > 0 && single) NFB_CUDA(cudaMemsetAsync(tmp.p, 0, sizeof(double) * nr * ncols, st));
         for (int s = 0; s < n_subjects; ++s) {
-            NFB_CUDA(cudaMemcpyAsync(rows.p, rows_host[s], sizeof(int) * nnz[s], cudaMemcpyHostToDevice, st));
-            NFB_CUDA(cudaMemcpyAsync(cols.p, cols_host[s], sizeof(int) * nnz[s], cudaMemcpyHostToDevice, st));
-            NFB_CUDA(cudaMemcpyAsync(vals.p, vals_host[s], sizeof(double) * nnz[s], cudaMemcpyHostToDevice, st));
-            NFB_TRY(ingest_scatter(rows.p, cols.p, vals.p, nnz[s], r0, nr, nrows, ncols, scale[s], tmp.p, acc.p,
-                                   h->d_int.p + 2, st));
             // the staging buffers are reused by the next subject: pageable H2D copies are synchronous
             // with respect to the host, the kernels are ordered on the stream.
+            if (n_subjects > 1) NFB_TRY(upload(s));
+            NFB_TRY(ingest_scatter(rows.p, cols.p, vals.p, nnz[s], r0, nr, nrows, ncols, scale[s], tmp.p,
+                                   single ? nullptr : acc.p, h->d_int.p + 2, st));
         }
         float* dst = x_out_dev ? x_out_dev + r0 * ncols : xblk.p;
-        NFB_TRY(ingest_finalize(acc.p, nr * ncols, recip, group_mode ? 1 : 0, dst, st));
+        if (single) NFB_TRY(ingest_finalize(tmp.p, nr * ncols, scale[0], 1, dst, st));
+        else NFB_TRY(ingest_finalize(acc.p, nr * ncols, recip, group_mode ? 1 : 0, dst, st));
         if (x_out_host)
             NFB_CUDA(cudaMemcpyAsync(x_out_host + r0 * ncols, dst, sizeof(float) * nr * ncols, cudaMemcpyDeviceToHost,
                                      st));
@@ -1234,6 +1244,19 @@ int nfb_ingest_coo(nfb_handle* h, int n_subjects, const int32_t* const* rows_hos
     NFB_CUDA(cudaStreamSynchronize(st));
     NFB_CHECK(oob == 0, "row/column index exceeds matrix dimensions");
     return 0;
+}
+
+int nfb_ingest_coo_matrix(nfb_handle* h, int n_subjects, const int32_t* const* rows_host,
+                          const int32_t* const* cols_host, const double* const* vals_host, const int64_t* nnz,
+                          const double* scale, int64_t nrows, int64_t ncols, int group_mode, nfb_matrix** out) {
+    NFB_CHECK(h != nullptr && out != nullptr, "NULL argument");
+    NFB_CUDA(cudaSetDevice(h->device));
+    // the float32 matrix exists only on the device and only until its fp16 planes are built
+    DevBuf<float> dense;
+    NFB_TRY(dense.alloc(static_cast<size_t>(nrows) * ncols, false, h->stream));
+    NFB_TRY(nfb_ingest_coo(h, n_subjects, rows_host, cols_host, vals_host, nnz, scale, nrows, ncols, group_mode,
+                           nullptr, dense.p));
+    return nfb_matrix_from_device(h, dense.p, nrows, ncols, ncols, out);
 }
 
 int nfb_matrix_matmul(nfb_handle* h, const nfb_matrix* x, int trans, const float* b_dev, int64_t n_b,

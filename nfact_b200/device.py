@@ -223,20 +223,36 @@ class NmfState:
             pass
 
 
-def ingest_coo(subjects, nrows: int, ncols: int, group_mode: bool, handle: Handle | None = None) -> np.ndarray:
-    """subjects: list of (rows int32 0-based, cols int32 0-based, vals float64, scale float)."""
-    handle = handle or get_handle()
+def _coo_args(subjects):
     n = len(subjects)
     rows = [np.ascontiguousarray(s[0], dtype=np.int32) for s in subjects]
     cols = [np.ascontiguousarray(s[1], dtype=np.int32) for s in subjects]
     vals = [np.ascontiguousarray(s[2], dtype=np.float64) for s in subjects]
     arr_t = c_void_p * n
-    rows_p = arr_t(*[r.ctypes.data for r in rows])
-    cols_p = arr_t(*[c.ctypes.data for c in cols])
-    vals_p = arr_t(*[v.ctypes.data for v in vals])
-    nnz = (c_int64 * n)(*[len(r) for r in rows])
-    scale = (c_double * n)(*[float(s[3]) for s in subjects])
-    out = np.empty((nrows, ncols), dtype=np.float32)
+    keep = (rows, cols, vals)
+    return (n, arr_t(*[r.ctypes.data for r in rows]), arr_t(*[c.ctypes.data for c in cols]),
+            arr_t(*[v.ctypes.data for v in vals]), (c_int64 * n)(*[len(r) for r in rows]),
+            (c_double * n)(*[float(s[3]) for s in subjects]), keep)
+
+
+def ingest_coo(subjects, nrows: int, ncols: int, group_mode: bool, handle: Handle | None = None) -> np.ndarray:
+    """subjects: list of (rows int32 0-based, cols int32 0-based, vals float64, scale float)."""
+    handle = handle or get_handle()
+    n, rows_p, cols_p, vals_p, nnz, scale, _keep = _coo_args(subjects)
+    # page-locked when it is cheap to be (pinning tens of GB costs seconds and starves the host)
+    big = 4 * nrows * ncols > (2 << 30)
+    out = np.empty((nrows, ncols), dtype=np.float32) if big else _lib.pinned_empty((nrows, ncols), np.float32)
     check(handle.lib.nfb_ingest_coo(handle.ptr, n, rows_p, cols_p, vals_p, nnz, scale, nrows, ncols,
                                     1 if group_mode else 0, out.ctypes.data, None))
     return out
+
+
+def ingest_coo_resident(subjects, nrows: int, ncols: int, group_mode: bool,
+                        handle: Handle | None = None) -> DeviceMatrix:
+    """Same ingest, but the matrix stays in HBM as a ``DeviceMatrix`` (no dense round trip through the host)."""
+    handle = handle or get_handle()
+    n, rows_p, cols_p, vals_p, nnz, scale, _keep = _coo_args(subjects)
+    ptr = c_void_p()
+    check(handle.lib.nfb_ingest_coo_matrix(handle.ptr, n, rows_p, cols_p, vals_p, nnz, scale, nrows, ncols,
+                                           1 if group_mode else 0, byref(ptr)))
+    return DeviceMatrix(handle, ptr, (nrows, ncols))

@@ -78,10 +78,13 @@ def dual_regression_subject(fdt_path: str, components: dict, seeds: list, thresh
     try:
         matrix_file = next((os.path.join(fdt_path, fname) for fname in ("fdt_matrix2.dot.lz4", "fdt_matrix2.dot")
                             if os.path.exists(os.path.join(fdt_path, fname))), None)
-        matrix = load_fdt_matrix(matrix_file)
+        matrix = load_fdt_matrix(matrix_file, resident=True)     # stays in HBM: no dense host round trip
     except Exception:
         error_and_exit(False, f"Unable to load {os.path.basename(os.path.normpath(fdt_path))} fdt matrix")
-    dr_results = run_decomp(nmf_dual_regression, components, matrix, parallel)
+    try:
+        dr_results = run_decomp(nmf_dual_regression, components, matrix, parallel)
+    finally:
+        matrix.free()
     dr_results = thresholding_components(int(threshold), os.path.join(fdt_path, "coords_for_fdt_matrix2"), seeds,
                                          dr_results)
     if normalise:

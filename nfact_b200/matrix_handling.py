@@ -73,10 +73,14 @@ def load_single_matrix(matfile: str) -> CooMatrix:
     return CooMatrix(rows.astype(np.int32), cols.astype(np.int32), data, (nrows, ncols), 1e8 / waytotal)
 
 
-def load_fdt_matrix(matfile: str) -> np.ndarray:
-    """NFACT/base/matrix_handling.py:143-158: dense float32 [m, n]."""
+def load_fdt_matrix(matfile: str, resident: bool = False):
+    """NFACT/base/matrix_handling.py:143-158: dense float32 [m, n].
+
+    ``resident=True`` keeps the matrix in HBM and returns a ``DeviceMatrix`` (what ``nmf_decomp`` /
+    ``nmf_dual_regression`` take directly) instead of copying 4mn bytes to the host and back."""
     coo = load_single_matrix(matfile)
-    return device.ingest_coo([(coo.rows, coo.cols, coo.data, coo.scale)], coo.shape[0], coo.shape[1], False)
+    ingest = device.ingest_coo_resident if resident else device.ingest_coo
+    return ingest([(coo.rows, coo.cols, coo.data, coo.scale)], coo.shape[0], coo.shape[1], False)
 
 
 def avg_fdt(list_of_matfiles: list) -> np.ndarray:

@@ -69,3 +69,19 @@ def test_empty_matrix_and_errors(tmp_path):
         nfact_b200.load_fdt_matrix(str(folder / "fdt_matrix2.dot"))
     with pytest.raises(SystemExit):                                   # reference: error_and_exit -> exit(1)
         nfact_b200.process_fdt_matrix2([str(folder)], False)
+
+
+def test_resident_ingest_feeds_the_solvers(golden, golden_subjects):
+    """load_fdt_matrix(resident=True): the matrix never leaves HBM; the dual regression on it equals the
+    one on the host copy bit for bit (same planes, same kernels)."""
+    import nfact_b200
+    from nfact_b200.device import DeviceMatrix
+    xres = nfact_b200.load_fdt_matrix(golden_subjects[0], resident=True)
+    assert isinstance(xres, DeviceMatrix) and xres.shape == golden["ingest_single_1"].shape
+    assert abs(xres.sumsq - float((golden["ingest_single_1"].astype(np.float64) ** 2).sum())) <= 1e-9 * xres.sumsq
+    comps = {"grey_components": golden["cd_fit_W"].astype(np.float64)}
+    a = nfact_b200.nmf_dual_regression(comps, xres)
+    b = nfact_b200.nmf_dual_regression(comps, golden["ingest_single_1"])
+    xres.free()
+    assert np.array_equal(a["white_components"], b["white_components"])
+    assert np.array_equal(a["grey_components"], b["grey_components"])
