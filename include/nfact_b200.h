@@ -145,6 +145,15 @@ int nfb_profile_gemms(nfb_handle* h, int enable, double* total_ms_out, int64_t* 
 int nfb_dual_regression_host(nfb_handle* h, const nfb_matrix* x, int k, const void* g_host, int g_is_f32,
                              double* gs_out, double* hs_out, int* n_unconverged_out, int* g_nonfinite_out);
 
+/* ---- NMF-sso similarity --------------------------------------------------------------------------------
+ * replaces  NFACT/decomp/decomposition/sso/sso_functions.py:29-68  compute_similairty_matrix:
+ * np.corrcoef of the (row-normalised) stacked white-matter components of all NMF-sso runs -- (N k)^2 n
+ * multiply-adds, 3.5 TFLOP at C3 -- as one pass of the split-precision GEMM over the standardised rows.
+ *   rows_host [r, n] float32;  sim_out_host [r, r] float32 Pearson correlations (unclipped);
+ *   dead_out_host [r] (nullable): 1 for a constant row (np.corrcoef gives NaN there; here its row/column is 0). */
+int nfb_row_correlation_host(nfb_handle* h, const float* rows_host, int64_t r, int64_t n, float* sim_out_host,
+                             int32_t* dead_out_host);
+
 /* ---- page-locked host buffers ------------------------------------------------------------------------
  * Result arrays are hundreds of MB; device-to-host copies into pageable memory run at a few GB/s, into
  * page-locked memory at PCIe speed.  The host layer allocates the arrays it returns (W, H, DR outputs)

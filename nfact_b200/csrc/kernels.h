@@ -78,6 +78,9 @@ int gram_f64(const float* f, int64_t k, int64_t cols, int64_t ld, double* gram64
 // out32[t][j] = (float) in64[t][j]; rowmax_bits as in mu_update
 int f64_to_f32_rowmax(const double* in, int64_t k, int64_t cols, int64_t ld_in, float* out, int64_t ld_out,
                       unsigned int* rowmax_bits, cudaStream_t stream);
+// z[r][:] = (x[r][:] - mean_r) / ||x[r][:] - mean_r||  (fp64 statistics); dead[r] = 1 for a constant row (z = 0)
+int rows_standardize(const float* x, int64_t rows, int64_t cols, int64_t ld, float* z, int64_t ldz, int* dead,
+                     cudaStream_t stream);
 // *out += sum_{t,u<k} a[t][u] * b[t][u]
 int dot_small(const float* a, const float* b, int64_t k, int64_t ld, double* out, cudaStream_t stream);
 // transpose [rows, cols] (ld_in) -> [cols, rows] (ld_out); *nonfinite (nullable) is set to 1 when an input

@@ -1288,6 +1288,34 @@ int nfb_matrix_matmul(nfb_handle* h, const nfb_matrix* x, int trans, const float
     return 0;
 }
 
+// ---- NMF-sso similarity ------------------------------------------------------------------------------
+int nfb_row_correlation_host(nfb_handle* h, const float* rows_host, int64_t r, int64_t n, float* sim_out_host,
+                             int32_t* dead_out_host) {
+    NFB_CHECK(h != nullptr && rows_host != nullptr && sim_out_host != nullptr, "NULL argument");
+    NFB_CHECK(r >= 1 && n >= 2, "need at least one row and two columns");
+    NFB_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    DevBuf<float> raw, z, sim;
+    DevBuf<int> dead;
+    NFB_TRY(raw.alloc(static_cast<size_t>(r) * n, false, st));
+    NFB_TRY(z.alloc(static_cast<size_t>(r) * n, false, st));
+    NFB_TRY(sim.alloc(static_cast<size_t>(r) * r, false, st));
+    NFB_TRY(dead.alloc(r, true, st));
+    NFB_CUDA(cudaMemcpyAsync(raw.p, rows_host, sizeof(float) * r * n, cudaMemcpyHostToDevice, st));
+    NFB_TRY(rows_standardize(raw.p, r, n, n, z.p, n, dead.p, st));
+    raw.release();
+    // corr = Z Z': Z as the resident "matrix" (K-major read), 512 rows of Z at a time as the factor operand
+    nfb_matrix* zmat = nullptr;
+    NFB_TRY(nfb_matrix_from_device(h, z.p, r, n, n, &zmat));
+    std::unique_ptr<nfb_matrix> guard(zmat);
+    NFB_TRY(nfb_matrix_matmul(h, zmat, 0, z.p, r, sim.p, r));
+    NFB_CUDA(cudaMemcpyAsync(sim_out_host, sim.p, sizeof(float) * r * r, cudaMemcpyDeviceToHost, st));
+    if (dead_out_host)
+        NFB_CUDA(cudaMemcpyAsync(dead_out_host, dead.p, sizeof(int) * r, cudaMemcpyDeviceToHost, st));
+    NFB_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
 // ---- test hook --------------------------------------------------------------------------------------
 int nfb_test_gemm(nfb_handle* h, const float* a_dev, int64_t a_rows, int64_t a_cols, int a_is_transposed,
                   const float* b_dev, int64_t n_b, float* out_dev, int64_t ld_out, int cta_group, int splits) {

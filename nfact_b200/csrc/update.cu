@@ -183,6 +183,37 @@ __global__ void f64_to_f32_rowmax_kernel(const double* __restrict__ in, int64_t 
     if ((threadIdx.x & 31) == 0 && vmax > 0.0f) atomicMax(&rowmax_bits[t], __float_as_uint(vmax));
 }
 
+// z[r][:] = (x[r][:] - mean_r) / ||x[r][:] - mean_r||_2   (fp64 statistics; a constant row becomes all zeros and
+// sets dead[r] = 1).  One CTA per row.
+__global__ void __launch_bounds__(256)
+rows_standardize_kernel(const float* __restrict__ x, int64_t cols, int64_t ld, float* __restrict__ z,
+                        int64_t ldz, int* __restrict__ dead) {
+    __shared__ double scratch[32];
+    __shared__ double stat[2];
+    const int64_t r = blockIdx.x;
+    const float* row = x + r * ld;
+    double sum = 0.0;
+    for (int64_t j = threadIdx.x; j < cols; j += blockDim.x) sum += static_cast<double>(row[j]);
+    sum = block_sum(sum, scratch);
+    if (threadIdx.x == 0) stat[0] = sum / static_cast<double>(cols);
+    __syncthreads();
+    const double mean = stat[0];
+    double ss = 0.0;
+    for (int64_t j = threadIdx.x; j < cols; j += blockDim.x) {
+        const double d = static_cast<double>(row[j]) - mean;
+        ss = fma(d, d, ss);
+    }
+    ss = block_sum(ss, scratch);
+    if (threadIdx.x == 0) {
+        stat[1] = ss > 0.0 ? 1.0 / sqrt(ss) : 0.0;
+        dead[r] = ss > 0.0 ? 0 : 1;
+    }
+    __syncthreads();
+    const double inv = stat[1];
+    for (int64_t j = threadIdx.x; j < cols; j += blockDim.x)
+        z[r * ldz + j] = static_cast<float>((static_cast<double>(row[j]) - mean) * inv);
+}
+
 int col_blocks(int64_t cols, int per_block, int cap) {
     return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(ceil_div64(cols, per_block), cap)));
 }
@@ -251,6 +282,14 @@ int f64_to_f32_rowmax(const double* in, int64_t k, int64_t cols, int64_t ld_in, 
     if (k * cols == 0) return 0;
     f64_to_f32_rowmax_kernel<<<dim3(col_blocks(cols, 256, 1024), static_cast<unsigned>(k)), 256, 0, stream>>>(
         in, cols, ld_in, out, ld_out, rowmax_bits);
+    NFB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int rows_standardize(const float* x, int64_t rows, int64_t cols, int64_t ld, float* z, int64_t ldz, int* dead,
+                     cudaStream_t stream) {
+    if (rows * cols == 0) return 0;
+    rows_standardize_kernel<<<static_cast<unsigned>(rows), 256, 0, stream>>>(x, cols, ld, z, ldz, dead);
     NFB_CUDA(cudaGetLastError());
     return 0;
 }

@@ -27,16 +27,32 @@ def rownorm(nmf_mat: np.ndarray) -> np.ndarray:
     return nmf_mat / norms
 
 
-def compute_similairty_matrix(components: np.ndarray) -> np.ndarray:
-    """sso_functions.py:49-68: correlation between the row-normalised components, clipped to [0, 1]."""
-    with np.errstate(invalid="ignore", divide="ignore"):
-        sim = np.corrcoef(rownorm(components))
+def compute_similairty_matrix(components: np.ndarray, handle=None) -> np.ndarray:
+    """sso_functions.py:49-68: correlation between the row-normalised components, clipped to [0, 1].
+
+    The (N k)^2 n product runs on the device (``nfb_row_correlation_host``: rows standardised with float64
+    statistics, then one split-precision GEMM pass); Pearson correlation is invariant to the row
+    normalisation the reference applies first, so ``rownorm`` is not needed.  float64 out like np.corrcoef."""
+    from ctypes import c_void_p
+    from . import _lib
+    from .device import get_handle
+    handle = handle or get_handle()
+    comps = np.ascontiguousarray(components, dtype=np.float32)
+    if comps.ndim != 2:
+        raise ValueError("expected a 2-D stack of components")
+    r, n = comps.shape
+    sim32 = np.empty((r, r), dtype=np.float32)
+    dead = np.zeros(r, dtype=np.int32)
+    _lib.check(handle.lib.nfb_row_correlation_host(handle.ptr, c_void_p(comps.ctypes.data), r, n,
+                                                   c_void_p(sim32.ctypes.data), c_void_p(dead.ctypes.data)))
+    sim = sim32.astype(np.float64)
+    sim = 0.5 * (sim + sim.T)                 # the two triangles come from different tile passes
     # A component that a run drove to all-zero has no variance: corrcoef gives NaN there and scipy's
     # linkage rejects the matrix (the reference crashes).  Treat it as dissimilar to everything.
-    dead = ~np.isfinite(sim)
     if dead.any():
-        sim[dead] = 0.0
-        np.fill_diagonal(sim, 1.0)
+        sim[dead.astype(bool), :] = 0.0
+        sim[:, dead.astype(bool)] = 0.0
+    np.fill_diagonal(sim, 1.0)
     np.clip(sim, 0, 1, out=sim)
     return sim
 

@@ -204,3 +204,22 @@ def test_more_than_256_components(solver):
     W, H = st.get_factors()
     assert rel_fro(W, rec[-1][1]) < MU_TOL
     assert rel_fro(H, rec[-1][2]) < MU_TOL
+
+
+def test_sso_similarity_matrix_matches_corrcoef():
+    """compute_similairty_matrix (sso_functions.py:49-68) on the device vs np.corrcoef(rownorm(.)) in float64:
+    ragged sizes (rows not a multiple of the 512-row factor tile is covered by r = 700), a dead component."""
+    from nfact_b200.nmfsso import compute_similairty_matrix, rownorm
+    rng = np.random.default_rng(12)
+    for r, n in ((37, 501), (700, 3001)):
+        comps = (rng.gamma(0.4, 1.0, (r, n)) * (rng.random((r, n)) < 0.3)).astype(np.float32)
+        comps[5] = 0.0                                        # a component a run drove to all-zero
+        sim = compute_similairty_matrix(comps)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            ref = np.corrcoef(rownorm(comps.astype(np.float64)))
+        ref[~np.isfinite(ref)] = 0.0
+        np.fill_diagonal(ref, 1.0)
+        np.clip(ref, 0, 1, out=ref)
+        assert sim.shape == (r, r) and sim.dtype == np.float64
+        assert np.abs(sim - ref).max() < 5e-6
+        assert np.array_equal(sim, sim.T) and (np.diag(sim) == 1.0).all()
