@@ -71,6 +71,12 @@ int nfb_ingest_coo_matrix(nfb_handle* h, int n_subjects, const int32_t* const* r
 int nfb_dot_count_lines(const char* buf, int64_t len, int nthreads, int64_t* n_lines_out);
 int nfb_dot_parse(const char* buf, int64_t len, int nthreads, int64_t n_lines, double* rows, double* cols,
                   double* vals);
+/* The same parse fused with what load_single_matrix does next (NFACT/base/matrix_handling.py:131-137): the
+ * first n_lines - 1 lines become 0-based int32 rows0 / cols0 and float64 vals -- exactly the arrays
+ * nfb_ingest_coo takes, so they can live in page-locked memory (nfb_host_alloc) -- and the last line becomes
+ * shape_out[2] = (nrows, ncols).  Index errors carry scipy's messages ("row index exceeds matrix dimensions" ...). */
+int nfb_dot_parse_coo(const char* buf, int64_t len, int nthreads, int64_t n_lines, int32_t* rows0, int32_t* cols0,
+                      double* vals, int64_t* shape_out);
 
 /* ---- resident matrix --------------------------------------------------------------------------
  * X float32 [m, n] -> fp16 hi/lo planes in HBM (4 B/element, read by both X H' and W'X). */

@@ -62,6 +62,53 @@ int64_t parse_range(const char* begin, const char* end, int64_t first, double* r
     return idx - first;
 }
 
+// same lines, but straight into what the ingest kernels take: 0-based int32 row / column (the reference's
+// `rows - 1`, truncated like its integer cast) and the float64 value; line `last` (the final line of the file)
+// is the matrix shape and goes to shape[3] instead.  Tracks the index range for the bounds check.
+struct CooStats {
+    int64_t parsed = 0;
+    double rmin = 1e300, rmax = -1e300, cmin = 1e300, cmax = -1e300;
+    bool bad_index = false;
+};
+
+CooStats parse_range_coo(const char* begin, const char* end, int64_t first, int64_t last, int32_t* rows,
+                         int32_t* cols, double* vals, double* shape) {
+    CooStats st;
+    int64_t idx = first;
+    const char* p = begin;
+    while (p < end) {
+        while (p < end && (is_blank(*p) || *p == '\n')) ++p;
+        if (p >= end) break;
+        double field[3];
+        for (int f = 0; f < 3; ++f) {
+            while (p < end && is_blank(*p)) ++p;
+            if (p < end && *p == '+') ++p;
+            auto res = std::from_chars(p, end, field[f]);
+            if (res.ec != std::errc()) { st.parsed = -1; return st; }
+            p = res.ptr;
+        }
+        while (p < end && is_blank(*p)) ++p;
+        if (p < end && *p != '\n') { st.parsed = -1; return st; }
+        if (idx == last) {
+            shape[0] = field[0]; shape[1] = field[1]; shape[2] = field[2];
+        } else {
+            const double r = field[0] - 1.0, c = field[1] - 1.0;
+            // NaN or beyond int32: reported as a bad index (the reference fails inside scipy's index cast)
+            if (!(r > -2147483648.0 && r < 2147483648.0 && c > -2147483648.0 && c < 2147483648.0)) st.bad_index = true;
+            else {
+                rows[idx] = static_cast<int32_t>(r);
+                cols[idx] = static_cast<int32_t>(c);
+            }
+            vals[idx] = field[2];
+            st.rmin = std::min(st.rmin, r); st.rmax = std::max(st.rmax, r);
+            st.cmin = std::min(st.cmin, c); st.cmax = std::max(st.cmax, c);
+        }
+        ++idx;
+    }
+    st.parsed = idx - first;
+    return st;
+}
+
 std::vector<const char*> chunk_starts(const char* buf, int64_t len, int nthreads) {
     std::vector<const char*> starts;
     starts.push_back(buf);
@@ -136,6 +183,62 @@ int nfb_dot_parse(const char* buf, int64_t len, int nthreads, int64_t n_lines, d
             nfb::set_error("could not convert string to float: malformed line in fdt_matrix2.dot (expected 3 columns)");
             return 2;
         }
+    return 0;
+}
+
+int nfb_dot_parse_coo(const char* buf, int64_t len, int nthreads, int64_t n_lines, int32_t* rows0, int32_t* cols0,
+                      double* vals, int64_t* shape_out) {
+    if (buf == nullptr || shape_out == nullptr || len < 0 || n_lines < 1 ||
+        (n_lines > 1 && (rows0 == nullptr || cols0 == nullptr || vals == nullptr))) {
+        nfb::set_error("nfb_dot_parse_coo: bad arguments");
+        return 2;
+    }
+    nthreads = pick_threads(len, nthreads);
+    auto starts = chunk_starts(buf, len, nthreads);
+    const size_t nchunks = starts.size() - 1;
+    std::vector<int64_t> counts(nchunks, 0);
+    {
+        std::vector<std::thread> pool;
+        for (size_t c = 0; c < nchunks; ++c)
+            pool.emplace_back([&, c] { counts[c] = count_lines(starts[c], starts[c + 1]); });
+        for (auto& th : pool) th.join();
+    }
+    std::vector<int64_t> first(nchunks + 1, 0);
+    for (size_t c = 0; c < nchunks; ++c) first[c + 1] = first[c] + counts[c];
+    if (first[nchunks] != n_lines) {
+        nfb::set_error("nfb_dot_parse_coo: line count changed between the two passes");
+        return 2;
+    }
+    double shape[3] = {0.0, 0.0, 0.0};
+    std::vector<CooStats> stats(nchunks);
+    {
+        std::vector<std::thread> pool;
+        for (size_t c = 0; c < nchunks; ++c)
+            pool.emplace_back([&, c] {
+                stats[c] = parse_range_coo(starts[c], starts[c + 1], first[c], n_lines - 1, rows0, cols0, vals, shape);
+            });
+        for (auto& th : pool) th.join();
+    }
+    CooStats all;
+    for (size_t c = 0; c < nchunks; ++c) {
+        if (stats[c].parsed != counts[c]) {
+            nfb::set_error("could not convert string to float: malformed line in fdt_matrix2.dot (expected 3 columns)");
+            return 2;
+        }
+        all.bad_index |= stats[c].bad_index;
+        all.rmin = std::min(all.rmin, stats[c].rmin); all.rmax = std::max(all.rmax, stats[c].rmax);
+        all.cmin = std::min(all.cmin, stats[c].cmin); all.cmax = std::max(all.cmax, stats[c].cmax);
+    }
+    const int64_t nrows = static_cast<int64_t>(shape[0]), ncols = static_cast<int64_t>(shape[1]);
+    shape_out[0] = nrows;
+    shape_out[1] = ncols;
+    if (n_lines > 1) {   // the messages scipy's coo/csc constructor raises
+        if (all.bad_index) { nfb::set_error("row / column index is not a 32-bit integer"); return 2; }
+        if (all.rmin <= -1.0) { nfb::set_error("negative row index found"); return 2; }
+        if (all.cmin <= -1.0) { nfb::set_error("negative column index found"); return 2; }
+        if (static_cast<int64_t>(all.rmax) >= nrows) { nfb::set_error("row index exceeds matrix dimensions"); return 2; }
+        if (static_cast<int64_t>(all.cmax) >= ncols) { nfb::set_error("column index exceeds matrix dimensions"); return 2; }
+    }
     return 0;
 }
 

@@ -54,23 +54,45 @@ def parse_dot_bytes(raw: bytes, name: str = "<buffer>") -> np.ndarray:
     return cols3
 
 
-def load_single_matrix(matfile: str) -> CooMatrix:
+def parse_dot_coo(raw: bytes, name: str = "<buffer>", pinned: bool = False):
+    """One native pass from the file's bytes to the ingest kernels' input (``nfb_dot_parse_coo``): 0-based int32
+    rows / cols and float64 values of all lines but the last, and the (nrows, ncols) the last line states.
+    ``pinned`` puts the three arrays in page-locked memory so their upload runs at PCIe speed."""
+    import ctypes
+    from . import _lib
+    lib = _lib.load()
+    buf = ctypes.c_char_p(raw)
+    n_lines = ctypes.c_int64()
+    _lib.check(lib.nfb_dot_count_lines(buf, len(raw), 0, ctypes.byref(n_lines)))
+    if n_lines.value == 0:
+        raise ValueError(f"{name}: file is empty")
+    nnz = n_lines.value - 1
+    alloc = _lib.pinned_empty if pinned else (lambda shape, dtype: np.empty(shape, dtype=dtype))
+    rows, cols, vals = alloc((nnz,), np.int32), alloc((nnz,), np.int32), alloc((nnz,), np.float64)
+    shape = (ctypes.c_int64 * 2)()
+    try:
+        _lib.check(lib.nfb_dot_parse_coo(buf, len(raw), 0, n_lines.value, rows.ctypes.data, cols.ctypes.data,
+                                         vals.ctypes.data, shape))
+    except _lib.NfbError as e:
+        raise ValueError(f"{e}") from None
+    return rows, cols, vals, (int(shape[0]), int(shape[1]))
+
+
+def load_single_matrix(matfile: str, pinned: bool = False) -> CooMatrix:
     """NFACT/base/matrix_handling.py:116-140.  Returns the COO triplets (0-based) plus the
     ``1e8 / waytotal`` scale; the sparse-matrix arithmetic itself happens on the device."""
-    col_r, col_c, col_v = parse_dot_bytes(_read_bytes(matfile), matfile)   # column-wise: no [T,3] copy
-    data = np.ascontiguousarray(col_v[:-1])
-    rows = np.array(col_r[:-1] - 1, dtype=np.int64)
-    cols = np.array(col_c[:-1] - 1, dtype=np.int64)
-    nrows = int(col_r[-1])
-    ncols = int(col_c[-1])
-    if rows.size and (rows.min() < 0 or cols.min() < 0):
-        raise ValueError("negative row index found" if rows.min() < 0 else "negative column index found")
-    if rows.size and rows.max() >= nrows:
-        raise ValueError("row index exceeds matrix dimensions")
-    if cols.size and cols.max() >= ncols:
-        raise ValueError("column index exceeds matrix dimensions")
+    rows, cols, data, shape = parse_dot_coo(_read_bytes(matfile), matfile, pinned)
     waytotal = float(np.loadtxt(os.path.join(os.path.dirname(matfile), "waytotal")))
-    return CooMatrix(rows.astype(np.int32), cols.astype(np.int32), data, (nrows, ncols), 1e8 / waytotal)
+    return CooMatrix(rows, cols, data, shape, 1e8 / waytotal)
+
+
+def _cuda_ready() -> bool:
+    """Page-locked staging needs a CUDA context; the parser alone also runs on a box without a GPU."""
+    try:
+        device.get_handle()
+        return True
+    except Exception:
+        return False
 
 
 def load_fdt_matrix(matfile: str, resident: bool = False):
@@ -78,7 +100,7 @@ def load_fdt_matrix(matfile: str, resident: bool = False):
 
     ``resident=True`` keeps the matrix in HBM and returns a ``DeviceMatrix`` (what ``nmf_decomp`` /
     ``nmf_dual_regression`` take directly) instead of copying 4mn bytes to the host and back."""
-    coo = load_single_matrix(matfile)
+    coo = load_single_matrix(matfile, pinned=_cuda_ready())
     ingest = device.ingest_coo_resident if resident else device.ingest_coo
     return ingest([(coo.rows, coo.cols, coo.data, coo.scale)], coo.shape[0], coo.shape[1], False)
 

@@ -117,3 +117,41 @@ def test_native_dot_parser_matches_loadtxt(tmp_path):
     bad.write_text("")
     with pytest.raises(ValueError):
         nfact_b200.read_in_matrix(str(bad))
+
+
+def test_fused_coo_parser_matches_the_reference_construction(tmp_path, golden_subjects):
+    """nfb_dot_parse_coo == loadtxt + `[:-1] - 1` + integer cast + last-line shape
+    (NFACT/base/matrix_handling.py:131-137), with scipy's index errors."""
+    import nfact_b200
+    from nfact_b200.matrix_handling import parse_dot_coo
+    for path in golden_subjects:
+        ref = np.loadtxt(path)
+        rows, cols, vals, shape = parse_dot_coo(open(path, "rb").read(), path)
+        assert rows.dtype == np.int32 and cols.dtype == np.int32 and vals.dtype == np.float64
+        assert np.array_equal(rows, (ref[:-1, 0] - 1).astype(np.int64))
+        assert np.array_equal(cols, (ref[:-1, 1] - 1).astype(np.int64))
+        assert np.array_equal(vals, ref[:-1, 2])
+        assert shape == (int(ref[-1, 0]), int(ref[-1, 1]))
+    rng = np.random.default_rng(1)
+    big = tmp_path / "sub" / "fdt_matrix2.dot"
+    big.parent.mkdir()
+    r = rng.integers(1, 4001, 250000)
+    c = rng.integers(1, 9001, 250000)
+    v = rng.uniform(0, 1e5, 250000)
+    with open(big, "w") as fh:
+        for a, b, x in zip(r, c, v):
+            fh.write(f"{a}  {b}  {float(x)!r}\n")
+        fh.write("4000  9000  0\n")
+    (big.parent / "waytotal").write_text("12500000\n")
+    coo = nfact_b200.load_single_matrix(str(big))
+    assert coo.shape == (4000, 9000) and coo.scale == 1e8 / 12500000.0
+    assert np.array_equal(coo.rows, r - 1) and np.array_equal(coo.cols, c - 1) and np.array_equal(coo.data, v)
+    only_shape = tmp_path / "empty.dot"
+    only_shape.write_text("7 9 0\n")
+    rows, cols, vals, shape = parse_dot_coo(only_shape.read_bytes())
+    assert rows.size == 0 and shape == (7, 9)
+    for text, msg in (("0 1 5\n3 3 0\n", "negative row"), ("1 0 5\n3 3 0\n", "negative column"),
+                      ("4 1 5\n3 3 0\n", "row index exceeds"), ("1 4 5\n3 3 0\n", "column index exceeds"),
+                      ("1 2\n3 3 0\n", "could not convert"), ("1 2 3 4\n3 3 0\n", "could not convert")):
+        with pytest.raises(ValueError, match=msg):
+            parse_dot_coo(text.encode())
