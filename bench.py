@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=os.environ.get("NFB_BENCH_WORKLOAD", "C3"), choices=sorted(WORKLOADS))
     ap.add_argument("--solver", default="cd", choices=["cd", "mu"])
+    ap.add_argument("--shape", default="", help="m,n,k[,density]: ad-hoc workload for experiments (overrides --workload)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-dr", action="store_true", help="skip the dual-regression subject after the e2e solve")
@@ -401,9 +402,10 @@ def run_ours(args):
                 from nfact_b200.device import ingest_coo_resident
                 xd = torch.from_numpy(x_np).to(dev)
                 idx = xd.nonzero()
-                coo_rows = idx[:, 0].to(torch.int32).cpu().numpy()
-                coo_cols = idx[:, 1].to(torch.int32).cpu().numpy()
-                coo_vals = xd[idx[:, 0], idx[:, 1]].to(torch.float64).cpu().numpy()
+                # page-locked like the arrays the product's own loader (parse_dot_coo(pinned=True)) produces
+                coo_rows = idx[:, 0].to(torch.int32).cpu().pin_memory().numpy()
+                coo_cols = idx[:, 1].to(torch.int32).cpu().pin_memory().numpy()
+                coo_vals = xd[idx[:, 0], idx[:, 1]].to(torch.float64).cpu().pin_memory().numpy()
                 del xd, idx
                 torch.cuda.empty_cache()
                 del dr
@@ -484,6 +486,10 @@ def run_ours(args):
 
 def main():
     args = parse_args()
+    if args.shape:
+        parts = args.shape.split(",")
+        WORKLOADS["custom"] = (int(parts[0]), int(parts[1]), int(parts[2]), float(parts[3]) if len(parts) > 3 else 0.05)
+        args.workload = "custom"
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -4,13 +4,10 @@
 //     grad = -XHt[i,t] + sum_r HHt[t,r] W[i,r]                       (k FMAs per coordinate, k^2 per sample)
 //     pg = W[i,t] == 0 ? min(0, grad) : grad ;  violation += |pg|
 //     W[i,t] = max(W[i,t] - grad / HHt[t,t], 0)
-// Samples are independent; components are Gauss-Seidel.  Here one WARP owns one sample (= one column j of
-// the component-major factor F [k, cols]) and keeps the whole gradient vector g = G F[:,j] - num[:,j]
-// in registers (k/32 values per lane).  g starts from the tensor-core product G.F (the same "denominator"
-// GEMM the multiplicative update uses) and is kept current with a rank-1 update g += delta * G[t,:]
-// only when coordinate t actually moves -- a coordinate that stays at zero costs O(1), so the sparse factors
-// NFACT's L1 penalty produces are swept in ~k*nnz instead of k^2 operations, with the Gauss-Seidel
-// order of the reference kept exactly.
+// Samples are independent; components are Gauss-Seidel.  The gradient g = G F[:,j] - num[:,j] of every sample
+// starts from the tensor-core product G.F (the same "denominator" GEMM the multiplicative update uses) and is
+// kept current incrementally, so a sweep costs k^2 / 2 FMAs per sample instead of k^2, in the exact
+// Gauss-Seidel order of the reference.
 #include <algorithm>
 #include <cstdlib>
 #include <type_traits>
@@ -20,215 +17,6 @@
 
 namespace nfb {
 namespace {
-
-constexpr int kTileCols = 32;
-constexpr int kWarps = 8;
-
-template <int KPL>  // components per lane: k <= 32 * KPL
-__global__ void __launch_bounds__(kWarps * 32)
-cd_sweep_warp_kernel(float* __restrict__ f, int k, int64_t cols, int64_t ld, const float* __restrict__ num,
-                     int num_splits, int64_t num_stride, const float* __restrict__ den, int64_t ld_part,
-                     const float* __restrict__ gram, int ldg, float l1, float l2, double* __restrict__ violation,
-                     unsigned int* __restrict__ rowmax_bits) {
-    extern __shared__ float sm[];
-    __shared__ double scratch[32];
-    const int kpad = k | 1;  // odd row length -> conflict-free transposed access
-    float* g_s = sm;                              // [kTileCols][kpad] gradient
-    float* f_s = sm + kTileCols * kpad;           // [kTileCols][kpad] factor values
-    unsigned int* max_s = reinterpret_cast<unsigned int*>(sm + 2 * kTileCols * kpad);  // [k]
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int u = threadIdx.x; u < k; u += blockDim.x) max_s[u] = 0u;
-    float viol = 0.0f;
-    const int64_t ntiles = (cols + kTileCols - 1) / kTileCols;
-
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int64_t j0 = tile * kTileCols;
-        const int64_t j = j0 + lane;
-        const bool active = j < cols;
-        __syncthreads();
-        // ---- phase 1: coalesced loads (row u, 32 consecutive columns), transposed into smem -----------
-        for (int u = warp; u < k; u += kWarps) {
-            float fv = 0.0f, gv = 0.0f;
-            if (active) {
-                fv = f[static_cast<int64_t>(u) * ld + j];
-                float nv = 0.0f;
-                for (int s = 0; s < num_splits; ++s) nv += num[s * num_stride + static_cast<int64_t>(u) * ld_part + j];
-                const float dv = den[static_cast<int64_t>(u) * ld_part + j];
-                gv = fmaf(l2, fv, dv) - (nv - l1);
-            }
-            g_s[lane * kpad + u] = gv;
-            f_s[lane * kpad + u] = fv;
-        }
-        __syncthreads();
-        // ---- phase 2: one warp per column, components in order -----------------------------------------
-        for (int jj = warp; jj < kTileCols; jj += kWarps) {
-            if (j0 + jj >= cols) break;
-            float g[KPL], fv[KPL];
-#pragma unroll
-            for (int i = 0; i < KPL; ++i) {
-                const int u = lane + 32 * i;
-                g[i] = u < k ? g_s[jj * kpad + u] : 0.0f;
-                fv[i] = u < k ? f_s[jj * kpad + u] : 0.0f;
-            }
-            for (int t = 0; t < k; ++t) {
-                const int owner = t & 31, slot = t >> 5;
-                float gt = 0.0f, ft = 0.0f;
-#pragma unroll
-                for (int i = 0; i < KPL; ++i)
-                    if (i == slot) { gt = g[i]; ft = fv[i]; }
-                gt = __shfl_sync(0xffffffffu, gt, owner);
-                ft = __shfl_sync(0xffffffffu, ft, owner);
-                const float* grow = gram + static_cast<int64_t>(t) * ldg;
-                const float hess = __ldg(grow + t) + l2;
-                const float pg = (ft == 0.0f) ? fminf(0.0f, gt) : gt;
-                viol += fabsf(pg);
-                if (hess != 0.0f) {
-                    const float fn = fmaxf(ft - gt / hess, 0.0f);
-                    const float delta = fn - ft;
-                    if (delta != 0.0f) {  // warp-uniform
-#pragma unroll
-                        for (int i = 0; i < KPL; ++i) {
-                            const int u = lane + 32 * i;
-                            // components below t are final for this sweep; skip their chunks
-                            if (32 * i + 31 >= t && u < k) g[i] = fmaf(delta, __ldg(grow + u), g[i]);
-                            if (i == slot && lane == owner) fv[i] = fn;
-                        }
-                    }
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < KPL; ++i) {
-                const int u = lane + 32 * i;
-                if (u < k) f_s[jj * kpad + u] = fv[i];
-            }
-        }
-        __syncthreads();
-        // ---- phase 3: coalesced store + per-row maxima -------------------------------------------------
-        for (int u = warp; u < k; u += kWarps) {
-            const float v = active ? f_s[lane * kpad + u] : 0.0f;
-            if (active) f[static_cast<int64_t>(u) * ld + j] = v;
-            const float m = warp_max(v);
-            if (lane == 0 && m > 0.0f) atomicMax(&max_s[u], __float_as_uint(m));
-        }
-    }
-    __syncthreads();
-    for (int u = threadIdx.x; u < k; u += blockDim.x)
-        if (max_s[u] != 0u) atomicMax(&rowmax_bits[u], max_s[u]);
-    // every lane of a warp accumulated the same violation; count it once per warp
-    const double total = block_sum(lane == 0 ? static_cast<double>(viol) : 0.0, scratch);
-    if (threadIdx.x == 0 && total != 0.0) atomicAdd(violation, total);
-}
-
-
-// ---- fast path: Gram matrix resident in shared memory (k <= ~216) ----------------------------------
-// One CTA per SM, 16 warps, one column per warp at a time.  Per component step the dependent chain is
-// shfl -> multiply by the precomputed 1/hess -> clamp -> rank-1 update from smem, ~20 instructions.
-constexpr int kFastWarps = 24;   // 6 warps per scheduler hide the per-step dependency chain
-constexpr int kFastTile = 24;    // one column per warp
-
-template <int KPL>
-__global__ void __launch_bounds__(kFastWarps * 32, 1)
-cd_sweep_smem_kernel(float* __restrict__ f, int k, int64_t cols, int64_t ld, const float* __restrict__ num,
-                     int num_splits, int64_t num_stride, const float* __restrict__ den, int64_t ld_part,
-                     const float* __restrict__ gram, int ldg, float l1, float l2, double* __restrict__ violation,
-                     unsigned int* __restrict__ rowmax_bits) {
-    extern __shared__ float sm[];
-    __shared__ double scratch[32];
-    const int kpad = k | 1;
-    constexpr int kRow = 32 * KPL;                        // zero-padded Gram row: no bounds predicate
-    float* gram_s = sm;                                   // [k][kRow]
-    float* invh_s = gram_s + k * kRow;                    // [k]  1 / (G[t][t] + l2), 0 when the hessian is 0
-    float* g_s = invh_s + k;                              // [kFastTile][kpad]
-    float* f_s = g_s + kFastTile * kpad;                  // [kFastTile][kpad]
-    unsigned int* max_s = reinterpret_cast<unsigned int*>(f_s + kFastTile * kpad);  // [k]
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int idx = threadIdx.x; idx < k * kRow; idx += blockDim.x) {
-        const int t = idx / kRow, u = idx - t * kRow;
-        gram_s[idx] = u < k ? gram[static_cast<int64_t>(t) * ldg + u] : 0.0f;
-    }
-    for (int u = threadIdx.x; u < k; u += blockDim.x) {
-        const float hess = gram[static_cast<int64_t>(u) * ldg + u] + l2;
-        invh_s[u] = hess != 0.0f ? 1.0f / hess : 0.0f;
-        max_s[u] = 0u;
-    }
-    float viol = 0.0f;
-    const int64_t ntiles = (cols + kFastTile - 1) / kFastTile;
-
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int64_t j0 = tile * kFastTile;
-        __syncthreads();
-        // ---- phase 1: consecutive threads read consecutive columns of one component row ------------------
-#pragma unroll 4
-        for (int idx = threadIdx.x; idx < k * kFastTile; idx += kFastWarps * 32) {
-            const int u = idx / kFastTile, c = idx - u * kFastTile;
-            const int64_t j = j0 + c;
-            float fv = 0.0f, gv = 0.0f;
-            if (j < cols) {
-                fv = f[static_cast<int64_t>(u) * ld + j];
-                float nv = 0.0f;
-                for (int s = 0; s < num_splits; ++s)
-                    nv += __ldcs(num + s * num_stride + static_cast<int64_t>(u) * ld_part + j);
-                const float dv = __ldcs(den + static_cast<int64_t>(u) * ld_part + j);
-                gv = fmaf(l2, fv, dv) - (nv - l1);
-            }
-            g_s[c * kpad + u] = gv;
-            f_s[c * kpad + u] = fv;
-        }
-        __syncthreads();
-        // ---- phase 2: one warp = one column ------------------------------------------------------------
-        if (j0 + warp < cols) {
-            float g[KPL], fv[KPL];
-#pragma unroll
-            for (int i = 0; i < KPL; ++i) {
-                const int u = lane + 32 * i;
-                g[i] = u < k ? g_s[warp * kpad + u] : 0.0f;
-                fv[i] = u < k ? f_s[warp * kpad + u] : 0.0f;
-            }
-#pragma unroll
-            for (int i = 0; i < KPL; ++i) {
-                const int t_end = min(32, k - 32 * i);
-                for (int o = 0; o < t_end; ++o) {
-                    const int t = 32 * i + o;
-                    const float gt = __shfl_sync(0xffffffffu, g[i], o);
-                    const float ft = __shfl_sync(0xffffffffu, fv[i], o);
-                    const float inv = invh_s[t];
-                    viol += fabsf((ft == 0.0f) ? fminf(0.0f, gt) : gt);
-                    const float fn = fmaxf(fmaf(-gt, inv, ft), 0.0f);
-                    const float delta = (inv != 0.0f) ? fn - ft : 0.0f;
-                    if (delta != 0.0f) {  // warp-uniform
-                        const float* grow = gram_s + t * kRow + lane;
-#pragma unroll
-                        for (int i2 = i; i2 < KPL; ++i2) g[i2] = fmaf(delta, grow[32 * i2], g[i2]);
-                        if (lane == o) fv[i] = fn;
-                    }
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < KPL; ++i) {
-                const int u = lane + 32 * i;
-                if (u < k) f_s[warp * kpad + u] = fv[i];
-            }
-        }
-        __syncthreads();
-        // ---- phase 3: store + per-row maxima --------------------------------------------------------------
-        for (int idx = threadIdx.x; idx < k * kFastTile; idx += kFastWarps * 32) {
-            const int u = idx / kFastTile, c = idx - u * kFastTile;
-            const int64_t j = j0 + c;
-            if (j < cols) {
-                const float v = f_s[c * kpad + u];
-                f[static_cast<int64_t>(u) * ld + j] = v;
-                const unsigned int bits = __float_as_uint(v);
-                if (bits > max_s[u]) atomicMax(&max_s[u], bits);   // v >= 0: float order == uint order
-            }
-        }
-    }
-    __syncthreads();
-    for (int u = threadIdx.x; u < k; u += blockDim.x)
-        if (max_s[u] != 0u) atomicMax(&rowmax_bits[u], max_s[u]);
-    const double total = block_sum(lane == 0 ? static_cast<double>(viol) : 0.0, scratch);
-    if (threadIdx.x == 0 && total != 0.0) atomicAdd(violation, total);
-}
-
 
 // ---- blocked sweep: thread-per-sample steps + register-tiled rank-16 updates -----------------------------
 // A CTA owns TJ samples (columns j of F).  Their gradient vectors live in shared memory as gs[u][c]
@@ -458,9 +246,8 @@ int cd_sweep(float* f, int64_t k, int64_t cols, int64_t ld, const float* num, in
     if (k * cols == 0) return 0;
     NFB_CHECK(k <= 512, "n_components > 512 is not supported by the coordinate-descent kernel");
     const int ldg = static_cast<int>(round_up64(k, 16));
-    const int kpad = static_cast<int>(k) | 1;
-    // preferred: blocked sweep.  Pick the sample tile that minimises waves x tile (one CTA per SM).
-    if (getenv("NFB_CD_KERNEL") == nullptr || atoi(getenv("NFB_CD_KERNEL")) == 0) {
+    // blocked sweep: pick the sample tile that minimises waves x tile (one CTA per SM)
+    {
         const int64_t kp4 = round_up64(k, 4);
         // 128-bit seed loads need 16-byte aligned rows in all three operands
         const bool vec = ((ld | ld_part | num_stride) % 4 == 0) &&
@@ -503,49 +290,8 @@ int cd_sweep(float* f, int64_t k, int64_t cols, int64_t ld, const float* num, in
             default: break;
         }
     }
-    const int kpl_fast = k <= 32 ? 1 : k <= 64 ? 2 : k <= 128 ? 4 : 7;
-    const size_t smem_fast = (static_cast<size_t>(k) * 32 * kpl_fast + 2 * k +
-                              static_cast<size_t>(2) * kFastTile * kpad) * sizeof(float);
-    if (k <= 32 * kpl_fast && smem_fast <= 224 * 1024) {
-        const int64_t ntiles_fast = ceil_div64(cols, kFastTile);
-        const int grid_fast = static_cast<int>(std::min<int64_t>(ntiles_fast, sm_count()));
-#define NFB_CD_FAST(KPL)                                                                                         \
-    do {                                                                                                         \
-        auto kernel = cd_sweep_smem_kernel<KPL>;                                                                 \
-        NFB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,                       \
-                                      static_cast<int>(smem_fast)));                                             \
-        kernel<<<grid_fast, kFastWarps * 32, smem_fast, stream>>>(f, static_cast<int>(k), cols, ld, num,         \
-                                                                  num_splits, num_stride, den, ld_part, gram,    \
-                                                                  ldg, l1, l2, violation, rowmax_bits);          \
-    } while (0)
-        if (k <= 32) NFB_CD_FAST(1);
-        else if (k <= 64) NFB_CD_FAST(2);
-        else if (k <= 128) NFB_CD_FAST(4);
-        else NFB_CD_FAST(7);
-#undef NFB_CD_FAST
-        NFB_CUDA(cudaGetLastError());
-        return 0;
-    }
-    const size_t smem = (static_cast<size_t>(2) * kTileCols * kpad + k) * sizeof(float);
-    const int64_t ntiles = ceil_div64(cols, kTileCols);
-    NFB_CHECK(smem <= 220 * 1024, "n_components too large for the coordinate-descent kernel");
-    const int blocks_per_sm = std::max<int>(1, std::min<int>(4, static_cast<int>((200 * 1024) / (smem + 1024))));
-    const int grid = static_cast<int>(std::min<int64_t>(ntiles, static_cast<int64_t>(sm_count()) * blocks_per_sm));
-#define NFB_CD_LAUNCH(KPL)                                                                                       \
-    do {                                                                                                         \
-        auto kernel = cd_sweep_warp_kernel<KPL>;                                                                 \
-        NFB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); \
-        kernel<<<grid, kWarps * 32, smem, stream>>>(f, static_cast<int>(k), cols, ld, num, num_splits, num_stride, \
-                                                    den, ld_part, gram, ldg, l1, l2, violation, rowmax_bits);    \
-    } while (0)
-    if (k <= 32) NFB_CD_LAUNCH(1);
-    else if (k <= 64) NFB_CD_LAUNCH(2);
-    else if (k <= 128) NFB_CD_LAUNCH(4);
-    else if (k <= 256) NFB_CD_LAUNCH(8);
-    else NFB_CD_LAUNCH(16);
-#undef NFB_CD_LAUNCH
-    NFB_CUDA(cudaGetLastError());
-    return 0;
+    NFB_CHECK(false, "n_components too large for the coordinate-descent kernel");
+    return 1;
 }
 
 }  // namespace nfb
