@@ -67,24 +67,15 @@ def run_decomp(decomp, components: dict, connectivity_matrix, parallel: int = No
     return components
 
 
-def dual_regression_subject(fdt_path: str, components: dict, seeds: list, threshold: int = 3,
-                            normalise: bool = False, parallel: int = 1) -> dict:
-    """Compute part of NFACT/dual_reg/dual_regression/run_dual_regression.py:66-199 for one subject:
-    load the subject's fdt_matrix2 -> dual regression -> z-threshold -> optional z-score normalisation.
-    Saving the images stays with the reference's ``save_dual_regression_images``."""
+def _subject_matrix_file(fdt_path: str):
     import os
-    from .matrix_handling import load_fdt_matrix, normalise_components, thresholding_components
-    matrix = None
-    try:
-        matrix_file = next((os.path.join(fdt_path, fname) for fname in ("fdt_matrix2.dot.lz4", "fdt_matrix2.dot")
-                            if os.path.exists(os.path.join(fdt_path, fname))), None)
-        matrix = load_fdt_matrix(matrix_file, resident=True)     # stays in HBM: no dense host round trip
-    except Exception:
-        error_and_exit(False, f"Unable to load {os.path.basename(os.path.normpath(fdt_path))} fdt matrix")
-    try:
-        dr_results = run_decomp(nmf_dual_regression, components, matrix, parallel)
-    finally:
-        matrix.free()
+    return next((os.path.join(fdt_path, fname) for fname in ("fdt_matrix2.dot.lz4", "fdt_matrix2.dot")
+                 if os.path.exists(os.path.join(fdt_path, fname))), None)
+
+
+def _postprocess_subject(fdt_path: str, dr_results: dict, seeds: list, threshold: int, normalise: bool) -> dict:
+    import os
+    from .matrix_handling import normalise_components, thresholding_components
     dr_results = thresholding_components(int(threshold), os.path.join(fdt_path, "coords_for_fdt_matrix2"), seeds,
                                          dr_results)
     if normalise:
@@ -94,18 +85,92 @@ def dual_regression_subject(fdt_path: str, components: dict, seeds: list, thresh
     return dr_results
 
 
+def dual_regression_subject(fdt_path: str, components: dict, seeds: list, threshold: int = 3,
+                            normalise: bool = False, parallel: int = 1, matrix=None) -> dict:
+    """Compute part of NFACT/dual_reg/dual_regression/run_dual_regression.py:66-199 for one subject:
+    load the subject's fdt_matrix2 -> dual regression -> z-threshold -> optional z-score normalisation.
+    Saving the images stays with the reference's ``save_dual_regression_images``.  ``matrix``: the subject's
+    matrix when it has already been loaded (a ``DeviceMatrix`` from the prefetching loop of ``run_locally``)."""
+    import os
+    from .matrix_handling import load_fdt_matrix
+    owns = matrix is None
+    if owns:
+        try:
+            matrix = load_fdt_matrix(_subject_matrix_file(fdt_path), resident=True)   # stays in HBM
+        except Exception:
+            error_and_exit(False, f"Unable to load {os.path.basename(os.path.normpath(fdt_path))} fdt matrix")
+    try:
+        dr_results = run_decomp(nmf_dual_regression, components, matrix, parallel)
+    finally:
+        if owns:
+            matrix.free()
+    return _postprocess_subject(fdt_path, dr_results, seeds, threshold, normalise)
+
+
+def stream_subjects(load_matrix, n_subjects: int, components: dict, device: int | None = None, prefetch: bool = True):
+    """Generator over ``(index, dual-regression result)`` for subjects ``0 .. n_subjects-1``.
+
+    ``load_matrix(index, handle) -> DeviceMatrix`` makes subject ``index`` resident using ``handle``.  With
+    ``prefetch`` the next subject is loaded (file parse, triplet upload, scatter-add ingest, plane split) by a
+    background thread on a second handle -- its own CUDA stream -- while the current subject's regression
+    runs, so a subject costs max(load, solve) instead of their sum; two subjects are resident at a time."""
+    from concurrent.futures import ThreadPoolExecutor
+    from .device import Handle, get_handle
+    first = get_handle(device)
+    handles = [first, Handle(first.device)] if prefetch and n_subjects > 1 else [first]
+    try:
+        if len(handles) == 1:
+            for idx in range(n_subjects):
+                xdev = load_matrix(idx, first)
+                try:
+                    yield idx, nmf_dual_regression(components, xdev)
+                finally:
+                    xdev.free()
+            return
+        with ThreadPoolExecutor(max_workers=1) as pool:
+            pending = pool.submit(load_matrix, 0, handles[0])
+            for idx in range(n_subjects):
+                xdev = pending.result()
+                if idx + 1 < n_subjects:
+                    pending = pool.submit(load_matrix, idx + 1, handles[(idx + 1) % 2])
+                try:
+                    result = nmf_dual_regression(components, xdev)   # runs on the stream that loaded xdev
+                finally:
+                    xdev.free()
+                yield idx, result
+    finally:
+        for extra in handles[1:]:
+            extra.close()
+
+
 def run_locally(list_of_subject_dirs: list, components: dict, seeds: list, threshold: int = 3,
-                normalise: bool = False, rank: int = 0, world: int = 1, save=None) -> dict:
+                normalise: bool = False, rank: int = 0, world: int = 1, save=None, prefetch: bool = True) -> dict:
     """Subject loop of NFACT/dual_reg/dual_regression/set_up_dual_regression.py:186-235.  Subjects are
     independent: with ``world`` processes (one per GPU) rank r takes subjects r, r+world, ... and no
     collective is needed.  ``save(subject_dir, dr_results)`` receives each result (the reference's image
-    writer); the results of this rank are also returned keyed by subject directory."""
+    writer); the results of this rank are also returned keyed by subject directory.  The next subject's
+    matrix is parsed and ingested while the current one is being regressed (``stream_subjects``)."""
+    import os
+    from .matrix_handling import load_fdt_matrix
+    mine = [d for idx, d in enumerate(list_of_subject_dirs) if idx % world == rank]
+
+    def load(idx, handle):
+        try:
+            return load_fdt_matrix(_subject_matrix_file(mine[idx]), resident=True, handle=handle)
+        except Exception:
+            error_and_exit(False, f"Unable to load {os.path.basename(os.path.normpath(mine[idx]))} fdt matrix")
+
     out = {}
-    for idx, subject_dir in enumerate(list_of_subject_dirs):
-        if idx % world != rank:
-            continue
-        dr_results = dual_regression_subject(subject_dir, components, seeds, threshold, normalise)
-        if save is not None:
-            save(subject_dir, dr_results)
-        out[subject_dir] = dr_results
+    try:
+        for idx, dr_results in stream_subjects(load, len(mine), components, prefetch=prefetch):
+            dr_results = _postprocess_subject(mine[idx], dr_results, seeds, threshold, normalise)
+            if save is not None:
+                save(mine[idx], dr_results)
+            out[mine[idx]] = dr_results
+    except ValueError as e:
+        error_and_exit(False, f"Components have incompatable size with connectivity Matrix {e}")
+    except SystemExit:
+        raise
+    except Exception as e:
+        error_and_exit(False, f"Unable to perform dual regression due to {e}")
     return out

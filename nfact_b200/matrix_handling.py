@@ -95,14 +95,14 @@ def _cuda_ready() -> bool:
         return False
 
 
-def load_fdt_matrix(matfile: str, resident: bool = False):
+def load_fdt_matrix(matfile: str, resident: bool = False, handle=None):
     """NFACT/base/matrix_handling.py:143-158: dense float32 [m, n].
 
     ``resident=True`` keeps the matrix in HBM and returns a ``DeviceMatrix`` (what ``nmf_decomp`` /
     ``nmf_dual_regression`` take directly) instead of copying 4mn bytes to the host and back."""
     coo = load_single_matrix(matfile, pinned=_cuda_ready())
     ingest = device.ingest_coo_resident if resident else device.ingest_coo
-    return ingest([(coo.rows, coo.cols, coo.data, coo.scale)], coo.shape[0], coo.shape[1], False)
+    return ingest([(coo.rows, coo.cols, coo.data, coo.scale)], coo.shape[0], coo.shape[1], False, handle)
 
 
 def avg_fdt(list_of_matfiles: list) -> np.ndarray:

@@ -127,8 +127,15 @@ class NMF:
         self.params = _check_params(dict(kwargs, n_components=n_components))
 
     def fit_transform(self, X, y=None, W=None, H=None):
+        import os
+        import time
         p = self.params
         k = int(p["n_components"])
+        marks = [("start", time.perf_counter())] if os.environ.get("NFB_HOST_TIMING") else None
+
+        def mark(name):
+            if marks is not None:
+                marks.append((name, time.perf_counter()))
         if isinstance(X, DeviceMatrix):
             xdev, x_mean, owns = X, None, False
         else:
@@ -140,6 +147,7 @@ class NMF:
             # the mean is only needed by the non-custom initialisations
             x_mean = float(X.mean()) if p["init"] != "custom" else None
             xdev, owns = DeviceMatrix.from_host(X), True
+        mark("upload+split X")
         try:
             if xdev.has_negative:     # sklearn check_non_negative, evaluated on the device during ingest
                 raise ValueError("Negative values in data passed to NMF (input X)")
@@ -162,16 +170,25 @@ class NMF:
                 W0, H0 = initialize_nmf(xdev, x_mean, k, p["init"], p["random_state"])
             # row-sharded runs: sklearn's n_samples is the number of seeds of the whole matrix
             regs = compute_regularization(global_rows(xdev.handle, m), n, p["alpha_W"], p["alpha_H"], p["l1_ratio"])
+            mark("init / checks")
             state = NmfState(xdev, k, make_params(p["solver"], p["max_iter"], p["tol"], regs, p["verbose"]))
             try:
                 state.set_factors(W0, H0)
+                mark("state + factor upload")
                 self.n_iter_, self.reconstruction_err_ = state.run()
+                mark("solve")
                 Wf, Hf = state.get_factors()
+                mark("download")
             finally:
                 state.free()
         finally:
             if owns:
                 xdev.free()
+        mark("free")
+        if marks is not None:
+            import sys
+            print("nfact_b200 host timing: " + "  ".join(f"{b[0]}={b[1] - a[1]:.3f}s" for a, b in zip(marks, marks[1:])),
+                  file=sys.stderr)
         self.components_ = Hf
         self.n_components_ = Hf.shape[0]
         return Wf

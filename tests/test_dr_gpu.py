@@ -94,3 +94,30 @@ def test_dr_float32_components_and_nonfinite(golden):
     xbad[5, 60] = np.inf
     with pytest.raises(ValueError):
         nfact_b200.nmf_dual_regression({"grey_components": g32}, xbad)
+
+
+def test_run_locally_prefetch_equals_sequential(golden, tmp_path):
+    """The prefetching subject loop (next subject ingested on a second stream while the current one is solved)
+    returns exactly what the sequential loop returns, subject by subject."""
+    import os
+    import shutil
+    import nfact_b200
+    from conftest import GOLDEN_DIR
+    dirs = []
+    for s in (1, 2, 3):
+        sub = tmp_path / f"sub-{s}"
+        shutil.copytree(os.path.join(GOLDEN_DIR, "data", f"sub-{s}"), sub)
+        coords = np.zeros((99, 5), dtype=int)
+        coords[40:, -2] = 1
+        np.savetxt(sub / "coords_for_fdt_matrix2", coords, fmt="%d")
+        dirs.append(str(sub))
+    comps = {"grey_components": golden["cd_fit_W"].astype(np.float64)}
+    seq = nfact_b200.run_locally(dirs, comps, ["L", "R"], threshold=2, prefetch=False)
+    pre = nfact_b200.run_locally(dirs, comps, ["L", "R"], threshold=2, prefetch=True)
+    assert list(seq) == list(pre) == dirs
+    for d in dirs:
+        for key in ("grey_components", "white_components"):
+            assert np.array_equal(seq[d][key], pre[d][key])
+    # rank r of `world` takes subjects r, r + world, ...
+    part = nfact_b200.run_locally(dirs, comps, ["L", "R"], threshold=2, rank=1, world=2)
+    assert list(part) == [dirs[1]] and np.array_equal(part[dirs[1]]["white_components"], seq[dirs[1]]["white_components"])

@@ -223,3 +223,38 @@ def test_sso_similarity_matrix_matches_corrcoef():
         assert sim.shape == (r, r) and sim.dtype == np.float64
         assert np.abs(sim - ref).max() < 5e-6
         assert np.array_equal(sim, sim.T) and (np.diag(sim) == 1.0).all()
+
+
+def test_cd_run_ahead_loop_equals_stepwise_loop(golden):
+    """nfb_nmf_run keeps one CD iteration in flight while it looks at the previous violation and rolls the
+    speculative iteration back when sklearn's rule says stop: same n_iter and bit-identical factors as
+    stepping one iteration at a time with a synchronous check."""
+    from nfact_b200.device import DeviceMatrix, NmfState, make_params
+    from oracle import nfact_oracle as orc
+    X = golden["ingest_group"]
+    k = 10
+    W0, H0 = golden["init_nndsvd_W"], golden["init_nndsvd_H"]
+    regs = orc.compute_regularization(X.shape[0], X.shape[1], 0.1, "same", 1.0)
+    xdev = DeviceMatrix.from_host(X)
+    for tol, max_iter in ((1e-4, 200), (5e-2, 200), (1e-4, 7), (1e-4, 1), (0.9, 200)):
+        fast = NmfState(xdev, k, make_params("cd", max_iter, tol, regs))
+        fast.set_factors(W0.copy(), H0.copy())
+        n_fast, err_fast = fast.run()
+        Wf, Hf = fast.get_factors()
+        fast.free()
+        slow = NmfState(xdev, k, make_params("cd", max_iter, tol, regs))
+        slow.set_factors(W0.copy(), H0.copy())
+        n_slow, v_init = 0, None
+        for it in range(1, max_iter + 1):
+            v = slow.iterate(1, want_violation=True)
+            n_slow = it
+            v_init = v if it == 1 else v_init
+            if v_init == 0 or v / v_init <= tol:
+                break
+        Ws, Hs = slow.get_factors()
+        err_slow = slow.error()
+        slow.free()
+        assert n_fast == n_slow, (tol, max_iter, n_fast, n_slow)
+        assert np.array_equal(Wf, Ws) and np.array_equal(Hf, Hs)
+        assert abs(err_fast - err_slow) <= 1e-9 * err_slow
+    xdev.free()
