@@ -227,9 +227,23 @@ cd_sweep_tile_kernel(float* __restrict__ f, int k, int64_t cols, int64_t ld, con
 #pragma unroll
             for (int i = 0; i < kBlk; ++i) gb[i * kp4 + tid] = pre[i];
         }
-        if (kp4 > NT) {                                    // columns the register prefetch does not cover
-            for (int i = 0; i < kBlk; ++i)
-                for (int u = tid + NT; u < kp4; u += NT) gb[i * kp4 + u] = load_g(t0 + kBlk + i, u);
+        if (kp4 > NT) {
+            // columns the register prefetch does not cover (k > NT): 16 independent clamped loads per pass, not
+            // 16 dependent round trips to L2
+            for (int base = NT; base < kp4; base += NT) {
+                const int u = base + tid, uc = min(u, k - 1);
+                float ov[kBlk];
+#pragma unroll
+                for (int i = 0; i < kBlk; ++i) {
+                    const int t = t0 + kBlk + i;
+                    const float v = __ldg(gram + static_cast<int64_t>(min(t, k - 1)) * ldg + uc);
+                    ov[i] = (t < k && u < k) ? v : 0.0f;
+                }
+                if (u < kp4) {
+#pragma unroll
+                    for (int i = 0; i < kBlk; ++i) gb[i * kp4 + u] = ov[i];
+                }
+            }
         }
         if (tid < kBlk) invh[tid] = hess_next != 0.0f ? 1.0f / hess_next : 0.0f;
         __syncthreads();

@@ -45,12 +45,13 @@ __device__ __forceinline__ float ld_peer(const float* p) {
     return v;
 }
 
-// spin until flags[p] >= epoch for all p < world (threads 0..world-1 of the CTA); ~4 s timeout
+// spin until flags[p] >= epoch for all p < world (threads 0..world-1 of the CTA); ~30 s timeout (ranks may
+// legitimately drift by the time one of them spends in a host-side step between two collective phases)
 __device__ __forceinline__ void wait_all(const int* flags, int world, int epoch, int* error) {
     if (threadIdx.x < world) {
         const long long t0 = clock64();
         while (ld_acquire_sys(flags + threadIdx.x) < epoch) {
-            if (clock64() - t0 > 8000000000LL) { *error = 1; break; }
+            if (clock64() - t0 > 60000000000LL) { *error = 1; break; }
             __nanosleep(64);
         }
     }
