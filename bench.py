@@ -415,21 +415,7 @@ def run_ours(args):
                 dr = nfact_b200.nmf_dual_regression(comps, xres)
                 t_pipe = time.perf_counter() - t0
                 xres.free()
-                del dr
-                # ... and the same for a run of subjects (C4 is 100 of them): nfact_b200.stream_subjects loads
-                # subject i+1 on a second stream while subject i is being regressed
-                n_stream = 4
-                t0 = time.perf_counter()
-                for _idx, _res in nfact_b200.stream_subjects(
-                        lambda i, hdl: ingest_coo_resident([(coo_rows, coo_cols, coo_vals, 1.0)], int(rows), int(n),
-                                                           False, hdl),
-                        n_stream, comps, device=local_rank):
-                    assert np.isfinite(_res["grey_components"]).all()
-                t_stream = (time.perf_counter() - t0) / n_stream
-                del _res
                 dr_info = {"value": 1.0 / min(times), "unit": "subjects/s", "seconds": min(times),
-                           "stream_value": 1.0 / t_stream, "stream_seconds_per_subject": t_stream,
-                           "stream_subjects": n_stream,
                            "e2e_value": 1.0 / t_host, "e2e_seconds": t_host,
                            "pipeline_value": 1.0 / t_pipe, "pipeline_seconds": t_pipe, "pipeline_ingest_seconds": t_ing,
                            "pipeline_triplets": int(coo_rows.size), "shape": [int(rows), int(n), int(k)],
