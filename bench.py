@@ -25,6 +25,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly one JSON line: NCCL's version banner and debug output go to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 WORKLOADS = {
     # name: (m seeds, n targets, k components, nnz density)   SURVEY.md section 8d

@@ -24,6 +24,7 @@
 // every finished chain into fp32 registers with round-to-nearest adds while the issuer fills the other
 // TMEM stage (the FP8-style "promotion" scheme, applied here to keep fp32-faithful sums).
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -456,6 +457,24 @@ int gemm_split(const GemmOperand& a, bool a_is_mn_major, const GemmOperand& b, i
                const float* row_scale, float scale, int cta_group, cudaStream_t stream) {
     NFB_CHECK(n_umma % 16 == 0 && n_umma >= 16, "n_umma must be a positive multiple of 16");
     const long long split_stride = static_cast<long long>(n_store) * ld_out;
+    // NFB_GEMM_TIMING=1: device time of every call (debug aid; synchronises the stream)
+    static const bool timing = getenv("NFB_GEMM_TIMING") != nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (timing && cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess) cudaEventRecord(e0, stream);
+    struct Report {
+        cudaEvent_t e0, e1; cudaStream_t st; int64_t m, k; int n, splits, cg; bool mn;
+        ~Report() {
+            if (!e0 || !e1) return;
+            cudaEventRecord(e1, st);
+            cudaEventSynchronize(e1);
+            float ms = 0.0f;
+            cudaEventElapsedTime(&ms, e0, e1);
+            fprintf(stderr, "nfact_b200 gemm: M=%lld K=%lld N=%d splits=%d cta_group=%d a_mn_major=%d  %.3f ms\n",
+                    static_cast<long long>(m), static_cast<long long>(k), n, splits, cg, mn ? 1 : 0, ms);
+            cudaEventDestroy(e0);
+            cudaEventDestroy(e1);
+        }
+    } report{e0, e1, stream, m_total, k_total, n_umma, splits, cta_group, a_is_mn_major};
     for (int t0 = 0; t0 < n_umma && t0 < n_store; t0 += 256) {
         const int n_tile = std::min(256, n_umma - t0);
         GemmOperand bt{b.hi + static_cast<int64_t>(t0) * b.ld, b.lo + static_cast<int64_t>(t0) * b.ld, b.rows - t0,
