@@ -144,8 +144,9 @@ class NMF:
                 raise ValueError(f"Expected 2D array, got {X.ndim}D array instead")
             if X.dtype not in (np.float32, np.float64):
                 X = X.astype(np.float64)
-            # the mean is only needed by the non-custom initialisations
-            x_mean = float(X.mean()) if p["init"] != "custom" else None
+            # the mean is only needed by the non-custom initialisations; for a large matrix a host pass costs
+            # seconds, so it is taken from the float64 sum the device accumulates while splitting X
+            x_mean = float(X.mean()) if p["init"] != "custom" and X.nbytes <= (256 << 20) else None
             xdev, owns = DeviceMatrix.from_host(X), True
         mark("upload+split X")
         try:

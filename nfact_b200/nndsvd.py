@@ -37,6 +37,11 @@ def randomized_svd_device(xdev, k: int, rng, n_oversamples: int = 10):
         return _matmul(xdev, trans=(mat_t != transpose), q=qq.contiguous())
 
     def lu_normalise(a):
+        # sklearn normalises the power iterations with the P.L factor of an LU decomposition; any basis of the
+        # same column space gives the same final subspace, and a tall-skinny LU (a serial panel factorisation)
+        # is the slow way to get one on a GPU -- Householder QR from cuSOLVER takes its place for big panels
+        if a.shape[0] > 8192:
+            return torch.linalg.qr(a, mode="reduced")[0]
         p, l, _ = torch.linalg.lu(a)
         return p @ l
 
