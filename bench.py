@@ -25,8 +25,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# stdout carries exactly one JSON line: NCCL's version banner and debug output go to stderr
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+# stdout carries exactly one JSON line: whatever libraries write to file descriptor 1 (NCCL's version banner,
+# MAGMA warnings) is sent to stderr, and the result goes to the real stdout kept here
+RESULT_OUT = sys.stdout     # replaced in main(); importing this module (tests, probes) leaves stdout alone
 
 WORKLOADS = {
     # name: (m seeds, n targets, k components, nnz density)   SURVEY.md section 8d
@@ -272,7 +273,7 @@ def run_reference(args):
         "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": time.perf_counter() - t_start,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=RESULT_OUT, flush=True)
 
 
 def run_ours(args):
@@ -481,12 +482,15 @@ def run_ours(args):
         line["ingest"] = ingest_benchmark(handle)
     if not args.no_cpu and world == 1:
         line["cpu_baseline"] = cpu_baseline(m, n, k, density, args.solver)
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=RESULT_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
 def main():
+    global RESULT_OUT
+    RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     args = parse_args()
     if args.shape:
         parts = args.shape.split(",")

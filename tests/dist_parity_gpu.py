@@ -52,6 +52,20 @@ def main():
                 ok &= abs(viol - rec[-1][3]) <= 1e-3 * rec[-1][3]
             print(line, flush=True)
             ok &= ew < 1e-4 and eh < 1e-4 and abs(err - eref) <= 1e-4 * eref
+        # sklearn's stopping rule through nfb_nmf_run: the loop keeps one iteration in flight and rolls the
+        # speculative one back when it stops early -- same n_iter and factors as the oracle, on every rank
+        for tol in (3e-1, 1e-2):
+            st = NmfState(xdev, k, make_params("cd", 60, tol, regs))
+            st.set_factors(W0[r0:r1], H0)
+            n_iter, err = st.run()
+            W, H = st.get_factors()
+            st.free()
+            Wr, Hr, n_ref = orc.fit_cd(X, W0, H0, *regs, tol=tol, max_iter=60)
+            ew = np.linalg.norm(W - Wr[r0:r1]) / np.linalg.norm(Wr[r0:r1])
+            eh = np.linalg.norm(H - Hr) / np.linalg.norm(Hr)
+            print(f"rank {rank} {m}x{n} k={k} cd run tol={tol}: n_iter={n_iter} (oracle {n_ref}) relW={ew:.2e} "
+                  f"relH={eh:.2e}", flush=True)
+            ok &= n_iter == n_ref and ew < 1e-3 and eh < 1e-3
         xdev.free()
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
