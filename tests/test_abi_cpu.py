@@ -155,3 +155,16 @@ def test_fused_coo_parser_matches_the_reference_construction(tmp_path, golden_su
                       ("1 2\n3 3 0\n", "could not convert"), ("1 2 3 4\n3 3 0\n", "could not convert")):
         with pytest.raises(ValueError, match=msg):
             parse_dot_coo(text.encode())
+
+
+def test_sso_clustering_glue_matches_reference():
+    """sim2dis / clustering_components / idx2centrotype (host code of nfact_b200.nmfsso) against the outputs of
+    the reference's own sso_functions.py on the committed golden stack (tests/golden/make_golden_sso.py)."""
+    from conftest import GOLDEN_DIR
+    from nfact_b200 import nmfsso
+    g = np.load(os.path.join(GOLDEN_DIR, "golden_sso.npz"))
+    dis = nmfsso.sim2dis(g["sim"])
+    assert np.array_equal(dis, g["dis"])
+    part = nmfsso.clustering_components(dis, int(g["dim"]))
+    assert np.array_equal(part, g["partition"])
+    assert np.array_equal(nmfsso.idx2centrotype(g["sim"], part), g["centrotypes"])

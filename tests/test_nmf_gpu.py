@@ -258,3 +258,17 @@ def test_cd_run_ahead_loop_equals_stepwise_loop(golden):
         assert np.array_equal(Wf, Ws) and np.array_equal(Hf, Hs)
         assert abs(err_fast - err_slow) <= 1e-9 * err_slow
     xdev.free()
+
+
+def test_sso_similarity_matches_reference_golden():
+    """Device similarity matrix vs the reference's compute_similairty_matrix output (golden), and the clustering
+    that follows from it: same partition and centrotypes as the reference run."""
+    import os
+    from conftest import GOLDEN_DIR
+    from nfact_b200 import nmfsso
+    g = np.load(os.path.join(GOLDEN_DIR, "golden_sso.npz"))
+    sim = nmfsso.compute_similairty_matrix(g["components"])
+    assert np.abs(sim - g["sim"]).max() < 5e-6
+    part = nmfsso.clustering_components(nmfsso.sim2dis(sim), int(g["dim"]))
+    assert np.array_equal(part, g["partition"])
+    assert np.array_equal(nmfsso.idx2centrotype(sim, part), g["centrotypes"])
