@@ -216,8 +216,8 @@ nnls_smem_kernel(const double* __restrict__ gram, int k, const float* __restrict
             // ---- conjugate gradients on the current support P = {h > 0} --------------------------------
             // Between two full sweeps the support is fixed and the problem is the linear system
             // G_PP z = r_P: CG needs O(sqrt(cond)) products with G where coordinate sweeps need O(cond).
-            // The step is cut at the first component that would turn negative; that component leaves P
-            // and the outer loop (full sweep) re-examines the support.
+            // The step is cut at the first component that would turn negative; that component leaves P and CG
+            // restarts on the reduced support; the outer loop (full sweep) re-examines what may enter P.
             double d[KPL], q[KPL];
             bool in_p[KPL];
             double rr = 0.0;
@@ -268,7 +268,19 @@ nnls_smem_kernel(const double* __restrict__ gram, int k, const float* __restrict
                     h[i] = blocked ? 0.0 : h_new;
                     if (in_p[i]) rr_new = fma(g[i], g[i], rr_new);
                 }
-                if (hit) break;
+                if (hit) {
+                    // the blocking component(s) left P: restart CG on the reduced support instead of paying a
+                    // full sweep per dropped component (the sweep is only needed to let components ENTER P)
+                    rr = 0.0;
+#pragma unroll
+                    for (int i = 0; i < KPL; ++i) {
+                        in_p[i] = in_p[i] && h[i] > 0.0;
+                        d[i] = in_p[i] ? -g[i] : 0.0;
+                        rr = fma(d[i], d[i], rr);
+                    }
+                    rr = warp_sum(rr);
+                    continue;
+                }
                 rr_new = warp_sum(rr_new);
                 const double beta = rr_new / rr;
 #pragma unroll
