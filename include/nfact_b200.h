@@ -78,6 +78,16 @@ int nfb_dot_parse(const char* buf, int64_t len, int nthreads, int64_t n_lines, d
 int nfb_dot_parse_coo(const char* buf, int64_t len, int nthreads, int64_t n_lines, int32_t* rows0, int32_t* cols0,
                       double* vals, int64_t* shape_out);
 
+/* LZ4 frame decoder for fdt_matrix2.dot.lz4 (replaces lz4.frame.open(matfile, "rb").read() at
+ * NFACT/base/matrix_handling.py:108-110; files written by NFACT/config/nfact_config_functions.py:601-604).
+ * Two calls: the decoded size of the whole file (all concatenated frames; skippable frames are skipped), then the
+ * decode into a caller-owned buffer of at least that size.  Header, block and content checksums (XXH32) are
+ * verified; a corrupt or truncated file is an error carrying LZ4F's error name.  Frames with independent blocks
+ * are decoded by `nthreads` host threads (<= 0: all cores), linked-block frames in order. */
+int nfb_lz4_frame_size(const void* src, int64_t src_len, int nthreads, int64_t* size_out);
+int nfb_lz4_frame_decompress(const void* src, int64_t src_len, void* dst, int64_t dst_cap, int nthreads,
+                             int64_t* written_out);
+
 /* ---- resident matrix --------------------------------------------------------------------------
  * X float32 [m, n] -> fp16 hi/lo planes in HBM (4 B/element, read by both X H' and W'X). */
 int nfb_matrix_from_host(nfb_handle* h, const float* x_host, int64_t m, int64_t n, nfb_matrix** out);

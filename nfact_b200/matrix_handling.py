@@ -4,7 +4,7 @@ Same names, arguments and error behaviour as
   NFACT/base/matrix_handling.py            read_in_matrix :93, load_single_matrix :116, load_fdt_matrix :143,
                                            normalise_components :45, thresholding :218, save_matrix :161
   NFACT/decomp/decomposition/matrix_handling.py   process_fdt_matrix2 :12, avg_fdt :73, load_previous_matrix :47
-The text parse stays on the host (it is I/O); duplicate summation, waytotal scaling, group averaging,
+LZ4 decoding and the text parse stay on the host (they are I/O, native and multi-threaded in libnfact_b200); duplicate summation, waytotal scaling, group averaging,
 densification and the float32 rounding run in libnfact_b200 (ingest.cu) and are bit-identical to the reference.
 """
 from __future__ import annotations
@@ -21,17 +21,40 @@ CooMatrix = namedtuple("CooMatrix", "rows cols data shape scale")
 
 
 def read_in_matrix(matfile: str) -> np.ndarray:
-    """NFACT/base/matrix_handling.py:93-113.  float64 [T+1, 3]; ``.lz4`` files need the lz4 module."""
+    """NFACT/base/matrix_handling.py:93-113.  float64 [T+1, 3], from ``.dot`` text or an ``.lz4`` frame."""
     return np.ascontiguousarray(parse_dot_bytes(_read_bytes(matfile), matfile).T)
 
 
-def _read_bytes(matfile: str) -> bytes:
-    if matfile.endswith(".lz4"):
-        import lz4.frame  # same optional dependency as the reference
-        with lz4.frame.open(matfile, "rb") as fil:
-            return fil.read()
+def _read_bytes(matfile: str):
+    """The file's text as a byte buffer; ``.lz4`` frames are decoded natively (``decompress_lz4_frame``)."""
     with open(matfile, "rb") as fil:
-        return fil.read()
+        raw = fil.read()
+    return decompress_lz4_frame(raw, matfile) if matfile.endswith(".lz4") else raw
+
+
+def decompress_lz4_frame(raw, name: str = "<buffer>") -> np.ndarray:
+    """``lz4.frame.open(matfile, "rb").read()`` (NFACT/base/matrix_handling.py:108-110) without the lz4 module:
+    libnfact_b200's multi-threaded LZ4 frame decoder (``nfb_lz4_frame_decompress``, checksums verified).
+    Returns the decoded bytes as a uint8 array; a corrupt file raises ``RuntimeError`` like python-lz4 does."""
+    import ctypes
+    from . import _lib
+    lib = _lib.load()
+    src = np.frombuffer(raw, dtype=np.uint8)
+    size, written = ctypes.c_int64(), ctypes.c_int64()
+    try:
+        _lib.check(lib.nfb_lz4_frame_size(src.ctypes.data, src.size, 0, ctypes.byref(size)))
+        out = np.empty(size.value, dtype=np.uint8)
+        _lib.check(lib.nfb_lz4_frame_decompress(src.ctypes.data, src.size, out.ctypes.data, out.size, 0,
+                                                ctypes.byref(written)))
+    except _lib.NfbError as e:
+        raise RuntimeError(f"{name}: {e}") from None
+    return out[:written.value]
+
+
+def _as_buffer(raw):
+    """(address, length, keep-alive) of a bytes-like object or uint8 array"""
+    arr = np.frombuffer(raw, dtype=np.uint8) if not isinstance(raw, np.ndarray) else np.ascontiguousarray(raw)
+    return arr.ctypes.data, arr.size, arr
 
 
 def parse_dot_bytes(raw: bytes, name: str = "<buffer>") -> np.ndarray:
@@ -40,14 +63,14 @@ def parse_dot_bytes(raw: bytes, name: str = "<buffer>") -> np.ndarray:
     import ctypes
     from . import _lib
     lib = _lib.load()
-    buf = ctypes.c_char_p(raw)
+    buf, nbytes, _keep = _as_buffer(raw)
     n_lines = ctypes.c_int64()
-    _lib.check(lib.nfb_dot_count_lines(buf, len(raw), 0, ctypes.byref(n_lines)))
+    _lib.check(lib.nfb_dot_count_lines(buf, nbytes, 0, ctypes.byref(n_lines)))
     if n_lines.value == 0:
         raise ValueError(f"{name}: file is empty")
     cols3 = np.empty((3, n_lines.value), dtype=np.float64)
     try:
-        _lib.check(lib.nfb_dot_parse(buf, len(raw), 0, n_lines.value, cols3[0].ctypes.data, cols3[1].ctypes.data,
+        _lib.check(lib.nfb_dot_parse(buf, nbytes, 0, n_lines.value, cols3[0].ctypes.data, cols3[1].ctypes.data,
                                      cols3[2].ctypes.data))
     except _lib.NfbError as e:
         raise ValueError(f"{name}: {e}") from None
@@ -61,9 +84,9 @@ def parse_dot_coo(raw: bytes, name: str = "<buffer>", pinned: bool = False):
     import ctypes
     from . import _lib
     lib = _lib.load()
-    buf = ctypes.c_char_p(raw)
+    buf, nbytes, _keep = _as_buffer(raw)
     n_lines = ctypes.c_int64()
-    _lib.check(lib.nfb_dot_count_lines(buf, len(raw), 0, ctypes.byref(n_lines)))
+    _lib.check(lib.nfb_dot_count_lines(buf, nbytes, 0, ctypes.byref(n_lines)))
     if n_lines.value == 0:
         raise ValueError(f"{name}: file is empty")
     nnz = n_lines.value - 1
@@ -71,7 +94,7 @@ def parse_dot_coo(raw: bytes, name: str = "<buffer>", pinned: bool = False):
     rows, cols, vals = alloc((nnz,), np.int32), alloc((nnz,), np.int32), alloc((nnz,), np.float64)
     shape = (ctypes.c_int64 * 2)()
     try:
-        _lib.check(lib.nfb_dot_parse_coo(buf, len(raw), 0, n_lines.value, rows.ctypes.data, cols.ctypes.data,
+        _lib.check(lib.nfb_dot_parse_coo(buf, nbytes, 0, n_lines.value, rows.ctypes.data, cols.ctypes.data,
                                          vals.ctypes.data, shape))
     except _lib.NfbError as e:
         raise ValueError(f"{e}") from None

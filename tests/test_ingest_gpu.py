@@ -85,3 +85,24 @@ def test_resident_ingest_feeds_the_solvers(golden, golden_subjects):
     xres.free()
     assert np.array_equal(a["white_components"], b["white_components"])
     assert np.array_equal(a["grey_components"], b["grey_components"])
+
+
+def test_lz4_subjects_bit_exact(tmp_path, golden, golden_subjects):
+    """fdt_matrix2.dot.lz4 (NFACT/base/matrix_handling.py:108-110) through the native frame decoder: the same
+    float32 matrices as the text files, single subject and group average, linked and independent blocks."""
+    import shutil
+    import nfact_b200
+    from oracle import lz4_frame as z
+    folders = []
+    for s, path in enumerate(golden_subjects):
+        folder = tmp_path / f"sub-{s + 1}"
+        folder.mkdir()
+        shutil.copy(os.path.join(os.path.dirname(path), "waytotal"), folder / "waytotal")
+        with open(folder / "fdt_matrix2.dot.lz4", "wb") as fh:
+            fh.write(z.compress(open(path, "rb").read(), independent=bool(s % 2), content_checksum=bool(s % 2)))
+        folders.append(str(folder))
+    for s, folder in enumerate(folders):
+        X = nfact_b200.load_fdt_matrix(os.path.join(folder, "fdt_matrix2.dot.lz4"))
+        assert np.array_equal(X, golden[f"ingest_single_{s + 1}"])
+    assert np.array_equal(nfact_b200.process_fdt_matrix2(folders, True), golden["ingest_group"])
+    assert np.array_equal(nfact_b200.process_fdt_matrix2(folders[:1], False), golden["ingest_single_1"])
