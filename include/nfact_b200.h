@@ -161,6 +161,30 @@ int nfb_profile_gemms(nfb_handle* h, int enable, double* total_ms_out, int64_t* 
 int nfb_dual_regression_host(nfb_handle* h, const nfb_matrix* x, int k, const void* g_host, int g_is_f32,
                              double* gs_out, double* hs_out, int* n_unconverged_out, int* g_nonfinite_out);
 
+/* The same regression followed, while the results are still in HBM, by the per-subject post-processing of
+ * NFACT/dual_reg/dual_regression/run_dual_regression.py:166-186:
+ *   zscore != 0: thresholding_components (NFACT/base/matrix_handling.py:241-277) -- white components: entries
+ *     below mean + zscore * std of their component -> 0 (:218-238); grey components: the same per (component,
+ *     seed), seed_id_host[m] = the seed index of every row (second-to-last column of coords_for_fdt_matrix2,
+ *     :184-215), rows with an index outside [0, n_seeds) are left alone;
+ *   gs_norm_out / hs_norm_out != NULL: normalise_components (:45-68), StandardScaler per component of the
+ *     (thresholded) maps, written to these extra [m, k] / [k, n] float64 arrays. */
+int nfb_dual_regression_post_host(nfb_handle* h, const nfb_matrix* x, int k, const void* g_host, int g_is_f32,
+                                  double zscore, const int32_t* seed_id_host, int n_seeds, double* gs_out,
+                                  double* hs_out, double* gs_norm_out, double* hs_norm_out, int* n_unconverged_out,
+                                  int* g_nonfinite_out);
+
+/* Post-processing of component maps given as host arrays (replaces the numpy / sklearn arithmetic of
+ * thresholding :218-238, threshold_grey_components :184-215 and normalise_components :45-68 in
+ * NFACT/base/matrix_handling.py).  data: float32 or float64 (is_f64), [k, len] when comp_major (white components)
+ * or [len, k] (grey components).  do_threshold: entries below mean + zscore * std of their (component, group)
+ * are zeroed IN PLACE; group_id[len] (NULL: one group) assigns every sample to a group in [0, n_groups), samples
+ * outside stay untouched.  norm_out (NULL: skip): same shape and dtype, receives the z-scored (StandardScaler)
+ * copy of the -- thresholded -- data.  Statistics are float64. */
+int nfb_component_postops_host(nfb_handle* h, void* data, int is_f64, int comp_major, int64_t k, int64_t len,
+                               const int32_t* group_id, int n_groups, int do_threshold, double zscore,
+                               void* norm_out);
+
 /* ---- NMF-sso similarity --------------------------------------------------------------------------------
  * replaces  NFACT/decomp/decomposition/sso/sso_functions.py:29-68  compute_similairty_matrix:
  * np.corrcoef of the (row-normalised) stacked white-matter components of all NMF-sso runs -- (N k)^2 n

@@ -74,6 +74,11 @@ SIGNATURES = {
     "nfb_profile_gemms": (c_int, [c_void_p, c_int, POINTER(c_double), POINTER(c_int64)]),
     "nfb_dual_regression_host": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p,
                                          POINTER(c_int), POINTER(c_int)]),
+    "nfb_dual_regression_post_host": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_double, c_void_p, c_int,
+                                              c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_int),
+                                              POINTER(c_int)]),
+    "nfb_component_postops_host": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_int64, c_void_p, c_int, c_int,
+                                           c_double, c_void_p]),
     "nfb_row_correlation_host": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     "nfb_host_alloc": (c_int, [c_int64, POINTER(c_void_p)]),
     "nfb_host_free": (c_int, [c_void_p]),

@@ -53,30 +53,111 @@ cd_sweep_tile_kernel(float* __restrict__ f, int k, int64_t cols, int64_t ld, con
     const bool stepper = tid < TJ;
     const bool active = stepper && j < cols;
 
-    auto load_g = [&](int t, int u) -> float {             // G[t][u], zero outside the k x k matrix
-        return (t < k && u < k) ? __ldg(gram + static_cast<int64_t>(t) * ldg + u) : 0.0f;
+    // column `tid` (and tid + NT, ...) of the 16 G rows of block tb: independent clamped loads whose values are
+    // only looked at when they are committed to shared memory, so the round trip to L2 overlaps whatever runs
+    // in between (the gradient seed for block 0, the apply phase afterwards)
+    const int u_own = min(tid, k - 1);
+    auto fetch_rows = [&](int tb, float (&pre)[kBlk]) {
+        if (tb + kBlk <= k) {                              // whole block inside the matrix: one base, 16 strides
+            const float* gp = gram + static_cast<int64_t>(tb) * ldg + u_own;
+#pragma unroll
+            for (int i = 0; i < kBlk; ++i) pre[i] = __ldg(gp + i * ldg);
+        } else {
+#pragma unroll
+            for (int i = 0; i < kBlk; ++i) pre[i] = __ldg(gram + static_cast<int64_t>(min(tb + i, k - 1)) * ldg + u_own);
+        }
     };
-    auto load_hess = [&](int t0) -> float {
-        return (tid < kBlk && t0 + tid < k) ? __ldg(gram + static_cast<int64_t>(t0 + tid) * ldg + t0 + tid) + l2 : 0.0f;
+    auto fetch_factor = [&](int tb, int64_t jc_own, float (&fl)[kBlk]) {   // F[tb + i][own sample], clamped rows
+        if (tb + kBlk <= k) {
+            const float* fp = f + static_cast<int64_t>(tb) * ld + jc_own;
+#pragma unroll
+            for (int i = 0; i < kBlk; ++i) fl[i] = fp[i * ld];
+        } else {
+#pragma unroll
+            for (int i = 0; i < kBlk; ++i) fl[i] = f[static_cast<int64_t>(min(tb + i, k - 1)) * ld + jc_own];
+        }
+    };
+    auto fetch_hess = [&](int tb) -> float {               // raw G[t][t] of component tb + tid (clamped)
+        const int t = min(tb + (tid & (kBlk - 1)), k - 1);
+        return __ldg(gram + static_cast<int64_t>(t) * ldg + t);
+    };
+    auto commit_rows = [&](int tb, const float (&pre)[kBlk], float hess_raw) {
+        if (tid < kp4) {
+#pragma unroll
+            for (int i = 0; i < kBlk; ++i) gb[i * kp4 + tid] = (tb + i < k && tid < k) ? pre[i] : 0.0f;
+        }
+        if (kp4 > NT) {
+            // columns the register prefetch does not cover (k > NT): 16 independent clamped loads per pass
+            for (int base = NT; base < kp4; base += NT) {
+                const int u = base + tid, uc = min(u, k - 1);
+                float ov[kBlk];
+#pragma unroll
+                for (int i = 0; i < kBlk; ++i) ov[i] = __ldg(gram + static_cast<int64_t>(min(tb + i, k - 1)) * ldg + uc);
+                if (u < kp4) {
+#pragma unroll
+                    for (int i = 0; i < kBlk; ++i) gb[i * kp4 + u] = (tb + i < k && u < k) ? ov[i] : 0.0f;
+                }
+            }
+        }
+        if (tid < kBlk) {
+            const float hess = tb + tid < k ? hess_raw + l2 : 0.0f;
+            invh[tid] = hess != 0.0f ? 1.0f / hess : 0.0f;
+        }
     };
 
-    // ---- block 0 operands, then the gradient seed g = G F[:, j] + l2 F[:, j] - (num[:, j] - l1) -----------
-#pragma unroll 4
-    for (int i = 0; i < kBlk; ++i)
-        for (int u = tid; u < kp4; u += NT) gb[i * kp4 + u] = load_g(i, u);
-    if (tid < kBlk) {
-        const float hess = load_hess(0);
-        invh[tid] = hess != 0.0f ? 1.0f / hess : 0.0f;
-        max_s[tid] = 0u;
-    }
+    // ---- block 0 operands in flight, then the gradient seed g = G F[:, j] + l2 F[:, j] - (num[:, j] - l1) ----
+    float pre0[kBlk];
+    fetch_rows(0, pre0);
+    const float hess0 = fetch_hess(0);
+    if (tid < kBlk) max_s[tid] = 0u;
     {
         // every thread owns 4 consecutive samples of one component row per pass; all (splits + 2) 128-bit loads
-        // of a pass are issued before the first use so the phase runs at memory bandwidth, not latency
+        // of a pass are issued before the first use, and the loads of pass p + 1 are in flight while pass p is
+        // summed (two register buffers), so the phase runs at memory bandwidth, not latency
         constexpr int kSeedBatch = 8;
         const int c4 = tid % JG;
         const int64_t jc = static_cast<int64_t>(blockIdx.x) * TJ + 4 * c4;
         const bool full = vec && jc + 3 < cols;
-        for (int u = tid / JG; u < kp4; u += UG) {
+        int u_first = tid / JG;
+        if (full && num_splits <= kSeedBatch) {
+            struct Row { float4 fv, dv, b[kSeedBatch]; };
+            auto issue = [&](int u, Row& r) {
+                const int64_t uc = min(u, k - 1);          // padding rows (u >= k) load row k - 1 and store zeros
+                r.fv = *reinterpret_cast<const float4*>(f + uc * ld + jc);
+                r.dv = __ldcs(reinterpret_cast<const float4*>(den + uc * ld_part + jc));
+                const float* np = num + uc * ld_part + jc;
+#pragma unroll
+                for (int q = 0; q < kSeedBatch; ++q)
+                    if (q < num_splits) r.b[q] = __ldcs(reinterpret_cast<const float4*>(np + q * num_stride));
+            };
+            auto finish = [&](int u, const Row& r) {
+                float4 nv = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#pragma unroll
+                for (int q = 0; q < kSeedBatch; ++q)
+                    if (q < num_splits) { nv.x += r.b[q].x; nv.y += r.b[q].y; nv.z += r.b[q].z; nv.w += r.b[q].w; }
+                float4 gv;
+                gv.x = fmaf(l2, r.fv.x, r.dv.x) - (nv.x - l1);
+                gv.y = fmaf(l2, r.fv.y, r.dv.y) - (nv.y - l1);
+                gv.z = fmaf(l2, r.fv.z, r.dv.z) - (nv.z - l1);
+                gv.w = fmaf(l2, r.fv.w, r.dv.w) - (nv.w - l1);
+                if (u >= k) gv = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                *reinterpret_cast<float4*>(gs + u * TJ + 4 * c4) = gv;
+            };
+            Row ra, rb;
+            int u = u_first;
+            if (u < kp4) issue(u, ra);
+            while (u < kp4) {
+                const int u1 = u + UG;
+                if (u1 < kp4) issue(u1, rb);
+                finish(u, ra);
+                if (u1 >= kp4) break;
+                u = u1 + UG;
+                if (u < kp4) issue(u, ra);
+                finish(u1, rb);
+            }
+            u_first = kp4;                                 // nothing left for the generic loop below
+        }
+        for (int u = u_first; u < kp4; u += UG) {
             float4 gv = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
             if (u < k && full) {
                 const float4 fv = *reinterpret_cast<const float4*>(f + static_cast<int64_t>(u) * ld + jc);
@@ -116,16 +197,12 @@ cd_sweep_tile_kernel(float* __restrict__ f, int k, int64_t cols, int64_t ld, con
             *reinterpret_cast<float4*>(gs + u * TJ + 4 * c4) = gv;
         }
     }
-    // factor values of the block in flight; loads are unconditional (clamped indices) and zeroed afterwards so
-    // that the 16 of them are independent straight-line loads
+    // factor values of the block in flight: unconditional loads (clamped indices) whose predicates are applied
+    // where the values are used, so that the 16 of them are independent straight-line loads
     const int64_t jc_own = active ? j : 0;
-    const int u_own = min(tid, k - 1);
     float fl[kBlk];
-#pragma unroll
-    for (int i = 0; i < kBlk; ++i) {
-        const float v = f[static_cast<int64_t>(min(i, k - 1)) * ld + jc_own];
-        fl[i] = (active && i < k) ? v : 0.0f;
-    }
+    fetch_factor(0, jc_own, fl);
+    commit_rows(0, pre0, hess0);
     __syncthreads();
 
     float viol = 0.0f;
@@ -133,24 +210,30 @@ cd_sweep_tile_kernel(float* __restrict__ f, int k, int64_t cols, int64_t ld, con
     // one block of coordinate steps for sample `tid`; kFull: all 16 components exist (no bounds predicates)
     auto step_block = [&](auto full_tag, int t0, int nb) {
         constexpr bool kFull = decltype(full_tag)::value;
-        float gl[kBlk];
+        // The 16 steps form one dependent chain per thread (fn -> delta -> next gradient), ~5 FP32 operations per
+        // step.  Nothing else may sit on that chain: the deltas and new values stay in registers until the block
+        // is done (a shared-memory store inside the loop would pin every later G load behind it, and the warp
+        // reduction for the per-component maximum brings a branch), so the broadcast loads of G's diagonal block
+        // can be issued ahead of the arithmetic.
+        float gl[kBlk], dl[kBlk];
+        unsigned int fb[kBlk];
 #pragma unroll
         for (int i = 0; i < kBlk; ++i) gl[i] = (kFull || i < nb) ? gs[(t0 + i) * TJ + tid] : 0.0f;
         float* fp = f + static_cast<int64_t>(t0) * ld + jc_own;
 #pragma unroll
         for (int i = 0; i < kBlk; ++i) {
+            dl[i] = 0.0f;
+            fb[i] = 0u;
             if (kFull || i < nb) {
-                const float ft = fl[i];
+                const float ft = active ? fl[i] : 0.0f;
                 const float gt = gl[i];
                 viol += fabsf((ft == 0.0f) ? fminf(0.0f, gt) : gt);
                 const float inv = invh[i];
                 const float fn = fmaxf(fmaf(-gt, inv, ft), 0.0f);
                 const float delta = inv != 0.0f ? fn - ft : 0.0f;
-                if (active && delta != 0.0f) *fp = fn;
-                fp += ld;
-                // values are >= 0, so unsigned order == float order
-                const unsigned int vmax = __reduce_max_sync(0xffffffffu, active ? __float_as_uint(ft + delta) : 0u);
-                if ((tid & 31) == 0 && vmax != 0u) atomicMax(&max_s[i], vmax);
+                if (active && delta != 0.0f) fp[static_cast<int64_t>(i) * ld] = fn;
+                dl[i] = delta;
+                fb[i] = active ? __float_as_uint(ft + delta) : 0u;   // values are >= 0: unsigned order == float order
                 // row i of the diagonal block of G, columns i+1..15, as 128-bit broadcast loads
                 const float4* grow4 = reinterpret_cast<const float4*>(gb + i * kp4 + t0);
                 float grow[kBlk];
@@ -162,8 +245,20 @@ cd_sweep_tile_kernel(float* __restrict__ f, int k, int64_t cols, int64_t ld, con
 #pragma unroll
                 for (int i2 = i + 1; i2 < kBlk; ++i2)
                     if (kFull || i2 < nb) gl[i2] = fmaf(delta, grow[i2], gl[i2]);
-                gs[(t0 + i) * TJ + tid] = delta;           // the gradient row is dead: it now carries the deltas
             }
+        }
+        // the gradient rows of the block are dead: they now carry the deltas for the apply phase
+#pragma unroll
+        for (int i = 0; i < kBlk; ++i)
+            if (kFull || i < nb) gs[(t0 + i) * TJ + tid] = dl[i];
+        // per-component maxima for the plane split: 16 independent warp reductions, one shared atomic per warp
+        unsigned int vmax[kBlk];
+#pragma unroll
+        for (int i = 0; i < kBlk; ++i) vmax[i] = __reduce_max_sync(0xffffffffu, fb[i]);
+        if ((tid & 31) == 0) {
+#pragma unroll
+            for (int i = 0; i < kBlk; ++i)
+                if (vmax[i] != 0u) atomicMax(&max_s[i], vmax[i]);
         }
     };
     for (int t0 = 0; t0 < k; t0 += kBlk) {
@@ -178,19 +273,9 @@ cd_sweep_tile_kernel(float* __restrict__ f, int k, int64_t cols, int64_t ld, con
         float pre[kBlk];                                   // column `tid` of the next block's G rows
         float hess_next = 0.0f;
         if (more) {
-#pragma unroll
-            for (int i = 0; i < kBlk; ++i) {
-                const int t = t0 + kBlk + i;
-                const float v = __ldg(gram + static_cast<int64_t>(min(t, k - 1)) * ldg + u_own);
-                pre[i] = (t < k && tid < k) ? v : 0.0f;
-            }
-            hess_next = load_hess(t0 + kBlk);
-#pragma unroll
-            for (int i = 0; i < kBlk; ++i) {
-                const int t = t0 + kBlk + i;
-                const float v = f[static_cast<int64_t>(min(t, k - 1)) * ld + jc_own];
-                fl[i] = (active && t < k) ? v : 0.0f;
-            }
+            fetch_rows(t0 + kBlk, pre);
+            hess_next = fetch_hess(t0 + kBlk);
+            fetch_factor(t0 + kBlk, jc_own, fl);
         }
         __syncthreads();
         if (tid < kBlk) {
@@ -223,29 +308,7 @@ cd_sweep_tile_kernel(float* __restrict__ f, int k, int64_t cols, int64_t ld, con
         }
         __syncthreads();
         // ---- next block's G rows / hessians into shared memory --------------------------------------------
-        if (tid < kp4) {
-#pragma unroll
-            for (int i = 0; i < kBlk; ++i) gb[i * kp4 + tid] = pre[i];
-        }
-        if (kp4 > NT) {
-            // columns the register prefetch does not cover (k > NT): 16 independent clamped loads per pass, not
-            // 16 dependent round trips to L2
-            for (int base = NT; base < kp4; base += NT) {
-                const int u = base + tid, uc = min(u, k - 1);
-                float ov[kBlk];
-#pragma unroll
-                for (int i = 0; i < kBlk; ++i) {
-                    const int t = t0 + kBlk + i;
-                    const float v = __ldg(gram + static_cast<int64_t>(min(t, k - 1)) * ldg + uc);
-                    ov[i] = (t < k && u < k) ? v : 0.0f;
-                }
-                if (u < kp4) {
-#pragma unroll
-                    for (int i = 0; i < kBlk; ++i) gb[i * kp4 + u] = ov[i];
-                }
-            }
-        }
-        if (tid < kBlk) invh[tid] = hess_next != 0.0f ? 1.0f / hess_next : 0.0f;
+        commit_rows(t0 + kBlk, pre, hess_next);
         __syncthreads();
     }
     const double total = block_sum(active ? static_cast<double>(viol) : 0.0, scratch);

@@ -92,6 +92,18 @@ int transpose_f64_to_f32(const double* in, int64_t rows, int64_t cols, int64_t l
 int transpose_f64(const double* in, int64_t rows, int64_t cols, int64_t ld_in, double* out, int64_t ld_out,
                   cudaStream_t stream);
 
+// ---- postops.cu -----------------------------------------------------------------------------------
+// Component maps, component-major [k, ld].  stats: device scratch of 4 * k * n_groups doubles.
+// x[t][j] = 0 where x[t][j] < mean + z * std of { x[t][j'] : gid[j'] == gid[j] }  (gid == nullptr: one group);
+// samples whose group id is outside [0, n_groups) are left untouched.
+template <typename T>
+int comp_threshold(T* x, int64_t k, int64_t len, int64_t ld, const int* gid, int n_groups, double z, double* stats,
+                   cudaStream_t stream);
+// out[t][:] = StandardScaler over the samples of component t (population std, constant components -> scale 1)
+template <typename T>
+int comp_standardize(const T* x, int64_t k, int64_t len, int64_t ld, T* out, int64_t ld_out, double* stats,
+                     cudaStream_t stream);
+
 // ---- p2p.cu ---------------------------------------------------------------------------------------
 // Row-sharded H half-step over NVLink peer memory (CUDA IPC mappings of every rank's arena and H master).
 constexpr int kP2pMaxWorld = 8;

@@ -1097,8 +1097,9 @@ int nfb_host_alloc(int64_t bytes, void** out) {
     const size_t size = std::max<size_t>(static_cast<size_t>(bytes), 64);
     {
         std::lock_guard<std::mutex> lock(g_pin_mutex);
-        auto it = g_pin_free.find(size);
-        if (it != g_pin_free.end()) {
+        auto range = g_pin_free.equal_range(size);
+        if (range.first != range.second) {
+            auto it = std::prev(range.second);         // most recently freed block of this size (its pages are warm)
             *out = it->second;
             g_pin_idle_bytes -= size;
             g_pin_free.erase(it);
@@ -1137,7 +1138,17 @@ int nfb_host_free(void* p) {
 
 int nfb_dual_regression_host(nfb_handle* h, const nfb_matrix* x, int k, const void* g_host, int g_is_f32,
                              double* gs_out, double* hs_out, int* n_unconverged_out, int* g_nonfinite_out) {
+    return nfb_dual_regression_post_host(h, x, k, g_host, g_is_f32, 0.0, nullptr, 0, gs_out, hs_out, nullptr, nullptr,
+                                         n_unconverged_out, g_nonfinite_out);
+}
+
+int nfb_dual_regression_post_host(nfb_handle* h, const nfb_matrix* x, int k, const void* g_host, int g_is_f32,
+                                  double zscore, const int32_t* seed_id_host, int n_seeds, double* gs_out,
+                                  double* hs_out, double* gs_norm_out, double* hs_norm_out, int* n_unconverged_out,
+                                  int* g_nonfinite_out) {
     NFB_CHECK(h != nullptr && x != nullptr && g_host != nullptr, "NULL argument");
+    NFB_CHECK(zscore == 0.0 || (seed_id_host != nullptr && n_seeds >= 1 && n_seeds <= 4096),
+              "thresholding needs the seed index of every row and 1..4096 seeds");
     NFB_CHECK(k >= 1 && k <= 512, "n_components must be in [1, 512] in this build");
     NFB_CUDA(cudaSetDevice(h->device));
     cudaStream_t st = h->stream;
@@ -1181,21 +1192,42 @@ int nfb_dual_regression_host(nfb_handle* h, const nfb_matrix* x, int k, const vo
                               400, h->d_int.p, st, reinterpret_cast<unsigned long long*>(h->d_scal.p + 8),
                               reinterpret_cast<unsigned long long*>(h->d_scal.p + 10)));
     }
-    // the white components can travel while stage 2 runs
-    cudaEvent_t hs_ready = nullptr;
-    if (hs_out) {
-        NFB_CUDA(cudaEventCreateWithFlags(&hs_ready, cudaEventDisableTiming));
-        NFB_CUDA(cudaEventRecord(hs_ready, st));
-        NFB_CUDA(cudaStreamWaitEvent(h->copy_stream, hs_ready, 0));
-        NFB_CUDA(cudaMemcpy2DAsync(hs_out, n * sizeof(double), sol_h.p, hs.ld * sizeof(double), n * sizeof(double), k,
-                                   cudaMemcpyDeviceToHost, h->copy_stream));
-    }
-    // ---- stage 2: grey matter.  Gs[i, :] = nnls(Hs, X[i, :])    (dual_regression_methods.py:151-163)
+    // ---- stage 2 operand: the (un-thresholded) white components as float32 planes ----------------------
     { NFB_PHASE(h, "planes2");
     NFB_CUDA(cudaMemsetAsync(hs.rowmax.p, 0, sizeof(unsigned int) * kp, st));
     NFB_TRY(f64_to_f32_rowmax(sol_h.p, k, n, hs.ld, hs.f.p, hs.ld, hs.rowmax.p, st));
     NFB_TRY(refresh_planes(hs, hs.f.p, nullptr, false, st));
     }
+    // post-processing of the white components (thresholding_components / normalise_components,
+    // NFACT/base/matrix_handling.py:241-277, 45-68) while they are still resident; sol_h is not read again
+    const bool post = zscore != 0.0;
+    DevBuf<double> stats, norm;
+    DevBuf<int> seed_dev;
+    if (post || hs_norm_out || gs_norm_out) {
+        NFB_TRY(stats.alloc(static_cast<size_t>(4) * k * std::max(1, n_seeds), false, st));
+        if (hs_norm_out || gs_norm_out) NFB_TRY(norm.alloc(static_cast<size_t>(k) * std::max(hs.ld, gt.ld), false, st));
+    }
+    { NFB_PHASE(h, "post_h");
+    if (post) NFB_TRY(comp_threshold<double>(sol_h.p, k, n, hs.ld, nullptr, 1, zscore, stats.p, st));
+    if (hs_norm_out) NFB_TRY(comp_standardize<double>(sol_h.p, k, n, hs.ld, norm.p, hs.ld, stats.p, st));
+    }
+    // the white components can travel while stage 2 runs
+    cudaEvent_t hs_ready = nullptr;
+    if (hs_out || hs_norm_out) {
+        NFB_CUDA(cudaEventCreateWithFlags(&hs_ready, cudaEventDisableTiming));
+        NFB_CUDA(cudaEventRecord(hs_ready, st));
+        NFB_CUDA(cudaStreamWaitEvent(h->copy_stream, hs_ready, 0));
+        if (hs_out)
+            NFB_CUDA(cudaMemcpy2DAsync(hs_out, n * sizeof(double), sol_h.p, hs.ld * sizeof(double), n * sizeof(double),
+                                       k, cudaMemcpyDeviceToHost, h->copy_stream));
+        if (hs_norm_out) {
+            NFB_CUDA(cudaMemcpy2DAsync(hs_norm_out, n * sizeof(double), norm.p, hs.ld * sizeof(double),
+                                       n * sizeof(double), k, cudaMemcpyDeviceToHost, h->copy_stream));
+            // the scratch is reused for the grey components: stage 2's post-processing waits for this copy
+            NFB_CUDA(cudaEventRecord(hs_ready, h->copy_stream));
+        }
+    }
+    // ---- stage 2: grey matter.  Gs[i, :] = nnls(Hs, X[i, :])    (dual_regression_methods.py:151-163)
     { NFB_PHASE(h, "gram2"); NFB_TRY(gram_f64(hs.f.p, k, n, hs.ld, gram64.p, st)); }
     { NFB_PHASE(h, "gemm_xhst");
     NFB_TRY(gemm_split(x->operand(), false, hs.operand(), m, n, static_cast<int>(kp), k, part.p, gt.ld, s2,
@@ -1207,10 +1239,24 @@ int nfb_dual_regression_host(nfb_handle* h, const nfb_matrix* x, int k, const vo
                               reinterpret_cast<unsigned long long*>(h->d_scal.p + 10)));
     }
     // ---- results -------------------------------------------------------------------------------------
+    { NFB_PHASE(h, "post_g");
+    if (post) {
+        // threshold_grey_components: statistics per (component, seed); rows of no listed seed stay as they are
+        NFB_TRY(seed_dev.alloc(static_cast<size_t>(m), false, st));
+        NFB_CUDA(cudaMemcpyAsync(seed_dev.p, seed_id_host, sizeof(int) * m, cudaMemcpyHostToDevice, st));
+        NFB_TRY(comp_threshold<double>(sol_g.p, k, m, gt.ld, seed_dev.p, n_seeds, zscore, stats.p, st));
+    }
+    }
     { NFB_PHASE(h, "d2h");
     if (gs_out) {
         NFB_TRY(transpose_f64(sol_g.p, k, m, gt.ld, g64.p, k, st));
         NFB_CUDA(cudaMemcpyAsync(gs_out, g64.p, sizeof(double) * m * k, cudaMemcpyDeviceToHost, st));
+    }
+    if (gs_norm_out) {
+        if (hs_norm_out) NFB_CUDA(cudaStreamWaitEvent(st, hs_ready, 0));
+        NFB_TRY(comp_standardize<double>(sol_g.p, k, m, gt.ld, norm.p, gt.ld, stats.p, st));
+        NFB_TRY(transpose_f64(norm.p, k, m, gt.ld, g64.p, k, st));   // ordered after the gs_out copy on the stream
+        NFB_CUDA(cudaMemcpyAsync(gs_norm_out, g64.p, sizeof(double) * m * k, cudaMemcpyDeviceToHost, st));
     }
     }
     int status[3] = {0, 0, 0};
@@ -1231,6 +1277,78 @@ int nfb_dual_regression_host(nfb_handle* h, const nfb_matrix* x, int k, const vo
                 static_cast<long long>(m), k);
     }
     return 0;
+}
+
+// ---- post-processing of component maps given as host arrays ------------------------------------------
+}  // extern "C"
+
+template <typename T>
+static int component_postops(nfb_handle* h, T* data, int comp_major, int64_t k, int64_t len, const int32_t* group_id,
+                             int n_groups, int do_threshold, double zscore, T* norm_out) {
+    cudaStream_t st = h->stream;
+    const int64_t ld = round_up64(len, 8);
+    const int groups = group_id ? n_groups : 1;
+    DevBuf<T> raw, cm, norm;
+    DevBuf<double> stats;
+    DevBuf<int> gid;
+    NFB_TRY(cm.alloc(static_cast<size_t>(k) * ld, false, st));
+    NFB_TRY(stats.alloc(static_cast<size_t>(4) * k * groups, false, st));
+    auto transpose = [&](const T* in, int64_t rows, int64_t cols, int64_t ld_in, T* out, int64_t ld_out) -> int {
+        if constexpr (sizeof(T) == 8) return transpose_f64(in, rows, cols, ld_in, out, ld_out, st);
+        else return transpose_f32(in, rows, cols, ld_in, out, ld_out, st);
+    };
+    if (comp_major) {
+        NFB_CUDA(cudaMemcpy2DAsync(cm.p, ld * sizeof(T), data, len * sizeof(T), len * sizeof(T), k,
+                                   cudaMemcpyHostToDevice, st));
+    } else {   // [len, k] on the host (grey components): component-major on the device
+        NFB_TRY(raw.alloc(static_cast<size_t>(k) * len, false, st));
+        NFB_CUDA(cudaMemcpyAsync(raw.p, data, sizeof(T) * k * len, cudaMemcpyHostToDevice, st));
+        NFB_TRY(transpose(raw.p, len, k, k, cm.p, ld));
+    }
+    if (do_threshold) {
+        if (group_id) {
+            NFB_TRY(gid.alloc(static_cast<size_t>(len), false, st));
+            NFB_CUDA(cudaMemcpyAsync(gid.p, group_id, sizeof(int) * len, cudaMemcpyHostToDevice, st));
+        }
+        NFB_TRY(comp_threshold<T>(cm.p, k, len, ld, group_id ? gid.p : nullptr, groups, zscore, stats.p, st));
+        if (comp_major) {
+            NFB_CUDA(cudaMemcpy2DAsync(data, len * sizeof(T), cm.p, ld * sizeof(T), len * sizeof(T), k,
+                                       cudaMemcpyDeviceToHost, st));
+        } else {
+            NFB_TRY(transpose(cm.p, k, len, ld, raw.p, k));
+            NFB_CUDA(cudaMemcpyAsync(data, raw.p, sizeof(T) * k * len, cudaMemcpyDeviceToHost, st));
+        }
+    }
+    if (norm_out) {
+        NFB_TRY(norm.alloc(static_cast<size_t>(k) * ld, false, st));
+        NFB_TRY(comp_standardize<T>(cm.p, k, len, ld, norm.p, ld, stats.p, st));
+        if (comp_major) {
+            NFB_CUDA(cudaMemcpy2DAsync(norm_out, len * sizeof(T), norm.p, ld * sizeof(T), len * sizeof(T), k,
+                                       cudaMemcpyDeviceToHost, st));
+        } else {
+            NFB_TRY(transpose(norm.p, k, len, ld, raw.p, k));
+            NFB_CUDA(cudaMemcpyAsync(norm_out, raw.p, sizeof(T) * k * len, cudaMemcpyDeviceToHost, st));
+        }
+    }
+    NFB_CUDA(cudaStreamSynchronize(st));
+    note_launch(4);
+    return 0;
+}
+
+extern "C" {
+
+int nfb_component_postops_host(nfb_handle* h, void* data, int is_f64, int comp_major, int64_t k, int64_t len,
+                               const int32_t* group_id, int n_groups, int do_threshold, double zscore,
+                               void* norm_out) {
+    NFB_CHECK(h != nullptr && (data != nullptr || k * len == 0) && k >= 0 && len >= 0, "bad nfb_component_postops_host arguments");
+    NFB_CHECK(group_id == nullptr || (n_groups >= 1 && n_groups <= 4096), "n_groups must be in [1, 4096]");
+    NFB_CUDA(cudaSetDevice(h->device));
+    if (k * len == 0) return 0;
+    if (is_f64)
+        return component_postops<double>(h, static_cast<double*>(data), comp_major, k, len, group_id, n_groups,
+                                         do_threshold, zscore, static_cast<double*>(norm_out));
+    return component_postops<float>(h, static_cast<float*>(data), comp_major, k, len, group_id, n_groups, do_threshold,
+                                    zscore, static_cast<float*>(norm_out));
 }
 
 // ---- ingest ----------------------------------------------------------------------------------------

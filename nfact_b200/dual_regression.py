@@ -16,12 +16,17 @@ from .device import DeviceMatrix
 from .utils import error_and_exit
 
 
-def nmf_dual_regression(components: dict, connectivity_matrix, n_jobs: int = 1) -> dict:
+def nmf_dual_regression(components: dict, connectivity_matrix, n_jobs: int = 1, *, threshold: float = 0,
+                        seeds_id=None, n_seeds: int = 0, normalise: bool = False) -> dict:
     """NFACT/dual_reg/dual_regression/dual_regression_methods.py:92-116.
 
     ``n_jobs`` is accepted for signature compatibility; the device solves all columns at once.
     Returns float64 arrays {"grey_components": [m,k], "white_components": [k,n]} like the reference.
-    """
+
+    Keyword extras (not in the reference's signature; ``dual_regression_subject`` uses them): the per-subject
+    post-processing the pipeline runs next (run_dual_regression.py:166-186) applied on the device before the
+    results are copied out -- ``threshold`` != 0: ``thresholding_components`` with ``seeds_id`` (the seed index of
+    every row) and ``n_seeds``; ``normalise``: adds "normalised_grey" / "normalised_white"."""
     grey = np.asarray(components["grey_components"])
     if grey.dtype != np.float32:          # scipy's nnls casts everything else to float64
         grey = grey.astype(np.float64, copy=False)
@@ -32,6 +37,7 @@ def nmf_dual_regression(components: dict, connectivity_matrix, n_jobs: int = 1) 
         xdev, owns = connectivity_matrix, False
     else:
         xdev, owns = DeviceMatrix.from_host(np.asarray(connectivity_matrix)), True
+    out = {}
     try:
         if xdev.has_nonfinite:
             raise ValueError("array must not contain infs or NaNs")
@@ -42,18 +48,31 @@ def nmf_dual_regression(components: dict, connectivity_matrix, n_jobs: int = 1) 
         k = grey.shape[1]
         gs = pinned_empty((m, k), np.float64)
         hs = pinned_empty((k, n), np.float64)
+        gs_norm = pinned_empty((m, k), np.float64) if normalise else None
+        hs_norm = pinned_empty((k, n), np.float64) if normalise else None
+        seed_arr = None
+        if threshold:
+            seed_arr = np.ascontiguousarray(np.zeros(m) if seeds_id is None else seeds_id, dtype=np.int32)
+            if seed_arr.shape != (m,):
+                raise ValueError(f"seeds_id has shape {seed_arr.shape}, expected {(m,)}")
+            n_seeds = int(n_seeds) if seeds_id is not None else 1
         bad, nonfinite = c_int(), c_int()
         h = xdev.handle
-        check(h.lib.nfb_dual_regression_host(h.ptr, xdev.ptr, k, grey.ctypes.data, int(grey.dtype == np.float32),
-                                             gs.ctypes.data, hs.ctypes.data, byref(bad), byref(nonfinite)))
+        check(h.lib.nfb_dual_regression_post_host(
+            h.ptr, xdev.ptr, k, grey.ctypes.data, int(grey.dtype == np.float32), float(threshold),
+            seed_arr.ctypes.data if seed_arr is not None else None, int(n_seeds), gs.ctypes.data, hs.ctypes.data,
+            gs_norm.ctypes.data if normalise else None, hs_norm.ctypes.data if normalise else None,
+            byref(bad), byref(nonfinite)))
         if nonfinite.value:               # checked on the device while G is transposed
             raise ValueError("array must not contain infs or NaNs")
         if bad.value:
             raise RuntimeError("Maximum number of iterations reached.")
+        if normalise:
+            out = {"normalised_grey": gs_norm, "normalised_white": hs_norm}
     finally:
         if owns:
             xdev.free()
-    return {"grey_components": gs, "white_components": hs}
+    return {"grey_components": gs, "white_components": hs, **out}
 
 
 def run_decomp(decomp, components: dict, connectivity_matrix, parallel: int = None) -> dict:
@@ -73,16 +92,22 @@ def _subject_matrix_file(fdt_path: str):
                  if os.path.exists(os.path.join(fdt_path, fname))), None)
 
 
-def _postprocess_subject(fdt_path: str, dr_results: dict, seeds: list, threshold: int, normalise: bool) -> dict:
+def _postprocess_options(fdt_path: str, seeds: list, threshold: int, normalise: bool) -> dict:
+    """Keyword arguments that make ``nmf_dual_regression`` run ``thresholding_components`` (seed index of every
+    row = second-to-last column of ``coords_for_fdt_matrix2``, NFACT/base/matrix_handling.py:205) and
+    ``normalise_components`` on the device."""
     import os
-    from .matrix_handling import normalise_components, thresholding_components
-    dr_results = thresholding_components(int(threshold), os.path.join(fdt_path, "coords_for_fdt_matrix2"), seeds,
-                                         dr_results)
+    from .utils import colours, nprint
+    col = colours()
+    shown = int(threshold) if int(threshold) != 0 else "Not thresholding"
+    nprint(f"{col['pink']}Thresholding value:{col['reset']} {shown}\n")
+    options = {"normalise": bool(normalise)}
+    if int(threshold) != 0:
+        seeds_id = np.loadtxt(os.path.join(fdt_path, "coords_for_fdt_matrix2"), dtype=int)[:, -2]
+        options.update(threshold=int(threshold), seeds_id=seeds_id, n_seeds=len(seeds))
     if normalise:
-        normalised = normalise_components(dr_results["grey_components"], dr_results["white_components"])
-        dr_results["normalised_white"] = normalised["white_matter"]
-        dr_results["normalised_grey"] = normalised["grey_matter"]
-    return dr_results
+        nprint(f"{col['pink']}Normalising:{col['reset']} Components")
+    return options
 
 
 def dual_regression_subject(fdt_path: str, components: dict, seeds: list, threshold: int = 3,
@@ -99,21 +124,25 @@ def dual_regression_subject(fdt_path: str, components: dict, seeds: list, thresh
             matrix = load_fdt_matrix(_subject_matrix_file(fdt_path), resident=True)   # stays in HBM
         except Exception:
             error_and_exit(False, f"Unable to load {os.path.basename(os.path.normpath(fdt_path))} fdt matrix")
+    options = _postprocess_options(fdt_path, seeds, threshold, normalise)
     try:
-        dr_results = run_decomp(nmf_dual_regression, components, matrix, parallel)
+        return run_decomp(lambda comp, mat, par: nmf_dual_regression(comp, mat, par, **options), components, matrix,
+                          parallel)
     finally:
         if owns:
             matrix.free()
-    return _postprocess_subject(fdt_path, dr_results, seeds, threshold, normalise)
 
 
-def stream_subjects(load_matrix, n_subjects: int, components: dict, device: int | None = None, prefetch: bool = True):
+def stream_subjects(load_matrix, n_subjects: int, components: dict, device: int | None = None, prefetch: bool = True,
+                    options=None):
     """Generator over ``(index, dual-regression result)`` for subjects ``0 .. n_subjects-1``.
 
     ``load_matrix(index, handle) -> DeviceMatrix`` makes subject ``index`` resident using ``handle``.  With
     ``prefetch`` the next subject is loaded (file parse, triplet upload, scatter-add ingest, plane split) by a
     background thread on a second handle -- its own CUDA stream -- while the current subject's regression
-    runs, so a subject costs max(load, solve) instead of their sum; two subjects are resident at a time."""
+    runs, so a subject costs max(load, solve) instead of their sum; two subjects are resident at a time.
+    ``options(index) -> dict``: per-subject keyword arguments for ``nmf_dual_regression`` (post-processing)."""
+    options = options or (lambda idx: {})
     from concurrent.futures import ThreadPoolExecutor
     from .device import Handle, get_handle
     first = get_handle(device)
@@ -123,7 +152,7 @@ def stream_subjects(load_matrix, n_subjects: int, components: dict, device: int 
             for idx in range(n_subjects):
                 xdev = load_matrix(idx, first)
                 try:
-                    yield idx, nmf_dual_regression(components, xdev)
+                    yield idx, nmf_dual_regression(components, xdev, **options(idx))
                 finally:
                     xdev.free()
             return
@@ -134,7 +163,7 @@ def stream_subjects(load_matrix, n_subjects: int, components: dict, device: int 
                 if idx + 1 < n_subjects:
                     pending = pool.submit(load_matrix, idx + 1, handles[(idx + 1) % 2])
                 try:
-                    result = nmf_dual_regression(components, xdev)   # runs on the stream that loaded xdev
+                    result = nmf_dual_regression(components, xdev, **options(idx))   # on the stream that loaded xdev
                 finally:
                     xdev.free()
                 yield idx, result
@@ -162,8 +191,8 @@ def run_locally(list_of_subject_dirs: list, components: dict, seeds: list, thres
 
     out = {}
     try:
-        for idx, dr_results in stream_subjects(load, len(mine), components, prefetch=prefetch):
-            dr_results = _postprocess_subject(mine[idx], dr_results, seeds, threshold, normalise)
+        options = lambda idx: _postprocess_options(mine[idx], seeds, threshold, normalise)   # noqa: E731
+        for idx, dr_results in stream_subjects(load, len(mine), components, prefetch=prefetch, options=options):
             if save is not None:
                 save(mine[idx], dr_results)
             out[mine[idx]] = dr_results

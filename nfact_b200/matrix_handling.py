@@ -183,37 +183,70 @@ def save_matrix(matrix: np.ndarray, directory: str, matrix_name: str) -> None:
         error_and_exit(False, f"Unable to save matrix due to {e}")
 
 
+def _component_postops(data: np.ndarray, comp_major: bool, group_id=None, n_groups: int = 0, threshold: bool = False,
+                       zscore: float = 0.0, normalise: bool = False):
+    """``nfb_component_postops_host``: z-threshold ``data`` in place and / or return its z-scored copy.
+    ``data`` must be a C-contiguous float32 / float64 2-D array ([k, len] when ``comp_major`` else [len, k])."""
+    from ctypes import c_void_p
+    from . import _lib
+    handle = device.get_handle()
+    k, length = data.shape if comp_major else data.shape[::-1]
+    gid = None if group_id is None else np.ascontiguousarray(group_id, dtype=np.int32)
+    if gid is not None and gid.shape != (length,):
+        raise ValueError(f"group ids have shape {gid.shape}, expected {(length,)}")
+    norm = np.empty_like(data) if normalise else None
+    _lib.check(handle.lib.nfb_component_postops_host(
+        handle.ptr, c_void_p(data.ctypes.data), int(data.dtype == np.float64), int(comp_major), k, length,
+        None if gid is None else c_void_p(gid.ctypes.data), int(n_groups), int(threshold), float(zscore),
+        None if norm is None else c_void_p(norm.ctypes.data)))
+    return norm
+
+
+def _device_ready(arr: np.ndarray) -> bool:
+    """The kernels take float32 / float64 C-contiguous 2-D arrays; other inputs are converted by the callers."""
+    return arr.ndim == 2 and arr.dtype in (np.float32, np.float64) and arr.flags.c_contiguous and arr.flags.writeable
+
+
 def thresholding(component: np.ndarray, zscore_val) -> np.ndarray:
-    """NFACT/base/matrix_handling.py:218-238 (in place; elementwise post-op after the D2H copy)."""
-    for comp in range(component.shape[0]):
-        tract = component[comp, :]
-        threshold = tract.mean() + (zscore_val * tract.std())
-        tract[tract < threshold] = 0.0
+    """NFACT/base/matrix_handling.py:218-238: entries below ``mean + zscore_val * std`` of their component (row)
+    are zeroed IN PLACE, on the device (float64 statistics)."""
+    if component.size == 0:
+        return component
+    if _device_ready(component):
+        _component_postops(component, True, threshold=True, zscore=zscore_val)
+        return component
+    work = np.ascontiguousarray(component, dtype=np.float64 if component.dtype != np.float32 else np.float32)
+    _component_postops(work, True, threshold=True, zscore=zscore_val)
+    component[...] = work           # non-contiguous view (e.g. per_seed = comps[rows].T in the reference) or other dtype
     return component
 
 
 def normalise_components(grey_matter: np.ndarray, white_matter: np.ndarray) -> dict:
-    """NFACT/base/matrix_handling.py:45-68 (StandardScaler semantics: population std, zero std -> 1)."""
-    def zscore_cols(arr):
-        arr64 = arr.astype(np.float64)
-        mean = arr64.mean(axis=0)
-        std = arr64.std(axis=0)
-        std[std < 10 * np.finfo(np.float64).eps] = 1.0
-        return ((arr64 - mean) / std).astype(arr.dtype)
+    """NFACT/base/matrix_handling.py:45-68 (StandardScaler semantics: population std, constant component ->
+    scale 1), on the device; returns new arrays of the inputs' dtype."""
+    def zscore(arr, comp_major):
+        arr = np.ascontiguousarray(arr, dtype=np.float32 if arr.dtype == np.float32 else np.float64)
+        if arr.size == 0:
+            return arr.copy()
+        return _component_postops(arr, comp_major, normalise=True)
     col = colours()
     nprint(f"{col['pink']}Normalising:{col['reset']} Components")
-    return {"grey_matter": zscore_cols(grey_matter), "white_matter": zscore_cols(white_matter.T).T}
+    return {"grey_matter": zscore(grey_matter, False), "white_matter": zscore(white_matter, True)}
 
 
 def threshold_grey_components(components: np.ndarray, coord_path: str, seeds: list, zscore_val) -> np.ndarray:
     """NFACT/base/matrix_handling.py:184-215: z-threshold the grey components separately for every seed
-    (the seed index of each row is the second-to-last column of ``coords_for_fdt_matrix2``)."""
+    (the seed index of each row is the second-to-last column of ``coords_for_fdt_matrix2``); one device pass
+    with per-(component, seed) statistics, in place."""
     seeds_id = np.loadtxt(coord_path, dtype=int)[:, -2]
-    for idx, _ in enumerate(seeds):
-        rows_of_seed = seeds_id == idx
-        per_seed = components[rows_of_seed, :].T
-        thresholding(per_seed, zscore_val)
-        components[rows_of_seed, :] = per_seed.T
+    if components.size == 0 or len(seeds) == 0:
+        return components
+    if _device_ready(components):
+        _component_postops(components, False, seeds_id, len(seeds), threshold=True, zscore=zscore_val)
+        return components
+    work = np.ascontiguousarray(components, dtype=np.float64 if components.dtype != np.float32 else np.float32)
+    _component_postops(work, False, seeds_id, len(seeds), threshold=True, zscore=zscore_val)
+    components[...] = work
     return components
 
 

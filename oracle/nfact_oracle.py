@@ -405,6 +405,26 @@ def normalise_components(grey: np.ndarray, white: np.ndarray) -> dict:
     return {"grey_matter": zscore_cols(grey), "white_matter": zscore_cols(white.T).T}
 
 
+def threshold_grey_components(components: np.ndarray, seeds_id: np.ndarray, n_seeds: int, zscore_val) -> np.ndarray:
+    """NFACT/base/matrix_handling.py:184-215: ``thresholding`` of the rows of every seed separately, in place
+    (``seeds_id`` = second-to-last column of coords_for_fdt_matrix2; the reference loops ``enumerate(seeds)``)."""
+    for idx in range(n_seeds):
+        rows = seeds_id == idx
+        per_seed = components[rows, :].T
+        thresholding(per_seed, zscore_val)
+        components[rows, :] = per_seed.T
+    return components
+
+
+def thresholding_components(threshold_val: int, seeds_id: np.ndarray, n_seeds: int, components: dict) -> dict:
+    """NFACT/base/matrix_handling.py:241-277."""
+    if threshold_val != 0:
+        components["white_components"] = thresholding(components["white_components"], threshold_val)
+        components["grey_components"] = threshold_grey_components(components["grey_components"], seeds_id, n_seeds,
+                                                                  threshold_val)
+    return components
+
+
 # --------------------------------------------------------------------------------------
 # a15  non-negative dual regression
 # --------------------------------------------------------------------------------------

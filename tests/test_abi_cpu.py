@@ -68,14 +68,6 @@ def test_host_parsing_matches_oracle(golden_subjects):
     assert coo.scale == 1e8 / 15000000.0
 
 
-def test_postops_match_reference(golden):
-    import nfact_b200
-    norm = nfact_b200.normalise_components(golden["cd_fit_W"].copy(), golden["cd_fit_H"].copy())
-    assert np.allclose(norm["grey_matter"], golden["norm_grey"], rtol=1e-5, atol=1e-6)
-    assert np.allclose(norm["white_matter"], golden["norm_white"], rtol=1e-5, atol=1e-6)
-    assert np.array_equal(nfact_b200.thresholding(golden["cd_fit_H"].copy(), 3), golden["thresh_white_3"])
-
-
 def test_parameter_validation():
     import nfact_b200
     with pytest.raises(TypeError):

@@ -134,3 +134,28 @@ def test_dual_regression(golden):
     dr2 = orc.nmf_dual_regression({"grey_components": golden["mu_fit_W"]}, golden["ingest_single_2"])
     assert rel_fro(dr2["grey_components"], golden["dr2_grey"]) < 1e-8
     assert rel_fro(dr2["white_components"], golden["dr2_white"]) < 1e-8
+
+
+def test_oracle_postops_match_reference():
+    """a14: the oracle's thresholding / threshold_grey_components / thresholding_components / normalise_components
+    against outputs of the reference's own functions (tests/golden/make_golden_postops.py)."""
+    import os
+    from conftest import GOLDEN_DIR
+    from oracle import nfact_oracle as orc
+    g = dict(np.load(os.path.join(GOLDEN_DIR, "golden_postops.npz")))
+    seeds_id, n_seeds = g["seeds_id"], int(g["n_seeds"])
+    for tag in ("f32", "f64"):
+        grey, white = g[f"grey_{tag}"], g[f"white_{tag}"]
+        for z in (1, 3):
+            assert np.array_equal(orc.thresholding(white.copy(), z), g[f"white_thr{z}_{tag}"])
+            assert np.array_equal(orc.threshold_grey_components(grey.copy(), seeds_id, n_seeds, z),
+                                  g[f"grey_thr{z}_{tag}"])
+        comps = orc.thresholding_components(2, seeds_id, n_seeds, {"grey_components": grey.copy(),
+                                                                   "white_components": white.copy()})
+        assert np.array_equal(comps["grey_components"], g[f"grey_thr2_{tag}"])
+        assert np.array_equal(comps["white_components"], g[f"white_thr2_{tag}"])
+        norm = orc.normalise_components(grey.copy(), white.copy())
+        tol = dict(rtol=2e-6, atol=2e-6) if tag == "f32" else dict(rtol=1e-12, atol=1e-12)
+        assert np.allclose(norm["grey_matter"], g[f"grey_norm_{tag}"], **tol)
+        assert np.allclose(norm["white_matter"], g[f"white_norm_{tag}"], **tol)
+        assert norm["grey_matter"].dtype == grey.dtype
