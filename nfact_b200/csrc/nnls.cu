@@ -116,12 +116,15 @@ nnls_cd_kernel(const double* __restrict__ gram, int k, const float* __restrict__
 // coordinate step has its slot (register index) as a compile-time constant, multiplies by a precomputed
 // 1/G[t][t] and reads row/column t of G from shared memory.
 
+constexpr int kInitialSweeps = 6;          // Gauss-Seidel passes before the first CG phase
+constexpr double kFaceReduction = 1e-2;    // residual reduction asked of one CG phase
+
 template <int KPL, int kNnlsWarps>
 __global__ void __launch_bounds__(kNnlsWarps * 32, 1)
 nnls_smem_kernel(const double* __restrict__ gram, int k, const float* __restrict__ rhs, int rhs_splits,
                  int64_t rhs_stride, int64_t ld_rhs, int64_t cols, double* __restrict__ sol, int64_t ld_sol,
                  int max_outer, double tol, int* __restrict__ status, unsigned long long* __restrict__ steps_total,
-                 unsigned long long* __restrict__ next_col) {
+                 unsigned long long* __restrict__ next_col, int initial_sweeps, double face_reduction) {
     extern __shared__ double smd[];
     const int ntri = k * (k + 1) / 2;
     double* g_tri = smd;                                 // k (k + 1) / 2 packed lower triangle, row-major
@@ -201,23 +204,41 @@ nnls_smem_kernel(const double* __restrict__ gram, int k, const float* __restrict
 
         bool converged = (rmax == 0.0);
         for (int outer = 0; outer < max_outer && !converged; ++outer) {
-            double viol = 0.0;
-            // full sweep: detects support changes
-            auto full = [&](auto slot_tag) {
+            // Gauss-Seidel sweeps over the coordinates that can move: the support (h > 0) and the candidates to
+            // enter it (g < 0).  Everything else has a zero projected gradient and a step there is a no-op, so a
+            // sweep costs |P| + |E| column updates instead of k visits.  The sweeps find the support -- they are
+            // as cheap as a CG iteration and change many coordinates at once --, several of them run before the
+            // first CG phase (from h = 0 the first pass is only a rough guess), one between CG phases.
+            auto sweep = [&](auto slot_tag) {
                 constexpr int I = decltype(slot_tag)::value;
-                const int t_end = min(32, k - 32 * I);
-                for (int o = 0; o < t_end; ++o) viol = fmax(viol, step(slot_tag, o));
+                unsigned mask = __ballot_sync(0xffffffffu, h[I] > 0.0 || g[I] < 0.0);
+                nsteps += __popc(mask);
+                while (mask) {
+                    const int o = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    step(slot_tag, o);
+                }
             };
-            [&]<int... Is>(std::integer_sequence<int, Is...>) {
-                (full(std::integral_constant<int, Is>{}), ...);
-            }(std::make_integer_sequence<int, KPL>{});
-            nsteps += k;
+            const int n_sweeps = outer == 0 ? initial_sweeps : 1;
+            for (int sw = 0; sw < n_sweeps; ++sw) {
+                [&]<int... Is>(std::integer_sequence<int, Is...>) {
+                    (sweep(std::integral_constant<int, Is>{}), ...);
+                }(std::make_integer_sequence<int, KPL>{});
+            }
+            // KKT residual of the state the sweeps left: max_t |projected gradient|
+            double viol = 0.0;
+#pragma unroll
+            for (int i = 0; i < KPL; ++i) viol = fmax(viol, h[i] > 0.0 ? fabs(g[i]) : fmax(-g[i], 0.0));
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) viol = fmax(viol, __shfl_xor_sync(0xffffffffu, viol, o));
             if (viol <= thresh) { converged = true; break; }
             // ---- conjugate gradients on the current support P = {h > 0} --------------------------------
-            // Between two full sweeps the support is fixed and the problem is the linear system
+            // Between two sweeps the support is fixed and the problem is the linear system
             // G_PP z = r_P: CG needs O(sqrt(cond)) products with G where coordinate sweeps need O(cond).
             // The step is cut at the first component that would turn negative; that component leaves P and CG
-            // restarts on the reduced support; the outer loop (full sweep) re-examines what may enter P.
+            // restarts on the reduced support; the next sweep re-examines what may enter P.  A phase only
+            // reduces the residual on its face by face_reduction (in norm): solving a face that is still going
+            // to change to full accuracy is wasted work, and the last phases reach the tolerance anyway.
             double d[KPL], q[KPL];
             bool in_p[KPL];
             double rr = 0.0;
@@ -228,7 +249,7 @@ nnls_smem_kernel(const double* __restrict__ gram, int k, const float* __restrict
                 rr = fma(d[i], d[i], rr);
             }
             rr = warp_sum(rr);
-            const double rr_stop = 0.01 * thresh * thresh;
+            const double rr_stop = fmax(0.01 * thresh * thresh, face_reduction * face_reduction * rr);
             for (int it = 0; it < 2 * k && rr > rr_stop; ++it) {
 #pragma unroll
                 for (int i = 0; i < KPL; ++i) q[i] = 0.0;
@@ -312,6 +333,8 @@ int nnls_gram_batched(const double* gram, int64_t k, const float* rhs, int rhs_s
         static const int warps_env = getenv("NFB_NNLS_WARPS") ? atoi(getenv("NFB_NNLS_WARPS")) : 0;
         const bool wide = warps_env ? warps_env >= 16 : true;
         const int kNnlsWarps = wide ? 16 : 12;
+        static const int sweeps0 = getenv("NFB_NNLS_SWEEPS") ? std::max(1, atoi(getenv("NFB_NNLS_SWEEPS"))) : kInitialSweeps;
+        static const double face_red = getenv("NFB_NNLS_FACE") ? atof(getenv("NFB_NNLS_FACE")) : kFaceReduction;
         const int grid = static_cast<int>(std::min<int64_t>(ceil_div64(cols, kNnlsWarps), sm_count()));
 #define NFB_NNLS_FAST(KPL)                                                                                       \
     do {                                                                                                         \
@@ -320,7 +343,7 @@ int nnls_gram_batched(const double* gram, int64_t k, const float* rhs, int rhs_s
                                       static_cast<int>(smem_fast)));                                             \
         kernel<<<grid, kNnlsWarps * 32, smem_fast, stream>>>(gram, static_cast<int>(k), rhs, rhs_splits,         \
                                                              rhs_stride, ld_rhs, cols, sol, ld_sol, max_outer,   \
-                                                             1e-10, status, steps_total, counter);               \
+                                                             1e-10, status, steps_total, counter, sweeps0, face_red); \
     } while (0)
         if (k <= 32) NFB_NNLS_FAST(1);
         else if (k <= 64) NFB_NNLS_FAST(2);
