@@ -252,6 +252,15 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // ------------------------------------------------------------------------------------------------
 // reductions
 // ------------------------------------------------------------------------------------------------
+// power of two that maps maxabs into [2^14, 2^15): the scale of the fp16 hi/lo operand planes (planes.cu)
+__device__ __forceinline__ float pow2_scale_for(float maxabs) {
+    if (!(maxabs > 0.0f) || !isfinite(maxabs)) return 1.0f;
+    int e = ilogbf(maxabs);           // 2^e <= maxabs < 2^(e+1)
+    int shift = 14 - e;
+    shift = max(-100, min(100, shift));
+    return ldexpf(1.0f, shift);
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

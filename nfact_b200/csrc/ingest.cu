@@ -57,6 +57,54 @@ __global__ void finalize_kernel(const double* __restrict__ acc, int64_t nelem, d
     }
 }
 
+// ---- single subject straight into the operand planes ------------------------------------------------------
+// A probtrackx matrix lists every (seed, target) pair once, so X[r][c] = float32(v * scale) needs neither the
+// float64 scratch nor a dense float32 matrix: pass 1 finds max |X| (the planes' scale), pass 2 writes the fp16
+// hi / lo halves of every triplet into the zeroed planes.  A one-bit-per-cell mask detects duplicate coordinates
+// (the reference SUMS them in float64, scipy csc_matrix): any duplicate raises dup_flag and the caller redoes the
+// subject on the exact scatter-add path.
+__global__ void coo_absmax_kernel(const double* __restrict__ vals, int64_t nnz, double scale,
+                                  unsigned int* __restrict__ out_bits) {
+    float m = 0.0f;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < nnz;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+        m = fmaxf(m, fabsf(__double2float_rn(__dmul_rn(vals[i], scale))));
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) atomicMax(out_bits, __float_as_uint(m));
+}
+
+__global__ void coo_to_planes_kernel(const int* __restrict__ rows, const int* __restrict__ cols,
+                                     const double* __restrict__ vals, int64_t nnz, double scale, int64_t nrows,
+                                     int64_t ncols, const unsigned int* __restrict__ max_bits,
+                                     __half* __restrict__ hi, __half* __restrict__ lo, int64_t ldp,
+                                     unsigned int* __restrict__ cell_mask, float* __restrict__ inv_scale,
+                                     double* __restrict__ sums, int* __restrict__ flags) {
+    __shared__ double scratch[32];
+    const float s = pow2_scale_for(__uint_as_float(max_bits[0]));
+    if (blockIdx.x == 0 && threadIdx.x == 0) inv_scale[0] = 1.0f / s;
+    double acc = 0.0, acc_sum = 0.0;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < nnz;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t r = rows[i], c = cols[i];
+        if (r < 0 || c < 0 || r >= nrows || c >= ncols) { flags[0] = 1; continue; }      // out of bounds
+        const int64_t cell = r * ldp + c;
+        const unsigned int bit = 1u << (cell & 31);
+        if (atomicOr(&cell_mask[cell >> 5], bit) & bit) { flags[1] = 1; continue; }       // duplicate coordinate
+        const float v = __double2float_rn(__dmul_rn(vals[i], scale));
+        acc += static_cast<double>(v) * static_cast<double>(v);
+        acc_sum += static_cast<double>(v);
+        if (v < 0.0f) flags[2] = 1;
+        const float vs = v * s;
+        const __half vh = __float2half_rn(vs);
+        hi[cell] = vh;
+        lo[cell] = __float2half_rn(vs - __half2float(vh));
+    }
+    const double total_sq = block_sum(acc, scratch);
+    if (threadIdx.x == 0) atomicAdd(sums, total_sq);
+    const double total_sum = block_sum(acc_sum, scratch);
+    if (threadIdx.x == 0) atomicAdd(sums + 1, total_sum);
+}
+
 int blocks_for(int64_t items) {
     return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(ceil_div64(items, 256), sm_count() * 16LL)));
 }
@@ -80,6 +128,21 @@ int ingest_scatter(const int* rows, const int* cols, const double* vals, int64_t
 int ingest_finalize(const double* acc, int64_t nelem, double recip, int apply_recip, float* x, cudaStream_t stream) {
     if (nelem == 0) return 0;
     finalize_kernel<<<blocks_for(nelem), 256, 0, stream>>>(acc, nelem, recip, apply_recip, x);
+    NFB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int ingest_coo_to_planes(const int* rows, const int* cols, const double* vals, int64_t nnz, double scale,
+                         int64_t nrows, int64_t ncols, unsigned int* max_bits, __half* hi, __half* lo, int64_t ldp,
+                         unsigned int* cell_mask, float* inv_scale, double* sums, int* flags, cudaStream_t stream) {
+    // callers zero max_bits, hi, lo, cell_mask, sums[2] and flags[3] on the same stream beforehand
+    if (nnz > 0) {
+        coo_absmax_kernel<<<blocks_for(nnz), 256, 0, stream>>>(vals, nnz, scale, max_bits);
+        NFB_CUDA(cudaGetLastError());
+    }
+    // launched even for nnz == 0: it writes the planes' inverse scale
+    coo_to_planes_kernel<<<blocks_for(std::max<int64_t>(nnz, 1)), 256, 0, stream>>>(
+        rows, cols, vals, nnz, scale, nrows, ncols, max_bits, hi, lo, ldp, cell_mask, inv_scale, sums, flags);
     NFB_CUDA(cudaGetLastError());
     return 0;
 }

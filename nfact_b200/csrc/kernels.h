@@ -138,6 +138,13 @@ int ingest_scatter(const int* rows, const int* cols, const double* vals, int64_t
 // X[r][c] = (float)(acc * recip)   (recip == 1.0 -> plain rounding)
 int ingest_finalize(const double* acc, int64_t nelem, double recip, int apply_recip, float* x, cudaStream_t stream);
 
+// One subject without duplicate coordinates straight into zeroed operand planes: X[r][c] = float32(v * scale)
+// split as planes.cu does.  max_bits[1], cell_mask[ceil(nrows * ldp / 32)], sums[2] (sum x^2, sum x) and
+// flags[3] (out of bounds, duplicate coordinate seen -> result invalid, negative value) must be zeroed before.
+int ingest_coo_to_planes(const int* rows, const int* cols, const double* vals, int64_t nnz, double scale,
+                         int64_t nrows, int64_t ncols, unsigned int* max_bits, __half* hi, __half* lo, int64_t ldp,
+                         unsigned int* cell_mask, float* inv_scale, double* sums, int* flags, cudaStream_t stream);
+
 // ---- nnls.cu --------------------------------------------------------------------------------------
 // Batched non-negative least squares with one shared Gram matrix:
 //   for every column j < cols:  min_{h >= 0} 0.5 h'Gh - rhs[:, j]'h ,  G [k,k] fp64, rhs [k, ld] fp32 partials

@@ -13,14 +13,6 @@
 namespace nfb {
 namespace {
 
-__device__ __forceinline__ float pow2_scale_for(float maxabs) {
-    if (!(maxabs > 0.0f) || !isfinite(maxabs)) return 1.0f;
-    int e = ilogbf(maxabs);           // 2^e <= maxabs < 2^(e+1)
-    int shift = 14 - e;
-    shift = max(-100, min(100, shift));
-    return ldexpf(1.0f, shift);
-}
-
 __global__ void absmax_kernel(const float* __restrict__ x, int64_t rows, int64_t cols, int64_t ld,
                               unsigned int* __restrict__ out_bits) {
     float m = 0.0f;

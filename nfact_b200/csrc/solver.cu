@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <chrono>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -1351,6 +1352,29 @@ int nfb_component_postops_host(nfb_handle* h, void* data, int is_f64, int comp_m
                                     zscore, static_cast<float*>(norm_out));
 }
 
+// NFB_HOST_TIMING=1: wall-clock marks of the host-visible phases of the ingest (each mark synchronises the stream)
+struct HostMarks {
+    cudaStream_t st;
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    std::string line;
+    explicit HostMarks(cudaStream_t stream) : st(stream), on(getenv("NFB_HOST_TIMING") != nullptr) {
+        if (on) t0 = std::chrono::steady_clock::now();
+    }
+    void mark(const char* name) {
+        if (!on) return;
+        cudaStreamSynchronize(st);
+        const auto t1 = std::chrono::steady_clock::now();
+        char buf[96];
+        snprintf(buf, sizeof(buf), "%s=%.1f ms  ", name, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        line += buf;
+        t0 = t1;
+    }
+    ~HostMarks() {
+        if (on && !line.empty()) fprintf(stderr, "nfact_b200 ingest (host clock): %s\n", line.c_str());
+    }
+};
+
 // ---- ingest ----------------------------------------------------------------------------------------
 int nfb_ingest_coo(nfb_handle* h, int n_subjects, const int32_t* const* rows_host, const int32_t* const* cols_host,
                    const double* const* vals_host, const int64_t* nnz, const double* scale, int64_t nrows,
@@ -1370,6 +1394,7 @@ int nfb_ingest_coo(nfb_handle* h, int n_subjects, const int32_t* const* rows_hos
     const double per_row = ((single ? 8.0 : 16.0) + (x_out_dev == nullptr ? 4.0 : 0.0)) * static_cast<double>(ncols);
     NFB_CHECK(budget > per_row, "not enough device memory for ingest");
     const int64_t blk_rows = std::max<int64_t>(1, std::min<int64_t>(nrows, static_cast<int64_t>(budget / per_row)));
+    HostMarks marks(st);
     DevBuf<double> tmp, acc, vals;
     DevBuf<int> rows, cols;
     DevBuf<float> xblk;
@@ -1380,6 +1405,7 @@ int nfb_ingest_coo(nfb_handle* h, int n_subjects, const int32_t* const* rows_hos
     NFB_TRY(cols.alloc(max_nnz, false, st));
     NFB_TRY(vals.alloc(max_nnz, false, st));
     NFB_CUDA(cudaMemsetAsync(h->d_int.p + 2, 0, sizeof(int), st));
+    marks.mark("alloc+zero");
     const double recip = 1.0 / static_cast<double>(n_subjects);
     auto upload = [&](int s) -> int {
         NFB_CUDA(cudaMemcpyAsync(rows.p, rows_host[s], sizeof(int) * nnz[s], cudaMemcpyHostToDevice, st));
@@ -1388,6 +1414,7 @@ int nfb_ingest_coo(nfb_handle* h, int n_subjects, const int32_t* const* rows_hos
         return 0;
     };
     if (n_subjects == 1) NFB_TRY(upload(0));   // one subject: its triplets are uploaded once for all row blocks
+    marks.mark("upload");
     for (int64_t r0 = 0; r0 < nrows; r0 += blk_rows) {
         const int64_t nr = std::min(blk_rows, nrows - r0);
         if (!single) NFB_CUDA(cudaMemsetAsync(acc.p, 0, sizeof(double) * nr * ncols, st));
@@ -1409,7 +1436,71 @@ int nfb_ingest_coo(nfb_handle* h, int n_subjects, const int32_t* const* rows_hos
     int oob = 0;
     NFB_CUDA(cudaMemcpyAsync(&oob, h->d_int.p + 2, sizeof(int), cudaMemcpyDeviceToHost, st));
     NFB_CUDA(cudaStreamSynchronize(st));
+    marks.mark("scatter+finalize");
     NFB_CHECK(oob == 0, "row/column index exceeds matrix dimensions");
+    tmp.release(); acc.release(); vals.release(); rows.release(); cols.release(); xblk.release();
+    marks.mark("free");
+    return 0;
+}
+
+// One subject whose triplets are all distinct: straight into the operand planes (ingest.cu), no dense float64
+// scratch and no dense float32 matrix.  *duplicates = true (and no matrix) when a coordinate occurs twice.
+static int ingest_single_to_planes(nfb_handle* h, const int32_t* rows_host, const int32_t* cols_host,
+                                   const double* vals_host, int64_t nnz, double scale, int64_t nrows, int64_t ncols,
+                                   nfb_matrix** out, bool* duplicates) {
+    cudaStream_t st = h->stream;
+    HostMarks marks(st);
+    std::unique_ptr<nfb_matrix> x(new nfb_matrix());
+    x->h = h;
+    x->m = nrows;
+    x->n = ncols;
+    x->ldp = round_up64(ncols, 8);
+    const size_t cells = static_cast<size_t>(nrows) * x->ldp;
+    DevBuf<unsigned int> mask;
+    DevBuf<int> rows, cols;
+    DevBuf<double> vals;
+    NFB_TRY(x->hi.alloc(cells, false, st));
+    NFB_TRY(x->lo.alloc(cells, false, st));
+    NFB_TRY(x->inv_scale.alloc(1, true, st));
+    NFB_TRY(mask.alloc((cells + 31) / 32, false, st));
+    NFB_TRY(rows.alloc(nnz, false, st));
+    NFB_TRY(cols.alloc(nnz, false, st));
+    NFB_TRY(vals.alloc(nnz, false, st));
+    marks.mark("alloc");
+    // the triplets travel on the copy stream while the planes and the mask are zeroed on the main one
+    cudaEvent_t uploaded = nullptr;
+    NFB_CUDA(cudaEventCreateWithFlags(&uploaded, cudaEventDisableTiming));
+    NFB_CUDA(cudaMemcpyAsync(rows.p, rows_host, sizeof(int) * nnz, cudaMemcpyHostToDevice, h->copy_stream));
+    NFB_CUDA(cudaMemcpyAsync(cols.p, cols_host, sizeof(int) * nnz, cudaMemcpyHostToDevice, h->copy_stream));
+    NFB_CUDA(cudaMemcpyAsync(vals.p, vals_host, sizeof(double) * nnz, cudaMemcpyHostToDevice, h->copy_stream));
+    NFB_CUDA(cudaEventRecord(uploaded, h->copy_stream));
+    NFB_CUDA(cudaMemsetAsync(x->hi.p, 0, cells * sizeof(__half), st));
+    NFB_CUDA(cudaMemsetAsync(x->lo.p, 0, cells * sizeof(__half), st));
+    NFB_CUDA(cudaMemsetAsync(mask.p, 0, ((cells + 31) / 32) * sizeof(unsigned int), st));
+    NFB_CUDA(cudaMemsetAsync(h->d_bits.p, 0, sizeof(unsigned int), st));
+    NFB_CUDA(cudaMemsetAsync(h->d_scal.p + 6, 0, 2 * sizeof(double), st));
+    NFB_CUDA(cudaMemsetAsync(h->d_int.p + 4, 0, 3 * sizeof(int), st));
+    NFB_CUDA(cudaStreamWaitEvent(st, uploaded, 0));
+    marks.mark("upload");
+    NFB_TRY(ingest_coo_to_planes(rows.p, cols.p, vals.p, nnz, scale, nrows, ncols, h->d_bits.p, x->hi.p, x->lo.p, x->ldp,
+                                 mask.p, x->inv_scale.p, h->d_scal.p + 6, h->d_int.p + 4, st));
+    int flags[3] = {0, 0, 0};
+    NFB_CUDA(cudaMemcpyAsync(flags, h->d_int.p + 4, sizeof(flags), cudaMemcpyDeviceToHost, st));
+    NFB_CUDA(cudaMemcpyAsync(h->h_scal + 6, h->d_scal.p + 6, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    NFB_CUDA(cudaMemcpyAsync(&x->inv_scale_host, x->inv_scale.p, sizeof(float), cudaMemcpyDeviceToHost, st));
+    NFB_CUDA(cudaStreamSynchronize(st));
+    cudaEventDestroy(uploaded);
+    marks.mark("scatter");
+    note_launch(2);
+    NFB_CHECK(flags[0] == 0, "row/column index exceeds matrix dimensions");
+    *duplicates = flags[1] != 0;
+    if (*duplicates) return 0;             // x (and its planes) is released; the caller takes the exact path
+    x->has_negative = flags[2];
+    x->sumsq = h->h_scal[6];
+    x->sum = h->h_scal[7];
+    rows.release(); cols.release(); vals.release(); mask.release();
+    marks.mark("free");
+    *out = x.release();
     return 0;
 }
 
@@ -1417,13 +1508,28 @@ int nfb_ingest_coo_matrix(nfb_handle* h, int n_subjects, const int32_t* const* r
                           const int32_t* const* cols_host, const double* const* vals_host, const int64_t* nnz,
                           const double* scale, int64_t nrows, int64_t ncols, int group_mode, nfb_matrix** out) {
     NFB_CHECK(h != nullptr && out != nullptr, "NULL argument");
+    NFB_CHECK(n_subjects >= 1 && nrows > 0 && ncols > 0, "bad ingest arguments");
     NFB_CUDA(cudaSetDevice(h->device));
-    // the float32 matrix exists only on the device and only until its fp16 planes are built
+    static const bool direct_ok = !(getenv("NFB_INGEST_DIRECT") && atoi(getenv("NFB_INGEST_DIRECT")) == 0);
+    if (!group_mode && n_subjects == 1 && direct_ok) {
+        bool duplicates = false;
+        *out = nullptr;
+        NFB_TRY(ingest_single_to_planes(h, rows_host[0], cols_host[0], vals_host[0], nnz[0], scale[0], nrows, ncols,
+                                        out, &duplicates));
+        if (!duplicates) return 0;
+    }
+    // group average, or duplicate coordinates to be summed in float64: the exact scatter-add path.
+    // The float32 matrix exists only on the device and only until its fp16 planes are built.
     DevBuf<float> dense;
     NFB_TRY(dense.alloc(static_cast<size_t>(nrows) * ncols, false, h->stream));
     NFB_TRY(nfb_ingest_coo(h, n_subjects, rows_host, cols_host, vals_host, nnz, scale, nrows, ncols, group_mode,
                            nullptr, dense.p));
-    return nfb_matrix_from_device(h, dense.p, nrows, ncols, ncols, out);
+    HostMarks marks(h->stream);
+    const int rc = nfb_matrix_from_device(h, dense.p, nrows, ncols, ncols, out);
+    marks.mark("planes");
+    dense.release();
+    marks.mark("free dense");
+    return rc;
 }
 
 int nfb_matrix_matmul(nfb_handle* h, const nfb_matrix* x, int trans, const float* b_dev, int64_t n_b,

@@ -106,3 +106,72 @@ def test_lz4_subjects_bit_exact(tmp_path, golden, golden_subjects):
         assert np.array_equal(X, golden[f"ingest_single_{s + 1}"])
     assert np.array_equal(nfact_b200.process_fdt_matrix2(folders, True), golden["ingest_group"])
     assert np.array_equal(nfact_b200.process_fdt_matrix2(folders[:1], False), golden["ingest_single_1"])
+
+
+def test_direct_plane_ingest_equals_the_exact_path(golden):
+    """A subject without duplicate coordinates goes straight into the operand planes (no float64 scratch, no
+    dense float32 matrix); the planes must be the ones the exact path builds: products with them and the dual
+    regression on them are bit-identical.  Subjects with duplicates fall back to the exact path."""
+    import torch
+    import nfact_b200
+    from nfact_b200.device import DeviceMatrix, ingest_coo_resident
+    rng = np.random.default_rng(77)
+    m, n, k = 203, 333, 5                              # n is not a multiple of 8: padded plane rows
+    cells = rng.choice(m * n, size=9000, replace=False)
+    rows, cols = (cells // n).astype(np.int32), (cells % n).astype(np.int32)
+    vals = rng.uniform(0.5, 900.0, size=cells.size)
+    scale = 1e8 / 9876543.0
+    dense = np.zeros((m, n), np.float64)
+    dense[rows, cols] = vals * scale
+    X = dense.astype(np.float32)
+    direct = ingest_coo_resident([(rows, cols, vals, scale)], m, n, False)
+    exact = DeviceMatrix.from_host(X)
+    assert direct.shape == (m, n)
+    assert abs(direct.sumsq - exact.sumsq) <= 1e-12 * exact.sumsq and abs(direct.mean - exact.mean) <= 1e-12 * exact.mean
+    assert not direct.has_negative
+    B = torch.from_numpy(rng.random((k, n)).astype(np.float32)).cuda()
+    outs = []
+    for mat in (direct, exact):
+        out = torch.zeros((k, m), dtype=torch.float32, device="cuda")
+        mat.matmul_dev(False, B.data_ptr(), k, out.data_ptr(), m)
+        torch.cuda.synchronize()
+        outs.append(out.cpu().numpy())
+    assert np.array_equal(outs[0], outs[1])
+    comps = {"grey_components": rng.gamma(0.5, 1.0, (m, k))}
+    a = nfact_b200.nmf_dual_regression(comps, direct)
+    b = nfact_b200.nmf_dual_regression(comps, exact)
+    assert np.array_equal(a["white_components"], b["white_components"])
+    assert np.array_equal(a["grey_components"], b["grey_components"])
+    direct.free()
+    exact.free()
+    # the duplicate-free golden subject (probtrackx --pd style) through the file loader
+    pd_path = os.path.join(GOLDEN_DIR, "data", "sub-pd", "fdt_matrix2.dot")
+    xres = nfact_b200.load_fdt_matrix(pd_path, resident=True)
+    want = golden["ingest_single_pd"]
+    assert abs(xres.sumsq - float((want.astype(np.float64) ** 2).sum())) <= 1e-12 * xres.sumsq
+    g = {"grey_components": rng.gamma(0.5, 1.0, (want.shape[0], 4))}
+    assert np.array_equal(nfact_b200.nmf_dual_regression(g, xres)["grey_components"],
+                          nfact_b200.nmf_dual_regression(g, want)["grey_components"])
+    xres.free()
+    # duplicates (summed in float64 by the reference) and a negative value: exact path, flags kept
+    rows2 = np.concatenate([rows, rows[:50]])
+    cols2 = np.concatenate([cols, cols[:50]])
+    vals2 = np.concatenate([vals, vals[:50] * 0.25])
+    dense2 = np.zeros((m, n), np.float64)
+    np.add.at(dense2, (rows2, cols2), vals2)
+    dup = ingest_coo_resident([(rows2, cols2, vals2, scale)], m, n, False)
+    want2 = (dense2 * scale).astype(np.float32).astype(np.float64)
+    assert abs(dup.sumsq - float((want2 ** 2).sum())) <= 1e-12 * dup.sumsq
+    dup.free()
+    vals3 = vals.copy()
+    vals3[7] = -3.0
+    neg = ingest_coo_resident([(rows, cols, vals3, scale)], m, n, False)
+    assert neg.has_negative
+    neg.free()
+    bad = rows.copy()
+    bad[3] = m
+    with pytest.raises(nfact_b200.NfbError, match="exceeds matrix dimensions"):
+        ingest_coo_resident([(bad, cols, vals, scale)], m, n, False)
+    empty = ingest_coo_resident([(rows[:0], cols[:0], vals[:0], scale)], m, n, False)
+    assert empty.sumsq == 0.0 and empty.shape == (m, n)
+    empty.free()
