@@ -185,6 +185,15 @@ int nfb_component_postops_host(nfb_handle* h, void* data, int is_f64, int comp_m
                                const int32_t* group_id, int n_groups, int do_threshold, double zscore,
                                void* norm_out);
 
+/* Component loadings (replaces __correlating at NFACT/stats/stats_component_loadings.py:199-231): for every
+ * component t the correlation between the subject's map and the group's map,
+ *   loadings_out[t] = [sum_j (s_tj - mean s_t)(g_tj - mean g_t) / (len - 1)] / (std s_t * std g_t)
+ * with population standard deviations, exactly the reference's (mixed) normalisation; a constant map gives NaN
+ * like numpy's 0 / 0.  subject / group: host arrays of the same dtype (is_f64) and layout, [k, len] when
+ * comp_major else [len, k] (the reference's voxels x components). */
+int nfb_component_loadings_host(nfb_handle* h, const void* subject, const void* group, int is_f64, int comp_major,
+                                int64_t k, int64_t len, double* loadings_out);
+
 /* ---- NMF-sso similarity --------------------------------------------------------------------------------
  * replaces  NFACT/decomp/decomposition/sso/sso_functions.py:29-68  compute_similairty_matrix:
  * np.corrcoef of the (row-normalised) stacked white-matter components of all NMF-sso runs -- (N k)^2 n

@@ -104,6 +104,11 @@ template <typename T>
 int comp_standardize(const T* x, int64_t k, int64_t len, int64_t ld, T* out, int64_t ld_out, double* stats,
                      cudaStream_t stream);
 
+// out[t] = per-component correlation of a[t][:] and b[t][:] as NFACT/stats/stats_component_loadings.py:199-231
+// computes it (covariance / (len - 1) over the product of the population standard deviations)
+template <typename T>
+int comp_loadings(const T* a, const T* b, int64_t k, int64_t len, int64_t ld, double* out, cudaStream_t stream);
+
 // ---- p2p.cu ---------------------------------------------------------------------------------------
 // Row-sharded H half-step over NVLink peer memory (CUDA IPC mappings of every rank's arena and H master).
 constexpr int kP2pMaxWorld = 8;

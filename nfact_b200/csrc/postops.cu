@@ -100,6 +100,46 @@ __global__ void comp_standardize_kernel(const T* __restrict__ x, int64_t k, int6
     }
 }
 
+// one CTA per component t: r_t = [sum_j (a_tj - mean a_t)(b_tj - mean b_t) / (len - 1)] / (std a_t * std b_t), population
+// standard deviations -- the mixed normalisation of NFACT/stats/stats_component_loadings.py:227-231, kept as is
+template <typename T>
+__global__ void __launch_bounds__(kStatThreads)
+comp_loadings_kernel(const T* __restrict__ a, const T* __restrict__ b, int64_t len, int64_t ld,
+                     double* __restrict__ out) {
+    __shared__ double scratch[32];
+    __shared__ double bcast[2];
+    const int t = blockIdx.x;
+    const T* ra = a + static_cast<int64_t>(t) * ld;
+    const T* rb = b + static_cast<int64_t>(t) * ld;
+    double sa = 0.0, sb = 0.0;
+    for (int64_t j = threadIdx.x; j < len; j += kStatThreads) {
+        sa += static_cast<double>(ra[j]);
+        sb += static_cast<double>(rb[j]);
+    }
+    sa = block_sum(sa, scratch);
+    sb = block_sum(sb, scratch);
+    if (threadIdx.x == 0) {
+        bcast[0] = sa / static_cast<double>(len);
+        bcast[1] = sb / static_cast<double>(len);
+    }
+    __syncthreads();
+    const double ma = bcast[0], mb = bcast[1];
+    double qab = 0.0, qaa = 0.0, qbb = 0.0;
+    for (int64_t j = threadIdx.x; j < len; j += kStatThreads) {
+        const double da = static_cast<double>(ra[j]) - ma, db = static_cast<double>(rb[j]) - mb;
+        qab = fma(da, db, qab);
+        qaa = fma(da, da, qaa);
+        qbb = fma(db, db, qbb);
+    }
+    qab = block_sum(qab, scratch);
+    qaa = block_sum(qaa, scratch);
+    qbb = block_sum(qbb, scratch);
+    if (threadIdx.x == 0) {
+        const double n = static_cast<double>(len);
+        out[t] = (qab / (n - 1.0)) / (sqrt(qaa / n) * sqrt(qbb / n));     // 0 / 0 -> NaN like numpy
+    }
+}
+
 int elementwise_grid(int64_t total) {
     return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(ceil_div64(total, 256), static_cast<int64_t>(sm_count()) * 16)));
 }
@@ -140,6 +180,16 @@ int comp_standardize(const T* x, int64_t k, int64_t len, int64_t ld, T* out, int
     return 0;
 }
 
+template <typename T>
+int comp_loadings(const T* a, const T* b, int64_t k, int64_t len, int64_t ld, double* out, cudaStream_t stream) {
+    if (k == 0) return 0;
+    comp_loadings_kernel<T><<<static_cast<unsigned>(k), kStatThreads, 0, stream>>>(a, b, len, ld, out);
+    NFB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template int comp_loadings<float>(const float*, const float*, int64_t, int64_t, int64_t, double*, cudaStream_t);
+template int comp_loadings<double>(const double*, const double*, int64_t, int64_t, int64_t, double*, cudaStream_t);
 template int comp_threshold<float>(float*, int64_t, int64_t, int64_t, const int*, int, double, double*, cudaStream_t);
 template int comp_threshold<double>(double*, int64_t, int64_t, int64_t, const int*, int, double, double*, cudaStream_t);
 template int comp_standardize<float>(const float*, int64_t, int64_t, int64_t, float*, int64_t, double*, cudaStream_t);

@@ -1336,6 +1336,34 @@ static int component_postops(nfb_handle* h, T* data, int comp_major, int64_t k, 
     return 0;
 }
 
+template <typename T>
+static int component_loadings(nfb_handle* h, const T* subject, const T* group, int comp_major, int64_t k, int64_t len,
+                              double* out_host) {
+    cudaStream_t st = h->stream;
+    const int64_t ld = round_up64(len, 8);
+    DevBuf<T> raw, cm[2];
+    DevBuf<double> out;
+    NFB_TRY(out.alloc(static_cast<size_t>(k), false, st));
+    if (!comp_major) NFB_TRY(raw.alloc(static_cast<size_t>(k) * len, false, st));
+    const T* src[2] = {subject, group};
+    for (int a = 0; a < 2; ++a) {
+        NFB_TRY(cm[a].alloc(static_cast<size_t>(k) * ld, false, st));
+        if (comp_major) {
+            NFB_CUDA(cudaMemcpy2DAsync(cm[a].p, ld * sizeof(T), src[a], len * sizeof(T), len * sizeof(T), k,
+                                       cudaMemcpyHostToDevice, st));
+        } else {
+            NFB_CUDA(cudaMemcpyAsync(raw.p, src[a], sizeof(T) * k * len, cudaMemcpyHostToDevice, st));
+            if constexpr (sizeof(T) == 8) NFB_TRY(transpose_f64(raw.p, len, k, k, cm[a].p, ld, st));
+            else NFB_TRY(transpose_f32(raw.p, len, k, k, cm[a].p, ld, st));
+        }
+    }
+    NFB_TRY(comp_loadings<T>(cm[0].p, cm[1].p, k, len, ld, out.p, st));
+    NFB_CUDA(cudaMemcpyAsync(out_host, out.p, sizeof(double) * k, cudaMemcpyDeviceToHost, st));
+    NFB_CUDA(cudaStreamSynchronize(st));
+    note_launch(1);
+    return 0;
+}
+
 extern "C" {
 
 int nfb_component_postops_host(nfb_handle* h, void* data, int is_f64, int comp_major, int64_t k, int64_t len,
@@ -1374,6 +1402,18 @@ struct HostMarks {
         if (on && !line.empty()) fprintf(stderr, "nfact_b200 ingest (host clock): %s\n", line.c_str());
     }
 };
+
+int nfb_component_loadings_host(nfb_handle* h, const void* subject, const void* group, int is_f64, int comp_major,
+                                int64_t k, int64_t len, double* loadings_out) {
+    NFB_CHECK(h != nullptr && subject != nullptr && group != nullptr && loadings_out != nullptr, "NULL argument");
+    NFB_CHECK(k >= 1 && len >= 1, "bad nfb_component_loadings_host shape");
+    NFB_CUDA(cudaSetDevice(h->device));
+    if (is_f64)
+        return component_loadings<double>(h, static_cast<const double*>(subject), static_cast<const double*>(group),
+                                          comp_major, k, len, loadings_out);
+    return component_loadings<float>(h, static_cast<const float*>(subject), static_cast<const float*>(group),
+                                     comp_major, k, len, loadings_out);
+}
 
 // ---- ingest ----------------------------------------------------------------------------------------
 int nfb_ingest_coo(nfb_handle* h, int n_subjects, const int32_t* const* rows_host, const int32_t* const* cols_host,

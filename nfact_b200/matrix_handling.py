@@ -250,6 +250,30 @@ def threshold_grey_components(components: np.ndarray, coord_path: str, seeds: li
     return components
 
 
+def component_loadings(subject_data: np.ndarray, group_data: np.ndarray) -> np.ndarray:
+    """``__correlating`` of NFACT/stats/stats_component_loadings.py:199-231: per-component correlation between a
+    subject's dual-regression maps and the group maps, both ``[samples, k]`` like the reference; float64 ``[k]``.
+    Computed on the device (``nfb_component_loadings_host``, float64 statistics)."""
+    from ctypes import c_void_p
+    from . import _lib
+    subject = np.asarray(subject_data)
+    group = np.asarray(group_data)
+    if subject.shape != group.shape or subject.ndim != 2:
+        raise ValueError(f"operands could not be broadcast together with shapes {subject.shape} {group.shape}")
+    dtype = np.float32 if subject.dtype == np.float32 and group.dtype == np.float32 else np.float64
+    subject = np.ascontiguousarray(subject, dtype=dtype)
+    group = np.ascontiguousarray(group, dtype=dtype)
+    length, k = subject.shape
+    out = np.empty(k, dtype=np.float64)
+    if k == 0 or length == 0:
+        return np.full(k, np.nan)
+    handle = device.get_handle()
+    _lib.check(handle.lib.nfb_component_loadings_host(handle.ptr, c_void_p(subject.ctypes.data),
+                                                      c_void_p(group.ctypes.data), int(dtype == np.float64), 0, k,
+                                                      length, c_void_p(out.ctypes.data)))
+    return out
+
+
 def thresholding_components(threshold_val: int, path_to_coords: str, seeds: list, components: dict) -> dict:
     """NFACT/base/matrix_handling.py:241-277."""
     col = colours()

@@ -144,3 +144,32 @@ def test_fused_dual_regression_postprocessing(tmp_path, normalise):
         assert np.allclose(got["normalised_white"], norm["white_matter"], rtol=1e-10, atol=1e-10)
     no_thr = nfact_b200.dual_regression_subject(str(sub), {"grey_components": G}, SEEDS, threshold=0)
     assert np.array_equal(no_thr["grey_components"], plain["grey_components"])
+
+
+def test_component_loadings_match_the_reference_formula(g):
+    """__correlating (NFACT/stats/stats_component_loadings.py:199-231), restated here verbatim in numpy."""
+    import nfact_b200
+
+    def correlating(subject_data, group_data):
+        group_mean, group_std = group_data.mean(axis=0), group_data.std(axis=0)
+        subj_mean, subj_std = subject_data.mean(axis=0), subject_data.std(axis=0)
+        cov = ((subject_data - subj_mean) * (group_data - group_mean)).sum(axis=0) / (subject_data.shape[0] - 1)
+        return cov / (subj_std * group_std)
+
+    rng = np.random.default_rng(12)
+    group = g["grey_f64"].copy()
+    group[:, 5] += rng.random(group.shape[0])                 # un-constant the constant component
+    subject = group * rng.uniform(0.5, 1.5, group.shape) + 0.1 * rng.random(group.shape)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        want = correlating(subject, group)
+    got = nfact_b200.component_loadings(subject, group)
+    assert got.shape == want.shape and got.dtype == np.float64
+    assert np.isnan(got[3]) and np.isnan(want[3])             # the dead component: 0 / 0 like numpy
+    ok = ~np.isnan(want)
+    assert np.allclose(got[ok], want[ok], rtol=1e-12, atol=1e-14)
+    got32 = nfact_b200.component_loadings(subject.astype(np.float32), group.astype(np.float32))
+    assert np.allclose(got32[ok], want[ok], rtol=1e-5)
+    big_s, big_g = rng.gamma(0.3, 1.0, (20011, 23)), rng.gamma(0.3, 1.0, (20011, 23))
+    assert np.allclose(nfact_b200.component_loadings(big_s, big_g), correlating(big_s, big_g), rtol=1e-10, atol=1e-13)
+    with pytest.raises(ValueError):
+        nfact_b200.component_loadings(big_s, big_g[:, :5])
