@@ -38,9 +38,10 @@ WORKLOADS = {
 }
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of gemm_split_kernel from the ncu --set full captures
 # of this same command (profiles/r01_ncu_full_gemm_split_C3.csv: X H' 26.63+0.28 GB with 6 split slabs;
-# profiles/r01_ncu_full_final_C3.csv: W'X 26.55+0.08 GB unsplit) -> mean of the two launches of an iteration
+# profiles/r01_ncu_full_final_C3.csv and profiles/r01b_ncu_full.csv: W'X 26.55+0.08 GB unsplit) -> mean of the two
+# launches of an iteration
 NCU_TRAFFIC_PER_LAUNCH = {"C3": 26.77e9}
-NCU_TENSOR_PIPE_ACTIVE = {"C3": 0.86}    # sm__pipe_tensor_cycles_active of the W'X launch, same capture
+NCU_TENSOR_PIPE_ACTIVE = {"C3": 0.85}    # sm__pipe_tensor_cycles_active of the W'X launch (r01b capture: 84.9 %)
 METRIC = "nmf_iterations_per_second"
 UNIT = "iter/s"
 ALPHA_W, L1_RATIO = 0.1, 1.0   # NFACT defaults (matrix_decomposition.py:100-107)

@@ -11,7 +11,8 @@ timeout 900 python -m pytest tests -m gpu -x -q > $out/${tag}_pytest.log 2>&1; t
 timeout 900 python bench.py > $out/${tag}_bench.json 2> $out/${tag}_bench.err || tail -5 $out/${tag}_bench.err
 tail -c 600 $out/${tag}_bench.json
 timeout 300 python bench.py --no-e2e --no-cpu --steps 2 --warmup 3 > /dev/null 2>&1 && \
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_launches.csv \
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base demangled -k regex:nfb:: \
+    -c 400 --csv --log-file $out/${tag}_launches.csv \
     python bench.py --no-e2e --no-cpu --steps 2 --warmup 3 > $out/${tag}_ncu_launches.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'gemm_split_kernel|cd_sweep_tile' \
     --launch-skip 12 -c 6 -o $out/${tag}_full -f python bench.py --no-e2e --no-cpu --steps 2 --warmup 3 \
