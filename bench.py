@@ -223,6 +223,38 @@ def cpu_baseline(m, n, k, density, solver):
     }
 
 
+def dual_regression_across_gpus(torch, dist, dev, handle, m, n, k, density, rank, world):
+    """nfact_dr with subjects distributed over the GPUs (BASELINE config C4; run_locally(rank, world) in the
+    product): every rank regresses its OWN full-size synthetic subject (seed 1000 + rank) onto the same
+    group components, no collective on the data path.  value = subjects finished per second by all ranks =
+    world / (slowest rank's time for one subject, X resident, float64 results copied to the host)."""
+    import nfact_b200
+    from nfact_b200.device import DeviceMatrix
+    torch.cuda.empty_cache()
+    x_sub = synth_rows_device(torch, dev, 0, m, n, k, density, seed=1000 + rank)
+    torch.cuda.synchronize()
+    xsub = DeviceMatrix.from_device_ptr(x_sub.data_ptr(), m, n, n, handle=handle)
+    del x_sub
+    torch.cuda.empty_cache()
+    rng = np.random.default_rng(0)                       # the same group components on every rank
+    comps = {"grey_components": rng.gamma(0.3, 1.0, (m, k)) * (rng.random((m, k)) < 0.3)}
+    times = []
+    for _ in range(3):
+        dist.barrier()
+        t0 = time.perf_counter()
+        dr = nfact_b200.nmf_dual_regression(comps, xsub)
+        times.append(time.perf_counter() - t0)
+        assert np.isfinite(dr["white_components"]).all()
+        del dr
+    xsub.free()
+    t = torch.tensor([min(times)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return {"value": world / float(t), "unit": "subjects/s", "seconds": float(t), "subjects_in_flight": world,
+            "shape": [int(m), int(n), int(k)],
+            "api": "nfact_b200.nmf_dual_regression(components, X) on every rank with its own resident subject "
+                   "(subjects are independent: no collective); seconds = slowest rank, best of 3"}
+
+
 def ingest_benchmark(handle):
     """Group-average ingest (a2-a5) of 3 synthetic C1-shaped subjects (5000 x 10000, 15 % nnz, integer counts
     with duplicates): host COO triplets -> dense float32 on the host, through nfb_ingest_coo; beside it the
@@ -436,6 +468,10 @@ def run_ours(args):
                    "api": "nfact_b200.nmf_decomp(parameters, X_host, W=W0, H=H0) with tol=0" +
                           (f", one call per rank on its {rows} seed rows" if world > 1 else "")}
 
+    # ---- C4 at N > 1: dual-regression subjects are independent, one full-size subject per GPU side by side ----
+    if world > 1 and want_e2e and not args.no_dr:
+        dr_info = dual_regression_across_gpus(torch, dist, dev, handle, m, n, k, density, rank, world)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -479,8 +515,8 @@ def run_ours(args):
     }
     if e2e is not None:
         line["e2e"] = e2e
-        if dr_info is not None:
-            line["dual_regression"] = dr_info
+    if dr_info is not None:
+        line["dual_regression"] = dr_info
     if world == 1 and not args.no_e2e:
         line["ingest"] = ingest_benchmark(handle)
     if not args.no_cpu and world == 1:
