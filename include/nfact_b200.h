@@ -26,6 +26,7 @@ extern "C" {
 
 typedef struct nfb_handle nfb_handle;   /* device + stream + scratch (+ optional NCCL communicator) */
 typedef struct nfb_matrix nfb_matrix;   /* a connectivity matrix X resident in HBM as fp16 hi/lo planes */
+typedef struct nfb_dr_components nfb_dr_components;   /* group components prepared for the dual regression */
 typedef struct nfb_nmf nfb_nmf;         /* NMF solver state for one (X, k): factors, Grams, workspaces */
 
 /* ---- library / handle ------------------------------------------------------------------------ */
@@ -173,6 +174,18 @@ int nfb_dual_regression_post_host(nfb_handle* h, const nfb_matrix* x, int k, con
                                   double zscore, const int32_t* seed_id_host, int n_seeds, double* gs_out,
                                   double* hs_out, double* gs_norm_out, double* hs_norm_out, int* n_unconverged_out,
                                   int* g_nonfinite_out);
+
+/* The subject loop of nfact_dr (NFACT/dual_reg/dual_regression/set_up_dual_regression.py:186-235) regresses every
+ * subject onto the SAME group components: nfb_dr_components_create uploads them once (float32 planes for the
+ * G'X product, float64 Gram matrix G'G; g_nonfinite_out as above) and nfb_dual_regression_resident_host is
+ * nfb_dual_regression_post_host on the prepared object, so a subject costs no component upload.  The object
+ * belongs to the handle it was created on. */
+int nfb_dr_components_create(nfb_handle* h, const void* g_host, int g_is_f32, int64_t m, int k,
+                             nfb_dr_components** out, int* g_nonfinite_out);
+int nfb_dr_components_free(nfb_dr_components* c);
+int nfb_dual_regression_resident_host(nfb_handle* h, const nfb_matrix* x, nfb_dr_components* comps, double zscore,
+                                      const int32_t* seed_id_host, int n_seeds, double* gs_out, double* hs_out,
+                                      double* gs_norm_out, double* hs_norm_out, int* n_unconverged_out);
 
 /* Post-processing of component maps given as host arrays (replaces the numpy / sklearn arithmetic of
  * thresholding :218-238, threshold_grey_components :184-215 and normalise_components :45-68 in

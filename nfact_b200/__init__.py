@@ -6,7 +6,7 @@ and the non-negative dual regression (``nmf_dual_regression``).  All arithmetic 
 ``libnfact_b200.so`` (hand-written CUDA, C ABI in ``include/nfact_b200.h``); there is no CPU path.
 """
 from ._lib import NfbError, load as load_library  # noqa: F401
-from .device import DeviceMatrix, NmfState, get_handle  # noqa: F401
+from .device import DeviceComponents, DeviceMatrix, NmfState, get_handle  # noqa: F401
 from .dual_regression import (dual_regression_subject, nmf_dual_regression, run_decomp, run_locally,  # noqa: F401
                               stream_subjects)
 from .matrix_handling import (avg_fdt, component_loadings, decompress_lz4_frame, load_fdt_matrix,  # noqa: F401

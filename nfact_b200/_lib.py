@@ -77,6 +77,10 @@ SIGNATURES = {
     "nfb_dual_regression_post_host": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_double, c_void_p, c_int,
                                               c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_int),
                                               POINTER(c_int)]),
+    "nfb_dr_components_create": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, POINTER(c_void_p), POINTER(c_int)]),
+    "nfb_dr_components_free": (c_int, [c_void_p]),
+    "nfb_dual_regression_resident_host": (c_int, [c_void_p, c_void_p, c_void_p, c_double, c_void_p, c_int, c_void_p,
+                                                  c_void_p, c_void_p, c_void_p, POINTER(c_int)]),
     "nfb_component_postops_host": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_int64, c_void_p, c_int, c_int,
                                            c_double, c_void_p]),
     "nfb_component_loadings_host": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_int64, c_void_p]),

@@ -42,24 +42,51 @@ int sm_count() {
 std::atomic<int64_t> g_launches{0};
 void note_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+// Device buffer.  alloc(): cudaMalloc / cudaFree -- long-lived solver state and everything that is shared through
+// CUDA IPC (pool memory cannot be).  alloc_pooled(): stream-ordered cudaMallocAsync / cudaFreeAsync for matrices and
+// per-call temporaries: cudaFree synchronises the whole device, so a call that ends on one stream would wait for the
+// next subject's upload running on another (the prefetching dual-regression loop), and a pooled free does not.
+// The pool keeps its default release threshold (unused memory goes back to the driver at the next synchronisation).
 template <typename T>
 struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
+    bool pooled = false;
+    cudaStream_t pool_stream = nullptr;
     DevBuf() = default;
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
     ~DevBuf() { release(); }
     void release() {
-        if (p) cudaFree(p);
+        if (p) {
+            if (pooled && cudaFreeAsync(p, pool_stream) != cudaSuccess) {
+                cudaGetLastError();      // e.g. the stream is gone: fall back to the synchronous free
+                cudaFree(p);
+            } else if (!pooled) {
+                cudaFree(p);
+            }
+        }
         p = nullptr;
         n = 0;
+        pooled = false;
     }
     int alloc(size_t count, bool zero, cudaStream_t stream) {
         release();
         if (count == 0) count = 1;
         NFB_CUDA(cudaMalloc(reinterpret_cast<void**>(&p), count * sizeof(T)));
         n = count;
+        if (zero) NFB_CUDA(cudaMemsetAsync(p, 0, count * sizeof(T), stream));
+        return 0;
+    }
+    int alloc_pooled(size_t count, bool zero, cudaStream_t stream) {
+        release();
+        if (count == 0) count = 1;
+        static const bool use_pool = !(getenv("NFB_POOL") && atoi(getenv("NFB_POOL")) == 0);
+        if (!use_pool) return alloc(count, zero, stream);
+        NFB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&p), count * sizeof(T), stream));
+        n = count;
+        pooled = true;
+        pool_stream = stream;
         if (zero) NFB_CUDA(cudaMemsetAsync(p, 0, count * sizeof(T), stream));
         return 0;
     }
@@ -123,16 +150,20 @@ struct Factor {
     DevBuf<__half> hi, lo;
     DevBuf<float> inv_scale;
     DevBuf<unsigned int> rowmax;
-    int init(int64_t k_, int64_t dim_, bool with_master, cudaStream_t stream, int64_t ld_override = 0) {
+    int init(int64_t k_, int64_t dim_, bool with_master, cudaStream_t stream, int64_t ld_override = 0,
+             bool pooled = false) {
         k = k_;
         kp = round_up64(k_, 16);
         dim = dim_;
         ld = ld_override > 0 ? ld_override : round_up64(std::max<int64_t>(dim_, 1), 8);
-        if (with_master) NFB_TRY(f.alloc(kp * ld, true, stream));
-        NFB_TRY(hi.alloc(kp * ld, true, stream));
-        NFB_TRY(lo.alloc(kp * ld, true, stream));
-        NFB_TRY(inv_scale.alloc(kp, true, stream));
-        NFB_TRY(rowmax.alloc(kp, true, stream));
+        auto get = [&](auto& buf, size_t count) {
+            return pooled ? buf.alloc_pooled(count, true, stream) : buf.alloc(count, true, stream);
+        };
+        if (with_master) NFB_TRY(get(f, kp * ld));
+        NFB_TRY(get(hi, kp * ld));
+        NFB_TRY(get(lo, kp * ld));
+        NFB_TRY(get(inv_scale, kp));
+        NFB_TRY(get(rowmax, kp));
         return 0;
     }
     GemmOperand operand() const { return GemmOperand{hi.p, lo.p, kp, ld}; }
@@ -621,6 +652,19 @@ int nfb_create(int device, void* stream, nfb_handle** out) {
     }
     h->cta_group = gemm_default_cta_group();
     h->phase_timing = getenv("NFB_PHASE_TIMING") != nullptr;
+    {
+        // stream-ordered pool behind DevBuf::alloc_pooled: keep up to half of the device (NFB_POOL_KEEP_GB
+        // overrides) cached between calls instead of handing everything back to the driver at every
+        // synchronisation -- a per-subject loop then re-uses its plane / staging / solution buffers
+        cudaMemPool_t pool = nullptr;
+        size_t free_b = 0, total_b = 0;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+            uint64_t keep = total_b / 2;
+            if (getenv("NFB_POOL_KEEP_GB")) keep = static_cast<uint64_t>(atof(getenv("NFB_POOL_KEEP_GB")) * (1ull << 30));
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
     NFB_TRY(h->d_scal.alloc(16, true, h->stream));
     NFB_TRY(h->d_bits.alloc(16, true, h->stream));
     NFB_TRY(h->d_int.alloc(16, true, h->stream));
@@ -725,9 +769,9 @@ int nfb_matrix_from_device(nfb_handle* h, const float* x_dev, int64_t m, int64_t
     x->m = m;
     x->n = n;
     x->ldp = round_up64(n, 8);
-    NFB_TRY(x->hi.alloc(m * x->ldp, false, h->stream));
-    NFB_TRY(x->lo.alloc(m * x->ldp, false, h->stream));
-    NFB_TRY(x->inv_scale.alloc(1, true, h->stream));
+    NFB_TRY(x->hi.alloc_pooled(m * x->ldp, false, h->stream));
+    NFB_TRY(x->lo.alloc_pooled(m * x->ldp, false, h->stream));
+    NFB_TRY(x->inv_scale.alloc_pooled(1, true, h->stream));
     NFB_CUDA(cudaMemsetAsync(h->d_bits.p, 0, sizeof(unsigned int), h->stream));
     NFB_CUDA(cudaMemsetAsync(h->d_scal.p + 6, 0, 2 * sizeof(double), h->stream));
     NFB_CUDA(cudaMemsetAsync(h->d_int.p + 3, 0, sizeof(int), h->stream));
@@ -757,9 +801,9 @@ int nfb_matrix_from_host(nfb_handle* h, const float* x_host, int64_t m, int64_t 
     x->m = m;
     x->n = n;
     x->ldp = round_up64(n, 8);
-    NFB_TRY(x->hi.alloc(m * x->ldp, false, h->stream));
-    NFB_TRY(x->lo.alloc(m * x->ldp, false, h->stream));
-    NFB_TRY(x->inv_scale.alloc(1, true, h->stream));
+    NFB_TRY(x->hi.alloc_pooled(m * x->ldp, false, h->stream));
+    NFB_TRY(x->lo.alloc_pooled(m * x->ldp, false, h->stream));
+    NFB_TRY(x->inv_scale.alloc_pooled(1, true, h->stream));
     NFB_CUDA(cudaMemsetAsync(h->d_bits.p, 0, sizeof(unsigned int), h->stream));
     NFB_CUDA(cudaMemsetAsync(h->d_scal.p + 6, 0, 2 * sizeof(double), h->stream));
     NFB_CUDA(cudaMemsetAsync(h->d_int.p + 3, 0, sizeof(int), h->stream));
@@ -769,7 +813,7 @@ int nfb_matrix_from_host(nfb_handle* h, const float* x_host, int64_t m, int64_t 
     int rc = 0;
     if (full_bytes + (static_cast<size_t>(2) << 30) < free_b / 2) {
         DevBuf<float> full;
-        NFB_TRY(full.alloc(static_cast<size_t>(m) * n, false, h->stream));
+        NFB_TRY(full.alloc_pooled(static_cast<size_t>(m) * n, false, h->stream));
         // 1 GiB pieces keep the driver's pageable staging pipeline busy and let the max scan overlap the copies
         const int64_t piece_rows = std::max<int64_t>(1, std::min<int64_t>(m, (int64_t(1) << 30) / (4 * n)));
         for (int64_t r0 = 0; r0 < m; r0 += piece_rows) {
@@ -784,7 +828,7 @@ int nfb_matrix_from_host(nfb_handle* h, const float* x_host, int64_t m, int64_t 
     } else {
         const int64_t chunk_rows = std::max<int64_t>(1, std::min<int64_t>(m, (int64_t(1) << 30) / (4 * n)));
         DevBuf<float> stage;
-        NFB_TRY(stage.alloc(chunk_rows * n, false, h->stream));
+        NFB_TRY(stage.alloc_pooled(chunk_rows * n, false, h->stream));
         for (int pass = 0; pass < 2 && rc == 0; ++pass) {
             for (int64_t r0 = 0; r0 < m && rc == 0; r0 += chunk_rows) {
                 const int64_t rows = std::min(chunk_rows, m - r0);
@@ -1137,6 +1181,81 @@ int nfb_host_free(void* p) {
     return 0;
 }
 
+// The group grey components prepared for stage 1 of the dual regression: component-major float32 master + fp16
+// planes (the operand of G'X) and the float64 Gram matrix G'G.  Built once per call by the *_host entry points, or
+// once per subject loop by nfb_dr_components_create (the group maps are the same for every subject).
+struct nfb_dr_components {
+    nfb_handle* h = nullptr;
+    int64_t m = 0;
+    int k = 0;
+    int nonfinite = 0;
+    Factor gt;
+    DevBuf<double> gram64;
+};
+
+static int dr_components_build(nfb_handle* h, const void* g_host, int g_is_f32, int64_t m, int k,
+                               nfb_dr_components* c) {
+    cudaStream_t st = h->stream;
+    c->h = h;
+    c->m = m;
+    c->k = k;
+    NFB_TRY(c->gt.init(k, m, true, st, 0, true));
+    NFB_TRY(c->gram64.alloc_pooled(static_cast<size_t>(k) * k, false, st));
+    DevBuf<double> g64;
+    NFB_TRY(g64.alloc_pooled(static_cast<size_t>(m) * k, false, st));
+    NFB_CUDA(cudaMemsetAsync(h->d_int.p + 2, 0, sizeof(int), st));
+    // group grey components: [m, k] float64 or float32 -> component-major float32 master + planes
+    // (scipy's nnls casts to float64; the product G'X runs on the float32 value either way)
+    { NFB_PHASE(h, "g_upload");
+    if (g_is_f32) {
+        float* g32 = reinterpret_cast<float*>(g64.p);
+        NFB_CUDA(cudaMemcpyAsync(g32, g_host, sizeof(float) * m * k, cudaMemcpyHostToDevice, st));
+        NFB_TRY(transpose_f32(g32, m, k, k, c->gt.f.p, c->gt.ld, st, h->d_int.p + 2));
+    } else {
+        NFB_CUDA(cudaMemcpyAsync(g64.p, g_host, sizeof(double) * m * k, cudaMemcpyHostToDevice, st));
+        NFB_TRY(transpose_f64_to_f32(g64.p, m, k, k, c->gt.f.p, c->gt.ld, st, h->d_int.p + 2));
+    }
+    NFB_TRY(refresh_planes(c->gt, c->gt.f.p, nullptr, true, st));
+    }
+    { NFB_PHASE(h, "gram1"); NFB_TRY(gram_f64(c->gt.f.p, k, m, c->gt.ld, c->gram64.p, st)); }
+    NFB_CUDA(cudaMemcpyAsync(&c->nonfinite, h->d_int.p + 2, sizeof(int), cudaMemcpyDeviceToHost, st));
+    NFB_CUDA(cudaStreamSynchronize(st));      // g64 (and the pageable host source) are done with
+    return 0;
+}
+
+static int dr_solve(nfb_handle* h, const nfb_matrix* x, nfb_dr_components& comps, double zscore,
+                    const int32_t* seed_id_host, int n_seeds, double* gs_out, double* hs_out, double* gs_norm_out,
+                    double* hs_norm_out, int* n_unconverged_out);
+
+int nfb_dr_components_create(nfb_handle* h, const void* g_host, int g_is_f32, int64_t m, int k,
+                             nfb_dr_components** out, int* g_nonfinite_out) {
+    NFB_CHECK(h != nullptr && g_host != nullptr && out != nullptr, "NULL argument");
+    NFB_CHECK(m >= 1 && k >= 1 && k <= 512, "n_components must be in [1, 512] in this build");
+    NFB_CUDA(cudaSetDevice(h->device));
+    std::unique_ptr<nfb_dr_components> c(new nfb_dr_components());
+    NFB_TRY(dr_components_build(h, g_host, g_is_f32, m, k, c.get()));
+    if (g_nonfinite_out) *g_nonfinite_out = c->nonfinite;
+    *out = c.release();
+    return 0;
+}
+
+int nfb_dr_components_free(nfb_dr_components* c) {
+    delete c;
+    return 0;
+}
+
+int nfb_dual_regression_resident_host(nfb_handle* h, const nfb_matrix* x, nfb_dr_components* comps, double zscore,
+                                      const int32_t* seed_id_host, int n_seeds, double* gs_out, double* hs_out,
+                                      double* gs_norm_out, double* hs_norm_out, int* n_unconverged_out) {
+    NFB_CHECK(h != nullptr && x != nullptr && comps != nullptr, "NULL argument");
+    NFB_CHECK(comps->h == h, "the components were prepared on another handle");
+    NFB_CHECK(comps->m == x->m, "Incompatible dimensions: the components have " + std::to_string(comps->m) +
+                                    " rows, the matrix " + std::to_string(x->m));
+    NFB_CUDA(cudaSetDevice(h->device));
+    return dr_solve(h, x, *comps, zscore, seed_id_host, n_seeds, gs_out, hs_out, gs_norm_out, hs_norm_out,
+                    n_unconverged_out);
+}
+
 int nfb_dual_regression_host(nfb_handle* h, const nfb_matrix* x, int k, const void* g_host, int g_is_f32,
                              double* gs_out, double* hs_out, int* n_unconverged_out, int* g_nonfinite_out) {
     return nfb_dual_regression_post_host(h, x, k, g_host, g_is_f32, 0.0, nullptr, 0, gs_out, hs_out, nullptr, nullptr,
@@ -1148,48 +1267,45 @@ int nfb_dual_regression_post_host(nfb_handle* h, const nfb_matrix* x, int k, con
                                   double* hs_out, double* gs_norm_out, double* hs_norm_out, int* n_unconverged_out,
                                   int* g_nonfinite_out) {
     NFB_CHECK(h != nullptr && x != nullptr && g_host != nullptr, "NULL argument");
-    NFB_CHECK(zscore == 0.0 || (seed_id_host != nullptr && n_seeds >= 1 && n_seeds <= 4096),
-              "thresholding needs the seed index of every row and 1..4096 seeds");
     NFB_CHECK(k >= 1 && k <= 512, "n_components must be in [1, 512] in this build");
     NFB_CUDA(cudaSetDevice(h->device));
+    nfb_dr_components comps;
+    NFB_TRY(dr_components_build(h, g_host, g_is_f32, x->m, k, &comps));
+    if (g_nonfinite_out) *g_nonfinite_out = comps.nonfinite;
+    return dr_solve(h, x, comps, zscore, seed_id_host, n_seeds, gs_out, hs_out, gs_norm_out, hs_norm_out,
+                    n_unconverged_out);
+}
+
+static int dr_solve(nfb_handle* h, const nfb_matrix* x, nfb_dr_components& comps, double zscore,
+                    const int32_t* seed_id_host, int n_seeds, double* gs_out, double* hs_out, double* gs_norm_out,
+                    double* hs_norm_out, int* n_unconverged_out) {
+    NFB_CHECK(zscore == 0.0 || (seed_id_host != nullptr && n_seeds >= 1 && n_seeds <= 4096),
+              "thresholding needs the seed index of every row and 1..4096 seeds");
     cudaStream_t st = h->stream;
+    const int k = comps.k;
     const int64_t m = x->m, n = x->n, kp = round_up64(k, 16);
     const int cg = h->cta_group;
-    Factor gt, hs;
-    NFB_TRY(gt.init(k, m, true, st));
-    NFB_TRY(hs.init(k, n, true, st));
+    Factor& gt = comps.gt;
+    Factor hs;
+    NFB_TRY(hs.init(k, n, true, st, 0, true));
     DevBuf<double> g64, gram64, sol_h, sol_g;
-    // g64 holds the uploaded group components first and the transposed stage-2 solution [m, k] at the end
-    NFB_TRY(g64.alloc(static_cast<size_t>(m) * k, false, st));
-    NFB_TRY(gram64.alloc(static_cast<size_t>(k) * k, false, st));
-    NFB_TRY(sol_h.alloc(static_cast<size_t>(k) * hs.ld, true, st));
-    NFB_TRY(sol_g.alloc(static_cast<size_t>(k) * gt.ld, true, st));
+    // g64 receives the transposed stage-2 solution [m, k] at the end; gram64 is stage 2's Gram matrix
+    NFB_TRY(g64.alloc_pooled(static_cast<size_t>(m) * k, false, st));
+    NFB_TRY(gram64.alloc_pooled(static_cast<size_t>(k) * k, false, st));
+    NFB_TRY(sol_h.alloc_pooled(static_cast<size_t>(k) * hs.ld, true, st));
+    NFB_TRY(sol_g.alloc_pooled(static_cast<size_t>(k) * gt.ld, true, st));
     const int s1 = gemm_pick_splits(n, m, cg, k), s2 = gemm_pick_splits(m, n, cg, k);
     DevBuf<float> part;
-    NFB_TRY(part.alloc(std::max(static_cast<size_t>(s1) * k * hs.ld, static_cast<size_t>(s2) * k * gt.ld), false, st));
-    NFB_CUDA(cudaMemsetAsync(h->d_int.p, 0, 3 * sizeof(int), st));
+    NFB_TRY(part.alloc_pooled(std::max(static_cast<size_t>(s1) * k * hs.ld, static_cast<size_t>(s2) * k * gt.ld), false, st));
+    NFB_CUDA(cudaMemsetAsync(h->d_int.p, 0, 2 * sizeof(int), st));
     NFB_CUDA(cudaMemsetAsync(h->d_scal.p + 8, 0, 2 * sizeof(double), st));
-    // group grey components: [m, k] float64 or float32 -> component-major float32 master + planes
-    // (scipy's nnls casts to float64; the product G'X runs on the float32 value either way)
-    { NFB_PHASE(h, "g_upload");
-    if (g_is_f32) {
-        float* g32 = reinterpret_cast<float*>(g64.p);
-        NFB_CUDA(cudaMemcpyAsync(g32, g_host, sizeof(float) * m * k, cudaMemcpyHostToDevice, st));
-        NFB_TRY(transpose_f32(g32, m, k, k, gt.f.p, gt.ld, st, h->d_int.p + 2));
-    } else {
-        NFB_CUDA(cudaMemcpyAsync(g64.p, g_host, sizeof(double) * m * k, cudaMemcpyHostToDevice, st));
-        NFB_TRY(transpose_f64_to_f32(g64.p, m, k, k, gt.f.p, gt.ld, st, h->d_int.p + 2));
-    }
-    NFB_TRY(refresh_planes(gt, gt.f.p, nullptr, true, st));
-    }
     // ---- stage 1: white matter.  Hs[:, j] = nnls(G, X[:, j])  (dual_regression_methods.py:137-149)
-    { NFB_PHASE(h, "gram1"); NFB_TRY(gram_f64(gt.f.p, k, m, gt.ld, gram64.p, st)); }
     { NFB_PHASE(h, "gemm_gtx");
     NFB_TRY(gemm_split(x->operand(), true, gt.operand(), n, m, static_cast<int>(kp), k, part.p, hs.ld, s1,
                        gt.inv_scale.p, nullptr, x->inv_scale_host, cg, st));
     }
     { NFB_PHASE(h, "nnls1");
-    NFB_TRY(nnls_gram_batched(gram64.p, k, part.p, s1, static_cast<int64_t>(k) * hs.ld, hs.ld, n, sol_h.p, hs.ld,
+    NFB_TRY(nnls_gram_batched(comps.gram64.p, k, part.p, s1, static_cast<int64_t>(k) * hs.ld, hs.ld, n, sol_h.p, hs.ld,
                               400, h->d_int.p, st, reinterpret_cast<unsigned long long*>(h->d_scal.p + 8),
                               reinterpret_cast<unsigned long long*>(h->d_scal.p + 10)));
     }
@@ -1205,8 +1321,8 @@ int nfb_dual_regression_post_host(nfb_handle* h, const nfb_matrix* x, int k, con
     DevBuf<double> stats, norm;
     DevBuf<int> seed_dev;
     if (post || hs_norm_out || gs_norm_out) {
-        NFB_TRY(stats.alloc(static_cast<size_t>(4) * k * std::max(1, n_seeds), false, st));
-        if (hs_norm_out || gs_norm_out) NFB_TRY(norm.alloc(static_cast<size_t>(k) * std::max(hs.ld, gt.ld), false, st));
+        NFB_TRY(stats.alloc_pooled(static_cast<size_t>(4) * k * std::max(1, n_seeds), false, st));
+        if (hs_norm_out || gs_norm_out) NFB_TRY(norm.alloc_pooled(static_cast<size_t>(k) * std::max(hs.ld, gt.ld), false, st));
     }
     { NFB_PHASE(h, "post_h");
     if (post) NFB_TRY(comp_threshold<double>(sol_h.p, k, n, hs.ld, nullptr, 1, zscore, stats.p, st));
@@ -1243,7 +1359,7 @@ int nfb_dual_regression_post_host(nfb_handle* h, const nfb_matrix* x, int k, con
     { NFB_PHASE(h, "post_g");
     if (post) {
         // threshold_grey_components: statistics per (component, seed); rows of no listed seed stay as they are
-        NFB_TRY(seed_dev.alloc(static_cast<size_t>(m), false, st));
+        NFB_TRY(seed_dev.alloc_pooled(static_cast<size_t>(m), false, st));
         NFB_CUDA(cudaMemcpyAsync(seed_dev.p, seed_id_host, sizeof(int) * m, cudaMemcpyHostToDevice, st));
         NFB_TRY(comp_threshold<double>(sol_g.p, k, m, gt.ld, seed_dev.p, n_seeds, zscore, stats.p, st));
     }
@@ -1260,15 +1376,14 @@ int nfb_dual_regression_post_host(nfb_handle* h, const nfb_matrix* x, int k, con
         NFB_CUDA(cudaMemcpyAsync(gs_norm_out, g64.p, sizeof(double) * m * k, cudaMemcpyDeviceToHost, st));
     }
     }
-    int status[3] = {0, 0, 0};
-    NFB_CUDA(cudaMemcpyAsync(status, h->d_int.p, 3 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    int status[2] = {0, 0};
+    NFB_CUDA(cudaMemcpyAsync(status, h->d_int.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
     NFB_CUDA(cudaStreamSynchronize(st));
     if (hs_ready) {
         NFB_CUDA(cudaStreamSynchronize(h->copy_stream));
         cudaEventDestroy(hs_ready);
     }
     if (n_unconverged_out) *n_unconverged_out = status[0] + status[1];
-    if (g_nonfinite_out) *g_nonfinite_out = status[2];
     report_phases(h, 1);
     if (getenv("NFB_DR_STATS")) {
         unsigned long long steps[2] = {0, 0};
@@ -1292,8 +1407,8 @@ static int component_postops(nfb_handle* h, T* data, int comp_major, int64_t k, 
     DevBuf<T> raw, cm, norm;
     DevBuf<double> stats;
     DevBuf<int> gid;
-    NFB_TRY(cm.alloc(static_cast<size_t>(k) * ld, false, st));
-    NFB_TRY(stats.alloc(static_cast<size_t>(4) * k * groups, false, st));
+    NFB_TRY(cm.alloc_pooled(static_cast<size_t>(k) * ld, false, st));
+    NFB_TRY(stats.alloc_pooled(static_cast<size_t>(4) * k * groups, false, st));
     auto transpose = [&](const T* in, int64_t rows, int64_t cols, int64_t ld_in, T* out, int64_t ld_out) -> int {
         if constexpr (sizeof(T) == 8) return transpose_f64(in, rows, cols, ld_in, out, ld_out, st);
         else return transpose_f32(in, rows, cols, ld_in, out, ld_out, st);
@@ -1302,13 +1417,13 @@ static int component_postops(nfb_handle* h, T* data, int comp_major, int64_t k, 
         NFB_CUDA(cudaMemcpy2DAsync(cm.p, ld * sizeof(T), data, len * sizeof(T), len * sizeof(T), k,
                                    cudaMemcpyHostToDevice, st));
     } else {   // [len, k] on the host (grey components): component-major on the device
-        NFB_TRY(raw.alloc(static_cast<size_t>(k) * len, false, st));
+        NFB_TRY(raw.alloc_pooled(static_cast<size_t>(k) * len, false, st));
         NFB_CUDA(cudaMemcpyAsync(raw.p, data, sizeof(T) * k * len, cudaMemcpyHostToDevice, st));
         NFB_TRY(transpose(raw.p, len, k, k, cm.p, ld));
     }
     if (do_threshold) {
         if (group_id) {
-            NFB_TRY(gid.alloc(static_cast<size_t>(len), false, st));
+            NFB_TRY(gid.alloc_pooled(static_cast<size_t>(len), false, st));
             NFB_CUDA(cudaMemcpyAsync(gid.p, group_id, sizeof(int) * len, cudaMemcpyHostToDevice, st));
         }
         NFB_TRY(comp_threshold<T>(cm.p, k, len, ld, group_id ? gid.p : nullptr, groups, zscore, stats.p, st));
@@ -1321,7 +1436,7 @@ static int component_postops(nfb_handle* h, T* data, int comp_major, int64_t k, 
         }
     }
     if (norm_out) {
-        NFB_TRY(norm.alloc(static_cast<size_t>(k) * ld, false, st));
+        NFB_TRY(norm.alloc_pooled(static_cast<size_t>(k) * ld, false, st));
         NFB_TRY(comp_standardize<T>(cm.p, k, len, ld, norm.p, ld, stats.p, st));
         if (comp_major) {
             NFB_CUDA(cudaMemcpy2DAsync(norm_out, len * sizeof(T), norm.p, ld * sizeof(T), len * sizeof(T), k,
@@ -1343,11 +1458,11 @@ static int component_loadings(nfb_handle* h, const T* subject, const T* group, i
     const int64_t ld = round_up64(len, 8);
     DevBuf<T> raw, cm[2];
     DevBuf<double> out;
-    NFB_TRY(out.alloc(static_cast<size_t>(k), false, st));
-    if (!comp_major) NFB_TRY(raw.alloc(static_cast<size_t>(k) * len, false, st));
+    NFB_TRY(out.alloc_pooled(static_cast<size_t>(k), false, st));
+    if (!comp_major) NFB_TRY(raw.alloc_pooled(static_cast<size_t>(k) * len, false, st));
     const T* src[2] = {subject, group};
     for (int a = 0; a < 2; ++a) {
-        NFB_TRY(cm[a].alloc(static_cast<size_t>(k) * ld, false, st));
+        NFB_TRY(cm[a].alloc_pooled(static_cast<size_t>(k) * ld, false, st));
         if (comp_major) {
             NFB_CUDA(cudaMemcpy2DAsync(cm[a].p, ld * sizeof(T), src[a], len * sizeof(T), len * sizeof(T), k,
                                        cudaMemcpyHostToDevice, st));
@@ -1438,12 +1553,12 @@ int nfb_ingest_coo(nfb_handle* h, int n_subjects, const int32_t* const* rows_hos
     DevBuf<double> tmp, acc, vals;
     DevBuf<int> rows, cols;
     DevBuf<float> xblk;
-    NFB_TRY(tmp.alloc(static_cast<size_t>(blk_rows) * ncols, true, st));
-    if (!single) NFB_TRY(acc.alloc(static_cast<size_t>(blk_rows) * ncols, false, st));
-    if (x_out_dev == nullptr) NFB_TRY(xblk.alloc(static_cast<size_t>(blk_rows) * ncols, false, st));
-    NFB_TRY(rows.alloc(max_nnz, false, st));
-    NFB_TRY(cols.alloc(max_nnz, false, st));
-    NFB_TRY(vals.alloc(max_nnz, false, st));
+    NFB_TRY(tmp.alloc_pooled(static_cast<size_t>(blk_rows) * ncols, true, st));
+    if (!single) NFB_TRY(acc.alloc_pooled(static_cast<size_t>(blk_rows) * ncols, false, st));
+    if (x_out_dev == nullptr) NFB_TRY(xblk.alloc_pooled(static_cast<size_t>(blk_rows) * ncols, false, st));
+    NFB_TRY(rows.alloc_pooled(max_nnz, false, st));
+    NFB_TRY(cols.alloc_pooled(max_nnz, false, st));
+    NFB_TRY(vals.alloc_pooled(max_nnz, false, st));
     NFB_CUDA(cudaMemsetAsync(h->d_int.p + 2, 0, sizeof(int), st));
     marks.mark("alloc+zero");
     const double recip = 1.0 / static_cast<double>(n_subjects);
@@ -1499,17 +1614,21 @@ static int ingest_single_to_planes(nfb_handle* h, const int32_t* rows_host, cons
     DevBuf<unsigned int> mask;
     DevBuf<int> rows, cols;
     DevBuf<double> vals;
-    NFB_TRY(x->hi.alloc(cells, false, st));
-    NFB_TRY(x->lo.alloc(cells, false, st));
-    NFB_TRY(x->inv_scale.alloc(1, true, st));
-    NFB_TRY(mask.alloc((cells + 31) / 32, false, st));
-    NFB_TRY(rows.alloc(nnz, false, st));
-    NFB_TRY(cols.alloc(nnz, false, st));
-    NFB_TRY(vals.alloc(nnz, false, st));
+    NFB_TRY(x->hi.alloc_pooled(cells, false, st));
+    NFB_TRY(x->lo.alloc_pooled(cells, false, st));
+    NFB_TRY(x->inv_scale.alloc_pooled(1, true, st));
+    NFB_TRY(mask.alloc_pooled((cells + 31) / 32, false, st));
+    NFB_TRY(rows.alloc_pooled(nnz, false, st));
+    NFB_TRY(cols.alloc_pooled(nnz, false, st));
+    NFB_TRY(vals.alloc_pooled(nnz, false, st));
     marks.mark("alloc");
     // the triplets travel on the copy stream while the planes and the mask are zeroed on the main one
+    // (the staging buffers are stream-ordered allocations of the main stream: the copy stream may only touch
+    // them after the point of allocation)
     cudaEvent_t uploaded = nullptr;
     NFB_CUDA(cudaEventCreateWithFlags(&uploaded, cudaEventDisableTiming));
+    NFB_CUDA(cudaEventRecord(uploaded, st));
+    NFB_CUDA(cudaStreamWaitEvent(h->copy_stream, uploaded, 0));
     NFB_CUDA(cudaMemcpyAsync(rows.p, rows_host, sizeof(int) * nnz, cudaMemcpyHostToDevice, h->copy_stream));
     NFB_CUDA(cudaMemcpyAsync(cols.p, cols_host, sizeof(int) * nnz, cudaMemcpyHostToDevice, h->copy_stream));
     NFB_CUDA(cudaMemcpyAsync(vals.p, vals_host, sizeof(double) * nnz, cudaMemcpyHostToDevice, h->copy_stream));
@@ -1561,7 +1680,7 @@ int nfb_ingest_coo_matrix(nfb_handle* h, int n_subjects, const int32_t* const* r
     // group average, or duplicate coordinates to be summed in float64: the exact scatter-add path.
     // The float32 matrix exists only on the device and only until its fp16 planes are built.
     DevBuf<float> dense;
-    NFB_TRY(dense.alloc(static_cast<size_t>(nrows) * ncols, false, h->stream));
+    NFB_TRY(dense.alloc_pooled(static_cast<size_t>(nrows) * ncols, false, h->stream));
     NFB_TRY(nfb_ingest_coo(h, n_subjects, rows_host, cols_host, vals_host, nnz, scale, nrows, ncols, group_mode,
                            nullptr, dense.p));
     HostMarks marks(h->stream);

@@ -160,6 +160,44 @@ class DeviceMatrix:
             pass
 
 
+class DeviceComponents:
+    """The group grey components ``[m, k]`` prepared once for many dual regressions on one handle
+    (``nfb_dr_components_create``): the nfact_dr subject loop regresses every subject onto the same maps."""
+
+    def __init__(self, grey: np.ndarray, handle: Handle | None = None):
+        grey = np.asarray(grey)
+        if grey.dtype != np.float32:          # scipy's nnls casts everything else to float64
+            grey = grey.astype(np.float64, copy=False)
+        grey = np.ascontiguousarray(grey)
+        if grey.ndim != 2:
+            raise ValueError(f"Expected a 2D array, but the shape of A is {grey.shape}")
+        self.handle = handle or get_handle()
+        self.shape = grey.shape
+        self._ptr = c_void_p()
+        nonfinite = c_int()
+        check(self.handle.lib.nfb_dr_components_create(self.handle.ptr, c_void_p(grey.ctypes.data),
+                                                       int(grey.dtype == np.float32), grey.shape[0], grey.shape[1],
+                                                       byref(self._ptr), byref(nonfinite)))
+        self.has_nonfinite = bool(nonfinite.value)
+
+    @property
+    def ptr(self) -> c_void_p:
+        if not self._ptr:
+            raise ValueError("the components have been freed")
+        return self._ptr
+
+    def free(self) -> None:
+        if self._ptr:
+            self.handle.lib.nfb_dr_components_free(self._ptr)
+            self._ptr = c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
 def make_params(solver: str, max_iter: int, tol: float, regs, verbose: int = 0) -> NmfParams:
     if solver not in ("cd", "mu"):
         raise ValueError(f"Invalid solver parameter '{solver}'.")

@@ -12,7 +12,7 @@ from ctypes import byref, c_int
 import numpy as np
 
 from ._lib import check, pinned_empty
-from .device import DeviceMatrix
+from .device import DeviceComponents, DeviceMatrix
 from .utils import error_and_exit
 
 
@@ -27,12 +27,15 @@ def nmf_dual_regression(components: dict, connectivity_matrix, n_jobs: int = 1, 
     post-processing the pipeline runs next (run_dual_regression.py:166-186) applied on the device before the
     results are copied out -- ``threshold`` != 0: ``thresholding_components`` with ``seeds_id`` (the seed index of
     every row) and ``n_seeds``; ``normalise``: adds "normalised_grey" / "normalised_white"."""
-    grey = np.asarray(components["grey_components"])
-    if grey.dtype != np.float32:          # scipy's nnls casts everything else to float64
-        grey = grey.astype(np.float64, copy=False)
-    grey = np.ascontiguousarray(grey)
-    if grey.ndim != 2:
-        raise ValueError(f"Expected a 2D array, but the shape of A is {grey.shape}")
+    grey = components["grey_components"]
+    prepared = grey if isinstance(grey, DeviceComponents) else None     # uploaded once by the subject loop
+    if prepared is None:
+        grey = np.asarray(grey)
+        if grey.dtype != np.float32:          # scipy's nnls casts everything else to float64
+            grey = grey.astype(np.float64, copy=False)
+        grey = np.ascontiguousarray(grey)
+        if grey.ndim != 2:
+            raise ValueError(f"Expected a 2D array, but the shape of A is {grey.shape}")
     if isinstance(connectivity_matrix, DeviceMatrix):
         xdev, owns = connectivity_matrix, False
     else:
@@ -58,11 +61,16 @@ def nmf_dual_regression(components: dict, connectivity_matrix, n_jobs: int = 1, 
             n_seeds = int(n_seeds) if seeds_id is not None else 1
         bad, nonfinite = c_int(), c_int()
         h = xdev.handle
-        check(h.lib.nfb_dual_regression_post_host(
-            h.ptr, xdev.ptr, k, grey.ctypes.data, int(grey.dtype == np.float32), float(threshold),
-            seed_arr.ctypes.data if seed_arr is not None else None, int(n_seeds), gs.ctypes.data, hs.ctypes.data,
-            gs_norm.ctypes.data if normalise else None, hs_norm.ctypes.data if normalise else None,
-            byref(bad), byref(nonfinite)))
+        post = (float(threshold), seed_arr.ctypes.data if seed_arr is not None else None, int(n_seeds),
+                gs.ctypes.data, hs.ctypes.data, gs_norm.ctypes.data if normalise else None,
+                hs_norm.ctypes.data if normalise else None)
+        if prepared is not None:
+            nonfinite.value = int(prepared.has_nonfinite)
+            check(h.lib.nfb_dual_regression_resident_host(h.ptr, xdev.ptr, prepared.ptr, *post, byref(bad)))
+        else:
+            check(h.lib.nfb_dual_regression_post_host(h.ptr, xdev.ptr, k, grey.ctypes.data,
+                                                      int(grey.dtype == np.float32), *post, byref(bad),
+                                                      byref(nonfinite)))
         if nonfinite.value:               # checked on the device while G is transposed
             raise ValueError("array must not contain infs or NaNs")
         if bad.value:
@@ -147,12 +155,17 @@ def stream_subjects(load_matrix, n_subjects: int, components: dict, device: int 
     from .device import Handle, get_handle
     first = get_handle(device)
     handles = [first, Handle(first.device)] if prefetch and n_subjects > 1 else [first]
+    # the group maps are the same for every subject: uploaded once per handle, not once per subject
+    grey = components["grey_components"]
+    prepared = [grey if isinstance(grey, DeviceComponents) else DeviceComponents(grey, hd) for hd in handles] \
+        if n_subjects > 0 else []
+    per_handle = [dict(components, grey_components=prep) for prep in prepared]
     try:
         if len(handles) == 1:
             for idx in range(n_subjects):
                 xdev = load_matrix(idx, first)
                 try:
-                    yield idx, nmf_dual_regression(components, xdev, **options(idx))
+                    yield idx, nmf_dual_regression(per_handle[0], xdev, **options(idx))
                 finally:
                     xdev.free()
             return
@@ -163,11 +176,15 @@ def stream_subjects(load_matrix, n_subjects: int, components: dict, device: int 
                 if idx + 1 < n_subjects:
                     pending = pool.submit(load_matrix, idx + 1, handles[(idx + 1) % 2])
                 try:
-                    result = nmf_dual_regression(components, xdev, **options(idx))   # on the stream that loaded xdev
+                    result = nmf_dual_regression(per_handle[idx % 2], xdev, **options(idx))   # on xdev's stream
                 finally:
                     xdev.free()
                 yield idx, result
+                result = None     # let the page-locked result blocks go back to the pool before the next subject
     finally:
+        for prep in prepared:
+            if prep is not grey:
+                prep.free()
         for extra in handles[1:]:
             extra.close()
 
@@ -177,7 +194,8 @@ def run_locally(list_of_subject_dirs: list, components: dict, seeds: list, thres
     """Subject loop of NFACT/dual_reg/dual_regression/set_up_dual_regression.py:186-235.  Subjects are
     independent: with ``world`` processes (one per GPU) rank r takes subjects r, r+world, ... and no
     collective is needed.  ``save(subject_dir, dr_results)`` receives each result (the reference's image
-    writer); the results of this rank are also returned keyed by subject directory.  The next subject's
+    writer); without ``save`` the results of this rank are returned keyed by subject directory (with it the
+    dictionary only records which subjects were done).  The next subject's
     matrix is parsed and ingested while the current one is being regressed (``stream_subjects``)."""
     import os
     from .matrix_handling import load_fdt_matrix
@@ -195,7 +213,9 @@ def run_locally(list_of_subject_dirs: list, components: dict, seeds: list, thres
         for idx, dr_results in stream_subjects(load, len(mine), components, prefetch=prefetch, options=options):
             if save is not None:
                 save(mine[idx], dr_results)
-            out[mine[idx]] = dr_results
+            # results are only kept when nobody consumes them on the way (100 C3-sized subjects are 27 GB)
+            out[mine[idx]] = dr_results if save is None else None
+            del dr_results
     except ValueError as e:
         error_and_exit(False, f"Components have incompatable size with connectivity Matrix {e}")
     except SystemExit:

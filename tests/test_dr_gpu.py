@@ -121,3 +121,40 @@ def test_run_locally_prefetch_equals_sequential(golden, tmp_path):
     # rank r of `world` takes subjects r, r + world, ...
     part = nfact_b200.run_locally(dirs, comps, ["L", "R"], threshold=2, rank=1, world=2)
     assert list(part) == [dirs[1]] and np.array_equal(part[dirs[1]]["white_components"], seq[dirs[1]]["white_components"])
+
+
+def test_prepared_components_equal_host_components(golden, tmp_path):
+    """DeviceComponents (group maps uploaded once for the whole subject loop, nfb_dr_components_create +
+    nfb_dual_regression_resident_host) give bit-identical results to passing the host array every time;
+    float32 maps, non-finite maps and a shape mismatch behave as on the host path."""
+    import os
+    import shutil
+    import nfact_b200
+    from conftest import GOLDEN_DIR
+    X = golden["ingest_single_1"]
+    for dtype in (np.float64, np.float32):
+        G = golden["cd_fit_W"].astype(dtype)
+        host = nfact_b200.nmf_dual_regression({"grey_components": G}, X)
+        prep = nfact_b200.DeviceComponents(G)
+        assert prep.shape == G.shape and not prep.has_nonfinite
+        for _ in range(2):                                    # re-used across subjects
+            dev = nfact_b200.nmf_dual_regression({"grey_components": prep}, X, threshold=0)
+            assert np.array_equal(dev["grey_components"], host["grey_components"])
+            assert np.array_equal(dev["white_components"], host["white_components"])
+        with pytest.raises(ValueError):
+            nfact_b200.nmf_dual_regression({"grey_components": prep}, X[:50])
+        prep.free()
+        with pytest.raises(ValueError):
+            nfact_b200.nmf_dual_regression({"grey_components": prep}, X)
+    bad = golden["cd_fit_W"].astype(np.float64)
+    bad[3, 2] = np.inf
+    with pytest.raises(ValueError):
+        nfact_b200.nmf_dual_regression({"grey_components": nfact_b200.DeviceComponents(bad)}, X)
+    # run_locally with a save callback hands every result to it and keeps none
+    sub = tmp_path / "sub-1"
+    shutil.copytree(os.path.join(GOLDEN_DIR, "data", "sub-1"), sub)
+    np.savetxt(sub / "coords_for_fdt_matrix2", np.zeros((99, 5), dtype=int), fmt="%d")
+    saved = {}
+    out = nfact_b200.run_locally([str(sub)], {"grey_components": golden["cd_fit_W"].astype(np.float64)}, ["L"],
+                                 threshold=0, save=lambda d, r: saved.update({d: r["white_components"].copy()}))
+    assert out == {str(sub): None} and saved[str(sub)].shape == (10, 199)
