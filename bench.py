@@ -402,6 +402,10 @@ def run_ours(args):
             x_np = x_host.numpy()
             import nfact_b200.device as nfdev
             nfdev.set_default_handle(handle)
+            # warm-up call (one iteration): first-use costs that are not part of a steady-state solve -- page-locking
+            # the result arrays (cudaHostAlloc of 136 MB took 0.06 - 0.4 s between runs), growing the device pool
+            warm = nfact_b200.nmf_decomp(dict(params, max_iter=1), x_np, W=w0_host, H=h0_host)
+            del warm
             if world > 1:
                 dist.barrier()
             torch.cuda.synchronize()
