@@ -64,6 +64,25 @@ int nfb_ingest_coo_matrix(nfb_handle* h, int n_subjects, const int32_t* const* r
                           const int32_t* const* cols_host, const double* const* vals_host, const int64_t* nnz,
                           const double* scale, int64_t nrows, int64_t ncols, int group_mode, nfb_matrix** out);
 
+/* The whole single-subject load on the device: the bytes of fdt_matrix2.dot (decompressed) are uploaded, parsed by
+ * the GPU (what np.loadtxt + the index arithmetic of NFACT/base/matrix_handling.py:93-137 do), scaled by
+ * `scale` = 1e8 / waytotal and written straight into the resident operand planes; shape_out[2] = (nrows, ncols)
+ * from the file's last line.  Numbers are converted exactly (one correctly rounded IEEE operation) when they have
+ * at most 19 significant digits, a mantissa <= 2^53 and a decimal exponent within +-22 -- probtrackx's integer
+ * counts and %g output.  *fallback_out != 0 and *out == NULL when the file needs the host path instead: 1 = a
+ * number outside that fast path (or inf / nan), 2 = duplicate coordinates (summed in float64 by the reference);
+ * the caller then uses nfb_dot_parse_coo + nfb_ingest_coo_matrix.  Malformed lines and index errors are errors
+ * with the same messages as nfb_dot_parse_coo. */
+int nfb_ingest_dot_matrix(nfb_handle* h, const char* text_host, int64_t len, double scale, nfb_matrix** out,
+                          int64_t* shape_out, int* fallback_out);
+
+/* The same device parse, but the triplets come back to the host (what the group average, which adds subjects in
+ * float64 from host triplets, needs): 0-based int32 rows / cols and float64 values of all lines but the last in
+ * page-locked blocks from nfb_host_alloc (the caller releases them with nfb_host_free), their number in *nnz_out,
+ * the last line in shape_out[2].  *fallback_out = 1 (and NULL arrays) when the file needs nfb_dot_parse_coo. */
+int nfb_dot_parse_coo_gpu(nfb_handle* h, const char* text_host, int64_t len, int32_t** rows0_out, int32_t** cols0_out,
+                          double** vals_out, int64_t* nnz_out, int64_t* shape_out, int* fallback_out);
+
 /* Text parser for fdt_matrix2.dot (replaces np.loadtxt at NFACT/base/matrix_handling.py:93-113).
  * `buf` is the (decompressed) file content.  Two calls: count the non-empty lines, then fill three
  * float64 arrays of that length with the row / column / value columns (the last line is the matrix

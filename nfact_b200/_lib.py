@@ -45,6 +45,10 @@ SIGNATURES = {
     "nfb_ingest_coo_matrix": (c_int, [c_void_p, c_int, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p),
                                       POINTER(c_int64), POINTER(c_double), c_int64, c_int64, c_int,
                                       POINTER(c_void_p)]),
+    "nfb_ingest_dot_matrix": (c_int, [c_void_p, c_void_p, c_int64, c_double, POINTER(c_void_p), POINTER(c_int64),
+                                      POINTER(c_int)]),
+    "nfb_dot_parse_coo_gpu": (c_int, [c_void_p, c_void_p, c_int64, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p),
+                                      POINTER(c_int64), POINTER(c_int64), POINTER(c_int)]),
     "nfb_dot_count_lines": (c_int, [c_void_p, c_int64, c_int, POINTER(c_int64)]),
     "nfb_dot_parse": (c_int, [c_void_p, c_int64, c_int, c_int64, c_void_p, c_void_p, c_void_p]),
     "nfb_dot_parse_coo": (c_int, [c_void_p, c_int64, c_int, c_int64, c_void_p, c_void_p, c_void_p,
@@ -126,6 +130,20 @@ def pinned_empty(shape, dtype):
     check(lib.nfb_host_alloc(nbytes, ctypes.byref(ptr)))
     raw = (ctypes.c_byte * max(nbytes, 1)).from_address(ptr.value)
     weakref.finalize(raw, lib.nfb_host_free, c_void_p(ptr.value))
+    return np.frombuffer(raw, dtype=dtype, count=nbytes // dtype.itemsize).reshape(shape)
+
+
+def pinned_wrap(ptr: int, shape, dtype):
+    """numpy view of a page-locked block handed out by the library (nfb_host_alloc inside a C call); the block goes
+    back to the pool when the array is garbage-collected."""
+    import weakref
+
+    import numpy as np
+    lib = load()
+    dtype = np.dtype(dtype)
+    nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
+    raw = (ctypes.c_byte * max(nbytes, 1)).from_address(ptr)
+    weakref.finalize(raw, lib.nfb_host_free, c_void_p(ptr))
     return np.frombuffer(raw, dtype=dtype, count=nbytes // dtype.itemsize).reshape(shape)
 
 

@@ -150,6 +150,19 @@ int ingest_coo_to_planes(const int* rows, const int* cols, const double* vals, i
                          int64_t nrows, int64_t ncols, unsigned int* max_bits, __half* hi, __half* lo, int64_t ldp,
                          unsigned int* cell_mask, float* inv_scale, double* sums, int* flags, cudaStream_t stream);
 
+// ---- dot_parse_gpu.cu -----------------------------------------------------------------------------
+// fdt_matrix2.dot text (device buffer) -> COO triplets.  count: lines per 128-byte segment (seg_lines[segments]),
+// per block (block_lines / block_first[blocks], exclusive scan) and in total; parse: rows0 / cols0 / vals of the
+// first n_lines - 1 lines, shape[3] from the last, flags[3] = {malformed line, number outside the exact fast path,
+// index not a 32-bit integer}, range[4] = {min row, max row, min col, max col}.
+int64_t dot_gpu_segments(int64_t len);
+int64_t dot_gpu_blocks(int64_t len);
+int dot_gpu_count(const char* txt, int64_t len, unsigned char* seg_lines, unsigned int* block_lines,
+                  long long* block_first, long long* total_out, cudaStream_t stream);
+int dot_gpu_parse(const char* txt, int64_t len, const unsigned char* seg_lines, const long long* block_first,
+                  long long n_lines, int* rows0, int* cols0, double* vals, double* shape, int* flags, int* range,
+                  cudaStream_t stream);
+
 // ---- nnls.cu --------------------------------------------------------------------------------------
 // Batched non-negative least squares with one shared Gram matrix:
 //   for every column j < cols:  min_{h >= 0} 0.5 h'Gh - rhs[:, j]'h ,  G [k,k] fp64, rhs [k, ld] fp32 partials

@@ -1600,8 +1600,11 @@ int nfb_ingest_coo(nfb_handle* h, int n_subjects, const int32_t* const* rows_hos
 
 // One subject whose triplets are all distinct: straight into the operand planes (ingest.cu), no dense float64
 // scratch and no dense float32 matrix.  *duplicates = true (and no matrix) when a coordinate occurs twice.
+// rows_host == nullptr: the triplets are already on the device in rows_dev / cols_dev / vals_dev (the device .dot
+// parser); otherwise they are uploaded from the host arrays.
 static int ingest_single_to_planes(nfb_handle* h, const int32_t* rows_host, const int32_t* cols_host,
-                                   const double* vals_host, int64_t nnz, double scale, int64_t nrows, int64_t ncols,
+                                   const double* vals_host, const int* rows_dev, const int* cols_dev,
+                                   const double* vals_dev, int64_t nnz, double scale, int64_t nrows, int64_t ncols,
                                    nfb_matrix** out, bool* duplicates) {
     cudaStream_t st = h->stream;
     HostMarks marks(st);
@@ -1611,6 +1614,7 @@ static int ingest_single_to_planes(nfb_handle* h, const int32_t* rows_host, cons
     x->n = ncols;
     x->ldp = round_up64(ncols, 8);
     const size_t cells = static_cast<size_t>(nrows) * x->ldp;
+    const bool upload = rows_host != nullptr;
     DevBuf<unsigned int> mask;
     DevBuf<int> rows, cols;
     DevBuf<double> vals;
@@ -1618,37 +1622,44 @@ static int ingest_single_to_planes(nfb_handle* h, const int32_t* rows_host, cons
     NFB_TRY(x->lo.alloc_pooled(cells, false, st));
     NFB_TRY(x->inv_scale.alloc_pooled(1, true, st));
     NFB_TRY(mask.alloc_pooled((cells + 31) / 32, false, st));
-    NFB_TRY(rows.alloc_pooled(nnz, false, st));
-    NFB_TRY(cols.alloc_pooled(nnz, false, st));
-    NFB_TRY(vals.alloc_pooled(nnz, false, st));
-    marks.mark("alloc");
-    // the triplets travel on the copy stream while the planes and the mask are zeroed on the main one
-    // (the staging buffers are stream-ordered allocations of the main stream: the copy stream may only touch
-    // them after the point of allocation)
     cudaEvent_t uploaded = nullptr;
-    NFB_CUDA(cudaEventCreateWithFlags(&uploaded, cudaEventDisableTiming));
-    NFB_CUDA(cudaEventRecord(uploaded, st));
-    NFB_CUDA(cudaStreamWaitEvent(h->copy_stream, uploaded, 0));
-    NFB_CUDA(cudaMemcpyAsync(rows.p, rows_host, sizeof(int) * nnz, cudaMemcpyHostToDevice, h->copy_stream));
-    NFB_CUDA(cudaMemcpyAsync(cols.p, cols_host, sizeof(int) * nnz, cudaMemcpyHostToDevice, h->copy_stream));
-    NFB_CUDA(cudaMemcpyAsync(vals.p, vals_host, sizeof(double) * nnz, cudaMemcpyHostToDevice, h->copy_stream));
-    NFB_CUDA(cudaEventRecord(uploaded, h->copy_stream));
+    if (upload) {
+        NFB_TRY(rows.alloc_pooled(nnz, false, st));
+        NFB_TRY(cols.alloc_pooled(nnz, false, st));
+        NFB_TRY(vals.alloc_pooled(nnz, false, st));
+        marks.mark("alloc");
+        // the triplets travel on the copy stream while the planes and the mask are zeroed on the main one
+        // (the staging buffers are stream-ordered allocations of the main stream: the copy stream may only touch
+        // them after the point of allocation)
+        NFB_CUDA(cudaEventCreateWithFlags(&uploaded, cudaEventDisableTiming));
+        NFB_CUDA(cudaEventRecord(uploaded, st));
+        NFB_CUDA(cudaStreamWaitEvent(h->copy_stream, uploaded, 0));
+        NFB_CUDA(cudaMemcpyAsync(rows.p, rows_host, sizeof(int) * nnz, cudaMemcpyHostToDevice, h->copy_stream));
+        NFB_CUDA(cudaMemcpyAsync(cols.p, cols_host, sizeof(int) * nnz, cudaMemcpyHostToDevice, h->copy_stream));
+        NFB_CUDA(cudaMemcpyAsync(vals.p, vals_host, sizeof(double) * nnz, cudaMemcpyHostToDevice, h->copy_stream));
+        NFB_CUDA(cudaEventRecord(uploaded, h->copy_stream));
+        rows_dev = rows.p;
+        cols_dev = cols.p;
+        vals_dev = vals.p;
+    }
     NFB_CUDA(cudaMemsetAsync(x->hi.p, 0, cells * sizeof(__half), st));
     NFB_CUDA(cudaMemsetAsync(x->lo.p, 0, cells * sizeof(__half), st));
     NFB_CUDA(cudaMemsetAsync(mask.p, 0, ((cells + 31) / 32) * sizeof(unsigned int), st));
     NFB_CUDA(cudaMemsetAsync(h->d_bits.p, 0, sizeof(unsigned int), st));
     NFB_CUDA(cudaMemsetAsync(h->d_scal.p + 6, 0, 2 * sizeof(double), st));
     NFB_CUDA(cudaMemsetAsync(h->d_int.p + 4, 0, 3 * sizeof(int), st));
-    NFB_CUDA(cudaStreamWaitEvent(st, uploaded, 0));
-    marks.mark("upload");
-    NFB_TRY(ingest_coo_to_planes(rows.p, cols.p, vals.p, nnz, scale, nrows, ncols, h->d_bits.p, x->hi.p, x->lo.p, x->ldp,
-                                 mask.p, x->inv_scale.p, h->d_scal.p + 6, h->d_int.p + 4, st));
+    if (upload) {
+        NFB_CUDA(cudaStreamWaitEvent(st, uploaded, 0));
+        marks.mark("upload");
+    }
+    NFB_TRY(ingest_coo_to_planes(rows_dev, cols_dev, vals_dev, nnz, scale, nrows, ncols, h->d_bits.p, x->hi.p, x->lo.p,
+                                 x->ldp, mask.p, x->inv_scale.p, h->d_scal.p + 6, h->d_int.p + 4, st));
     int flags[3] = {0, 0, 0};
     NFB_CUDA(cudaMemcpyAsync(flags, h->d_int.p + 4, sizeof(flags), cudaMemcpyDeviceToHost, st));
     NFB_CUDA(cudaMemcpyAsync(h->h_scal + 6, h->d_scal.p + 6, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
     NFB_CUDA(cudaMemcpyAsync(&x->inv_scale_host, x->inv_scale.p, sizeof(float), cudaMemcpyDeviceToHost, st));
     NFB_CUDA(cudaStreamSynchronize(st));
-    cudaEventDestroy(uploaded);
+    if (uploaded) cudaEventDestroy(uploaded);
     marks.mark("scatter");
     note_launch(2);
     NFB_CHECK(flags[0] == 0, "row/column index exceeds matrix dimensions");
@@ -1663,6 +1674,127 @@ static int ingest_single_to_planes(nfb_handle* h, const int32_t* rows_host, cons
     return 0;
 }
 
+// fdt_matrix2.dot text -> COO triplets in device memory (dot_parse_gpu.cu)
+struct DotCoo {
+    DevBuf<int> rows, cols;
+    DevBuf<double> vals;
+    int64_t nnz = 0, nrows = 0, ncols = 0;
+    int fallback = 0;      // 1: a number outside the device parser's exact fast path
+};
+
+static int dot_text_to_device_coo(nfb_handle* h, const char* text_host, int64_t len, DotCoo* coo) {
+    cudaStream_t st = h->stream;
+    HostMarks marks(st);
+    NFB_CHECK(len > 0, "file is empty");
+    const int64_t nseg = dot_gpu_segments(len), nblocks = dot_gpu_blocks(len);
+    DevBuf<char> txt;
+    DevBuf<unsigned char> seg_lines;
+    DevBuf<unsigned int> block_lines;
+    DevBuf<long long> block_first, total;
+    NFB_TRY(txt.alloc_pooled(static_cast<size_t>(len), false, st));
+    NFB_TRY(seg_lines.alloc_pooled(static_cast<size_t>(nseg), false, st));
+    NFB_TRY(block_lines.alloc_pooled(static_cast<size_t>(nblocks), false, st));
+    NFB_TRY(block_first.alloc_pooled(static_cast<size_t>(nblocks), false, st));
+    NFB_TRY(total.alloc_pooled(1, true, st));
+    NFB_CUDA(cudaMemcpyAsync(txt.p, text_host, static_cast<size_t>(len), cudaMemcpyHostToDevice, st));
+    marks.mark("text upload");
+    NFB_TRY(dot_gpu_count(txt.p, len, seg_lines.p, block_lines.p, block_first.p, total.p, st));
+    long long n_lines = 0;
+    NFB_CUDA(cudaMemcpyAsync(&n_lines, total.p, sizeof(long long), cudaMemcpyDeviceToHost, st));
+    NFB_CUDA(cudaStreamSynchronize(st));
+    NFB_CHECK(n_lines > 0, "file is empty");
+    coo->nnz = n_lines - 1;
+    DevBuf<int> meta;
+    DevBuf<double> shape;
+    NFB_TRY(coo->rows.alloc_pooled(static_cast<size_t>(coo->nnz), false, st));
+    NFB_TRY(coo->cols.alloc_pooled(static_cast<size_t>(coo->nnz), false, st));
+    NFB_TRY(coo->vals.alloc_pooled(static_cast<size_t>(coo->nnz), false, st));
+    NFB_TRY(shape.alloc_pooled(3, true, st));
+    NFB_TRY(meta.alloc_pooled(8, true, st));             // flags[3] + range[4]
+    NFB_TRY(dot_gpu_parse(txt.p, len, seg_lines.p, block_first.p, n_lines, coo->rows.p, coo->cols.p, coo->vals.p,
+                          shape.p, meta.p, meta.p + 3, st));
+    int meta_h[7] = {0, 0, 0, 0, 0, 0, 0};
+    double shape_h[3] = {0.0, 0.0, 0.0};
+    NFB_CUDA(cudaMemcpyAsync(meta_h, meta.p, sizeof(meta_h), cudaMemcpyDeviceToHost, st));
+    NFB_CUDA(cudaMemcpyAsync(shape_h, shape.p, sizeof(shape_h), cudaMemcpyDeviceToHost, st));
+    NFB_CUDA(cudaStreamSynchronize(st));
+    marks.mark("parse");
+    note_launch(4);
+    NFB_CHECK(meta_h[0] == 0, "could not convert string to float: malformed line in fdt_matrix2.dot (expected 3 columns)");
+    if (meta_h[1] != 0) {                                // a number outside the exact fast path: host parser
+        coo->fallback = 1;
+        return 0;
+    }
+    coo->nrows = static_cast<int64_t>(shape_h[0]);
+    coo->ncols = static_cast<int64_t>(shape_h[1]);
+    if (coo->nnz > 0) {                                  // the messages scipy's coo / csc constructor raises
+        NFB_CHECK(meta_h[2] == 0, "row / column index is not a 32-bit integer");
+        NFB_CHECK(meta_h[3] >= 0, "negative row index found");
+        NFB_CHECK(meta_h[5] >= 0, "negative column index found");
+        NFB_CHECK(meta_h[4] < coo->nrows, "row index exceeds matrix dimensions");
+        NFB_CHECK(meta_h[6] < coo->ncols, "column index exceeds matrix dimensions");
+    }
+    return 0;
+}
+
+// ... and on to the resident matrix, entirely on the device (+ ingest.cu)
+int nfb_ingest_dot_matrix(nfb_handle* h, const char* text_host, int64_t len, double scale, nfb_matrix** out,
+                          int64_t* shape_out, int* fallback_out) {
+    NFB_CHECK(h != nullptr && out != nullptr && shape_out != nullptr && fallback_out != nullptr && len >= 0 &&
+                  (text_host != nullptr || len == 0), "bad nfb_ingest_dot_matrix arguments");
+    NFB_CUDA(cudaSetDevice(h->device));
+    *out = nullptr;
+    *fallback_out = 0;
+    DotCoo coo;
+    NFB_TRY(dot_text_to_device_coo(h, text_host, len, &coo));
+    if (coo.fallback) {
+        *fallback_out = coo.fallback;
+        return 0;
+    }
+    shape_out[0] = coo.nrows;
+    shape_out[1] = coo.ncols;
+    NFB_CHECK(coo.nrows > 0 && coo.ncols > 0, "bad ingest arguments");
+    bool duplicates = false;
+    NFB_TRY(ingest_single_to_planes(h, nullptr, nullptr, nullptr, coo.rows.p, coo.cols.p, coo.vals.p, coo.nnz, scale,
+                                    coo.nrows, coo.ncols, out, &duplicates));
+    if (duplicates) *fallback_out = 2;                   // duplicate coordinates: exact scatter-add path (host triplets)
+    return 0;
+}
+
+// ... or back to the host as page-locked arrays (the group average adds subjects in float64 from host triplets)
+int nfb_dot_parse_coo_gpu(nfb_handle* h, const char* text_host, int64_t len, int32_t** rows0_out, int32_t** cols0_out,
+                          double** vals_out, int64_t* nnz_out, int64_t* shape_out, int* fallback_out) {
+    NFB_CHECK(h != nullptr && rows0_out != nullptr && cols0_out != nullptr && vals_out != nullptr &&
+                  nnz_out != nullptr && shape_out != nullptr && fallback_out != nullptr && len >= 0 &&
+                  (text_host != nullptr || len == 0), "bad nfb_dot_parse_coo_gpu arguments");
+    NFB_CUDA(cudaSetDevice(h->device));
+    *rows0_out = *cols0_out = nullptr;
+    *vals_out = nullptr;
+    *fallback_out = 0;
+    DotCoo coo;
+    NFB_TRY(dot_text_to_device_coo(h, text_host, len, &coo));
+    if (coo.fallback) {
+        *fallback_out = coo.fallback;
+        return 0;
+    }
+    void *r = nullptr, *c = nullptr, *v = nullptr;
+    NFB_TRY(nfb_host_alloc(static_cast<int64_t>(sizeof(int32_t)) * coo.nnz, &r));
+    NFB_TRY(nfb_host_alloc(static_cast<int64_t>(sizeof(int32_t)) * coo.nnz, &c));
+    NFB_TRY(nfb_host_alloc(static_cast<int64_t>(sizeof(double)) * coo.nnz, &v));
+    cudaStream_t st = h->stream;
+    NFB_CUDA(cudaMemcpyAsync(r, coo.rows.p, sizeof(int32_t) * coo.nnz, cudaMemcpyDeviceToHost, st));
+    NFB_CUDA(cudaMemcpyAsync(c, coo.cols.p, sizeof(int32_t) * coo.nnz, cudaMemcpyDeviceToHost, st));
+    NFB_CUDA(cudaMemcpyAsync(v, coo.vals.p, sizeof(double) * coo.nnz, cudaMemcpyDeviceToHost, st));
+    NFB_CUDA(cudaStreamSynchronize(st));
+    *rows0_out = static_cast<int32_t*>(r);
+    *cols0_out = static_cast<int32_t*>(c);
+    *vals_out = static_cast<double*>(v);
+    *nnz_out = coo.nnz;
+    shape_out[0] = coo.nrows;
+    shape_out[1] = coo.ncols;
+    return 0;
+}
+
 int nfb_ingest_coo_matrix(nfb_handle* h, int n_subjects, const int32_t* const* rows_host,
                           const int32_t* const* cols_host, const double* const* vals_host, const int64_t* nnz,
                           const double* scale, int64_t nrows, int64_t ncols, int group_mode, nfb_matrix** out) {
@@ -1673,8 +1805,8 @@ int nfb_ingest_coo_matrix(nfb_handle* h, int n_subjects, const int32_t* const* r
     if (!group_mode && n_subjects == 1 && direct_ok) {
         bool duplicates = false;
         *out = nullptr;
-        NFB_TRY(ingest_single_to_planes(h, rows_host[0], cols_host[0], vals_host[0], nnz[0], scale[0], nrows, ncols,
-                                        out, &duplicates));
+        NFB_TRY(ingest_single_to_planes(h, rows_host[0], cols_host[0], vals_host[0], nullptr, nullptr, nullptr, nnz[0],
+                                        scale[0], nrows, ncols, out, &duplicates));
         if (!duplicates) return 0;
     }
     // group average, or duplicate coordinates to be summed in float64: the exact scatter-add path.

@@ -294,3 +294,36 @@ def ingest_coo_resident(subjects, nrows: int, ncols: int, group_mode: bool,
     check(handle.lib.nfb_ingest_coo_matrix(handle.ptr, n, rows_p, cols_p, vals_p, nnz, scale, nrows, ncols,
                                            1 if group_mode else 0, byref(ptr)))
     return DeviceMatrix(handle, ptr, (nrows, ncols))
+
+
+def ingest_dot_resident(raw, scale: float, handle: Handle | None = None):
+    """The bytes of one subject's ``fdt_matrix2.dot`` -> resident ``DeviceMatrix``, parsed on the device
+    (``nfb_ingest_dot_matrix``).  Returns ``None`` when the file needs the host parser (a number outside the exact
+    fast path, or duplicate coordinates that the reference sums in float64)."""
+    handle = handle or get_handle()
+    buf = np.frombuffer(raw, dtype=np.uint8) if not isinstance(raw, np.ndarray) else np.ascontiguousarray(raw)
+    ptr, fallback = c_void_p(), c_int()
+    shape = (c_int64 * 2)()
+    check(handle.lib.nfb_ingest_dot_matrix(handle.ptr, c_void_p(buf.ctypes.data), buf.size, float(scale), byref(ptr),
+                                           shape, byref(fallback)))
+    if fallback.value:
+        return None
+    return DeviceMatrix(handle, ptr, (int(shape[0]), int(shape[1])))
+
+
+def parse_dot_coo_device(raw, handle: Handle | None = None):
+    """``parse_dot_coo`` on the device (``nfb_dot_parse_coo_gpu``): ``(rows0, cols0, vals, (nrows, ncols))`` as
+    page-locked arrays, or ``None`` when the file needs the host parser."""
+    handle = handle or get_handle()
+    buf = np.frombuffer(raw, dtype=np.uint8) if not isinstance(raw, np.ndarray) else np.ascontiguousarray(raw)
+    rows, cols, vals = c_void_p(), c_void_p(), c_void_p()
+    nnz, fallback = c_int64(), c_int()
+    shape = (c_int64 * 2)()
+    check(handle.lib.nfb_dot_parse_coo_gpu(handle.ptr, c_void_p(buf.ctypes.data), buf.size, byref(rows), byref(cols),
+                                           byref(vals), byref(nnz), shape, byref(fallback)))
+    if fallback.value:
+        return None
+    n = nnz.value
+    return (_lib.pinned_wrap(rows.value, (n,), np.int32), _lib.pinned_wrap(cols.value, (n,), np.int32),
+            _lib.pinned_wrap(vals.value, (n,), np.float64), (int(shape[0]), int(shape[1])))
+

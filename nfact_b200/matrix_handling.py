@@ -104,7 +104,15 @@ def parse_dot_coo(raw: bytes, name: str = "<buffer>", pinned: bool = False):
 def load_single_matrix(matfile: str, pinned: bool = False) -> CooMatrix:
     """NFACT/base/matrix_handling.py:116-140.  Returns the COO triplets (0-based) plus the
     ``1e8 / waytotal`` scale; the sparse-matrix arithmetic itself happens on the device."""
-    rows, cols, data, shape = parse_dot_coo(_read_bytes(matfile), matfile, pinned)
+    raw = _read_bytes(matfile)
+    parsed = None
+    if pinned and len(raw) and os.environ.get("NFB_DOT_ON_DEVICE", "1") != "0":
+        # a CUDA context is up (pinned staging was asked for): parse on the device, host parser as the fallback
+        try:
+            parsed = device.parse_dot_coo_device(raw)
+        except Exception as e:
+            raise ValueError(f"{e}") from None
+    rows, cols, data, shape = parsed if parsed is not None else parse_dot_coo(raw, matfile, pinned)
     waytotal = float(np.loadtxt(os.path.join(os.path.dirname(matfile), "waytotal")))
     return CooMatrix(rows, cols, data, shape, 1e8 / waytotal)
 
@@ -122,8 +130,24 @@ def load_fdt_matrix(matfile: str, resident: bool = False, handle=None):
     """NFACT/base/matrix_handling.py:143-158: dense float32 [m, n].
 
     ``resident=True`` keeps the matrix in HBM and returns a ``DeviceMatrix`` (what ``nmf_decomp`` /
-    ``nmf_dual_regression`` take directly) instead of copying 4mn bytes to the host and back."""
-    coo = load_single_matrix(matfile, pinned=_cuda_ready())
+    ``nmf_dual_regression`` take directly) instead of copying 4mn bytes to the host and back; the text itself is
+    then parsed on the device too (``nfb_ingest_dot_matrix``), the host parser only takes over for files with
+    numbers outside the device parser's exact fast path or with duplicate coordinates."""
+    if resident and os.environ.get("NFB_DOT_ON_DEVICE", "1") != "0":
+        raw = _read_bytes(matfile)
+        if len(raw) == 0:
+            raise ValueError(f"{matfile}: file is empty")
+        waytotal = float(np.loadtxt(os.path.join(os.path.dirname(matfile), "waytotal")))
+        try:
+            xdev = device.ingest_dot_resident(raw, 1e8 / waytotal, handle)
+        except Exception as e:
+            raise ValueError(f"{e}") from None
+        if xdev is not None:
+            return xdev
+        rows, cols, data, shape = parse_dot_coo(raw, matfile, pinned=True)
+        coo = CooMatrix(rows, cols, data, shape, 1e8 / waytotal)
+    else:
+        coo = load_single_matrix(matfile, pinned=_cuda_ready())
     ingest = device.ingest_coo_resident if resident else device.ingest_coo
     return ingest([(coo.rows, coo.cols, coo.data, coo.scale)], coo.shape[0], coo.shape[1], False, handle)
 
