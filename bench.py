@@ -284,7 +284,29 @@ def ingest_benchmark(handle):
     x_ref = acc.toarray().astype(np.float32)
     t_ref = time.perf_counter() - t0
     total = 3 * nnz
-    return {"triplets": total, "shape": [nrows, ncols], "subjects": 3, "seconds": t_gpu,
+    # the text in front of it (a1): one subject's fdt_matrix2.dot, host parser (all cores) against the device parser
+    from nfact_b200.device import parse_dot_coo_device
+    from nfact_b200.matrix_handling import parse_dot_coo
+    n_txt = 2_000_000
+    cells = np.unique(rng.integers(0, nrows * ncols, int(n_txt * 1.05)))[:n_txt]
+    text = ("\n".join(f"{r} {c} {v}" for r, c, v in zip((cells // ncols + 1).tolist(), (cells % ncols + 1).tolist(),
+                                                          rng.integers(1, 5000, cells.size).tolist()))
+            + f"\n{nrows} {ncols} 0\n").encode()
+    t_host = t_dev = float("inf")
+    for _ in range(3):
+        t0 = time.perf_counter()
+        host = parse_dot_coo(text, pinned=True)
+        t_host = min(t_host, time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        dev = parse_dot_coo_device(text, handle)
+        t_dev = min(t_dev, time.perf_counter() - t0)
+    parse_ok = dev is not None and all(np.array_equal(a, b) for a, b in zip(host[:3], dev[:3]))
+    dot_parse = {"lines": int(cells.size), "text_bytes": len(text), "host_lines_per_s": cells.size / t_host,
+                 "host_threads": os.cpu_count(), "device_lines_per_s": cells.size / t_dev,
+                 "device_equals_host": bool(parse_ok),
+                 "api": "nfb_dot_parse_coo (host, std::from_chars) vs nfb_dot_parse_coo_gpu (pageable text upload + "
+                        "device parse + page-locked triplets back on the host)"}
+    return {"triplets": total, "shape": [nrows, ncols], "subjects": 3, "seconds": t_gpu, "dot_parse": dot_parse,
             "value": total / t_gpu, "unit": "triplets/s", "bit_exact_vs_scipy": bool(np.array_equal(x_gpu, x_ref)),
             "reference_seconds": t_ref, "reference_value": total / t_ref,
             "api": "nfb_ingest_coo (host triplets in, host float32 matrix out)"}
