@@ -223,6 +223,54 @@ def cpu_baseline(m, n, k, density, solver):
     }
 
 
+def _nnls_columns(a, cols):
+    """The reference's inner loop (dual_regression_methods.py:258-264): scipy.optimize.nnls per column."""
+    from scipy.optimize import nnls
+    return [nnls(a, cols[:, j])[0] for j in range(cols.shape[1])]
+
+
+def dr_cpu_baseline(grey, white, x_np, per_core=1):
+    """nfact_dr's reference arithmetic on this box's host cores, on a bounded sample of the same subject:
+    stage 1 = scipy.optimize.nnls(G, X[:, j]) for `cores * per_core` sampled target columns, stage 2 =
+    nnls(Hs, X[i, :]) for as many sampled seed rows (Hs = the white components of the full stage 1, taken from the
+    device result: the same minimisers), run the way nnls_parallel does it (joblib, n_jobs = all cores,
+    NFACT/dual_reg/dual_regression/dual_regression_methods.py:301-340).  Seconds per subject = wall time per
+    sampled problem x (n columns + m rows): every problem has the same shape, so the sample scales linearly."""
+    import joblib
+    m, n = x_np.shape
+    cores = os.cpu_count() or 1
+    ns = cores * per_core
+    rng = np.random.default_rng(11)
+    jc = np.sort(rng.choice(n, size=min(ns, n), replace=False))
+    ir = np.sort(rng.choice(m, size=min(ns, m), replace=False))
+    g64 = np.ascontiguousarray(grey, dtype=np.float64)            # nnls casts to float64 on every call
+    hs = np.ascontiguousarray(np.asarray(white, dtype=np.float64).T)   # [n, k] like wm_component_white_map
+    xc = np.ascontiguousarray(x_np[:, jc])                        # [m, ns] float32, as the reference slices them
+    xr = np.ascontiguousarray(x_np[ir, :].T)                      # [n, ns]
+    with joblib.Parallel(n_jobs=cores) as pool:
+        pool(joblib.delayed(_nnls_columns)(g64[:64], xc[:64, :1]) for _ in range(cores))     # start the workers
+        t0 = time.perf_counter()
+        sol1 = pool(joblib.delayed(_nnls_columns)(g64, xc[:, c::cores]) for c in range(cores))
+        t1 = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        sol2 = pool(joblib.delayed(_nnls_columns)(hs, xr[:, c::cores]) for c in range(cores))
+        t2 = time.perf_counter() - t0
+    # agreement of the device result with the reference on the sampled columns (the parity gate of the tests)
+    ref1 = np.empty((white.shape[0], jc.size))
+    for c, block in enumerate(sol1):
+        for i, h in enumerate(block):
+            ref1[:, c + i * cores] = h
+    rel = float(np.linalg.norm(np.asarray(white)[:, jc] - ref1) / max(np.linalg.norm(ref1), 1e-300))
+    seconds = t1 / jc.size * n + t2 / ir.size * m
+    del sol2
+    return {"value": 1.0 / seconds, "unit": "subjects/s", "seconds_per_subject": seconds, "cores": cores,
+            "kind": "reference", "stage1_rel_diff_on_sample": rel,
+            "sample": (f"scipy {__import__('scipy').__version__} optimize.nnls as called by NFACT "
+                       f"dual_regression_methods.py:301-340 (joblib, n_jobs={cores}): {jc.size} of {n} target "
+                       f"columns against G [{m}x{grey.shape[1]}] in {t1:.2f}s, {ir.size} of {m} seed rows against "
+                       f"Hs [{n}x{grey.shape[1]}] in {t2:.2f}s, scaled linearly to the whole subject")}
+
+
 def dual_regression_across_gpus(torch, dist, dev, handle, m, n, k, density, rank, world):
     """nfact_dr with subjects distributed over the GPUs (BASELINE config C4; run_locally(rank, world) in the
     product): every rank regresses its OWN full-size synthetic subject (seed 1000 + rank) onto the same
@@ -440,7 +488,7 @@ def run_ours(args):
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 t_e2e = float(t)
             assert np.isfinite(res["white_components"]).all()
-            if not args.no_dr and world == 1:
+            def dr_single_gpu():
                 # nfact_dr on one subject of the same shape (C4 is 100 such subjects; subjects are independent,
                 # so N GPUs run N of these side by side): regress the matrix onto the grey components the
                 # solve just produced, through the reference-facing call -- once with the subject's matrix
@@ -488,6 +536,17 @@ def run_ours(args):
                                   "(best of 3, float64 results copied to the host); e2e_value = X passed as a dense "
                                   "host array; pipeline_value = subject given as COO triplets in host memory -> "
                                   "nfb_ingest_coo_matrix -> dual regression (the nfact_dr per-subject path)"}
+                if not args.no_cpu:
+                    try:
+                        dr_info["cpu_baseline"] = dr_cpu_baseline(res["grey_components"], dr["white_components"], x_np)
+                    except Exception as exc:      # a side figure must not cost the bench line
+                        dr_info["cpu_baseline"] = {"error": f"{type(exc).__name__}: {exc}"}
+                return dr_info
+            if not args.no_dr and world == 1:
+                try:
+                    dr_info = dr_single_gpu()
+                except Exception as exc:      # a side figure must not cost the bench line
+                    dr_info = {"error": f"{type(exc).__name__}: {exc}"}
             e2e = {"value": iters / t_e2e, "unit": UNIT, "iters": iters, "seconds": t_e2e,
                    "h2d_bytes_per_step": int(world * (x_np.nbytes + w0_host.nbytes + h0_host.nbytes) / iters),
                    "d2h_bytes_per_step": int(world * (w0_host.nbytes + h0_host.nbytes) / iters),
@@ -544,7 +603,10 @@ def run_ours(args):
     if dr_info is not None:
         line["dual_regression"] = dr_info
     if world == 1 and not args.no_e2e:
-        line["ingest"] = ingest_benchmark(handle)
+        try:
+            line["ingest"] = ingest_benchmark(handle)
+        except Exception as exc:                  # side figures must not cost the bench line
+            line["ingest"] = {"error": f"{type(exc).__name__}: {exc}"}
     if not args.no_cpu and world == 1:
         line["cpu_baseline"] = cpu_baseline(m, n, k, density, args.solver)
     print(json.dumps(line), file=RESULT_OUT, flush=True)
