@@ -405,6 +405,31 @@ def normalise_components(grey: np.ndarray, white: np.ndarray) -> dict:
     return {"grey_matter": zscore_cols(grey), "white_matter": zscore_cols(white.T).T}
 
 
+def create_wta_map(component: np.ndarray, axis: int, z_thr: float) -> np.ndarray:
+    """NFACT/decomp/pipes/image_handling.py:216-245: winner-takes-all map.  StandardScaler z-scores every COLUMN of
+    ``component`` (float64 statistics; ``X -= mean_; X /= scale_`` each rounded to the array's dtype,
+    sklearn/preprocessing/_data.py StandardScaler.transform; a constant column gets scale 1,
+    ``_is_constant_feature`` + ``_handle_zeros_in_scale``), then the 1-based index of the first maximum along
+    ``axis`` (0: white components [k, n]; 1: grey components [m, k]), 0 where that maximum is below ``z_thr``
+    (compared in the array's dtype)."""
+    a = np.asarray(component)
+    dtype = a.dtype if a.dtype in (np.float32, np.float64) else np.dtype(np.float64)
+    a64 = a.astype(np.float64)
+    n = a.shape[0]
+    mean = a64.sum(axis=0) / n
+    var = ((a64 - mean) ** 2).sum(axis=0) / n
+    eps = np.finfo(np.float64).eps
+    scale = np.sqrt(var)
+    constant = var <= n * eps * var + (n * mean * eps) ** 2
+    scale[constant | (scale < 10 * eps)] = 1.0
+    z = (a.astype(dtype) - mean).astype(dtype)
+    z = (z / scale).astype(dtype)
+    top = np.max(z, axis=axis, keepdims=True)
+    wta = np.argmax(z, axis=axis, keepdims=True) + 1
+    wta[top < dtype.type(z_thr)] = 0
+    return np.array(wta, dtype=int)
+
+
 def threshold_grey_components(components: np.ndarray, seeds_id: np.ndarray, n_seeds: int, zscore_val) -> np.ndarray:
     """NFACT/base/matrix_handling.py:184-215: ``thresholding`` of the rows of every seed separately, in place
     (``seeds_id`` = second-to-last column of coords_for_fdt_matrix2; the reference loops ``enumerate(seeds)``)."""

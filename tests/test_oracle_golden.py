@@ -159,3 +159,17 @@ def test_oracle_postops_match_reference():
         assert np.allclose(norm["grey_matter"], g[f"grey_norm_{tag}"], **tol)
         assert np.allclose(norm["white_matter"], g[f"white_norm_{tag}"], **tol)
         assert norm["grey_matter"].dtype == grey.dtype
+
+
+def test_oracle_wta_matches_reference():
+    """create_wta_map restatement against outputs of the reference's own function (make_golden_wta.py)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_wta.npz"))
+    for tag in ("f32", "f64"):
+        for key in ("0p0", "1p0", "2p5"):
+            z = float(key.replace("p", "."))
+            white = orc.create_wta_map(g[f"white_{tag}"].copy(), 0, z)
+            grey = orc.create_wta_map(g[f"grey_{tag}"].copy(), 1, z)
+            assert white.dtype == g[f"white_wta_{key}_{tag}"].dtype and white.shape == g[f"white_wta_{key}_{tag}"].shape
+            assert np.array_equal(white, g[f"white_wta_{key}_{tag}"]), (tag, key)
+            assert np.array_equal(grey, g[f"grey_wta_{key}_{tag}"]), (tag, key)
