@@ -217,6 +217,16 @@ int nfb_component_postops_host(nfb_handle* h, void* data, int is_f64, int comp_m
                                const int32_t* group_id, int n_groups, int do_threshold, double zscore,
                                void* norm_out);
 
+/* Winner-takes-all map (replaces create_wta_map, NFACT/decomp/pipes/image_handling.py:216-245: StandardScaler
+ * z-scores of every column of the host array, then 1 + the index of the first maximum over the components, 0 where
+ * that maximum is below z_thr, compared in the array's dtype).  data: float32 or float64 (is_f64);
+ *   comp_major = 1: [k, len] (white components, the reference's axis = 0): every sample is standardised over its k
+ *                   component values;
+ *   comp_major = 0: [len, k] (grey components, axis = 1): every component is standardised over its len samples.
+ * wta_out[len]: int64 like numpy's int. */
+int nfb_component_wta_host(nfb_handle* h, const void* data, int is_f64, int comp_major, int64_t k, int64_t len,
+                           double z_thr, int64_t* wta_out);
+
 /* Component loadings (replaces __correlating at NFACT/stats/stats_component_loadings.py:199-231): for every
  * component t the correlation between the subject's map and the group's map,
  *   loadings_out[t] = [sum_j (s_tj - mean s_t)(g_tj - mean g_t) / (len - 1)] / (std s_t * std g_t)

@@ -87,6 +87,7 @@ SIGNATURES = {
                                                   c_void_p, c_void_p, c_void_p, POINTER(c_int)]),
     "nfb_component_postops_host": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_int64, c_void_p, c_int, c_int,
                                            c_double, c_void_p]),
+    "nfb_component_wta_host": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_int64, c_double, c_void_p]),
     "nfb_component_loadings_host": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_int64, c_void_p]),
     "nfb_row_correlation_host": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     "nfb_host_alloc": (c_int, [c_int64, POINTER(c_void_p)]),

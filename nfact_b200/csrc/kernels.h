@@ -104,6 +104,12 @@ template <typename T>
 int comp_standardize(const T* x, int64_t k, int64_t len, int64_t ld, T* out, int64_t ld_out, double* stats,
                      cudaStream_t stream);
 
+// winner-takes-all map: out[j] = 1 + first argmax_t z[t][j] of the StandardScaler z-scores (0 below z_thr);
+// per_component: the scaler standardises every component over its samples, else every sample over the components
+template <typename T>
+int comp_wta(const T* x, int64_t k, int64_t len, int64_t ld, int per_component, double z_thr, double* stats,
+             long long* out, cudaStream_t stream);
+
 // out[t] = per-component correlation of a[t][:] and b[t][:] as NFACT/stats/stats_component_loadings.py:199-231
 // computes it (covariance / (len - 1) over the product of the population standard deviations)
 template <typename T>

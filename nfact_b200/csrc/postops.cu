@@ -2,6 +2,7 @@
 //   thresholding               NFACT/base/matrix_handling.py:218-238   x[x < mean + z std] = 0 per component
 //   threshold_grey_components  NFACT/base/matrix_handling.py:184-215   the same per (component, seed)
 //   normalise_components       NFACT/base/matrix_handling.py:45-68     StandardScaler().fit_transform per component
+//   create_wta_map             NFACT/decomp/pipes/image_handling.py:216-245   winner-takes-all map of z-scored maps
 // All maps are handled component-major, [k, ld] with the samples of one component contiguous (the layout the
 // solvers keep W' and H in).  Statistics are float64 two-pass sums with a fixed reduction tree (deterministic):
 // population mean / standard deviation like ndarray.mean() / .std() and sklearn's StandardScaler.
@@ -100,6 +101,57 @@ __global__ void comp_standardize_kernel(const T* __restrict__ x, int64_t k, int6
     }
 }
 
+// StandardScaler's scale for a feature of n values with the given mean / population variance: constant features
+// (sklearn/preprocessing/_data.py _is_constant_feature) and vanishing scales (_handle_zeros_in_scale) get 1
+__device__ __forceinline__ double scaler_scale(double mu, double v, double n) {
+    const double eps = DBL_EPSILON;
+    const double bound = n * eps * v + (n * mu * eps) * (n * mu * eps);
+    const double scale = sqrt(v);
+    return (v <= bound || scale < 10.0 * eps) ? 1.0 : scale;
+}
+
+// winner-takes-all map, one thread per sample j of the component-major map x[k][ld]:
+//   z[t][j] = T(T(x[t][j] - mean) / scale)  (the two roundings of StandardScaler.transform on an array of dtype T)
+//   out[j]  = 1 + first argmax_t z[t][j], or 0 when that maximum is below T(z_thr).
+// per_component != 0: the scaler's features are the components (grey maps [len, k] on the host: statistics over the
+// samples, precomputed by comp_stats_kernel); otherwise its features are the samples (white maps [k, len] on the
+// host: mean / variance over the k components of sample j, summed here in component order).
+template <typename T>
+__global__ void comp_wta_kernel(const T* __restrict__ x, int64_t k, int64_t len, int64_t ld, int per_component,
+                                const double* __restrict__ mean, const double* __restrict__ var, double z_thr,
+                                long long* __restrict__ out) {
+    for (int64_t j = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; j < len;
+         j += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        double mu = 0.0, scale = 1.0;
+        if (!per_component) {
+            double s = 0.0;
+            for (int64_t t = 0; t < k; ++t) s += static_cast<double>(x[t * ld + j]);
+            mu = s / static_cast<double>(k);
+            double q = 0.0;
+            for (int64_t t = 0; t < k; ++t) {
+                const double d = static_cast<double>(x[t * ld + j]) - mu;
+                q = fma(d, d, q);
+            }
+            scale = scaler_scale(mu, q / static_cast<double>(k), static_cast<double>(k));
+        }
+        T best = static_cast<T>(0);
+        int64_t arg = 0;
+        for (int64_t t = 0; t < k; ++t) {
+            if (per_component) {
+                mu = mean[t];
+                scale = scaler_scale(mu, var[t], static_cast<double>(len));
+            }
+            const T centred = static_cast<T>(static_cast<double>(x[t * ld + j]) - mu);
+            const T z = static_cast<T>(static_cast<double>(centred) / scale);
+            if (t == 0 || z > best) {      // strict: the first maximum wins, like np.argmax
+                best = z;
+                arg = t;
+            }
+        }
+        out[j] = best < static_cast<T>(z_thr) ? 0LL : static_cast<long long>(arg + 1);
+    }
+}
+
 // one CTA per component t: r_t = [sum_j (a_tj - mean a_t)(b_tj - mean b_t) / (len - 1)] / (std a_t * std b_t), population
 // standard deviations -- the mixed normalisation of NFACT/stats/stats_component_loadings.py:227-231, kept as is
 template <typename T>
@@ -188,8 +240,28 @@ int comp_loadings(const T* a, const T* b, int64_t k, int64_t len, int64_t ld, do
     return 0;
 }
 
+template <typename T>
+int comp_wta(const T* x, int64_t k, int64_t len, int64_t ld, int per_component, double z_thr, double* stats,
+             long long* out, cudaStream_t stream) {
+    if (k * len == 0) return 0;
+    double* mean = stats;
+    double* sd = stats + k;
+    double* var = stats + 2 * k;
+    long long* count = reinterpret_cast<long long*>(stats + 3 * k);
+    if (per_component) {
+        comp_stats_kernel<T><<<dim3(static_cast<unsigned>(k), 1), kStatThreads, 0, stream>>>(x, len, ld, nullptr, 1,
+                                                                                            mean, sd, var, count);
+        NFB_CUDA(cudaGetLastError());
+    }
+    comp_wta_kernel<T><<<elementwise_grid(len), 256, 0, stream>>>(x, k, len, ld, per_component, mean, var, z_thr, out);
+    NFB_CUDA(cudaGetLastError());
+    return 0;
+}
+
 template int comp_loadings<float>(const float*, const float*, int64_t, int64_t, int64_t, double*, cudaStream_t);
 template int comp_loadings<double>(const double*, const double*, int64_t, int64_t, int64_t, double*, cudaStream_t);
+template int comp_wta<float>(const float*, int64_t, int64_t, int64_t, int, double, double*, long long*, cudaStream_t);
+template int comp_wta<double>(const double*, int64_t, int64_t, int64_t, int, double, double*, long long*, cudaStream_t);
 template int comp_threshold<float>(float*, int64_t, int64_t, int64_t, const int*, int, double, double*, cudaStream_t);
 template int comp_threshold<double>(double*, int64_t, int64_t, int64_t, const int*, int, double, double*, cudaStream_t);
 template int comp_standardize<float>(const float*, int64_t, int64_t, int64_t, float*, int64_t, double*, cudaStream_t);

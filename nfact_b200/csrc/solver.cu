@@ -1479,6 +1479,34 @@ static int component_loadings(nfb_handle* h, const T* subject, const T* group, i
     return 0;
 }
 
+template <typename T>
+static int component_wta(nfb_handle* h, const T* data, int comp_major, int64_t k, int64_t len, double z_thr,
+                         int64_t* wta_out) {
+    cudaStream_t st = h->stream;
+    const int64_t ld = round_up64(len, 8);
+    DevBuf<T> raw, cm;
+    DevBuf<double> stats;
+    DevBuf<long long> out;
+    NFB_TRY(cm.alloc_pooled(static_cast<size_t>(k) * ld, false, st));
+    NFB_TRY(stats.alloc_pooled(static_cast<size_t>(4) * k, false, st));
+    NFB_TRY(out.alloc_pooled(static_cast<size_t>(len), false, st));
+    if (comp_major) {
+        NFB_CUDA(cudaMemcpy2DAsync(cm.p, ld * sizeof(T), data, len * sizeof(T), len * sizeof(T), k,
+                                   cudaMemcpyHostToDevice, st));
+    } else {   // [len, k] on the host (grey components): component-major on the device
+        NFB_TRY(raw.alloc_pooled(static_cast<size_t>(k) * len, false, st));
+        NFB_CUDA(cudaMemcpyAsync(raw.p, data, sizeof(T) * k * len, cudaMemcpyHostToDevice, st));
+        if constexpr (sizeof(T) == 8) NFB_TRY(transpose_f64(raw.p, len, k, k, cm.p, ld, st));
+        else NFB_TRY(transpose_f32(raw.p, len, k, k, cm.p, ld, st));
+    }
+    NFB_TRY(comp_wta<T>(cm.p, k, len, ld, comp_major ? 0 : 1, z_thr, stats.p, out.p, st));
+    static_assert(sizeof(long long) == sizeof(int64_t), "int64 output");
+    NFB_CUDA(cudaMemcpyAsync(wta_out, out.p, sizeof(int64_t) * len, cudaMemcpyDeviceToHost, st));
+    NFB_CUDA(cudaStreamSynchronize(st));
+    note_launch(comp_major ? 1 : 3);
+    return 0;
+}
+
 extern "C" {
 
 int nfb_component_postops_host(nfb_handle* h, void* data, int is_f64, int comp_major, int64_t k, int64_t len,
@@ -1493,6 +1521,16 @@ int nfb_component_postops_host(nfb_handle* h, void* data, int is_f64, int comp_m
                                          do_threshold, zscore, static_cast<double*>(norm_out));
     return component_postops<float>(h, static_cast<float*>(data), comp_major, k, len, group_id, n_groups, do_threshold,
                                     zscore, static_cast<float*>(norm_out));
+}
+
+int nfb_component_wta_host(nfb_handle* h, const void* data, int is_f64, int comp_major, int64_t k, int64_t len,
+                           double z_thr, int64_t* wta_out) {
+    NFB_CHECK(h != nullptr && data != nullptr && wta_out != nullptr, "NULL argument");
+    NFB_CHECK(k >= 1 && len >= 1, "bad nfb_component_wta_host shape");
+    NFB_CUDA(cudaSetDevice(h->device));
+    if (is_f64)
+        return component_wta<double>(h, static_cast<const double*>(data), comp_major, k, len, z_thr, wta_out);
+    return component_wta<float>(h, static_cast<const float*>(data), comp_major, k, len, z_thr, wta_out);
 }
 
 // NFB_HOST_TIMING=1: wall-clock marks of the host-visible phases of the ingest (each mark synchronises the stream)

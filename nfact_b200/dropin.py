@@ -32,6 +32,8 @@ _DEFINITIONS = {
     "NFACT.decomp.decomposition.sso.sso_functions": ("compute_similairty_matrix",),
     # hyper-parameters a6 (matrix_decomposition.py:74-107)
     "NFACT.decomp.decomposition.matrix_decomposition": ("get_parameters",),
+    # winner-takes-all maps f3 (pipes/image_handling.py:216-245; winner_takes_all :186-187 looks the name up here)
+    "NFACT.decomp.pipes.image_handling": ("create_wta_map",),
     # dual regression a15 (dual_regression_methods.py:8-42, 92-116)
     "NFACT.dual_reg.dual_regression.dual_regression_methods": ("nmf_dual_regression", "run_decomp"),
 }

@@ -298,6 +298,33 @@ def component_loadings(subject_data: np.ndarray, group_data: np.ndarray) -> np.n
     return out
 
 
+def create_wta_map(component: np.ndarray, axis: int, z_thr: float) -> np.ndarray:
+    """NFACT/decomp/pipes/image_handling.py:216-245: winner-takes-all map.  The columns of ``component`` are
+    z-scored (StandardScaler), then every entry along ``axis`` is replaced by the 1-based index of its first maximum,
+    0 where that maximum is below ``z_thr``: ``create_wta_map(white [k, n], 0, z)`` -> int [1, n],
+    ``create_wta_map(grey [m, k], 1, z)`` -> int [m, 1].  On the device (``nfb_component_wta_host``, float64
+    statistics, z-scores rounded to the array's dtype like sklearn's in-place transform)."""
+    from ctypes import c_void_p
+    from . import _lib
+    arr = np.asarray(component)
+    if arr.ndim != 2 or axis not in (0, 1):
+        raise ValueError(f"expected a 2-D array and axis 0 or 1, got shape {arr.shape}, axis {axis}")
+    arr = np.ascontiguousarray(arr, dtype=np.float32 if arr.dtype == np.float32 else np.float64)
+    rows, cols = arr.shape
+    if rows == 0:
+        raise ValueError(f"Found array with 0 sample(s) (shape={arr.shape}) while a minimum of 1 is required by "
+                         "StandardScaler.")
+    if cols == 0:
+        raise ValueError(f"Found array with 0 feature(s) (shape={arr.shape}) while a minimum of 1 is required by "
+                         "StandardScaler.")
+    k, length = (rows, cols) if axis == 0 else (cols, rows)
+    out = np.empty(length, dtype=np.int64)
+    handle = device.get_handle()
+    _lib.check(handle.lib.nfb_component_wta_host(handle.ptr, c_void_p(arr.ctypes.data), int(arr.dtype == np.float64),
+                                                 int(axis == 0), k, length, float(z_thr), c_void_p(out.ctypes.data)))
+    return np.array(out.reshape((1, cols) if axis == 0 else (rows, 1)), dtype=int)
+
+
 def thresholding_components(threshold_val: int, path_to_coords: str, seeds: list, components: dict) -> dict:
     """NFACT/base/matrix_handling.py:241-277."""
     col = colours()

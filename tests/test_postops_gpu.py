@@ -173,3 +173,46 @@ def test_component_loadings_match_the_reference_formula(g):
     assert np.allclose(nfact_b200.component_loadings(big_s, big_g), correlating(big_s, big_g), rtol=1e-10, atol=1e-13)
     with pytest.raises(ValueError):
         nfact_b200.component_loadings(big_s, big_g[:, :5])
+
+
+# ---- winner-takes-all maps (reference outputs from tests/golden/make_golden_wta.py) ------------------
+@pytest.mark.parametrize("tag", ["f32", "f64"])
+def test_wta_maps_match_reference(tag):
+    import nfact_b200
+    w = np.load(os.path.join(GOLDEN_DIR, "golden_wta.npz"))
+    for key in ("0p0", "1p0", "2p5"):
+        z = float(key.replace("p", "."))
+        white_in, grey_in = w[f"white_{tag}"].copy(), w[f"grey_{tag}"].copy()
+        white = nfact_b200.create_wta_map(white_in, 0, z)
+        grey = nfact_b200.create_wta_map(grey_in, 1, z)
+        want_w, want_g = w[f"white_wta_{key}_{tag}"], w[f"grey_wta_{key}_{tag}"]
+        assert white.shape == want_w.shape and white.dtype == want_w.dtype
+        assert grey.shape == want_g.shape and grey.dtype == want_g.dtype
+        assert np.array_equal(white, want_w), (tag, key, np.flatnonzero(white != want_w)[:8])
+        assert np.array_equal(grey, want_g), (tag, key, np.flatnonzero(grey != want_g)[:8])
+        assert np.array_equal(white_in, w[f"white_{tag}"]) and np.array_equal(grey_in, w[f"grey_{tag}"])  # inputs untouched
+
+
+def test_wta_against_oracle_on_ragged_shapes():
+    """Shapes that are no multiple of anything, k = 1, one sample, integer-valued and non-contiguous inputs."""
+    import nfact_b200
+    from oracle import nfact_oracle as orc
+    rng = np.random.default_rng(99)
+    for (m, k) in ((1, 1), (1, 7), (5, 1), (1031, 13), (77, 203), (4099, 50)):
+        for dtype in (np.float32, np.float64):
+            grey = (rng.gamma(0.5, 1.0, (m, k)) * (rng.random((m, k)) < 0.7)).astype(dtype)
+            white = np.ascontiguousarray(grey.T)
+            for z in (-1.0, 0.5, 2.0):
+                assert np.array_equal(nfact_b200.create_wta_map(grey, 1, z), orc.create_wta_map(grey, 1, z)), (m, k, z)
+                assert np.array_equal(nfact_b200.create_wta_map(white, 0, z), orc.create_wta_map(white, 0, z)), (m, k, z)
+                # the scaler always works on the columns of what it is given: both axes on both layouts
+                assert np.array_equal(nfact_b200.create_wta_map(grey, 0, z), orc.create_wta_map(grey, 0, z))
+                assert np.array_equal(nfact_b200.create_wta_map(white, 1, z), orc.create_wta_map(white, 1, z))
+    counts = rng.integers(0, 40, (300, 9))                                   # integer maps are scaled as float64
+    assert np.array_equal(nfact_b200.create_wta_map(counts, 1, 1.0), orc.create_wta_map(counts, 1, 1.0))
+    view = (rng.random((200, 24)) * 3).astype(np.float32)[:, ::2]            # a strided view
+    assert np.array_equal(nfact_b200.create_wta_map(view, 1, 0.0), orc.create_wta_map(view, 1, 0.0))
+    with pytest.raises(ValueError):
+        nfact_b200.create_wta_map(np.zeros((0, 4), np.float32), 1, 1.0)
+    with pytest.raises(ValueError):
+        nfact_b200.create_wta_map(np.zeros(5, np.float32), 0, 1.0)
