@@ -8,7 +8,8 @@
 // the lines that START in its segment.  Pass 1 counts them (a line counts when it holds a non-blank character, like
 // the host parser and loadtxt), a scan turns the counts into line indices, pass 2 parses each line into
 //     rows0[i] = int32(trunc(field0 - 1)), cols0[i] = int32(trunc(field1 - 1)), vals[i] = field2     (float64)
-// and the last line into shape[3].
+// and the last line into shape[3].  Like loadtxt (comments='#'), everything from a '#' to the end of its line is
+// ignored and lines that hold nothing else are skipped.
 //
 // Exactness.  The ingest downstream is bit-exact against the reference, so a number must convert exactly as
 // strtod / Python float() / std::from_chars do.  The parser handles the decimal forms whose conversion is a single
@@ -39,7 +40,13 @@ enum : int { kOk = 0, kMalformed = 1, kHard = 2 };
 
 // one decimal number at p (no leading blanks); advances p; returns kOk / kMalformed / kHard
 __device__ int parse_number(const char*& p, const char* end, double& out) {
-    if (p < end && *p == '+') ++p;                     // loadtxt accepts a leading '+', from_chars does not
+    if (p < end && *p == '+') {                        // loadtxt accepts a leading '+' (not "+-5"), from_chars none
+        if (p + 1 >= end) return kMalformed;
+        const char c = p[1];
+        if (c == 'i' || c == 'I' || c == 'n' || c == 'N') return kHard;
+        if (!(is_digit(c) || c == '.')) return kMalformed;
+        ++p;
+    }
     bool neg = false;
     if (p < end && *p == '-') { neg = true; ++p; }
     if (p < end && (*p == 'i' || *p == 'I' || *p == 'n' || *p == 'N')) return kHard;   // inf / nan: host parser
@@ -84,9 +91,10 @@ __device__ int parse_number(const char*& p, const char* end, double& out) {
     return kOk;
 }
 
-// does a line starting at p hold a non-blank character?  (the line ends at '\n' or at the end of the text)
+// does a line starting at p hold data?  The line ends at '\n' or at the end of the text; loadtxt (comments='#')
+// drops everything from a '#' on, so a line of blanks and / or a comment holds none
 __device__ __forceinline__ bool line_has_content(const char* p, const char* end) {
-    for (; p < end && *p != '\n'; ++p)
+    for (; p < end && *p != '\n' && *p != '#'; ++p)
         if (!is_blank(*p)) return true;
     return false;
 }
@@ -194,7 +202,7 @@ dot_parse_kernel(const char* __restrict__ txt, int64_t len, const unsigned char*
         }
         if (status == kOk) {
             while (p < end && is_blank(*p)) ++p;
-            if (p < end && *p != '\n') status = kMalformed;           // more than three columns / trailing garbage
+            if (p < end && *p != '\n' && *p != '#') status = kMalformed;   // more than three columns / garbage
         }
         if (status == kMalformed) flags[0] = 1;
         else if (status == kHard) flags[1] = 1;

@@ -22,15 +22,30 @@ namespace {
 
 inline bool is_blank(char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\v' || c == '\f'; }
 
-// number of non-empty lines in [begin, end)
+// a leading '+' is accepted by loadtxt (float("+5")) but not by from_chars; "+-5" is an error for both
+inline bool plus_sign_ok(const char* p, const char* end) {
+    if (p + 1 >= end) return false;
+    const char c = p[1];
+    return (c >= '0' && c <= '9') || c == '.' || c == 'i' || c == 'I' || c == 'n' || c == 'N';
+}
+
+inline const char* skip_comment(const char* p, const char* end) {   // from a '#' to the end of its line
+    while (p < end && *p != '\n') ++p;
+    return p;
+}
+
+// number of lines in [begin, end) that hold data: np.loadtxt drops everything from a '#' to the end of the line
+// (comments='#') and skips lines that are empty afterwards
 int64_t count_lines(const char* begin, const char* end) {
     int64_t lines = 0;
-    bool content = false;
+    bool content = false, comment = false;
     for (const char* p = begin; p < end; ++p) {
         if (*p == '\n') {
             lines += content;
-            content = false;
-        } else if (!is_blank(*p)) {
+            content = comment = false;
+        } else if (*p == '#') {
+            comment = true;
+        } else if (!comment && !is_blank(*p)) {
             content = true;
         }
     }
@@ -42,17 +57,18 @@ int64_t parse_range(const char* begin, const char* end, int64_t first, double* r
     int64_t idx = first;
     const char* p = begin;
     while (p < end) {
-        while (p < end && (is_blank(*p) || *p == '\n')) ++p;
+        while (p < end && (is_blank(*p) || *p == '\n' || *p == '#')) p = *p == '#' ? skip_comment(p, end) : p + 1;
         if (p >= end) break;
         double field[3];
         for (int f = 0; f < 3; ++f) {
             while (p < end && is_blank(*p)) ++p;
-            if (p < end && *p == '+') ++p;  // from_chars rejects a leading '+', loadtxt accepts it
+            if (p < end && *p == '+' && plus_sign_ok(p, end)) ++p;
             auto res = std::from_chars(p, end, field[f]);
             if (res.ec != std::errc()) return -1;
             p = res.ptr;
         }
         while (p < end && is_blank(*p)) ++p;
+        if (p < end && *p == '#') p = skip_comment(p, end);
         if (p < end && *p != '\n') return -1;  // more than three columns
         rows[idx] = field[0];
         cols[idx] = field[1];
@@ -77,17 +93,18 @@ CooStats parse_range_coo(const char* begin, const char* end, int64_t first, int6
     int64_t idx = first;
     const char* p = begin;
     while (p < end) {
-        while (p < end && (is_blank(*p) || *p == '\n')) ++p;
+        while (p < end && (is_blank(*p) || *p == '\n' || *p == '#')) p = *p == '#' ? skip_comment(p, end) : p + 1;
         if (p >= end) break;
         double field[3];
         for (int f = 0; f < 3; ++f) {
             while (p < end && is_blank(*p)) ++p;
-            if (p < end && *p == '+') ++p;
+            if (p < end && *p == '+' && plus_sign_ok(p, end)) ++p;
             auto res = std::from_chars(p, end, field[f]);
             if (res.ec != std::errc()) { st.parsed = -1; return st; }
             p = res.ptr;
         }
         while (p < end && is_blank(*p)) ++p;
+        if (p < end && *p == '#') p = skip_comment(p, end);
         if (p < end && *p != '\n') { st.parsed = -1; return st; }
         if (idx == last) {
             shape[0] = field[0]; shape[1] = field[1]; shape[2] = field[2];

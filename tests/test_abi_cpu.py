@@ -111,6 +111,58 @@ def test_native_dot_parser_matches_loadtxt(tmp_path):
         nfact_b200.read_in_matrix(str(bad))
 
 
+def test_native_dot_parser_comments_and_signs(tmp_path):
+    """np.loadtxt (comments='#') drops everything from a '#' to the end of the line and skips what is empty then;
+    a leading '+' is a sign, '+-' is not a number."""
+    import nfact_b200
+    from nfact_b200.matrix_handling import parse_dot_coo
+    text = ("# probtrackx matrix2\n1 101 117\n   # indented comment\n2 106 234.5 # trailing note\n3 107 96#x\n"
+            "\n#\n+4 +5 +7.5\n5 6 +.5\n99 199 438 # shape")
+    path = tmp_path / "fdt_matrix2.dot"
+    path.write_text(text)
+    got = nfact_b200.read_in_matrix(str(path))
+    ref = np.loadtxt(str(path))
+    assert got.shape == ref.shape == (6, 3) and np.array_equal(got, ref)
+    rows, cols, vals, shape = parse_dot_coo(text.encode())
+    assert shape == (99, 199) and np.array_equal(rows, ref[:-1, 0].astype(np.int32) - 1)
+    assert np.array_equal(cols, ref[:-1, 1].astype(np.int32) - 1) and np.array_equal(vals, ref[:-1, 2])
+    for bad in ("1 2 #3\n4 5 6\n", "+-1 2 3\n", "1 2 +\n", "1 + 2 3\n"):
+        path.write_text(bad)
+        with pytest.raises(ValueError):
+            np.loadtxt(str(path))
+        with pytest.raises(ValueError):
+            nfact_b200.read_in_matrix(str(path))
+
+
+def test_native_dot_parser_fuzz_against_loadtxt(tmp_path):
+    """Random legal files in the number formats probtrackx and printf produce: the native parser returns exactly the
+    float64 array np.loadtxt returns (correct rounding of every decimal string)."""
+    import nfact_b200
+    rng = np.random.default_rng(20261020)
+    formats = ["{:d}", "{:.6g}", "{:.9e}", "{:.3f}", "{:.17g}", "{!r}", "{:.1f}", "{:E}"]
+    seps = [" ", "  ", "\t", " \t "]
+    path = tmp_path / "fuzz.dot"
+    for trial in range(25):
+        n = int(rng.integers(1, 400))
+        lines = []
+        for _ in range(n):
+            fmt = formats[int(rng.integers(len(formats)))]
+            mag = 10.0 ** rng.uniform(-8, 12)
+            v = float(rng.uniform(0, 1) * mag)
+            val = fmt.format(int(v) if fmt == "{:d}" else v)
+            sep = seps[int(rng.integers(len(seps)))]
+            lead = " " * int(rng.integers(0, 3))
+            tail = ["", " ", "\r", " # c"][int(rng.integers(4))]
+            lines.append(f"{lead}{int(rng.integers(1, 70000))}{sep}{int(rng.integers(1, 120000))}{sep}{val}{tail}")
+            if rng.random() < 0.05:
+                lines.append(["", "   ", "# comment", "\t"][int(rng.integers(4))])
+        lines.append("70000 120000 0")
+        path.write_text("\n".join(lines) + ("\n" if trial % 2 else ""))
+        got = nfact_b200.read_in_matrix(str(path))
+        ref = np.loadtxt(str(path), ndmin=2)
+        assert got.shape == ref.shape and np.array_equal(got, ref), trial
+
+
 def test_fused_coo_parser_matches_the_reference_construction(tmp_path, golden_subjects):
     """nfb_dot_parse_coo == loadtxt + `[:-1] - 1` + integer cast + last-line shape
     (NFACT/base/matrix_handling.py:131-137), with scipy's index errors."""

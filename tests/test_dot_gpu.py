@@ -87,6 +87,25 @@ def test_hard_numbers_fall_back_to_the_host_parser(tmp_path):
     x.free()
 
 
+def test_comments_are_dropped_like_loadtxt():
+    """np.loadtxt(comments='#'): everything from a '#' to the end of its line is ignored, on both parsers."""
+    text = (b"# probtrackx matrix2\n1 101 117\n   # indented comment\n2 106 234.5 # trailing note\n3 107 96#x\n"
+            b"\n#\n+4 +5 +7.5\n5 6 +.5\n99 199 438 # shape")
+    host, dev = _both(text)
+    _assert_same(host, dev)
+    assert host[3] == (99, 199) and host[0].tolist() == [0, 1, 2, 3, 4] and host[2].tolist() == [117, 234.5, 96, 7.5, 0.5]
+    # a comment longer than a parser segment, and comments at segment boundaries
+    rng = np.random.default_rng(5)
+    lines = []
+    for i in range(20000):
+        lines.append(f"{int(rng.integers(1, 900))} {int(rng.integers(1, 700))} {int(rng.integers(0, 5000))}")
+        if i % 37 == 0:
+            lines.append("#" + "c" * int(rng.integers(0, 400)))
+        if i % 53 == 0:
+            lines[-1] += "   # " + "n" * int(rng.integers(0, 200))
+    _assert_same(*_both(("\n".join(lines) + "\n900 700 0\n").encode()))
+
+
 def test_errors_match_the_host_parser():
     import nfact_b200
     from nfact_b200.device import parse_dot_coo_device
@@ -101,6 +120,9 @@ def test_errors_match_the_host_parser():
         b"0 1 5\n3 3 0\n": "negative row",
         b"1 -1 5\n3 3 0\n": "negative column",
         b"1e12 1 5\n3 3 0\n": "32-bit",
+        b"+-1 1 5\n3 3 0\n": "malformed",
+        b"1 1 +\n3 3 0\n": "malformed",
+        b"1 1 #5\n3 3 0\n": "malformed",
     }
     for text, what in bad.items():
         with pytest.raises(Exception, match=what):
