@@ -124,21 +124,31 @@ __global__ void __launch_bounds__(kNnlsWarps * 32, 1)
 nnls_smem_kernel(const double* __restrict__ gram, int k, const float* __restrict__ rhs, int rhs_splits,
                  int64_t rhs_stride, int64_t ld_rhs, int64_t cols, double* __restrict__ sol, int64_t ld_sol,
                  int max_outer, double tol, int* __restrict__ status, unsigned long long* __restrict__ steps_total,
-                 unsigned long long* __restrict__ next_col, int initial_sweeps, double face_reduction) {
+                 unsigned long long* __restrict__ next_col, int initial_sweeps, double face_reduction,
+                 int scale_diag) {
     extern __shared__ double smd[];
     const int ntri = k * (k + 1) / 2;
     double* g_tri = smd;                                 // k (k + 1) / 2 packed lower triangle, row-major
     double* zeros = smd + ntri;                          // k zeros: "column t" of the padding rows u >= k
     double* inv_diag = zeros + k;                        // k  (0 where G[t][t] <= 0)
+    double* scl = inv_diag + k;                          // k  symmetric diagonal scaling s_t = 1 / sqrt(G[t][t])
     const int lane = threadIdx.x & 31;
-    for (int idx = threadIdx.x; idx < k * k; idx += blockDim.x) {
-        const int r = idx / k, c = idx - r * k;
-        if (c <= r) g_tri[r * (r + 1) / 2 + c] = gram[idx];
-    }
+    // The problems are solved in the variables h' = h / s with G' = S G S (unit diagonal), r' = S r: the
+    // constraint h >= 0 and the coordinate steps are invariant under a positive diagonal scaling, and plain CG
+    // on G' is Jacobi-preconditioned CG on G -- the component norms of NMF maps spread over orders of magnitude.
     for (int t = threadIdx.x; t < k; t += blockDim.x) {
         const double d = gram[static_cast<int64_t>(t) * k + t];
-        inv_diag[t] = d > 0.0 ? 1.0 / d : 0.0;
+        scl[t] = (scale_diag && d > 0.0) ? 1.0 / sqrt(d) : 1.0;
         zeros[t] = 0.0;
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < k * k; idx += blockDim.x) {
+        const int r = idx / k, c = idx - r * k;
+        if (c <= r) g_tri[r * (r + 1) / 2 + c] = gram[idx] * scl[r] * scl[c];
+    }
+    for (int t = threadIdx.x; t < k; t += blockDim.x) {
+        const double d = gram[static_cast<int64_t>(t) * k + t] * scl[t] * scl[t];
+        inv_diag[t] = d > 0.0 ? 1.0 / d : 0.0;
     }
     // G[u][t] for this lane's coordinates u = lane + 32 i:
     //   u >= t : g_tri[ro[i] + t]  with ro[i] = u (u + 1) / 2  (padding rows point at the zero region)
@@ -176,6 +186,7 @@ nnls_smem_kernel(const double* __restrict__ gram, int k, const float* __restrict
             double r = 0.0;
             if (t < k)
                 for (int s = 0; s < rhs_splits; ++s) r += static_cast<double>(rhs[s * rhs_stride + t * ld_rhs + j]);
+            if (t < k) r *= scl[t];
             h[i] = 0.0;
             g[i] = -r;
             rmax = fmax(rmax, fabs(r));
@@ -314,7 +325,7 @@ nnls_smem_kernel(const double* __restrict__ gram, int k, const float* __restrict
 #pragma unroll
         for (int i = 0; i < KPL; ++i) {
             const int t = lane + 32 * i;
-            if (t < k) sol[t * ld_sol + j] = h[i];
+            if (t < k) sol[t * ld_sol + j] = h[i] * scl[t];
         }
     }
 }
@@ -326,7 +337,7 @@ int nnls_gram_batched(const double* gram, int64_t k, const float* rhs, int rhs_s
                       cudaStream_t stream, unsigned long long* steps_total, unsigned long long* counter) {
     if (k == 0 || cols == 0) return 0;
     NFB_CHECK(k <= 512, "n_components > 512 is not supported by the NNLS kernel");
-    const size_t smem_fast = (static_cast<size_t>(k) * (k + 1) / 2 + 2 * k) * sizeof(double);
+    const size_t smem_fast = (static_cast<size_t>(k) * (k + 1) / 2 + 3 * k) * sizeof(double);
     if (smem_fast <= 220 * 1024 && k <= 224 && counter != nullptr) {
         NFB_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream));
         // 16 warps per SM (128 registers, a few spilled values at k > 192) measured faster than 12 spill-free ones
@@ -335,6 +346,7 @@ int nnls_gram_batched(const double* gram, int64_t k, const float* rhs, int rhs_s
         const int kNnlsWarps = wide ? 16 : 12;
         static const int sweeps0 = getenv("NFB_NNLS_SWEEPS") ? std::max(1, atoi(getenv("NFB_NNLS_SWEEPS"))) : kInitialSweeps;
         static const double face_red = getenv("NFB_NNLS_FACE") ? atof(getenv("NFB_NNLS_FACE")) : kFaceReduction;
+        static const int scale_diag = getenv("NFB_NNLS_SCALE") ? atoi(getenv("NFB_NNLS_SCALE")) : 1;
         const int grid = static_cast<int>(std::min<int64_t>(ceil_div64(cols, kNnlsWarps), sm_count()));
 #define NFB_NNLS_FAST(KPL)                                                                                       \
     do {                                                                                                         \
@@ -343,7 +355,8 @@ int nnls_gram_batched(const double* gram, int64_t k, const float* rhs, int rhs_s
                                       static_cast<int>(smem_fast)));                                             \
         kernel<<<grid, kNnlsWarps * 32, smem_fast, stream>>>(gram, static_cast<int>(k), rhs, rhs_splits,         \
                                                              rhs_stride, ld_rhs, cols, sol, ld_sol, max_outer,   \
-                                                             1e-10, status, steps_total, counter, sweeps0, face_red); \
+                                                             1e-10, status, steps_total, counter, sweeps0, face_red, \
+                                                             scale_diag);                                        \
     } while (0)
         if (k <= 32) NFB_NNLS_FAST(1);
         else if (k <= 64) NFB_NNLS_FAST(2);
