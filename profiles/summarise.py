@@ -78,3 +78,9 @@ if os.path.exists(rep):
     print(open(os.path.join(dst, f"{tag}_ncu_full.csv")).read()[:3000])
 if os.path.exists(os.path.join(src, f"{tag}_bench.json")):
     shutil.copy(os.path.join(src, f"{tag}_bench.json"), os.path.join(dst, f"{tag}_bench_C3_cd.json"))
+nnls = os.path.join(src, f"{tag}_nnls_full.ncu-rep")
+if os.path.exists(nnls):
+    subprocess.run([sys.executable, os.path.join(dst, "extract_full.py"), nnls, os.path.join(dst, f"{tag}_ncu_full_nnls_C3.csv"),
+                    "ncu --set full --clock-control none --import-source on -k regex:nnls_smem_kernel -c 2 python "
+                    "tests/gpu_dr_probe.py C3 1 (stage 1: 110000 columns, stage 2: 59412 rows, k=200)"],
+                   stdout=subprocess.DEVNULL)
