@@ -6,7 +6,10 @@ where the oracle cannot run.  Inputs are generated on the device exactly like be
   * both against a float64 evaluation of the same trace on a row sample (anchors the value, not only the symmetry);
   * coordinate descent is monotone: the penalised objective 0.5 ||X - WH||^2 + l1_W |W|_1 + l1_H |H|_1 never
     increases from one iteration to the next (sklearn's solver has the same property);
-  * factors stay non-negative and finite; the multiplicative update is monotone in ||X - WH||_F.
+  * factors stay non-negative and finite; the multiplicative update is monotone in ||X - WH||_F;
+  * the dual regression of the full-size subject satisfies the NNLS optimality (KKT) conditions of both stages,
+    evaluated in float64 on sampled target columns / seed rows, for group components whose norms spread over four
+    orders of magnitude (the solver works in diagonally scaled variables).
 """
 import numpy as np
 import pytest
@@ -27,12 +30,15 @@ def resident():
     handle = get_handle()
     sample_rows = torch.arange(0, M, 997, device=dev)
     x_sample = x[sample_rows].double().cpu().numpy()
+    sample_cols = torch.arange(0, N, 1999, device=dev)
+    x_cols = x[:, sample_cols].double().cpu().numpy()
     x_mean = float(x.sum(dtype=torch.float64)) / (M * N)
     xmat = DeviceMatrix.from_device_ptr(x.data_ptr(), M, N, N, handle=handle)
     del x
     torch.cuda.empty_cache()
     w0, h0 = random_init(torch, dev, x_mean, M, N, K, 0)
-    yield {"xmat": xmat, "w0": w0, "h0": h0, "rows": sample_rows.cpu().numpy(), "x_sample": x_sample, "torch": torch}
+    yield {"xmat": xmat, "w0": w0, "h0": h0, "rows": sample_rows.cpu().numpy(), "x_sample": x_sample, "torch": torch,
+           "cols": sample_cols.cpu().numpy(), "x_cols": x_cols}
     xmat.free()
 
 
@@ -80,3 +86,33 @@ def test_objective_is_monotone_at_full_size(resident, solver):
     for before, after in zip(values, values[1:]):
         assert after <= before * (1 + 1e-6), values
     assert values[-1] < values[0]
+
+
+def test_dual_regression_kkt_at_full_size(resident):
+    """nmf_dual_regression at C3: h >= 0, gradient >= 0 off the support and == 0 on it (scipy's nnls returns the
+    point with exactly these properties), both stages, on every 1999th target column and every 997th seed row."""
+    import nfact_b200
+    xmat = resident["xmat"]
+    rng = np.random.default_rng(4)
+    G = rng.gamma(0.3, 1.0, (M, K)) * (rng.random((M, K)) < 0.3)
+    G *= 10.0 ** rng.uniform(-2, 2, K)                       # component norms over four orders of magnitude
+    G[:, 7] = 0.0                                            # a dead component
+    dr = nfact_b200.nmf_dual_regression({"grey_components": G}, xmat)
+    Hs, Gs = dr["white_components"], dr["grey_components"]
+    assert Hs.shape == (K, N) and Gs.shape == (M, K) and Hs.dtype == np.float64 and Gs.dtype == np.float64
+    assert np.isfinite(Hs).all() and np.isfinite(Gs).all() and Hs.min() >= 0 and Gs.min() >= 0
+    assert not Hs[7].any()
+    # stage 1: min_h ||G h - x_j||, gradient G'(G h - x_j)
+    cols, xc = resident["cols"], resident["x_cols"]          # [M, c]
+    hc = Hs[:, cols]
+    grad1 = G.T @ (G @ hc - xc)
+    scale1 = np.abs(G.T @ xc).max()
+    assert grad1.min() > -1e-5 * scale1, grad1.min() / scale1
+    assert np.abs(grad1[hc > 0]).max() < 1e-5 * scale1, np.abs(grad1[hc > 0]).max() / scale1
+    # stage 2: min_g ||Hs' g - x_i||, gradient (g Hs - x_i) Hs'
+    rows, xr = resident["rows"], resident["x_sample"]        # [r, N]
+    gr = Gs[rows]
+    grad2 = (gr @ Hs - xr) @ Hs.T
+    scale2 = np.abs(xr @ Hs.T).max()
+    assert grad2.min() > -1e-5 * scale2, grad2.min() / scale2
+    assert np.abs(grad2[gr > 0]).max() < 1e-5 * scale2, np.abs(grad2[gr > 0]).max() / scale2
