@@ -93,3 +93,31 @@ def test_row_range_is_a_partition():
             assert max(sizes) - min(sizes) <= 1
     with pytest.raises(ValueError):
         row_range(10, 2, 2)
+
+
+def test_dual_regression_subjects_are_partitioned_over_ranks(monkeypatch, tmp_path):
+    """run_locally(rank, world): rank r takes subjects r, r + world, ... (no collective); every subject is done by
+    exactly one rank, in list order, and `save` sees each of them once.  The device work is replaced by a recorder:
+    this is the host-side distribution logic only."""
+    import nfact_b200.dual_regression as drmod
+    subjects = [str(tmp_path / f"sub-{i:02d}") for i in range(11)]
+    seen = {}
+
+    def fake_stream(load_matrix, n_subjects, components, device=0, prefetch=True, options=None):
+        for idx in range(n_subjects):
+            yield idx, {"grey_components": np.zeros((2, 1)), "white_components": np.zeros((1, 3))}
+
+    monkeypatch.setattr(drmod, "stream_subjects", fake_stream)
+    monkeypatch.setattr(drmod, "_postprocess_options", lambda *a, **k: {})
+    for world in (1, 2, 3, 8):
+        done = []
+        for rank in range(world):
+            saved = []
+            out = drmod.run_locally(subjects, {"grey_components": np.zeros((2, 1))}, ["l.gii"], rank=rank, world=world,
+                                    save=lambda d, res: saved.append(d))
+            assert list(out) == saved == subjects[rank::world]
+            assert all(v is None for v in out.values())          # results are handed to `save`, not kept
+            done += saved
+        assert sorted(done) == subjects
+    kept = drmod.run_locally(subjects, {"grey_components": np.zeros((2, 1))}, ["l.gii"], rank=1, world=4)
+    assert list(kept) == subjects[1::4] and all(v is not None for v in kept.values())
