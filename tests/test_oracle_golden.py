@@ -173,3 +173,29 @@ def test_oracle_wta_matches_reference():
             assert white.dtype == g[f"white_wta_{key}_{tag}"].dtype and white.shape == g[f"white_wta_{key}_{tag}"].shape
             assert np.array_equal(white, g[f"white_wta_{key}_{tag}"]), (tag, key)
             assert np.array_equal(grey, g[f"grey_wta_{key}_{tag}"]), (tag, key)
+
+
+def test_oracle_wta_against_sklearn_formula():
+    """The restatement against the reference's own three lines (StandardScaler + max / argmax, image_handling.py
+    :240-245) evaluated with the installed sklearn, on shapes and value patterns the golden file does not hold."""
+    from sklearn.preprocessing import StandardScaler
+
+    def reference_formula(component, axis, z_thr):
+        z = StandardScaler().fit_transform(component)
+        top = np.max(z, axis=axis, keepdims=True)
+        wta = np.argmax(z, axis=axis, keepdims=True) + 1
+        wta[top < z_thr] = 0.0
+        return np.array(wta, dtype=int)
+
+    rng = np.random.default_rng(123)
+    for (m, k) in ((1, 1), (1, 7), (5, 1), (257, 13), (77, 203)):
+        for dtype in (np.float32, np.float64):
+            grey = (rng.gamma(0.5, 1.0, (m, k)) * (rng.random((m, k)) < 0.7)).astype(dtype)
+            grey[:, 0] = 1.25                                     # a constant column
+            white = np.ascontiguousarray(grey.T)
+            for z in (-1.0, 0.0, 0.5, 2.0):
+                for arr, axis in ((grey, 1), (white, 0), (grey, 0), (white, 1)):
+                    assert np.array_equal(orc.create_wta_map(arr, axis, z), reference_formula(arr.copy(), axis, z)), \
+                        (m, k, dtype, z, axis)
+    counts = rng.integers(0, 40, (300, 9))
+    assert np.array_equal(orc.create_wta_map(counts, 1, 1.0), reference_formula(counts, 1, 1.0))
