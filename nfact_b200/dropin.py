@@ -50,6 +50,9 @@ _IMPORTERS = {
                                                            "normalise_components"),
 }
 
+_DR_LOOP = ("NFACT.dual_reg.dual_regression.set_up_dual_regression", "run_locally")
+_DR_LOOP_IMPORTERS = ("NFACT.dual_reg.__main__",)                                                        # :2-5
+
 _ENTRY_POINTS = {   # pyproject.toml:41-48
     "nfact_decomp": ("NFACT.decomp.__main__", "nfact_decomp_main"),
     "nfact_dr": ("NFACT.dual_reg.__main__", "nfact_dr_main"),
@@ -64,6 +67,51 @@ def _replacement(name: str):
     if hasattr(nfact_b200, name):
         return getattr(nfact_b200, name)
     return getattr(nmfsso, name)
+
+
+def run_locally(args: dict, paths: dict) -> None:
+    """Drop-in for ``run_locally(args, paths)``, NFACT/dual_reg/dual_regression/set_up_dual_regression.py:186-235:
+    the subject loop of ``nfact_dr``.  The reference loads, regresses, post-processes and saves one subject after the
+    other through ``dual_regression_pipeline`` (run_dual_regression.py:66-199); here the same steps run through
+    ``nfact_b200.run_locally``: the next subject's ``fdt_matrix2.dot[.lz4]`` is decoded, parsed and ingested straight
+    into HBM while the current one is regressed, the group components are uploaded once, thresholding / z-scoring
+    happen on the device, and every result goes to the reference's own ``save_dual_regression_images`` with the
+    reference's arguments.  ICA keeps the reference's loop."""
+    import os
+    original = _originals.get(_DR_LOOP)
+    if str(args["algo"]).lower() != "nmf":
+        if original is None:
+            raise RuntimeError("nfact_b200 only replaces the NMF dual regression")
+        return original(args, paths)
+    import nfact_b200
+    from nfact_b200.utils import colours, error_and_exit, nprint
+    drf = importlib.import_module("NFACT.dual_reg.nfact_dr_functions")
+    col = colours()
+    nprint(f"{col['pink']}Running:{col['reset']} Locally")
+    nprint(f"{col['pink']}DR Method:{col['reset']} Non-negative Regression")
+    nprint(f"{col['pink']}Obtaining:{col['reset']} Components")
+    try:
+        components = drf.get_group_level_components(paths["component_path"], paths["group_average_path"],
+                                                    args["seeds"], args["roi"])
+    except Exception as e:
+        error_and_exit(False, f"Unable to find components due to {e}")
+    out_dir = os.path.join(args["outdir"], "nfact_dr")
+    algo = str(args["algo"]).upper()
+
+    def save(subject_dir, dr_results):
+        sub_id = drf.get_subject_id(subject_dir)
+        nprint(f"{col['pink']}Saving{col['reset']}: Components ({sub_id})", to_flush=True)
+        try:
+            drf.save_dual_regression_images(dr_results, out_dir, args["seeds"], algo,
+                                            dr_results["white_components"].shape[0], sub_id, subject_dir,
+                                            args["roi"], args["cifti"])
+        except Exception as e:
+            error_and_exit(False, f"Unable to save images due to {e}")
+        nprint(f"{col['pink']}Completed{col['reset']}: {sub_id}", to_flush=True)
+
+    nfact_b200.run_locally(list(args["ptxdir"]), components, args["seeds"], threshold=int(args["threshold"]),
+                           normalise=bool(args["normalise"]), save=save)
+    return None
 
 
 def install(strict: bool = False) -> list:
@@ -95,6 +143,20 @@ def install(strict: bool = False) -> list:
                 _originals.setdefault((modname, name), old)
                 setattr(module, name, new)
                 patched.append(f"{modname}.{name}")
+    # the subject loop of nfact_dr (not a same-named nfact_b200 function: it takes the reference's args / paths dicts)
+    for modname in (_DR_LOOP[0],) + _DR_LOOP_IMPORTERS:
+        try:
+            module = importlib.import_module(modname)
+        except Exception:
+            if strict:
+                raise
+            continue
+        old = getattr(module, _DR_LOOP[1], None)
+        if old is None or old is run_locally:
+            continue
+        _originals.setdefault((modname, _DR_LOOP[1]), old)
+        setattr(module, _DR_LOOP[1], run_locally)
+        patched.append(f"{modname}.{_DR_LOOP[1]}")
     return patched
 
 

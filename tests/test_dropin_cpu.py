@@ -9,6 +9,7 @@ import os
 import sys
 import types
 
+import numpy as np
 import pytest
 
 import nfact_b200
@@ -136,3 +137,61 @@ def test_entry_point_modules_pick_up_the_rebound_functions(reference):
 def test_usage_message():
     with pytest.raises(SystemExit):
         dropin.main(["nfact_pp"])
+
+
+def test_nfact_dr_subject_loop_is_rebound_and_keeps_the_reference_calls(reference, monkeypatch, tmp_path):
+    """run_locally(args, paths) of set_up_dual_regression.py:186-235: after install() nfact_dr's main calls the
+    nfact_b200 loop, which fetches the group components and saves every subject through the reference's own
+    functions with the reference's arguments (checked against their real signatures); ICA keeps the reference loop."""
+    try:
+        setup = importlib.import_module("NFACT.dual_reg.dual_regression.set_up_dual_regression")
+        drf = importlib.import_module("NFACT.dual_reg.nfact_dr_functions")
+    except Exception as exc:
+        pytest.skip(f"reference dual-regression modules need an image library that cannot be stubbed: {exc}")
+    reference_loop = setup.run_locally
+    dropin.install()
+    assert setup.run_locally is dropin.run_locally and reference_loop is not dropin.run_locally
+
+    subjects = [str(tmp_path / "subjects" / f"sub_{i:02d}" / "omatrix2") for i in range(3)]
+    args = {"algo": "nmf", "ptxdir": subjects, "seeds": ["l.surf.gii", "r.surf.gii"], "roi": ["l_roi.gii", "r_roi.gii"],
+            "outdir": str(tmp_path / "out"), "threshold": "3", "normalise": True, "cifti": False, "n_cores": 2}
+    paths = {"component_path": str(tmp_path / "comp"), "group_average_path": str(tmp_path / "avg")}
+    calls = {"components": [], "saved": [], "loop": []}
+    save_sig = inspect.signature(drf.save_dual_regression_images)
+    comp_sig = inspect.signature(drf.get_group_level_components)
+
+    def fake_components(*a, **k):
+        bound = comp_sig.bind(*a, **k)
+        calls["components"].append(tuple(bound.arguments.values()))
+        return {"grey_components": np.ones((4, 2)), "white_components": np.ones((2, 5))}
+
+    def fake_save(*a, **k):
+        bound = save_sig.bind(*a, **k)
+        bound.apply_defaults()
+        calls["saved"].append(bound.arguments)
+
+    def fake_loop(list_of_subject_dirs, components, seeds, threshold=3, normalise=False, rank=0, world=1, save=None,
+                  prefetch=True):
+        calls["loop"].append((list(list_of_subject_dirs), seeds, threshold, normalise))
+        for d in list_of_subject_dirs:
+            save(d, {"grey_components": np.zeros((4, 2)), "white_components": np.zeros((2, 5)),
+                     "normalised_grey": np.zeros((4, 2)), "normalised_white": np.zeros((2, 5))})
+        return {d: None for d in list_of_subject_dirs}
+
+    monkeypatch.setattr(drf, "get_group_level_components", fake_components)
+    monkeypatch.setattr(drf, "save_dual_regression_images", fake_save)
+    monkeypatch.setattr(nfact_b200, "run_locally", fake_loop)
+    assert setup.run_locally(args, paths) is None
+    assert calls["components"] == [(paths["component_path"], paths["group_average_path"], args["seeds"], args["roi"])]
+    assert calls["loop"] == [(subjects, args["seeds"], 3, True)]
+    assert [c["ptx_directory"] for c in calls["saved"]] == subjects
+    first = calls["saved"][0]
+    assert first["nfact_path"] == os.path.join(args["outdir"], "nfact_dr") and first["algo"] == "NMF"
+    assert first["dim"] == 2 and first["seeds"] == args["seeds"] and first["roi"] == args["roi"]
+    assert first["sub"] == drf.get_subject_id(subjects[0]) == "sub_00" and first["cifti_save"] is False
+    assert "normalised_white" in first["components"]
+
+    seen = []
+    monkeypatch.setitem(dropin._originals, dropin._DR_LOOP, lambda a, p: seen.append(a["algo"]))
+    dropin.run_locally(dict(args, algo="ica"), paths)
+    assert seen == ["ica"] and len(calls["loop"]) == 1           # ICA went to the reference's loop
