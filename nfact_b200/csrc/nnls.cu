@@ -118,6 +118,7 @@ nnls_cd_kernel(const double* __restrict__ gram, int k, const float* __restrict__
 
 constexpr int kInitialSweeps = 6;          // Gauss-Seidel passes before the first CG phase
 constexpr double kFaceReduction = 1e-2;    // residual reduction asked of one CG phase
+constexpr int kGreedyBudget = 8;           // greedy coordinate steps per problem, in multiples of k
 
 template <int KPL, int kNnlsWarps>
 __global__ void __launch_bounds__(kNnlsWarps * 32, 1)
@@ -125,7 +126,7 @@ nnls_smem_kernel(const double* __restrict__ gram, int k, const float* __restrict
                  int64_t rhs_stride, int64_t ld_rhs, int64_t cols, double* __restrict__ sol, int64_t ld_sol,
                  int max_outer, double tol, int* __restrict__ status, unsigned long long* __restrict__ steps_total,
                  unsigned long long* __restrict__ next_col, int initial_sweeps, double face_reduction,
-                 int scale_diag) {
+                 int scale_diag, int greedy_budget) {
     extern __shared__ double smd[];
     const int ntri = k * (k + 1) / 2;
     double* g_tri = smd;                                 // k (k + 1) / 2 packed lower triangle, row-major
@@ -214,6 +215,61 @@ nnls_smem_kernel(const double* __restrict__ gram, int k, const float* __restrict
         };
 
         bool converged = (rmax == 0.0);
+        // ---- greedy (Gauss-Southwell) coordinate descent ------------------------------------------------------
+        // Every step takes the coordinate with the largest projected gradient (unit diagonal after the scaling, so
+        // that is also the largest decrease of the objective) and minimises over it exactly.  On NMF-type problems
+        // the support is found and solved to the KKT tolerance in 2-3 k column updates, against 5-10 k for cyclic
+        // sweeps + CG (simulated on C3-shaped problems, scratch/nnls_sim7.py): a cyclic sweep spends most of its
+        // updates on coordinates that enter the support only to leave it again.  The selection costs no shared-
+        // memory traffic: a 24-bit key (sign-stripped high word of the gradient, truncated) + the coordinate index
+        // per slot, one redux.sync per step.  The sweeps + CG loop below stays as the fallback for whatever the
+        // budget did not finish (ill-conditioned Gram matrices).
+        bool greedy_used = false;
+        if (greedy_budget > 0 && !converged) {
+            greedy_used = true;
+            // stop at half the tolerance: the truncated keys under-estimate by < 2^-11, the exact check follows
+            const unsigned stop_key = static_cast<unsigned>(__double2hiint(0.5 * thresh)) & 0x7fffff00u;
+            auto greedy_step = [&](auto slot_tag, int o) -> bool {
+                constexpr int I = decltype(slot_tag)::value;
+                const int t = 32 * I + o;
+                const double gt = shfl_d(g[I], o);
+                const double ht = shfl_d(h[I], o);
+                const double inv = inv_diag[t];
+                const double hn = fmax(fma(-gt, inv, ht), 0.0);
+                const double delta = inv != 0.0 ? hn - ht : 0.0;
+                if (delta != 0.0) {  // warp-uniform
+                    axpy_col(slot_tag, o, delta, g);
+                    if (lane == o) h[I] = hn;
+                }
+                return delta != 0.0;
+            };
+            for (int left = greedy_budget; left > 0; --left) {
+                unsigned best = 0u;
+#pragma unroll
+                for (int i = 0; i < KPL; ++i) {
+                    const int ghi = __double2hiint(g[i]);
+                    // projected gradient: |g| on the support (h > 0), max(-g, 0) off it
+                    const bool take = (32 * i + lane < k) && (__double2hiint(h[i]) > 0 || ghi < 0);
+                    const unsigned key = ((static_cast<unsigned>(ghi) & 0x7fffff00u) | static_cast<unsigned>(32 * i + lane));
+                    best = max(best, take ? key : 0u);
+                }
+                best = __reduce_max_sync(0xffffffffu, best);
+                if ((best & 0x7fffff00u) <= stop_key) break;
+                const int t = static_cast<int>(best & 0xffu);
+                bool moved = false;
+                [&]<int... Is>(std::integer_sequence<int, Is...>) {
+                    ((((t >> 5) == Is) ? (void)(moved = greedy_step(std::integral_constant<int, Is>{}, t & 31)) : (void)0), ...);
+                }(std::make_integer_sequence<int, KPL>{});
+                ++nsteps;
+                if (!moved) break;       // a step lost to rounding: leave the rest to the loop below
+            }
+            double viol = 0.0;
+#pragma unroll
+            for (int i = 0; i < KPL; ++i) viol = fmax(viol, h[i] > 0.0 ? fabs(g[i]) : fmax(-g[i], 0.0));
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) viol = fmax(viol, __shfl_xor_sync(0xffffffffu, viol, o));
+            converged = viol <= thresh;
+        }
         for (int outer = 0; outer < max_outer && !converged; ++outer) {
             // Gauss-Seidel sweeps over the coordinates that can move: the support (h > 0) and the candidates to
             // enter it (g < 0).  Everything else has a zero projected gradient and a step there is a no-op, so a
@@ -230,7 +286,7 @@ nnls_smem_kernel(const double* __restrict__ gram, int k, const float* __restrict
                     step(slot_tag, o);
                 }
             };
-            const int n_sweeps = outer == 0 ? initial_sweeps : 1;
+            const int n_sweeps = (outer == 0 && !greedy_used) ? initial_sweeps : 1;
             for (int sw = 0; sw < n_sweeps; ++sw) {
                 [&]<int... Is>(std::integer_sequence<int, Is...>) {
                     (sweep(std::integral_constant<int, Is>{}), ...);
@@ -347,6 +403,9 @@ int nnls_gram_batched(const double* gram, int64_t k, const float* rhs, int rhs_s
         static const int sweeps0 = getenv("NFB_NNLS_SWEEPS") ? std::max(1, atoi(getenv("NFB_NNLS_SWEEPS"))) : kInitialSweeps;
         static const double face_red = getenv("NFB_NNLS_FACE") ? atof(getenv("NFB_NNLS_FACE")) : kFaceReduction;
         static const int scale_diag = getenv("NFB_NNLS_SCALE") ? atoi(getenv("NFB_NNLS_SCALE")) : 1;
+        // greedy coordinate steps before the sweeps + CG loop takes over, in multiples of k (0: no greedy phase)
+        static const int greedy_mult = getenv("NFB_NNLS_GREEDY") ? std::max(0, atoi(getenv("NFB_NNLS_GREEDY"))) : kGreedyBudget;
+        const int greedy_budget = scale_diag ? greedy_mult * static_cast<int>(k) : 0;   // the keys assume a unit diagonal
         const int grid = static_cast<int>(std::min<int64_t>(ceil_div64(cols, kNnlsWarps), sm_count()));
 #define NFB_NNLS_FAST(KPL)                                                                                       \
     do {                                                                                                         \
@@ -356,7 +415,7 @@ int nnls_gram_batched(const double* gram, int64_t k, const float* rhs, int rhs_s
         kernel<<<grid, kNnlsWarps * 32, smem_fast, stream>>>(gram, static_cast<int>(k), rhs, rhs_splits,         \
                                                              rhs_stride, ld_rhs, cols, sol, ld_sol, max_outer,   \
                                                              1e-10, status, steps_total, counter, sweeps0, face_red, \
-                                                             scale_diag);                                        \
+                                                             scale_diag, greedy_budget);                         \
     } while (0)
         if (k <= 32) NFB_NNLS_FAST(1);
         else if (k <= 64) NFB_NNLS_FAST(2);
