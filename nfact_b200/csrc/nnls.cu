@@ -119,6 +119,7 @@ nnls_cd_kernel(const double* __restrict__ gram, int k, const float* __restrict__
 constexpr int kInitialSweeps = 6;          // Gauss-Seidel passes before the first CG phase
 constexpr double kFaceReduction = 1e-2;    // residual reduction asked of one CG phase
 constexpr int kGreedyBudget = 8;           // greedy coordinate steps per problem, in multiples of k
+constexpr int kGreedyBatch = 3;            // steps taken per pass over the gradient keys
 
 template <int KPL, int kNnlsWarps>
 __global__ void __launch_bounds__(kNnlsWarps * 32, 1)
@@ -126,7 +127,7 @@ nnls_smem_kernel(const double* __restrict__ gram, int k, const float* __restrict
                  int64_t rhs_stride, int64_t ld_rhs, int64_t cols, double* __restrict__ sol, int64_t ld_sol,
                  int max_outer, double tol, int* __restrict__ status, unsigned long long* __restrict__ steps_total,
                  unsigned long long* __restrict__ next_col, int initial_sweeps, double face_reduction,
-                 int scale_diag, int greedy_budget) {
+                 int scale_diag, int greedy_budget, int greedy_batch) {
     extern __shared__ double smd[];
     const int ntri = k * (k + 1) / 2;
     double* g_tri = smd;                                 // k (k + 1) / 2 packed lower triangle, row-major
@@ -189,7 +190,7 @@ nnls_smem_kernel(const double* __restrict__ gram, int k, const float* __restrict
                 for (int s = 0; s < rhs_splits; ++s) r += static_cast<double>(rhs[s * rhs_stride + t * ld_rhs + j]);
             if (t < k) r *= scl[t];
             h[i] = 0.0;
-            g[i] = -r;
+            g[i] = t < k ? -r : 0.0;         // padding slots: +0, they stay +0 (their Gram entries are zeros)
             rmax = fmax(rmax, fabs(r));
         }
 #pragma unroll
@@ -243,25 +244,35 @@ nnls_smem_kernel(const double* __restrict__ gram, int k, const float* __restrict
                 }
                 return delta != 0.0;
             };
-            for (int left = greedy_budget; left > 0; --left) {
-                unsigned best = 0u;
+            for (int left = greedy_budget; left > 0;) {
+                // this lane's best candidate.  Projected gradient: |g| on the support (h > 0), max(-g, 0) off it;
+                // the padding slots hold h = 0, g = +0 and never qualify
+                unsigned mine = 0u;
 #pragma unroll
                 for (int i = 0; i < KPL; ++i) {
                     const int ghi = __double2hiint(g[i]);
-                    // projected gradient: |g| on the support (h > 0), max(-g, 0) off it
-                    const bool take = (32 * i + lane < k) && (__double2hiint(h[i]) > 0 || ghi < 0);
-                    const unsigned key = ((static_cast<unsigned>(ghi) & 0x7fffff00u) | static_cast<unsigned>(32 * i + lane));
-                    best = max(best, take ? key : 0u);
+                    const bool take = __double2hiint(h[i]) > 0 || ghi < 0;
+                    const unsigned key = (static_cast<unsigned>(ghi) & 0x7fffff00u) | static_cast<unsigned>(32 * i + lane);
+                    mine = max(mine, take ? key : 0u);
                 }
-                best = __reduce_max_sync(0xffffffffu, best);
-                if ((best & 0x7fffff00u) <= stop_key) break;
-                const int t = static_cast<int>(best & 0xffu);
-                bool moved = false;
-                [&]<int... Is>(std::integer_sequence<int, Is...>) {
-                    ((((t >> 5) == Is) ? (void)(moved = greedy_step(std::integral_constant<int, Is>{}, t & 31)) : (void)0), ...);
-                }(std::make_integer_sequence<int, KPL>{});
-                ++nsteps;
-                if (!moved) break;       // a step lost to rounding: leave the rest to the loop below
+                // one key pass serves up to greedy_batch steps: the best candidates of distinct lanes, largest
+                // first.  The later ones were chosen on a gradient that is one or two updates old; the step itself
+                // is always exact on the current gradient (a candidate that no longer moves costs no update).
+                bool any_moved = false, done = false;
+                for (int b = 0; b < greedy_batch && left > 0; ++b) {
+                    const unsigned best = __reduce_max_sync(0xffffffffu, mine);
+                    if ((best & 0x7fffff00u) <= stop_key) { done = (b == 0); break; }
+                    const int t = static_cast<int>(best & 0xffu);
+                    if (lane == (t & 31)) mine = 0u;
+                    bool moved = false;
+                    [&]<int... Is>(std::integer_sequence<int, Is...>) {
+                        ((((t >> 5) == Is) ? (void)(moved = greedy_step(std::integral_constant<int, Is>{}, t & 31)) : (void)0), ...);
+                    }(std::make_integer_sequence<int, KPL>{});
+                    any_moved |= moved;
+                    ++nsteps;
+                    --left;
+                }
+                if (done || !any_moved) break;   // converged on fresh keys / steps lost to rounding: exact check below
             }
             double viol = 0.0;
 #pragma unroll
@@ -406,6 +417,7 @@ int nnls_gram_batched(const double* gram, int64_t k, const float* rhs, int rhs_s
         // greedy coordinate steps before the sweeps + CG loop takes over, in multiples of k (0: no greedy phase)
         static const int greedy_mult = getenv("NFB_NNLS_GREEDY") ? std::max(0, atoi(getenv("NFB_NNLS_GREEDY"))) : kGreedyBudget;
         const int greedy_budget = scale_diag ? greedy_mult * static_cast<int>(k) : 0;   // the keys assume a unit diagonal
+        static const int greedy_batch = getenv("NFB_NNLS_BATCH") ? std::max(1, atoi(getenv("NFB_NNLS_BATCH"))) : kGreedyBatch;
         const int grid = static_cast<int>(std::min<int64_t>(ceil_div64(cols, kNnlsWarps), sm_count()));
 #define NFB_NNLS_FAST(KPL)                                                                                       \
     do {                                                                                                         \
@@ -415,7 +427,7 @@ int nnls_gram_batched(const double* gram, int64_t k, const float* rhs, int rhs_s
         kernel<<<grid, kNnlsWarps * 32, smem_fast, stream>>>(gram, static_cast<int>(k), rhs, rhs_splits,         \
                                                              rhs_stride, ld_rhs, cols, sol, ld_sol, max_outer,   \
                                                              1e-10, status, steps_total, counter, sweeps0, face_red, \
-                                                             scale_diag, greedy_budget);                         \
+                                                             scale_diag, greedy_budget, greedy_batch);           \
     } while (0)
         if (k <= 32) NFB_NNLS_FAST(1);
         else if (k <= 64) NFB_NNLS_FAST(2);
