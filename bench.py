@@ -195,7 +195,7 @@ def cpu_reference_seconds_per_iter(m, n, k, density, solver, budget_rows=(512, 8
                 warnings.simplefilter("ignore")
                 est.fit_transform(x, W=w0.copy(), H=h0.copy())
             times[iters] = time.perf_counter() - t0
-        per_iter.append((times[3] - times[1]) / 2.0)
+        per_iter.append(max((times[3] - times[1]) / 2.0, 1e-9))     # timer noise on a tiny ad-hoc shape
     (m1, m2), (t1, t2) = (min(budget_rows[0], m), min(budget_rows[1], m)), per_iter
     if m2 == m1:
         return t2, per_iter
@@ -204,6 +204,8 @@ def cpu_reference_seconds_per_iter(m, n, k, density, solver, budget_rows=(512, 8
     if a <= 0:   # noise swamped the slope: fall back to the m-independent part only (favours the CPU)
         a, b = 0.0, min(t1, t2)
     full = a * m + b
+    if full <= 0:
+        full = max(t1, t2)
     return full, per_iter
 
 
