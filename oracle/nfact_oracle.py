@@ -22,7 +22,9 @@ so the oracle is pinned against OUTPUTS OF THE REFERENCE ITSELF run in the build
 container: ``tests/golden/make_golden.py`` imports ``/root/reference`` (NFACT's own
 ``load_fdt_matrix``/``avg_fdt``/``nmf_decomp``/``nmf_dual_regression`` on top of the
 installed sklearn/scipy) and commits the vectors under ``tests/golden/``;
-``tests/test_oracle_golden.py`` checks every function below against them.
+``tests/test_oracle_golden.py`` checks every function below against them, and
+``tests/test_oracle_live_cpu.py`` runs the solvers, ``nnls`` and the random init against the
+installed sklearn / scipy themselves on random problems (both boxes have them).
 
 Each function cites the reference (or sklearn/scipy) file:line it follows.
 """
