@@ -1,9 +1,10 @@
 // Multi-threaded parser for probtrackx `fdt_matrix2.dot` text (host code, part of libnfact_b200.so).
 //
 // Replaces the `np.loadtxt` call of NFACT/base/matrix_handling.py:93-113 (single-threaded, minutes per
-// subject).  Every line is `row col value` separated by blanks; numbers are parsed with
-// std::from_chars(double), which is correctly rounded like strtod / Python float(), so the float64 triplets
-// -- and therefore the bit-exact ingest downstream -- are identical to what np.loadtxt returns.
+// subject).  Every line is `row col value` separated by blanks; numbers are converted exactly -- plain decimals on
+// a one-operation fast path, everything else with std::from_chars(double), both correctly rounded like strtod /
+// Python float() --, so the float64 triplets -- and therefore the bit-exact ingest downstream -- are identical to
+// what np.loadtxt returns.
 #include <algorithm>
 #include <charconv>
 #include <cstdint>
@@ -35,21 +36,72 @@ inline const char* skip_comment(const char* p, const char* end) {   // from a '#
 }
 
 // number of lines in [begin, end) that hold data: np.loadtxt drops everything from a '#' to the end of the line
-// (comments='#') and skips lines that are empty afterwards
+// (comments='#') and skips lines that are empty afterwards.  A line holds data when its first non-blank character is
+// neither the end of the line nor a '#'; the line ends are found with memchr.
 int64_t count_lines(const char* begin, const char* end) {
     int64_t lines = 0;
-    bool content = false, comment = false;
-    for (const char* p = begin; p < end; ++p) {
-        if (*p == '\n') {
-            lines += content;
-            content = comment = false;
-        } else if (*p == '#') {
-            comment = true;
-        } else if (!comment && !is_blank(*p)) {
-            content = true;
+    const char* p = begin;
+    while (p < end) {
+        const char* nl = static_cast<const char*>(memchr(p, '\n', static_cast<size_t>(end - p)));
+        const char* stop = nl ? nl : end;
+        const char* q = p;
+        while (q < stop && is_blank(*q)) ++q;
+        lines += (q < stop && *q != '#');
+        p = stop + 1;
+    }
+    return lines;
+}
+
+// Powers of ten that are exact in float64.
+const double kPow10[23] = {1e0,  1e1,  1e2,  1e3,  1e4,  1e5,  1e6,  1e7,  1e8,  1e9,  1e10, 1e11,
+                           1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
+
+// One number at p (no leading blanks).  Plain decimals -- [+-]digits[.digits] with at most 19 significant digits, an
+// integer value of the digit string <= 2^53 and at most 22 fraction digits -- convert with ONE correctly rounded IEEE
+// operation on two exact operands (Clinger's fast path), which is the correctly rounded value strtod / Python float()
+// / np.loadtxt produce; that covers streamline counts and printf's %f / %g output without exponent.  Everything else
+// (exponents, long digit strings, inf / nan, errors) goes to std::from_chars, which is correctly rounded as well.
+inline bool parse_field(const char*& p, const char* end, double& out) {
+    const char* q = p;
+    if (q < end && *q == '+') {
+        if (!plus_sign_ok(q, end)) return false;
+        ++q;
+    }
+    const char* start = q;
+    bool neg = false;
+    if (q < end && *q == '-') { neg = true; ++q; }
+    uint64_t mant = 0;
+    int ndig = 0, frac = 0;
+    bool any = false, fast = true;
+    while (q < end && static_cast<unsigned>(*q - '0') <= 9u) {
+        any = true;
+        if (ndig >= 19) { fast = false; break; }
+        mant = mant * 10u + static_cast<unsigned>(*q - '0');
+        ndig += (mant != 0);
+        ++q;
+    }
+    if (fast && q < end && *q == '.') {
+        ++q;
+        while (q < end && static_cast<unsigned>(*q - '0') <= 9u) {
+            any = true;
+            if (ndig >= 19) { fast = false; break; }
+            mant = mant * 10u + static_cast<unsigned>(*q - '0');
+            ndig += (mant != 0);
+            ++frac;
+            ++q;
         }
     }
-    return lines + (content ? 1 : 0);
+    if (fast && any && !(q < end && (*q == 'e' || *q == 'E')) && mant <= (1ull << 53) && frac <= 22) {
+        double v = static_cast<double>(mant);
+        if (frac) v /= kPow10[frac];
+        out = neg ? -v : v;
+        p = q;
+        return true;
+    }
+    auto res = std::from_chars(start, end, out);
+    if (res.ec != std::errc()) return false;
+    p = res.ptr;
+    return true;
 }
 
 // parse the lines of [begin, end) into out arrays starting at index `first`; returns lines parsed or -1
@@ -62,10 +114,7 @@ int64_t parse_range(const char* begin, const char* end, int64_t first, double* r
         double field[3];
         for (int f = 0; f < 3; ++f) {
             while (p < end && is_blank(*p)) ++p;
-            if (p < end && *p == '+' && plus_sign_ok(p, end)) ++p;
-            auto res = std::from_chars(p, end, field[f]);
-            if (res.ec != std::errc()) return -1;
-            p = res.ptr;
+            if (!parse_field(p, end, field[f])) return -1;
         }
         while (p < end && is_blank(*p)) ++p;
         if (p < end && *p == '#') p = skip_comment(p, end);
@@ -98,10 +147,7 @@ CooStats parse_range_coo(const char* begin, const char* end, int64_t first, int6
         double field[3];
         for (int f = 0; f < 3; ++f) {
             while (p < end && is_blank(*p)) ++p;
-            if (p < end && *p == '+' && plus_sign_ok(p, end)) ++p;
-            auto res = std::from_chars(p, end, field[f]);
-            if (res.ec != std::errc()) { st.parsed = -1; return st; }
-            p = res.ptr;
+            if (!parse_field(p, end, field[f])) { st.parsed = -1; return st; }
         }
         while (p < end && is_blank(*p)) ++p;
         if (p < end && *p == '#') p = skip_comment(p, end);

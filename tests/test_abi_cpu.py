@@ -163,6 +163,37 @@ def test_native_dot_parser_fuzz_against_loadtxt(tmp_path):
         assert got.shape == ref.shape and np.array_equal(got, ref), trial
 
 
+def test_native_dot_parser_fast_path_boundaries(tmp_path):
+    """The one-operation decimal fast path of the host parser and its hand-over to std::from_chars: digit strings
+    around 2^53 and 19 significant digits, up to 25 fraction digits, signs, bare '.', exponents -- every value equal to
+    Python's float() of the same token (np.loadtxt's conversion), bit for bit."""
+    import nfact_b200
+    rng = np.random.default_rng(7)
+    tokens = ["9007199254740992", "9007199254740993", "9007199254740991", "90071992547409925", "1234567890123456789",
+              "12345678901234567890", "0.1", "0.30000000000000004", "5.", ".5", "-0", "-0.0", "+7.25", "007.5000",
+              "0.0000000000000000000001", "0.00000000000000000000001", "123456789.123456789", "1.7976931348623157e308",
+              "4.9e-324", "1e22", "1e23", "8.5e-5", "2.5E+3", "123456789012345.6789", "0.1234567890123456789012",
+              "99999999999999999999", "0.000000000000000000000000000001", "1.5e", "3.25e+"]
+    for _ in range(400):
+        digits = int(rng.integers(1, 22))
+        frac = int(rng.integers(0, 26))
+        body = "".join(str(int(d)) for d in rng.integers(0, 10, digits))
+        tail = "".join(str(int(d)) for d in rng.integers(0, 10, frac))
+        tokens.append(("-" if rng.random() < 0.2 else "") + body + ("." + tail if frac else ""))
+    good = [t for t in tokens if not t.endswith(("e", "e+"))]
+    path = tmp_path / "fdt_matrix2.dot"
+    path.write_text("".join(f"{i + 1} {i + 2} {t}\n" for i, t in enumerate(good)) + "5000 5000 0\n")
+    got = nfact_b200.read_in_matrix(str(path))
+    want = np.array([float(t) for t in good])
+    assert got.shape == (len(good) + 1, 3)
+    assert np.array_equal(got[:-1, 2].view(np.uint64), want.view(np.uint64))        # bit for bit, also -0.0
+    assert np.array_equal(got, np.loadtxt(str(path)))
+    for bad in ("1.5e", "3.25e+", ".", "-", "+", "1..2", "--1"):
+        path.write_text(f"1 2 {bad}\n3 3 0\n")
+        with pytest.raises(ValueError):
+            nfact_b200.read_in_matrix(str(path))
+
+
 def test_fused_coo_parser_matches_the_reference_construction(tmp_path, golden_subjects):
     """nfb_dot_parse_coo == loadtxt + `[:-1] - 1` + integer cast + last-line shape
     (NFACT/base/matrix_handling.py:131-137), with scipy's index errors."""
