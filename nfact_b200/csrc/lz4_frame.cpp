@@ -150,7 +150,11 @@ int64_t block_decode(const uint8_t* p, size_t n, uint8_t* dst, int64_t cap, int6
             } while (b == 255);
         }
         if (lit > static_cast<size_t>(end - p) || lit > static_cast<size_t>(oend - op)) return -1;
-        memcpy(op, p, lit);
+        // short literal runs dominate text: one fixed 16 / 32-byte copy (a single vector move) instead of a memcpy
+        // call of variable length, when both buffers have the slack; the surplus bytes are overwritten by what follows
+        if (lit <= 16 && end - p >= 16 && oend - op >= 16) memcpy(op, p, 16);
+        else if (lit <= 32 && end - p >= 32 && oend - op >= 32) memcpy(op, p, 32);
+        else memcpy(op, p, lit);
         p += lit;
         op += lit;
         if (p == end) break;
@@ -170,7 +174,13 @@ int64_t block_decode(const uint8_t* p, size_t n, uint8_t* dst, int64_t cap, int6
         if (off == 0 || static_cast<int64_t>(off) > (op - dst) + hist) return -1;
         if (ml > static_cast<size_t>(oend - op)) return -1;
         const uint8_t* m = op - off;
-        if (off >= ml) {
+        uint8_t* const match_end = op + ml;
+        if (off >= 16 && oend - match_end >= 16) {
+            // fixed 16-byte steps that may run up to 15 bytes past the match (inside this block's own output, which
+            // the next sequences overwrite); a step never reads what it writes because the distance is >= 16
+            do { memcpy(op, m, 16); op += 16; m += 16; } while (op < match_end);
+            op = match_end;
+        } else if (off >= ml) {
             memcpy(op, m, ml);
             op += ml;
         } else if (off >= 8) {          // overlapping, period >= 8: forward 8-byte copies are safe
