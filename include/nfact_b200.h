@@ -107,6 +107,10 @@ int nfb_dot_parse_coo(const char* buf, int64_t len, int nthreads, int64_t n_line
 int nfb_lz4_frame_size(const void* src, int64_t src_len, int nthreads, int64_t* size_out);
 int nfb_lz4_frame_decompress(const void* src, int64_t src_len, void* dst, int64_t dst_cap, int nthreads,
                              int64_t* written_out);
+/* Diagnostics of the last nfb_lz4_frame_decompress call on the calling thread: how many chunks of linked-block frames
+ * were decoded side by side (beyond the first chunk of each frame), and how many of them had to wait for their
+ * predecessor because the bytes in front of them could not be reconstructed independently. */
+int nfb_lz4_last_chunks(int64_t* parallel_chunks_out, int64_t* deferred_out);
 
 /* ---- resident matrix --------------------------------------------------------------------------
  * X float32 [m, n] -> fp16 hi/lo planes in HBM (4 B/element, read by both X H' and W'X). */

@@ -55,6 +55,7 @@ SIGNATURES = {
                                   POINTER(c_int64)]),
     "nfb_lz4_frame_size": (c_int, [c_void_p, c_int64, c_int, POINTER(c_int64)]),
     "nfb_lz4_frame_decompress": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, POINTER(c_int64)]),
+    "nfb_lz4_last_chunks": (c_int, [POINTER(c_int64), POINTER(c_int64)]),
     "nfb_matrix_from_host": (c_int, [c_void_p, c_void_p, c_int64, c_int64, POINTER(c_void_p)]),
     "nfb_matrix_from_device": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, POINTER(c_void_p)]),
     "nfb_matrix_free": (c_int, [c_void_p]),

@@ -15,10 +15,11 @@
 // Frames with independent blocks (the `lz4` command line default) are decoded by all host threads: one pass
 // measures every block's decoded size (token walk, no copies), a prefix sum places the blocks, a second pass
 // decodes them in place.  Linked blocks (python-lz4's default) may reference the previous 64 KB of output and
-// are decoded in order into the same contiguous buffer.
+// are decoded in order into the same contiguous buffer (optionally in side-by-side chunks, NFB_LZ4_CHUNK_BYTES).
 #include <algorithm>
 #include <atomic>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -195,6 +196,62 @@ int64_t block_decode(const uint8_t* p, size_t n, uint8_t* dst, int64_t cap, int6
     return op - dst;
 }
 
+// The same block format decoded into a scratch stream whose beginning is NOT the beginning of the frame: `pos` bytes
+// of the stream exist, `known` (<= 65536) bytes of real history precede this block in the frame.  A match that reaches
+// before the stream copies unknown bytes; taint[] marks every byte whose value depends on them (copied from a marked
+// byte, directly or through a chain of matches).  Bytes with taint 0 are exactly what a decode from the start of the
+// frame produces.  Plain byte loops: this only runs over the few MB in front of a chunk.
+int64_t block_decode_taint(const uint8_t* p, size_t n, uint8_t* buf, uint8_t* taint, int64_t pos, int64_t cap,
+                           int64_t known) {
+    const uint8_t* const end = p + n;
+    int64_t op = pos;
+    const int64_t oend = pos + cap;
+    if (n == 0) return -1;
+    for (;;) {
+        if (p >= end) return -1;
+        const unsigned token = *p++;
+        size_t lit = token >> 4;
+        if (lit == 15) {
+            unsigned b;
+            do {
+                if (p >= end) return -1;
+                b = *p++;
+                lit += b;
+            } while (b == 255);
+        }
+        if (lit > static_cast<size_t>(end - p) || static_cast<int64_t>(lit) > oend - op) return -1;
+        memcpy(buf + op, p, lit);
+        memset(taint + op, 0, lit);
+        p += lit;
+        op += static_cast<int64_t>(lit);
+        if (p == end) break;
+        if (end - p < 2) return -1;
+        const int64_t off = p[0] | (p[1] << 8);
+        p += 2;
+        size_t ml = token & 15;
+        if (ml == 15) {
+            unsigned b;
+            do {
+                if (p >= end) return -1;
+                b = *p++;
+                ml += b;
+            } while (b == 255);
+        }
+        ml += 4;
+        if (off == 0 || off > (op - pos) + known) return -1;
+        if (static_cast<int64_t>(ml) > oend - op) return -1;
+        for (size_t i = 0; i < ml; ++i, ++op) {
+            const int64_t from = op - off;
+            if (from < 0) { buf[op] = 0; taint[op] = 1; }
+            else { buf[op] = buf[from]; taint[op] = taint[from]; }
+        }
+    }
+    return op - pos;
+}
+
+// diagnostics of the last nfb_lz4_frame_decompress call on this thread (nfb_lz4_last_chunks)
+thread_local int64_t g_last_chunks = 0, g_last_deferred = 0;
+
 struct Parsed {
     std::vector<Frame> frames;
     std::vector<Block> blocks;
@@ -367,31 +424,106 @@ int nfb_lz4_frame_decompress(const void* src, int64_t src_len, void* dst, int64_
         return 2;
     }
     uint8_t* const out = static_cast<uint8_t*>(dst);
-    // work items: every block of an independent-block frame; every linked-block frame as one sequential item
-    struct Item { size_t first, count; bool linked; };
+    // Work items: every block of an independent-block frame; a linked-block frame (python-lz4's default: every block
+    // may reference the previous 64 KB of output) as one sequential item -- or, as an option, as several chunks
+    // of consecutive blocks decoded side by side.  A chunk that does not start the frame first decodes the few MB in
+    // front of it into a scratch stream with unknown history and exact taint tracking (block_decode_taint): once its
+    // own first 64 KB come out untainted they are the true bytes, are copied into place, and the rest of the chunk
+    // is decoded in place at full speed.  A chunk whose start stays tainted (long copy chains) is decoded after its
+    // predecessor, from the real history.
+    struct Item { size_t first, count; bool linked; int64_t frame_start; bool chunk_head; };
     std::vector<Item> items;
+    const int threads_avail = pick_threads(nthreads, static_cast<size_t>(1) << 30);
+    // Off unless NFB_LZ4_CHUNK_BYTES is set: on probtrackx text (rows sorted, the same prefixes copied forward from
+    // match to match) the taint of a chunk's start never clears -- measured: every chunk of a 40 MB .dot frame had to
+    // wait for its predecessor, and the warm-up is then pure overhead.  It pays on data whose copy chains are short.
+    const int64_t chunk_min = getenv("NFB_LZ4_CHUNK_BYTES") ? std::max<int64_t>(1 << 17, atoll(getenv("NFB_LZ4_CHUNK_BYTES")))
+                                                            : INT64_MAX;
+    const int64_t warm_bytes = getenv("NFB_LZ4_WARM_BYTES") ? std::max<int64_t>(1 << 16, atoll(getenv("NFB_LZ4_WARM_BYTES")))
+                                                                  : (static_cast<int64_t>(4) << 20);
     for (const Frame& fr : c.frames) {
         if (fr.independent) {
-            for (size_t i = 0; i < fr.n_blocks; ++i) items.push_back({fr.first_block + i, 1, false});
+            for (size_t i = 0; i < fr.n_blocks; ++i)
+                items.push_back({fr.first_block + i, 1, false, c.blocks[fr.first_block + i].dst_off, true});
         } else if (fr.n_blocks) {
-            items.push_back({fr.first_block, fr.n_blocks, true});
+            const Block& first = c.blocks[fr.first_block];
+            const Block& last = c.blocks[fr.first_block + fr.n_blocks - 1];
+            const int64_t bytes = last.dst_off + last.dsize - first.dst_off;
+            const int64_t n_chunks = std::max<int64_t>(1, std::min<int64_t>(threads_avail, bytes / chunk_min));
+            const int64_t per_chunk = (bytes + n_chunks - 1) / n_chunks;
+            size_t begin = fr.first_block;
+            for (int64_t ch = 0; ch < n_chunks && begin < fr.first_block + fr.n_blocks; ++ch) {
+                size_t stop = begin;
+                const int64_t limit = first.dst_off + (ch + 1) * per_chunk;
+                while (stop < fr.first_block + fr.n_blocks && (c.blocks[stop].dst_off < limit || ch == n_chunks - 1)) ++stop;
+                if (stop == begin) ++stop;
+                items.push_back({begin, stop - begin, true, first.dst_off, begin == fr.first_block});
+                begin = stop;
+            }
         }
     }
     std::atomic<bool> ok{true};
-    parallel_for(items.size(), nthreads, [&](size_t w) {
-        const Item& it = items[w];
-        const int64_t frame_start = c.blocks[it.first].dst_off;
-        for (size_t i = it.first; i < it.first + it.count; ++i) {
+    std::vector<char> deferred(items.size(), 0);
+    g_last_chunks = 0;
+    for (const Item& it : items) g_last_chunks += (it.linked && !it.chunk_head);
+    g_last_deferred = 0;
+    // in-place decode of blocks [from, to) of a linked frame whose history is already in the output buffer
+    auto decode_in_place = [&](size_t from, size_t to, int64_t frame_start, bool linked) {
+        for (size_t i = from; i < to; ++i) {
             const Block& b = c.blocks[i];
             uint8_t* d = out + b.dst_off;
             if (b.stored) {
                 memcpy(d, b.src, b.csize);
                 continue;
             }
-            const int64_t hist = it.linked ? std::min<int64_t>(b.dst_off - frame_start, 65536) : 0;
+            const int64_t hist = linked ? std::min<int64_t>(b.dst_off - frame_start, 65536) : 0;
             if (block_decode(b.src, b.csize, d, b.dsize, hist) != b.dsize) ok = false;
         }
+    };
+    parallel_for(items.size(), nthreads, [&](size_t w) {
+        const Item& it = items[w];
+        if (!it.linked || it.chunk_head) {
+            decode_in_place(it.first, it.first + it.count, it.frame_start, it.linked);
+            return;
+        }
+        // warm-up: walk back until ~warm_bytes of output (or the start of the frame) lie in front of the chunk
+        const size_t frame_first = [&] { size_t i = it.first; while (c.blocks[i].dst_off > it.frame_start) --i; return i; }();
+        size_t warm = it.first;
+        while (warm > frame_first && c.blocks[it.first].dst_off - c.blocks[warm].dst_off < warm_bytes) --warm;
+        // own blocks decoded into the scratch stream as well, until 64 KB of own output exist
+        size_t own_end = it.first;
+        int64_t own_bytes = 0;
+        while (own_end < it.first + it.count && own_bytes < 65536) own_bytes += c.blocks[own_end++].dsize;
+        const int64_t stream_start = c.blocks[warm].dst_off;
+        const int64_t stream_len = c.blocks[own_end - 1].dst_off + c.blocks[own_end - 1].dsize - stream_start;
+        std::vector<uint8_t> buf(static_cast<size_t>(stream_len)), taint(static_cast<size_t>(stream_len));
+        bool bad = false;
+        for (size_t i = warm; i < own_end && !bad; ++i) {
+            const Block& b = c.blocks[i];
+            const int64_t pos = b.dst_off - stream_start;
+            if (b.stored) {
+                memcpy(buf.data() + pos, b.src, b.csize);
+                memset(taint.data() + pos, 0, b.csize);
+                continue;
+            }
+            // real history in front of this block; what lies before the stream is unknown unless the stream starts the frame
+            const int64_t known = std::min<int64_t>(b.dst_off - it.frame_start, 65536);
+            // (a stream that begins at the frame start has known <= pos: nothing can reach in front of it)
+            if (block_decode_taint(b.src, b.csize, buf.data(), taint.data(), pos, b.dsize, known) != b.dsize) bad = true;
+        }
+        if (bad) { ok = false; return; }
+        const int64_t own_pos = c.blocks[it.first].dst_off - stream_start;
+        const bool clean = memchr(taint.data() + own_pos, 1, static_cast<size_t>(stream_len - own_pos)) == nullptr;
+        if (!clean) { deferred[w] = 1; return; }
+        memcpy(out + c.blocks[it.first].dst_off, buf.data() + own_pos, static_cast<size_t>(stream_len - own_pos));
+        decode_in_place(own_end, it.first + it.count, it.frame_start, true);
     });
+    // chunks whose first bytes stayed tainted: in order, each after everything in front of it is final
+    for (size_t w = 0; w < items.size(); ++w)
+        if (deferred[w]) {
+            ++g_last_deferred;
+            decode_in_place(items[w].first, items[w].first + items[w].count, items[w].frame_start, true);
+        }
     if (!ok) { fail("ERROR_decompressionFailed (match offset outside the window)"); return 2; }
     // content checksums: one frame per thread (XXH32 is sequential within a frame)
     std::atomic<bool> sums_ok{true};
@@ -408,6 +540,12 @@ int nfb_lz4_frame_decompress(const void* src, int64_t src_len, void* dst, int64_
     });
     if (!sums_ok) { fail("ERROR_contentChecksum_invalid"); return 2; }
     *written_out = total;
+    return 0;
+}
+
+int nfb_lz4_last_chunks(int64_t* parallel_chunks_out, int64_t* deferred_out) {
+    if (parallel_chunks_out) *parallel_chunks_out = g_last_chunks;
+    if (deferred_out) *deferred_out = g_last_deferred;
     return 0;
 }
 

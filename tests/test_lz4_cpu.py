@@ -141,3 +141,72 @@ def test_compressed_subject_parses_like_the_text(tmp_path, golden_subjects):
     with pytest.raises(RuntimeError, match="frameType"):
         nfact_b200.read_in_matrix(lz4_path)
     assert os.path.exists(os.path.join(GOLDEN_DIR, "data", "sub-1", "fdt_matrix2.dot"))
+
+
+def _decode_with(frame: bytes, nthreads: int):
+    import ctypes
+    from nfact_b200._lib import load
+    lib = load()
+    src = np.frombuffer(frame, dtype=np.uint8)
+    size, written = ctypes.c_int64(), ctypes.c_int64()
+    assert lib.nfb_lz4_frame_size(ctypes.c_void_p(src.ctypes.data), src.size, nthreads, ctypes.byref(size)) == 0
+    out = np.empty(max(size.value, 1), dtype=np.uint8)
+    rc = lib.nfb_lz4_frame_decompress(ctypes.c_void_p(src.ctypes.data), src.size, ctypes.c_void_p(out.ctypes.data),
+                                      size.value, nthreads, ctypes.byref(written))
+    assert rc == 0 and written.value == size.value
+    chunks, deferred = ctypes.c_int64(), ctypes.c_int64()
+    lib.nfb_lz4_last_chunks(ctypes.byref(chunks), ctypes.byref(deferred))
+    return out[:size.value].tobytes(), chunks.value, deferred.value
+
+
+def test_linked_frames_are_decoded_in_parallel_chunks(monkeypatch):
+    """python-lz4's default frames (linked 64 KB blocks) are split into chunks decoded side by side: a chunk
+    reconstructs the bytes in front of it in a scratch stream with exact taint tracking and starts on its own once its
+    first 64 KB are untainted; chunks that stay tainted (copy chains back to the start of the frame) wait for their
+    predecessor.  Either way the output equals the sequential decode and the format oracle."""
+    from oracle import lz4_frame as z
+    rng = np.random.default_rng(11)
+    n = 120_000
+    text = ("\n".join(f"{a} {b} {v}" for a, b, v in zip(np.sort(rng.integers(1, 60000, n)).tolist(),
+                                                          rng.integers(1, 110000, n).tolist(),
+                                                          rng.integers(1, 5000, n).tolist())) + "\n").encode()
+    periodic = b"abcdefgh" * 150_000 + text[:300_000]          # every match chains back: the taint never clears
+    mixed = text[:500_000] + bytes(rng.integers(0, 256, 200_000, dtype=np.uint8)) + text[500_000:]   # stored blocks inside
+    monkeypatch.setenv("NFB_LZ4_CHUNK_BYTES", str(1 << 17))
+    saw_clean = saw_deferred = False
+    for warm in (1 << 16, 1 << 18, 1 << 20):
+        monkeypatch.setenv("NFB_LZ4_WARM_BYTES", str(warm))
+        for name, payload in (("text", text), ("periodic", periodic), ("mixed", mixed)):
+            for opts in (dict(independent=False, content_checksum=False),
+                         dict(independent=False, content_checksum=True, block_checksum=True, block_size_id=5)):
+                frame = z.compress(payload, **opts)
+                sequential, chunks1, _ = _decode_with(frame, 1)
+                assert sequential == payload and chunks1 == 0
+                for nthreads in (2, 5, 8):
+                    got, chunks, deferred = _decode_with(frame, nthreads)
+                    assert got == payload, (name, warm, nthreads)
+                    assert chunks >= 1 and 0 <= deferred <= chunks
+                    saw_clean |= deferred < chunks
+                    saw_deferred |= deferred > 0
+                # two frames back to back, the second one chunked as well
+                got, chunks, _ = _decode_with(frame + frame, 4)
+                assert got == payload + payload and chunks >= 2
+    assert saw_clean and saw_deferred
+
+
+def test_damaged_linked_frames_fail_cleanly_in_chunked_mode(monkeypatch):
+    from oracle import lz4_frame as z
+    monkeypatch.setenv("NFB_LZ4_CHUNK_BYTES", str(1 << 17))
+    monkeypatch.setenv("NFB_LZ4_WARM_BYTES", str(1 << 17))
+    payload = _payloads()["dot_text"] * 6
+    frame = bytearray(z.compress(payload, independent=False, content_checksum=False))
+    rng = np.random.default_rng(2)
+    for _ in range(150):
+        bad = bytearray(frame)
+        for pos in rng.integers(7, len(bad), 3):
+            bad[pos] = int(rng.integers(0, 256))
+        try:
+            out = _native(bytes(bad))
+            assert len(out) <= 2 * len(payload) + (1 << 22)
+        except RuntimeError:
+            pass

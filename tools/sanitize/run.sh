@@ -10,5 +10,7 @@ g++ $flags "$here/lz4_harness.cpp" "$root/nfact_b200/csrc/lz4_frame.cpp" -o "$wo
 g++ $flags "$here/dot_harness.cpp" "$root/nfact_b200/csrc/dot_parser.cpp" -o "$work/dot_harness" -lpthread
 PYTHONPATH="$root" python "$here/make_corpus.py" "$work"
 ASAN_OPTIONS=detect_leaks=0 "$work/lz4_harness" "$work"/lz4/*
+# the same files with linked frames split into side-by-side chunks (scratch streams + taint tracking)
+NFB_LZ4_CHUNK_BYTES=131072 NFB_LZ4_WARM_BYTES=65536 ASAN_OPTIONS=detect_leaks=0 "$work/lz4_harness" "$work"/lz4/*
 ASAN_OPTIONS=detect_leaks=0 "$work/dot_harness" "$work"/dot/*
 rm -rf "$work"
