@@ -407,17 +407,18 @@ int nnls_gram_batched(const double* gram, int64_t k, const float* rhs, int rhs_s
     const size_t smem_fast = (static_cast<size_t>(k) * (k + 1) / 2 + 3 * k) * sizeof(double);
     if (smem_fast <= 220 * 1024 && k <= 224 && counter != nullptr) {
         NFB_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream));
-        // 16 warps per SM (128 registers, a few spilled values at k > 192) measured faster than 12 spill-free ones
-        static const int warps_env = getenv("NFB_NNLS_WARPS") ? atoi(getenv("NFB_NNLS_WARPS")) : 0;
+        // 16 warps per SM (128 registers, a few spilled values at k > 192) measured faster than 12 spill-free ones.
+        // The knobs are read on every call so that one process can compare settings (tests/gpu_nnls_probe.py).
+        const int warps_env = getenv("NFB_NNLS_WARPS") ? atoi(getenv("NFB_NNLS_WARPS")) : 0;
         const bool wide = warps_env ? warps_env >= 16 : true;
         const int kNnlsWarps = wide ? 16 : 12;
-        static const int sweeps0 = getenv("NFB_NNLS_SWEEPS") ? std::max(1, atoi(getenv("NFB_NNLS_SWEEPS"))) : kInitialSweeps;
-        static const double face_red = getenv("NFB_NNLS_FACE") ? atof(getenv("NFB_NNLS_FACE")) : kFaceReduction;
-        static const int scale_diag = getenv("NFB_NNLS_SCALE") ? atoi(getenv("NFB_NNLS_SCALE")) : 1;
+        const int sweeps0 = getenv("NFB_NNLS_SWEEPS") ? std::max(1, atoi(getenv("NFB_NNLS_SWEEPS"))) : kInitialSweeps;
+        const double face_red = getenv("NFB_NNLS_FACE") ? atof(getenv("NFB_NNLS_FACE")) : kFaceReduction;
+        const int scale_diag = getenv("NFB_NNLS_SCALE") ? atoi(getenv("NFB_NNLS_SCALE")) : 1;
         // greedy coordinate steps before the sweeps + CG loop takes over, in multiples of k (0: no greedy phase)
-        static const int greedy_mult = getenv("NFB_NNLS_GREEDY") ? std::max(0, atoi(getenv("NFB_NNLS_GREEDY"))) : kGreedyBudget;
+        const int greedy_mult = getenv("NFB_NNLS_GREEDY") ? std::max(0, atoi(getenv("NFB_NNLS_GREEDY"))) : kGreedyBudget;
         const int greedy_budget = scale_diag ? greedy_mult * static_cast<int>(k) : 0;   // the keys assume a unit diagonal
-        static const int greedy_batch = getenv("NFB_NNLS_BATCH") ? std::max(1, atoi(getenv("NFB_NNLS_BATCH"))) : kGreedyBatch;
+        const int greedy_batch = getenv("NFB_NNLS_BATCH") ? std::max(1, atoi(getenv("NFB_NNLS_BATCH"))) : kGreedyBatch;
         const int grid = static_cast<int>(std::min<int64_t>(ceil_div64(cols, kNnlsWarps), sm_count()));
 #define NFB_NNLS_FAST(KPL)                                                                                       \
     do {                                                                                                         \
