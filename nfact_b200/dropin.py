@@ -109,8 +109,10 @@ def run_locally(args: dict, paths: dict) -> None:
             error_and_exit(False, f"Unable to save images due to {e}")
         nprint(f"{col['pink']}Completed{col['reset']}: {sub_id}", to_flush=True)
 
+    # NFB_READ_AHEAD=N: N host threads read / decompress the next subjects' files ahead of the GPU (run_locally)
     nfact_b200.run_locally(list(args["ptxdir"]), components, args["seeds"], threshold=int(args["threshold"]),
-                           normalise=bool(args["normalise"]), save=save)
+                           normalise=bool(args["normalise"]), save=save,
+                           read_ahead=int(os.environ.get("NFB_READ_AHEAD", "0")))
     return None
 
 

@@ -190,20 +190,42 @@ def stream_subjects(load_matrix, n_subjects: int, components: dict, device: int 
 
 
 def run_locally(list_of_subject_dirs: list, components: dict, seeds: list, threshold: int = 3,
-                normalise: bool = False, rank: int = 0, world: int = 1, save=None, prefetch: bool = True) -> dict:
+                normalise: bool = False, rank: int = 0, world: int = 1, save=None, prefetch: bool = True,
+                read_ahead: int = 0) -> dict:
     """Subject loop of NFACT/dual_reg/dual_regression/set_up_dual_regression.py:186-235.  Subjects are
     independent: with ``world`` processes (one per GPU) rank r takes subjects r, r+world, ... and no
     collective is needed.  ``save(subject_dir, dr_results)`` receives each result (the reference's image
     writer); without ``save`` the results of this rank are returned keyed by subject directory (with it the
     dictionary only records which subjects were done).  The next subject's
-    matrix is parsed and ingested while the current one is being regressed (``stream_subjects``)."""
+    matrix is parsed and ingested while the current one is being regressed (``stream_subjects``).
+
+    ``read_ahead`` > 0: that many host threads read -- and, for ``.dot.lz4``, decompress -- the files of the next
+    subjects while the current ones are ingested and regressed.  An LZ4 frame with linked blocks (what python-lz4
+    writes) decodes on one core, ~4 s for a 5 GB matrix, far longer than the 0.2 s the GPU needs per subject;
+    different subjects' files are independent, so N readers give N times the decode throughput.  Every pending file
+    holds its decompressed text in host memory (~5 GB at C3).  Off by default."""
     import os
-    from .matrix_handling import load_fdt_matrix
+    from .matrix_handling import _read_bytes, load_fdt_matrix
     mine = [d for idx, d in enumerate(list_of_subject_dirs) if idx % world == rank]
+    readers, pending = None, {}
+    if read_ahead > 0 and os.environ.get("NFB_DOT_ON_DEVICE", "1") != "0":
+        from concurrent.futures import ThreadPoolExecutor
+        readers = ThreadPoolExecutor(max_workers=int(read_ahead))
+
+    def schedule_reads(upto):
+        # files [0, upto) have been asked for: keep `read_ahead` of the following ones in flight
+        for nxt in range(upto, min(upto + int(read_ahead), len(mine))):
+            if nxt not in pending:
+                pending[nxt] = readers.submit(_read_bytes, _subject_matrix_file(mine[nxt]))
 
     def load(idx, handle):
         try:
-            return load_fdt_matrix(_subject_matrix_file(mine[idx]), resident=True, handle=handle)
+            raw = None
+            if readers is not None:
+                schedule_reads(idx)
+                raw = pending.pop(idx).result()
+                schedule_reads(idx + 1)
+            return load_fdt_matrix(_subject_matrix_file(mine[idx]), resident=True, handle=handle, raw=raw)
         except Exception:
             error_and_exit(False, f"Unable to load {os.path.basename(os.path.normpath(mine[idx]))} fdt matrix")
 
@@ -222,4 +244,7 @@ def run_locally(list_of_subject_dirs: list, components: dict, seeds: list, thres
         raise
     except Exception as e:
         error_and_exit(False, f"Unable to perform dual regression due to {e}")
+    finally:
+        if readers is not None:
+            readers.shutdown(wait=False, cancel_futures=True)
     return out

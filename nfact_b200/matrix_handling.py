@@ -126,7 +126,7 @@ def _cuda_ready() -> bool:
         return False
 
 
-def load_fdt_matrix(matfile: str, resident: bool = False, handle=None):
+def load_fdt_matrix(matfile: str, resident: bool = False, handle=None, raw=None):
     """NFACT/base/matrix_handling.py:143-158: dense float32 [m, n].
 
     ``resident=True`` keeps the matrix in HBM and returns a ``DeviceMatrix`` (what ``nmf_decomp`` /
@@ -134,7 +134,8 @@ def load_fdt_matrix(matfile: str, resident: bool = False, handle=None):
     then parsed on the device too (``nfb_ingest_dot_matrix``), the host parser only takes over for files with
     numbers outside the device parser's exact fast path or with duplicate coordinates."""
     if resident and os.environ.get("NFB_DOT_ON_DEVICE", "1") != "0":
-        raw = _read_bytes(matfile)
+        if raw is None:           # ``raw``: the file's (decompressed) bytes when a reader thread already has them
+            raw = _read_bytes(matfile)
         if len(raw) == 0:
             raise ValueError(f"{matfile}: file is empty")
         waytotal = float(np.loadtxt(os.path.join(os.path.dirname(matfile), "waytotal")))

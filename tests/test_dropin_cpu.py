@@ -171,7 +171,7 @@ def test_nfact_dr_subject_loop_is_rebound_and_keeps_the_reference_calls(referenc
         calls["saved"].append(bound.arguments)
 
     def fake_loop(list_of_subject_dirs, components, seeds, threshold=3, normalise=False, rank=0, world=1, save=None,
-                  prefetch=True):
+                  prefetch=True, read_ahead=0):
         calls["loop"].append((list(list_of_subject_dirs), seeds, threshold, normalise))
         for d in list_of_subject_dirs:
             save(d, {"grey_components": np.zeros((4, 2)), "white_components": np.zeros((2, 5)),

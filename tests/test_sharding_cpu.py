@@ -121,3 +121,61 @@ def test_dual_regression_subjects_are_partitioned_over_ranks(monkeypatch, tmp_pa
         assert sorted(done) == subjects
     kept = drmod.run_locally(subjects, {"grey_components": np.zeros((2, 1))}, ["l.gii"], rank=1, world=4)
     assert list(kept) == subjects[1::4] and all(v is not None for v in kept.values())
+
+
+def test_read_ahead_reads_every_subject_once_and_hands_the_bytes_on(monkeypatch, tmp_path):
+    """run_locally(read_ahead=N): N host threads read / decompress the next subjects' files while the current one is
+    loaded; every file is read exactly once, in time, and its bytes reach load_fdt_matrix(raw=...).  Host logic only:
+    the reader, the loader and the subject stream are recorders."""
+    import threading
+    import time
+    import nfact_b200.dual_regression as drmod
+    import nfact_b200.matrix_handling as mh
+    subjects = []
+    for i in range(7):
+        d = tmp_path / f"sub-{i:02d}"
+        d.mkdir()
+        (d / ("fdt_matrix2.dot.lz4" if i % 2 else "fdt_matrix2.dot")).write_bytes(b"x")
+        subjects.append(str(d))
+    reads, loads, lock = [], [], threading.Lock()
+    in_flight = {"now": 0, "max": 0}
+
+    def fake_read(path):
+        with lock:
+            in_flight["now"] += 1
+            in_flight["max"] = max(in_flight["max"], in_flight["now"])
+        time.sleep(0.02)
+        with lock:
+            in_flight["now"] -= 1
+            reads.append(path)
+        return ("bytes of " + path).encode()
+
+    def fake_load(matfile, resident=False, handle=None, raw=None):
+        loads.append((matfile, raw))
+        return object()
+
+    def fake_stream(load_matrix, n_subjects, components, device=0, prefetch=True, options=None):
+        for idx in range(n_subjects):
+            load_matrix(idx, None)
+            yield idx, {"grey_components": np.zeros((2, 1)), "white_components": np.zeros((1, 3))}
+
+    monkeypatch.setattr(mh, "_read_bytes", fake_read)
+    monkeypatch.setattr(mh, "load_fdt_matrix", fake_load)
+    monkeypatch.setattr(drmod, "stream_subjects", fake_stream)
+    monkeypatch.setattr(drmod, "_postprocess_options", lambda *a, **k: {})
+    comps = {"grey_components": np.zeros((2, 1))}
+    for ahead in (1, 3):
+        reads.clear(), loads.clear()
+        in_flight.update(now=0, max=0)
+        out = drmod.run_locally(subjects, comps, ["l.gii"], read_ahead=ahead)
+        files = [drmod._subject_matrix_file(d) for d in subjects]
+        assert list(out) == subjects and sorted(reads) == sorted(files)           # each file once
+        assert [m for m, _ in loads] == files                                     # loaded in order
+        assert all(raw == ("bytes of " + m).encode() for m, raw in loads)         # the reader's bytes
+        assert 1 <= in_flight["max"] <= ahead
+    reads.clear(), loads.clear()
+    drmod.run_locally(subjects[:3], comps, ["l.gii"])                            # default: no reader threads
+    assert reads == [] and all(raw is None for _, raw in loads)
+    reads.clear(), loads.clear()
+    drmod.run_locally(subjects, comps, ["l.gii"], rank=1, world=3, read_ahead=2)  # with subject sharding
+    assert [m for m, _ in loads] == [drmod._subject_matrix_file(d) for d in subjects[1::3]]
