@@ -36,12 +36,38 @@ WORKLOADS = {
     "C3": (59412, 110000, 200, 0.05),
     "C5": (59412, 230000, 500, 0.05),   # 54.7 GB of planes; run with --no-e2e (the host copy would need as much RAM)
 }
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of gemm_split_kernel from the ncu --set full captures
-# of this same command (profiles/r01_ncu_full_gemm_split_C3.csv: X H' 26.63+0.28 GB with 6 split slabs;
-# profiles/r01_ncu_full_final_C3.csv and profiles/r01b_ncu_full.csv: W'X 26.55+0.08 GB unsplit) -> mean of the two
-# launches of an iteration
-NCU_TRAFFIC_PER_LAUNCH = {"C3": 26.77e9}
-NCU_TENSOR_PIPE_ACTIVE = {"C3": 0.85}    # sm__pipe_tensor_cycles_active of the W'X launch (r01b capture: 84.9 %)
+def ncu_capture(workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch and tensor-pipe activity of the X-streaming
+    gemm_split_kernel launches, read at run time from the newest `profiles/*ncu_full_<workload>.csv` (written by
+    profiles/extract_full.py from an `ncu --set full` capture of this same command) -- not typed in.  None when no
+    capture of this workload is tracked."""
+    import csv
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", f"*ncu_full_{workload}.csv")))
+    if not files:
+        return None
+    path = files[-1]
+    try:
+        with open(path) as fh:
+            rows = [r for r in csv.reader(l for l in fh if not l.startswith("#"))]
+        head = rows[0]
+        col = {name: head.index(name) for name in ("Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum",
+                                                   "dram__bytes_write.sum",
+                                                   "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active")}
+        units = rows[1]
+        scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+        big = [r for r in rows[2:] if "gemm_split_kernel" in r[col["Kernel Name"]]
+               and float(r[col["gpu__time_duration.sum"]]) > 0.25 * max(
+                   float(q[col["gpu__time_duration.sum"]]) for q in rows[2:] if "gemm_split_kernel" in q[col["Kernel Name"]])]
+        traffic = [float(r[col["dram__bytes_read.sum"]]) * scale[units[col["dram__bytes_read.sum"]]] +
+                   float(r[col["dram__bytes_write.sum"]]) * scale[units[col["dram__bytes_write.sum"]]] for r in big]
+        pipe = [float(r[col["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]]) / 100.0 for r in big]
+        return {"traffic": float(np.mean(traffic)), "tensor_pipe_active": float(np.mean(pipe)),
+                "source": os.path.relpath(path, ROOT), "launches": len(big)}
+    except Exception as exc:        # a malformed summary must not cost the bench line
+        return {"traffic": None, "tensor_pipe_active": None, "source": f"{os.path.relpath(path, ROOT)}: {exc}"}
+
+
 METRIC = "nmf_iterations_per_second"
 UNIT = "iter/s"
 ALPHA_W, L1_RATIO = 0.1, 1.0   # NFACT defaults (matrix_decomposition.py:100-107)
@@ -59,6 +85,8 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-dr", action="store_true", help="skip the dual-regression subject after the e2e solve")
+    ap.add_argument("--no-side", action="store_true", help="skip the side figures (C3 other solver, C2 CD)")
+    ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the multi-GPU parity block")
     ap.add_argument("--e2e-iters", type=int, default=0,
                     help="iterations of the e2e call (default: NFACT's max_iter=200)")
     return ap.parse_args()
@@ -84,31 +112,42 @@ def regularization(m_total, n, k):
 # synthetic connectivity matrix: planted Gamma factors, Bernoulli mask, integer
 # "streamline counts" scaled by 1e8 / waytotal.  Generated on the device, one row block at a time.
 # ------------------------------------------------------------------------------------------------
+GEN_BLOCK = 2048     # rows per generator block: blocks are indexed by GLOBAL seed row, so every rank count sees one X
+
+
 def synth_rows_device(torch, dev, row0, rows, n, k, density, seed=0):
+    """Rows [row0, row0 + rows) of the synthetic matrix.  The generator is seeded per block of GEN_BLOCK global
+    seed rows (a rank regenerates the blocks its range touches and keeps its rows), so the matrix -- and with it
+    `config.final_error` -- does not depend on how many GPUs the rows are spread over."""
     gen = torch.Generator(device=dev)
     gen.manual_seed(seed * 1000003 + 17)
     h_star = torch._standard_gamma(torch.full((k, n), 0.3, device=dev), generator=gen)
     out = torch.empty((rows, n), dtype=torch.float32, device=dev)
-    blk = 2048
-    for r in range(0, rows, blk):
-        nr = min(blk, rows - r)
-        gen.manual_seed(seed * 1000003 + 1000 + row0 + r)
-        w_star = torch._standard_gamma(torch.full((nr, k), 0.3, device=dev), generator=gen)
+    for b in range(row0 // GEN_BLOCK, (row0 + rows + GEN_BLOCK - 1) // GEN_BLOCK):
+        gen.manual_seed(seed * 1000003 + 1000 + b)
+        w_star = torch._standard_gamma(torch.full((GEN_BLOCK, k), 0.3, device=dev), generator=gen)
         dense = torch.floor(300.0 * (w_star @ h_star))
-        mask = torch.rand((nr, n), device=dev, generator=gen) < density
+        mask = torch.rand((GEN_BLOCK, n), device=dev, generator=gen) < density
         counts = (dense * mask).to(torch.float64) * (1e8 / 1.5e7)
-        out[r:r + nr] = counts.to(torch.float32)
+        lo, hi = max(row0, b * GEN_BLOCK), min(row0 + rows, (b + 1) * GEN_BLOCK)
+        out[lo - row0:hi - row0] = counts[lo - b * GEN_BLOCK:hi - b * GEN_BLOCK].to(torch.float32)
+        del w_star, dense, mask, counts
     return out
 
 
 def random_init(torch, dev, x_mean, rows, n, k, row0, seed=1):
-    """sklearn's init='random' formula (avg * |N(0,1)|) with a device RNG."""
+    """sklearn's init='random' formula (avg * |N(0,1)|) with a device RNG; W0 is drawn per block of GEN_BLOCK
+    global seed rows like the matrix, so every rank count starts from the same (W0, H0)."""
     gen = torch.Generator(device=dev)
     avg = float(np.sqrt(x_mean / k))
     gen.manual_seed(seed)
     h0 = (avg * torch.randn((k, n), device=dev, generator=gen)).abs_().float()
-    gen.manual_seed(seed + 7919 + row0)
-    w0 = (avg * torch.randn((rows, k), device=dev, generator=gen)).abs_().float()
+    w0 = torch.empty((rows, k), dtype=torch.float32, device=dev)
+    for b in range(row0 // GEN_BLOCK, (row0 + rows + GEN_BLOCK - 1) // GEN_BLOCK):
+        gen.manual_seed(seed + 7919 + b)
+        blk = (avg * torch.randn((GEN_BLOCK, k), device=dev, generator=gen)).abs_().float()
+        lo, hi = max(row0, b * GEN_BLOCK), min(row0 + rows, (b + 1) * GEN_BLOCK)
+        w0[lo - row0:hi - row0] = blk[lo - b * GEN_BLOCK:hi - b * GEN_BLOCK]
     return w0.contiguous(), h0.contiguous()
 
 
@@ -165,63 +204,149 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# reference CPU path: sklearn.decomposition.NMF called exactly as NFACT does
-# (NFACT/decomp/decomposition/sso/nmfsso.py:54-56 with get_parameters defaults), on a bounded row sample.
+# reference CPU path.  NFACT is pure Python and delegates the solve to sklearn (un-vendored);
+# /root/reference does not exist on the GPU box, so the call below restates NFACT's own call site
+# (NFACT/decomp/decomposition/sso/nmfsso.py:32-59) on top of the installed sklearn, with the hyper-parameters
+# NFACT's get_parameters(None, "nmf", k) produces (matrix_decomposition.py:100-107).
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_seconds_per_iter(m, n, k, density, solver, budget_rows=(512, 8192)):
-    """Fit t(m_s) = a*m_s + b from two row samples (per-iteration slope between max_iter=1 and 3) and
-    extrapolate to the full m: the H half-step costs do not shrink with the row sample."""
+def reference_nmf_decomp(parameters, fdt_matrix, W=None, H=None):
     import warnings
     from sklearn.decomposition import NMF
+    if W is not None and H is not None:
+        parameters = dict(parameters, init="custom")
+    decomp = NMF(**parameters)
+    with warnings.catch_warnings():          # the reference suppresses the ConvergenceWarning too (nmfsso.py:31)
+        warnings.simplefilter("ignore")
+        grey = decomp.fit_transform(fdt_matrix, W=W, H=H)
+    return {"grey_components": grey, "white_components": decomp.components_}
+
+
+def reference_parameters(k, solver, max_iter):
+    """NFACT's defaults (alpha_W = 0.1, l1_ratio = 1, init = nndsvd -> custom once W, H are passed), tol = 0 so a fit
+    runs exactly max_iter iterations."""
+    import nfact_b200.nmf as nfnmf           # get_parameters is host-only Python (no device code involved)
+    return dict(nfnmf.get_parameters(None, "nmf", k), solver=solver, tol=0.0, max_iter=int(max_iter))
+
+
+def host_available_bytes():
+    try:
+        with open("/proc/meminfo") as fh:
+            for line in fh:
+                if line.startswith("MemAvailable:"):
+                    return int(line.split()[1]) * 1024
+    except OSError:
+        pass
+    return 0
+
+
+def synth_host(m, n, k, density, rows=None):
+    """The bench's synthetic matrix (all m rows, or the first `rows`) as a host float32 array, with sklearn-style
+    random (W0, H0).  With a GPU present it is the SAME matrix the GPU arm solves (generated on the device in row
+    blocks and copied back); without one (CPU tests of tiny shapes) numpy generates one of the same recipe."""
+    rows = m if rows is None else min(rows, m)
+    try:
+        import torch
+        cuda = torch.cuda.is_available()
+    except Exception:
+        cuda = False
+    if cuda:
+        dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+        x = np.empty((rows, n), dtype=np.float32)
+        total = 0.0
+        step = 4 * GEN_BLOCK
+        for r0 in range(0, rows, step):
+            nr = min(step, rows - r0)
+            blk = synth_rows_device(torch, dev, r0, nr, n, k, density)
+            total += float(blk.sum(dtype=torch.float64))
+            x[r0:r0 + nr] = blk.cpu().numpy()
+            del blk
+        x_mean = total / (rows * n)
+        w0, h0 = random_init(torch, dev, x_mean, rows, n, k, 0)
+        w0, h0 = w0.cpu().numpy(), h0.cpu().numpy()
+        torch.cuda.empty_cache()
+        return x, w0, h0
     rng = np.random.default_rng(0)
     h_star = rng.gamma(0.3, 1.0, (k, n)).astype(np.float32)
-    per_iter = []
-    for ms in budget_rows:
-        ms = min(ms, m)
-        w_star = rng.gamma(0.3, 1.0, (ms, k)).astype(np.float32)
-        x = np.floor(300.0 * (w_star @ h_star))
-        x *= rng.random((ms, n), dtype=np.float32) < density
-        x *= np.float32(1e8 / 1.5e7)
-        avg = np.sqrt(x.mean() / k)
-        w0 = np.abs(avg * rng.standard_normal((ms, k))).astype(np.float32)
-        h0 = np.abs(avg * rng.standard_normal((k, n))).astype(np.float32)
-        times = {}
-        for iters in (1, 3):
-            est = NMF(n_components=k, init="custom", solver=solver, beta_loss="frobenius", tol=0.0, max_iter=iters,
-                      random_state=None, alpha_W=ALPHA_W, alpha_H=ALPHA_W * m / ms,
-                      l1_ratio=L1_RATIO, verbose=0, shuffle=False)
-            t0 = time.perf_counter()
-            with warnings.catch_warnings():
-                warnings.simplefilter("ignore")
-                est.fit_transform(x, W=w0.copy(), H=h0.copy())
-            times[iters] = time.perf_counter() - t0
-        per_iter.append(max((times[3] - times[1]) / 2.0, 1e-9))     # timer noise on a tiny ad-hoc shape
-    (m1, m2), (t1, t2) = (min(budget_rows[0], m), min(budget_rows[1], m)), per_iter
-    if m2 == m1:
-        return t2, per_iter
-    a = (t2 - t1) / (m2 - m1)
-    b = t1 - a * m1
-    if a <= 0:   # noise swamped the slope: fall back to the m-independent part only (favours the CPU)
-        a, b = 0.0, min(t1, t2)
-    full = a * m + b
-    if full <= 0:
-        full = max(t1, t2)
-    return full, per_iter
+    w_star = rng.gamma(0.3, 1.0, (rows, k)).astype(np.float32)
+    x = np.floor(300.0 * (w_star @ h_star))
+    x *= rng.random((rows, n), dtype=np.float32) < density
+    x *= np.float32(1e8 / 1.5e7)
+    avg = np.sqrt(x.mean() / k)
+    w0 = np.abs(avg * rng.standard_normal((rows, k))).astype(np.float32)
+    h0 = np.abs(avg * rng.standard_normal((k, n))).astype(np.float32)
+    return x, w0, h0
 
 
-def cpu_baseline(m, n, k, density, solver):
+def _timed_fit(x, w0, h0, k, solver, iters, alpha_h_scale=1.0):
+    params = reference_parameters(k, solver, iters)
+    if alpha_h_scale != 1.0:     # row sample: keep l1_reg_H = m_full * alpha at the full matrix's value
+        params["alpha_H"] = params["alpha_W"] * alpha_h_scale
+    t0 = time.perf_counter()
+    reference_nmf_decomp(params, x, W=w0.copy(), H=h0.copy())
+    return time.perf_counter() - t0
+
+
+def cpu_reference(m, n, k, density, solver, warm_iters, timed_iters, budget_s, x_host=None, w0=None, h0=None):
+    """Seconds per iteration of the reference solve on this box's host cores, at the FULL shape when the host has
+    the memory for it (sklearn's final reconstruction error materialises X - WH: 3 x the matrix): one fit with
+    max_iter = warm_iters and one with max_iter = warm_iters + timed_iters, tol = 0; the difference is exactly
+    timed_iters iterations (initial checks, the final error pass and the warm iterations cancel).  timed_iters is
+    cut so the two fits stay inside `budget_s`.  Short of memory: row samples of 3 sizes and a least-squares line
+    in m, flagged in `fit`."""
+    x_bytes = 4.0 * m * n
+    need = (3.3 if x_host is None else 2.3) * x_bytes + (2 << 30)
+    info = {"warm_iters": int(warm_iters)}
+    if host_available_bytes() >= need or x_bytes < (1 << 30):
+        if x_host is None:
+            x_host, w0, h0 = synth_host(m, n, k, density)
+        rs = min(m, 256)          # library start-up (imports, BLAS thread pool) stays out of the first timed fit
+        _timed_fit(np.ascontiguousarray(x_host[:rs]), w0[:rs], h0, k, solver, 1)
+        t_a = _timed_fit(x_host, w0, h0, k, solver, warm_iters)
+        est = t_a / max(warm_iters, 1)                  # upper estimate of one iteration (includes the fixed costs)
+        timed = int(max(2, min(timed_iters, (budget_s - t_a) / max(est, 1e-9) - warm_iters)))
+        t_b = _timed_fit(x_host, w0, h0, k, solver, warm_iters + timed)
+        per_iter = (t_b - t_a) / timed
+        info.update(sample="full", timed_iters=timed, fit_seconds=[t_a, t_b], fit="slope of two full-size fits")
+        if per_iter <= 0:
+            per_iter, info["fit"] = t_b / (warm_iters + timed), "degenerate (timer noise): whole-fit average"
+        return per_iter, info
+    sizes = [s for s in (2048, 8192, 16384) if s < m] or [m]
+    per = []
+    for ms in sizes:
+        xs, w0s, h0s = synth_host(m, n, k, density, rows=ms)
+        t1 = _timed_fit(xs, w0s, h0s, k, solver, 1, alpha_h_scale=m / ms)
+        t3 = _timed_fit(xs, w0s, h0s, k, solver, 3, alpha_h_scale=m / ms)
+        per.append((t3 - t1) / 2.0)
+        del xs
+    info.update(sample=f"row samples of {sizes} seeds (host memory {host_available_bytes() / 2**30:.0f} GiB < "
+                       f"{need / 2**30:.0f} GiB needed for the full matrix)", timed_iters=2, fit_seconds=per)
+    if len(sizes) >= 2:
+        a, b = np.polyfit(np.asarray(sizes, dtype=np.float64), np.asarray(per, dtype=np.float64), 1)
+        full = a * m + b
+        if a > 0 and full > 0:
+            info["fit"] = "least-squares line in m over the row samples, extrapolated"
+            return float(full), info
+    info["fit"] = "degenerate"
+    return float(max(per) * m / sizes[int(np.argmax(per))]), info
+
+
+def cpu_baseline(m, n, k, density, solver, warm_iters=1, timed_iters=2, budget_s=120.0, x_host=None, w0=None, h0=None):
     import threadpoolctl
     # torchrun exports OMP_NUM_THREADS=1 to every rank; the reference gets all the host cores it can use
     with threadpoolctl.threadpool_limits(limits=os.cpu_count()):
-        full, samples = cpu_reference_seconds_per_iter(m, n, k, density, solver)
-        info = threadpoolctl.threadpool_info()
-    threads = max([i.get("num_threads", 1) for i in info] or [1])
+        per_iter, info = cpu_reference(m, n, k, density, solver, warm_iters, timed_iters, budget_s, x_host, w0, h0)
+        pools = threadpoolctl.threadpool_info()
+    threads = max([i.get("num_threads", 1) for i in pools] or [1])
+    secs = ", ".join(f"{t:.2f}s" for t in info["fit_seconds"])
     return {
-        "value": 1.0 / full, "unit": UNIT, "cores": int(threads), "kind": "reference",
-        "sample": (f"sklearn {__import__('sklearn').__version__} NMF(init=custom, solver={solver}, NFACT default "
-                   f"alpha_W/l1_ratio) as called by NFACT nmfsso.py:54-56, on row samples of 512 and 8192 seeds x "
-                   f"{n} targets, k={k}; seconds/iter from the max_iter 1->3 slope ({samples[0]:.3f}s, "
-                   f"{samples[1]:.3f}s), linear fit in m extrapolated to m={m}; host cpu_count={os.cpu_count()}"),
+        "value": 1.0 / per_iter, "unit": UNIT, "cores": int(threads), "kind": "reference",
+        "seconds_per_iter": per_iter, "timed_iters": info["timed_iters"], "warm_iters": info["warm_iters"],
+        "fit": info["fit"],
+        "sample": (f"{info['sample']}: sklearn {__import__('sklearn').__version__} NMF called as NFACT does "
+                   f"(nmfsso.py:54-56 with get_parameters(None,'nmf',{k}) defaults alpha_W=0.1 l1_ratio=1, "
+                   f"solver={solver}, init=custom, tol=0) on {m}x{n}; fits of max_iter={info['warm_iters']} and "
+                   f"{info['warm_iters'] + info['timed_iters']} took {secs}; seconds/iter = their difference / "
+                   f"{info['timed_iters']}; host cpu_count={os.cpu_count()}"),
     }
 
 
@@ -305,6 +430,140 @@ def dual_regression_across_gpus(torch, dist, dev, handle, m, n, k, density, rank
                    "(subjects are independent: no collective); seconds = slowest rank, best of 3"}
 
 
+def multi_gpu_parity(torch, dist, dev, handle, rank, world):
+    """N > 1, outside the timed region: the row-sharded solver against the CPU oracle (the checker) on a
+    2 003 x 3 001, k = 24 problem -- 4 CD and 4 MU iterations through the default peer-memory exchange (p2p.cu) and
+    again with NFB_P2P=0 (NCCL reduce-scatter / all-gather); then NFACT's DEFAULT call,
+    nmf_decomp(get_parameters(None, 'nmf', k) | {random_state: 0}, X_rows) with its NNDSVD initialisation computed
+    across the ranks, against the same call on one GPU (CD gate: objective within 0.5 %, Hungarian-matched
+    component correlation >= 0.99).  Every figure is the maximum over ranks."""
+    import nfact_b200
+    from nfact_b200.device import DeviceMatrix, Handle, NmfState, make_params
+    from nfact_b200.sharding import row_range
+    from oracle import nfact_oracle as orc      # test infrastructure, used here as the checker only
+    m, n, k = 2003, 3001, 24
+    rng = np.random.default_rng(3)
+    x = (np.floor(300 * (rng.gamma(0.3, 1.0, (m, k)) @ rng.gamma(0.3, 1.0, (k, n)))) * (rng.random((m, n)) < 0.3)
+         * (1e8 / 1.5e7)).astype(np.float32)
+    w0, h0 = orc.init_random(x, k, 1)
+    regs = orc.compute_regularization(m, n, 0.1, "same", 1.0)
+    r0, r1 = row_range(m, rank, world)
+    ref = {}
+    for solver, fit in (("cd", orc.fit_cd), ("mu", orc.fit_mu)):
+        rec = []
+        fit(x, w0, h0, *regs, tol=0, max_iter=4, record=rec)
+        ref[solver] = rec[-1]
+    out = {"shape": [m, n, k], "iterations": 4}
+    saved = os.environ.get("NFB_P2P")
+    xdev = DeviceMatrix.from_host(x[r0:r1], handle)
+    for path in ("p2p", "nccl"):
+        if path == "nccl":
+            os.environ["NFB_P2P"] = "0"
+        elif saved is None:
+            os.environ.pop("NFB_P2P", None)
+        worst_w = worst_h = 0.0
+        for solver in ("cd", "mu"):
+            st = NmfState(xdev, k, make_params(solver, 200, 0.0, regs))
+            out[f"{path}_mode"] = st.exchange_mode
+            st.set_factors(w0[r0:r1], h0)
+            st.iterate(4)
+            w, h = st.get_factors()
+            st.free()
+            wr, hr = ref[solver][1], ref[solver][2]
+            worst_w = max(worst_w, float(np.linalg.norm(w - wr[r0:r1]) / max(np.linalg.norm(wr[r0:r1]), 1e-30)))
+            worst_h = max(worst_h, float(np.linalg.norm(h - hr) / np.linalg.norm(hr)))
+        t = torch.tensor([worst_w, worst_h], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out[f"{path}_relW"], out[f"{path}_relH"] = float(t[0]), float(t[1])
+    if saved is None:
+        os.environ.pop("NFB_P2P", None)
+    else:
+        os.environ["NFB_P2P"] = saved
+    # NFACT's default flow (init = nndsvd, CD, alpha_W = 0.1, l1_ratio = 1, tol = 1e-4, max_iter = 200), sharded vs one GPU
+    params = dict(nfact_b200.get_parameters(None, "nmf", k), random_state=0)
+    res = nfact_b200.nmf_decomp(dict(params), xdev)
+    xdev.free()
+    w_parts = [None] * world
+    dist.all_gather_object(w_parts, res["grey_components"])
+    if rank == 0:
+        single = Handle(handle.device)                       # no communicator: a plain one-GPU solve
+        x1 = DeviceMatrix.from_host(x, single)
+        one = nfact_b200.nmf_decomp(dict(params), x1)
+        x1.free()
+        w_all = np.concatenate(w_parts)
+        obj = orc.nmf_objective(x, w_all, res["white_components"], *regs)
+        obj1 = orc.nmf_objective(x, one["grey_components"], one["white_components"], *regs)
+        from scipy.optimize import linear_sum_assignment
+
+        def min_matched_corr(a, b):
+            a = a - a.mean(axis=1, keepdims=True)
+            b = b - b.mean(axis=1, keepdims=True)
+            an, bn = np.linalg.norm(a, axis=1, keepdims=True), np.linalg.norm(b, axis=1, keepdims=True)
+            live = (an[:, 0] > 0) & (bn[:, 0] > 0)
+            c = (a / np.where(an > 0, an, 1)) @ (b / np.where(bn > 0, bn, 1)).T
+            rr, cc = linear_sum_assignment(-c)
+            return float(c[rr, cc][live].min())
+        out["default_flow"] = {
+            "objective_rel_diff": float(abs(obj - obj1) / obj1),
+            "min_corr_H": min_matched_corr(res["white_components"], one["white_components"]),
+            "min_corr_W": min_matched_corr(w_all.T, one["grey_components"].T),
+            "api": "nmf_decomp(get_parameters(None,'nmf',k) | {random_state: 0}, X_rows) on N ranks vs on one GPU"}
+        d = out["default_flow"]
+        d["ok"] = bool(d["objective_rel_diff"] <= 5e-3 and d["min_corr_H"] >= 0.99 and d["min_corr_W"] >= 0.99)
+        out["ok"] = bool(max(out["p2p_relW"], out["p2p_relH"], out["nccl_relW"], out["nccl_relH"]) < 1e-4 and d["ok"])
+    dist.barrier()
+    return out
+
+
+def _time_iterations(torch, stream, handle, state, warm, steps):
+    state.iterate(warm)
+    handle.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    state.iterate(steps)
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    return ev0.elapsed_time(ev1) / steps / 1000.0
+
+
+def side_figures(torch, dev, stream, handle, xmat, w0, h0, k, main_solver):
+    """Driver-visible side figures (seconds per iteration, device-timed like `value`, 3 warm-up + 8 timed
+    iterations): the OTHER solver on the resident C3 matrix and the coordinate-descent solve of C2 (BASELINE
+    configs[1]: 29 696 x 60 000, k = 100)."""
+    from nfact_b200.device import DeviceMatrix, NmfState, make_params
+    out = {}
+    try:
+        other = "mu" if main_solver == "cd" else "cd"
+        m, n = xmat.shape
+        st = NmfState(xmat, k, make_params(other, 10 ** 6, 0.0, regularization(m, n, k)))
+        st.set_factors_dev(w0.data_ptr(), h0.data_ptr())
+        sec = _time_iterations(torch, stream, handle, st, 3, 8)
+        st.free()
+        out[f"C3_{other}"] = {"seconds_per_iter": sec, "iter_per_s": 1.0 / sec,
+                              "roofline_step_frac": (8.0 * m * n / (measured_peaks()[0] * 1e9)) / sec}
+        m2, n2, k2, d2 = WORKLOADS["C2"]
+        x2 = synth_rows_device(torch, dev, 0, m2, n2, k2, d2)
+        mean2 = float(x2.sum(dtype=torch.float64)) / (m2 * n2)
+        stream.synchronize()
+        xm2 = DeviceMatrix.from_device_ptr(x2.data_ptr(), m2, n2, n2, handle=handle)
+        del x2
+        torch.cuda.empty_cache()
+        w2, h2 = random_init(torch, dev, mean2, m2, n2, k2, 0)
+        st = NmfState(xm2, k2, make_params("cd", 10 ** 6, 0.0, regularization(m2, n2, k2)))
+        stream.synchronize()
+        st.set_factors_dev(w2.data_ptr(), h2.data_ptr())
+        sec = _time_iterations(torch, stream, handle, st, 3, 8)
+        st.free()
+        xm2.free()
+        out["C2_cd"] = {"seconds_per_iter": sec, "iter_per_s": 1.0 / sec,
+                        "roofline_step_frac": (8.0 * m2 * n2 / (measured_peaks()[0] * 1e9)) / sec}
+        del w2, h2
+        torch.cuda.empty_cache()
+    except Exception as exc:              # a side figure must not cost the bench line
+        out["error"] = f"{type(exc).__name__}: {exc}"
+    return out
+
+
 def ingest_benchmark(handle):
     """Group-average ingest (a2-a5) of 3 synthetic C1-shaped subjects (5000 x 10000, 15 % nnz, integer counts
     with duplicates): host COO triplets -> dense float32 on the host, through nfb_ingest_coo; beside it the
@@ -364,15 +623,21 @@ def ingest_benchmark(handle):
 
 # ------------------------------------------------------------------------------------------------
 def run_reference(args):
+    """`--impl reference`: the reference's own CPU implementation of the path (sklearn's NMF called the way NFACT
+    calls it) on this box's host cores, same workload, metric and unit as the GPU arm.  Rank 0 alone runs it."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     m, n, k, density = WORKLOADS[args.workload]
     t_start = time.perf_counter()
-    base = cpu_baseline(m, n, k, density, args.solver)
+    warm = max(1, args.warmup)
+    base = cpu_baseline(m, n, k, density, args.solver, warm_iters=warm, timed_iters=max(2, args.steps),
+                        budget_s=float(os.environ.get("NFB_REFERENCE_BUDGET_S", "240")))
     line = {
         "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / base["value"],
+        # steps / warmup: the iterations actually timed (the difference of the two fits) and warmed
+        "steps": base["timed_iters"], "warmup": base["warm_iters"], "steps_requested": args.steps,
+        "ms_per_step": 1000.0 / base["value"],
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {m}x{n} k={k} solver={args.solver} "
                                f"(NFACT defaults alpha_W=0.1 l1_ratio=1), reference CPU path on the host cores"},
@@ -458,12 +723,15 @@ def run_ours(args):
             elapsed_ms = float(t)
         final_err = state.error()
         state.free()
+        side = None
+        if world == 1 and not args.no_side and args.workload == "C3":
+            side = side_figures(torch, dev, stream, handle, xmat, w0, h0, k, args.solver)
 
         # ---- e2e through the reference-facing call with host buffers ------------------------------
         # Every rank holds its seed rows of X (and of W0) in pinned host memory and calls
         # nmf_decomp(parameters, X_rows, W=W0_rows, H=H0): H2D of X, plane split, `iters` iterations
         # (NCCL inside when row-sharded), D2H of W rows and H -- all inside the timed region.
-        e2e = dr_info = None
+        e2e = dr_info = w0_host = h0_host = None
         if want_e2e:
             xmat.free()
             torch.cuda.empty_cache()
@@ -559,6 +827,15 @@ def run_ours(args):
     if world > 1 and want_e2e and not args.no_dr:
         dr_info = dual_regression_across_gpus(torch, dist, dev, handle, m, n, k, density, rank, world)
 
+    parity = None
+    if world > 1 and not args.no_parity:
+        import nfact_b200.device as nfdev
+        nfdev.set_default_handle(handle)
+        try:
+            parity = multi_gpu_parity(torch, dist, dev, handle, rank, world)
+        except BaseException as exc:          # nmf_decomp turns errors into SystemExit like the reference
+            parity = {"ok": False, "error": f"{type(exc).__name__}: {exc}"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -580,6 +857,7 @@ def run_ours(args):
         bound, unit, peak = "tensor", "TFLOP/s", tc_peak
         achieved = flops_per_launch / (gemm_avg_ms * 1e-3) / 1e12 if gemm_launches else 0.0
     t_step_roof = 2.0 * max(t_hbm, t_tc)
+    ncu = ncu_capture(args.workload)
     line = {
         "metric": METRIC, "value": 1000.0 / ms_per_step, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
@@ -592,14 +870,19 @@ def run_ours(args):
         "clocks": clocks,
         "roofline": {"bound": bound, "kernel": "gemm_split_kernel (X H' and W'X)", "achieved": achieved,
                      "peak": peak, "unit": unit, "frac": achieved / peak,
-                     "traffic": NCU_TRAFFIC_PER_LAUNCH.get(args.workload) if world == 1 else None,
-                     "tensor_pipe_active_ncu": NCU_TENSOR_PIPE_ACTIVE.get(args.workload),
+                     "traffic": (ncu or {}).get("traffic") if world == 1 else None,
+                     "tensor_pipe_active_ncu": (ncu or {}).get("tensor_pipe_active"),
+                     "traffic_source": (ncu or {}).get("source"),
                      "peak_source": peak_src, "avg_launch_ms": gemm_avg_ms, "launches": int(gemm_launches),
                      "algorithmic_bytes_per_launch": bytes_per_launch,
                      "algorithmic_flops_per_launch": flops_per_launch,
                      "mma_flops_per_launch": 3.0 * 2.0 * rows * n * (16 * ((k + 15) // 16)),
                      "step_frac": t_step_roof / (ms_per_step * 1e-3)},
     }
+    if parity is not None:
+        line["parity_check"] = parity
+    if side:
+        line["side"] = side
     if e2e is not None:
         line["e2e"] = e2e
     if dr_info is not None:
@@ -610,7 +893,12 @@ def run_ours(args):
         except Exception as exc:                  # side figures must not cost the bench line
             line["ingest"] = {"error": f"{type(exc).__name__}: {exc}"}
     if not args.no_cpu and world == 1:
-        line["cpu_baseline"] = cpu_baseline(m, n, k, density, args.solver)
+        # bounded sample of the same workload: the full matrix (the pinned host copy the e2e call used), exactly
+        # 2 iterations as the difference of a max_iter=1 and a max_iter=3 fit
+        have = x_host is not None
+        line["cpu_baseline"] = cpu_baseline(m, n, k, density, args.solver, 1, 2, 120.0,
+                                            x_host.numpy() if have else None, w0_host if have else None,
+                                            h0_host if have else None)
     print(json.dumps(line), file=RESULT_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -167,6 +167,9 @@ int nfb_nmf_iterate(nfb_nmf* s, int n_iters, double* violation_out);
 int nfb_nmf_run(nfb_nmf* s, int* n_iter_out, double* recon_err_out);
 /* ||X - WH||_F for the current factors (one extra X H' pass). */
 int nfb_nmf_error(nfb_nmf* s, double* err_out);
+/* How the row-sharded H half-step of this solver exchanges data: *out = 0 single GPU (no exchange),
+ * 1 NCCL reduce-scatter / all-gather, 2 NVLink peer-memory kernels (p2p.cu). */
+int nfb_nmf_exchange_mode(const nfb_nmf* s, int* out);
 /* number of kernels the last iterate/run call launched (for the benchmark's gpu_launches) */
 int64_t nfb_launch_count(const nfb_handle* h);
 /* Per-kernel timing of the two X-streaming GEMMs (X H' and W'X) with CUDA events on the launch stream.

@@ -75,6 +75,7 @@ SIGNATURES = {
     "nfb_nmf_iterate": (c_int, [c_void_p, c_int, POINTER(c_double)]),
     "nfb_nmf_run": (c_int, [c_void_p, POINTER(c_int), POINTER(c_double)]),
     "nfb_nmf_error": (c_int, [c_void_p, POINTER(c_double)]),
+    "nfb_nmf_exchange_mode": (c_int, [c_void_p, POINTER(c_int)]),
     "nfb_launch_count": (c_int64, [c_void_p]),
     "nfb_profile_gemms": (c_int, [c_void_p, c_int, POINTER(c_double), POINTER(c_int64)]),
     "nfb_dual_regression_host": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p,

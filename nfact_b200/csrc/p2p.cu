@@ -46,12 +46,20 @@ __device__ __forceinline__ float ld_peer(const float* p) {
 }
 
 // spin until flags[p] >= epoch for all p < world (threads 0..world-1 of the CTA); ~30 s timeout (ranks may
-// legitimately drift by the time one of them spends in a host-side step between two collective phases)
-__device__ __forceinline__ void wait_all(const int* flags, int world, int epoch, int* error) {
+// legitimately drift by the time one of them spends in a host-side step between two collective phases).
+// A wait that times out raises the error flag in EVERY rank's arena, and a raised flag ends every later wait at
+// once: a dead or out-of-step peer costs one timeout, not one per remaining phase.
+__device__ __forceinline__ void wait_all(const P2pPeers& peers, int world, int rank, int flag_offset, int epoch) {
+    int* my = reinterpret_cast<int*>(peers.arena[rank]);
     if (threadIdx.x < world) {
+        const int* flag = my + flag_offset + threadIdx.x;
         const long long t0 = clock64();
-        while (ld_acquire_sys(flags + threadIdx.x) < epoch) {
-            if (clock64() - t0 > 60000000000LL) { *error = 1; break; }
+        while (ld_acquire_sys(flag) < epoch) {
+            if (ld_acquire_sys(my + kP2pError) != 0) break;
+            if (clock64() - t0 > 60000000000LL) {
+                for (int p = 0; p < world; ++p) st_release_sys(reinterpret_cast<int*>(peers.arena[p]) + kP2pError, 1);
+                break;
+            }
             __nanosleep(64);
         }
     }
@@ -69,8 +77,7 @@ __global__ void __launch_bounds__(256)
 p2p_pull_kernel(P2pPeers peers, int world, int rank, int epoch, int k, int64_t ns, int64_t ld, int64_t c0,
                 int64_t num_offset, int64_t gram_offset, int gram_elems, float* __restrict__ out,
                 float* __restrict__ gram_out) {
-    int* my = reinterpret_cast<int*>(peers.arena[rank]);
-    wait_all(my + kP2pRsFlag, world, epoch, my + kP2pError);
+    wait_all(peers, world, rank, kP2pRsFlag, epoch);
     const int64_t w4 = ns / 4;                                        // ns % 8 == 0
     const int64_t valid4 = max(static_cast<int64_t>(0), min(ns, ld - c0)) / 4;   // ld % 8 == 0, c0 % 8 == 0
     const int64_t vecs = static_cast<int64_t>(k) * w4;
@@ -133,13 +140,15 @@ p2p_push_kernel(P2pPeers peers, int world, int rank, int k, int64_t ld, int64_t 
 // wait for every peer's slice, then scal_out[i] = sum_p scal[p][i] in rank order
 __global__ void p2p_gather_wait_kernel(P2pPeers peers, int world, int rank, int epoch, int64_t scal_offset,
                                        double* __restrict__ scal_out) {
-    int* my = reinterpret_cast<int*>(peers.arena[rank]);
-    wait_all(my + kP2pAgFlag, world, epoch, my + kP2pError);
+    wait_all(peers, world, rank, kP2pAgFlag, epoch);
     if (threadIdx.x < 2 && scal_out != nullptr) {
         const volatile double* scal =
             reinterpret_cast<const volatile double*>(reinterpret_cast<char*>(peers.arena[rank]) + scal_offset);
         double acc = 0.0;
         for (int p = 0; p < world; ++p) acc += scal[2 * p + threadIdx.x];
+        // a failed exchange poisons the scalars the host reads every iteration (the CD violation), so the
+        // stopping-rule check sees it at once instead of after the whole loop
+        if (ld_acquire_sys(reinterpret_cast<int*>(peers.arena[rank]) + kP2pError) != 0) acc = __longlong_as_double(0x7ff8000000000000LL);
         scal_out[threadIdx.x] = acc;
     }
 }

@@ -200,6 +200,10 @@ struct nfb_nmf {
     int64_t slice_cols = 0;       // ns: H columns per rank (multiple of 8)
     // NVLink peer-memory path (p2p.cu): arena + H master of every rank mapped through CUDA IPC
     bool p2p = false;
+    // H columns are sliced over the ranks (p2p or NCCL reduce-scatter / all-gather) rather than replicated.
+    // Decided once from rank-independent state: every rank must issue the same collectives even when its own
+    // slice is empty or happens to cover all of H (n <= slice_cols).
+    bool h_sliced = false;
     DevBuf<char> arena;
     P2pPeers peers{};
     std::vector<void*> ipc_opened;
@@ -381,7 +385,7 @@ static int gemm_wtx(nfb_nmf* s, HNumerator* out) {
 // after a sliced H update: every rank contributes its columns, everyone ends up with the full H
 static int gather_h_slices(nfb_nmf* s, const HNumerator& hn) {
     nfb_handle* h = s->h;
-    if (h->world <= 1 || hn.width == s->x->n) return 0;
+    if (!s->h_sliced) return 0;
     const int64_t ns = s->slice_cols, n = s->x->n;
     if (s->p2p) {
         // CD: the two violation partial sums travel with the slice and come back summed over ranks
@@ -427,7 +431,7 @@ static int gemm_den(nfb_nmf* s, Factor& fac, Factor& gram, int64_t col0, int64_t
 // refresh planes + Gram of H after its update (slices gathered first in sharded runs)
 static int finish_h(nfb_nmf* s, const HNumerator& hn) {
     nfb_handle* h = s->h;
-    const bool sliced = hn.width != s->x->n;
+    const bool sliced = s->h_sliced;
     NFB_TRY(gather_h_slices(s, hn));
     NFB_TRY(refresh_planes(s->hh, s->hh.f.p, nullptr, sliced, h->stream));
     NFB_TRY(compute_gram(s, s->hh, s->gh, s->s_gh, false));
@@ -500,7 +504,7 @@ static int cd_iteration(nfb_nmf* s, double* violation_out, double* host_slot = n
     }
     { NFB_PHASE(h, "finish_h"); NFB_TRY(finish_h(s, hn)); }
     // W rows are sharded; H columns are sharded too when the update was sliced, replicated otherwise
-    const bool h_sliced = hn.width != s->x->n;
+    const bool h_sliced = s->h_sliced;
     if (host_slot != nullptr || violation_out != nullptr) {
         if (!s->p2p) NFB_TRY(allreduce_f64(h, h->d_scal.p + 2, h_sliced ? 2 : 1));   // p2p: summed with the gather
         double* dst = host_slot != nullptr ? host_slot : h->h_scal + 2;
@@ -922,6 +926,7 @@ int nfb_nmf_create(nfb_handle* h, const nfb_matrix* x, int k, const nfb_nmf_para
         NFB_TRY(s->pack.alloc(static_cast<size_t>(k) * s->slice_cols, true, st));
     }
     if (h->world > 1) NFB_TRY(p2p_setup(s.get()));
+    s->h_sliced = h->world > 1 && (s->p2p || (h->reduce_scatter != nullptr && h->all_gather != nullptr));
     // ||X||^2 over all row shards
     h->h_scal[5] = x->sumsq;
     if (h->world > 1) {
@@ -1028,6 +1033,12 @@ int nfb_nmf_error(nfb_nmf* s, double* err_out) {
     return nmf_error(s, err_out);
 }
 
+int nfb_nmf_exchange_mode(const nfb_nmf* s, int* out) {
+    NFB_CHECK(s != nullptr && out != nullptr, "NULL argument");
+    *out = s->h->world <= 1 ? 0 : (s->p2p ? 2 : 1);
+    return 0;
+}
+
 int nfb_nmf_run(nfb_nmf* s, int* n_iter_out, double* recon_err_out) {
     NFB_CHECK(s != nullptr, "NULL argument");
     NFB_CUDA(cudaSetDevice(s->h->device));
@@ -1044,6 +1055,7 @@ int nfb_nmf_run(nfb_nmf* s, int* n_iter_out, double* recon_err_out) {
             NFB_TRY(gemm_xht(s));
             if (p.tol > 0 && n_iter % 10 == 0) {
                 double error = 0.0;
+                NFB_TRY(p2p_check(s));
                 NFB_TRY(nmf_error(s, &error));
                 if (p.verbose) printf("Epoch %02d, error: %f\n", n_iter, error);
                 if ((previous_error - error) / error_at_init < p.tol) break;
@@ -1074,6 +1086,7 @@ int nfb_nmf_run(nfb_nmf* s, int* n_iter_out, double* recon_err_out) {
             const int b = it & 1;
             NFB_CUDA(cudaEventSynchronize(s->viol_ready[b]));
             const double violation = h->h_scal[8 + 2 * b] + h->h_scal[9 + 2 * b];
+            if (s->p2p && violation != violation) NFB_TRY(p2p_check(s));   // the exchange poisons it on a time-out
             s->last_violation = violation;
             if (it == 1) violation_init = violation;
             if (violation_init == 0) { stop_at = it; return 0; }

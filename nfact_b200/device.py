@@ -26,7 +26,7 @@ class Handle:
         self.device = int(device)
         self._ptr = c_void_p()
         check(self.lib.nfb_create(self.device, c_void_p(stream) if stream else None, byref(self._ptr)))
-        self.rank, self.world = 0, 1
+        self.rank, self.world, self.group = 0, 1, None
 
     @property
     def ptr(self) -> c_void_p:
@@ -243,6 +243,13 @@ class NmfState:
         n_iter, err = c_int(), c_double()
         check(self.handle.lib.nfb_nmf_run(self._ptr, byref(n_iter), byref(err)))
         return n_iter.value, err.value
+
+    @property
+    def exchange_mode(self) -> str:
+        """'single', 'nccl' or 'p2p': how the H half-step of a row-sharded solve exchanges data."""
+        out = c_int()
+        check(self.handle.lib.nfb_nmf_exchange_mode(self._ptr, byref(out)))
+        return ("single", "nccl", "p2p")[out.value]
 
     def error(self) -> float:
         err = c_double()

@@ -50,16 +50,22 @@ def compute_regularization(n_samples: int, n_features: int, alpha_W, alpha_H, l1
             n_features * alpha_W * (1.0 - l1_ratio), n_samples * alpha_H * (1.0 - l1_ratio))
 
 
+def handle_comm(handle):
+    """Collectives of the handle's row-sharded world (``nndsvd.Comm`` over torch.distributed, which is also what
+    brought up the library's NCCL communicator); the identity when the handle is not sharded."""
+    from .nndsvd import Comm
+    if getattr(handle, "world", 1) <= 1:
+        return Comm()
+    return Comm(handle.rank, handle.world, getattr(handle, "group", None))
+
+
 def global_rows(handle, m_local: int) -> int:
     """Seed rows of the whole matrix when X is row-sharded over the handle's NCCL world (one process per
     GPU, torch.distributed as the rendezvous); the local count otherwise."""
     if getattr(handle, "world", 1) <= 1:
         return int(m_local)
     import torch
-    import torch.distributed as dist
-    total = torch.tensor([int(m_local)], dtype=torch.int64, device=torch.device("cuda", handle.device))
-    dist.all_reduce(total)
-    return int(total.item())
+    return handle_comm(handle).row_layout(m_local, torch.device("cuda", handle.device))[1]
 
 
 def _check_params(p: dict) -> dict:
@@ -87,33 +93,70 @@ def _random_state(seed):
     raise ValueError(f"{seed!r} cannot be used to seed a numpy.random.RandomState instance")
 
 
-def initialize_nmf(xdev: DeviceMatrix, x_mean: float, k: int, init, random_state):
+def _shared_random_state(seed, comm):
+    """RandomState every rank agrees on: a row-sharded initialisation draws ONE stream and slices it by global
+    seed row, so ``random_state=None`` (NFACT's default) needs a seed picked by rank 0."""
+    if comm.world > 1 and not isinstance(seed, (int, np.integer)):
+        import torch.distributed as dist
+        if isinstance(seed, np.random.RandomState):
+            box = [int(seed.randint(0, 2 ** 31 - 1))]
+        elif seed is None:
+            box = [int(np.random.RandomState().randint(0, 2 ** 31 - 1))]
+        else:
+            box = [seed]
+        dist.broadcast_object_list(box, src=0, group=comm.group)
+        seed = box[0]
+    return _random_state(seed)
+
+
+def initialize_nmf(xdev: DeviceMatrix, x_mean: float, k: int, init, random_state, comm=None):
     """sklearn/decomposition/_nmf.py:214-366 for init in {random, nndsvd, nndsvda, nndsvdar}.
 
     The random draws come from numpy's RandomState exactly as in sklearn (so a fixed ``random_state``
     gives sklearn's starting point); every product with X runs on the device.
+
+    ``comm`` (``nndsvd.Comm``, world > 1): ``xdev`` holds this rank's seed rows and ``x_mean`` is the mean of
+    the WHOLE matrix; the returned W has this rank's rows of the unsharded initialisation, H is the same on
+    every rank.  Every rank draws the full random stream and slices it by global seed row.
     """
-    m, n = xdev.shape
+    from .nndsvd import Comm, nndsvd_device
+    comm = comm or Comm()
+    m_local, n = xdev.shape
+    row0, m = 0, m_local
+    if comm.world > 1:
+        import torch
+        row0, m = comm.row_layout(m_local, torch.device("cuda", xdev.handle.device))
     if init is None:
         init = "nndsvda" if k <= min(m, n) else "random"
     if init != "random" and k > min(m, n):
         raise ValueError(f"init = '{init}' can only be used when n_components <= min(n_samples, n_features)")
-    rng = _random_state(random_state)
+    rng = _shared_random_state(random_state, comm)
     if init == "random":
         avg = np.sqrt(x_mean / k)
         H = avg * rng.standard_normal(size=(k, n)).astype(np.float32, copy=False)
         W = avg * rng.standard_normal(size=(m, k)).astype(np.float32, copy=False)
+        W = np.ascontiguousarray(W[row0:row0 + m_local])
         return np.abs(W, out=W), np.abs(H, out=H)
     if init not in ("nndsvd", "nndsvda", "nndsvdar"):
         raise ValueError(f"Invalid init parameter: got {init!r} instead of one of "
                          "(None, 'random', 'nndsvd', 'nndsvda', 'nndsvdar')")
-    from .nndsvd import nndsvd_device
-    W, H = nndsvd_device(xdev, k, rng)
+    W, H = nndsvd_device(xdev, k, rng, comm=comm)
     if init == "nndsvda":
         W[W == 0] = x_mean
         H[H == 0] = x_mean
     elif init == "nndsvdar":
-        W[W == 0] = abs(x_mean * rng.standard_normal(size=int((W == 0).sum())) / 100)
+        # sklearn fills the zeros of W (row-major), then of H, from one stream: a rank's zeros of W are a
+        # contiguous run of that sequence
+        nz_w = int((W == 0).sum())
+        before, total = 0, nz_w
+        if comm.world > 1:
+            import torch
+            counts = comm.allgather(torch.tensor([nz_w], dtype=torch.int64,
+                                                 device=torch.device("cuda", xdev.handle.device)))
+            counts = [int(c.item()) for c in counts]
+            before, total = sum(counts[:comm.rank]), sum(counts)
+        draws = rng.standard_normal(size=total)
+        W[W == 0] = abs(x_mean * draws[before:before + nz_w] / 100)
         H[H == 0] = abs(x_mean * rng.standard_normal(size=int((H == 0).sum())) / 100)
     return W, H
 
@@ -166,9 +209,16 @@ class NMF:
                 W0 = np.array(W, dtype=np.float32, order="C")
                 H0 = np.array(H, dtype=np.float32, order="C")
             else:
-                if x_mean is None:      # resident matrix: float64 mean accumulated during the split
+                comm = handle_comm(xdev.handle)
+                if comm.world > 1:      # seed-row shard: mean of the whole matrix from the per-rank float64 sums
+                    import torch
+                    tot = torch.tensor([xdev.mean * m * n, float(m)], dtype=torch.float64,
+                                       device=torch.device("cuda", xdev.handle.device))
+                    tot = comm.allreduce(tot)
+                    x_mean = float(tot[0]) / (float(tot[1]) * n)
+                elif x_mean is None:    # resident matrix: float64 mean accumulated during the split
                     x_mean = xdev.mean
-                W0, H0 = initialize_nmf(xdev, x_mean, k, p["init"], p["random_state"])
+                W0, H0 = initialize_nmf(xdev, x_mean, k, p["init"], p["random_state"], comm)
             # row-sharded runs: sklearn's n_samples is the number of seeds of the whole matrix
             regs = compute_regularization(global_rows(xdev.handle, m), n, p["alpha_W"], p["alpha_H"], p["l1_ratio"])
             mark("init / checks")

@@ -24,3 +24,4 @@ def init_nccl_from_torch(handle, group=None) -> None:
         dist.broadcast_object_list(obj, src=0, group=group)
         return obj[0]
     handle.init_nccl(rank, world, bcast)
+    handle.group = group      # the host-side collectives of the sharded initialisation use the same world
