@@ -209,7 +209,48 @@ class ClockSampler:
 # (NFACT/decomp/decomposition/sso/nmfsso.py:32-59) on top of the installed sklearn, with the hyper-parameters
 # NFACT's get_parameters(None, "nmf", k) produces (matrix_decomposition.py:100-107).
 # ------------------------------------------------------------------------------------------------
+_REFERENCE = {}
+
+
+def load_reference():
+    """The UNMODIFIED reference, when a copy of it travelled to this box: `baseline/_ref` (pip-installed from
+    /root/reference in the build container, git-ignored) or $NFB_REFERENCE_PATH.  Its optional dependencies that are
+    not installed (nibabel, lz4, matplotlib, ... -- image I/O and plotting, none on the solve path) are registered
+    as empty modules so `NFACT.decomp.decomposition.sso.nmfsso` and `matrix_decomposition` import.  Returns
+    (nmf_decomp, get_parameters, where) or None."""
+    if "value" in _REFERENCE:
+        return _REFERENCE["value"]
+    import importlib
+    import types
+    found = None
+    for root in (os.environ.get("NFB_REFERENCE_PATH"), os.path.join(ROOT, "baseline", "_ref"), "/root/reference"):
+        if not root or not os.path.isdir(os.path.join(root, "NFACT")):
+            continue
+        try:
+            for name in ("lz4", "lz4.frame", "nibabel", "matplotlib", "matplotlib.pyplot", "matplotlib.colors",
+                         "seaborn", "file_tree", "networkx", "fsl", "fsl.wrappers", "fsl_sub"):
+                try:
+                    importlib.import_module(name)
+                except Exception:
+                    sys.modules[name] = types.ModuleType(name)
+            sys.path.insert(0, root)
+            sso = importlib.import_module("NFACT.decomp.decomposition.sso.nmfsso")
+            md = importlib.import_module("NFACT.decomp.decomposition.matrix_decomposition")
+            found = (sso.nmf_decomp, md.get_parameters, root)
+            break
+        except Exception:
+            if root in sys.path:
+                sys.path.remove(root)
+    _REFERENCE["value"] = found
+    return found
+
+
 def reference_nmf_decomp(parameters, fdt_matrix, W=None, H=None):
+    """The reference's solve: NFACT's own `nmf_decomp` (NFACT/decomp/decomposition/sso/nmfsso.py:32-59) from the
+    installed copy when there is one, else the same three lines restated over the installed sklearn."""
+    ref = load_reference()
+    if ref is not None:
+        return ref[0](parameters, fdt_matrix, W=W, H=H)
     import warnings
     from sklearn.decomposition import NMF
     if W is not None and H is not None:
@@ -224,6 +265,9 @@ def reference_nmf_decomp(parameters, fdt_matrix, W=None, H=None):
 def reference_parameters(k, solver, max_iter):
     """NFACT's defaults (alpha_W = 0.1, l1_ratio = 1, init = nndsvd -> custom once W, H are passed), tol = 0 so a fit
     runs exactly max_iter iterations."""
+    ref = load_reference()
+    if ref is not None:
+        return dict(ref[1](None, "nmf", k), solver=solver, tol=0.0, max_iter=int(max_iter))
     import nfact_b200.nmf as nfnmf           # get_parameters is host-only Python (no device code involved)
     return dict(nfnmf.get_parameters(None, "nmf", k), solver=solver, tol=0.0, max_iter=int(max_iter))
 
@@ -342,6 +386,8 @@ def cpu_baseline(m, n, k, density, solver, warm_iters=1, timed_iters=2, budget_s
         "value": 1.0 / per_iter, "unit": UNIT, "cores": int(threads), "kind": "reference",
         "seconds_per_iter": per_iter, "timed_iters": info["timed_iters"], "warm_iters": info["warm_iters"],
         "fit": info["fit"],
+        "call_path": ("NFACT's own nmf_decomp + get_parameters imported from " + os.path.relpath(load_reference()[2], ROOT)
+                      if load_reference() else "nmfsso.py:32-59 restated over the installed sklearn (no reference copy on this box)"),
         "sample": (f"{info['sample']}: sklearn {__import__('sklearn').__version__} NMF called as NFACT does "
                    f"(nmfsso.py:54-56 with get_parameters(None,'nmf',{k}) defaults alpha_W=0.1 l1_ratio=1, "
                    f"solver={solver}, init=custom, tol=0) on {m}x{n}; fits of max_iter={info['warm_iters']} and "

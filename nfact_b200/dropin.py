@@ -9,6 +9,10 @@ output files and only the arithmetic moves to the GPU::
     python -m nfact_b200.dropin nfact_decomp -l sub_list -s seeds... -o out -d 200
     python -m nfact_b200.dropin nfact_dr -l sub_list -n out/nfact_decomp -a NMF -o out
 
+or on all GPUs of a node (rank 0 runs the tool, the other ranks serve its solves: ``nfact_b200/multigpu.py``)::
+
+    python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 -m nfact_b200.dropin nfact_decomp ...
+
 or, from Python, ``import nfact_b200.dropin; nfact_b200.dropin.install()`` before NFACT's mains are imported
 or called.  There is no CPU fallback behind the patched names: without ``libnfact_b200.so`` or a Blackwell GPU
 they raise, which NFACT reports through its own ``error_and_exit``.  ICA (``--algo ICA``) is out of scope and
@@ -61,9 +65,24 @@ _ENTRY_POINTS = {   # pyproject.toml:41-48
 _originals: dict = {}
 
 
+def get_parameters(parameters: dict, algo: str, n_components: int) -> dict:
+    """Drop-in for NFACT/decomp/decomposition/matrix_decomposition.py:74-107.  The NMF block is nfact_b200's mirror
+    (same defaults); every other algorithm (``--algo ICA``) goes to the reference's own function untouched --
+    ICA is out of this package's scope and must keep working under the drop-in."""
+    if str(algo).lower() == "nmf" or parameters:
+        import nfact_b200
+        return nfact_b200.get_parameters(parameters, algo, n_components)
+    original = _originals.get(("NFACT.decomp.decomposition.matrix_decomposition", "get_parameters"))
+    if original is None:
+        raise ValueError("nfact_b200 implements the NMF decomposition path only")
+    return original(parameters, algo, n_components)
+
+
 def _replacement(name: str):
     import nfact_b200
     from nfact_b200 import nmfsso
+    if name == "get_parameters":
+        return get_parameters
     if hasattr(nfact_b200, name):
         return getattr(nfact_b200, name)
     return getattr(nmfsso, name)
@@ -95,25 +114,40 @@ def run_locally(args: dict, paths: dict) -> None:
                                                     args["seeds"], args["roi"])
     except Exception as e:
         error_and_exit(False, f"Unable to find components due to {e}")
-    out_dir = os.path.join(args["outdir"], "nfact_dr")
-    algo = str(args["algo"]).upper()
+    spec = {"out_dir": os.path.join(args["outdir"], "nfact_dr"), "seeds": args["seeds"],
+            "algo": str(args["algo"]).upper(), "roi": args["roi"], "cifti": args["cifti"]}
+    read_ahead = int(os.environ.get("NFB_READ_AHEAD", "0"))
+    from nfact_b200 import multigpu
+    if multigpu.active():
+        # torchrun: subjects rank, rank + world, ... per GPU; every rank writes its own subjects' images
+        nprint(f"{col['pink']}GPUs:{col['reset']} {multigpu.context().world}")
+        multigpu.dr_distributed(list(args["ptxdir"]), components, args["seeds"], int(args["threshold"]),
+                                bool(args["normalise"]), spec, read_ahead)
+        return None
+    # NFB_READ_AHEAD=N: N host threads read / decompress the next subjects' files ahead of the GPU (run_locally)
+    nfact_b200.run_locally(list(args["ptxdir"]), components, args["seeds"], threshold=int(args["threshold"]),
+                           normalise=bool(args["normalise"]), save=make_dr_saver(spec), read_ahead=read_ahead)
+    return None
+
+
+def make_dr_saver(spec: dict):
+    """``save(subject_dir, dr_results)`` that hands a subject's result to the reference's own
+    ``save_dual_regression_images`` with the reference's arguments (run_dual_regression.py:181-196)."""
+    from nfact_b200.utils import colours, error_and_exit, nprint
+    drf = importlib.import_module("NFACT.dual_reg.nfact_dr_functions")
+    col = colours()
 
     def save(subject_dir, dr_results):
         sub_id = drf.get_subject_id(subject_dir)
         nprint(f"{col['pink']}Saving{col['reset']}: Components ({sub_id})", to_flush=True)
         try:
-            drf.save_dual_regression_images(dr_results, out_dir, args["seeds"], algo,
+            drf.save_dual_regression_images(dr_results, spec["out_dir"], spec["seeds"], spec["algo"],
                                             dr_results["white_components"].shape[0], sub_id, subject_dir,
-                                            args["roi"], args["cifti"])
+                                            spec["roi"], spec["cifti"])
         except Exception as e:
             error_and_exit(False, f"Unable to save images due to {e}")
         nprint(f"{col['pink']}Completed{col['reset']}: {sub_id}", to_flush=True)
-
-    # NFB_READ_AHEAD=N: N host threads read / decompress the next subjects' files ahead of the GPU (run_locally)
-    nfact_b200.run_locally(list(args["ptxdir"]), components, args["seeds"], threshold=int(args["threshold"]),
-                           normalise=bool(args["normalise"]), save=save,
-                           read_ahead=int(os.environ.get("NFB_READ_AHEAD", "0")))
-    return None
+    return save
 
 
 def install(strict: bool = False) -> list:
@@ -184,8 +218,19 @@ def main(argv=None) -> None:
     modname, func = _ENTRY_POINTS[tool]
     module = importlib.import_module(modname)      # from-imports inside now bind the rebound functions
     install()                                      # and anything the main module imported under its own name
+    # torchrun --nproc-per-node N -m nfact_b200.dropin ...: rank 0 runs the tool, the other ranks serve its
+    # solves (nfact_b200/multigpu.py); a plain `python -m` launch is the single-GPU tool
+    from nfact_b200 import multigpu
+    ctx = multigpu.init_from_env()
+    if ctx is not None and ctx.rank != 0:
+        multigpu.serve()
+        return
     sys.argv = [tool] + argv[1:]                   # the reference parses sys.argv itself
-    getattr(module, func)()
+    try:
+        getattr(module, func)()
+    finally:
+        if ctx is not None:
+            multigpu.shutdown()
 
 
 if __name__ == "__main__":

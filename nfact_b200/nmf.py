@@ -161,6 +161,19 @@ def initialize_nmf(xdev: DeviceMatrix, x_mean: float, k: int, init, random_state
     return W, H
 
 
+def _check_custom(W, H, m: int, n: int, k: int) -> None:
+    """sklearn/decomposition/_nmf.py:1186-1203 (_check_w_h -> _check_init) for ``init='custom'``."""
+    for name, arr, shape in (("H", H, (k, n)), ("W", W, (m, k))):
+        arr = np.asarray(arr)
+        if arr.shape != shape:
+            raise ValueError(f"Array with wrong shape passed to NMF (input {name}). "
+                             f"Expected {shape}, but got {arr.shape} ")
+        if arr.size and arr.min() < 0:
+            raise ValueError(f"Negative values in data passed to NMF (input {name})")
+        if arr.size and arr.max() == 0:
+            raise ValueError(f"Array passed to NMF (input {name}) is full of zeros.")
+
+
 class NMF:
     """The slice of sklearn.decomposition.NMF that NFACT touches (nmfsso.py:54-59):
     ``NMF(**parameters).fit_transform(X, W=W, H=H)``, ``components_``, ``n_iter_``,
@@ -187,6 +200,14 @@ class NMF:
                 raise ValueError(f"Expected 2D array, got {X.ndim}D array instead")
             if X.dtype not in (np.float32, np.float64):
                 X = X.astype(np.float64)
+            from . import multigpu
+            if multigpu.active():
+                # torchrun drop-in, rank 0: a host matrix is solved row-sharded over all GPUs (multigpu.py)
+                if p["init"] == "custom":
+                    _check_custom(W, H, X.shape[0], X.shape[1], k)
+                Wf, Hf, self.n_iter_, self.reconstruction_err_ = multigpu.nmf_fit_sharded(p, X, W, H)
+                self.components_, self.n_components_ = Hf, Hf.shape[0]
+                return Wf
             # the mean is only needed by the non-custom initialisations; for a large matrix a host pass costs
             # seconds, so it is taken from the float64 sum the device accumulates while splitting X
             x_mean = float(X.mean()) if p["init"] != "custom" and X.nbytes <= (256 << 20) else None
@@ -197,15 +218,7 @@ class NMF:
                 raise ValueError("Negative values in data passed to NMF (input X)")
             m, n = xdev.shape
             if p["init"] == "custom":
-                for name, arr, shape in (("H", H, (k, n)), ("W", W, (m, k))):
-                    arr = np.asarray(arr)
-                    if arr.shape != shape:
-                        raise ValueError(f"Array with wrong shape passed to NMF (input {name}). "
-                                         f"Expected {shape}, but got {arr.shape} ")
-                    if arr.size and arr.min() < 0:
-                        raise ValueError(f"Negative values in data passed to NMF (input {name})")
-                    if arr.size and arr.max() == 0:
-                        raise ValueError(f"Array passed to NMF (input {name}) is full of zeros.")
+                _check_custom(W, H, m, n, k)
                 W0 = np.array(W, dtype=np.float32, order="C")
                 H0 = np.array(H, dtype=np.float32, order="C")
             else:

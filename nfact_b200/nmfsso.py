@@ -135,14 +135,43 @@ class NMFsso:
         return results
 
 
+def _reference_sso_outputs(args: dict, sim, dis, partitions, centroids) -> None:
+    """The reference ends ``nmf_sso`` with ``nmf_sso_output_wrapper(args['outdir'], ...)`` (nmfsso.py:264-320, 359):
+    cluster_stats.csv and the similarity / cluster plots under nfact_decomp/sso_output.  Those writers are plotting
+    code outside the hot path; when the reference is importable (the drop-in) its own function is called so the
+    tool keeps its output files, otherwise there is nothing to write them with."""
+    import sys
+    if "outdir" not in args:
+        return
+    ref = sys.modules.get("NFACT.decomp.decomposition.sso.nmfsso")
+    wrapper = getattr(ref, "nmf_sso_output_wrapper", None) if ref is not None else None
+    if wrapper is None:
+        return
+    try:
+        wrapper(args["outdir"], sim, dis, partitions, centroids)
+    except Exception as e:          # the reference's wrapper reports and carries on as well
+        nprint(f"Unable to save graphs due to: {e}")
+
+
 def nmf_sso(fdt_matrix, parameters: dict, args: dict) -> dict:
-    """NFACT/decomp/decomposition/sso/nmfsso.py:322-360."""
+    """NFACT/decomp/decomposition/sso/nmfsso.py:322-360.
+
+    Under torchrun (``nfact_b200.multigpu``) the N random-initialised runs are spread over the GPUs -- every rank
+    holds its own resident copy of X, the reference's joblib workers over a shared-memory X (nmfsso.py:140-190)
+    turned into one process per GPU -- and rank 0 clusters the gathered components and runs the final solve."""
     if args["no_sso"]:
         return nmf_decomp(parameters, fdt_matrix)
+    from . import multigpu
     owns = not isinstance(fdt_matrix, DeviceMatrix)
-    xdev = DeviceMatrix.from_host(np.asarray(fdt_matrix)) if owns else fdt_matrix
+    xdev = None
     try:
-        results = NMFsso(xdev, args["iterations"], parameters, args.get("n_cores", 1)).run()
+        if owns and multigpu.active():
+            nprint(f"{colours()['pink']}NMF iterations: {colours()['reset']}{args['iterations']} "
+                   f"over {multigpu.context().world} GPUs")
+            results, xdev = multigpu.sso_runs_distributed(parameters, np.asarray(fdt_matrix), args["iterations"])
+        else:
+            xdev = DeviceMatrix.from_host(np.asarray(fdt_matrix)) if owns else fdt_matrix
+            results = NMFsso(xdev, args["iterations"], parameters, args.get("n_cores", 1)).run()
         w_components = np.vstack(results["white"])
         g_components = np.hstack(results["grey"])
         sim = compute_similairty_matrix(w_components)
@@ -156,7 +185,9 @@ def nmf_sso(fdt_matrix, parameters: dict, args: dict) -> dict:
         parameters["n_components"] = centroids.shape[0]
         w_mat = np.ascontiguousarray(g_components[:, centroids])
         h_mat = np.ascontiguousarray(w_components[centroids, :])
-        return nmf_decomp(parameters, xdev, W=w_mat, H=h_mat)
+        final_nmf = nmf_decomp(parameters, xdev, W=w_mat, H=h_mat)
+        _reference_sso_outputs(args, sim, dis, partitions, centroids)
+        return final_nmf
     finally:
-        if owns:
+        if owns and xdev is not None:
             xdev.free()

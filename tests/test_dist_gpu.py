@@ -31,3 +31,72 @@ def test_row_sharded_solver_parity_under_torchrun():
         fh.write("$ " + " ".join(cmd[1:]) + "\n" + proc.stdout + "\n---- stderr (tail) ----\n" + proc.stderr[-4000:])
     assert proc.returncode == 0, proc.stdout[-3000:] + proc.stderr[-3000:]
     assert "DIST PARITY OK" in proc.stdout
+
+
+def _torchrun(ranks, script_args, log_name, env=None):
+    port = 29500 + (os.getpid() + len(log_name)) % 400
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={ranks}",
+           "--master-addr", "127.0.0.1", "--master-port", str(port)] + script_args
+    proc = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT, env=dict(os.environ, **(env or {})))
+    out_dir = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(out_dir, exist_ok=True)
+    with open(os.path.join(out_dir, log_name), "a") as fh:
+        fh.write("$ " + " ".join(cmd[1:]) + "\n" + proc.stdout[-6000:] + "\n---- stderr (tail) ----\n" + proc.stderr[-3000:] + "\n")
+    assert proc.returncode == 0, proc.stdout[-3000:] + proc.stderr[-3000:]
+    return proc
+
+
+def test_reference_tools_on_two_gpus(tmp_path):
+    """`torchrun ... nfact_b200.dropin nfact_decomp / nfact_dr`: rank 0 runs the reference's main, rank 1 serves.
+    nfact_decomp without sso = ONE row-sharded solve with NFACT's default NNDSVD init computed across the ranks;
+    with sso = the random-init runs spread over the GPUs (replicas) + final solve; nfact_dr = subjects round-robin.
+    Outputs against a single-process run of the same tool (CD gate) / against direct calls."""
+    import numpy as np
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least 2 GPUs (run through `gpurun --gpus 2`)")
+    from test_reference_mains_gpu import M, N, _cd_gate, _reference_root, _study
+    ref = _reference_root()
+    if ref is None:
+        pytest.skip("no reference checkout (NFB_REFERENCE_PATH, /root/reference, baseline/_ref)")
+    script = os.path.join(ROOT, "tests", "dist_dropin_gpu.py")
+    subs, sub_list, seed_list, out = _study(tmp_path)
+    out1 = str(tmp_path / "out1")
+    os.makedirs(out1)
+    common = ["-l", sub_list, "-s", seed_list, "-d", "5", "--disk"]
+    _torchrun(2, [script, ref, "nfact_decomp", "-o", out] + common + ["-X", "1"], "dist_dropin_n2.log")
+    _torchrun(1, [script, ref, "nfact_decomp", "-o", out1] + common + ["-X", "1"], "dist_dropin_n2.log")
+    comp = os.path.join(out, "nfact_decomp", "components", "NMF", "decomp")
+    comp1 = os.path.join(out1, "nfact_decomp", "components", "NMF", "decomp")
+    avg = np.load(os.path.join(out, "nfact_decomp", "group_averages", "average_matrix2.npy"))
+    assert np.array_equal(avg, np.load(os.path.join(out1, "nfact_decomp", "group_averages", "average_matrix2.npy")))
+    W, G = np.load(os.path.join(comp, "W_NMF_dim5.npy")), np.load(os.path.join(comp, "G_NMF_dim5.npy"))
+    W1, G1 = np.load(os.path.join(comp1, "W_NMF_dim5.npy")), np.load(os.path.join(comp1, "G_NMF_dim5.npy"))
+    assert W.shape == (5, N) and G.shape == (M, 5)
+    _cd_gate(G, W, G1, W1, avg, 5)
+    # NMF-sso over two GPUs
+    out_sso = str(tmp_path / "out_sso")
+    os.makedirs(out_sso)
+    _torchrun(2, [script, ref, "nfact_decomp", "-o", out_sso, "-l", sub_list, "-s", seed_list, "-d", "4", "--disk",
+                  "-i", "5"], "dist_dropin_n2.log")
+    comp_sso = os.path.join(out_sso, "nfact_decomp", "components", "NMF", "decomp")
+    Ws, Gs = np.load(os.path.join(comp_sso, "W_NMF_dim4.npy")), np.load(os.path.join(comp_sso, "G_NMF_dim4.npy"))
+    assert 2 <= Ws.shape[0] <= 4 and Ws.shape[1] == N and Gs.shape == (M, Ws.shape[0])
+    assert np.isfinite(Ws).all() and np.isfinite(Gs).all() and Ws.min() >= 0 and Gs.min() >= 0
+    # nfact_dr: subjects round-robin over the two ranks
+    import nfact_b200
+    _torchrun(2, [script, ref, "nfact_dr", "-l", sub_list, "-s", seed_list, "-d", os.path.join(out, "nfact_decomp"),
+                  "-o", out, "-a", "NMF"], "dist_dropin_n2.log", env={"NFB_TEST_DR_NPY": comp})
+    group = {"white_components": W, "grey_components": G.astype(np.float64)}
+    ranks_seen = set()
+    for idx, s in enumerate(subs):
+        sub_id = os.path.basename(s)
+        ranks_seen.add(open(os.path.join(out, "nfact_dr", "NMF", f"rank_of_{sub_id}.txt")).read())
+        Gd = np.load(os.path.join(out, "nfact_dr", "NMF", f"G_{sub_id}_dim5.npy"))
+        Wd = np.load(os.path.join(out, "nfact_dr", "NMF", f"W_{sub_id}_dim5.npy"))
+        x = nfact_b200.load_fdt_matrix(os.path.join(s, "fdt_matrix2.dot"))
+        direct = nfact_b200.nmf_dual_regression(group, x)
+        direct = nfact_b200.thresholding_components(3, os.path.join(s, "coords_for_fdt_matrix2"), [seed_list], direct)
+        assert np.allclose(Gd, direct["grey_components"], rtol=1e-9, atol=1e-12)
+        assert np.allclose(Wd, direct["white_components"], rtol=1e-9, atol=1e-12)
+    assert ranks_seen == {"0", "1"}

@@ -99,7 +99,12 @@ def test_install_rebinds_the_reference_seams(reference):
     assert ref_sso.nmf_decomp is nfact_b200.nmf_decomp
     assert ref_sso.thresholding is nfact_b200.thresholding                 # a from-import copy, rebound too
     md = importlib.import_module("NFACT.decomp.decomposition.matrix_decomposition")
-    assert md.nmf_sso is nfact_b200.nmf_sso and md.get_parameters is nfact_b200.get_parameters
+    assert md.nmf_sso is nfact_b200.nmf_sso and md.get_parameters is dropin.get_parameters
+    # NMF: nfact_b200's mirror of the defaults; ICA (out of scope) goes through to the reference's own function
+    assert md.get_parameters(None, "nmf", 7) == nfact_b200.get_parameters(None, "nmf", 7)
+    ica = md.get_parameters(None, "ica", 7)
+    ref_get = dropin._originals[("NFACT.decomp.decomposition.matrix_decomposition", "get_parameters")]
+    assert ica == ref_get(None, "ica", 7) and ica["n_components"] == 7 and "alpha_W" not in ica
     mh = importlib.import_module("NFACT.decomp.decomposition.matrix_handling")
     assert mh.process_fdt_matrix2 is nfact_b200.process_fdt_matrix2 and mh.avg_fdt is nfact_b200.avg_fdt
     drm = importlib.import_module("NFACT.dual_reg.dual_regression.dual_regression_methods")

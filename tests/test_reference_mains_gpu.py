@@ -1,0 +1,179 @@
+"""GPU: the reference's OWN command-line mains, unmodified, on the B200 path through ``nfact_b200.dropin``.
+
+``nfact_decomp_main`` (NFACT/decomp/__main__.py:42-211) and ``nfact_dr_main`` (NFACT/dual_reg/__main__.py:27-96)
+are imported from a reference checkout -- ``$NFB_REFERENCE_PATH``, ``/root/reference`` (build container) or
+``baseline/_ref`` (the pip-installed copy that travels to the GPU box; git-ignored, never part of the repo's
+history) -- and run on the golden subjects after ``dropin.install()``.  The reference's optional dependencies that
+are not installed (nibabel, lz4, matplotlib, ...) are stubbed as in tests/test_dropin_cpu.py; image I/O therefore
+goes through the reference's own ``.npy`` writer (``--disk`` -> ``save_components_to_disk``,
+decomp/pipes/image_handling.py:78-110) for ``nfact_decomp``, and through ``.npy`` stand-ins for the two NIfTI/GIFTI
+functions of ``nfact_dr`` (component loader, image writer).  Every output file is checked against the same steps
+called directly on ``nfact_b200``.  Skipped when no reference checkout is present.
+"""
+import importlib
+import os
+import shutil
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_DIR, ROOT
+from test_dropin_cpu import _Stub
+from test_nmf_gpu import matched_correlation
+
+pytestmark = pytest.mark.gpu
+
+M, N = 99, 199            # the golden subjects' matrix
+
+
+def _reference_root():
+    for cand in (os.environ.get("NFB_REFERENCE_PATH"), "/root/reference", os.path.join(ROOT, "baseline", "_ref")):
+        if cand and os.path.isdir(os.path.join(cand, "NFACT")):
+            return cand
+    return None
+
+
+@pytest.fixture
+def reference_tools():
+    root = _reference_root()
+    if root is None:
+        pytest.skip("no reference checkout (NFB_REFERENCE_PATH, /root/reference, baseline/_ref)")
+    from nfact_b200 import dropin
+    added = []
+    for name in ("lz4", "lz4.frame", "nibabel", "matplotlib", "matplotlib.pyplot", "matplotlib.colors", "seaborn",
+                 "file_tree", "networkx", "fsl", "fsl.wrappers", "fsl_sub"):
+        if name in sys.modules:
+            continue
+        try:
+            importlib.import_module(name)
+        except Exception:
+            sys.modules[name] = _Stub(name)
+            added.append(name)
+    sys.path.insert(0, root)
+    argv = list(sys.argv)
+    yield dropin
+    sys.argv = argv
+    dropin.uninstall()
+    sys.path.remove(root)
+    for name in added:
+        sys.modules.pop(name, None)
+    for name in [n for n in sys.modules if n == "NFACT" or n.startswith("NFACT.")]:
+        del sys.modules[name]
+
+
+def _study(tmp_path):
+    """Three probtrackx-like subject folders from the golden fixtures + the list files the tools take."""
+    subs = []
+    for s in (1, 2, 3):
+        d = tmp_path / f"sub_{s}"          # get_subject_id (nfact_dr_functions.py:484-508) looks for sub_<id>
+        d.mkdir()
+        for f in ("fdt_matrix2.dot", "waytotal"):
+            shutil.copy(os.path.join(GOLDEN_DIR, "data", f"sub-{s}", f), d)
+        coords = np.zeros((M, 5), dtype=int)
+        coords[:, 3] = 0                                   # one seed: every row belongs to seed 0
+        coords[:, 4] = np.arange(M)
+        np.savetxt(d / "coords_for_fdt_matrix2", coords, fmt="%d")
+        np.savetxt(d / "tract_space_coords_for_fdt_matrix2", np.zeros((N, 3), dtype=int), fmt="%d")
+        (d / "lookup_tractspace_fdt_matrix2.nii.gz").write_bytes(b"x")
+        subs.append(str(d))
+    (tmp_path / "subs.txt").write_text("\n".join(subs) + "\n")
+    seed = tmp_path / "seed.nii.gz"
+    seed.write_bytes(b"x")
+    (tmp_path / "seeds.txt").write_text(str(seed) + "\n")
+    out = tmp_path / "out"
+    out.mkdir()
+    return subs, str(tmp_path / "subs.txt"), str(tmp_path / "seeds.txt"), str(out)
+
+
+def _run_tool(dropin, argv):
+    try:
+        dropin.main(argv)
+    except SystemExit as e:            # the reference ends a command-line run with exit(0)
+        assert e.code in (0, None), f"tool exited with {e.code}"
+
+
+def _cd_gate(W, H, Wd, Hd, X, k):
+    from oracle import nfact_oracle as orc
+    regs = orc.compute_regularization(X.shape[0], X.shape[1], 0.1, "same", 1.0)
+    obj, obj_d = orc.nmf_objective(X, W, H, *regs), orc.nmf_objective(X, Wd, Hd, *regs)
+    assert abs(obj - obj_d) <= 5e-3 * obj_d
+    corr, live = matched_correlation(H, Hd)
+    assert corr[live].min() >= 0.99
+
+
+def test_nfact_decomp_main_single_solve(reference_tools, tmp_path):
+    """nfact_decomp -l subs -s seeds -o out -d 5 --disk -X 1 (no sso): ingest -> average_matrix2.npy ->
+    default NNDSVD + CD solve -> thresholding -> W / G .npy files."""
+    import nfact_b200
+    from oracle import nfact_oracle as orc
+    dropin = reference_tools
+    subs, sub_list, seed_list, out = _study(tmp_path)
+    _run_tool(dropin, ["nfact_decomp", "-l", sub_list, "-s", seed_list, "-o", out, "-d", "5", "--disk", "-X", "1"])
+    mod = sys.modules["NFACT.decomp.__main__"]
+    assert mod.process_fdt_matrix2 is nfact_b200.process_fdt_matrix2          # the run went through the rebound seams
+    avg = np.load(os.path.join(out, "nfact_decomp", "group_averages", "average_matrix2.npy"))
+    files = [os.path.join(s, "fdt_matrix2.dot") for s in subs]
+    assert avg.dtype == np.float32 and np.array_equal(avg, orc.avg_fdt(files))           # bit-exact ingest
+    comp_dir = os.path.join(out, "nfact_decomp", "components", "NMF", "decomp")
+    W = np.load(os.path.join(comp_dir, "W_NMF_dim5.npy"))       # white components [k, n]
+    G = np.load(os.path.join(comp_dir, "G_NMF_dim5.npy"))       # grey components [m, k]
+    assert W.shape == (5, N) and G.shape == (M, 5)
+    # the same steps called directly (random_state=None in both: the randomised SVD differs run to run -> CD gate)
+    direct = nfact_b200.nmf_decomp(nfact_b200.get_parameters(None, "nmf", 5), avg)
+    coords = os.path.join(out, "nfact_decomp", "group_averages", "coords_for_fdt_matrix2")
+    direct = nfact_b200.thresholding_components(3, coords, [seed_list], direct)
+    _cd_gate(G, W, direct["grey_components"], direct["white_components"], avg, 5)
+    assert (W == 0).mean() > 0.3 and abs((W == 0).mean() - (direct["white_components"] == 0).mean()) < 0.05
+
+
+def test_nfact_decomp_main_default_sso_flow(reference_tools, tmp_path):
+    """NFACT's default: NMF-sso (here 4 runs instead of 20) -> clustering -> final custom-init solve, through the
+    reference's main.  The reference itself cannot run this configuration (`range(colours)` TypeError at
+    nmfsso.py:207 with n_cores unset); the drop-in keeps the intended behaviour."""
+    dropin = reference_tools
+    subs, sub_list, seed_list, out = _study(tmp_path)
+    _run_tool(dropin, ["nfact_decomp", "-l", sub_list, "-s", seed_list, "-o", out, "-d", "4", "--disk", "-i", "4"])
+    comp_dir = os.path.join(out, "nfact_decomp", "components", "NMF", "decomp")
+    files = sorted(os.listdir(comp_dir))
+    assert files == ["G_NMF_dim4.npy", "W_NMF_dim4.npy"], files
+    W = np.load(os.path.join(comp_dir, "W_NMF_dim4.npy"))
+    G = np.load(os.path.join(comp_dir, "G_NMF_dim4.npy"))
+    kf = W.shape[0]
+    assert 2 <= kf <= 4 and W.shape == (kf, N) and G.shape == (M, kf)
+    assert np.isfinite(W).all() and np.isfinite(G).all() and W.min() >= 0 and G.min() >= 0
+
+
+def test_nfact_dr_main(reference_tools, tmp_path, monkeypatch):
+    """nfact_dr -l subs -s seeds -d out/nfact_decomp -o out -a NMF: the rebound subject loop -> per-subject files,
+    equal to nmf_dual_regression + thresholding called directly."""
+    import nfact_b200
+    dropin = reference_tools
+    subs, sub_list, seed_list, out = _study(tmp_path)
+    _run_tool(dropin, ["nfact_decomp", "-l", sub_list, "-s", seed_list, "-o", out, "-d", "5", "--disk", "-X", "1"])
+    comp_dir = os.path.join(out, "nfact_decomp", "components", "NMF", "decomp")
+    group = {"white_components": np.load(os.path.join(comp_dir, "W_NMF_dim5.npy")),
+             "grey_components": np.load(os.path.join(comp_dir, "G_NMF_dim5.npy")).astype(np.float64)}
+    drf = importlib.import_module("NFACT.dual_reg.nfact_dr_functions")
+    # the two NIfTI / GIFTI functions of nfact_dr, as .npy stand-ins (nibabel is not installed)
+    monkeypatch.setattr(drf, "get_group_level_components", lambda comp, avg, seeds, roi: dict(group))
+    saved = {}
+
+    def save_npy(dr_results, out_dir, seeds, algo, dim, sub_id, subject_dir, roi, cifti):
+        np.save(os.path.join(out_dir, algo, f"G_{sub_id}_dim{dim}.npy"), dr_results["grey_components"])
+        np.save(os.path.join(out_dir, algo, f"W_{sub_id}_dim{dim}.npy"), dr_results["white_components"])
+        saved[sub_id] = subject_dir
+    monkeypatch.setattr(drf, "save_dual_regression_images", save_npy)
+    _run_tool(dropin, ["nfact_dr", "-l", sub_list, "-s", seed_list, "-d", os.path.join(out, "nfact_decomp"),
+                       "-o", out, "-a", "NMF"])
+    assert len(saved) == 3
+    for sub_id, subject_dir in saved.items():
+        Gs = np.load(os.path.join(out, "nfact_dr", "NMF", f"G_{sub_id}_dim5.npy"))
+        Ws = np.load(os.path.join(out, "nfact_dr", "NMF", f"W_{sub_id}_dim5.npy"))
+        assert Gs.shape == (M, 5) and Ws.shape == (5, N) and Gs.dtype == np.float64
+        x = nfact_b200.load_fdt_matrix(os.path.join(subject_dir, "fdt_matrix2.dot"))
+        direct = nfact_b200.nmf_dual_regression(group, x)
+        direct = nfact_b200.thresholding_components(3, os.path.join(subject_dir, "coords_for_fdt_matrix2"), [seed_list],
+                                                    direct)
+        assert np.allclose(Gs, direct["grey_components"], rtol=1e-9, atol=1e-12)
+        assert np.allclose(Ws, direct["white_components"], rtol=1e-9, atol=1e-12)
