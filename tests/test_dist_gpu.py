@@ -74,15 +74,25 @@ def test_reference_tools_on_two_gpus(tmp_path):
     W1, G1 = np.load(os.path.join(comp1, "W_NMF_dim5.npy")), np.load(os.path.join(comp1, "G_NMF_dim5.npy"))
     assert W.shape == (5, N) and G.shape == (M, 5)
     _cd_gate(G, W, G1, W1, avg, 5)
-    # NMF-sso over two GPUs
-    out_sso = str(tmp_path / "out_sso")
-    os.makedirs(out_sso)
-    _torchrun(2, [script, ref, "nfact_decomp", "-o", out_sso, "-l", sub_list, "-s", seed_list, "-d", "4", "--disk",
-                  "-i", "5"], "dist_dropin_n2.log")
+    # NMF-sso over two GPUs (the random-init runs are the replicas axis), planted study + config file
+    from test_reference_mains_gpu import _study_planted
+    from test_nmf_gpu import matched_correlation
+    planted = tmp_path / "planted"
+    planted.mkdir()
+    Xp, p_list, p_seeds, p_config, out_sso = _study_planted(planted)
+    out_sso1 = str(planted / "out1")
+    os.makedirs(out_sso1)
+    sso_args = ["-l", p_list, "-s", p_seeds, "-d", "4", "--disk", "-i", "6", "-f", p_config, "-t", "0"]
+    _torchrun(2, [script, ref, "nfact_decomp", "-o", out_sso] + sso_args, "dist_dropin_n2.log")
+    _torchrun(1, [script, ref, "nfact_decomp", "-o", out_sso1] + sso_args, "dist_dropin_n2.log")
     comp_sso = os.path.join(out_sso, "nfact_decomp", "components", "NMF", "decomp")
+    comp_sso1 = os.path.join(out_sso1, "nfact_decomp", "components", "NMF", "decomp")
     Ws, Gs = np.load(os.path.join(comp_sso, "W_NMF_dim4.npy")), np.load(os.path.join(comp_sso, "G_NMF_dim4.npy"))
-    assert 2 <= Ws.shape[0] <= 4 and Ws.shape[1] == N and Gs.shape == (M, Ws.shape[0])
+    Ws1 = np.load(os.path.join(comp_sso1, "W_NMF_dim4.npy"))
+    assert Ws.shape == Ws1.shape == (4, Xp.shape[1]) and Gs.shape == (Xp.shape[0], 4)
     assert np.isfinite(Ws).all() and np.isfinite(Gs).all() and Ws.min() >= 0 and Gs.min() >= 0
+    corr, live = matched_correlation(Ws, Ws1)
+    assert live.all() and corr.min() >= 0.99, corr
     # nfact_dr: subjects round-robin over the two ranks
     import nfact_b200
     _torchrun(2, [script, ref, "nfact_dr", "-l", sub_list, "-s", seed_list, "-d", os.path.join(out, "nfact_decomp"),

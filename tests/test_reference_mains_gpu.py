@@ -127,21 +127,91 @@ def test_nfact_decomp_main_single_solve(reference_tools, tmp_path):
     assert (W == 0).mean() > 0.3 and abs((W == 0).mean() - (direct["white_components"] == 0).mean()) < 0.05
 
 
+def _study_planted(tmp_path, k=4, seed=12):
+    """One subject whose matrix has k planted sparse components (integer streamline counts, waytotal 1e8 -> scale
+    1): the NMF-sso flow needs runs that agree, which the 99 x 199 fixtures do not give (with them the reference's
+    own clustering fails on all-zero thresholded components).  Returns (X, subject list, seed list, config, out)."""
+    import json
+    rng = np.random.default_rng(seed)
+    m, n = 120, 210
+    Wp = rng.gamma(0.4, 1.0, (m, k)) * (rng.random((m, k)) < 0.4)
+    Hp = rng.gamma(0.4, 1.0, (k, n)) * (rng.random((k, n)) < 0.4)
+    X = np.floor(Wp @ Hp * 100 + 3 * rng.random((m, n)))
+    d = tmp_path / "sub_1"
+    d.mkdir()
+    rows, cols = np.nonzero(X)
+    with open(d / "fdt_matrix2.dot", "wb") as fh:
+        np.savetxt(fh, np.column_stack([rows + 1, cols + 1, X[rows, cols].astype(np.int64)]), fmt="%d %d %d")
+        fh.write(f"{m} {n} 0\n".encode())
+    (d / "waytotal").write_text("100000000\n")
+    coords = np.zeros((m, 5), dtype=int)
+    coords[:, 4] = np.arange(m)
+    np.savetxt(d / "coords_for_fdt_matrix2", coords, fmt="%d")
+    np.savetxt(d / "tract_space_coords_for_fdt_matrix2", np.zeros((n, 3), dtype=int), fmt="%d")
+    (d / "lookup_tractspace_fdt_matrix2.nii.gz").write_bytes(b"x")
+    (tmp_path / "subs.txt").write_text(str(d) + "\n")
+    seed_img = tmp_path / "seed.nii.gz"
+    seed_img.write_bytes(b"x")
+    (tmp_path / "seeds.txt").write_text(str(seed_img) + "\n")
+    # nfact_config-style hyper-parameter file (-f): sklearn NMF's signature, NFACT's defaults with a small penalty
+    params = {"init": "nndsvd", "solver": "cd", "beta_loss": "frobenius", "tol": 1e-4, "max_iter": 150,
+              "random_state": None, "alpha_W": 1e-4, "alpha_H": "same", "l1_ratio": 1, "verbose": 0, "shuffle": False}
+    (tmp_path / "config.json").write_text(json.dumps({"nmf": params, "ica": {}}))
+    out = tmp_path / "out"
+    out.mkdir(exist_ok=True)
+    return (X.astype(np.float32), str(tmp_path / "subs.txt"), str(tmp_path / "seeds.txt"), str(tmp_path / "config.json"),
+            str(out))
+
+
+def reference_sso_flow(X, params, iterations, dim):
+    """The reference's NMF-sso flow with its own functions on the CPU (sklearn), run serially: NMFsso's parallel
+    branch (nmfsso.py:120-138: random init, thresholding(H, 3) per run) -- its single-core branch cannot run
+    (`range(colours)`, nmfsso.py:207) and joblib workers cannot see the test's stub modules --, then nmf_sso's own
+    lines (nmfsso.py:346-358)."""
+    sso = importlib.import_module("NFACT.decomp.decomposition.sso.nmfsso")
+    fn = importlib.import_module("NFACT.decomp.decomposition.sso.sso_functions")
+    bmh = importlib.import_module("NFACT.base.matrix_handling")
+    run_params = dict(params, init="random", random_state=None)
+    white, grey = [], []
+    for _ in range(iterations):
+        res = sso.nmf_decomp(run_params, X)
+        grey.append(res["grey_components"])
+        white.append(bmh.thresholding(res["white_components"], 3))
+    w_components, g_components = np.vstack(white), np.hstack(grey)
+    sim = fn.compute_similairty_matrix(w_components)
+    partitions = fn.clustering_components(fn.sim2dis(sim), dim)
+    centroids = fn.idx2centrotype(sim, partitions)
+    final = dict(params, random_state=None, init="custom", n_components=centroids.shape[0])
+    return sso.nmf_decomp(final, X, W=np.ascontiguousarray(g_components[:, centroids]),
+                          H=np.ascontiguousarray(w_components[centroids, :]))
+
+
 def test_nfact_decomp_main_default_sso_flow(reference_tools, tmp_path):
-    """NFACT's default: NMF-sso (here 4 runs instead of 20) -> clustering -> final custom-init solve, through the
-    reference's main.  The reference itself cannot run this configuration (`range(colours)` TypeError at
-    nmfsso.py:207 with n_cores unset); the drop-in keeps the intended behaviour."""
+    """NFACT's default flow through the reference's main: NMF-sso (6 random-init runs) -> similarity -> clustering ->
+    centrotypes -> final custom-init solve, hyper-parameters from a -f config file.  Compared with the reference's
+    own functions run on the CPU BEFORE the drop-in is installed: same number of components, Hungarian-matched
+    component correlation.  (The reference's CLI cannot run this configuration itself: `range(colours)` TypeError at
+    nmfsso.py:207 with n_cores = 1; the drop-in keeps the intended behaviour.)"""
+    import json
     dropin = reference_tools
-    subs, sub_list, seed_list, out = _study(tmp_path)
-    _run_tool(dropin, ["nfact_decomp", "-l", sub_list, "-s", seed_list, "-o", out, "-d", "4", "--disk", "-i", "4"])
+    X, sub_list, seed_list, config, out = _study_planted(tmp_path)
+    params = dict(json.load(open(config))["nmf"], n_components=4)
+    ref = reference_sso_flow(X, params, 6, 4)                              # the reference's arithmetic, untouched
+    _run_tool(dropin, ["nfact_decomp", "-l", sub_list, "-s", seed_list, "-o", out, "-d", "4", "--disk", "-i", "6",
+                       "-f", config, "-t", "0"])
     comp_dir = os.path.join(out, "nfact_decomp", "components", "NMF", "decomp")
-    files = sorted(os.listdir(comp_dir))
-    assert files == ["G_NMF_dim4.npy", "W_NMF_dim4.npy"], files
     W = np.load(os.path.join(comp_dir, "W_NMF_dim4.npy"))
     G = np.load(os.path.join(comp_dir, "G_NMF_dim4.npy"))
     kf = W.shape[0]
-    assert 2 <= kf <= 4 and W.shape == (kf, N) and G.shape == (M, kf)
+    assert kf == ref["white_components"].shape[0] == 4 and W.shape == (kf, X.shape[1]) and G.shape == (X.shape[0], kf)
     assert np.isfinite(W).all() and np.isfinite(G).all() and W.min() >= 0 and G.min() >= 0
+    corr, live = matched_correlation(W, ref["white_components"])
+    assert live.all() and corr.min() >= 0.99, corr
+    corr_g, live_g = matched_correlation(G.T, ref["grey_components"].T)
+    assert live_g.all() and corr_g.min() >= 0.99, corr_g
+    rel = np.linalg.norm(X - G @ W) / np.linalg.norm(X)
+    rel_ref = np.linalg.norm(X - ref["grey_components"] @ ref["white_components"]) / np.linalg.norm(X)
+    assert abs(rel - rel_ref) < 0.01, (rel, rel_ref)
 
 
 def test_nfact_dr_main(reference_tools, tmp_path, monkeypatch):
