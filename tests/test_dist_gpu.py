@@ -63,7 +63,9 @@ def test_reference_tools_on_two_gpus(tmp_path):
     subs, sub_list, seed_list, out = _study(tmp_path)
     out1 = str(tmp_path / "out1")
     os.makedirs(out1)
-    common = ["-l", sub_list, "-s", seed_list, "-d", "5", "--disk"]
+    from test_reference_mains_gpu import _config
+    config, _ = _config(tmp_path, random_state=0)      # repeatable NNDSVD draw: N = 2 vs N = 1 differ by rounding only
+    common = ["-l", sub_list, "-s", seed_list, "-d", "5", "--disk", "-f", config, "-t", "0"]
     _torchrun(2, [script, ref, "nfact_decomp", "-o", out] + common + ["-X", "1"], "dist_dropin_n2.log")
     _torchrun(1, [script, ref, "nfact_decomp", "-o", out1] + common + ["-X", "1"], "dist_dropin_n2.log")
     comp = os.path.join(out, "nfact_decomp", "components", "NMF", "decomp")

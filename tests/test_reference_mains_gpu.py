@@ -102,14 +102,30 @@ def _cd_gate(W, H, Wd, Hd, X, k):
     assert corr[live].min() >= 0.99
 
 
+def _config(tmp_path, **overrides):
+    """nfact_config-style hyper-parameter file (-f): sklearn NMF's signature with NFACT's defaults
+    (matrix_decomposition.py:100-107) and the given overrides."""
+    import json
+    params = {"init": "nndsvd", "solver": "cd", "beta_loss": "frobenius", "tol": 1e-4, "max_iter": 200,
+              "random_state": None, "alpha_W": 0.1, "alpha_H": "same", "l1_ratio": 1, "verbose": 0, "shuffle": False}
+    params.update(overrides)
+    path = tmp_path / "config.json"
+    path.write_text(json.dumps({"nmf": params, "ica": {}}))
+    return str(path), params
+
+
 def test_nfact_decomp_main_single_solve(reference_tools, tmp_path):
-    """nfact_decomp -l subs -s seeds -o out -d 5 --disk -X 1 (no sso): ingest -> average_matrix2.npy ->
-    default NNDSVD + CD solve -> thresholding -> W / G .npy files."""
+    """nfact_decomp -l subs -s seeds -o out -d 5 --disk -X 1 -f config (no sso): ingest -> average_matrix2.npy ->
+    NNDSVD + CD solve with NFACT's default penalties -> thresholding -> W / G .npy files.  random_state = 0 in the
+    config file makes the randomised SVD of the initialisation repeatable, so the files must equal the same steps
+    called directly."""
     import nfact_b200
     from oracle import nfact_oracle as orc
     dropin = reference_tools
     subs, sub_list, seed_list, out = _study(tmp_path)
-    _run_tool(dropin, ["nfact_decomp", "-l", sub_list, "-s", seed_list, "-o", out, "-d", "5", "--disk", "-X", "1"])
+    config, params = _config(tmp_path, random_state=0)
+    _run_tool(dropin, ["nfact_decomp", "-l", sub_list, "-s", seed_list, "-o", out, "-d", "5", "--disk", "-X", "1",
+                       "-f", config])
     mod = sys.modules["NFACT.decomp.__main__"]
     assert mod.process_fdt_matrix2 is nfact_b200.process_fdt_matrix2          # the run went through the rebound seams
     avg = np.load(os.path.join(out, "nfact_decomp", "group_averages", "average_matrix2.npy"))
@@ -119,19 +135,25 @@ def test_nfact_decomp_main_single_solve(reference_tools, tmp_path):
     W = np.load(os.path.join(comp_dir, "W_NMF_dim5.npy"))       # white components [k, n]
     G = np.load(os.path.join(comp_dir, "G_NMF_dim5.npy"))       # grey components [m, k]
     assert W.shape == (5, N) and G.shape == (M, 5)
-    # the same steps called directly (random_state=None in both: the randomised SVD differs run to run -> CD gate)
-    direct = nfact_b200.nmf_decomp(nfact_b200.get_parameters(None, "nmf", 5), avg)
+    direct = nfact_b200.nmf_decomp(nfact_b200.get_parameters(dict(params), "nmf", 5), avg)
+    # un-thresholded solve against sklearn itself from the same (sklearn-made) NNDSVD start: the CD gate
+    from sklearn.decomposition import NMF
+    from sklearn.decomposition._nmf import _initialize_nmf
+    W0, H0 = _initialize_nmf(avg, 5, init="nndsvd", random_state=0)
+    sk = NMF(**dict(params, n_components=5, init="custom"))
+    Wsk = sk.fit_transform(avg, W=W0.copy(), H=H0.copy())
+    _cd_gate(direct["grey_components"], direct["white_components"], Wsk, sk.components_, avg, 5)
     coords = os.path.join(out, "nfact_decomp", "group_averages", "coords_for_fdt_matrix2")
     direct = nfact_b200.thresholding_components(3, coords, [seed_list], direct)
-    _cd_gate(G, W, direct["grey_components"], direct["white_components"], avg, 5)
-    assert (W == 0).mean() > 0.3 and abs((W == 0).mean() - (direct["white_components"] == 0).mean()) < 0.05
+    assert np.allclose(G, direct["grey_components"], rtol=1e-6, atol=0)
+    assert np.allclose(W, direct["white_components"], rtol=1e-6, atol=0)
+    assert (W == 0).mean() > 0.3                                # the z = 3 threshold did its work
 
 
 def _study_planted(tmp_path, k=4, seed=12):
     """One subject whose matrix has k planted sparse components (integer streamline counts, waytotal 1e8 -> scale
     1): the NMF-sso flow needs runs that agree, which the 99 x 199 fixtures do not give (with them the reference's
     own clustering fails on all-zero thresholded components).  Returns (X, subject list, seed list, config, out)."""
-    import json
     rng = np.random.default_rng(seed)
     m, n = 120, 210
     Wp = rng.gamma(0.4, 1.0, (m, k)) * (rng.random((m, k)) < 0.4)
@@ -153,14 +175,10 @@ def _study_planted(tmp_path, k=4, seed=12):
     seed_img = tmp_path / "seed.nii.gz"
     seed_img.write_bytes(b"x")
     (tmp_path / "seeds.txt").write_text(str(seed_img) + "\n")
-    # nfact_config-style hyper-parameter file (-f): sklearn NMF's signature, NFACT's defaults with a small penalty
-    params = {"init": "nndsvd", "solver": "cd", "beta_loss": "frobenius", "tol": 1e-4, "max_iter": 150,
-              "random_state": None, "alpha_W": 1e-4, "alpha_H": "same", "l1_ratio": 1, "verbose": 0, "shuffle": False}
-    (tmp_path / "config.json").write_text(json.dumps({"nmf": params, "ica": {}}))
+    config, _ = _config(tmp_path, alpha_W=1e-4, max_iter=150)      # a small penalty: the planted factors survive
     out = tmp_path / "out"
     out.mkdir(exist_ok=True)
-    return (X.astype(np.float32), str(tmp_path / "subs.txt"), str(tmp_path / "seeds.txt"), str(tmp_path / "config.json"),
-            str(out))
+    return X.astype(np.float32), str(tmp_path / "subs.txt"), str(tmp_path / "seeds.txt"), config, str(out)
 
 
 def reference_sso_flow(X, params, iterations, dim):
