@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(NT, 1)
 cd_sweep_tile_kernel(float* __restrict__ f, int k, int64_t cols, int64_t ld, const float* __restrict__ num,
                      int num_splits, int64_t num_stride, const float* __restrict__ den, int64_t ld_part,
                      const float* __restrict__ gram, int ldg, float l1, float l2, double* __restrict__ violation,
-                     unsigned int* __restrict__ rowmax_bits, bool vec) {
+                     unsigned int* __restrict__ rowmax_bits, bool vec, const PeerMirror mirror) {
     constexpr int JG = TJ / 4;        // groups of 4 samples
     constexpr int UG = NT / JG;       // groups of 4 components updated concurrently in the apply phase
     static_assert(TJ % 32 == 0 && NT % TJ == 0 && NT % JG == 0, "tile shape");
@@ -251,6 +251,21 @@ cd_sweep_tile_kernel(float* __restrict__ f, int k, int64_t cols, int64_t ld, con
 #pragma unroll
         for (int i = 0; i < kBlk; ++i)
             if (kFull || i < nb) gs[(t0 + i) * TJ + tid] = dl[i];
+        // Row-sharded runs: every value that moved goes straight into the peers' copies of H (the all-gather of
+        // the slices, fused): the peers hold the previous H, so unchanged entries -- most zeros stay zero -- cost
+        // no NVLink traffic, and the stores of this tile travel while the other tiles are still computing.
+        if (mirror.n > 0 && active) {
+            const int64_t off = static_cast<int64_t>(t0) * ld + jc_own;
+#pragma unroll
+            for (int i = 0; i < kBlk; ++i) {
+                if ((kFull || i < nb) && dl[i] != 0.0f) {
+                    const float v = __uint_as_float(fb[i]);
+#pragma unroll
+                    for (int p = 0; p < 7; ++p)
+                        if (p < mirror.n) mirror.f[p][off + static_cast<int64_t>(i) * ld] = v;
+                }
+            }
+        }
         // per-component maxima for the plane split: 16 independent warp reductions, one shared atomic per warp
         unsigned int vmax[kBlk];
 #pragma unroll
@@ -319,9 +334,10 @@ cd_sweep_tile_kernel(float* __restrict__ f, int k, int64_t cols, int64_t ld, con
 
 int cd_sweep(float* f, int64_t k, int64_t cols, int64_t ld, const float* num, int num_splits, int64_t num_stride,
              const float* den, int64_t ld_part, const float* gram, float l1, float l2, double* violation,
-             unsigned int* rowmax_bits, cudaStream_t stream) {
+             unsigned int* rowmax_bits, cudaStream_t stream, const PeerMirror* mirror) {
     if (k * cols == 0) return 0;
     NFB_CHECK(k <= 512, "n_components > 512 is not supported by the coordinate-descent kernel");
+    const PeerMirror mir = mirror ? *mirror : PeerMirror{};
     const int ldg = static_cast<int>(round_up64(k, 16));
     // blocked sweep: pick the sample tile that minimises waves x tile (one CTA per SM)
     {
@@ -339,7 +355,7 @@ int cd_sweep(float* f, int64_t k, int64_t cols, int64_t ld, const float* num, in
             NFB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
             kernel<<<static_cast<unsigned>(ceil_div64(cols, TJ)), NT, smem, stream>>>(
                 f, static_cast<int>(k), cols, ld, num, num_splits, num_stride, den, ld_part, gram, ldg, l1, l2,
-                violation, rowmax_bits, vec);
+                violation, rowmax_bits, vec, mir);
             NFB_CUDA(cudaGetLastError());
             return 0;
         };

@@ -60,6 +60,14 @@ struct GemmArgs {
     long long split_stride;  // elements between consecutive split slabs
     int num_stages;
     int b_tile_bytes;        // per plane, per CTA
+    // Fused reduce-scatter (row-sharded W'X, p2p.cu): row r of D (an H column) is stored straight into the inbox of
+    // the rank that owns it -- peer memory over NVLink -- instead of into `out`:
+    //   scatter_base[r / scatter_slice][(scatter_src * scatter_rows + col0 + col) * scatter_slice + r % scatter_slice]
+    int scatter_slice;       // H columns per rank (0: plain store into `out`)
+    int scatter_rows;        // k: component rows per source slab
+    int scatter_src;         // this rank
+    int scatter_col0;        // first component of this N slab
+    float* scatter_base[kGemmMaxPeers];
 };
 
 // 64-bit shared-memory matrix descriptor (sm_100 layout: version=1 at bit 46, SWIZZLE_128B = 2 at bit 61)
@@ -265,6 +273,13 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
             const long long m_row = static_cast<long long>(mb * kCtaGroup + static_cast<int>(cta_rank)) * kBlockM + row;
             if (m_row < args.m_total) {
                 float* outp = args.out + static_cast<long long>(ks) * args.split_stride + m_row;
+                if (args.scatter_slice > 0) {
+                    // the tile's rows may straddle two owners: every thread (= row) picks its own destination
+                    const int owner = static_cast<int>(m_row / args.scatter_slice);
+                    outp = args.scatter_base[owner] +
+                           static_cast<long long>(args.scatter_src * args.scatter_rows + args.scatter_col0) * args.scatter_slice +
+                           (m_row - static_cast<long long>(owner) * args.scatter_slice);
+                }
                 const float rs = args.row_scale ? __ldg(args.row_scale + m_row) * args.scale : args.scale;
 #pragma unroll
                 for (int c = 0; c < kNch; ++c) {
@@ -395,7 +410,7 @@ int gemm_pick_splits(int64_t m_total, int64_t k_total, int cta_group, int64_t n_
 static int gemm_split_tile(const GemmOperand& a, bool a_is_mn_major, const GemmOperand& b, int64_t m_total,
                            int64_t k_total, int n_umma, int n_store, float* out, int64_t ld_out,
                            long long split_stride, int splits, const float* col_scale, const float* row_scale,
-                           float scale, int cta_group, cudaStream_t stream) {
+                           float scale, int cta_group, cudaStream_t stream, const GemmScatter* scatter, int col0) {
     NFB_CHECK(n_umma % 16 == 0 && n_umma >= 16 && n_umma <= 256, "n_umma must be a multiple of 16 in [16,256]");
     NFB_CHECK(cta_group == 1 || cta_group == 2, "cta_group must be 1 or 2");
     NFB_CHECK(n_store <= n_umma, "n_store exceeds n_umma");
@@ -431,6 +446,19 @@ static int gemm_split_tile(const GemmOperand& a, bool a_is_mn_major, const GemmO
     args.m_blocks = static_cast<int>(ceil_div64(m_total, static_cast<int64_t>(kBlockM) * cta_group));
     args.ld_out = static_cast<int>(ld_out);
     args.split_stride = split_stride;
+    args.scatter_slice = 0;
+    args.scatter_rows = args.scatter_src = args.scatter_col0 = 0;
+    for (int p = 0; p < kGemmMaxPeers; ++p) args.scatter_base[p] = nullptr;
+    if (scatter != nullptr && scatter->slice > 0) {
+        NFB_CHECK(splits == 1, "the fused reduce-scatter epilogue needs an unsplit GEMM");
+        NFB_CHECK(ceil_div64(m_total, scatter->slice) <= kGemmMaxPeers, "more owners than peers in the scatter epilogue");
+        args.scatter_slice = static_cast<int>(scatter->slice);
+        args.scatter_rows = scatter->rows;
+        args.scatter_src = scatter->src;
+        args.scatter_col0 = col0;
+        args.ld_out = static_cast<int>(scatter->slice);
+        for (int p = 0; p < kGemmMaxPeers; ++p) args.scatter_base[p] = scatter->base[p];
+    }
     args.b_tile_bytes = n_load * 128;
     const int stage_bytes = 2 * kATileBytes + 2 * args.b_tile_bytes;
     const int smem_budget = 227 * 1024 - 1024 /*align*/ - 256 /*barriers*/;
@@ -454,7 +482,7 @@ static int gemm_split_tile(const GemmOperand& a, bool a_is_mn_major, const GemmO
 // N (the component dimension) is tiled in slabs of <= 256 columns: one launch per slab, each streaming A once.
 int gemm_split(const GemmOperand& a, bool a_is_mn_major, const GemmOperand& b, int64_t m_total, int64_t k_total,
                int n_umma, int n_store, float* out, int64_t ld_out, int splits, const float* col_scale,
-               const float* row_scale, float scale, int cta_group, cudaStream_t stream) {
+               const float* row_scale, float scale, int cta_group, cudaStream_t stream, const GemmScatter* scatter) {
     NFB_CHECK(n_umma % 16 == 0 && n_umma >= 16, "n_umma must be a positive multiple of 16");
     const long long split_stride = static_cast<long long>(n_store) * ld_out;
     // NFB_GEMM_TIMING=1: device time of every call (debug aid; synchronises the stream)
@@ -481,7 +509,7 @@ int gemm_split(const GemmOperand& a, bool a_is_mn_major, const GemmOperand& b, i
                        b.ld};
         NFB_TRY(gemm_split_tile(a, a_is_mn_major, bt, m_total, k_total, n_tile, std::min(n_tile, n_store - t0),
                                 out + static_cast<int64_t>(t0) * ld_out, ld_out, split_stride, splits,
-                                col_scale ? col_scale + t0 : nullptr, row_scale, scale, cta_group, stream));
+                                col_scale ? col_scale + t0 : nullptr, row_scale, scale, cta_group, stream, scatter, t0));
     }
     return 0;
 }

@@ -23,9 +23,20 @@ int gemm_pick_splits(int64_t m_total, int64_t k_total, int cta_group, int64_t n_
 //     = scale * col_scale[t] * row_scale[r] * sum_{K in split s} A[r,K] B[t,K]      (null scale vectors -> 1)
 //   a_is_mn_major == false : A planes are [m_total rows, K cols]     (X      for X H^T)
 //   a_is_mn_major == true  : A planes are [K rows, m_total cols]     (X read as X^T for W^T X)
+// scatter (nullable, unsplit launches only): the fused reduce-scatter epilogue of the row-sharded W'X -- row r of
+// the result (an H column) goes to  base[r / slice][(src * rows + t) * slice + r % slice]  (peer memory) instead of
+// out[t][r]
+constexpr int kGemmMaxPeers = 8;
+struct GemmScatter {
+    float* base[kGemmMaxPeers];
+    int64_t slice;     // H columns per rank
+    int rows;          // k: component rows per source slab of an inbox
+    int src;           // this rank
+};
 int gemm_split(const GemmOperand& a, bool a_is_mn_major, const GemmOperand& b, int64_t m_total, int64_t k_total,
                int n_umma, int n_store, float* out, int64_t ld_out, int splits, const float* col_scale,
-               const float* row_scale, float scale, int cta_group, cudaStream_t stream);
+               const float* row_scale, float scale, int cta_group, cudaStream_t stream,
+               const GemmScatter* scatter = nullptr);
 
 // ---- planes.cu ------------------------------------------------------------------------------------
 // max |x| over a [rows, cols] fp32 matrix (ld >= cols) -> *out_bits (float bits, must be zeroed first)
@@ -47,6 +58,12 @@ int split_factor(const float* f, int64_t k, int64_t cols, int64_t ld, const floa
                  const unsigned int* rowmax_bits, __half* hi, __half* lo, int64_t ldp, float* inv_scale,
                  cudaStream_t stream);
 
+// the same block of a factor matrix in the memory of up to 7 peers (pointers already offset like the local one)
+struct PeerMirror {
+    float* f[7];
+    int n;
+};
+
 // ---- update.cu ------------------------------------------------------------------------------------
 // out[t][j] = sum_s part[s][t][j] + bias     (t < k, j < cols)
 int reduce_partials(const float* part, int splits, int64_t split_stride, int64_t k, int64_t cols, int64_t ld,
@@ -57,16 +74,18 @@ int reduce_partials_sliced(const float* part, int splits, int64_t split_stride, 
 // multiplicative update of one factor (sklearn _multiplicative_update_w/_h, beta = 2):
 //   F[t][j] *= (sum_s num[s][t][j]) / den,  den = sum_s dpart[s][t][j] + l1 + l2 F[t][j], den == 0 -> eps
 // rowmax_bits[k] (zeroed by the caller) receives the new per-row maxima.
+// mirror (nullable): the same block of F in the memory of the other ranks of a row-sharded run; every value the
+// kernel writes is written there as well (the all-gather of the H slices, fused into the update).
 int mu_update(float* f, int64_t k, int64_t cols, int64_t ld, const float* num, int num_splits, int64_t num_stride,
               const float* den, int den_splits, int64_t den_stride, int64_t ld_part, float l1, float l2,
-              unsigned int* rowmax_bits, cudaStream_t stream);
+              unsigned int* rowmax_bits, cudaStream_t stream, const PeerMirror* mirror = nullptr);
 // one coordinate-descent sweep over all k components for every column j of F [k, cols]
 // (sklearn _cdnmf_fast.pyx with F = W^T):  num = sum_s part[s] - l1, G = gram (+ l2 on the diagonal).
 // violation (fp64, accumulated) and rowmax_bits as above.
 // den [k][ld_part] = G F from the tensor-core denominator GEMM seeds the per-column gradient.
 int cd_sweep(float* f, int64_t k, int64_t cols, int64_t ld, const float* num, int num_splits, int64_t num_stride,
              const float* den, int64_t ld_part, const float* gram, float l1, float l2, double* violation,
-             unsigned int* rowmax_bits, cudaStream_t stream);
+             unsigned int* rowmax_bits, cudaStream_t stream, const PeerMirror* mirror = nullptr);
 // *out += sum_{t<k, j<cols} a[t][j] * (sum_s b[s][t][j])        (fp64 accumulation)
 int dot_partials(const float* a, int64_t lda, const float* b, int splits, int64_t b_stride, int64_t ldb, int64_t k,
                  int64_t cols, double* out, cudaStream_t stream);
@@ -116,28 +135,31 @@ template <typename T>
 int comp_loadings(const T* a, const T* b, int64_t k, int64_t len, int64_t ld, double* out, cudaStream_t stream);
 
 // ---- p2p.cu ---------------------------------------------------------------------------------------
-// Row-sharded H half-step over NVLink peer memory (CUDA IPC mappings of every rank's arena and H master).
+// Row-sharded H half-step over NVLink peer memory (CUDA IPC mappings of every rank's arena and H master).  The bulk
+// data moves inside the compute kernels (GemmScatter in the W'X epilogue, PeerMirror in the sweep / update); these
+// are the small kernels around them.
 constexpr int kP2pMaxWorld = 8;
 constexpr int kP2pRsFlag = 0, kP2pAgFlag = 16, kP2pError = 32;   // int offsets into the arena header
 constexpr int64_t kP2pScalOffset = 256;                          // byte offset of double scal[16][2]
-constexpr int64_t kP2pGramOffset = 512;                          // byte offset of float gram[kp * kp]
+constexpr int64_t kP2pHeaderBytes = 512;
 struct P2pPeers {
     void* arena[kP2pMaxWorld];
     void* hmaster[kP2pMaxWorld];
 };
-// arena_p.flag[flag_offset + rank] = epoch on every rank p (system-scope release after a fence)
-int p2p_post(const P2pPeers& peers, int world, int rank, int flag_offset, int epoch, cudaStream_t stream);
-// wait for every rank's numerator of `epoch`; out[t][j] = sum_p arena_p.num[t][c0 + j] for j < width (0 up to ns),
-// gram_out = sum_p arena_p.gram.  arena num is [k][ld]; c0, ns, ld are multiples of 8.
-int p2p_pull(const P2pPeers& peers, int world, int rank, int epoch, int k, int64_t ns, int64_t ld, int64_t c0,
-             int64_t num_offset, int64_t gram_offset, int gram_elems, float* out, float* gram_out,
-             cudaStream_t stream);
-// own H columns [c0, c0 + width) -> every peer's H master; scal_src[2] (nullable) -> slot `rank` of every arena
-int p2p_push(const P2pPeers& peers, int world, int rank, int k, int64_t ld, int64_t c0, int64_t width,
-             const double* scal_src, int64_t scal_offset, cudaStream_t stream);
-// wait for every rank's slice of `epoch`; scal_out[i] (nullable) = sum_p scal[p][i]
+// scal_src[2] / rowmax_src[kp] (nullable) -> slot `rank` of every arena, then arena_p.flag[flag_offset + rank] =
+// epoch on every rank p (system-scope release after a fence)
+int p2p_post(const P2pPeers& peers, int world, int rank, int flag_offset, int epoch, cudaStream_t stream,
+             const double* scal_src = nullptr, int64_t scal_offset = 0, const unsigned int* rowmax_src = nullptr,
+             int64_t rowmax_offset = 0, int kp = 0);
+// this rank's Gram (slot `rank` of its gram_in at byte offset gram_offset) -> the same slot in every peer's arena
+int p2p_push_gram(const P2pPeers& peers, int world, int rank, int64_t gram_offset, int gram_elems, cudaStream_t stream);
+// wait for every rank's numerator of `epoch`; gram_out = sum_p gram_in[p]
+int p2p_wait_sum_gram(const P2pPeers& peers, int world, int rank, int epoch, int64_t gram_offset, int gram_elems,
+                      float* gram_out, cudaStream_t stream);
+// wait for every rank's slice of `epoch`; scal_out[i] (nullable) = sum_p scal[p][i]; rowmax_out[t] (nullable) =
+// max_p rowmax_in[p][t]
 int p2p_gather_wait(const P2pPeers& peers, int world, int rank, int epoch, int64_t scal_offset, double* scal_out,
-                    cudaStream_t stream);
+                    int64_t rowmax_offset, int kp, unsigned int* rowmax_out, cudaStream_t stream);
 
 // ---- ingest.cu ------------------------------------------------------------------------------------
 // phase A: tmp[r*ncols+c] += v for every triplet with row in [row0, row0+nrows_blk)  (fp64 atomics)

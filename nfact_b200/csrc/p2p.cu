@@ -1,24 +1,29 @@
 // Row-sharded H half-step over NVLink peer memory (one process per GPU, CUDA IPC mappings).
 //
 // Every rank owns an "arena" (one cudaMalloc, mapped into all peers):
-//     int    rs_flag[16]      rs_flag[p] = last epoch for which rank p's local numerator is complete
-//     int    ag_flag[16]      ag_flag[p] = last epoch for which rank p's H slice (and scalars) have landed HERE
-//     int    error            a wait timed out (peer died): results are garbage, the host raises
-//     double scal[16][2]      scal[p] = rank p's local (violation_W, violation_H) / error cross term, pushed with the slice
-//     float  gram[kp * kp]    this rank's local W'W
-//     float  num[k][ld]       this rank's local W'X (the GEMM writes it here directly when it runs unsplit);
-//                             rank r needs columns [r ns, (r + 1) ns) of every rank's copy
-// and its H master [kp][ld] is mapped into all peers as well.
+//     int    rs_flag[16]        rs_flag[p] = last epoch for which rank p's numerator tiles and Gram have landed HERE
+//     int    ag_flag[16]        ag_flag[p] = last epoch for which rank p's H slice (and scalars) have landed HERE
+//     int    error              a wait timed out (peer died): results are garbage, the host raises
+//     double scal[16][2]        scal[p] = rank p's local (violation_W, violation_H), posted with its H slice
+//     float  gram_in[P][kp*kp]  gram_in[p] = rank p's local W'W
+//     uint   rowmax_in[P][kp]   rowmax_in[p] = per-component maxima of rank p's H slice (bit patterns)
+//     float  num_in[P][k][ns]   num_in[p] = rank p's local W'X restricted to MY H columns [rank ns, (rank+1) ns)
+// and its H master [kp][ld] is mapped into all peers as well.  Nothing here is a separate "collective" pass:
 //
-//   reduce-scatter  : rank r PULLS its column slice of num from every arena (7 remote reads + 1 local per element, summed in rank
-//                     order -> deterministic) and the k x k Gram from every arena, instead of ncclReduceScatter +
-//                     ncclAllReduce; the kernel first spins (on local memory) until every peer has posted its epoch.
-//   all-gather      : after the sweep, rank r PUSHES its H columns straight into every peer's H master (no pack /
-//                     unpack copies) together with its two fp64 scalars, then posts ag_flag; a one-CTA kernel waits
-//                     for all peers and sums the scalars in rank order.
+//   reduce-scatter  : the W'X GEMM's epilogue stores every finished tile straight into the inbox (num_in[rank]) of
+//                     the rank that owns those H columns (gemm_split.cu, GemmScatter) -- remote stores over NVLink
+//                     that overlap the mainloop of the following tiles; the consumer (sweep / multiplicative update)
+//                     reads the P slabs as split-K partials, summed in rank order -> deterministic.  The k x k Gram
+//                     is pushed to every peer by a small kernel before the GEMM.  After the GEMM a one-CTA kernel
+//                     posts rs_flag; the owner waits for all P flags and sums the P Grams.
+//   all-gather      : the sweep / update kernel writes every H value it changes into all peers' H masters as part
+//                     of its own write-back (cd_sweep.cu / update.cu, PeerMirror); the post kernel adds this rank's
+//                     two float64 scalars and per-component maxima and raises ag_flag; a one-CTA kernel waits for
+//                     all peers, sums the scalars in rank order and takes the maxima (the plane split of the
+//                     gathered H then needs no pass of its own to find them).
 // Epochs only grow, flags are never reset.  Buffer reuse is safe because each phase is fenced by the other one:
 // nobody can start epoch e+1's numerator before having passed the all-gather of epoch e, which needs my post,
-// which I issue after my pull of epoch e (and symmetrically for the H master).
+// which I issue after my sweep of epoch e has read its inbox (and symmetrically for the H master).
 #include "common.cuh"
 #include "kernels.h"
 
@@ -66,80 +71,61 @@ __device__ __forceinline__ void wait_all(const P2pPeers& peers, int world, int r
     __syncthreads();
 }
 
-__global__ void p2p_post_kernel(P2pPeers peers, int world, int rank, int flag_offset, int epoch) {
-    __threadfence_system();   // the producing kernels ran before this one on the same stream
+// payloads (nullable) -> slot `rank` of every peer's arena, then fence + flag[rank] = epoch everywhere
+__global__ void __launch_bounds__(256)
+p2p_post_kernel(P2pPeers peers, int world, int rank, int flag_offset, int epoch, const double* __restrict__ scal_src,
+                int64_t scal_offset, const unsigned int* __restrict__ rowmax_src, int64_t rowmax_offset, int kp) {
+    if (scal_src != nullptr && threadIdx.x < 2 * world) {
+        const int p = threadIdx.x / 2, i = threadIdx.x & 1;
+        double* dst = reinterpret_cast<double*>(reinterpret_cast<char*>(peers.arena[p]) + scal_offset) + 2 * rank + i;
+        *dst = scal_src[i];
+    }
+    if (rowmax_src != nullptr) {
+        for (int e = threadIdx.x; e < world * kp; e += blockDim.x) {
+            const int p = e / kp, t = e - p * kp;
+            unsigned int* dst = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(peers.arena[p]) + rowmax_offset);
+            dst[static_cast<int64_t>(rank) * kp + t] = rowmax_src[t];
+        }
+    }
+    __threadfence_system();   // the payload above and whatever the producing kernels stored before this one
+    __syncthreads();
     if (threadIdx.x < world)
         st_release_sys(reinterpret_cast<int*>(peers.arena[threadIdx.x]) + flag_offset + rank, epoch);
 }
 
-// out[t][j] = sum_p arena_p.num[t][c0 + j]   (t < k, j < ns; 0 past the matrix);  gram_out = sum_p arena_p.gram
+// this rank's Gram (slot `rank` of its own gram_in) -> slot `rank` of every peer's gram_in
 __global__ void __launch_bounds__(256)
-p2p_pull_kernel(P2pPeers peers, int world, int rank, int epoch, int k, int64_t ns, int64_t ld, int64_t c0,
-                int64_t num_offset, int64_t gram_offset, int gram_elems, float* __restrict__ out,
-                float* __restrict__ gram_out) {
-    wait_all(peers, world, rank, kP2pRsFlag, epoch);
-    const int64_t w4 = ns / 4;                                        // ns % 8 == 0
-    const int64_t valid4 = max(static_cast<int64_t>(0), min(ns, ld - c0)) / 4;   // ld % 8 == 0, c0 % 8 == 0
-    const int64_t vecs = static_cast<int64_t>(k) * w4;
-    const int64_t tid = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-    const int64_t nthreads = static_cast<int64_t>(gridDim.x) * blockDim.x;
-    for (int64_t v = tid; v < vecs; v += nthreads) {
-        const int64_t t = v / w4, j4 = v - t * w4;
-        float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        if (j4 < valid4) {
-            float4 part[kP2pMaxWorld];
-            const int64_t off = num_offset + t * ld + c0 + 4 * j4;
+p2p_push_gram_kernel(P2pPeers peers, int world, int rank, int64_t gram_offset, int gram_elems) {
+    const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const char*>(peers.arena[rank]) + gram_offset) +
+                        static_cast<int64_t>(rank) * (gram_elems / 4);
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < gram_elems / 4; e += gridDim.x * blockDim.x) {
+        const float4 v = src[e];
 #pragma unroll
-            for (int p = 0; p < kP2pMaxWorld; ++p)
-                if (p < world) part[p] = ld_peer4(reinterpret_cast<const float*>(peers.arena[p]) + off);
-#pragma unroll
-            for (int p = 0; p < kP2pMaxWorld; ++p)
-                if (p < world) { acc.x += part[p].x; acc.y += part[p].y; acc.z += part[p].z; acc.w += part[p].w; }
-        }
-        reinterpret_cast<float4*>(out)[v] = acc;
+        for (int p = 0; p < kP2pMaxWorld; ++p)
+            if (p < world && p != rank)
+                (reinterpret_cast<float4*>(reinterpret_cast<char*>(peers.arena[p]) + gram_offset) +
+                 static_cast<int64_t>(rank) * (gram_elems / 4))[e] = v;
     }
-    for (int64_t e = tid; e < gram_elems; e += nthreads) {
+}
+
+// wait for every rank's numerator tiles + Gram of `epoch`; gram_out = sum_p gram_in[p] (rank order)
+__global__ void __launch_bounds__(256)
+p2p_wait_sum_gram_kernel(P2pPeers peers, int world, int rank, int epoch, int64_t gram_offset, int gram_elems,
+                         float* __restrict__ gram_out) {
+    wait_all(peers, world, rank, kP2pRsFlag, epoch);
+    const float* in = reinterpret_cast<const float*>(reinterpret_cast<const char*>(peers.arena[rank]) + gram_offset);
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < gram_elems; e += gridDim.x * blockDim.x) {
         float acc = 0.0f;
-        for (int p = 0; p < world; ++p) acc += ld_peer(reinterpret_cast<const float*>(peers.arena[p]) + gram_offset + e);
+        for (int p = 0; p < world; ++p) acc += ld_peer(in + static_cast<int64_t>(p) * gram_elems + e);
         gram_out[e] = acc;
     }
 }
 
-// H[t][c0 + j] (t < k, j < width) -> the same place in every peer's H master; scal[2] -> slot `rank` of every arena
+// wait for every peer's slice, then scal_out[i] = sum_p scal[p][i] in rank order, rowmax_out[t] = max_p rowmax_in[p][t]
 __global__ void __launch_bounds__(256)
-p2p_push_kernel(P2pPeers peers, int world, int rank, int k, int64_t ld, int64_t c0, int64_t width,
-                const double* __restrict__ scal_src, int64_t scal_offset) {
-    const float* src = reinterpret_cast<const float*>(peers.hmaster[rank]);
-    const int64_t tid = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-    const int64_t nthreads = static_cast<int64_t>(gridDim.x) * blockDim.x;
-    const int64_t w4 = width / 4;     // c0 % 8 == 0 and ld % 8 == 0: rows start 16-byte aligned
-    for (int64_t e = tid; e < static_cast<int64_t>(k) * w4; e += nthreads) {
-        const int64_t t = e / w4, j = (e - t * w4) * 4;
-        const int64_t off = t * ld + c0 + j;
-        const float4 v = *reinterpret_cast<const float4*>(src + off);
-#pragma unroll
-        for (int p = 0; p < kP2pMaxWorld; ++p)
-            if (p < world && p != rank) *reinterpret_cast<float4*>(reinterpret_cast<float*>(peers.hmaster[p]) + off) = v;
-    }
-    const int64_t tail = width - 4 * w4;
-    for (int64_t e = tid; e < static_cast<int64_t>(k) * tail; e += nthreads) {
-        const int64_t t = e / tail, j = 4 * w4 + (e - t * tail);
-        const int64_t off = t * ld + c0 + j;
-        const float v = src[off];
-        for (int p = 0; p < world; ++p)
-            if (p != rank) reinterpret_cast<float*>(peers.hmaster[p])[off] = v;
-    }
-    if (tid < 2 * world) {
-        const int p = static_cast<int>(tid) / 2, i = static_cast<int>(tid) & 1;
-        double* dst = reinterpret_cast<double*>(reinterpret_cast<char*>(peers.arena[p]) + scal_offset) + 2 * rank + i;
-        *dst = scal_src != nullptr ? scal_src[i] : 0.0;
-    }
-    __threadfence_system();
-}
-
-// wait for every peer's slice, then scal_out[i] = sum_p scal[p][i] in rank order
-__global__ void p2p_gather_wait_kernel(P2pPeers peers, int world, int rank, int epoch, int64_t scal_offset,
-                                       double* __restrict__ scal_out) {
+p2p_gather_wait_kernel(P2pPeers peers, int world, int rank, int epoch, int64_t scal_offset,
+                       double* __restrict__ scal_out, int64_t rowmax_offset, int kp,
+                       unsigned int* __restrict__ rowmax_out) {
     wait_all(peers, world, rank, kP2pAgFlag, epoch);
     if (threadIdx.x < 2 && scal_out != nullptr) {
         const volatile double* scal =
@@ -151,39 +137,49 @@ __global__ void p2p_gather_wait_kernel(P2pPeers peers, int world, int rank, int 
         if (ld_acquire_sys(reinterpret_cast<int*>(peers.arena[rank]) + kP2pError) != 0) acc = __longlong_as_double(0x7ff8000000000000LL);
         scal_out[threadIdx.x] = acc;
     }
+    if (rowmax_out != nullptr) {
+        const volatile unsigned int* in =
+            reinterpret_cast<const volatile unsigned int*>(reinterpret_cast<char*>(peers.arena[rank]) + rowmax_offset);
+        for (int t = threadIdx.x; t < kp; t += blockDim.x) {
+            unsigned int m = 0u;
+            for (int p = 0; p < world; ++p) m = max(m, in[static_cast<int64_t>(p) * kp + t]);   // values >= 0: uint order
+            rowmax_out[t] = m;
+        }
+    }
 }
 
 }  // namespace
 
-int p2p_post(const P2pPeers& peers, int world, int rank, int flag_offset, int epoch, cudaStream_t stream) {
-    p2p_post_kernel<<<1, 32, 0, stream>>>(peers, world, rank, flag_offset, epoch);
+int p2p_post(const P2pPeers& peers, int world, int rank, int flag_offset, int epoch, cudaStream_t stream,
+             const double* scal_src, int64_t scal_offset, const unsigned int* rowmax_src, int64_t rowmax_offset,
+             int kp) {
+    p2p_post_kernel<<<1, 256, 0, stream>>>(peers, world, rank, flag_offset, epoch, scal_src, scal_offset, rowmax_src,
+                                           rowmax_offset, kp);
     NFB_CUDA(cudaGetLastError());
     return 0;
 }
 
-int p2p_pull(const P2pPeers& peers, int world, int rank, int epoch, int k, int64_t ns, int64_t ld, int64_t c0,
-             int64_t num_offset, int64_t gram_offset, int gram_elems, float* out, float* gram_out,
-             cudaStream_t stream) {
-    const int64_t vecs = static_cast<int64_t>(k) * ns / 4;
-    const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(ceil_div64(vecs, 256), 4 * sm_count())));
-    p2p_pull_kernel<<<grid, 256, 0, stream>>>(peers, world, rank, epoch, k, ns, ld, c0, num_offset, gram_offset,
-                                              gram_elems, out, gram_out);
+int p2p_push_gram(const P2pPeers& peers, int world, int rank, int64_t gram_offset, int gram_elems,
+                  cudaStream_t stream) {
+    NFB_CHECK(gram_elems % 4 == 0, "Gram size must be a multiple of 4 floats");
+    const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(ceil_div64(gram_elems / 4, 256), sm_count())));
+    p2p_push_gram_kernel<<<grid, 256, 0, stream>>>(peers, world, rank, gram_offset, gram_elems);
     NFB_CUDA(cudaGetLastError());
     return 0;
 }
 
-int p2p_push(const P2pPeers& peers, int world, int rank, int k, int64_t ld, int64_t c0, int64_t width,
-             const double* scal_src, int64_t scal_offset, cudaStream_t stream) {
-    const int64_t vecs = std::max<int64_t>(1, static_cast<int64_t>(k) * (width / 4 + 1));
-    const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(ceil_div64(vecs, 256), 4 * sm_count())));
-    p2p_push_kernel<<<grid, 256, 0, stream>>>(peers, world, rank, k, ld, c0, width, scal_src, scal_offset);
+int p2p_wait_sum_gram(const P2pPeers& peers, int world, int rank, int epoch, int64_t gram_offset, int gram_elems,
+                      float* gram_out, cudaStream_t stream) {
+    const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(ceil_div64(gram_elems, 256), sm_count())));
+    p2p_wait_sum_gram_kernel<<<grid, 256, 0, stream>>>(peers, world, rank, epoch, gram_offset, gram_elems, gram_out);
     NFB_CUDA(cudaGetLastError());
     return 0;
 }
 
 int p2p_gather_wait(const P2pPeers& peers, int world, int rank, int epoch, int64_t scal_offset, double* scal_out,
-                    cudaStream_t stream) {
-    p2p_gather_wait_kernel<<<1, 32, 0, stream>>>(peers, world, rank, epoch, scal_offset, scal_out);
+                    int64_t rowmax_offset, int kp, unsigned int* rowmax_out, cudaStream_t stream) {
+    p2p_gather_wait_kernel<<<1, 256, 0, stream>>>(peers, world, rank, epoch, scal_offset, scal_out, rowmax_offset, kp,
+                                                  rowmax_out);
     NFB_CUDA(cudaGetLastError());
     return 0;
 }

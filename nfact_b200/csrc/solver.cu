@@ -208,9 +208,19 @@ struct nfb_nmf {
     P2pPeers peers{};
     std::vector<void*> ipc_opened;
     int epoch = 0;
-    int64_t arena_num_off = 0;    // float offset of num[k][ld] inside the arena
-    float* arena_num() const { return reinterpret_cast<float*>(arena.p) + arena_num_off; }
-    float* arena_gram() const { return reinterpret_cast<float*>(arena.p + kP2pGramOffset); }
+    // byte offsets inside the arena (p2p.cu): gram_in[P][kp*kp], rowmax_in[P][kp], num_in[P][k][ns]
+    int64_t arena_gram_off = 0, arena_rowmax_off = 0, arena_num_off = 0;
+    float* arena_num() const { return reinterpret_cast<float*>(arena.p + arena_num_off); }
+    float* arena_gram() const {       // this rank's own slot of gram_in
+        return reinterpret_cast<float*>(arena.p + arena_gram_off) + static_cast<int64_t>(h->rank) * kp * kp;
+    }
+    PeerMirror h_mirror(int64_t col0) const {   // the H columns from col0 on in every OTHER rank's H master
+        PeerMirror mir{};
+        if (!p2p) return mir;
+        for (int r = 0; r < h->world; ++r)
+            if (r != h->rank) mir.f[mir.n++] = static_cast<float*>(peers.hmaster[r]) + col0;
+        return mir;
+    }
     int s_w = 1, s_h = 1, s_gw = 1, s_gh = 1;
     double sumsq_global = 0.0;
     bool p1_valid = false;  // part_w holds X H' for the current H
@@ -328,37 +338,46 @@ struct HNumerator {
 
 static int gemm_wtx(nfb_nmf* s, HNumerator* out) {
     nfb_handle* h = s->h;
-    // peer-memory path, unsplit GEMM: the epilogue writes the local numerator straight into the arena
-    const bool direct = s->p2p && s->s_h == 1;
+    const int64_t n = s->x->n;
+    if (s->p2p) {
+        // Peer-memory path: the k x k Gram goes to every peer first (small), then the unsplit GEMM whose epilogue
+        // stores each finished tile into the inbox of the rank that owns those H columns -- the reduce-scatter
+        // happens inside the GEMM, tile by tile, over NVLink.  Then: post, wait for everybody, sum the Grams.
+        const int64_t ns = s->slice_cols;
+        const int gram_elems = static_cast<int>(s->kp * s->kp);
+        NFB_TRY(p2p_push_gram(s->peers, h->world, h->rank, s->arena_gram_off, gram_elems, h->stream));
+        GemmScatter sc{};
+        for (int r = 0; r < h->world; ++r)
+            sc.base[r] = reinterpret_cast<float*>(static_cast<char*>(s->peers.arena[r]) + s->arena_num_off);
+        sc.slice = ns;
+        sc.rows = s->k;
+        sc.src = h->rank;
+        {
+        GemmTimer timer(h);
+        NFB_TRY(gemm_split(s->x->operand(), true, s->wt.operand(), n, s->x->m, static_cast<int>(s->kp), s->k,
+                           s->arena_num(), ns, 1, s->wt.inv_scale.p, nullptr, s->x->inv_scale_host, h->cta_group,
+                           h->stream, &sc));
+        }
+        ++s->epoch;
+        NFB_PHASE(h, "rs_wait");
+        NFB_TRY(p2p_post(s->peers, h->world, h->rank, kP2pRsFlag, s->epoch, h->stream));
+        NFB_TRY(p2p_wait_sum_gram(s->peers, h->world, h->rank, s->epoch, s->arena_gram_off, gram_elems, s->gw.f.p,
+                                  h->stream));
+        note_launch(4);
+        const int64_t c0 = std::min<int64_t>(n, h->rank * ns);
+        // the P inbox slabs are the split-K partials of this rank's columns: the consumer sums them in rank order
+        *out = HNumerator{s->arena_num(), h->world, static_cast<int64_t>(s->k) * ns, ns, c0, std::min<int64_t>(ns, n - c0)};
+        return 0;
+    }
     {
     GemmTimer timer(h);
     NFB_TRY(gemm_split(s->x->operand(), true, s->wt.operand(), s->x->n, s->x->m, static_cast<int>(s->kp), s->k,
-                       direct ? s->arena_num() : s->part_h.p, s->hh.ld, s->s_h, s->wt.inv_scale.p, nullptr,
-                       s->x->inv_scale_host, h->cta_group, h->stream));
+                       s->part_h.p, s->hh.ld, s->s_h, s->wt.inv_scale.p, nullptr, s->x->inv_scale_host, h->cta_group,
+                       h->stream));
     }
     note_launch(1);
-    const int64_t n = s->x->n;
     if (h->world <= 1) {
         *out = HNumerator{s->part_h.p, s->s_h, static_cast<int64_t>(s->k) * s->hh.ld, s->hh.ld, 0, n};
-        return 0;
-    }
-    if (s->p2p) {
-        // (split-K sum into the peer-visible arena,) post, then pull this rank's column slice from everybody
-        const int64_t ns = s->slice_cols;
-        if (!direct) {
-            NFB_PHASE(h, "rs_local");
-            NFB_TRY(reduce_partials(s->part_h.p, s->s_h, static_cast<int64_t>(s->k) * s->hh.ld, s->k, n, s->hh.ld, 0.0f,
-                                    s->arena_num(), s->hh.ld, h->stream));
-            note_launch(1);
-        }
-        ++s->epoch;
-        NFB_PHASE(h, "rs_pull");
-        const int64_t c0 = std::min<int64_t>(n, h->rank * ns);
-        NFB_TRY(p2p_post(s->peers, h->world, h->rank, kP2pRsFlag, s->epoch, h->stream));
-        NFB_TRY(p2p_pull(s->peers, h->world, h->rank, s->epoch, s->k, ns, s->hh.ld, h->rank * ns, s->arena_num_off,
-                         kP2pGramOffset / 4, static_cast<int>(s->kp * s->kp), s->num_h.p, s->gw.f.p, h->stream));
-        note_launch(2);
-        *out = HNumerator{s->num_h.p, 1, 0, ns, c0, std::min<int64_t>(ns, n - c0)};
         return 0;
     }
     if (h->reduce_scatter != nullptr && h->all_gather != nullptr) {
@@ -388,14 +407,15 @@ static int gather_h_slices(nfb_nmf* s, const HNumerator& hn) {
     if (!s->h_sliced) return 0;
     const int64_t ns = s->slice_cols, n = s->x->n;
     if (s->p2p) {
-        // CD: the two violation partial sums travel with the slice and come back summed over ranks
+        // the slice itself travelled inside the sweep / update kernel (PeerMirror); what is left is this rank's two
+        // violation partial sums (CD) and the per-component maxima of its slice, the flag, and the wait
         double* scal = s->p.solver == 0 ? h->d_scal.p + 2 : nullptr;
-        NFB_PHASE(h, "ag_push");
-        NFB_TRY(p2p_push(s->peers, h->world, h->rank, s->k, s->hh.ld, hn.col0, std::max<int64_t>(hn.width, 0), scal,
-                         kP2pScalOffset, h->stream));
-        NFB_TRY(p2p_post(s->peers, h->world, h->rank, kP2pAgFlag, s->epoch, h->stream));
-        NFB_TRY(p2p_gather_wait(s->peers, h->world, h->rank, s->epoch, kP2pScalOffset, scal, h->stream));
-        note_launch(3);
+        NFB_PHASE(h, "ag_wait");
+        NFB_TRY(p2p_post(s->peers, h->world, h->rank, kP2pAgFlag, s->epoch, h->stream, scal, kP2pScalOffset,
+                         s->hh.rowmax.p, s->arena_rowmax_off, static_cast<int>(s->kp)));
+        NFB_TRY(p2p_gather_wait(s->peers, h->world, h->rank, s->epoch, kP2pScalOffset, scal, s->arena_rowmax_off,
+                                static_cast<int>(s->kp), s->hh.rowmax.p, h->stream));
+        note_launch(2);
         return 0;
     }
     if (hn.width > 0)
@@ -433,7 +453,7 @@ static int finish_h(nfb_nmf* s, const HNumerator& hn) {
     nfb_handle* h = s->h;
     const bool sliced = s->h_sliced;
     NFB_TRY(gather_h_slices(s, hn));
-    NFB_TRY(refresh_planes(s->hh, s->hh.f.p, nullptr, sliced, h->stream));
+    NFB_TRY(refresh_planes(s->hh, s->hh.f.p, nullptr, sliced && !s->p2p, h->stream));   // p2p: maxima came with the gather
     NFB_TRY(compute_gram(s, s->hh, s->gh, s->s_gh, false));
     return 0;
 }
@@ -461,9 +481,10 @@ static int mu_iteration(nfb_nmf* s) {
     NFB_CUDA(cudaMemsetAsync(s->hh.rowmax.p, 0, sizeof(unsigned int) * s->kp, h->stream));
     if (hn.width > 0) {
         NFB_PHASE(h, "update_h");
+        const PeerMirror mir = s->h_mirror(hn.col0);
         NFB_TRY(mu_update(s->hh.f.p + hn.col0, s->k, hn.width, s->hh.ld, hn.num, hn.splits, hn.stride, s->part_den.p,
                           1, 0, hn.ld_part, static_cast<float>(p.l1_reg_H), static_cast<float>(p.l2_reg_H),
-                          s->hh.rowmax.p, h->stream));
+                          s->hh.rowmax.p, h->stream, &mir));
         note_launch(1);
     }
     { NFB_PHASE(h, "finish_h"); NFB_TRY(finish_h(s, hn)); }
@@ -497,9 +518,10 @@ static int cd_iteration(nfb_nmf* s, double* violation_out, double* host_slot = n
     NFB_CUDA(cudaMemsetAsync(s->hh.rowmax.p, 0, sizeof(unsigned int) * s->kp, h->stream));
     if (hn.width > 0) {
         NFB_PHASE(h, "update_h");
+        const PeerMirror mir = s->h_mirror(hn.col0);
         NFB_TRY(cd_sweep(s->hh.f.p + hn.col0, s->k, hn.width, s->hh.ld, hn.num, hn.splits, hn.stride, s->part_den.p,
                          hn.ld_part, s->gw.f.p, static_cast<float>(p.l1_reg_H), static_cast<float>(p.l2_reg_H),
-                         h->d_scal.p + 3, s->hh.rowmax.p, h->stream));
+                         h->d_scal.p + 3, s->hh.rowmax.p, h->stream, &mir));
         note_launch(1);
     }
     { NFB_PHASE(h, "finish_h"); NFB_TRY(finish_h(s, hn)); }
@@ -554,9 +576,11 @@ static int p2p_setup(nfb_nmf* s) {
     cudaStream_t st = h->stream;
     const char* env = getenv("NFB_P2P");
     const bool want = h->world <= kP2pMaxWorld && h->all_gather != nullptr && !(env != nullptr && atoi(env) == 0);
-    const int64_t gram_bytes = round_up64(s->kp * s->kp * 4, 256);
-    s->arena_num_off = (kP2pGramOffset + gram_bytes) / 4;
-    const size_t arena_bytes = static_cast<size_t>(s->arena_num_off) * 4 + sizeof(float) * s->k * s->hh.ld;
+    s->arena_gram_off = kP2pHeaderBytes;
+    s->arena_rowmax_off = s->arena_gram_off + round_up64(static_cast<int64_t>(h->world) * s->kp * s->kp * 4, 256);
+    s->arena_num_off = s->arena_rowmax_off + round_up64(static_cast<int64_t>(h->world) * s->kp * 4, 256);
+    const size_t arena_bytes = static_cast<size_t>(s->arena_num_off) +
+                               sizeof(float) * static_cast<size_t>(h->world) * s->k * s->slice_cols;
     int failed = want ? 0 : 1;
     cudaIpcMemHandle_t mine[2];
     memset(mine, 0, sizeof(mine));
@@ -912,7 +936,8 @@ int nfb_nmf_create(nfb_handle* h, const nfb_matrix* x, int k, const nfb_nmf_para
     NFB_TRY(s->gd.init(k, k, false, st, s->kp));
     const int cg = h->cta_group;
     s->s_w = gemm_pick_splits(x->m, x->n, cg, k);
-    s->s_h = gemm_pick_splits(x->n, x->m, cg, k);
+    // row-sharded: W'X runs unsplit (its tiles go straight to their owners' inboxes on the peer-memory path)
+    s->s_h = h->world > 1 ? 1 : gemm_pick_splits(x->n, x->m, cg, k);
     s->s_gw = gemm_pick_splits(k, x->m, cg, k);
     s->s_gh = gemm_pick_splits(k, x->n, cg, k);
     NFB_TRY(s->part_w.alloc(static_cast<size_t>(s->s_w) * k * s->wt.ld, false, st));

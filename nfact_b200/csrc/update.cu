@@ -49,7 +49,7 @@ __device__ __forceinline__ float mu_one(float old, float numerator, float denomi
 __global__ void mu_update_kernel(float* __restrict__ f, int64_t cols, int64_t ld, const float* __restrict__ num,
                                  int num_splits, int64_t num_stride, const float* __restrict__ den, int den_splits,
                                  int64_t den_stride, int64_t ld_part, float l1, float l2,
-                                 unsigned int* __restrict__ rowmax_bits) {
+                                 unsigned int* __restrict__ rowmax_bits, const PeerMirror mirror) {
     const int64_t t = blockIdx.y;
     float vmax = 0.0f;
     const int64_t groups = (cols + 3) / 4;
@@ -72,6 +72,10 @@ __global__ void mu_update_kernel(float* __restrict__ f, int64_t cols, int64_t ld
         cur.z = (j + 2 < cols) ? mu_one(cur.z, numerator.z, denominator.z, l1, l2) : 0.0f;
         cur.w = (j + 3 < cols) ? mu_one(cur.w, numerator.w, denominator.w, l1, l2) : 0.0f;
         *reinterpret_cast<float4*>(f + t * ld + j) = cur;
+        // row-sharded runs: the updated H columns go straight into every peer's copy (the all-gather, fused)
+#pragma unroll
+        for (int p = 0; p < kGemmMaxPeers - 1; ++p)
+            if (p < mirror.n) *reinterpret_cast<float4*>(mirror.f[p] + t * ld + j) = cur;
         vmax = fmaxf(fmaxf(vmax, fmaxf(fabsf(cur.x), fabsf(cur.y))), fmaxf(fabsf(cur.z), fabsf(cur.w)));
     }
     vmax = warp_max(vmax);
@@ -240,10 +244,12 @@ int reduce_partials_sliced(const float* part, int splits, int64_t split_stride, 
 
 int mu_update(float* f, int64_t k, int64_t cols, int64_t ld, const float* num, int num_splits, int64_t num_stride,
               const float* den, int den_splits, int64_t den_stride, int64_t ld_part, float l1, float l2,
-              unsigned int* rowmax_bits, cudaStream_t stream) {
+              unsigned int* rowmax_bits, cudaStream_t stream, const PeerMirror* mirror) {
     if (k * cols == 0) return 0;
+    PeerMirror none{};
     mu_update_kernel<<<dim3(col_blocks(cols, 256 * 4, 1024), static_cast<unsigned>(k)), 256, 0, stream>>>(
-        f, cols, ld, num, num_splits, num_stride, den, den_splits, den_stride, ld_part, l1, l2, rowmax_bits);
+        f, cols, ld, num, num_splits, num_stride, den, den_splits, den_stride, ld_part, l1, l2, rowmax_bits,
+        mirror ? *mirror : none);
     NFB_CUDA(cudaGetLastError());
     return 0;
 }
