@@ -68,7 +68,26 @@ struct GemmArgs {
     int scatter_src;         // this rank
     int scatter_col0;        // first component of this N slab
     float* scatter_base[kGemmMaxPeers];
+    // Tile order of the scatter epilogue.  In natural order the 74 tiles that run side by side cover ~1.4 owners,
+    // and they do so on every rank at once: all ranks store into the same one or two inboxes (incast on one
+    // NVLink ingress port while the other seven idle).  With perm_groups = P the M blocks are dealt out round-robin
+    // over P contiguous groups of perm_bpo blocks (about one owner each), starting at group perm_rot, so that at
+    // any time every rank's stores are spread evenly over all owners.  0: natural order.
+    int perm_groups, perm_bpo, perm_rot;
+    int num_tiles;           // tiles to walk (m_blocks * splits, or perm_groups * perm_bpo: some are empty)
 };
+
+// tile index -> (K split, M block); false for the empty tiles of the permuted order
+__device__ __forceinline__ bool map_tile(const GemmArgs& args, int tile, int& ks, int& mb) {
+    if (args.perm_groups > 0) {
+        ks = 0;
+        mb = ((tile % args.perm_groups + args.perm_rot) % args.perm_groups) * args.perm_bpo + tile / args.perm_groups;
+        return mb < args.m_blocks;
+    }
+    ks = tile / args.m_blocks;
+    mb = tile % args.m_blocks;
+    return true;
+}
 
 // 64-bit shared-memory matrix descriptor (sm_100 layout: version=1 at bit 46, SWIZZLE_128B = 2 at bit 61)
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -140,7 +159,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
-    const int num_tiles = args.m_blocks * args.splits;
+    const int num_tiles = args.num_tiles;
     const int num_workers = gridDim.x / kCtaGroup;
     const int worker = blockIdx.x / kCtaGroup;
     const int n_load = args.n_umma / kCtaGroup;  // rows of B staged by this CTA
@@ -154,7 +173,8 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
       if (lane_idx == 0) {
         // =========================== TMA producer ===============================================
         for (int tile = worker; tile < num_tiles; tile += num_workers) {
-            const int ks = tile / args.m_blocks, mb = tile % args.m_blocks;
+            int ks, mb;
+            if (!map_tile(args, tile, ks, mb)) continue;
             const int kb0 = static_cast<int>(static_cast<long long>(ks) * args.num_kb / args.splits);
             const int kb1 = static_cast<int>(static_cast<long long>(ks + 1) * args.num_kb / args.splits);
             const int m_idx = (mb * kCtaGroup + static_cast<int>(cta_rank)) * kBlockM;
@@ -199,7 +219,8 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
         const uint32_t a_kstep = kAMajorMN ? kUmmaK * 128 : kUmmaK * 2;
         uint32_t chain = 0;  // running index of TMEM accumulation chains (stage = chain & 1)
         for (int tile = worker; tile < num_tiles; tile += num_workers) {
-            const int ks = tile / args.m_blocks;
+            int ks, mb;
+            if (!map_tile(args, tile, ks, mb)) continue;
             const int kb0 = static_cast<int>(static_cast<long long>(ks) * args.num_kb / args.splits);
             const int kb1 = static_cast<int>(static_cast<long long>(ks + 1) * args.num_kb / args.splits);
             for (int kc0 = kb0; kc0 < kb1; kc0 += kChunkKB, ++chain) {
@@ -245,7 +266,8 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
         const int nch = col_half == 0 ? nch_first : nch_total - nch_first;   // chunks owned (<= kNch)
         uint32_t chain = 0;
         for (int tile = worker; tile < num_tiles; tile += num_workers) {
-            const int ks = tile / args.m_blocks, mb = tile % args.m_blocks;
+            int ks, mb;
+            if (!map_tile(args, tile, ks, mb)) continue;
             const int kb0 = static_cast<int>(static_cast<long long>(ks) * args.num_kb / args.splits);
             const int kb1 = static_cast<int>(static_cast<long long>(ks + 1) * args.num_kb / args.splits);
             float acc[kNch * 16];
@@ -449,6 +471,8 @@ static int gemm_split_tile(const GemmOperand& a, bool a_is_mn_major, const GemmO
     args.scatter_slice = 0;
     args.scatter_rows = args.scatter_src = args.scatter_col0 = 0;
     for (int p = 0; p < kGemmMaxPeers; ++p) args.scatter_base[p] = nullptr;
+    args.perm_groups = args.perm_bpo = args.perm_rot = 0;
+    args.num_tiles = args.m_blocks * splits;
     if (scatter != nullptr && scatter->slice > 0) {
         NFB_CHECK(splits == 1, "the fused reduce-scatter epilogue needs an unsplit GEMM");
         NFB_CHECK(ceil_div64(m_total, scatter->slice) <= kGemmMaxPeers, "more owners than peers in the scatter epilogue");
@@ -458,6 +482,14 @@ static int gemm_split_tile(const GemmOperand& a, bool a_is_mn_major, const GemmO
         args.scatter_col0 = col0;
         args.ld_out = static_cast<int>(scatter->slice);
         for (int p = 0; p < kGemmMaxPeers; ++p) args.scatter_base[p] = scatter->base[p];
+        const int owners = static_cast<int>(ceil_div64(m_total, scatter->slice));
+        static const bool permute = !(getenv("NFB_SCATTER_PERM") && atoi(getenv("NFB_SCATTER_PERM")) == 0);
+        if (permute && owners > 1 && args.m_blocks >= 2 * owners) {
+            args.perm_groups = owners;
+            args.perm_bpo = (args.m_blocks + owners - 1) / owners;
+            args.perm_rot = scatter->src % owners;
+            args.num_tiles = args.perm_groups * args.perm_bpo;
+        }
     }
     args.b_tile_bytes = n_load * 128;
     const int stage_bytes = 2 * kATileBytes + 2 * args.b_tile_bytes;
@@ -466,7 +498,7 @@ static int gemm_split_tile(const GemmOperand& a, bool a_is_mn_major, const GemmO
     NFB_CHECK(args.num_stages >= 2, "not enough shared memory for a 2-stage pipeline");
     const size_t smem_bytes = static_cast<size_t>(args.num_stages) * stage_bytes + 1024 + 256;
 
-    const int64_t tiles = static_cast<int64_t>(args.m_blocks) * splits;
+    const int64_t tiles = args.num_tiles;
     int workers = static_cast<int>(std::min<int64_t>(tiles, sm_count() / cta_group));
 
     Launch l{&tm_a_hi, &tm_a_lo, &tm_b_hi, &tm_b_lo, &args, workers * cta_group, smem_bytes, stream};

@@ -127,7 +127,11 @@ nnls_smem_kernel(const double* __restrict__ gram, int k, const float* __restrict
                  int64_t rhs_stride, int64_t ld_rhs, int64_t cols, double* __restrict__ sol, int64_t ld_sol,
                  int max_outer, double tol, int* __restrict__ status, unsigned long long* __restrict__ steps_total,
                  unsigned long long* __restrict__ next_col, int initial_sweeps, double face_reduction,
-                 int scale_diag, int greedy_budget, int greedy_batch) {
+                 int scale_diag, int greedy_budget, int greedy_batch,
+                 const unsigned long long* __restrict__ flagged) {
+    // flagged != nullptr: clean-up pass behind nnls_greedy_kernel -- only the columns that kernel marked (NaN in
+    // row 0 of their solution) are solved, from scratch; nothing to do (the usual case) costs one global load
+    if (flagged != nullptr && *flagged == 0ULL) return;
     extern __shared__ double smd[];
     const int ntri = k * (k + 1) / 2;
     double* g_tri = smd;                                 // k (k + 1) / 2 packed lower triangle, row-major
@@ -175,11 +179,29 @@ nnls_smem_kernel(const double* __restrict__ gram, int k, const float* __restrict
     };
     __syncthreads();
 
+    unsigned pending = 0u;                 // flagged mode: marked columns of the current chunk of 32
+    unsigned long long chunk_base = 0;
     for (;;) {
         unsigned long long j = 0;
-        if (lane == 0) j = atomicAdd(next_col, 1ULL);
-        j = __shfl_sync(0xffffffffu, j, 0);
-        if (j >= static_cast<unsigned long long>(cols)) break;
+        if (flagged == nullptr) {
+            if (lane == 0) j = atomicAdd(next_col, 1ULL);
+            j = __shfl_sync(0xffffffffu, j, 0);
+            if (j >= static_cast<unsigned long long>(cols)) break;
+        } else {
+            bool out_of_work = false;
+            while (pending == 0u) {
+                unsigned long long c = 0;
+                if (lane == 0) c = atomicAdd(next_col, 1ULL);
+                chunk_base = __shfl_sync(0xffffffffu, c, 0) * 32ULL;
+                if (chunk_base >= static_cast<unsigned long long>(cols)) { out_of_work = true; break; }
+                const unsigned long long jj = chunk_base + lane;
+                const bool marked = jj < static_cast<unsigned long long>(cols) && sol[jj] != sol[jj];
+                pending = __ballot_sync(0xffffffffu, marked);
+            }
+            if (out_of_work) break;
+            j = chunk_base + (__ffs(pending) - 1);
+            pending &= pending - 1;
+        }
         double h[KPL], g[KPL];
         double rmax = 0.0;
 #pragma unroll
@@ -397,6 +419,157 @@ nnls_smem_kernel(const double* __restrict__ gram, int k, const float* __restrict
     }
 }
 
+
+// ---- greedy-only kernel: 32 warps per SM ------------------------------------------------------------------
+// The greedy (Gauss-Southwell) phase of nnls_smem_kernel on its own.  It needs only the gradient and the solution
+// (no CG vectors), so it fits 64 registers per thread and runs 32 warps per SM instead of 16: a coordinate step is
+// one dependent chain (key pass -> redux -> shuffle -> 7 LDS.64 + DFMA), and what hides a dependent chain is more
+// chains per SM.  The scaled Gram matrix G' = S G S lives in shared memory as 32 x 32 blocks (row stride 33) of the
+// block lower triangle, diagonal blocks in full: row t of G' restricted to block column i <= I is the contiguous run
+// [o][lane] of block (I, i), its continuation below the diagonal block is column o of block (i, I), i > I,
+// [lane][o] -- both conflict-free, both addressed as one per-step base + an immediate, no per-lane row offsets and
+// no select on the diagonal.  Problems the step budget does not finish are marked (NaN in row 0 of their solution)
+// and counted; nnls_smem_kernel solves exactly those afterwards.
+constexpr int kGBlk = 32 * 33;     // doubles per padded block
+
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+
+__host__ __device__ constexpr int greedy_block_off(int R, int C, int last, int rl33) {
+    return R < last ? (R * (R + 1) / 2 + C) * kGBlk : (last * (last + 1) / 2) * kGBlk + C * rl33;
+}
+__host__ inline size_t greedy_smem_bytes(int k) {
+    const int nb = (k + 31) / 32, rows_last = k - 32 * (nb - 1);
+    return (static_cast<size_t>(greedy_block_off(nb - 1, nb, nb - 1, rows_last * 33)) + k) * sizeof(double);
+}
+
+template <int NB, int kWarps>      // NB = ceil(k / 32): block rows = coordinates per lane
+__global__ void __launch_bounds__(kWarps * 32, 1)
+nnls_greedy_kernel(const double* __restrict__ gram, int k, const float* __restrict__ rhs, int rhs_splits,
+                   int64_t rhs_stride, int64_t ld_rhs, int64_t cols, double* __restrict__ sol, int64_t ld_sol,
+                   double tol, unsigned long long* __restrict__ steps_total, unsigned long long* __restrict__ counters,
+                   int budget, int batch) {
+    extern __shared__ double smd[];
+    constexpr int kLast = NB - 1;
+    const int rows_last = k - 32 * kLast;
+    const int rl33 = rows_last * 33;
+    double* scl = smd + greedy_block_off(kLast, NB, kLast, rl33);      // k scales s_t = 1 / sqrt(G[t][t])
+    const int lane = threadIdx.x & 31;
+    for (int t = threadIdx.x; t < k; t += blockDim.x) {
+        const double d = gram[static_cast<int64_t>(t) * k + t];
+        scl[t] = d > 0.0 ? 1.0 / sqrt(d) : 1.0;
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < k * k; idx += blockDim.x) {
+        const int r = idx / k, c = idx - r * k;
+        const int R = r >> 5, C = c >> 5;
+        if (C <= R) smd[greedy_block_off(R, C, kLast, rl33) + (r & 31) * 33 + (c & 31)] = gram[idx] * scl[r] * scl[c];
+    }
+    __syncthreads();
+    const bool last_valid = lane < rows_last;          // the last slot holds coordinates 32 (NB - 1) + lane < k only
+    const uint32_t sa_lane = smem_u32(smd) + lane * 8, sb_lane = smem_u32(smd) + lane * (33 * 8);
+
+    for (;;) {
+        unsigned long long j = 0;
+        if (lane == 0) j = atomicAdd(counters, 1ULL);
+        j = __shfl_sync(0xffffffffu, j, 0);
+        if (j >= static_cast<unsigned long long>(cols)) break;
+        double h[NB], g[NB];
+        double rmax = 0.0;
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+            const int t = lane + 32 * i;
+            double r = 0.0;
+            if (t < k) {
+                for (int s = 0; s < rhs_splits; ++s) r += static_cast<double>(rhs[s * rhs_stride + t * ld_rhs + j]);
+                r *= scl[t];
+            }
+            h[i] = 0.0;
+            g[i] = t < k ? -r : 0.0;         // padding slots: +0, they stay +0 and never qualify
+            rmax = fmax(rmax, fabs(r));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) rmax = fmax(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
+        const double thresh = tol * rmax;
+        const unsigned stop_key = static_cast<unsigned>(__double2hiint(0.5 * thresh)) & 0x7fffff00u;
+
+        // exact minimisation over coordinate t = 32 I + o (unit diagonal): every lane forms the step of its own
+        // slot-I coordinate, lane o's is broadcast; g += delta * G'[:, t].  A step that does not move (a candidate
+        // picked on a stale gradient, or a move lost to rounding) costs no update; the budget bounds the loop.
+        auto step = [&](auto slot_tag, int o) {
+            constexpr int I = decltype(slot_tag)::value;
+            const double hm = h[I] - g[I];
+            const double hn = hm > 0.0 ? hm : 0.0;
+            const double delta = shfl_d(hn - h[I], o);
+            if (delta == 0.0) return;                             // warp-uniform
+            if (lane == o) h[I] = hn;
+            const uint32_t pa = sa_lane + o * (33 * 8);           // [o][lane] of the blocks (I, i), i <= I
+            const uint32_t pb = sb_lane + o * 8;                  // [lane][o] of the blocks (i, I), i > I
+#pragma unroll
+            for (int i = 0; i < NB; ++i) {
+                double v = 0.0;
+                if (i < kLast || last_valid)
+                    v = i <= I ? lds_f64(pa + 8 * greedy_block_off(I, i, kLast, rl33))
+                               : lds_f64(pb + 8 * greedy_block_off(i, I, kLast, rl33));
+                g[i] = fma(delta, v, g[i]);
+            }
+        };
+
+        int left = rmax != 0.0 ? budget : 0;
+        while (left > 0) {
+            // this lane's best candidate: |g| on the support (h > 0), max(-g, 0) off it, as a 24-bit key
+            // (sign-stripped, truncated high word) + the coordinate index
+            unsigned mine = 0u;
+#pragma unroll
+            for (int i = 0; i < NB; ++i) {
+                const int ghi = __double2hiint(g[i]);
+                const bool take = __double2hiint(h[i]) > 0 || ghi < 0;
+                const unsigned key = (static_cast<unsigned>(ghi) & 0x7fffff00u) | static_cast<unsigned>(32 * i + lane);
+                mine = max(mine, take ? key : 0u);
+            }
+            // one key pass serves up to `batch` steps: the best candidates of distinct lanes, largest first (the
+            // later ones chosen on a gradient that is one or two updates old; the step itself is always exact)
+            bool done = false;
+            for (int b = 0; b < batch && left > 0; ++b) {
+                const unsigned best = __reduce_max_sync(0xffffffffu, mine);
+                if ((best & 0x7fffff00u) <= stop_key) { done = (b == 0); break; }
+                const int o = static_cast<int>(best & 31u);
+                if (lane == o) mine = 0u;
+                switch ((best >> 5) & 7u) {
+                    case 0: step(std::integral_constant<int, 0>{}, o); break;
+                    case 1: if constexpr (NB > 1) step(std::integral_constant<int, 1>{}, o); break;
+                    case 2: if constexpr (NB > 2) step(std::integral_constant<int, 2>{}, o); break;
+                    case 3: if constexpr (NB > 3) step(std::integral_constant<int, 3>{}, o); break;
+                    case 4: if constexpr (NB > 4) step(std::integral_constant<int, 4>{}, o); break;
+                    case 5: if constexpr (NB > 5) step(std::integral_constant<int, 5>{}, o); break;
+                    default: if constexpr (NB > 6) step(std::integral_constant<int, 6>{}, o); break;
+                }
+                --left;
+            }
+            if (done) break;                     // converged on fresh keys: the exact check follows
+        }
+        const unsigned nsteps = rmax != 0.0 ? static_cast<unsigned>(budget - left) : 0u;
+        double viol = 0.0;
+#pragma unroll
+        for (int i = 0; i < NB; ++i) viol = fmax(viol, h[i] > 0.0 ? fabs(g[i]) : fmax(-g[i], 0.0));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) viol = fmax(viol, __shfl_xor_sync(0xffffffffu, viol, o));
+        const bool converged = viol <= thresh;
+        if (lane == 0) {
+            if (steps_total != nullptr) atomicAdd(steps_total, static_cast<unsigned long long>(nsteps));
+            if (!converged) atomicAdd(counters + 1, 1ULL);
+        }
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+            const int t = lane + 32 * i;
+            if (t < k) sol[t * ld_sol + j] = (converged || t != 0) ? h[i] * scl[t] : __longlong_as_double(0x7ff8000000000000LL);
+        }
+    }
+}
+
 }  // namespace
 
 int nnls_gram_batched(const double* gram, int64_t k, const float* rhs, int rhs_splits, int64_t rhs_stride,
@@ -406,7 +579,9 @@ int nnls_gram_batched(const double* gram, int64_t k, const float* rhs, int rhs_s
     NFB_CHECK(k <= 512, "n_components > 512 is not supported by the NNLS kernel");
     const size_t smem_fast = (static_cast<size_t>(k) * (k + 1) / 2 + 3 * k) * sizeof(double);
     if (smem_fast <= 220 * 1024 && k <= 224 && counter != nullptr) {
-        NFB_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream));
+        // counter[0]: column hand-out of the first kernel, [1]: columns the greedy kernel left unfinished,
+        // [2]: chunk hand-out of the clean-up pass
+        NFB_CUDA(cudaMemsetAsync(counter, 0, 3 * sizeof(unsigned long long), stream));
         // 16 warps per SM (128 registers, a few spilled values at k > 192) measured faster than 12 spill-free ones.
         // The knobs are read on every call so that one process can compare settings (tests/gpu_nnls_probe.py).
         const int warps_env = getenv("NFB_NNLS_WARPS") ? atoi(getenv("NFB_NNLS_WARPS")) : 0;
@@ -419,6 +594,38 @@ int nnls_gram_batched(const double* gram, int64_t k, const float* rhs, int rhs_s
         const int greedy_mult = getenv("NFB_NNLS_GREEDY") ? std::max(0, atoi(getenv("NFB_NNLS_GREEDY"))) : kGreedyBudget;
         const int greedy_budget = scale_diag ? greedy_mult * static_cast<int>(k) : 0;   // the keys assume a unit diagonal
         const int greedy_batch = getenv("NFB_NNLS_BATCH") ? std::max(1, atoi(getenv("NFB_NNLS_BATCH"))) : kGreedyBatch;
+        // NFB_NNLS_SPLIT=0: everything in the one 16-warp kernel (greedy phase + sweeps / CG), as before the
+        // 32-warp greedy kernel existed
+        const bool split = !(getenv("NFB_NNLS_SPLIT") && atoi(getenv("NFB_NNLS_SPLIT")) == 0);
+        const size_t smem_greedy = greedy_smem_bytes(static_cast<int>(k));
+        const unsigned long long* flagged = nullptr;
+        unsigned long long* fast_counter = counter;
+        if (split && greedy_budget > 0 && smem_greedy <= 226 * 1024) {
+            const int gw = warps_env > 16 ? std::min(32, warps_env & ~3) : 32;
+            const int ggrid = static_cast<int>(std::min<int64_t>(ceil_div64(cols, gw), sm_count()));
+#define NFB_NNLS_GREEDY_LAUNCH(NB)                                                                                \
+    do {                                                                                                         \
+        auto gk = gw >= 32 ? nnls_greedy_kernel<NB, 32> : (gw >= 24 ? nnls_greedy_kernel<NB, 24> : nnls_greedy_kernel<NB, 20>); \
+        NFB_CUDA(cudaFuncSetAttribute(gk, cudaFuncAttributeMaxDynamicSharedMemorySize,                           \
+                                      static_cast<int>(smem_greedy)));                                           \
+        gk<<<ggrid, (gw >= 32 ? 32 : (gw >= 24 ? 24 : 20)) * 32, smem_greedy, stream>>>(                          \
+            gram, static_cast<int>(k), rhs, rhs_splits, rhs_stride, ld_rhs, cols, sol, ld_sol, 1e-10, steps_total, \
+            counter, greedy_budget, greedy_batch);                                                               \
+    } while (0)
+            switch ((k + 31) / 32) {
+                case 1: NFB_NNLS_GREEDY_LAUNCH(1); break;
+                case 2: NFB_NNLS_GREEDY_LAUNCH(2); break;
+                case 3: NFB_NNLS_GREEDY_LAUNCH(3); break;
+                case 4: NFB_NNLS_GREEDY_LAUNCH(4); break;
+                case 5: NFB_NNLS_GREEDY_LAUNCH(5); break;
+                case 6: NFB_NNLS_GREEDY_LAUNCH(6); break;
+                default: NFB_NNLS_GREEDY_LAUNCH(7); break;
+            }
+#undef NFB_NNLS_GREEDY_LAUNCH
+            NFB_CUDA(cudaGetLastError());
+            flagged = counter + 1;
+            fast_counter = counter + 2;
+        }
         const int grid = static_cast<int>(std::min<int64_t>(ceil_div64(cols, kNnlsWarps), sm_count()));
 #define NFB_NNLS_FAST(KPL)                                                                                       \
     do {                                                                                                         \
@@ -427,8 +634,9 @@ int nnls_gram_batched(const double* gram, int64_t k, const float* rhs, int rhs_s
                                       static_cast<int>(smem_fast)));                                             \
         kernel<<<grid, kNnlsWarps * 32, smem_fast, stream>>>(gram, static_cast<int>(k), rhs, rhs_splits,         \
                                                              rhs_stride, ld_rhs, cols, sol, ld_sol, max_outer,   \
-                                                             1e-10, status, steps_total, counter, sweeps0, face_red, \
-                                                             scale_diag, greedy_budget, greedy_batch);           \
+                                                             1e-10, status, steps_total, fast_counter, sweeps0,  \
+                                                             face_red, scale_diag, greedy_budget, greedy_batch,  \
+                                                             flagged);                                           \
     } while (0)
         if (k <= 32) NFB_NNLS_FAST(1);
         else if (k <= 64) NFB_NNLS_FAST(2);

@@ -26,8 +26,10 @@ x = synth_rows_device(torch, dev, 0, m, n, k, density)
 x_mean = float(x.sum(dtype=torch.float64)) / (m * n)
 torch.cuda.synchronize()
 xmat = DeviceMatrix.from_device_ptr(x.data_ptr(), m, n, n)
-del x
-torch.cuda.empty_cache()
+dump = os.environ.get("NFB_PROBE_DUMP")        # path: Gram matrices + sampled right-hand sides for CPU simulations
+if not dump:
+    del x
+    torch.cuda.empty_cache()
 w0, h0 = random_init(torch, dev, x_mean, m, n, k, 0)
 params = dict(nfact_b200.get_parameters(None, "nmf", k), tol=0.0, max_iter=iters)
 t0 = time.perf_counter()
@@ -35,6 +37,21 @@ res = nfact_b200.nmf_decomp(params, xmat, W=w0.cpu().numpy(), H=h0.cpu().numpy()
 print(f"{name}: {iters} CD iterations in {time.perf_counter() - t0:.2f}s; grey nnz={np.mean(res['grey_components'] > 0):.3f}",
       flush=True)
 comps = {"grey_components": res["grey_components"]}
+if dump:
+    rng = np.random.default_rng(0)
+    cols = np.sort(rng.choice(n, 256, replace=False))
+    rows = np.sort(rng.choice(m, 256, replace=False))
+    wd = torch.from_numpy(res["grey_components"]).to(dev, torch.float64)
+    g1 = (wd.T @ wd).cpu().numpy()
+    r1 = (wd.T @ x[:, torch.from_numpy(cols).to(dev)].to(torch.float64)).cpu().numpy()
+    dr0 = nfact_b200.nmf_dual_regression(comps, xmat)
+    hs = torch.from_numpy(dr0["white_components"]).to(dev, torch.float64)
+    g2 = (hs @ hs.T).cpu().numpy()
+    r2 = (hs @ x[torch.from_numpy(rows).to(dev), :].to(torch.float64).T).cpu().numpy()
+    np.savez(dump, G1=g1, R1=r1, G2=g2, R2=r2, H1=dr0["white_components"][:, cols],
+             H2=dr0["grey_components"][rows, :].T)
+    del x, wd, hs, dr0
+    torch.cuda.empty_cache()
 reference = None
 touched = set()
 for group in groups:
