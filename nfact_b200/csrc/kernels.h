@@ -139,7 +139,7 @@ int comp_loadings(const T* a, const T* b, int64_t k, int64_t len, int64_t ld, do
 // data moves inside the compute kernels (GemmScatter in the W'X epilogue, PeerMirror in the sweep / update); these
 // are the small kernels around them.
 constexpr int kP2pMaxWorld = 8;
-constexpr int kP2pRsFlag = 0, kP2pAgFlag = 16, kP2pError = 32;   // int offsets into the arena header
+constexpr int kP2pRsFlag = 0, kP2pAgFlag = 16, kP2pError = 32, kP2pGramFlag = 48;   // int offsets into the arena header
 constexpr int64_t kP2pScalOffset = 256;                          // byte offset of double scal[16][2]
 constexpr int64_t kP2pHeaderBytes = 512;
 struct P2pPeers {
@@ -153,9 +153,11 @@ int p2p_post(const P2pPeers& peers, int world, int rank, int flag_offset, int ep
              int64_t rowmax_offset = 0, int kp = 0);
 // this rank's Gram (slot `rank` of its gram_in at byte offset gram_offset) -> the same slot in every peer's arena
 int p2p_push_gram(const P2pPeers& peers, int world, int rank, int64_t gram_offset, int gram_elems, cudaStream_t stream);
-// wait for every rank's numerator of `epoch`; gram_out = sum_p gram_in[p]
-int p2p_wait_sum_gram(const P2pPeers& peers, int world, int rank, int epoch, int64_t gram_offset, int gram_elems,
-                      float* gram_out, cudaStream_t stream);
+// wait for flag row `flag_offset` of every rank to reach `epoch`; gram_out = sum_p gram_in[p]
+int p2p_wait_sum_gram(const P2pPeers& peers, int world, int rank, int flag_offset, int epoch, int64_t gram_offset,
+                      int gram_elems, float* gram_out, cudaStream_t stream);
+// wait only
+int p2p_wait(const P2pPeers& peers, int world, int rank, int flag_offset, int epoch, cudaStream_t stream);
 // wait for every rank's slice of `epoch`; scal_out[i] (nullable) = sum_p scal[p][i]; rowmax_out[t] (nullable) =
 // max_p rowmax_in[p][t]
 int p2p_gather_wait(const P2pPeers& peers, int world, int rank, int epoch, int64_t scal_offset, double* scal_out,

@@ -3,6 +3,9 @@
 // Every rank owns an "arena" (one cudaMalloc, mapped into all peers):
 //     int    rs_flag[16]        rs_flag[p] = last epoch for which rank p's numerator tiles and Gram have landed HERE
 //     int    ag_flag[16]        ag_flag[p] = last epoch for which rank p's H slice (and scalars) have landed HERE
+//     int    gram_flag[16]      gram_flag[p] = last epoch for which rank p's W'W has landed HERE (posted before the
+//                               W'X GEMM starts, so that the Gram sum and the denominator GEMM that needs it run on
+//                               the aux stream beside the GEMM instead of after it)
 //     int    error              a wait timed out (peer died): results are garbage, the host raises
 //     double scal[16][2]        scal[p] = rank p's local (violation_W, violation_H), posted with its H slice
 //     float  gram_in[P][kp*kp]  gram_in[p] = rank p's local W'W
@@ -14,8 +17,8 @@
 //                     the rank that owns those H columns (gemm_split.cu, GemmScatter) -- remote stores over NVLink
 //                     that overlap the mainloop of the following tiles; the consumer (sweep / multiplicative update)
 //                     reads the P slabs as split-K partials, summed in rank order -> deterministic.  The k x k Gram
-//                     is pushed to every peer by a small kernel before the GEMM.  After the GEMM a one-CTA kernel
-//                     posts rs_flag; the owner waits for all P flags and sums the P Grams.
+//                     is pushed to every peer by a small kernel before the GEMM and flagged on its own (gram_flag).
+//                     After the GEMM a one-CTA kernel posts rs_flag; the owner waits for all P flags.
 //   all-gather      : the sweep / update kernel writes every H value it changes into all peers' H masters as part
 //                     of its own write-back (cd_sweep.cu / update.cu, PeerMirror); the post kernel adds this rank's
 //                     two float64 scalars and per-component maxima and raises ag_flag; a one-CTA kernel waits for
@@ -37,12 +40,6 @@ __device__ __forceinline__ int ld_acquire_sys(const int* p) {
 }
 __device__ __forceinline__ void st_release_sys(int* p, int v) {
     asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ float4 ld_peer4(const float* p) {
-    float4 v;
-    asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];"
-                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
-    return v;
 }
 __device__ __forceinline__ float ld_peer(const float* p) {
     float v;
@@ -110,15 +107,21 @@ p2p_push_gram_kernel(P2pPeers peers, int world, int rank, int64_t gram_offset, i
 
 // wait for every rank's numerator tiles + Gram of `epoch`; gram_out = sum_p gram_in[p] (rank order)
 __global__ void __launch_bounds__(256)
-p2p_wait_sum_gram_kernel(P2pPeers peers, int world, int rank, int epoch, int64_t gram_offset, int gram_elems,
-                         float* __restrict__ gram_out) {
-    wait_all(peers, world, rank, kP2pRsFlag, epoch);
+p2p_wait_sum_gram_kernel(P2pPeers peers, int world, int rank, int flag_offset, int epoch, int64_t gram_offset,
+                         int gram_elems, float* __restrict__ gram_out) {
+    wait_all(peers, world, rank, flag_offset, epoch);
     const float* in = reinterpret_cast<const float*>(reinterpret_cast<const char*>(peers.arena[rank]) + gram_offset);
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < gram_elems; e += gridDim.x * blockDim.x) {
         float acc = 0.0f;
         for (int p = 0; p < world; ++p) acc += ld_peer(in + static_cast<int64_t>(p) * gram_elems + e);
         gram_out[e] = acc;
     }
+}
+
+// wait only: every rank has raised flag row `flag_offset` to `epoch`
+__global__ void __launch_bounds__(32)
+p2p_wait_kernel(P2pPeers peers, int world, int rank, int flag_offset, int epoch) {
+    wait_all(peers, world, rank, flag_offset, epoch);
 }
 
 // wait for every peer's slice, then scal_out[i] = sum_p scal[p][i] in rank order, rowmax_out[t] = max_p rowmax_in[p][t]
@@ -168,10 +171,17 @@ int p2p_push_gram(const P2pPeers& peers, int world, int rank, int64_t gram_offse
     return 0;
 }
 
-int p2p_wait_sum_gram(const P2pPeers& peers, int world, int rank, int epoch, int64_t gram_offset, int gram_elems,
-                      float* gram_out, cudaStream_t stream) {
+int p2p_wait_sum_gram(const P2pPeers& peers, int world, int rank, int flag_offset, int epoch, int64_t gram_offset,
+                      int gram_elems, float* gram_out, cudaStream_t stream) {
     const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(ceil_div64(gram_elems, 256), sm_count())));
-    p2p_wait_sum_gram_kernel<<<grid, 256, 0, stream>>>(peers, world, rank, epoch, gram_offset, gram_elems, gram_out);
+    p2p_wait_sum_gram_kernel<<<grid, 256, 0, stream>>>(peers, world, rank, flag_offset, epoch, gram_offset, gram_elems,
+                                                       gram_out);
+    NFB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int p2p_wait(const P2pPeers& peers, int world, int rank, int flag_offset, int epoch, cudaStream_t stream) {
+    p2p_wait_kernel<<<1, 32, 0, stream>>>(peers, world, rank, flag_offset, epoch);
     NFB_CUDA(cudaGetLastError());
     return 0;
 }

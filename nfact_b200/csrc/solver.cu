@@ -127,6 +127,12 @@ struct nfb_handle {
     DevBuf<int> d_int;
     double* h_scal = nullptr;     // pinned mirror
     cudaStream_t copy_stream = nullptr;   // D2H of finished results while the compute stream carries on
+    // second compute stream: the small k x k "denominator" GEMMs run beside the X-streaming GEMM they do not
+    // depend on (their CTAs fill the SMs the big launch's last, partial wave leaves idle); NFB_DEN_OVERLAP=0: off
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t aux_fork = nullptr, aux_join = nullptr;
+    bool den_overlap = true;
+    bool gram_overlap = true;    // the Gram products as well (NFB_DEN_OVERLAP=1: denominators only)
 };
 
 struct nfb_matrix {
@@ -224,6 +230,10 @@ struct nfb_nmf {
     int s_w = 1, s_h = 1, s_gw = 1, s_gh = 1;
     double sumsq_global = 0.0;
     bool p1_valid = false;  // part_w holds X H' for the current H
+    bool den_w_valid = false;    // part_den holds (HH') W' for the current W planes and Gram (launched beside X H')
+    bool den_h_done = false;     // gemm_wtx already launched the H denominator on the aux stream
+    bool gh_valid = false;       // gh holds HH' of the current H planes (with the overlap it is computed beside X H')
+    bool aux_pending = false;    // work on the aux stream that the main stream has not joined yet
     double last_violation = 0.0;
 };
 
@@ -246,13 +256,15 @@ static int allreduce_f64(nfb_handle* h, double* buf, size_t count) {
 
 // G = F F' (fp32 [k][kp]) through the tensor-core path; partial sums over `splits` K ranges.
 // to_arena: leave the local Gram in the peer-visible arena; the pull kernel of the H half-step sums all ranks'
-static int compute_gram(nfb_nmf* s, Factor& fac, Factor& gram, int splits, bool allreduce, bool to_arena = false) {
+static int compute_gram(nfb_nmf* s, Factor& fac, Factor& gram, int splits, bool allreduce, bool to_arena = false,
+                        cudaStream_t stream = nullptr) {
     nfb_handle* h = s->h;
+    if (stream == nullptr) stream = h->stream;
     NFB_TRY(gemm_split(fac.operand(), false, fac.operand(), fac.k, fac.dim, static_cast<int>(fac.kp),
                        static_cast<int>(fac.k), s->part_gram.p, gram.ld, splits, fac.inv_scale.p, fac.inv_scale.p,
-                       1.0f, h->cta_group, h->stream));
+                       1.0f, h->cta_group, stream));
     NFB_TRY(reduce_partials(s->part_gram.p, splits, fac.k * gram.ld, fac.k, fac.k, gram.ld, 0.0f,
-                            to_arena ? s->arena_gram() : gram.f.p, gram.ld, h->stream));
+                            to_arena ? s->arena_gram() : gram.f.p, gram.ld, stream));
     note_launch(2);
     if (allreduce && !to_arena) NFB_TRY(allreduce_f32(h, gram.f.p, static_cast<size_t>(gram.kp * gram.ld)));
     return 0;
@@ -336,6 +348,10 @@ struct HNumerator {
     int64_t width;      // number of H columns this rank updates
 };
 
+static int aux_fork(nfb_handle* h);
+static int gemm_den(nfb_nmf* s, Factor& fac, Factor& gram, int64_t col0, int64_t width, int64_t ld_out,
+                    cudaStream_t stream = nullptr);
+
 static int gemm_wtx(nfb_nmf* s, HNumerator* out) {
     nfb_handle* h = s->h;
     const int64_t n = s->x->n;
@@ -346,6 +362,10 @@ static int gemm_wtx(nfb_nmf* s, HNumerator* out) {
         const int64_t ns = s->slice_cols;
         const int gram_elems = static_cast<int>(s->kp * s->kp);
         NFB_TRY(p2p_push_gram(s->peers, h->world, h->rank, s->arena_gram_off, gram_elems, h->stream));
+        ++s->epoch;
+        NFB_TRY(p2p_post(s->peers, h->world, h->rank, kP2pGramFlag, s->epoch, h->stream));
+        const bool side = h->den_overlap;
+        if (side) NFB_TRY(aux_fork(h));
         GemmScatter sc{};
         for (int r = 0; r < h->world; ++r)
             sc.base[r] = reinterpret_cast<float*>(static_cast<char*>(s->peers.arena[r]) + s->arena_num_off);
@@ -358,15 +378,24 @@ static int gemm_wtx(nfb_nmf* s, HNumerator* out) {
                            s->arena_num(), ns, 1, s->wt.inv_scale.p, nullptr, s->x->inv_scale_host, h->cta_group,
                            h->stream, &sc));
         }
-        ++s->epoch;
+        const int64_t c0 = std::min<int64_t>(n, h->rank * ns);
+        const int64_t width = std::min<int64_t>(ns, n - c0);
+        // the P inbox slabs are the split-K partials of this rank's columns: the consumer sums them in rank order
+        *out = HNumerator{s->arena_num(), h->world, static_cast<int64_t>(s->k) * ns, ns, c0, width};
+        // the Gram sum needs only the peers' Gram flags (raised before their GEMMs): with the aux stream it and the
+        // denominator GEMM run beside this rank's W'X instead of after it
+        cudaStream_t gst = side ? h->aux_stream : h->stream;
+        NFB_TRY(p2p_wait_sum_gram(s->peers, h->world, h->rank, kP2pGramFlag, s->epoch, s->arena_gram_off, gram_elems,
+                                  s->gw.f.p, gst));
+        if (side) {
+            NFB_TRY(gemm_den(s, s->hh, s->gw, c0, width, ns, h->aux_stream));
+            s->aux_pending = true;
+            s->den_h_done = true;
+        }
         NFB_PHASE(h, "rs_wait");
         NFB_TRY(p2p_post(s->peers, h->world, h->rank, kP2pRsFlag, s->epoch, h->stream));
-        NFB_TRY(p2p_wait_sum_gram(s->peers, h->world, h->rank, s->epoch, s->arena_gram_off, gram_elems, s->gw.f.p,
-                                  h->stream));
-        note_launch(4);
-        const int64_t c0 = std::min<int64_t>(n, h->rank * ns);
-        // the P inbox slabs are the split-K partials of this rank's columns: the consumer sums them in rank order
-        *out = HNumerator{s->arena_num(), h->world, static_cast<int64_t>(s->k) * ns, ns, c0, std::min<int64_t>(ns, n - c0)};
+        NFB_TRY(p2p_wait(s->peers, h->world, h->rank, kP2pRsFlag, s->epoch, h->stream));
+        note_launch(6);
         return 0;
     }
     {
@@ -436,15 +465,53 @@ static int gather_h_slices(nfb_nmf* s, const HNumerator& hn) {
 
 // G F for the columns [col0, col0 + width) of F:  part_den[t][j] = sum_r G[t][r] F[r][col0 + j]
 // (denominator of the multiplicative update; seed of the coordinate-descent gradient)
-static int gemm_den(nfb_nmf* s, Factor& fac, Factor& gram, int64_t col0, int64_t width, int64_t ld_out) {
+static int gemm_den(nfb_nmf* s, Factor& fac, Factor& gram, int64_t col0, int64_t width, int64_t ld_out,
+                    cudaStream_t stream) {
     nfb_handle* h = s->h;
+    if (stream == nullptr) stream = h->stream;
     // fold the per-component scales of F's planes (the K side of this product) into G's columns
-    NFB_TRY(refresh_planes(s->gd, gram.f.p, fac.inv_scale.p, true, h->stream));
+    NFB_TRY(refresh_planes(s->gd, gram.f.p, fac.inv_scale.p, true, stream));
     if (width <= 0) return 0;
     GemmOperand a{fac.hi.p + col0, fac.lo.p + col0, fac.k, fac.ld};
     NFB_TRY(gemm_split(a, true, s->gd.operand(), width, fac.k, static_cast<int>(s->kp), s->k, s->part_den.p, ld_out,
-                       1, s->gd.inv_scale.p, nullptr, 1.0f, h->cta_group, h->stream));
+                       1, s->gd.inv_scale.p, nullptr, 1.0f, h->cta_group, stream));
     note_launch(1);
+    return 0;
+}
+
+// The denominator GEMM of a half-step needs the factor's planes and the OTHER factor's Gram -- not the X-streaming
+// product that precedes the update.  fork: everything enqueued on the main stream so far is the aux stream's
+// starting point; the caller then launches the big GEMM on the main stream FIRST (its persistent CTAs take the
+// SMs) and the denominator work on the aux stream, whose GEMM CTAs start as the big launch's CTAs retire.
+static int aux_fork(nfb_handle* h) {
+    NFB_CUDA(cudaEventRecord(h->aux_fork, h->stream));
+    NFB_CUDA(cudaStreamWaitEvent(h->aux_stream, h->aux_fork, 0));
+    return 0;
+}
+static int aux_join(nfb_nmf* s) {
+    if (!s->aux_pending) return 0;
+    nfb_handle* h = s->h;
+    NFB_CUDA(cudaEventRecord(h->aux_join, h->aux_stream));
+    NFB_CUDA(cudaStreamWaitEvent(h->stream, h->aux_join, 0));
+    s->aux_pending = false;
+    return 0;
+}
+
+// X H' for the current H on the main stream and, beside it, the denominator of the W half-step
+static int gemm_xht_with_den(nfb_nmf* s) {
+    nfb_handle* h = s->h;
+    if (!h->den_overlap) {
+        if (!s->gh_valid) NFB_TRY(compute_gram(s, s->hh, s->gh, s->s_gh, false));
+        s->gh_valid = true;
+        return gemm_xht(s);
+    }
+    NFB_TRY(aux_fork(h));
+    NFB_TRY(gemm_xht(s));
+    if (!s->gh_valid) NFB_TRY(compute_gram(s, s->hh, s->gh, s->s_gh, false, false, h->aux_stream));
+    s->gh_valid = true;
+    NFB_TRY(gemm_den(s, s->wt, s->gh, 0, s->x->m, s->wt.ld, h->aux_stream));
+    s->den_w_valid = true;
+    s->aux_pending = true;
     return 0;
 }
 
@@ -454,16 +521,20 @@ static int finish_h(nfb_nmf* s, const HNumerator& hn) {
     const bool sliced = s->h_sliced;
     NFB_TRY(gather_h_slices(s, hn));
     NFB_TRY(refresh_planes(s->hh, s->hh.f.p, nullptr, sliced && !s->p2p, h->stream));   // p2p: maxima came with the gather
-    NFB_TRY(compute_gram(s, s->hh, s->gh, s->s_gh, false));
+    // HH' is needed by the next W half-step (and the error): with the overlap it is computed beside the next X H'
+    if (h->gram_overlap) s->gh_valid = false;
+    else { NFB_TRY(compute_gram(s, s->hh, s->gh, s->s_gh, false)); s->gh_valid = true; }
     return 0;
 }
 
 static int mu_iteration(nfb_nmf* s) {
     nfb_handle* h = s->h;
     const nfb_nmf_params& p = s->p;
-    if (!s->p1_valid) { NFB_PHASE(h, "gemm_xht"); NFB_TRY(gemm_xht(s)); }
+    if (!s->p1_valid) { NFB_PHASE(h, "gemm_xht"); NFB_TRY(gemm_xht_with_den(s)); }
     // ---- W half-step ----
-    { NFB_PHASE(h, "den_w"); NFB_TRY(gemm_den(s, s->wt, s->gh, 0, s->x->m, s->wt.ld)); }
+    if (!s->den_w_valid) { NFB_PHASE(h, "den_w"); NFB_TRY(gemm_den(s, s->wt, s->gh, 0, s->x->m, s->wt.ld)); }
+    NFB_TRY(aux_join(s));
+    s->den_w_valid = false;
     NFB_CUDA(cudaMemsetAsync(s->wt.rowmax.p, 0, sizeof(unsigned int) * s->kp, h->stream));
     { NFB_PHASE(h, "update_w");
     NFB_TRY(mu_update(s->wt.f.p, s->k, s->x->m, s->wt.ld, s->part_w.p, s->s_w, static_cast<int64_t>(s->k) * s->wt.ld,
@@ -473,11 +544,28 @@ static int mu_iteration(nfb_nmf* s) {
     note_launch(1);
     s->p1_valid = false;
     { NFB_PHASE(h, "split_w"); NFB_TRY(refresh_planes(s->wt, s->wt.f.p, nullptr, false, h->stream)); }
-    { NFB_PHASE(h, "gram_w"); NFB_TRY(compute_gram(s, s->wt, s->gw, s->s_gw, true, s->p2p)); }
+    const bool side = h->world <= 1 && h->den_overlap;
+    if (!side || !h->gram_overlap) { NFB_PHASE(h, "gram_w"); NFB_TRY(compute_gram(s, s->wt, s->gw, s->s_gw, true, s->p2p)); }
     // ---- H half-step ----
     HNumerator hn;
-    { NFB_PHASE(h, "gemm_wtx"); NFB_TRY(gemm_wtx(s, &hn)); }
-    { NFB_PHASE(h, "den_h"); NFB_TRY(gemm_den(s, s->hh, s->gw, hn.col0, hn.width, hn.ld_part)); }
+    if (side) {
+        // single GPU: W'W and the H denominator run beside the X-streaming GEMM (see gemm_xht_with_den)
+        NFB_TRY(aux_fork(h));
+        { NFB_PHASE(h, "gemm_wtx"); NFB_TRY(gemm_wtx(s, &hn)); }
+        if (h->gram_overlap) NFB_TRY(compute_gram(s, s->wt, s->gw, s->s_gw, false, false, h->aux_stream));
+        NFB_TRY(gemm_den(s, s->hh, s->gw, hn.col0, hn.width, hn.ld_part, h->aux_stream));
+        s->aux_pending = true;
+        NFB_TRY(aux_join(s));
+    } else {
+        { NFB_PHASE(h, "gemm_wtx"); NFB_TRY(gemm_wtx(s, &hn)); }
+        if (s->den_h_done) {           // peer-memory path: launched beside the GEMM (gemm_wtx)
+            NFB_TRY(aux_join(s));
+            s->den_h_done = false;
+        } else {
+            NFB_PHASE(h, "den_h");
+            NFB_TRY(gemm_den(s, s->hh, s->gw, hn.col0, hn.width, hn.ld_part));
+        }
+    }
     NFB_CUDA(cudaMemsetAsync(s->hh.rowmax.p, 0, sizeof(unsigned int) * s->kp, h->stream));
     if (hn.width > 0) {
         NFB_PHASE(h, "update_h");
@@ -498,9 +586,11 @@ static int cd_iteration(nfb_nmf* s, double* violation_out, double* host_slot = n
     nfb_handle* h = s->h;
     const nfb_nmf_params& p = s->p;
     NFB_CUDA(cudaMemsetAsync(h->d_scal.p + 2, 0, 2 * sizeof(double), h->stream));
-    if (!s->p1_valid) { NFB_PHASE(h, "gemm_xht"); NFB_TRY(gemm_xht(s)); }
+    if (!s->p1_valid) { NFB_PHASE(h, "gemm_xht"); NFB_TRY(gemm_xht_with_den(s)); }
     // ---- W half-step ----
-    { NFB_PHASE(h, "den_w"); NFB_TRY(gemm_den(s, s->wt, s->gh, 0, s->x->m, s->wt.ld)); }  // seeds the gradient
+    if (!s->den_w_valid) { NFB_PHASE(h, "den_w"); NFB_TRY(gemm_den(s, s->wt, s->gh, 0, s->x->m, s->wt.ld)); }  // seeds the gradient
+    NFB_TRY(aux_join(s));
+    s->den_w_valid = false;
     NFB_CUDA(cudaMemsetAsync(s->wt.rowmax.p, 0, sizeof(unsigned int) * s->kp, h->stream));
     { NFB_PHASE(h, "update_w");
     NFB_TRY(cd_sweep(s->wt.f.p, s->k, s->x->m, s->wt.ld, s->part_w.p, s->s_w, static_cast<int64_t>(s->k) * s->wt.ld,
@@ -510,11 +600,28 @@ static int cd_iteration(nfb_nmf* s, double* violation_out, double* host_slot = n
     note_launch(1);
     s->p1_valid = false;
     { NFB_PHASE(h, "split_w"); NFB_TRY(refresh_planes(s->wt, s->wt.f.p, nullptr, false, h->stream)); }
-    { NFB_PHASE(h, "gram_w"); NFB_TRY(compute_gram(s, s->wt, s->gw, s->s_gw, true, s->p2p)); }
+    const bool side = h->world <= 1 && h->den_overlap;
+    if (!side || !h->gram_overlap) { NFB_PHASE(h, "gram_w"); NFB_TRY(compute_gram(s, s->wt, s->gw, s->s_gw, true, s->p2p)); }
     // ---- H half-step ----
     HNumerator hn;
-    { NFB_PHASE(h, "gemm_wtx"); NFB_TRY(gemm_wtx(s, &hn)); }
-    { NFB_PHASE(h, "den_h"); NFB_TRY(gemm_den(s, s->hh, s->gw, hn.col0, hn.width, hn.ld_part)); }
+    if (side) {
+        // single GPU: W'W and the H denominator run beside the X-streaming GEMM (see gemm_xht_with_den)
+        NFB_TRY(aux_fork(h));
+        { NFB_PHASE(h, "gemm_wtx"); NFB_TRY(gemm_wtx(s, &hn)); }
+        if (h->gram_overlap) NFB_TRY(compute_gram(s, s->wt, s->gw, s->s_gw, false, false, h->aux_stream));
+        NFB_TRY(gemm_den(s, s->hh, s->gw, hn.col0, hn.width, hn.ld_part, h->aux_stream));
+        s->aux_pending = true;
+        NFB_TRY(aux_join(s));
+    } else {
+        { NFB_PHASE(h, "gemm_wtx"); NFB_TRY(gemm_wtx(s, &hn)); }
+        if (s->den_h_done) {           // peer-memory path: launched beside the GEMM (gemm_wtx)
+            NFB_TRY(aux_join(s));
+            s->den_h_done = false;
+        } else {
+            NFB_PHASE(h, "den_h");
+            NFB_TRY(gemm_den(s, s->hh, s->gw, hn.col0, hn.width, hn.ld_part));
+        }
+    }
     NFB_CUDA(cudaMemsetAsync(s->hh.rowmax.p, 0, sizeof(unsigned int) * s->kp, h->stream));
     if (hn.width > 0) {
         NFB_PHASE(h, "update_h");
@@ -542,7 +649,8 @@ static int cd_iteration(nfb_nmf* s, double* violation_out, double* host_slot = n
 // ||X - WH||_F via  ||X||^2 - 2 <W, X H'> + <W'W, HH'>   (float64 accumulation)
 static int nmf_error(nfb_nmf* s, double* err_out) {
     nfb_handle* h = s->h;
-    if (!s->p1_valid) NFB_TRY(gemm_xht(s));
+    if (!s->p1_valid) NFB_TRY(gemm_xht_with_den(s));
+    NFB_TRY(aux_join(s));          // HH' may have been computed on the aux stream
     NFB_CUDA(cudaMemsetAsync(h->d_scal.p, 0, 2 * sizeof(double), h->stream));
     NFB_TRY(dot_partials(s->wt.f.p, s->wt.ld, s->part_w.p, s->s_w, static_cast<int64_t>(s->k) * s->wt.ld, s->wt.ld,
                          s->k, s->x->m, h->d_scal.p, h->stream));
@@ -558,10 +666,13 @@ static int nmf_error(nfb_nmf* s, double* err_out) {
 
 static int nmf_prepare_factors(nfb_nmf* s) {
     nfb_handle* h = s->h;
+    NFB_TRY(aux_join(s));          // a denominator launched beside the last X H' belongs to the old factors
+    s->den_w_valid = false;
     NFB_TRY(refresh_planes(s->wt, s->wt.f.p, nullptr, true, h->stream));
     NFB_TRY(refresh_planes(s->hh, s->hh.f.p, nullptr, true, h->stream));
     NFB_TRY(compute_gram(s, s->wt, s->gw, s->s_gw, true));
     NFB_TRY(compute_gram(s, s->hh, s->gh, s->s_gh, false));
+    s->gh_valid = true;
     s->p1_valid = false;
     return 0;
 }
@@ -698,6 +809,13 @@ int nfb_create(int device, void* stream, nfb_handle** out) {
     NFB_TRY(h->d_int.alloc(16, true, h->stream));
     NFB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h->h_scal), 16 * sizeof(double)));
     NFB_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    NFB_CUDA(cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
+    NFB_CUDA(cudaEventCreateWithFlags(&h->aux_fork, cudaEventDisableTiming));
+    NFB_CUDA(cudaEventCreateWithFlags(&h->aux_join, cudaEventDisableTiming));
+    h->den_overlap = !(getenv("NFB_DEN_OVERLAP") && atoi(getenv("NFB_DEN_OVERLAP")) == 0);
+    // the Gram GEMMs want 128 CTAs of their own: beside the big launch they cost it as much as they save on one
+    // GPU (measured), so only NFB_DEN_OVERLAP=2 moves them as well
+    h->gram_overlap = h->den_overlap && getenv("NFB_DEN_OVERLAP") && atoi(getenv("NFB_DEN_OVERLAP")) >= 2;
     NFB_CUDA(cudaStreamSynchronize(h->stream));
     *out = h.release();
     return 0;
@@ -714,6 +832,9 @@ int nfb_destroy(nfb_handle* h) {
     }
     if (h->h_scal) cudaFreeHost(h->h_scal);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->aux_stream) { cudaStreamSynchronize(h->aux_stream); cudaStreamDestroy(h->aux_stream); }
+    if (h->aux_fork) cudaEventDestroy(h->aux_fork);
+    if (h->aux_join) cudaEventDestroy(h->aux_join);
     if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
     return 0;
@@ -975,6 +1096,7 @@ int nfb_nmf_free(nfb_nmf* s) {
         for (void* ptr : s->ipc_opened) cudaIpcCloseMemHandle(ptr);
     }
     cudaStreamSynchronize(s->h->stream);
+    if (s->h->aux_stream) cudaStreamSynchronize(s->h->aux_stream);
     for (cudaEvent_t ev : s->viol_ready)
         if (ev) cudaEventDestroy(ev);
     delete s;
@@ -1041,7 +1163,7 @@ int nfb_nmf_iterate(nfb_nmf* s, int n_iters, double* violation_out) {
     for (int it = 0; it < n_iters; ++it) {
         if (s->p.solver == 1) {
             NFB_TRY(mu_iteration(s));
-            { NFB_PHASE(s->h, "gemm_xht"); NFB_TRY(gemm_xht(s)); }  // numerator of the next W half-step
+            { NFB_PHASE(s->h, "gemm_xht"); NFB_TRY(gemm_xht_with_den(s)); }  // numerator of the next W half-step
         } else {
             NFB_TRY(cd_iteration(s, (it == n_iters - 1) ? violation_out : nullptr));
         }
@@ -1077,7 +1199,7 @@ int nfb_nmf_run(nfb_nmf* s, int* n_iter_out, double* recon_err_out) {
         double previous_error = error_at_init;
         for (n_iter = 1; n_iter <= p.max_iter; ++n_iter) {
             NFB_TRY(mu_iteration(s));
-            NFB_TRY(gemm_xht(s));
+            NFB_TRY(gemm_xht_with_den(s));
             if (p.tol > 0 && n_iter % 10 == 0) {
                 double error = 0.0;
                 NFB_TRY(p2p_check(s));
