@@ -87,6 +87,9 @@ def parse_args():
     ap.add_argument("--no-dr", action="store_true", help="skip the dual-regression subject after the e2e solve")
     ap.add_argument("--no-side", action="store_true", help="skip the side figures (C3 other solver, C2 CD)")
     ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the multi-GPU parity block")
+    ap.add_argument("--dr-subjects", type=int, default=-1,
+                    help="subjects of the C4 stream (default: 100 at N > 1 -- BASELINE config C4 --, 13 = one "
+                         "rank's share of it at N = 1; 0: skip)")
     ap.add_argument("--e2e-iters", type=int, default=0,
                     help="iterations of the e2e call (default: NFACT's max_iter=200)")
     return ap.parse_args()
@@ -474,6 +477,72 @@ def dual_regression_across_gpus(torch, dist, dev, handle, m, n, k, density, rank
             "shape": [int(m), int(n), int(k)],
             "api": "nfact_b200.nmf_dual_regression(components, X) on every rank with its own resident subject "
                    "(subjects are independent: no collective); seconds = slowest rank, best of 3"}
+
+
+def dual_regression_c4_stream(torch, dist, dev, handle, m, n, k, density, rank, world, grey, n_subjects, pool_size=2):
+    """BASELINE config C4 as written: `n_subjects` C3-shaped synthetic subjects regressed onto the k group components,
+    subjects distributed over the GPUs exactly like the product's run_locally(rank, world) (rank r takes subjects
+    r, r + world, ...; no collective), every subject through the nfact_dr per-subject pipeline: COO triplets in
+    page-locked host memory (what the .dot parser leaves) -> nfb_ingest_coo_matrix (upload + scatter into the operand
+    planes) -> dual regression -> float64 components back on the host, the next subject's ingest running beside the
+    current regression (nfact_b200.dual_regression.stream_subjects, the loop run_locally drives).
+    Host RAM cannot hold 100 x 5.2 GB of triplets, so every rank keeps `pool_size` distinct subjects (seeds
+    1000 + rank, 1000 + rank + world, ...: SURVEY 8d) and subject s re-reads pool[(s // world) % pool_size]; every
+    subject pays the full upload / ingest / solve / copy-out.  value = subjects / slowest rank's wall time."""
+    import nfact_b200
+    from nfact_b200.device import ingest_coo_resident
+    from nfact_b200.dual_regression import stream_subjects
+    mine = list(range(rank, n_subjects, world))
+    pool = []
+    for p_idx in range(min(pool_size, max(len(mine), 1))):
+        torch.cuda.empty_cache()
+        xd = synth_rows_device(torch, dev, 0, m, n, k, density, seed=1000 + rank + world * p_idx)
+        idx = xd.nonzero()
+        rows_h = torch.empty(idx.shape[0], dtype=torch.int32, pin_memory=True)
+        cols_h = torch.empty(idx.shape[0], dtype=torch.int32, pin_memory=True)
+        vals_h = torch.empty(idx.shape[0], dtype=torch.float64, pin_memory=True)
+        rows_h.copy_(idx[:, 0].to(torch.int32))
+        cols_h.copy_(idx[:, 1].to(torch.int32))
+        vals_h.copy_(xd[idx[:, 0], idx[:, 1]].to(torch.float64))
+        pool.append((rows_h.numpy(), cols_h.numpy(), vals_h.numpy()))
+        del xd, idx
+    torch.cuda.empty_cache()
+    comps = {"grey_components": grey}
+
+    def load(i, hd):
+        r_, c_, v_ = pool[i % len(pool)]
+        return ingest_coo_resident([(r_, c_, v_, 1.0)], int(m), int(n), False, hd)
+
+    # warm-up: two subjects through both handles of the prefetching loop (pool growth, page-locked result blocks)
+    for _i, _res in stream_subjects(load, min(2, len(mine)), comps, device=handle.device):
+        del _res
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    nnz_white = 0.0
+    for _i, res in stream_subjects(load, len(mine), comps, device=handle.device):
+        assert res["white_components"].shape == (k, n) and res["grey_components"].shape == (m, k)
+        nnz_white = float(np.mean(res["white_components"][:, ::997] > 0))
+        del res
+    torch.cuda.synchronize()
+    t_mine = time.perf_counter() - t0
+    t_all = t_mine
+    if world > 1:
+        t = torch.tensor([t_mine], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_all = float(t)
+    triplets = int(pool[0][0].size) if pool else 0
+    return {"value": n_subjects / t_all, "unit": "subjects/s", "subjects": int(n_subjects), "seconds": t_all,
+            "subjects_per_rank": [len(range(r, n_subjects, world)) for r in range(world)],
+            "rank0_seconds": t_mine, "triplets_per_subject": triplets,
+            "h2d_bytes_per_subject": 16 * triplets, "d2h_bytes_per_subject": 8 * k * (m + n),
+            "distinct_subjects_per_rank": len(pool), "shape": [int(m), int(n), int(k)],
+            "white_nnz_frac_sample": nnz_white,
+            "api": "nfact_b200.dual_regression.stream_subjects (the loop behind run_locally(rank, world)): triplets in "
+                   "page-locked host memory -> nfb_ingest_coo_matrix -> nmf_dual_regression -> float64 results on "
+                   "the host, next subject's ingest beside the current regression; subjects round-robin over the "
+                   "ranks, no collective"}
 
 
 def multi_gpu_parity(torch, dist, dev, handle, rank, world):
@@ -872,6 +941,30 @@ def run_ours(args):
     # ---- C4 at N > 1: dual-regression subjects are independent, one full-size subject per GPU side by side ----
     if world > 1 and want_e2e and not args.no_dr:
         dr_info = dual_regression_across_gpus(torch, dist, dev, handle, m, n, k, density, rank, world)
+    # ---- C4 as written: a stream of subjects from host triplets through the per-subject pipeline --------------
+    n_stream = args.dr_subjects if args.dr_subjects >= 0 else (100 if world > 1 else 13)
+    if want_e2e and not args.no_dr and n_stream > 0 and args.workload == "C3":
+        try:
+            grey_rows = torch.from_numpy(np.ascontiguousarray(res["grey_components"])).to(dev)
+            if world > 1:      # every rank needs the whole group map: gather the seed-row shards of the solve
+                counts = [row_range(m, r, world)[1] - row_range(m, r, world)[0] for r in range(world)]
+                padded = torch.zeros((max(counts), k), dtype=grey_rows.dtype, device=dev)
+                padded[:rows] = grey_rows
+                parts = [torch.empty_like(padded) for _ in range(world)]
+                dist.all_gather(parts, padded)
+                grey_rows = torch.cat([part[:c] for part, c in zip(parts, counts)], dim=0)
+            grey_full = grey_rows.cpu().numpy()
+            del grey_rows
+            if world > 1 and x_host is not None:
+                del x_np
+                x_host = None          # page-locked memory back before the triplet pools are pinned
+            stream_info = dual_regression_c4_stream(torch, dist, dev, handle, m, n, k, density, rank, world, grey_full,
+                                                    n_stream)
+        except Exception as exc:          # a side figure must not cost the bench line
+            stream_info = {"error": f"{type(exc).__name__}: {exc}"}
+        if dr_info is None:
+            dr_info = {}
+        dr_info["c4_stream"] = stream_info
 
     parity = None
     if world > 1 and not args.no_parity:

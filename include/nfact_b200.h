@@ -36,6 +36,9 @@ const char* nfb_version(void);
 int nfb_create(int device, void* stream, nfb_handle** out);
 int nfb_destroy(nfb_handle* h);
 int nfb_synchronize(nfb_handle* h);
+/* frees the per-subject buffers (operand planes, triplet staging) a dual-regression subject loop left cached on
+ * this handle for the next subject */
+int nfb_release_cached(nfb_handle* h);
 /* Row-sharded multi-GPU: attach an initialised ncclComm_t (one rank per GPU).  When set, the H half-step
  * all-reduces the k x n numerator and the k x k Gram W'W across ranks; W shards stay local.
  * `nccl_allreduce_fn` is the address of ncclAllReduce in the NCCL library that created the communicator. */
@@ -251,6 +254,26 @@ int nfb_component_loadings_host(nfb_handle* h, const void* subject, const void* 
  *   dead_out_host [r] (nullable): 1 for a constant row (np.corrcoef gives NaN there; here its row/column is 0). */
 int nfb_row_correlation_host(nfb_handle* h, const float* rows_host, int64_t r, int64_t n, float* sim_out_host,
                              int32_t* dead_out_host);
+
+/* ---- NMF-sso with the runs' components resident in HBM ---------------------------------------------------
+ * replaces the data movement of  NFACT/decomp/decomposition/sso/nmfsso.py:120-190 (NMFsso.run: every run's W, H
+ * returned to the parent), :137 (per-run thresholding), sso_functions.py:29-68 (similarity of the stack) and
+ * nmfsso.py:346-357 (centrotype rows as the start of the final solve).  The stacks [runs k, n] / [runs k, m] stay
+ * on the device; only the [runs k, runs k] similarity matrix and the final factors travel.
+ *   nfb_nmf_init_random : |avg N(0,1)| into both factors of a solver state (the reference draws the runs with
+ *                         random_state=None, so only the distribution is part of the contract)
+ *   nfb_sso_add_run     : factors of a finished solve -> slot `run` of the stacks, white copy z-thresholded
+ *   nfb_sso_similarity_host : Pearson correlations of the stacked white components, dead rows flagged
+ *   nfb_sso_seed_final  : gathers the centrotype rows into the (k = n_centroids) state of the final solve
+ *   nfb_nmf_factors_all_zero : sklearn's "full of zeros" check of a custom start, on the resident factors */
+typedef struct nfb_sso nfb_sso;
+int nfb_sso_create(nfb_handle* h, int64_t m, int64_t n, int k, int runs, nfb_sso** out);
+int nfb_sso_free(nfb_sso* sso);
+int nfb_nmf_init_random(nfb_nmf* s, double avg, uint64_t seed);
+int nfb_sso_add_run(nfb_sso* sso, nfb_nmf* s, int run, double zscore);
+int nfb_sso_similarity_host(nfb_sso* sso, float* sim_out_host, int32_t* dead_out_host);
+int nfb_sso_seed_final(nfb_sso* sso, nfb_nmf* s, const int32_t* centroids_host, int n_centroids);
+int nfb_nmf_factors_all_zero(nfb_nmf* s, int32_t* flags_host);
 
 /* ---- page-locked host buffers ------------------------------------------------------------------------
  * Result arrays are hundreds of MB; device-to-host copies into pageable memory run at a few GB/s, into

@@ -37,6 +37,7 @@ SIGNATURES = {
     "nfb_create": (c_int, [c_int, c_void_p, POINTER(c_void_p)]),
     "nfb_destroy": (c_int, [c_void_p]),
     "nfb_synchronize": (c_int, [c_void_p]),
+    "nfb_release_cached": (c_int, [c_void_p]),
     "nfb_set_comm": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int]),
     "nfb_nccl_unique_id": (c_int, [c_char_p, c_void_p]),
     "nfb_nccl_init_rank": (c_int, [c_void_p, c_char_p, c_void_p, c_int, c_int]),
@@ -92,6 +93,13 @@ SIGNATURES = {
     "nfb_component_wta_host": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_int64, c_double, c_void_p]),
     "nfb_component_loadings_host": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_int64, c_void_p]),
     "nfb_row_correlation_host": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
+    "nfb_sso_create": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, POINTER(c_void_p)]),
+    "nfb_sso_free": (c_int, [c_void_p]),
+    "nfb_nmf_init_random": (c_int, [c_void_p, c_double, ctypes.c_uint64]),
+    "nfb_sso_add_run": (c_int, [c_void_p, c_void_p, c_int, c_double]),
+    "nfb_sso_similarity_host": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "nfb_sso_seed_final": (c_int, [c_void_p, c_void_p, c_void_p, c_int]),
+    "nfb_nmf_factors_all_zero": (c_int, [c_void_p, c_void_p]),
     "nfb_host_alloc": (c_int, [c_int64, POINTER(c_void_p)]),
     "nfb_host_free": (c_int, [c_void_p]),
     "nfb_test_gemm": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_int64, c_void_p, c_int64,

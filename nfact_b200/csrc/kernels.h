@@ -100,6 +100,9 @@ int f64_to_f32_rowmax(const double* in, int64_t k, int64_t cols, int64_t ld_in, 
 // z[r][:] = (x[r][:] - mean_r) / ||x[r][:] - mean_r||  (fp64 statistics); dead[r] = 1 for a constant row (z = 0)
 int rows_standardize(const float* x, int64_t rows, int64_t cols, int64_t ld, float* z, int64_t ldz, int* dead,
                      cudaStream_t stream);
+// out[t][c] = |avg * N(0, 1)|, t < k, c < cols (counter-based generator keyed by seed and element index)
+int fill_abs_normal(float* out, int64_t k, int64_t cols, int64_t ld, float avg, unsigned long long seed,
+                    cudaStream_t stream);
 // *out += sum_{t,u<k} a[t][u] * b[t][u]
 int dot_small(const float* a, const float* b, int64_t k, int64_t ld, double* out, cudaStream_t stream);
 // transpose [rows, cols] (ld_in) -> [cols, rows] (ld_out); *nonfinite (nullable) is set to 1 when an input

@@ -47,17 +47,56 @@ void note_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 // per-call temporaries: cudaFree synchronises the whole device, so a call that ends on one stream would wait for the
 // next subject's upload running on another (the prefetching dual-regression loop), and a pooled free does not.
 // The pool keeps its default release threshold (unused memory goes back to the driver at the next synchronisation).
+// Exact-size recycling of the large per-subject buffers of the nfact_dr loop (operand planes, cell mask, triplet
+// staging: 32 GB per C3 subject), one cache per handle = per stream.  The stream-ordered pool is the wrong tool for
+// these: with two subjects in flight on two streams its best-fit reuse hands stream B a block stream A freed and
+// makes B wait for A's pending work (the ingest ran behind the regression instead of beside it), or it re-maps
+// tens of GB (0.2 - 0.7 s stalls in cudaMallocAsync).  A buffer returned here was last used on the handle's own
+// stream and is handed out again on that stream only: no dependency, no mapping.
+struct BigCache {
+    std::mutex mu;
+    std::vector<std::pair<void*, size_t>> idle;
+    void* get(size_t bytes) {
+        std::lock_guard<std::mutex> lock(mu);
+        for (size_t i = 0; i < idle.size(); ++i)
+            if (idle[i].second == bytes) {
+                void* ptr = idle[i].first;
+                idle.erase(idle.begin() + i);
+                return ptr;
+            }
+        return nullptr;
+    }
+    void put(void* ptr, size_t bytes) {
+        {
+            std::lock_guard<std::mutex> lock(mu);
+            if (idle.size() < 16) { idle.emplace_back(ptr, bytes); return; }
+        }
+        cudaFree(ptr);
+    }
+    void clear() {
+        std::lock_guard<std::mutex> lock(mu);
+        for (auto& e : idle) cudaFree(e.first);
+        idle.clear();
+    }
+};
+
 template <typename T>
 struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
     bool pooled = false;
     cudaStream_t pool_stream = nullptr;
+    BigCache* cache = nullptr;
     DevBuf() = default;
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
     ~DevBuf() { release(); }
     void release() {
+        if (p && cache) {
+            cache->put(p, n * sizeof(T));
+            p = nullptr;
+            cache = nullptr;
+        }
         if (p) {
             if (pooled && cudaFreeAsync(p, pool_stream) != cudaSuccess) {
                 cudaGetLastError();      // e.g. the stream is gone: fall back to the synchronous free
@@ -76,6 +115,16 @@ struct DevBuf {
         NFB_CUDA(cudaMalloc(reinterpret_cast<void**>(&p), count * sizeof(T)));
         n = count;
         if (zero) NFB_CUDA(cudaMemsetAsync(p, 0, count * sizeof(T), stream));
+        return 0;
+    }
+    // from the handle's exact-size cache (a miss is a plain cudaMalloc); goes back to the cache on release
+    int alloc_cached(BigCache* c, size_t count, cudaStream_t stream) {
+        release();
+        if (count == 0) count = 1;
+        p = static_cast<T*>(c->get(count * sizeof(T)));
+        if (p == nullptr) NFB_CUDA(cudaMalloc(reinterpret_cast<void**>(&p), count * sizeof(T)));
+        n = count;
+        cache = c;
         return 0;
     }
     int alloc_pooled(size_t count, bool zero, cudaStream_t stream) {
@@ -127,6 +176,7 @@ struct nfb_handle {
     DevBuf<int> d_int;
     double* h_scal = nullptr;     // pinned mirror
     cudaStream_t copy_stream = nullptr;   // D2H of finished results while the compute stream carries on
+    BigCache big;                         // per-subject buffers of the dual-regression loop (see BigCache)
     // second compute stream: the small k x k "denominator" GEMMs run beside the X-streaming GEMM they do not
     // depend on (their CTAs fill the SMs the big launch's last, partial wave leaves idle); NFB_DEN_OVERLAP=0: off
     cudaStream_t aux_stream = nullptr;
@@ -798,7 +848,10 @@ int nfb_create(int device, void* stream, nfb_handle** out) {
         cudaMemPool_t pool = nullptr;
         size_t free_b = 0, total_b = 0;
         if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
-            uint64_t keep = total_b / 2;
+            // 85 % of the device: the subject loop of nfact_dr keeps two C3-sized subjects (2 x 32 GB of planes and
+            // triplets) plus the regression's buffers in flight on two streams; with half the device the pool was
+            // trimmed at synchronisations and re-mapping the planes stalled cudaMallocAsync for 0.1 - 0.7 s
+            uint64_t keep = total_b / 100 * 85;
             if (getenv("NFB_POOL_KEEP_GB")) keep = static_cast<uint64_t>(atof(getenv("NFB_POOL_KEEP_GB")) * (1ull << 30));
             cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
         }
@@ -830,6 +883,7 @@ int nfb_destroy(nfb_handle* h) {
         DestroyFn fn = reinterpret_cast<DestroyFn>(dlsym(h->nccl_lib, "ncclCommDestroy"));
         if (fn) fn(h->comm);
     }
+    h->big.clear();
     if (h->h_scal) cudaFreeHost(h->h_scal);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->aux_stream) { cudaStreamSynchronize(h->aux_stream); cudaStreamDestroy(h->aux_stream); }
@@ -837,6 +891,14 @@ int nfb_destroy(nfb_handle* h) {
     if (h->aux_join) cudaEventDestroy(h->aux_join);
     if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
+    return 0;
+}
+
+int nfb_release_cached(nfb_handle* h) {
+    NFB_CHECK(h != nullptr, "handle is NULL");
+    NFB_CUDA(cudaSetDevice(h->device));
+    NFB_CUDA(cudaStreamSynchronize(h->stream));
+    h->big.clear();
     return 0;
 }
 
@@ -1049,22 +1111,29 @@ int nfb_nmf_create(nfb_handle* h, const nfb_matrix* x, int k, const nfb_nmf_para
     s->kp = round_up64(k, 16);
     s->p = *p;
     cudaStream_t st = h->stream;
-    NFB_TRY(s->wt.init(k, x->m, true, st));
-    NFB_TRY(s->hh.init(k, x->n, true, st));
+    // One GPU: the state comes from the stream-ordered pool (a cudaMalloc / cudaFree of these ~1 GB costs 5 - 100 ms
+    // of driver time per solve, and NMF-sso creates 21 states); row-sharded runs map the H master into the peers
+    // with CUDA IPC, which needs cudaMalloc memory.
+    const bool pooled = h->world <= 1;
+    auto get = [&](auto& buf, size_t count) {
+        return pooled ? buf.alloc_pooled(count, false, st) : buf.alloc(count, false, st);
+    };
+    NFB_TRY(s->wt.init(k, x->m, true, st, 0, pooled));
+    NFB_TRY(s->hh.init(k, x->n, true, st, 0, pooled));
     // the Gram factors share the padded leading dimension kp so the sweep can use float4 rows
-    NFB_TRY(s->gw.init(k, k, true, st, s->kp));
-    NFB_TRY(s->gh.init(k, k, true, st, s->kp));
-    NFB_TRY(s->gd.init(k, k, false, st, s->kp));
+    NFB_TRY(s->gw.init(k, k, true, st, s->kp, pooled));
+    NFB_TRY(s->gh.init(k, k, true, st, s->kp, pooled));
+    NFB_TRY(s->gd.init(k, k, false, st, s->kp, pooled));
     const int cg = h->cta_group;
     s->s_w = gemm_pick_splits(x->m, x->n, cg, k);
     // row-sharded: W'X runs unsplit (its tiles go straight to their owners' inboxes on the peer-memory path)
     s->s_h = h->world > 1 ? 1 : gemm_pick_splits(x->n, x->m, cg, k);
     s->s_gw = gemm_pick_splits(k, x->m, cg, k);
     s->s_gh = gemm_pick_splits(k, x->n, cg, k);
-    NFB_TRY(s->part_w.alloc(static_cast<size_t>(s->s_w) * k * s->wt.ld, false, st));
-    NFB_TRY(s->part_h.alloc(static_cast<size_t>(s->s_h) * k * s->hh.ld, false, st));
-    NFB_TRY(s->part_den.alloc(static_cast<size_t>(k) * std::max(s->wt.ld, s->hh.ld), false, st));
-    NFB_TRY(s->part_gram.alloc(static_cast<size_t>(std::max(s->s_gw, s->s_gh)) * k * s->kp, false, st));
+    NFB_TRY(get(s->part_w, static_cast<size_t>(s->s_w) * k * s->wt.ld));
+    NFB_TRY(get(s->part_h, static_cast<size_t>(s->s_h) * k * s->hh.ld));
+    NFB_TRY(get(s->part_den, static_cast<size_t>(k) * std::max(s->wt.ld, s->hh.ld)));
+    NFB_TRY(get(s->part_gram, static_cast<size_t>(std::max(s->s_gw, s->s_gh)) * k * s->kp));
     if (h->world > 1) {
         s->slice_cols = round_up64(ceil_div64(x->n, h->world), 8);
         NFB_TRY(s->num_h.alloc(static_cast<size_t>(k) * std::max<int64_t>(s->hh.ld, s->slice_cols), true, st));
@@ -1222,8 +1291,8 @@ int nfb_nmf_run(nfb_nmf* s, int* n_iter_out, double* recon_err_out) {
         nfb_handle* h = s->h;
         const size_t w_elems = static_cast<size_t>(s->wt.kp) * s->wt.ld, h_elems = static_cast<size_t>(s->hh.kp) * s->hh.ld;
         for (int b = 0; b < 2; ++b) {
-            if (s->snap_w[b].p == nullptr) NFB_TRY(s->snap_w[b].alloc(w_elems, false, h->stream));
-            if (s->snap_h[b].p == nullptr) NFB_TRY(s->snap_h[b].alloc(h_elems, false, h->stream));
+            if (s->snap_w[b].p == nullptr) NFB_TRY(s->snap_w[b].alloc_pooled(w_elems, false, h->stream));
+            if (s->snap_h[b].p == nullptr) NFB_TRY(s->snap_h[b].alloc_pooled(h_elems, false, h->stream));
             if (s->viol_ready[b] == nullptr) NFB_CUDA(cudaEventCreateWithFlags(&s->viol_ready[b], cudaEventDisableTiming));
         }
         double violation_init = 0.0;
@@ -1816,15 +1885,17 @@ static int ingest_single_to_planes(nfb_handle* h, const int32_t* rows_host, cons
     DevBuf<unsigned int> mask;
     DevBuf<int> rows, cols;
     DevBuf<double> vals;
-    NFB_TRY(x->hi.alloc_pooled(cells, false, st));
-    NFB_TRY(x->lo.alloc_pooled(cells, false, st));
+    NFB_TRY(x->hi.alloc_cached(&h->big, cells, st));
+    NFB_TRY(x->lo.alloc_cached(&h->big, cells, st));
     NFB_TRY(x->inv_scale.alloc_pooled(1, true, st));
-    NFB_TRY(mask.alloc_pooled((cells + 31) / 32, false, st));
+    NFB_TRY(mask.alloc_cached(&h->big, (cells + 31) / 32, st));
     cudaEvent_t uploaded = nullptr;
     if (upload) {
-        NFB_TRY(rows.alloc_pooled(nnz, false, st));
-        NFB_TRY(cols.alloc_pooled(nnz, false, st));
-        NFB_TRY(vals.alloc_pooled(nnz, false, st));
+        // staging sized in 64 Mi-triplet steps so that subjects with slightly different counts share the cache
+        const size_t nnz_cap = static_cast<size_t>(round_up64(std::max<int64_t>(nnz, 1), int64_t(1) << 26));
+        NFB_TRY(rows.alloc_cached(&h->big, nnz_cap, st));
+        NFB_TRY(cols.alloc_cached(&h->big, nnz_cap, st));
+        NFB_TRY(vals.alloc_cached(&h->big, nnz_cap, st));
         marks.mark("alloc");
         // the triplets travel on the copy stream while the planes and the mask are zeroed on the main one
         // (the staging buffers are stream-ordered allocations of the main stream: the copy stream may only touch
@@ -2051,21 +2122,16 @@ int nfb_matrix_matmul(nfb_handle* h, const nfb_matrix* x, int trans, const float
 }
 
 // ---- NMF-sso similarity ------------------------------------------------------------------------------
-int nfb_row_correlation_host(nfb_handle* h, const float* rows_host, int64_t r, int64_t n, float* sim_out_host,
-                             int32_t* dead_out_host) {
-    NFB_CHECK(h != nullptr && rows_host != nullptr && sim_out_host != nullptr, "NULL argument");
-    NFB_CHECK(r >= 1 && n >= 2, "need at least one row and two columns");
-    NFB_CUDA(cudaSetDevice(h->device));
+// rows_dev [r, n] float32 (contiguous) -> Pearson correlations of the rows on the host
+static int row_correlation_dev(nfb_handle* h, const float* rows_dev, int64_t r, int64_t n, float* sim_out_host,
+                               int32_t* dead_out_host) {
     cudaStream_t st = h->stream;
-    DevBuf<float> raw, z, sim;
+    DevBuf<float> z, sim;
     DevBuf<int> dead;
-    NFB_TRY(raw.alloc(static_cast<size_t>(r) * n, false, st));
     NFB_TRY(z.alloc(static_cast<size_t>(r) * n, false, st));
     NFB_TRY(sim.alloc(static_cast<size_t>(r) * r, false, st));
     NFB_TRY(dead.alloc(r, true, st));
-    NFB_CUDA(cudaMemcpyAsync(raw.p, rows_host, sizeof(float) * r * n, cudaMemcpyHostToDevice, st));
-    NFB_TRY(rows_standardize(raw.p, r, n, n, z.p, n, dead.p, st));
-    raw.release();
+    NFB_TRY(rows_standardize(rows_dev, r, n, n, z.p, n, dead.p, st));
     // corr = Z Z': Z as the resident "matrix" (K-major read), 512 rows of Z at a time as the factor operand
     nfb_matrix* zmat = nullptr;
     NFB_TRY(nfb_matrix_from_device(h, z.p, r, n, n, &zmat));
@@ -2075,6 +2141,139 @@ int nfb_row_correlation_host(nfb_handle* h, const float* rows_host, int64_t r, i
     if (dead_out_host)
         NFB_CUDA(cudaMemcpyAsync(dead_out_host, dead.p, sizeof(int) * r, cudaMemcpyDeviceToHost, st));
     NFB_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int nfb_row_correlation_host(nfb_handle* h, const float* rows_host, int64_t r, int64_t n, float* sim_out_host,
+                             int32_t* dead_out_host) {
+    NFB_CHECK(h != nullptr && rows_host != nullptr && sim_out_host != nullptr, "NULL argument");
+    NFB_CHECK(r >= 1 && n >= 2, "need at least one row and two columns");
+    NFB_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    DevBuf<float> raw;
+    NFB_TRY(raw.alloc(static_cast<size_t>(r) * n, false, st));
+    NFB_CUDA(cudaMemcpyAsync(raw.p, rows_host, sizeof(float) * r * n, cudaMemcpyHostToDevice, st));
+    return row_correlation_dev(h, raw.p, r, n, sim_out_host, dead_out_host);
+}
+
+// ---- NMF-sso on the device --------------------------------------------------------------------------------
+// The reference's NMFsso (nmfsso.py:62-238, 322-360) runs N random-initialised solves, z-thresholds every run's white
+// components, stacks all runs, correlates the stack, clusters it on the host and starts the final solve from the
+// centrotype rows.  Here the stacks live in HBM: a run's factors are copied from the solver state into the stacks
+// (device to device) and thresholded there, the similarity is computed from the resident stack, the centrotypes
+// are gathered on the device straight into the final solver state.  Only the [R, R] similarity matrix and the
+// final factors ever travel to the host.
+struct nfb_sso {
+    nfb_handle* h = nullptr;
+    int64_t m = 0, n = 0;
+    int k = 0, runs = 0;
+    DevBuf<float> white;    // [runs * k][n]   thresholded white components of every run
+    DevBuf<float> grey;     // [runs * k][m]   grey components of every run, component-major
+    DevBuf<double> stats;
+};
+
+int nfb_sso_create(nfb_handle* h, int64_t m, int64_t n, int k, int runs, nfb_sso** out) {
+    NFB_CHECK(h != nullptr && out != nullptr, "NULL argument");
+    NFB_CHECK(m > 0 && n > 0 && k > 0 && runs > 0, "bad NMF-sso shape");
+    NFB_CUDA(cudaSetDevice(h->device));
+    std::unique_ptr<nfb_sso> s(new nfb_sso());
+    s->h = h;
+    s->m = m;
+    s->n = n;
+    s->k = k;
+    s->runs = runs;
+    NFB_TRY(s->white.alloc(static_cast<size_t>(runs) * k * n, true, h->stream));
+    NFB_TRY(s->grey.alloc(static_cast<size_t>(runs) * k * m, true, h->stream));
+    NFB_TRY(s->stats.alloc(static_cast<size_t>(4) * k, false, h->stream));
+    *out = s.release();
+    return 0;
+}
+
+int nfb_sso_free(nfb_sso* s) {
+    if (s == nullptr) return 0;
+    cudaSetDevice(s->h->device);
+    cudaStreamSynchronize(s->h->stream);
+    delete s;
+    return 0;
+}
+
+// |avg N(0,1)| into both factors of a solver state (sklearn's init='random' distribution, _nmf.py:296-307)
+int nfb_nmf_init_random(nfb_nmf* s, double avg, uint64_t seed) {
+    NFB_CHECK(s != nullptr, "NULL argument");
+    nfb_handle* h = s->h;
+    NFB_CHECK(h->world <= 1, "nfb_nmf_init_random is for replicas on one GPU (row-sharded runs draw on the host)");
+    NFB_CUDA(cudaSetDevice(h->device));
+    NFB_TRY(fill_abs_normal(s->hh.f.p, s->k, s->x->n, s->hh.ld, static_cast<float>(avg), seed, h->stream));
+    NFB_TRY(fill_abs_normal(s->wt.f.p, s->k, s->x->m, s->wt.ld, static_cast<float>(avg), seed ^ 0x5bf03635f0a5b0c1ULL,
+                            h->stream));
+    return nmf_prepare_factors(s);
+}
+
+// factors of a finished run -> rows [run k, (run + 1) k) of the stacks; the white copy is z-thresholded per
+// component in place (thresholding(components, zscore), base/matrix_handling.py:218-238; zscore <= 0: left as is)
+int nfb_sso_add_run(nfb_sso* sso, nfb_nmf* s, int run, double zscore) {
+    NFB_CHECK(sso != nullptr && s != nullptr, "NULL argument");
+    NFB_CHECK(run >= 0 && run < sso->runs, "run index out of range");
+    NFB_CHECK(s->k == sso->k && s->x->m == sso->m && s->x->n == sso->n, "solver state does not match the NMF-sso shape");
+    nfb_handle* h = sso->h;
+    NFB_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    float* white = sso->white.p + static_cast<int64_t>(run) * sso->k * sso->n;
+    float* grey = sso->grey.p + static_cast<int64_t>(run) * sso->k * sso->m;
+    NFB_CUDA(cudaMemcpy2DAsync(white, sso->n * sizeof(float), s->hh.f.p, s->hh.ld * sizeof(float),
+                               sso->n * sizeof(float), sso->k, cudaMemcpyDeviceToDevice, st));
+    NFB_CUDA(cudaMemcpy2DAsync(grey, sso->m * sizeof(float), s->wt.f.p, s->wt.ld * sizeof(float),
+                               sso->m * sizeof(float), sso->k, cudaMemcpyDeviceToDevice, st));
+    if (zscore > 0.0) {
+        NFB_TRY(comp_threshold<float>(white, sso->k, sso->n, sso->n, nullptr, 1, zscore, sso->stats.p, st));
+        note_launch(2);
+    }
+    return 0;
+}
+
+int nfb_sso_similarity_host(nfb_sso* sso, float* sim_out_host, int32_t* dead_out_host) {
+    NFB_CHECK(sso != nullptr && sim_out_host != nullptr, "NULL argument");
+    NFB_CHECK(sso->n >= 2, "need at least two columns");
+    NFB_CUDA(cudaSetDevice(sso->h->device));
+    return row_correlation_dev(sso->h, sso->white.p, static_cast<int64_t>(sso->runs) * sso->k, sso->n, sim_out_host,
+                               dead_out_host);
+}
+
+// start of the final solve (nmfsso.py:346-357): W = stacked grey[:, centroids], H = stacked white[centroids, :]
+int nfb_sso_seed_final(nfb_sso* sso, nfb_nmf* s, const int32_t* centroids_host, int n_centroids) {
+    NFB_CHECK(sso != nullptr && s != nullptr && centroids_host != nullptr, "NULL argument");
+    NFB_CHECK(n_centroids == s->k, "the final solver state must have one component per centrotype");
+    NFB_CHECK(s->x->m == sso->m && s->x->n == sso->n, "solver state does not match the NMF-sso shape");
+    nfb_handle* h = sso->h;
+    NFB_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    const int64_t rows = static_cast<int64_t>(sso->runs) * sso->k;
+    for (int c = 0; c < n_centroids; ++c) {
+        const int64_t r = centroids_host[c];
+        NFB_CHECK(r >= 0 && r < rows, "centrotype index out of range");
+        NFB_CUDA(cudaMemcpyAsync(s->hh.f.p + static_cast<int64_t>(c) * s->hh.ld, sso->white.p + r * sso->n,
+                                 sizeof(float) * sso->n, cudaMemcpyDeviceToDevice, st));
+        NFB_CUDA(cudaMemcpyAsync(s->wt.f.p + static_cast<int64_t>(c) * s->wt.ld, sso->grey.p + r * sso->m,
+                                 sizeof(float) * sso->m, cudaMemcpyDeviceToDevice, st));
+    }
+    return nmf_prepare_factors(s);
+}
+
+// sklearn's checks on a custom start (_nmf.py:1186-1203) for factors that never visit the host:
+// flags[0] = 1 when W is all zeros, flags[1] = 1 when H is all zeros (values are non-negative by construction)
+int nfb_nmf_factors_all_zero(nfb_nmf* s, int32_t* flags_host) {
+    NFB_CHECK(s != nullptr && flags_host != nullptr, "NULL argument");
+    nfb_handle* h = s->h;
+    NFB_CUDA(cudaSetDevice(h->device));
+    std::vector<unsigned int> bits(2 * s->kp);
+    NFB_CUDA(cudaMemcpyAsync(bits.data(), s->wt.rowmax.p, sizeof(unsigned int) * s->kp, cudaMemcpyDeviceToHost, h->stream));
+    NFB_CUDA(cudaMemcpyAsync(bits.data() + s->kp, s->hh.rowmax.p, sizeof(unsigned int) * s->kp, cudaMemcpyDeviceToHost, h->stream));
+    NFB_CUDA(cudaStreamSynchronize(h->stream));
+    for (int f = 0; f < 2; ++f) {
+        unsigned int any = 0;
+        for (int t = 0; t < s->k; ++t) any |= bits[f * s->kp + t];
+        flags_host[f] = any == 0u ? 1 : 0;
+    }
     return 0;
 }
 

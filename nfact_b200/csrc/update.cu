@@ -218,6 +218,34 @@ rows_standardize_kernel(const float* __restrict__ x, int64_t cols, int64_t ld, f
         z[r * ldz + j] = static_cast<float>((static_cast<double>(row[j]) - mean) * inv);
 }
 
+
+// |avg * N(0, 1)| into a factor [k, cols] (ld): counter-based generator (splitmix64 of seed and element index ->
+// two uniforms -> Box-Muller), one normal pair per two elements.  The NMF-sso runs draw their random initialisation
+// with random_state=None in the reference (nmfsso.py:133), so only the distribution is part of the contract.
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
+    x += 0x9E3779B97F4A7C15ULL;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+    return x ^ (x >> 31);
+}
+__global__ void fill_abs_normal_kernel(float* __restrict__ out, int64_t k, int64_t cols, int64_t ld, float avg,
+                                       unsigned long long seed) {
+    const int64_t pairs_per_row = (cols + 1) / 2;
+    const int64_t total = k * pairs_per_row;
+    for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t t = idx / pairs_per_row, c = 2 * (idx - t * pairs_per_row);
+        const unsigned long long bits = splitmix64(splitmix64(seed) ^ static_cast<unsigned long long>(idx));
+        const float u1 = (static_cast<float>(static_cast<unsigned int>(bits >> 40)) + 1.0f) * (1.0f / 16777216.0f);  // (0, 1]
+        const float u2 = static_cast<float>(static_cast<unsigned int>(bits) >> 8) * (1.0f / 16777216.0f);           // [0, 1)
+        const float rad = sqrtf(-2.0f * __logf(u1));
+        float sn, cs;
+        __sincosf(6.283185307179586f * u2, &sn, &cs);
+        out[t * ld + c] = fabsf(avg * rad * cs);
+        if (c + 1 < cols) out[t * ld + c + 1] = fabsf(avg * rad * sn);
+    }
+}
+
 int col_blocks(int64_t cols, int per_block, int cap) {
     return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(ceil_div64(cols, per_block), cap)));
 }
@@ -330,6 +358,16 @@ int transpose_f64(const double* in, int64_t rows, int64_t cols, int64_t ld_in, d
     if (rows * cols == 0) return 0;
     dim3 grid(static_cast<unsigned>(ceil_div64(cols, 32)), static_cast<unsigned>(ceil_div64(rows, 32)));
     transpose_kernel<double, double><<<grid, dim3(32, 8), 0, stream>>>(in, rows, cols, ld_in, out, ld_out, nullptr);
+    NFB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int fill_abs_normal(float* out, int64_t k, int64_t cols, int64_t ld, float avg, unsigned long long seed,
+                    cudaStream_t stream) {
+    if (k * cols == 0) return 0;
+    const int64_t pairs = k * ((cols + 1) / 2);
+    const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(ceil_div64(pairs, 256), sm_count() * 8)));
+    fill_abs_normal_kernel<<<grid, 256, 0, stream>>>(out, k, cols, ld, avg, seed);
     NFB_CUDA(cudaGetLastError());
     return 0;
 }

@@ -244,6 +244,16 @@ class NmfState:
         check(self.handle.lib.nfb_nmf_run(self._ptr, byref(n_iter), byref(err)))
         return n_iter.value, err.value
 
+    def init_random(self, avg: float, seed: int) -> None:
+        """|avg N(0, 1)| into both factors on the device (the distribution of sklearn's init='random')."""
+        check(self.handle.lib.nfb_nmf_init_random(self._ptr, float(avg), int(seed) & 0xFFFFFFFFFFFFFFFF))
+
+    def factors_all_zero(self):
+        """(W is all zeros, H is all zeros) for the factors currently in the state."""
+        flags = (c_int * 2)()
+        check(self.handle.lib.nfb_nmf_factors_all_zero(self._ptr, flags))
+        return bool(flags[0]), bool(flags[1])
+
     @property
     def exchange_mode(self) -> str:
         """'single', 'nccl' or 'p2p': how the H half-step of a row-sharded solve exchanges data."""
@@ -259,6 +269,45 @@ class NmfState:
     def free(self) -> None:
         if self._ptr:
             self.handle.lib.nfb_nmf_free(self._ptr)
+            self._ptr = c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class SsoStacks:
+    """The components of all NMF-sso runs, resident in HBM (nfb_sso_*): every finished run's factors are copied
+    into the stacks on the device (white copy z-thresholded there), the similarity matrix of the stack is the only
+    thing that goes to the host for clustering, and the centrotype rows are gathered on the device into the state
+    of the final solve."""
+
+    def __init__(self, x: DeviceMatrix, k: int, runs: int):
+        self.handle, self.k, self.runs = x.handle, int(k), int(runs)
+        self.m, self.n = x.shape
+        self._ptr = c_void_p()
+        check(self.handle.lib.nfb_sso_create(self.handle.ptr, self.m, self.n, self.k, self.runs, byref(self._ptr)))
+
+    def add_run(self, state: "NmfState", run: int, zscore: float) -> None:
+        check(self.handle.lib.nfb_sso_add_run(self._ptr, state._ptr, int(run), float(zscore)))
+
+    def similarity(self):
+        """(Pearson correlations [R, R] float32 of the stacked white components, dead-row flags [R])."""
+        rows = self.runs * self.k
+        sim = np.empty((rows, rows), dtype=np.float32)
+        dead = np.zeros(rows, dtype=np.int32)
+        check(self.handle.lib.nfb_sso_similarity_host(self._ptr, sim.ctypes.data, dead.ctypes.data))
+        return sim, dead
+
+    def seed_final(self, state: "NmfState", centroids) -> None:
+        idx = np.ascontiguousarray(centroids, dtype=np.int32)
+        check(self.handle.lib.nfb_sso_seed_final(self._ptr, state._ptr, idx.ctypes.data, int(idx.size)))
+
+    def free(self) -> None:
+        if self._ptr:
+            self.handle.lib.nfb_sso_free(self._ptr)
             self._ptr = c_void_p()
 
     def __del__(self):

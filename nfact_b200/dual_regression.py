@@ -187,6 +187,8 @@ def stream_subjects(load_matrix, n_subjects: int, components: dict, device: int 
                 prep.free()
         for extra in handles[1:]:
             extra.close()
+        # the ingest keeps every subject's planes / staging buffers for the next subject: hand them back now
+        check(first.lib.nfb_release_cached(first.ptr))
 
 
 def run_locally(list_of_subject_dirs: list, components: dict, seeds: list, threshold: int = 3,

@@ -236,9 +236,10 @@ class NMF:
             regs = compute_regularization(global_rows(xdev.handle, m), n, p["alpha_W"], p["alpha_H"], p["l1_ratio"])
             mark("init / checks")
             state = NmfState(xdev, k, make_params(p["solver"], p["max_iter"], p["tol"], regs, p["verbose"]))
+            mark("state")
             try:
                 state.set_factors(W0, H0)
-                mark("state + factor upload")
+                mark("factor upload")
                 self.n_iter_, self.reconstruction_err_ = state.run()
                 mark("solve")
                 Wf, Hf = state.get_factors()

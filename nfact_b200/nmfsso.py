@@ -9,7 +9,10 @@ centrotype per cluster -> final ``init='custom'`` solve.
 Difference by design: the reference copies X into POSIX shared memory and forks ``n_cores`` joblib workers;
 here X is uploaded to HBM once (``DeviceMatrix``) and the N+1 solves reuse it, so ``n_cores`` only keeps its
 meaning as "run the sso loop" and the single-run path does not inherit the reference's ``range(colours)``
-TypeError (nmfsso.py:207).  Plots / csv (sso_plotting.py) are out of scope.
+TypeError (nmfsso.py:207).  ``nmf_sso`` on one GPU keeps the runs' components on the device as well
+(``nmf_sso_resident``: device random starts, resident stacks, similarity from the stack, centrotypes gathered
+into the final solve; ``NFB_SSO_RESIDENT=0`` or the ``NMFsso`` class give the host-stack flow).  Plots / csv
+(sso_plotting.py) are out of scope.
 """
 from __future__ import annotations
 
@@ -45,6 +48,11 @@ def compute_similairty_matrix(components: np.ndarray, handle=None) -> np.ndarray
     dead = np.zeros(r, dtype=np.int32)
     _lib.check(handle.lib.nfb_row_correlation_host(handle.ptr, c_void_p(comps.ctypes.data), r, n,
                                                    c_void_p(sim32.ctypes.data), c_void_p(dead.ctypes.data)))
+    return _finish_similarity(sim32, dead)
+
+
+def _finish_similarity(sim32: np.ndarray, dead: np.ndarray) -> np.ndarray:
+    """Device correlations -> the matrix ``compute_similairty_matrix`` returns (float64, symmetric, clipped)."""
     sim = sim32.astype(np.float64)
     sim = 0.5 * (sim + sim.T)                 # the two triangles come from different tile passes
     # A component that a run drove to all-zero has no variance: corrcoef gives NaN there and scipy's
@@ -135,6 +143,85 @@ class NMFsso:
         return results
 
 
+def _run_seed(run: int) -> int:
+    """64-bit seed of a run's random start: OS entropy like ``random_state=None`` in the reference (nmfsso.py:133);
+    NFB_SSO_SEED pins it (base + run index) for reproducible tests."""
+    import os
+    pinned = os.environ.get("NFB_SSO_SEED")
+    if pinned is not None:
+        return (int(pinned) * 1000003 + run) & 0xFFFFFFFFFFFFFFFF
+    return int.from_bytes(os.urandom(8), "little")
+
+
+def nmf_sso_resident(xdev: DeviceMatrix, parameters: dict, args: dict) -> dict:
+    """``nmf_sso`` with everything between the upload of X and the download of the final factors on the device
+    (SURVEY section 8 f1): the N random starts are drawn on the device, every run's factors go from the solver
+    state into the resident stacks (white copy z-thresholded there, nmfsso.py:137), the similarity of the stack is
+    computed from the stack where it lies, the centrotype rows are gathered on the device into the final solve's
+    state.  Host traffic: the [N k, N k] similarity matrix for scipy's linkage, and the final W, H.
+
+    Returns (final_nmf, sim, dis, partitions, centroids)."""
+    from .device import NmfState, SsoStacks, make_params
+    from .nmf import _check_params, compute_regularization
+    col = colours()
+    runs = int(args["iterations"])
+    p = _check_params(dict(parameters, init="random"))
+    k = int(p["n_components"])
+    m, n = xdev.shape
+    regs = compute_regularization(m, n, p["alpha_W"], p["alpha_H"], p["l1_ratio"])
+    nprint(f"{col['pink']}NMF iterations: {col['reset']}{runs}")
+    stacks = None
+    try:
+        try:
+            if xdev.has_negative:
+                raise ValueError("Negative values in data passed to NMF (input X)")
+            stacks = SsoStacks(xdev, k, runs)
+            avg = float(np.sqrt(xdev.mean / k))          # sklearn _nmf.py:296
+            for run in range(runs):
+                nprint(f"{col['pink']}Run: {col['reset']}{run + 1}/{runs}")
+                state = NmfState(xdev, k, make_params(p["solver"], p["max_iter"], p["tol"], regs, p["verbose"]))
+                try:
+                    state.init_random(avg, _run_seed(run))
+                    state.run()
+                    stacks.add_run(state, run, 3)       # thresholding(components, 3), nmfsso.py:137
+                finally:
+                    state.free()
+        except Exception as e:
+            error_and_exit(False, f"Unable to perform NMF due to {e}")
+        sim = _finish_similarity(*stacks.similarity())
+        dis = sim2dis(sim)
+        partitions = clustering_components(dis, args["dim"])
+        error_and_exit(partitions is not None and partitions.size != 0,
+                       "Clustering Failed. Please check Num of dims")
+        centroids = idx2centrotype(sim, partitions)
+        parameters["random_state"] = None
+        parameters["init"] = "custom"
+        parameters["n_components"] = centroids.shape[0]
+        kc = int(centroids.shape[0])
+        final_nmf = None
+        try:
+            regs_c = compute_regularization(m, n, p["alpha_W"], p["alpha_H"], p["l1_ratio"])
+            state = NmfState(xdev, kc, make_params(p["solver"], p["max_iter"], p["tol"], regs_c, p["verbose"]))
+            try:
+                stacks.seed_final(state, centroids)
+                w_zero, h_zero = state.factors_all_zero()        # sklearn _check_init on a custom start
+                if h_zero:
+                    raise ValueError("Array passed to NMF (input H) is full of zeros.")
+                if w_zero:
+                    raise ValueError("Array passed to NMF (input W) is full of zeros.")
+                state.run()
+                w_fin, h_fin = state.get_factors()
+            finally:
+                state.free()
+            final_nmf = {"grey_components": w_fin, "white_components": h_fin}
+        except Exception as e:
+            error_and_exit(False, f"Unable to perform NMF due to {e}")
+        return final_nmf, sim, dis, partitions, centroids
+    finally:
+        if stacks is not None:
+            stacks.free()
+
+
 def _reference_sso_outputs(args: dict, sim, dis, partitions, centroids) -> None:
     """The reference ends ``nmf_sso`` with ``nmf_sso_output_wrapper(args['outdir'], ...)`` (nmfsso.py:264-320, 359):
     cluster_stats.csv and the similarity / cluster plots under nfact_decomp/sso_output.  Those writers are plotting
@@ -170,7 +257,13 @@ def nmf_sso(fdt_matrix, parameters: dict, args: dict) -> dict:
                    f"over {multigpu.context().world} GPUs")
             results, xdev = multigpu.sso_runs_distributed(parameters, np.asarray(fdt_matrix), args["iterations"])
         else:
+            import os
             xdev = DeviceMatrix.from_host(np.asarray(fdt_matrix)) if owns else fdt_matrix
+            if os.environ.get("NFB_SSO_RESIDENT", "1") != "0":
+                # one H2D of X, one D2H of the result: the runs' components never leave the GPU
+                final_nmf, sim, dis, partitions, centroids = nmf_sso_resident(xdev, parameters, args)
+                _reference_sso_outputs(args, sim, dis, partitions, centroids)
+                return final_nmf
             results = NMFsso(xdev, args["iterations"], parameters, args.get("n_cores", 1)).run()
         w_components = np.vstack(results["white"])
         g_components = np.hstack(results["grey"])

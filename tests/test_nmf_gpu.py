@@ -187,6 +187,67 @@ def test_nmf_sso_runs_on_resident_matrix():
     assert single["white_components"].shape == (k, 210)
 
 
+def test_nmf_sso_resident_flow_matches_host_stack_flow(monkeypatch):
+    """nmf_sso with the runs' components resident (device random starts, stacks, similarity from the
+    stack, centrotypes gathered into the final solve) against the host-stack flow (NMFsso: every run's W, H copied
+    out, stacked and re-uploaded) on a planted study whose runs agree: same number of components, matched
+    components correlate, same quality of fit.  The starts differ (device generator vs numpy), the fixed point of
+    a well-separated study does not."""
+    import nfact_b200
+    from scipy.optimize import linear_sum_assignment
+    rng = np.random.default_rng(5)
+    k, m, n = 4, 150, 260
+    Wp = np.zeros((m, k)); Hp = np.zeros((k, n))
+    for t in range(k):                                   # disjoint supports: the runs agree up to permutation
+        r0, r1, c0, c1 = t * m // k, (t + 1) * m // k, t * n // k, (t + 1) * n // k
+        Wp[r0:r1, t] = rng.gamma(2.0, 1.0, r1 - r0)
+        Hp[t, c0:c1] = rng.gamma(2.0, 1.0, c1 - c0)
+    X = (Wp @ Hp * 50 + 0.01 * rng.random((m, n))).astype(np.float32)
+    args = {"no_sso": False, "iterations": 5, "n_cores": 1, "dim": k}
+    monkeypatch.setenv("NFB_SSO_SEED", "11")
+    res_dev = nfact_b200.nmf_sso(X, dict(nfact_b200.get_parameters(None, "nmf", k), alpha_W=1e-4, max_iter=200), dict(args))
+    monkeypatch.setenv("NFB_SSO_RESIDENT", "0")
+    res_host = nfact_b200.nmf_sso(X, dict(nfact_b200.get_parameters(None, "nmf", k), alpha_W=1e-4, max_iter=200), dict(args))
+    assert res_dev["white_components"].shape == res_host["white_components"].shape == (k, n)
+    assert res_dev["grey_components"].shape == (m, k)
+    corr = np.corrcoef(res_dev["white_components"], res_host["white_components"])[:k, k:]
+    rows, cols = linear_sum_assignment(-corr)
+    assert corr[rows, cols].min() > 0.99
+    for res in (res_dev, res_host):
+        rel = np.linalg.norm(X - res["grey_components"] @ res["white_components"]) / np.linalg.norm(X)
+        assert rel < 0.05
+
+
+def test_device_random_start_has_sklearns_distribution():
+    """nfb_nmf_init_random: |avg N(0, 1)| (sklearn _nmf.py:296-307) -- half-normal moments of both factors, different
+    seeds give different draws, the same seed the same."""
+    from nfact_b200.device import DeviceMatrix, NmfState, make_params
+    rng = np.random.default_rng(0)
+    m, n, k = 700, 1500, 12
+    X = rng.random((m, n)).astype(np.float32)
+    xdev = DeviceMatrix.from_host(X)
+    st = NmfState(xdev, k, make_params("cd", 5, 0.0, (0.0, 0.0, 0.0, 0.0)))
+    try:
+        avg = 0.37
+        st.init_random(avg, 123)
+        W1, H1 = st.get_factors()
+        st.init_random(avg, 123)
+        W2, H2 = st.get_factors()
+        st.init_random(avg, 124)
+        W3, H3 = st.get_factors()
+    finally:
+        st.free(); xdev.free()
+    assert np.array_equal(W1, W2) and np.array_equal(H1, H2)
+    assert not np.array_equal(W1, W3) and not np.array_equal(H1, H3)
+    for F in (W1, H1, H3):
+        assert (F >= 0).all()
+        z = F.astype(np.float64) / avg
+        assert abs(z.mean() - np.sqrt(2 / np.pi)) < 0.02          # E|N| = sqrt(2/pi)
+        assert abs((z ** 2).mean() - 1.0) < 0.03                 # E N^2 = 1
+        assert abs((z > 1.0).mean() - 0.3173) < 0.02             # P(|N| > 1)
+    assert abs(np.corrcoef(W1.ravel()[:8000], H1.ravel()[:8000])[0, 1]) < 0.05
+
+
 @pytest.mark.parametrize("solver", ["mu", "cd"])
 def test_more_than_256_components(solver):
     """k > 256 (configs[4] uses k = 500): the component dimension is tiled over several GEMM launches."""
