@@ -676,6 +676,44 @@ def side_figures(torch, dev, stream, handle, xmat, w0, h0, k, main_solver):
         torch.cuda.empty_cache()
     except Exception as exc:              # a side figure must not cost the bench line
         out["error"] = f"{type(exc).__name__}: {exc}"
+    try:
+        # BASELINE configs[4]: 59 412 x 230 000, k = 500 (54.7 GB of operand planes).  k > 256: the component
+        # dimension is tiled over two GEMM launches per product, so X is streamed four times per iteration; the
+        # bound is the tensor pipe (4 m n k flops at the measured bf16 rate against 8 m n bytes).
+        free_b, _total_b = torch.cuda.mem_get_info(dev)
+        m5, n5, k5, d5 = WORKLOADS["C5"]
+        if free_b > 2.4 * 4.0 * m5 * n5:
+            x5 = torch.empty((m5, n5), dtype=torch.float32, device=dev)
+            step = (m5 + 7) // 8
+            total5 = 0.0
+            for r0 in range(0, m5, step):          # in row blocks: the generator's scratch is a few times its output
+                r1 = min(m5, r0 + step)
+                x5[r0:r1] = synth_rows_device(torch, dev, r0, r1 - r0, n5, k5, d5)
+                total5 += float(x5[r0:r1].sum(dtype=torch.float64))
+                torch.cuda.empty_cache()
+            mean5 = total5 / (m5 * n5)
+            stream.synchronize()
+            xm5 = DeviceMatrix.from_device_ptr(x5.data_ptr(), m5, n5, n5, handle=handle)
+            del x5
+            torch.cuda.empty_cache()
+            w5, h5 = random_init(torch, dev, mean5, m5, n5, k5, 0)
+            st = NmfState(xm5, k5, make_params("cd", 10 ** 6, 0.0, regularization(m5, n5, k5)))
+            stream.synchronize()
+            st.set_factors_dev(w5.data_ptr(), h5.data_ptr())
+            sec = _time_iterations(torch, stream, handle, st, 3, 5)
+            st.free()
+            xm5.free()
+            hbm_peak, tc_peak, _src = measured_peaks()
+            t_roof = max(8.0 * m5 * n5 / (hbm_peak * 1e9), 4.0 * m5 * n5 * k5 / (tc_peak * 1e12))
+            out["C5_cd"] = {"seconds_per_iter": sec, "iter_per_s": 1.0 / sec, "roofline_step_frac": t_roof / sec,
+                            "bound": "tensor", "mma_flops_per_iter": 3.0 * 4.0 * m5 * n5 * (16 * ((k5 + 15) // 16))}
+            del w5, h5
+            torch.cuda.empty_cache()
+        else:
+            out["C5_cd"] = {"skipped": "not enough free device memory beside the resident C3 matrix"}
+    except Exception as exc:              # a side figure must not cost the bench line
+        out["C5_cd"] = {"error": f"{type(exc).__name__}: {exc}"}
+        torch.cuda.empty_cache()
     return out
 
 

@@ -129,8 +129,10 @@ nnls_smem_kernel(const double* __restrict__ gram, int k, const float* __restrict
                  unsigned long long* __restrict__ next_col, int initial_sweeps, double face_reduction,
                  int scale_diag, int greedy_budget, int greedy_batch,
                  const unsigned long long* __restrict__ flagged) {
-    // flagged != nullptr: clean-up pass behind nnls_greedy_kernel -- only the columns that kernel marked (NaN in
-    // row 0 of their solution) are solved, from scratch; nothing to do (the usual case) costs one global load
+    // flagged != nullptr: clean-up pass behind nnls_greedy_kernel -- only the columns that kernel marked (negative
+    // row 0 of their solution) are finished, by sweeps + CG from the state its greedy steps left (what the greedy
+    // budget did not finish is ill-conditioned: more greedy steps are the wrong tool); nothing to do (the usual case)
+    // costs one global load
     if (flagged != nullptr && *flagged == 0ULL) return;
     extern __shared__ double smd[];
     const int ntri = k * (k + 1) / 2;
@@ -195,7 +197,7 @@ nnls_smem_kernel(const double* __restrict__ gram, int k, const float* __restrict
                 chunk_base = __shfl_sync(0xffffffffu, c, 0) * 32ULL;
                 if (chunk_base >= static_cast<unsigned long long>(cols)) { out_of_work = true; break; }
                 const unsigned long long jj = chunk_base + lane;
-                const bool marked = jj < static_cast<unsigned long long>(cols) && sol[jj] != sol[jj];
+                const bool marked = jj < static_cast<unsigned long long>(cols) && sol[jj] < 0.0;
                 pending = __ballot_sync(0xffffffffu, marked);
             }
             if (out_of_work) break;
@@ -219,6 +221,28 @@ nnls_smem_kernel(const double* __restrict__ gram, int k, const float* __restrict
         for (int o = 16; o > 0; o >>= 1) rmax = fmax(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
         const double thresh = tol * rmax;
         unsigned long long nsteps = 0;
+        if (flagged != nullptr) {
+            // warm start: h' = h / s from the greedy kernel's output, g = G'h' - r'
+#pragma unroll
+            for (int i = 0; i < KPL; ++i) {
+                const int t = lane + 32 * i;
+                double v = t < k ? sol[t * ld_sol + j] : 0.0;
+                if (t == 0) v = v <= -1.0e-300 ? -v : 0.0;          // the marker: -h_0, or -DBL_MIN for h_0 == 0
+                h[i] = t < k ? v / scl[t] : 0.0;
+            }
+            auto add_columns = [&](auto slot_tag) {
+                constexpr int I = decltype(slot_tag)::value;
+                unsigned mask = __ballot_sync(0xffffffffu, h[I] > 0.0);
+                while (mask) {
+                    const int o = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    axpy_col(slot_tag, o, shfl_d(h[I], o), g);
+                }
+            };
+            [&]<int... Is>(std::integer_sequence<int, Is...>) {
+                (add_columns(std::integral_constant<int, Is>{}), ...);
+            }(std::make_integer_sequence<int, KPL>{});
+        }
 
         // exact coordinate step on component t = 32 * I + o (I compile-time); returns |projected gradient|
         auto step = [&](auto slot_tag, int o) -> double {
@@ -247,8 +271,8 @@ nnls_smem_kernel(const double* __restrict__ gram, int k, const float* __restrict
         // memory traffic: a 24-bit key (sign-stripped high word of the gradient, truncated) + the coordinate index
         // per slot, one redux.sync per step.  The sweeps + CG loop below stays as the fallback for whatever the
         // budget did not finish (ill-conditioned Gram matrices).
-        bool greedy_used = false;
-        if (greedy_budget > 0 && !converged) {
+        bool greedy_used = flagged != nullptr;
+        if (greedy_budget > 0 && !converged && flagged == nullptr) {
             greedy_used = true;
             // stop at half the tolerance: the truncated keys under-estimate by < 2^-11, the exact check follows
             const unsigned stop_key = static_cast<unsigned>(__double2hiint(0.5 * thresh)) & 0x7fffff00u;
@@ -562,10 +586,16 @@ nnls_greedy_kernel(const double* __restrict__ gram, int k, const float* __restri
             if (steps_total != nullptr) atomicAdd(steps_total, static_cast<unsigned long long>(nsteps));
             if (!converged) atomicAdd(counters + 1, 1ULL);
         }
+        // an unfinished problem keeps its state for the clean-up pass and is marked by the sign of row 0
+        // (solutions are >= 0): -h_0 for h_0 > 0, -DBL_MIN for h_0 == 0
 #pragma unroll
         for (int i = 0; i < NB; ++i) {
             const int t = lane + 32 * i;
-            if (t < k) sol[t * ld_sol + j] = (converged || t != 0) ? h[i] * scl[t] : __longlong_as_double(0x7ff8000000000000LL);
+            if (t < k) {
+                double v = h[i] * scl[t];
+                if (!converged && t == 0) v = v > 0.0 ? -v : -2.2250738585072014e-308;
+                sol[t * ld_sol + j] = v;
+            }
         }
     }
 }

@@ -1538,6 +1538,8 @@ static int dr_solve(nfb_handle* h, const nfb_matrix* x, nfb_dr_components& comps
                               400, h->d_int.p, st, reinterpret_cast<unsigned long long*>(h->d_scal.p + 8),
                               reinterpret_cast<unsigned long long*>(h->d_scal.p + 10)));
     }
+    unsigned long long flagged_cols[2] = {0, 0};   // NFB_DR_STATS: columns the greedy NNLS kernel left to the clean-up pass
+    if (getenv("NFB_DR_STATS")) cudaMemcpy(&flagged_cols[0], h->d_scal.p + 11, sizeof(unsigned long long), cudaMemcpyDeviceToHost);
     // ---- stage 2 operand: the (un-thresholded) white components as float32 planes ----------------------
     { NFB_PHASE(h, "planes2");
     NFB_CUDA(cudaMemsetAsync(hs.rowmax.p, 0, sizeof(unsigned int) * kp, st));
@@ -1617,9 +1619,11 @@ static int dr_solve(nfb_handle* h, const nfb_matrix* x, nfb_dr_components& comps
     if (getenv("NFB_DR_STATS")) {
         unsigned long long steps[2] = {0, 0};
         cudaMemcpy(steps, h->d_scal.p + 8, sizeof(steps), cudaMemcpyDeviceToHost);
-        fprintf(stderr, "nfact_b200 DR: stage1 %.1f coordinate steps/column (n=%lld), stage2 %.1f steps/row (m=%lld), k=%d\n",
-                static_cast<double>(steps[0]) / n, static_cast<long long>(n), static_cast<double>(steps[1]) / m,
-                static_cast<long long>(m), k);
+        cudaMemcpy(&flagged_cols[1], h->d_scal.p + 11, sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "nfact_b200 DR: stage1 %.1f coordinate steps/column (n=%lld, %llu left to the clean-up pass), "
+                "stage2 %.1f steps/row (m=%lld, %llu left to the clean-up pass), k=%d\n",
+                static_cast<double>(steps[0]) / n, static_cast<long long>(n), flagged_cols[0],
+                static_cast<double>(steps[1]) / m, static_cast<long long>(m), flagged_cols[1], k);
     }
     return 0;
 }
