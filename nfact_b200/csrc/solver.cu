@@ -141,6 +141,26 @@ struct DevBuf {
     }
 };
 
+// An event whose last record is on a side stream that reads / writes buffers of the enclosing scope: on EVERY exit path
+// (early NFB_TRY / NFB_CUDA returns included) the side stream is drained before those buffers are released, and the
+// event is destroyed.  Declare it after the buffers it protects.
+struct SideStreamEvent {
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev = nullptr;
+    explicit SideStreamEvent(cudaStream_t s) : side(s) {}
+    SideStreamEvent(const SideStreamEvent&) = delete;
+    SideStreamEvent& operator=(const SideStreamEvent&) = delete;
+    int create() { return cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess ? 0 : 1; }
+    void finish() {
+        if (ev) {
+            cudaStreamSynchronize(side);
+            cudaEventDestroy(ev);
+            ev = nullptr;
+        }
+    }
+    ~SideStreamEvent() { finish(); }
+};
+
 typedef int (*NcclAllReduceFn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
 typedef int (*NcclReduceScatterFn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
 typedef int (*NcclAllGatherFn)(const void*, void*, size_t, int, void*, cudaStream_t);
@@ -1560,9 +1580,10 @@ static int dr_solve(nfb_handle* h, const nfb_matrix* x, nfb_dr_components& comps
     if (hs_norm_out) NFB_TRY(comp_standardize<double>(sol_h.p, k, n, hs.ld, norm.p, hs.ld, stats.p, st));
     }
     // the white components can travel while stage 2 runs
-    cudaEvent_t hs_ready = nullptr;
+    SideStreamEvent hs_guard(h->copy_stream);
+    cudaEvent_t& hs_ready = hs_guard.ev;
     if (hs_out || hs_norm_out) {
-        NFB_CUDA(cudaEventCreateWithFlags(&hs_ready, cudaEventDisableTiming));
+        NFB_CHECK(hs_guard.create() == 0, "cudaEventCreate failed");
         NFB_CUDA(cudaEventRecord(hs_ready, st));
         NFB_CUDA(cudaStreamWaitEvent(h->copy_stream, hs_ready, 0));
         if (hs_out)
@@ -1610,10 +1631,8 @@ static int dr_solve(nfb_handle* h, const nfb_matrix* x, nfb_dr_components& comps
     int status[2] = {0, 0};
     NFB_CUDA(cudaMemcpyAsync(status, h->d_int.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
     NFB_CUDA(cudaStreamSynchronize(st));
-    if (hs_ready) {
-        NFB_CUDA(cudaStreamSynchronize(h->copy_stream));
-        cudaEventDestroy(hs_ready);
-    }
+    hs_guard.finish();
+    NFB_CUDA(cudaGetLastError());
     if (n_unconverged_out) *n_unconverged_out = status[0] + status[1];
     report_phases(h, 1);
     if (getenv("NFB_DR_STATS")) {
@@ -1893,7 +1912,8 @@ static int ingest_single_to_planes(nfb_handle* h, const int32_t* rows_host, cons
     NFB_TRY(x->lo.alloc_cached(&h->big, cells, st));
     NFB_TRY(x->inv_scale.alloc_pooled(1, true, st));
     NFB_TRY(mask.alloc_cached(&h->big, (cells + 31) / 32, st));
-    cudaEvent_t uploaded = nullptr;
+    SideStreamEvent up_guard(h->copy_stream);
+    cudaEvent_t& uploaded = up_guard.ev;
     if (upload) {
         // staging sized in 64 Mi-triplet steps so that subjects with slightly different counts share the cache
         const size_t nnz_cap = static_cast<size_t>(round_up64(std::max<int64_t>(nnz, 1), int64_t(1) << 26));
@@ -1904,7 +1924,7 @@ static int ingest_single_to_planes(nfb_handle* h, const int32_t* rows_host, cons
         // the triplets travel on the copy stream while the planes and the mask are zeroed on the main one
         // (the staging buffers are stream-ordered allocations of the main stream: the copy stream may only touch
         // them after the point of allocation)
-        NFB_CUDA(cudaEventCreateWithFlags(&uploaded, cudaEventDisableTiming));
+        NFB_CHECK(up_guard.create() == 0, "cudaEventCreate failed");
         NFB_CUDA(cudaEventRecord(uploaded, st));
         NFB_CUDA(cudaStreamWaitEvent(h->copy_stream, uploaded, 0));
         NFB_CUDA(cudaMemcpyAsync(rows.p, rows_host, sizeof(int) * nnz, cudaMemcpyHostToDevice, h->copy_stream));
@@ -1932,7 +1952,7 @@ static int ingest_single_to_planes(nfb_handle* h, const int32_t* rows_host, cons
     NFB_CUDA(cudaMemcpyAsync(h->h_scal + 6, h->d_scal.p + 6, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
     NFB_CUDA(cudaMemcpyAsync(&x->inv_scale_host, x->inv_scale.p, sizeof(float), cudaMemcpyDeviceToHost, st));
     NFB_CUDA(cudaStreamSynchronize(st));
-    if (uploaded) cudaEventDestroy(uploaded);
+    up_guard.finish();
     marks.mark("scatter");
     note_launch(2);
     NFB_CHECK(flags[0] == 0, "row/column index exceeds matrix dimensions");
