@@ -75,7 +75,72 @@ struct GemmArgs {
     // any time every rank's stores are spread evenly over all owners.  0: natural order.
     int perm_groups, perm_bpo, perm_rot;
     int num_tiles;           // tiles to walk (m_blocks * splits, or perm_groups * perm_bpo: some are empty)
+    // Stream-K tail (unsplit launches): every worker first takes sk_full whole tiles (tile = worker + i * workers); the
+    // remaining sk_tail tiles are cut into equal shares of sk_share K blocks per worker, so the last, partial wave of
+    // tiles costs its share of the K loop instead of a whole tile time.  A share covers the end of one tile and / or
+    // the beginning of the next: the worker that holds a tile's LAST K blocks owns the tile -- it waits for the other
+    // workers' raw fp32 partials (sk_ws, one slot per worker, arrivals counted in sk_cnt), adds them in worker order
+    // (deterministic) and stores the tile once.  sk_share == 0: off.
+    int sk_full, sk_tail, sk_share;
+    float* sk_ws;            // [workers][n_store][256] raw partial accumulators of a worker's contributed segment
+    unsigned int* sk_cnt;    // [workers][2]: epilogue warps that have stored / read slot w (reset by the last reader)
 };
+
+struct WorkItem {
+    int mb, ks, kb0, kb1;
+    int role;                // 0: whole tile (or split slab), 1: contributes a partial, 2: owns a tile others contribute to
+    int first;               // owner: contributors are the workers first .. worker - 1
+};
+constexpr int kItemEnd = -1, kItemSkip = 0, kItemWork = 1;
+
+__device__ __forceinline__ bool map_tile(const GemmArgs& args, int tile, int& ks, int& mb);
+
+// idx-th work item of a worker; the three roles of a CTA pair walk the same list
+__device__ __forceinline__ int next_item(const GemmArgs& args, int worker, int num_workers, int idx, WorkItem& it) {
+    it.role = 0;
+    it.first = 0;
+    if (args.sk_share == 0) {
+        const int tile = worker + idx * num_workers;
+        if (tile >= args.num_tiles) return kItemEnd;
+        if (!map_tile(args, tile, it.ks, it.mb)) return kItemSkip;
+        it.kb0 = static_cast<int>(static_cast<long long>(it.ks) * args.num_kb / args.splits);
+        it.kb1 = static_cast<int>(static_cast<long long>(it.ks + 1) * args.num_kb / args.splits);
+        return kItemWork;
+    }
+    it.ks = 0;
+    if (idx < args.sk_full) {
+        it.mb = worker + idx * num_workers;
+        it.kb0 = 0;
+        it.kb1 = args.num_kb;
+        return kItemWork;
+    }
+    const int kb = args.num_kb;
+    const long long u0 = static_cast<long long>(worker) * args.sk_share;
+    const long long u1 = min(u0 + args.sk_share, static_cast<long long>(args.sk_tail) * kb);
+    if (u0 >= u1) return kItemEnd;
+    const int ta = static_cast<int>(u0 / kb);
+    const long long end_a = min(u1, static_cast<long long>(ta + 1) * kb);
+    const bool has_b = u1 > end_a;
+    const int j = idx - args.sk_full;
+    // contribution first, owned tile last: an owner never waits for a worker that is itself still waiting
+    if (has_b && j == 0) {                       // the beginning of tile ta + 1
+        it.mb = args.sk_full * num_workers + ta + 1;
+        it.kb0 = 0;
+        it.kb1 = static_cast<int>(u1 - end_a);
+        it.role = 1;
+        return kItemWork;
+    }
+    if (j > (has_b ? 1 : 0)) return kItemEnd;
+    it.mb = args.sk_full * num_workers + ta;
+    it.kb0 = static_cast<int>(u0 - static_cast<long long>(ta) * kb);
+    it.kb1 = static_cast<int>(end_a - static_cast<long long>(ta) * kb);
+    if (it.kb1 < kb) it.role = 1;
+    else if (it.kb0 > 0) {
+        it.role = 2;
+        it.first = static_cast<int>((static_cast<long long>(ta) * kb) / args.sk_share);
+    }
+    return kItemWork;
+}
 
 // tile index -> (K split, M block); false for the empty tiles of the permuted order
 __device__ __forceinline__ bool map_tile(const GemmArgs& args, int tile, int& ks, int& mb) {
@@ -159,7 +224,6 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
-    const int num_tiles = args.num_tiles;
     const int num_workers = gridDim.x / kCtaGroup;
     const int worker = blockIdx.x / kCtaGroup;
     const int n_load = args.n_umma / kCtaGroup;  // rows of B staged by this CTA
@@ -172,11 +236,12 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
     if (warp_idx == 0) {
       if (lane_idx == 0) {
         // =========================== TMA producer ===============================================
-        for (int tile = worker; tile < num_tiles; tile += num_workers) {
-            int ks, mb;
-            if (!map_tile(args, tile, ks, mb)) continue;
-            const int kb0 = static_cast<int>(static_cast<long long>(ks) * args.num_kb / args.splits);
-            const int kb1 = static_cast<int>(static_cast<long long>(ks + 1) * args.num_kb / args.splits);
+        for (int idx = 0;; ++idx) {
+            WorkItem item;
+            const int what = next_item(args, worker, num_workers, idx, item);
+            if (what == kItemEnd) break;
+            if (what == kItemSkip) continue;
+            const int mb = item.mb, kb0 = item.kb0, kb1 = item.kb1;
             const int m_idx = (mb * kCtaGroup + static_cast<int>(cta_rank)) * kBlockM;
             const int n_idx = static_cast<int>(cta_rank) * n_load;
             for (int kb = kb0; kb < kb1; ++kb) {
@@ -218,11 +283,12 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
         const uint32_t a_lbo = kAMajorMN ? kBlockK * 128 : 0;
         const uint32_t a_kstep = kAMajorMN ? kUmmaK * 128 : kUmmaK * 2;
         uint32_t chain = 0;  // running index of TMEM accumulation chains (stage = chain & 1)
-        for (int tile = worker; tile < num_tiles; tile += num_workers) {
-            int ks, mb;
-            if (!map_tile(args, tile, ks, mb)) continue;
-            const int kb0 = static_cast<int>(static_cast<long long>(ks) * args.num_kb / args.splits);
-            const int kb1 = static_cast<int>(static_cast<long long>(ks + 1) * args.num_kb / args.splits);
+        for (int idx = 0;; ++idx) {
+            WorkItem item;
+            const int what = next_item(args, worker, num_workers, idx, item);
+            if (what == kItemEnd) break;
+            if (what == kItemSkip) continue;
+            const int kb0 = item.kb0, kb1 = item.kb1;
             for (int kc0 = kb0; kc0 < kb1; kc0 += kChunkKB, ++chain) {
                 const int kc1 = min(kc0 + kChunkKB, kb1);
                 const uint32_t as = chain & 1, aphase = (chain >> 1) & 1;
@@ -265,11 +331,12 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
         const int ch0 = col_half == 0 ? 0 : nch_first;                       // first 16-col chunk
         const int nch = col_half == 0 ? nch_first : nch_total - nch_first;   // chunks owned (<= kNch)
         uint32_t chain = 0;
-        for (int tile = worker; tile < num_tiles; tile += num_workers) {
-            int ks, mb;
-            if (!map_tile(args, tile, ks, mb)) continue;
-            const int kb0 = static_cast<int>(static_cast<long long>(ks) * args.num_kb / args.splits);
-            const int kb1 = static_cast<int>(static_cast<long long>(ks + 1) * args.num_kb / args.splits);
+        for (int idx = 0;; ++idx) {
+            WorkItem item;
+            const int what = next_item(args, worker, num_workers, idx, item);
+            if (what == kItemEnd) break;
+            if (what == kItemSkip) continue;
+            const int ks = item.ks, mb = item.mb, kb0 = item.kb0, kb1 = item.kb1;
             float acc[kNch * 16];
 #pragma unroll
             for (int i = 0; i < kNch * 16; ++i) acc[i] = 0.0f;
@@ -291,6 +358,62 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                 tc_fence_before();
                 if constexpr (kCtaGroup == 2) mbar_arrive_cluster(&tmem_empty_bar[as], 0);
                 else mbar_arrive(&tmem_empty_bar[as]);
+            }
+            if (item.role != 0) {
+                // stream-K: slot layout [n_store][kCtaGroup * 128 rows], rows of a warp contiguous (coalesced)
+                const int pair_rows = kCtaGroup * kBlockM;
+                const int prow = static_cast<int>(cta_rank) * kBlockM + static_cast<int>(row);
+                constexpr unsigned int kWarpsPerSlot = kCtaGroup * kNumEpilogueWarps;
+                if (item.role == 1) {
+                    float* ws = args.sk_ws + static_cast<size_t>(worker) * args.n_store * pair_rows + prow;
+#pragma unroll
+                    for (int c = 0; c < kNch; ++c) {
+                        if (c < nch) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                const int col = (ch0 + c) * 16 + j;
+                                if (col < args.n_store) ws[static_cast<size_t>(col) * pair_rows] = acc[c * 16 + j];
+                            }
+                        }
+                    }
+                    __threadfence();
+                    __syncwarp();
+                    if (lane_idx == 0) atomicAdd(args.sk_cnt + 2 * worker, 1u);
+                    continue;
+                }
+                for (int src = item.first; src < worker; ++src) {
+                    unsigned int* cnt = args.sk_cnt + 2 * src;
+                    if (lane_idx == 0) {
+                        unsigned int seen;
+                        do {
+                            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(cnt) : "memory");
+                            if (seen < kWarpsPerSlot) __nanosleep(40);
+                        } while (seen < kWarpsPerSlot);
+                    }
+                    __syncwarp();
+                    __threadfence();
+                    const float* ws = args.sk_ws + static_cast<size_t>(src) * args.n_store * pair_rows + prow;
+#pragma unroll
+                    for (int c = 0; c < kNch; ++c) {
+                        if (c < nch) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                const int col = (ch0 + c) * 16 + j;
+                                if (col < args.n_store)
+                                    acc[c * 16 + j] = __fadd_rn(acc[c * 16 + j], __ldcg(ws + static_cast<size_t>(col) * pair_rows));
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    if (lane_idx == 0) {
+                        // the last of the owner's warps to have read the slot re-arms it for the next launch
+                        if (atomicAdd(cnt + 1, 1u) == kWarpsPerSlot - 1) {
+                            cnt[1] = 0u;
+                            __threadfence();
+                            cnt[0] = 0u;
+                        }
+                    }
+                }
             }
             const long long m_row = static_cast<long long>(mb * kCtaGroup + static_cast<int>(cta_rank)) * kBlockM + row;
             if (m_row < args.m_total) {
@@ -407,6 +530,7 @@ int gemm_default_cta_group() {
     return value;
 }
 
+
 int gemm_pick_splits(int64_t m_total, int64_t k_total, int cta_group, int64_t n_out) {
     const int64_t m_blocks = ceil_div64(m_total, static_cast<int64_t>(kBlockM) * cta_group);
     const int64_t num_kb = ceil_div64(k_total, kBlockK);
@@ -429,10 +553,51 @@ int gemm_pick_splits(int64_t m_total, int64_t k_total, int cta_group, int64_t n_
     return static_cast<int>(best);
 }
 
+bool gemm_streamk_enabled() {
+    // Off unless NFB_STREAMK=1.  Measured on B200: the tail engages as planned and buys nothing --
+    // C3's W'X runs at the power cap (the SMs a partial wave leaves idle are power the busy ones use), C2's is HBM-bound
+    // (the tiles of a partial wave get the whole memory system and finish early); wave quantisation is not what these
+    // launches pay for.
+    static const bool on = getenv("NFB_STREAMK") && atoi(getenv("NFB_STREAMK")) != 0;
+    return on;
+}
+
+// the stream-K decision for an unsplit launch over m_total rows and k_total contraction elements: tiles per worker
+// before the shared tail, tiles in the tail, K blocks of the tail per worker; false when whole tiles do as well
+static bool streamk_plan(int64_t m_total, int64_t k_total, int cta_group, int* full_out, int* tail_out, int* share_out) {
+    const int64_t m_blocks = ceil_div64(m_total, static_cast<int64_t>(kBlockM) * cta_group);
+    const int64_t num_kb = ceil_div64(k_total, kBlockK);
+    const int64_t w_all = sm_count() / cta_group;
+    const int64_t full = m_blocks / w_all, tail = m_blocks - full * w_all;
+    const int64_t share = tail > 0 ? (tail * num_kb + w_all - 1) / w_all : 0;
+    // Worth it when the shared tail beats a whole extra wave by more than the fix-up costs: the partials of a shared
+    // tile are written, awaited and re-read at the very end of the launch, ~30-50 us that nothing hides (the 8-GPU
+    // shard's W'X, where the tail saves 22 of 700 K blocks, ran 0.03 ms slower), so the saving must be worth ~100 K
+    // blocks.  At C3 the tail saves 175 of 5574 K-block times of W'X -- and buys nothing measurable there: the launch
+    // runs at the power cap, and the SMs a partial wave leaves idle are power the busy ones use (5.60-5.64 ms either
+    // way); at C2 (HBM-bound) the unsplit launch + tail is 1 % of the iteration faster than the split-K slabs.
+    const double t_plain = static_cast<double>(full + 1) * num_kb, t_sk = static_cast<double>(full) * num_kb + share;
+    if (!(tail > 0 && share >= 2 * kChunkKB && share < num_kb && t_plain - t_sk >= std::max(96.0, 0.02 * t_plain)))
+        return false;
+    if (full_out) *full_out = static_cast<int>(full);
+    if (tail_out) *tail_out = static_cast<int>(tail);
+    if (share_out) *share_out = static_cast<int>(share);
+    return true;
+}
+bool gemm_streamk_pays(int64_t m_total, int64_t k_total, int cta_group) {
+    return gemm_streamk_enabled() && streamk_plan(m_total, k_total, cta_group, nullptr, nullptr, nullptr);
+}
+
+size_t gemm_streamk_ws_floats(int n_store) {
+    return static_cast<size_t>(sm_count()) * std::min(n_store, 256) * kBlockM;   // workers * cta_group * 128 rows
+}
+int gemm_streamk_max_workers() { return sm_count(); }
+
 static int gemm_split_tile(const GemmOperand& a, bool a_is_mn_major, const GemmOperand& b, int64_t m_total,
                            int64_t k_total, int n_umma, int n_store, float* out, int64_t ld_out,
                            long long split_stride, int splits, const float* col_scale, const float* row_scale,
-                           float scale, int cta_group, cudaStream_t stream, const GemmScatter* scatter, int col0) {
+                           float scale, int cta_group, cudaStream_t stream, const GemmScatter* scatter, int col0,
+                           const GemmStreamK* sk) {
     NFB_CHECK(n_umma % 16 == 0 && n_umma >= 16 && n_umma <= 256, "n_umma must be a multiple of 16 in [16,256]");
     NFB_CHECK(cta_group == 1 || cta_group == 2, "cta_group must be 1 or 2");
     NFB_CHECK(n_store <= n_umma, "n_store exceeds n_umma");
@@ -500,6 +665,23 @@ static int gemm_split_tile(const GemmOperand& a, bool a_is_mn_major, const GemmO
 
     const int64_t tiles = args.num_tiles;
     int workers = static_cast<int>(std::min<int64_t>(tiles, sm_count() / cta_group));
+    args.sk_full = args.sk_tail = args.sk_share = 0;
+    args.sk_ws = nullptr;
+    args.sk_cnt = nullptr;
+    if (sk != nullptr && (sk->force || gemm_streamk_enabled()) && splits == 1 && args.scatter_slice == 0 &&
+        args.perm_groups == 0) {
+        const int w_all = sm_count() / cta_group;
+        const size_t need = static_cast<size_t>(w_all) * n_store * cta_group * kBlockM;
+        int full = 0, tail = 0, share = 0;
+        if (w_all <= sk->workers && need <= sk->ws_floats && streamk_plan(m_total, k_total, cta_group, &full, &tail, &share)) {
+            args.sk_full = full;
+            args.sk_tail = tail;
+            args.sk_share = share;
+            args.sk_ws = sk->ws;
+            args.sk_cnt = sk->cnt;
+            workers = w_all;
+        }
+    }
 
     Launch l{&tm_a_hi, &tm_a_lo, &tm_b_hi, &tm_b_lo, &args, workers * cta_group, smem_bytes, stream};
     const int nch_per_thread = ((n_umma >> 4) + 1) >> 1;
@@ -514,7 +696,8 @@ static int gemm_split_tile(const GemmOperand& a, bool a_is_mn_major, const GemmO
 // N (the component dimension) is tiled in slabs of <= 256 columns: one launch per slab, each streaming A once.
 int gemm_split(const GemmOperand& a, bool a_is_mn_major, const GemmOperand& b, int64_t m_total, int64_t k_total,
                int n_umma, int n_store, float* out, int64_t ld_out, int splits, const float* col_scale,
-               const float* row_scale, float scale, int cta_group, cudaStream_t stream, const GemmScatter* scatter) {
+               const float* row_scale, float scale, int cta_group, cudaStream_t stream, const GemmScatter* scatter,
+               const GemmStreamK* sk) {
     NFB_CHECK(n_umma % 16 == 0 && n_umma >= 16, "n_umma must be a positive multiple of 16");
     const long long split_stride = static_cast<long long>(n_store) * ld_out;
     // NFB_GEMM_TIMING=1: device time of every call (debug aid; synchronises the stream)
@@ -541,7 +724,8 @@ int gemm_split(const GemmOperand& a, bool a_is_mn_major, const GemmOperand& b, i
                        b.ld};
         NFB_TRY(gemm_split_tile(a, a_is_mn_major, bt, m_total, k_total, n_tile, std::min(n_tile, n_store - t0),
                                 out + static_cast<int64_t>(t0) * ld_out, ld_out, split_stride, splits,
-                                col_scale ? col_scale + t0 : nullptr, row_scale, scale, cta_group, stream, scatter, t0));
+                                col_scale ? col_scale + t0 : nullptr, row_scale, scale, cta_group, stream, scatter, t0,
+                                sk));
     }
     return 0;
 }

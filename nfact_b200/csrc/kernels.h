@@ -33,10 +33,25 @@ struct GemmScatter {
     int rows;          // k: component rows per source slab of an inbox
     int src;           // this rank
 };
+// Workspace of the stream-K tail (gemm_split.cu): ws holds one raw partial tile per worker, cnt two counters per
+// worker (zeroed once by the owner of the buffers; the kernel re-arms them itself).  One workspace serves one stream.
+struct GemmStreamK {
+    float* ws;
+    unsigned int* cnt;
+    size_t ws_floats;     // capacity of ws
+    int workers;          // capacity of cnt / 2
+    bool force;           // engage wherever the plan pays even when NFB_STREAMK is not set (the test hook)
+};
+// floats of workspace a launch with n_store output columns needs at most
+size_t gemm_streamk_ws_floats(int n_store);
+int gemm_streamk_max_workers();
+bool gemm_streamk_enabled();     // NFB_STREAMK=1 switches the stream-K tail on (off by default: measured, no gain)
+// an unsplit launch of this shape would run with the stream-K tail (else: whole tiles, or split-K slabs)
+bool gemm_streamk_pays(int64_t m_total, int64_t k_total, int cta_group);
 int gemm_split(const GemmOperand& a, bool a_is_mn_major, const GemmOperand& b, int64_t m_total, int64_t k_total,
                int n_umma, int n_store, float* out, int64_t ld_out, int splits, const float* col_scale,
                const float* row_scale, float scale, int cta_group, cudaStream_t stream,
-               const GemmScatter* scatter = nullptr);
+               const GemmScatter* scatter = nullptr, const GemmStreamK* sk = nullptr);
 
 // ---- planes.cu ------------------------------------------------------------------------------------
 // max |x| over a [rows, cols] fp32 matrix (ld >= cols) -> *out_bits (float bits, must be zeroed first)

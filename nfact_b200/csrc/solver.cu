@@ -270,6 +270,10 @@ struct nfb_nmf {
     Factor gw, gh;        // Gram matrices W'W and HH' (fp32 [kp][kp]); planes are only used as scratch
     Factor gd;            // planes of a Gram matrix with the K-side scales folded in (denominator GEMM)
     DevBuf<float> part_w, part_h, part_den, part_gram, num_h;
+    DevBuf<float> sk_ws;              // stream-K workspace of the two X-streaming GEMMs (main stream only)
+    DevBuf<unsigned int> sk_cnt;
+    GemmStreamK sk{};
+    bool use_sk = false;
     DevBuf<float> num_sl, pack;   // sharded runs: slice-major numerator / gather buffer [P][k][ns], packed slice
     DevBuf<float> snap_w[2], snap_h[2];   // nfb_nmf_run (CD): factors after the last two iterations (see there)
     cudaEvent_t viol_ready[2] = {nullptr, nullptr};
@@ -472,7 +476,7 @@ static int gemm_wtx(nfb_nmf* s, HNumerator* out) {
     GemmTimer timer(h);
     NFB_TRY(gemm_split(s->x->operand(), true, s->wt.operand(), s->x->n, s->x->m, static_cast<int>(s->kp), s->k,
                        s->part_h.p, s->hh.ld, s->s_h, s->wt.inv_scale.p, nullptr, s->x->inv_scale_host, h->cta_group,
-                       h->stream));
+                       h->stream, nullptr, s->use_sk ? &s->sk : nullptr));
     }
     note_launch(1);
     if (h->world <= 1) {
@@ -1145,11 +1149,24 @@ int nfb_nmf_create(nfb_handle* h, const nfb_matrix* x, int k, const nfb_nmf_para
     NFB_TRY(s->gh.init(k, k, true, st, s->kp, pooled));
     NFB_TRY(s->gd.init(k, k, false, st, s->kp, pooled));
     const int cg = h->cta_group;
+    // NFB_STREAMK=1: W'X unsplit with a stream-K tail (gemm_split.cu) where its plan pays; default: split-K slabs
+    // chosen by the cost model.
+    s->use_sk = h->world <= 1 && gemm_streamk_pays(x->n, x->m, cg);
+    // X H' keeps its split-K slabs: the cost model fills its waves to 99 % and the unsplit stream-K form measured
+    // slower there (5.43 -> 5.57 ms at C3); the stream-K tail is for W'X, whose 430 tiles leave a 0.81 wave
     s->s_w = gemm_pick_splits(x->m, x->n, cg, k);
     // row-sharded: W'X runs unsplit (its tiles go straight to their owners' inboxes on the peer-memory path)
-    s->s_h = h->world > 1 ? 1 : gemm_pick_splits(x->n, x->m, cg, k);
+    s->s_h = (h->world > 1 || s->use_sk) ? 1 : gemm_pick_splits(x->n, x->m, cg, k);
     s->s_gw = gemm_pick_splits(k, x->m, cg, k);
     s->s_gh = gemm_pick_splits(k, x->n, cg, k);
+    if (s->use_sk) {
+        const size_t ws_floats = gemm_streamk_ws_floats(std::min(k, 256));
+        const int workers = gemm_streamk_max_workers();
+        NFB_TRY(get(s->sk_ws, ws_floats));
+        NFB_TRY(pooled ? s->sk_cnt.alloc_pooled(2 * static_cast<size_t>(workers), true, st)
+                       : s->sk_cnt.alloc(2 * static_cast<size_t>(workers), true, st));
+        s->sk = GemmStreamK{s->sk_ws.p, s->sk_cnt.p, ws_floats, workers, false};
+    }
     NFB_TRY(get(s->part_w, static_cast<size_t>(s->s_w) * k * s->wt.ld));
     NFB_TRY(get(s->part_h, static_cast<size_t>(s->s_h) * k * s->hh.ld));
     NFB_TRY(get(s->part_den, static_cast<size_t>(k) * std::max(s->wt.ld, s->hh.ld)));
@@ -1543,7 +1560,20 @@ static int dr_solve(nfb_handle* h, const nfb_matrix* x, nfb_dr_components& comps
     NFB_TRY(gram64.alloc_pooled(static_cast<size_t>(k) * k, false, st));
     NFB_TRY(sol_h.alloc_pooled(static_cast<size_t>(k) * hs.ld, true, st));
     NFB_TRY(sol_g.alloc_pooled(static_cast<size_t>(k) * gt.ld, true, st));
-    const int s1 = gemm_pick_splits(n, m, cg, k), s2 = gemm_pick_splits(m, n, cg, k);
+    int s1 = gemm_pick_splits(n, m, cg, k);
+    const int s2 = gemm_pick_splits(m, n, cg, k);
+    // stage 1's G'X is a W'X-type launch: unsplit with the stream-K tail (see nfb_nmf_create)
+    DevBuf<float> sk_ws;
+    DevBuf<unsigned int> sk_cnt;
+    GemmStreamK sk{};
+    const bool use_sk = gemm_streamk_pays(n, m, cg);
+    if (use_sk) {
+        const size_t ws_floats = gemm_streamk_ws_floats(std::min(k, 256));
+        NFB_TRY(sk_ws.alloc_pooled(ws_floats, false, st));
+        NFB_TRY(sk_cnt.alloc_pooled(2 * static_cast<size_t>(gemm_streamk_max_workers()), true, st));
+        sk = GemmStreamK{sk_ws.p, sk_cnt.p, ws_floats, gemm_streamk_max_workers(), false};
+        s1 = 1;
+    }
     DevBuf<float> part;
     NFB_TRY(part.alloc_pooled(std::max(static_cast<size_t>(s1) * k * hs.ld, static_cast<size_t>(s2) * k * gt.ld), false, st));
     NFB_CUDA(cudaMemsetAsync(h->d_int.p, 0, 2 * sizeof(int), st));
@@ -1551,7 +1581,7 @@ static int dr_solve(nfb_handle* h, const nfb_matrix* x, nfb_dr_components& comps
     // ---- stage 1: white matter.  Hs[:, j] = nnls(G, X[:, j])  (dual_regression_methods.py:137-149)
     { NFB_PHASE(h, "gemm_gtx");
     NFB_TRY(gemm_split(x->operand(), true, gt.operand(), n, m, static_cast<int>(kp), k, part.p, hs.ld, s1,
-                       gt.inv_scale.p, nullptr, x->inv_scale_host, cg, st));
+                       gt.inv_scale.p, nullptr, x->inv_scale_host, cg, st, nullptr, use_sk ? &sk : nullptr));
     }
     { NFB_PHASE(h, "nnls1");
     NFB_TRY(nnls_gram_batched(comps.gram64.p, k, part.p, s1, static_cast<int64_t>(k) * hs.ld, hs.ld, n, sol_h.p, hs.ld,
@@ -2321,12 +2351,25 @@ int nfb_test_gemm(nfb_handle* h, const float* a_dev, int64_t a_rows, int64_t a_c
                                n_b, cudaMemcpyDeviceToDevice, st));
     NFB_TRY(refresh_planes(b, bpad.p, nullptr, true, st));
     if (cta_group == 0) cta_group = h->cta_group;
+    // splits == -1: unsplit with the stream-K tail (the launch falls back to whole tiles where that does not pay)
+    const bool streamk = splits == -1;
+    if (streamk) splits = 1;
     if (splits <= 0) splits = gemm_pick_splits(m_total, k_total, cta_group, n_b);
-    DevBuf<float> part;
+    DevBuf<float> part, sk_ws;
+    DevBuf<unsigned int> sk_cnt;
+    GemmStreamK sk{};
+    if (streamk) {
+        const size_t ws_floats = gemm_streamk_ws_floats(static_cast<int>(std::min<int64_t>(n_b, 256)));
+        NFB_TRY(sk_ws.alloc(ws_floats, false, st));
+        NFB_TRY(sk_cnt.alloc(2 * static_cast<size_t>(gemm_streamk_max_workers()), true, st));
+        sk = GemmStreamK{sk_ws.p, sk_cnt.p, ws_floats, gemm_streamk_max_workers(), true};
+    }
     NFB_TRY(part.alloc(static_cast<size_t>(splits) * n_b * ld_out, false, st));
+    // twice with the same workspace: the second launch sees the counters the first one re-armed
+    for (int rep = 0; rep < (streamk ? 2 : 1); ++rep)
     NFB_TRY(gemm_split(a->operand(), a_is_transposed != 0, b.operand(), m_total, k_total, static_cast<int>(b.kp),
                        static_cast<int>(n_b), part.p, ld_out, splits, b.inv_scale.p, nullptr, a->inv_scale_host,
-                       cta_group, st));
+                       cta_group, st, nullptr, streamk ? &sk : nullptr));
     NFB_TRY(reduce_partials(part.p, splits, n_b * ld_out, n_b, m_total, ld_out, 0.0f, out_dev, ld_out, st));
     NFB_CUDA(cudaStreamSynchronize(st));
     return 0;

@@ -74,3 +74,33 @@ def test_gemm_signed_values_and_splits(cta_group):
     for splits in (1, 3, 8):
         out = _run_gemm(a, b, False, cta_group, splits)
         assert np.abs(out - ref).max() / np.abs(ref).max() < 1e-5, splits
+
+
+STREAMK_CASES = [
+    # (rows, cols, n_b, transposed): M blocks against 74 CTA pairs / 148 CTAs -- fewer tiles than workers (every tile
+    # shared by several workers), one tile more than a wave, a ragged last tile, a K that is not a multiple of 64
+    (1300, 9000, 50, False),      # 6 / 11 tiles, 141 K blocks
+    (5000, 10000, 50, False),     # C1's X H': 20 / 40 tiles on 74 / 148 workers
+    (9000, 2100, 200, True),      # M = 2100 (9 / 17 tiles), K = 9000
+    (2050, 19300, 64, True),      # M = 19300: 76 / 151 tiles = one wave + a few tiles, K = 2050 (33 K blocks)
+    (20000, 2050, 208, False),    # M = 20000 (79 / 157 tiles), K = 2050
+]
+
+
+@pytest.mark.parametrize("cta_group", [1, 2])
+@pytest.mark.parametrize("rows,cols,n_b,transposed", STREAMK_CASES)
+def test_gemm_streamk_tail_matches_float64(rows, cols, n_b, transposed, cta_group):
+    """Unsplit launches with the stream-K tail (splits = -1; launched twice on one workspace): the tiles of the last,
+    partial wave are shared between the workers and fixed up inside the kernel -- same accuracy as whole tiles, and
+    identical results from run to run (fixed summation order)."""
+    rng = np.random.default_rng(rows + 3 * cols + n_b)
+    a = (rng.gamma(0.3, 1.0, size=(rows, cols)) * 300 * (rng.random((rows, cols)) < 0.3)).astype(np.float32)
+    k_total = rows if transposed else cols
+    b = rng.gamma(0.5, 2.0, size=(n_b, k_total)).astype(np.float32)
+    out = _run_gemm(a, b, transposed, cta_group, splits=-1)
+    ref = _reference(a, b, transposed)
+    scale = np.abs(ref).max(axis=1, keepdims=True) + 1e-300
+    assert (np.abs(out - ref) / scale).max() < 1e-5
+    assert np.linalg.norm(out - ref) / np.linalg.norm(ref) < 5e-6
+    again = _run_gemm(a, b, transposed, cta_group, splits=-1)
+    assert np.array_equal(out, again)
