@@ -470,12 +470,16 @@ __host__ inline size_t greedy_smem_bytes(int k) {
     return (static_cast<size_t>(greedy_block_off(nb - 1, nb, nb - 1, rows_last * 33)) + k) * sizeof(double);
 }
 
+// byte offsets of the blocks (last block row, C): their row count depends on k, so they are not immediates -- handed
+// to the kernel as arguments (constant bank operands) instead of being rebuilt from k in every step
+struct GreedyLastOff { int v[8]; };
+
 template <int NB, int kWarps>      // NB = ceil(k / 32): block rows = coordinates per lane
 __global__ void __launch_bounds__(kWarps * 32, 1)
 nnls_greedy_kernel(const double* __restrict__ gram, int k, const float* __restrict__ rhs, int rhs_splits,
                    int64_t rhs_stride, int64_t ld_rhs, int64_t cols, double* __restrict__ sol, int64_t ld_sol,
                    double tol, unsigned long long* __restrict__ steps_total, unsigned long long* __restrict__ counters,
-                   int budget, int batch) {
+                   int budget, int batch, const GreedyLastOff last_off) {
     extern __shared__ double smd[];
     constexpr int kLast = NB - 1;
     const int rows_last = k - 32 * kLast;
@@ -525,8 +529,10 @@ nnls_greedy_kernel(const double* __restrict__ gram, int k, const float* __restri
         // picked on a stale gradient, or a move lost to rounding) costs no update; the budget bounds the loop.
         auto step = [&](auto slot_tag, int o) {
             constexpr int I = decltype(slot_tag)::value;
+            // max(h - g, 0) on the sign bit: three integer operations instead of the six of a NaN-aware fmax
             const double hm = h[I] - g[I];
-            const double hn = hm > 0.0 ? hm : 0.0;
+            const int keep = ~(__double2hiint(hm) >> 31);
+            const double hn = __hiloint2double(__double2hiint(hm) & keep, __double2loint(hm) & keep);
             const double delta = shfl_d(hn - h[I], o);
             if (delta == 0.0) return;                             // warp-uniform
             if (lane == o) h[I] = hn;
@@ -535,9 +541,12 @@ nnls_greedy_kernel(const double* __restrict__ gram, int k, const float* __restri
 #pragma unroll
             for (int i = 0; i < NB; ++i) {
                 double v = 0.0;
-                if (i < kLast || last_valid)
-                    v = i <= I ? lds_f64(pa + 8 * greedy_block_off(I, i, kLast, rl33))
-                               : lds_f64(pb + 8 * greedy_block_off(i, I, kLast, rl33));
+                if (i < kLast || last_valid) {
+                    if constexpr (I == kLast) v = lds_f64(pa + last_off.v[i]);                 // blocks (last, i)
+                    else if (i == kLast) v = lds_f64(pb + last_off.v[I]);                      // block (last, I)
+                    else v = i <= I ? lds_f64(pa + 8 * greedy_block_off(I, i, kLast, rl33))
+                                    : lds_f64(pb + 8 * greedy_block_off(i, I, kLast, rl33));
+                }
                 g[i] = fma(delta, v, g[i]);
             }
         };
@@ -632,6 +641,11 @@ int nnls_gram_batched(const double* gram, int64_t k, const float* rhs, int rhs_s
         unsigned long long* fast_counter = counter;
         if (split && greedy_budget > 0 && smem_greedy <= 226 * 1024) {
             const int gw = warps_env > 16 ? std::min(32, warps_env & ~3) : 32;
+            GreedyLastOff last_off{};
+            {
+                const int nb = static_cast<int>((k + 31) / 32), rows_last = static_cast<int>(k) - 32 * (nb - 1);
+                for (int c = 0; c < 8; ++c) last_off.v[c] = 8 * greedy_block_off(nb - 1, std::min(c, nb), nb - 1, rows_last * 33);
+            }
             const int ggrid = static_cast<int>(std::min<int64_t>(ceil_div64(cols, gw), sm_count()));
 #define NFB_NNLS_GREEDY_LAUNCH(NB)                                                                                \
     do {                                                                                                         \
@@ -640,7 +654,7 @@ int nnls_gram_batched(const double* gram, int64_t k, const float* rhs, int rhs_s
                                       static_cast<int>(smem_greedy)));                                           \
         gk<<<ggrid, (gw >= 32 ? 32 : (gw >= 24 ? 24 : 20)) * 32, smem_greedy, stream>>>(                          \
             gram, static_cast<int>(k), rhs, rhs_splits, rhs_stride, ld_rhs, cols, sol, ld_sol, 1e-10, steps_total, \
-            counter, greedy_budget, greedy_batch);                                                               \
+            counter, greedy_budget, greedy_batch, last_off);                                                     \
     } while (0)
             switch ((k + 31) / 32) {
                 case 1: NFB_NNLS_GREEDY_LAUNCH(1); break;
