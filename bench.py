@@ -680,6 +680,8 @@ def side_figures(torch, dev, stream, handle, xmat, w0, h0, k, main_solver):
         # BASELINE configs[4]: 59 412 x 230 000, k = 500 (54.7 GB of operand planes).  k > 256: the component
         # dimension is tiled over two GEMM launches per product, so X is streamed four times per iteration; the
         # bound is the tensor pipe (4 m n k flops at the measured bf16 rate against 8 m n bytes).
+        handle.release_cached()            # what the library's pool holds cached counts as used memory
+        torch.cuda.empty_cache()
         free_b, _total_b = torch.cuda.mem_get_info(dev)
         m5, n5, k5, d5 = WORKLOADS["C5"]
         if free_b > 2.4 * 4.0 * m5 * n5:

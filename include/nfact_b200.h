@@ -37,7 +37,7 @@ int nfb_create(int device, void* stream, nfb_handle** out);
 int nfb_destroy(nfb_handle* h);
 int nfb_synchronize(nfb_handle* h);
 /* frees the per-subject buffers (operand planes, triplet staging) a dual-regression subject loop left cached on
- * this handle for the next subject */
+ * this handle for the next subject, and trims the stream-ordered pool the library allocates from */
 int nfb_release_cached(nfb_handle* h);
 /* Row-sharded multi-GPU: attach an initialised ncclComm_t (one rank per GPU).  When set, the H half-step
  * all-reduces the k x n numerator and the k x k Gram W'W across ranks; W shards stay local.

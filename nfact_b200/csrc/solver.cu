@@ -923,6 +923,10 @@ int nfb_release_cached(nfb_handle* h) {
     NFB_CUDA(cudaSetDevice(h->device));
     NFB_CUDA(cudaStreamSynchronize(h->stream));
     h->big.clear();
+    // and what the stream-ordered pool keeps cached (its release threshold is most of the device)
+    cudaMemPool_t pool = nullptr;
+    if (cudaDeviceGetDefaultMemPool(&pool, h->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+    cudaGetLastError();
     return 0;
 }
 

@@ -38,6 +38,11 @@ class Handle:
     def launch_count(self) -> int:
         return int(self.lib.nfb_launch_count(self._ptr))
 
+    def release_cached(self) -> None:
+        """Hand back the device memory the library keeps cached between calls (the subject loop's per-subject
+        buffers, the stream-ordered pool)."""
+        check(self.lib.nfb_release_cached(self._ptr))
+
     def profile_gemms(self, enable: bool):
         """(total ms, launches) of the X-streaming GEMMs since the last call; then set the enable flag."""
         total, count = c_double(), c_int64()
