@@ -55,28 +55,45 @@ void note_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 // stream and is handed out again on that stream only: no dependency, no mapping.
 struct BigCache {
     std::mutex mu;
-    std::vector<std::pair<void*, size_t>> idle;
+    std::vector<std::pair<void*, size_t>> idle;      // oldest first
+    size_t idle_bytes = 0;
+    size_t cap_bytes = 0;                             // 0: not yet known (40 % of the device on first use)
     void* get(size_t bytes) {
         std::lock_guard<std::mutex> lock(mu);
         for (size_t i = 0; i < idle.size(); ++i)
             if (idle[i].second == bytes) {
                 void* ptr = idle[i].first;
                 idle.erase(idle.begin() + i);
+                idle_bytes -= bytes;
                 return ptr;
             }
         return nullptr;
     }
+    // keeps the buffer for the next subject; buffers of sizes nobody asks for any more (subjects of another shape)
+    // are evicted oldest first once the cache holds more than its share of the device
     void put(void* ptr, size_t bytes) {
+        std::vector<void*> evict;
         {
             std::lock_guard<std::mutex> lock(mu);
-            if (idle.size() < 16) { idle.emplace_back(ptr, bytes); return; }
+            if (cap_bytes == 0) {
+                size_t free_b = 0, total_b = 0;
+                cap_bytes = cudaMemGetInfo(&free_b, &total_b) == cudaSuccess ? total_b / 10 * 4 : (size_t(64) << 30);
+            }
+            idle.emplace_back(ptr, bytes);
+            idle_bytes += bytes;
+            while (!idle.empty() && (idle_bytes > cap_bytes || idle.size() > 16)) {
+                evict.push_back(idle.front().first);
+                idle_bytes -= idle.front().second;
+                idle.erase(idle.begin());
+            }
         }
-        cudaFree(ptr);
+        for (void* e : evict) cudaFree(e);
     }
     void clear() {
         std::lock_guard<std::mutex> lock(mu);
         for (auto& e : idle) cudaFree(e.first);
         idle.clear();
+        idle_bytes = 0;
     }
 };
 
@@ -122,7 +139,12 @@ struct DevBuf {
         release();
         if (count == 0) count = 1;
         p = static_cast<T*>(c->get(count * sizeof(T)));
-        if (p == nullptr) NFB_CUDA(cudaMalloc(reinterpret_cast<void**>(&p), count * sizeof(T)));
+        if (p == nullptr && cudaMalloc(reinterpret_cast<void**>(&p), count * sizeof(T)) != cudaSuccess) {
+            cudaGetLastError();
+            c->clear();          // out of memory with idle buffers of other sizes around: give them back and retry
+            p = nullptr;
+            NFB_CUDA(cudaMalloc(reinterpret_cast<void**>(&p), count * sizeof(T)));
+        }
         n = count;
         cache = c;
         return 0;
