@@ -142,7 +142,7 @@ __global__ void reduce_partials_f64_kernel(const float* __restrict__ part, int s
 }
 
 // 4 x 4 block of the Gram matrix per CTA column slice, float64 products of the fp32 factor.
-// gram64 += F F' over a chunk of columns: 64 x 64 output tiles (lower triangle of tiles), 256 threads with a 4 x 4
+// partial[z] = F F' over column chunk z: 64 x 64 output tiles (lower triangle of tiles), 256 threads with a 4 x 4
 // register tile each, operands converted to float64 on their way into shared memory ([column][row], row stride 65:
 // the transposing store and the row reads are both conflict-free enough), 16 DFMA per 8 LDS.64 -- DFMA-bound, where the
 // first version (4 x 4 outputs per BLOCK, operands straight from L2) moved 4.5 GB through L2 for a C3 Gram.
@@ -195,16 +195,28 @@ gram_f64_kernel(const float* __restrict__ f, int k, int64_t cols, int64_t ld, do
         }
         __syncthreads();
     }
+    // every (tile, column chunk) owns its entries of partial[z][t][u], u <= t: no atomics, the chunks are summed in
+    // order by gram_f64_reduce_kernel -> the Gram matrix (and with it the regression) is bit-reproducible
+    double* part = gram64 + static_cast<int64_t>(blockIdx.z) * k * k;
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int l = 0; l < 4; ++l) {
             const int t = t0 + 4 * ty + i, u = u0 + tx + 16 * l;
-            if (t < k && u < k && (ti != ui || u <= t)) {
-                atomicAdd(&gram64[static_cast<int64_t>(t) * k + u], acc[i][l]);
-                if (u != t) atomicAdd(&gram64[static_cast<int64_t>(u) * k + t], acc[i][l]);
-            }
+            if (t < k && u < k && u <= t) part[static_cast<int64_t>(t) * k + u] = acc[i][l];
         }
+}
+
+// gram[t][u] = gram[u][t] = sum_z partial[z][t][u]  (u <= t), chunks in order
+__global__ void gram_f64_reduce_kernel(const double* __restrict__ partial, int k, int chunks, double* __restrict__ gram64) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= k * k) return;
+    const int t = idx / k, u = idx - t * k;
+    if (u > t) return;
+    double acc = 0.0;
+    for (int z = 0; z < chunks; ++z) acc += partial[static_cast<int64_t>(z) * k * k + idx];
+    gram64[static_cast<int64_t>(t) * k + u] = acc;
+    gram64[static_cast<int64_t>(u) * k + t] = acc;
 }
 
 __global__ void f64_to_f32_rowmax_kernel(const double* __restrict__ in, int64_t cols, int64_t ld_in,
@@ -337,8 +349,10 @@ int reduce_partials_f64(const float* part, int splits, int64_t split_stride, int
 
 int gram_f64(const float* f, int64_t k, int64_t cols, int64_t ld, double* gram64, cudaStream_t stream) {
     if (k == 0) return 0;
-    NFB_CUDA(cudaMemsetAsync(gram64, 0, sizeof(double) * k * k, stream));
-    if (cols == 0) return 0;
+    if (cols == 0) {
+        NFB_CUDA(cudaMemsetAsync(gram64, 0, sizeof(double) * k * k, stream));
+        return 0;
+    }
     const int64_t kt = ceil_div64(k, kGramTile);
     const int64_t tiles = kt * (kt + 1) / 2;
     // enough column chunks to give every SM two blocks, chunks a multiple of the 32-column step
@@ -346,9 +360,15 @@ int gram_f64(const float* f, int64_t k, int64_t cols, int64_t ld, double* gram64
                                                         ceil_div64(cols, 4 * kGramCols)));
     const int64_t per_block = round_up64(ceil_div64(cols, jz), kGramCols);
     jz = ceil_div64(cols, per_block);
+    double* partial = nullptr;                       // [jz][k][k], stream-ordered scratch
+    NFB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&partial), sizeof(double) * jz * k * k, stream));
     gram_f64_kernel<<<dim3(static_cast<unsigned>(kt), static_cast<unsigned>(kt), static_cast<unsigned>(jz)), 256, 0,
-                      stream>>>(f, static_cast<int>(k), cols, ld, gram64, per_block);
-    NFB_CUDA(cudaGetLastError());
+                      stream>>>(f, static_cast<int>(k), cols, ld, partial, per_block);
+    gram_f64_reduce_kernel<<<static_cast<unsigned>(ceil_div64(k * k, 256)), 256, 0, stream>>>(
+        partial, static_cast<int>(k), static_cast<int>(jz), gram64);
+    const cudaError_t launch_err = cudaGetLastError();
+    cudaFreeAsync(partial, stream);
+    NFB_CUDA(launch_err);
     return 0;
 }
 
