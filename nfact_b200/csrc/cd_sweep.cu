@@ -219,7 +219,6 @@ cd_sweep_tile_kernel(float* __restrict__ f, int k, int64_t cols, int64_t ld, con
         unsigned int fb[kBlk];
 #pragma unroll
         for (int i = 0; i < kBlk; ++i) gl[i] = (kFull || i < nb) ? gs[(t0 + i) * TJ + tid] : 0.0f;
-        float* fp = f + static_cast<int64_t>(t0) * ld + jc_own;
 #pragma unroll
         for (int i = 0; i < kBlk; ++i) {
             dl[i] = 0.0f;
@@ -229,11 +228,10 @@ cd_sweep_tile_kernel(float* __restrict__ f, int k, int64_t cols, int64_t ld, con
                 const float gt = gl[i];
                 viol += fabsf((ft == 0.0f) ? fminf(0.0f, gt) : gt);
                 const float inv = invh[i];
-                const float fn = fmaxf(fmaf(-gt, inv, ft), 0.0f);
-                const float delta = inv != 0.0f ? fn - ft : 0.0f;
-                if (active && delta != 0.0f) fp[static_cast<int64_t>(i) * ld] = fn;
+                const float fn = inv != 0.0f ? fmaxf(fmaf(-gt, inv, ft), 0.0f) : ft;   // a dead component keeps its value
+                const float delta = fn - ft;
                 dl[i] = delta;
-                fb[i] = active ? __float_as_uint(ft + delta) : 0u;   // values are >= 0: unsigned order == float order
+                fb[i] = active ? __float_as_uint(fn) : 0u;   // the value to store; >= 0: unsigned order == float order
                 // row i of the diagonal block of G, columns i+1..15, as 128-bit broadcast loads
                 const float4* grow4 = reinterpret_cast<const float4*>(gb + i * kp4 + t0);
                 float grow[kBlk];
@@ -251,6 +249,18 @@ cd_sweep_tile_kernel(float* __restrict__ f, int k, int64_t cols, int64_t ld, con
 #pragma unroll
         for (int i = 0; i < kBlk; ++i)
             if (kFull || i < nb) gs[(t0 + i) * TJ + tid] = dl[i];
+        // The block's new values leave the chain in one run of stores behind it (a store per step inside the chain
+        // cost a 64-bit address, a predicate and -- where no lane of the warp moved -- a branch per coordinate:
+        // ~10 of the ~44 instructions of a step).  Unchanged values are rewritten: the whole factor, 4 B per entry
+        // and iteration, against the (S + 3) x 4 B the seed phase reads.
+        if (active) {
+            float* fp = f + static_cast<int64_t>(t0) * ld + jc_own;
+#pragma unroll
+            for (int i = 0; i < kBlk; ++i) {
+                if (kFull || i < nb) *fp = __uint_as_float(fb[i]);
+                fp += ld;
+            }
+        }
         // Row-sharded runs with rows that cannot take the 128-bit path below: every value that moved goes straight
         // into the peers' copies of H from here
         if (mirror.n > 0 && !vec && active) {
