@@ -174,6 +174,12 @@ int p2p_push_gram(const P2pPeers& peers, int world, int rank, int64_t gram_offse
 // wait for flag row `flag_offset` of every rank to reach `epoch`; gram_out = sum_p gram_in[p]
 int p2p_wait_sum_gram(const P2pPeers& peers, int world, int rank, int flag_offset, int epoch, int64_t gram_offset,
                       int gram_elems, float* gram_out, cudaStream_t stream);
+// post + wait in one launch
+int p2p_post_wait(const P2pPeers& peers, int world, int rank, int flag_offset, int epoch, cudaStream_t stream);
+// all-gather round trip in one launch: scal_src[2] (nullable) and rowmax[kp] -> every peer, flag, wait for all,
+// scal_out[i] = sum_p scal[p][i] (nullable), rowmax[t] = max_p rowmax_in[p][t]
+int p2p_post_gather(const P2pPeers& peers, int world, int rank, int epoch, const double* scal_src, int64_t scal_offset,
+                    double* scal_out, unsigned int* rowmax, int64_t rowmax_offset, int kp, cudaStream_t stream);
 // wait only
 int p2p_wait(const P2pPeers& peers, int world, int rank, int flag_offset, int epoch, cudaStream_t stream);
 // wait for every rank's slice of `epoch`; scal_out[i] (nullable) = sum_p scal[p][i]; rowmax_out[t] (nullable) =

@@ -90,6 +90,53 @@ p2p_post_kernel(P2pPeers peers, int world, int rank, int flag_offset, int epoch,
         st_release_sys(reinterpret_cast<int*>(peers.arena[threadIdx.x]) + flag_offset + rank, epoch);
 }
 
+// p2p_post_kernel + p2p_wait_kernel in one launch (the reduce-scatter's flag round trip)
+__global__ void __launch_bounds__(256)
+p2p_post_wait_kernel(P2pPeers peers, int world, int rank, int flag_offset, int epoch) {
+    __threadfence_system();   // whatever the producing kernels stored before this one
+    __syncthreads();
+    if (threadIdx.x < world)
+        st_release_sys(reinterpret_cast<int*>(peers.arena[threadIdx.x]) + flag_offset + rank, epoch);
+    wait_all(peers, world, rank, flag_offset, epoch);
+}
+
+// p2p_post_kernel (scalars + row maxima + flag) and p2p_gather_wait_kernel in one launch (the all-gather's round trip)
+__global__ void __launch_bounds__(256)
+p2p_post_gather_kernel(P2pPeers peers, int world, int rank, int epoch, const double* scal_src,
+                       int64_t scal_offset, double* scal_out, unsigned int* rowmax,
+                       int64_t rowmax_offset, int kp) {
+    if (scal_src != nullptr && threadIdx.x < 2 * world) {
+        const int p = threadIdx.x / 2, i = threadIdx.x & 1;
+        double* dst = reinterpret_cast<double*>(reinterpret_cast<char*>(peers.arena[p]) + scal_offset) + 2 * rank + i;
+        *dst = scal_src[i];
+    }
+    for (int e = threadIdx.x; e < world * kp; e += blockDim.x) {
+        const int p = e / kp, t = e - p * kp;
+        unsigned int* dst = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(peers.arena[p]) + rowmax_offset);
+        dst[static_cast<int64_t>(rank) * kp + t] = rowmax[t];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < world)
+        st_release_sys(reinterpret_cast<int*>(peers.arena[threadIdx.x]) + kP2pAgFlag + rank, epoch);
+    wait_all(peers, world, rank, kP2pAgFlag, epoch);
+    if (threadIdx.x < 2 && scal_out != nullptr) {
+        const volatile double* scal =
+            reinterpret_cast<const volatile double*>(reinterpret_cast<char*>(peers.arena[rank]) + scal_offset);
+        double acc = 0.0;
+        for (int p = 0; p < world; ++p) acc += scal[2 * p + threadIdx.x];
+        if (ld_acquire_sys(reinterpret_cast<int*>(peers.arena[rank]) + kP2pError) != 0) acc = __longlong_as_double(0x7ff8000000000000LL);
+        scal_out[threadIdx.x] = acc;
+    }
+    const volatile unsigned int* in =
+        reinterpret_cast<const volatile unsigned int*>(reinterpret_cast<char*>(peers.arena[rank]) + rowmax_offset);
+    for (int t = threadIdx.x; t < kp; t += blockDim.x) {
+        unsigned int m = 0u;
+        for (int p = 0; p < world; ++p) m = max(m, in[static_cast<int64_t>(p) * kp + t]);   // values >= 0: uint order
+        rowmax[t] = m;
+    }
+}
+
 // this rank's Gram (slot `rank` of its own gram_in) -> slot `rank` of every peer's gram_in
 __global__ void __launch_bounds__(256)
 p2p_push_gram_kernel(P2pPeers peers, int world, int rank, int64_t gram_offset, int gram_elems) {
@@ -158,6 +205,20 @@ int p2p_post(const P2pPeers& peers, int world, int rank, int flag_offset, int ep
              int kp) {
     p2p_post_kernel<<<1, 256, 0, stream>>>(peers, world, rank, flag_offset, epoch, scal_src, scal_offset, rowmax_src,
                                            rowmax_offset, kp);
+    NFB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int p2p_post_wait(const P2pPeers& peers, int world, int rank, int flag_offset, int epoch, cudaStream_t stream) {
+    p2p_post_wait_kernel<<<1, 256, 0, stream>>>(peers, world, rank, flag_offset, epoch);
+    NFB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int p2p_post_gather(const P2pPeers& peers, int world, int rank, int epoch, const double* scal_src, int64_t scal_offset,
+                    double* scal_out, unsigned int* rowmax, int64_t rowmax_offset, int kp, cudaStream_t stream) {
+    p2p_post_gather_kernel<<<1, 256, 0, stream>>>(peers, world, rank, epoch, scal_src, scal_offset, scal_out, rowmax,
+                                                  rowmax_offset, kp);
     NFB_CUDA(cudaGetLastError());
     return 0;
 }

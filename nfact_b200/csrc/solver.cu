@@ -457,11 +457,16 @@ static int gemm_wtx(nfb_nmf* s, HNumerator* out) {
         // happens inside the GEMM, tile by tile, over NVLink.  Then: post, wait for everybody, sum the Grams.
         const int64_t ns = s->slice_cols;
         const int gram_elems = static_cast<int>(s->kp * s->kp);
-        NFB_TRY(p2p_push_gram(s->peers, h->world, h->rank, s->arena_gram_off, gram_elems, h->stream));
-        ++s->epoch;
-        NFB_TRY(p2p_post(s->peers, h->world, h->rank, kP2pGramFlag, s->epoch, h->stream));
+        // W'W of this shard, its push to the peers' slots and its flag need only the planes of W: with the aux stream
+        // they run beside the GEMM as well, like the Gram sum and the denominator behind them
         const bool side = h->den_overlap;
+        cudaStream_t gst = side ? h->aux_stream : h->stream;
         if (side) NFB_TRY(aux_fork(h));
+        NFB_TRY(compute_gram(s, s->wt, s->gw, s->s_gw, false, true, gst));
+        NFB_TRY(p2p_push_gram(s->peers, h->world, h->rank, s->arena_gram_off, gram_elems, gst));
+        ++s->epoch;
+        NFB_TRY(p2p_post(s->peers, h->world, h->rank, kP2pGramFlag, s->epoch, gst));
+        if (side) s->aux_pending = true;
         GemmScatter sc{};
         for (int r = 0; r < h->world; ++r)
             sc.base[r] = reinterpret_cast<float*>(static_cast<char*>(s->peers.arena[r]) + s->arena_num_off);
@@ -480,7 +485,6 @@ static int gemm_wtx(nfb_nmf* s, HNumerator* out) {
         *out = HNumerator{s->arena_num(), h->world, static_cast<int64_t>(s->k) * ns, ns, c0, width};
         // the Gram sum needs only the peers' Gram flags (raised before their GEMMs): with the aux stream it and the
         // denominator GEMM run beside this rank's W'X instead of after it
-        cudaStream_t gst = side ? h->aux_stream : h->stream;
         NFB_TRY(p2p_wait_sum_gram(s->peers, h->world, h->rank, kP2pGramFlag, s->epoch, s->arena_gram_off, gram_elems,
                                   s->gw.f.p, gst));
         if (side) {
@@ -489,9 +493,8 @@ static int gemm_wtx(nfb_nmf* s, HNumerator* out) {
             s->den_h_done = true;
         }
         NFB_PHASE(h, "rs_wait");
-        NFB_TRY(p2p_post(s->peers, h->world, h->rank, kP2pRsFlag, s->epoch, h->stream));
-        NFB_TRY(p2p_wait(s->peers, h->world, h->rank, kP2pRsFlag, s->epoch, h->stream));
-        note_launch(6);
+        NFB_TRY(p2p_post_wait(s->peers, h->world, h->rank, kP2pRsFlag, s->epoch, h->stream));
+        note_launch(5);
         return 0;
     }
     {
@@ -536,11 +539,9 @@ static int gather_h_slices(nfb_nmf* s, const HNumerator& hn) {
         // violation partial sums (CD) and the per-component maxima of its slice, the flag, and the wait
         double* scal = s->p.solver == 0 ? h->d_scal.p + 2 : nullptr;
         NFB_PHASE(h, "ag_wait");
-        NFB_TRY(p2p_post(s->peers, h->world, h->rank, kP2pAgFlag, s->epoch, h->stream, scal, kP2pScalOffset,
-                         s->hh.rowmax.p, s->arena_rowmax_off, static_cast<int>(s->kp)));
-        NFB_TRY(p2p_gather_wait(s->peers, h->world, h->rank, s->epoch, kP2pScalOffset, scal, s->arena_rowmax_off,
-                                static_cast<int>(s->kp), s->hh.rowmax.p, h->stream));
-        note_launch(2);
+        NFB_TRY(p2p_post_gather(s->peers, h->world, h->rank, s->epoch, scal, kP2pScalOffset, scal, s->hh.rowmax.p,
+                                s->arena_rowmax_off, static_cast<int>(s->kp), h->stream));
+        note_launch(1);
         return 0;
     }
     if (hn.width > 0)
@@ -641,7 +642,8 @@ static int mu_iteration(nfb_nmf* s) {
     s->p1_valid = false;
     { NFB_PHASE(h, "split_w"); NFB_TRY(refresh_planes(s->wt, s->wt.f.p, nullptr, false, h->stream)); }
     const bool side = h->world <= 1 && h->den_overlap;
-    if (!side || !h->gram_overlap) { NFB_PHASE(h, "gram_w"); NFB_TRY(compute_gram(s, s->wt, s->gw, s->s_gw, true, s->p2p)); }
+    // peer-memory path: W'W is computed, pushed and summed inside gemm_wtx (beside the GEMM)
+    if (!s->p2p && (!side || !h->gram_overlap)) { NFB_PHASE(h, "gram_w"); NFB_TRY(compute_gram(s, s->wt, s->gw, s->s_gw, true)); }
     // ---- H half-step ----
     HNumerator hn;
     if (side) {
@@ -697,7 +699,8 @@ static int cd_iteration(nfb_nmf* s, double* violation_out, double* host_slot = n
     s->p1_valid = false;
     { NFB_PHASE(h, "split_w"); NFB_TRY(refresh_planes(s->wt, s->wt.f.p, nullptr, false, h->stream)); }
     const bool side = h->world <= 1 && h->den_overlap;
-    if (!side || !h->gram_overlap) { NFB_PHASE(h, "gram_w"); NFB_TRY(compute_gram(s, s->wt, s->gw, s->s_gw, true, s->p2p)); }
+    // peer-memory path: W'W is computed, pushed and summed inside gemm_wtx (beside the GEMM)
+    if (!s->p2p && (!side || !h->gram_overlap)) { NFB_PHASE(h, "gram_w"); NFB_TRY(compute_gram(s, s->wt, s->gw, s->s_gw, true)); }
     // ---- H half-step ----
     HNumerator hn;
     if (side) {
